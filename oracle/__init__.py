@@ -1,0 +1,186 @@
+"""CPU ORACLE bindings (ctypes over oracle/librf_oracle.so) -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this package.  Nothing under recommendflow_b200/ does.  See the header of
+oracle/rf_oracle.c for what is restated (reference file:line) and for the parity-pinning
+statement (public TF/Keras KATs pin the hashes; FarmHash >16-byte branches are unpinned).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "librf_oracle.so")
+_lib = None
+
+COMBINERS = {"sum": 0, "avg": 1, "min": 2, "max": 3}
+
+
+def build(force=False):
+    """Compile the C restatement (gcc).  Building the checker is not using it."""
+    src = os.path.join(_HERE, "rf_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        _lib.rfo_fingerprint64.restype = C.c_uint64
+        _lib.rfo_fingerprint64.argtypes = [C.c_char_p, C.c_uint64]
+        _lib.rfo_siphash24.restype = C.c_uint64
+        _lib.rfo_siphash24.argtypes = [C.c_uint64, C.c_uint64, C.c_char_p, C.c_uint64]
+        _lib.rfo_inbatch_softmax_ce.restype = C.c_double
+        _lib.rfo_num_threads.restype = C.c_int
+    return _lib
+
+
+def _p(a, t=C.c_void_p):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+def fingerprint64(b: bytes) -> int:
+    return lib().rfo_fingerprint64(b, len(b))
+
+
+def siphash24(k0: int, k1: int, b: bytes) -> int:
+    return lib().rfo_siphash24(k0, k1, b, len(b))
+
+
+def encode_strings(values):
+    """list of str/bytes -> (uint8 arena, int32 offsets[n+1])."""
+    enc = [v.encode() if isinstance(v, str) else bytes(v) for v in values]
+    offs = np.zeros(len(enc) + 1, dtype=np.int32)
+    if enc:
+        offs[1:] = np.cumsum([len(e) for e in enc])
+    arena = np.frombuffer(b"".join(enc), dtype=np.uint8).copy() if offs[-1] else np.zeros(0, np.uint8)
+    return arena, offs
+
+
+def _salt(salt):
+    if salt is None:
+        return 0, 0, 0
+    if isinstance(salt, (int, np.integer)):
+        return 1, int(salt), int(salt)
+    return 1, int(salt[0]), int(salt[1])
+
+
+def hash_strings(arena, offs, num_bins, mask_value=None, salt=None):
+    """Keras Hashing over a string column.  Returns int64[n]."""
+    n = len(offs) - 1
+    out = np.empty(n, dtype=np.int64)
+    strong, k0, k1 = _salt(salt)
+    arena = np.ascontiguousarray(arena, dtype=np.uint8)
+    offs = np.ascontiguousarray(offs, dtype=np.int32)
+    has_mask = mask_value is not None
+    m = (mask_value.encode() if isinstance(mask_value, str) else mask_value) if has_mask else b""
+    lib().rfo_hash_strings(_p(arena), _p(offs), C.c_int64(n), C.c_int64(num_bins), C.c_int(strong),
+                           C.c_uint64(k0), C.c_uint64(k1), C.c_int(has_mask), C.c_char_p(m),
+                           C.c_int32(len(m)), _p(out))
+    return out
+
+
+def hash_ints(vals, num_bins, mask_value=None, salt=None):
+    vals = np.ascontiguousarray(vals, dtype=np.int64).ravel()
+    out = np.empty(vals.size, dtype=np.int64)
+    strong, k0, k1 = _salt(salt)
+    has_mask = mask_value is not None
+    lib().rfo_hash_ints(_p(vals), C.c_int64(vals.size), C.c_int64(num_bins), C.c_int(strong),
+                        C.c_uint64(k0), C.c_uint64(k1), C.c_int(has_mask),
+                        C.c_int64(int(mask_value) if has_mask else 0), _p(out))
+    return out
+
+
+def bag_pool(ids, W, combiner="sum", L=None, bag_offsets=None):
+    """ids flat int64; dense bags of length L or CSR bag_offsets[B+1].  Returns [B, D] fp32."""
+    ids = np.ascontiguousarray(ids, dtype=np.int64).ravel()
+    W = np.ascontiguousarray(W, dtype=np.float32)
+    N, D = W.shape
+    if bag_offsets is not None:
+        bag_offsets = np.ascontiguousarray(bag_offsets, dtype=np.int32)
+        B, L = len(bag_offsets) - 1, 0
+    else:
+        B = ids.size // L if L else 0
+    out = np.empty((B, D), dtype=np.float32)
+    lib().rfo_bag_pool(_p(ids), C.c_int64(B), C.c_int64(L or 0), _p(bag_offsets), _p(W), C.c_int64(N),
+                       C.c_int64(D), C.c_int(COMBINERS[combiner]), _p(out), C.c_int64(D))
+    return out
+
+
+def gather_rows(ids, W):
+    ids = np.ascontiguousarray(ids, dtype=np.int64).ravel()
+    W = np.ascontiguousarray(W, dtype=np.float32)
+    out = np.empty((ids.size, W.shape[1]), dtype=np.float32)
+    lib().rfo_gather_rows(_p(ids), C.c_int64(ids.size), _p(W), C.c_int64(W.shape[1]), _p(out))
+    return out
+
+
+def hashed_bag_forward(arena, offs, B, L, tables, num_bins, salts, combiner="sum", mask_empty=True,
+                       bag_offsets=None, out=None, out_col=0):
+    """Fused oracle forward of one hashed field with T tables -> [B, T*D] (DoubleHashingEmbedding,
+    /root/reference/backend/layers/preprocess_layers.py:94-97 when T == 2)."""
+    T = len(tables)
+    tables = [np.ascontiguousarray(w, dtype=np.float32) for w in tables]
+    D = tables[0].shape[1]
+    arena = np.ascontiguousarray(arena, dtype=np.uint8)
+    offs = np.ascontiguousarray(offs, dtype=np.int32)
+    if out is None:
+        out = np.empty((B, T * D), dtype=np.float32)
+        out_col = 0
+    assert out.dtype == np.float32 and out.flags.c_contiguous
+    Wp = (C.c_void_p * T)(*[w.ctypes.data for w in tables])
+    nb = (C.c_int64 * T)(*[int(x) for x in num_bins])
+    s = [_salt(x) for x in salts]
+    us = (C.c_int * T)(*[x[0] for x in s])
+    k0 = (C.c_uint64 * T)(*[x[1] for x in s])
+    k1 = (C.c_uint64 * T)(*[x[2] for x in s])
+    if bag_offsets is not None:
+        bag_offsets = np.ascontiguousarray(bag_offsets, dtype=np.int32)
+    optr = C.c_void_p(out.ctypes.data + 4 * out_col)
+    lib().rfo_hashed_bag_forward(_p(arena), _p(offs), C.c_int64(B), C.c_int64(L), _p(bag_offsets), C.c_int(T),
+                                 Wp, nb, us, k0, k1, C.c_int(1 if mask_empty else 0), C.c_int64(D),
+                                 C.c_int(COMBINERS[combiner]), optr, C.c_int64(out.shape[1]))
+    return out
+
+
+def sdpa(q, k, v, mask=None):
+    """q,k,v [..., S, dh] fp32; mask [..., S, 1] or [..., S] (query-row mask, see rf_oracle.c)."""
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    k = np.ascontiguousarray(k, dtype=np.float32)
+    v = np.ascontiguousarray(v, dtype=np.float32)
+    S, dh = q.shape[-2:]
+    NB = q.size // (S * dh)
+    m = None
+    if mask is not None:
+        m = np.ascontiguousarray(np.broadcast_to(np.asarray(mask, dtype=np.float32).reshape(q.shape[:-1]),
+                                                 q.shape[:-1]), dtype=np.float32)
+    out = np.empty_like(q)
+    lib().rfo_sdpa(_p(q), _p(k), _p(v), _p(m), C.c_int64(NB), C.c_int64(S), C.c_int64(dh), _p(out))
+    return out
+
+
+def inbatch_softmax_ce(y_true, query, doc, scale=20.0):
+    """batch_neg_sample_scaled_multi_class_ce_loss; returns (loss, row_lse[B], diag[B]) in float64."""
+    q = np.ascontiguousarray(query, dtype=np.float32)
+    d = np.ascontiguousarray(doc, dtype=np.float32)
+    y = np.ascontiguousarray(y_true, dtype=np.float32).ravel()
+    B, Dt = q.shape
+    lse = np.empty(B, dtype=np.float64)
+    diag = np.empty(B, dtype=np.float64)
+    loss = lib().rfo_inbatch_softmax_ce(_p(q), _p(d), _p(y), C.c_int64(B), C.c_int64(Dt), C.c_double(scale),
+                                        _p(lse), _p(diag))
+    return float(loss), lse, diag
+
+
+def num_threads():
+    return int(lib().rfo_num_threads())
+
+
+def set_num_threads(n):
+    lib().rfo_set_num_threads(C.c_int(int(n)))
