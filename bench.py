@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- lookup+pool samples/s of the fused hash + gather + pool path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c2x2|small]
+
+Workload (config.workload) at every N: SURVEY.md §8(d) "C2" = BASELINE.json configs[1]: 26 hashed
+sparse fields, 1M-row x 64-dim fp32 tables, batch 65536, sum pooling, 4 keys per bag, keys
+"fNN_<v>" (FarmHash Fingerprint64 mod N, Keras mask_value=""), tables U(-0.05, 0.05).
+A step = one pass of the hot path over one batch = ONE fused kernel launch.
+N > 1: one process per GPU (torchrun), each rank holds a full replica of the 6.66 GB tables and
+its own batch (what the reference's MirroredStrategy does) -- no data-path collective, weak scaling.
+
+`--impl reference` times the CPU restatement of the reference's TF path (oracle/, all host
+threads): TensorFlow is not installable here, so the oracle port is the reference arm.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "lookup+pool samples/sec"
+UNIT = "samples/s"
+
+WORKLOADS = {
+    #        fields rows     dim  batch  L  tables/field
+    "c2":   (26, 1_000_000, 64, 65536, 4, 1),
+    "c2x2": (26, 1_000_000, 64, 65536, 4, 2),     # reference-faithful double SipHash variant
+    "small": (4, 3000, 16, 2048, 4, 2),
+}
+N_KEY_BATCHES = 4
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(name):
+    F, N, D, B, L, T = WORKLOADS[name]
+    return {"workload": f"{name}: {F} hashed fields x {T} table(s), {N}-row x {D}-dim fp32 tables, batch {B}, "
+                        f"{L} keys/bag, sum pooling, {'SipHash-2-4 seeds [2022,2023]' if T == 2 else 'Fingerprint64'}"
+                        f" mod N, mask_value=''",
+            "fields": F, "rows": N, "dim": D, "batch_per_gpu": B, "bag_len": L, "tables_per_field": T,
+            "l2_policy": f"inputs larger than L2: {F * T * N * D * 4 / 1e9:.2f} GB of tables gathered at random rows; "
+                         f"{N_KEY_BATCHES} distinct key batches rotate across steps"}
+
+
+def salts_for(T):
+    return [None] if T == 1 else [[2022, 2022], [2023, 2023]]
+
+
+def make_keys(name, rank):
+    """{field name: (arena, offsets, shape)} for each of the rotating key batches."""
+    from recommendflow_b200.synth import c2_field_keys
+    F, N, D, B, L, T = WORKLOADS[name]
+    batches = []
+    for bi in range(N_KEY_BATCHES):
+        fields = {}
+        for f in range(F):
+            arena, offs = c2_field_keys(f, B, L, batch_index=bi + 16 * rank)
+            fields[f"f{f:02d}"] = (arena, offs, (B, L))
+        batches.append(fields)
+    return batches
+
+
+def algorithmic_bytes_per_sample(name, key_batches):
+    """sum_f [T*l*4D (row gathers) + l*(s + 4) (key bytes + offsets) + T*4D (output)]."""
+    F, N, D, B, L, T = WORKLOADS[name]
+    key_bytes = np.mean([sum(a.size for a, _, _ in kb.values()) for kb in key_batches]) / B
+    return F * (T * L * 4 * D + L * 4 + T * 4 * D) + key_bytes
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return None
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's TF CPU path
+# ------------------------------------------------------------------------------------------
+def cpu_one_pass(name, kb, host_tables, out):
+    """One batch of the workload through the oracle port of the reference's CPU path."""
+    import oracle
+    F, N, D, B, L, T = WORKLOADS[name]
+    salts = salts_for(T)
+    for f, (fname, (arena, offs, _)) in enumerate(kb.items()):
+        oracle.hashed_bag_forward(arena, offs, B, L, host_tables[f], [N] * T, salts, "sum", mask_empty=True,
+                                  out=out, out_col=f * T * D)
+
+
+def tune_cpu_threads(name, key_batches, host_tables, out):
+    """Use as many host threads as actually help (probe = one field of one batch)."""
+    import oracle
+    F, N, D, B, L, T = WORKLOADS[name]
+    fname = next(iter(key_batches[0]))
+    arena, offs, _ = key_batches[0][fname]
+    th, _ = oracle.autotune_threads(lambda: oracle.hashed_bag_forward(
+        arena, offs, B, L, host_tables[0], [N] * T, salts_for(T), "sum", mask_empty=True, out=out, out_col=0))
+    return th
+
+
+def cpu_reference_run(name, key_batches, host_tables, budget_s=12.0, max_passes=4):
+    """Times whole batches of the workload on all host threads; returns (record, last output, its batch index)."""
+    import oracle
+    F, N, D, B, L, T = WORKLOADS[name]
+    out = np.empty((B, F * T * D), dtype=np.float32)
+    cpu_one_pass(name, key_batches[0], host_tables, out)          # warm-up (pages the tables in)
+    threads = tune_cpu_threads(name, key_batches, host_tables, out)
+    t0, passes = time.perf_counter(), 0
+    while passes < max_passes and (passes == 0 or time.perf_counter() - t0 < budget_s):
+        cpu_one_pass(name, key_batches[passes % len(key_batches)], host_tables, out)
+        passes += 1
+    dt = time.perf_counter() - t0
+    return {"value": passes * B / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{passes} full batch(es) of {B} samples x {F} fields through oracle/rf_oracle.c "
+                      f"(OpenMP, {threads} threads) in {dt:.2f} s; TensorFlow unavailable, so the reference's TF CPU "
+                      f"path is represented by its restated CPU port"}, out, (passes - 1) % len(key_batches)
+
+
+def host_tables_numpy(name, seed0=7):
+    F, N, D, B, L, T = WORKLOADS[name]
+    tabs = []
+    for f in range(F):
+        row = []
+        for t in range(T):
+            w = np.random.default_rng(seed0 + f * T + t).random((N, D), dtype=np.float32)
+            w -= np.float32(0.5)
+            w *= np.float32(0.1)                       # U(-0.05, 0.05), Keras 'uniform'
+            row.append(w)
+        tabs.append(row)
+    return tabs
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.workload
+    F, N, D, B, L, T = WORKLOADS[name]
+    key_batches = make_keys(name, 0)[:2]
+    tabs = host_tables_numpy(name)
+    import oracle
+    out = np.empty((B, F * T * D), dtype=np.float32)
+    cpu_one_pass(name, key_batches[0], tabs, out)
+    threads = tune_cpu_threads(name, key_batches, tabs, out)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        cpu_one_pass(name, key_batches[i % len(key_batches)], tabs, out)
+        times.append(time.perf_counter() - t0)
+        if sum(times) > 150:          # keep the whole run within a few minutes
+            break
+    timed = times[min(args.warmup, max(len(times) - 1, 0)):]
+    ms = 1e3 * float(np.mean(timed))
+    value = B / (ms / 1e3)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": len(timed), "warmup": min(args.warmup, len(times) - len(timed)), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 pooling / u64 hashing",
+            "data": "synthetic", "config": workload_config(name),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"each step = one full batch of {B} samples x {F} fields on the host CPU "
+                                       f"(oracle/rf_oracle.c, OpenMP); runs on rank 0 only"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from recommendflow_b200 import _native as nat
+    from recommendflow_b200.backend.layers.preprocess_layers import DoubleHashingEmbedding, EmbeddingBag  # noqa: F401
+    from recommendflow_b200.bag_ops import FieldCall, bag_forward
+    from recommendflow_b200.synth import PackedBatch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    name = args.workload
+    F, N, D, B, L, T = WORKLOADS[name]
+    salts = salts_for(T)
+    K, W = args.steps, max(args.warmup, 3)
+
+    # ---- resident state: tables (synthetic U(-0.05, 0.05), same values as the CPU arm) --------
+    host_tabs = host_tables_numpy(name) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    tables = []
+    for f in range(F):
+        row = []
+        for t in range(T):
+            if host_tabs is not None:
+                row.append(torch.from_numpy(host_tabs[f][t]).to(dev))
+            else:
+                g = torch.Generator(device=dev)
+                g.manual_seed(7 + f * T + t + 1000 * rank)
+                row.append(torch.empty(N, D, dtype=torch.float32, device=dev).uniform_(-0.05, 0.05, generator=g))
+        tables.append(row)
+
+    key_batches = make_keys(name, rank)
+    host_packed = [PackedBatch.pack(kb, pin=True) for kb in key_batches]
+    dev_packed = [hp.to(dev) for hp in host_packed]
+    dev_cols = [dp.columns() for dp in dev_packed]
+    out = torch.empty(B, F * T * D, dtype=torch.float32, device=dev)
+    names = list(key_batches[0].keys())
+
+    def calls_for(cols):
+        return [FieldCall([(tables[f][t], N, salts[t]) for t in range(T)], D, "sum", keys=cols[n],
+                          mask_mode=nat.MASK_EMPTY_STRING, out=out[:, f * T * D:(f + 1) * T * D], bag_len=L)
+                for f, n in enumerate(names)]
+
+    all_calls = [calls_for(c) for c in dev_cols]
+
+    def step(i):
+        bag_forward(all_calls[i % N_KEY_BATCHES], B)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value, roofline) ------------------------------------------------
+    for i in range(W):
+        step(i)
+    barrier()
+    launches0 = nat.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        t_all0.record()
+        for i in range(K):
+            ev[i][0].record()
+            step(W + i)
+            ev[i][1].record()
+        t_all1.record()
+        barrier()
+    launches = nat.launch_count() - launches0
+    total_ms = t_all0.elapsed_time(t_all1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / K
+    value = world * B / (ms_per_step / 1e3)
+
+    # ---- end to end: host key buffers in, pooled vectors out to host, every step ---------------
+    e2e = None
+    if not args.no_e2e:
+        # device staging buffers sized for the largest batch
+        max_b = max(int(h.data.numel()) for h in host_packed)
+        max_o = max(int(h.offsets.numel()) for h in host_packed)
+        stage = PackedBatch(torch.empty(max_b, dtype=torch.uint8, device=dev),
+                            torch.empty(max_o, dtype=torch.int32, device=dev), None)
+        host_out = torch.empty(B, F * T * D, dtype=torch.float32).pin_memory()
+
+        def e2e_step(i):
+            hp = host_packed[i % N_KEY_BATCHES]
+            stage.data[:hp.data.numel()].copy_(hp.data, non_blocking=True)
+            stage.offsets[:hp.offsets.numel()].copy_(hp.offsets, non_blocking=True)
+            stage.layout = hp.layout
+            bag_forward(calls_for(stage.columns()), B)
+            host_out.copy_(out, non_blocking=True)
+
+        for i in range(3):
+            e2e_step(i)
+        barrier()
+        ke = max(3, min(K, 20))
+        t0 = time.perf_counter()
+        for i in range(ke):
+            e2e_step(i)
+            torch.cuda.synchronize()          # the caller consumes the host result every step
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / ke
+        if world > 1:
+            t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        e2e = {"value": world * B / (e2e_ms / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": int(np.mean([h.nbytes for h in host_packed])),
+               "d2h_bytes_per_step": int(host_out.numel() * 4), "ms_per_step": e2e_ms, "steps": ke,
+               "path": "pinned host key arena+offsets -> H2D -> rf_bag_forward -> D2H of the pooled [B, sum(T*D)] fp32"}
+
+    # ---- roofline of the one kernel ------------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    bps = algorithmic_bytes_per_sample(name, key_batches)
+    achieved = bps * B / (kern_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "rf::bag_forward_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                "frac_of_nominal_8TBs": achieved / 8000.0, "algorithmic_bytes_per_sample": bps,
+                "algorithmic_bytes_per_launch": bps * B, "kernel_ms": kern_ms, "traffic": None}
+
+    # ---- CPU baseline beside it (rank 0, N == 1 only) ------------------------------------------
+    cpu, parity = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, cpu_out, bi = cpu_reference_run(name, key_batches, host_tabs)
+        # the checker comes for free: the GPU's result for the same batch must equal the CPU arm's
+        step(bi)
+        torch.cuda.synchronize()
+        same = bool(np.array_equal(out.cpu().numpy().view(np.uint32), cpu_out.view(np.uint32)))
+        parity = f"GPU output {'==' if same else '!='} CPU arm output, bit for bit, on key batch {bi} ({B} x {F * T * D} fp32)"
+        if not same:
+            raise SystemExit("bench: " + parity)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 pooling / u64 hashing", "data": "synthetic", "config": workload_config(name),
+                "gpu_launches": int(launches), "clocks": clocks.summary(), "e2e": e2e, "roofline": roofline,
+                "cpu_baseline": cpu, "parity_check": parity}
+        line["config"]["parallelism"] = f"dp{world} (replicated tables, no data-path collective)"
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

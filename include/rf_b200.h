@@ -1,0 +1,118 @@
+/*
+ * rf_b200.h -- C-ABI of the B200-native feature-to-embedding hot path of RecommendFlow.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / TF types.  Every entry
+ * point is stream-ordered (pass a cudaStream_t as `void*`, NULL = legacy default stream),
+ * returns RF_OK (0) or a negative rf_status, and leaves a message for rf_last_error()
+ * (thread-local) on failure.  There is NO CPU fallback: without a CUDA device every compute
+ * entry point fails with RF_ERR_CUDA.
+ *
+ * The reference (/root/reference, pure Python on TensorFlow/Keras ops) has no FFI of its own;
+ * each entry point below names the reference interface it replaces.  INTEGRATION.md shows
+ * the ctypes / TF-custom-op stubs a maintainer of the reference would add.
+ */
+#ifndef RF_B200_H_
+#define RF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RF_B200_ABI_VERSION 1
+
+typedef enum rf_status {
+    RF_OK = 0,
+    RF_ERR_INVALID = -1,     /* bad argument (the Python layer raises ValueError)            */
+    RF_ERR_CUDA = -2,        /* CUDA runtime error or no device                               */
+    RF_ERR_UNSUPPORTED = -3  /* valid in the reference but outside this library's envelope    */
+} rf_status;
+
+/* Combiners of EmbeddingBag.get_combiner (backend/layers/preprocess_layers.py:43-64).
+ * "null"/"first"/"last" are resolved by the host layer as bags of one item (a plain gather). */
+typedef enum rf_combiner {
+    RF_COMBINER_SUM = 0,
+    RF_COMBINER_AVG = 1,
+    RF_COMBINER_MIN = 2,
+    RF_COMBINER_MAX = 3
+} rf_combiner;
+
+/* Keras `Hashing(mask_value=...)`: which input value is sent to bucket 0. */
+typedef enum rf_mask_mode {
+    RF_MASK_NONE = 0,        /* mask_value=None: ids in [0, num_bins)                          */
+    RF_MASK_EMPTY_STRING = 1,/* mask_value="" (what get_preprocess_layers passes,             */
+                             /* backend/utils/preprocess_utils.py:15): "" -> 0, else 1+h%(N-1) */
+    RF_MASK_INT_VALUE = 2    /* integer inputs: value == int_mask_value -> 0                  */
+} rf_mask_mode;
+
+/* One embedding table + the hash that feeds it: replaces one Keras `Hashing` + `Embedding`
+ * pair (preprocess_layers.py:89-92, :31-39). */
+typedef struct rf_table_desc {
+    const float *weights;    /* device, [num_bins, dim] fp32 row-major (Embedding.embeddings)  */
+    int64_t num_bins;        /* Hashing num_bins == Embedding input_dim                        */
+    int32_t use_strong;      /* 1: salt given -> SipHash-2-4 (to_hash_bucket_strong)           */
+                             /* 0: salt None  -> FarmHash Fingerprint64 (to_hash_bucket_fast)  */
+    int32_t reserved;
+    uint64_t key0, key1;     /* SipHash key: salt=[key0,key1]; int salt s -> (s, s)            */
+} rf_table_desc;
+
+#define RF_MAX_TABLES_PER_FIELD 2
+
+/* One feature field of one batch: replaces `DoubleHashingEmbedding.call`
+ * (preprocess_layers.py:94-97; n_tables == 2) or `EmbeddingBag.call` (:66-68; pre-hashed
+ * ids, n_tables == 1).  Exactly one of {bytes+str_offsets, int_values, ids} is non-NULL. */
+typedef struct rf_field_desc {
+    /* --- input keys, flat over the field's items (dense: item = b * bag_len + l) ----------- */
+    const uint8_t *bytes;        /* device string arena; >= 16 readable bytes past the end     */
+    const int32_t *str_offsets;  /* device [n_items + 1], byte offsets into `bytes`            */
+    const int64_t *int_values;   /* device [n_items]; hashed as tf.as_string(value)            */
+    const int64_t *ids;          /* device [n_tables][n_items] pre-hashed row ids (no hashing) */
+    /* --- bags -------------------------------------------------------------------------------- */
+    const int32_t *bag_offsets;  /* device [batch + 1] CSR over items (jagged mode), or NULL   */
+    int64_t n_items;             /* jagged mode: total items (= bag_offsets[batch]); dense     */
+                                 /* mode derives batch * bag_len and ignores this              */
+    int32_t bag_len;             /* dense mode (bag_offsets == NULL): items per bag, pads      */
+                                 /* included -- the reference pools row 0 in for every pad     */
+    int32_t n_tables;            /* 1 .. RF_MAX_TABLES_PER_FIELD                                */
+    rf_table_desc tables[RF_MAX_TABLES_PER_FIELD];
+    int32_t dim;                 /* embedding dim D; 0 = hash only (needs ids_out)             */
+    int32_t combiner;            /* rf_combiner                                                 */
+    int32_t mask_mode;           /* rf_mask_mode                                                */
+    int32_t reserved;
+    int64_t int_mask_value;      /* RF_MASK_INT_VALUE only                                      */
+    /* --- outputs ----------------------------------------------------------------------------- */
+    float *out;                  /* device; bag b, table t -> out[b*out_stride + t*dim .. +dim] */
+    int64_t out_stride;          /* floats between consecutive bags' rows                       */
+    int64_t *ids_out;            /* optional device [n_tables][n_items]: the bucket ids         */
+} rf_field_desc;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int rf_abi_version(void);
+const char *rf_last_error(void);
+
+/* ---- hashing only: Keras `Hashing.call` (preprocess_layers.py:95) ------------------------- */
+int rf_hash_strings(const uint8_t *d_bytes, const int32_t *d_str_offsets, int64_t n_items,
+                    int64_t num_bins, int mask_mode, int use_strong, uint64_t key0, uint64_t key1,
+                    int64_t *d_ids_out, void *stream);
+int rf_hash_int64(const int64_t *d_values, int64_t n_items, int64_t num_bins, int mask_mode,
+                  int64_t int_mask_value, int use_strong, uint64_t key0, uint64_t key1,
+                  int64_t *d_ids_out, void *stream);
+
+/* ---- fused hash + gather + pool over n_fields fields of one batch, ONE kernel launch ------- */
+/* Replaces the per-feature loop `self.preprocessor[name](batch[name])`                        */
+/* (models/matching/que2search.py:68,76-79) over the layers built by get_preprocess_layers     */
+/* (backend/utils/preprocess_utils.py:7-20).                                                   */
+int rf_bag_forward(const rf_field_desc *fields, int n_fields, int64_t batch, void *stream);
+
+/* Number of kernels launched by this library since load (bench.py's gpu_launches counter).   */
+int64_t rf_launch_count(void);
+
+/* Host-side check of the division-by-invariant used for `h mod bins` (tests only). */
+uint64_t rf_debug_fastmod(uint64_t x, uint64_t d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RF_B200_H_ */

@@ -31,6 +31,7 @@ def lib():
     if _lib is None:
         if not os.path.exists(_SO):
             build()
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")   # idle OpenMP threads sleep instead of spinning
         _lib = C.CDLL(_SO)
         _lib.rfo_fingerprint64.restype = C.c_uint64
         _lib.rfo_fingerprint64.argtypes = [C.c_char_p, C.c_uint64]
@@ -184,3 +185,27 @@ def num_threads():
 
 def set_num_threads(n):
     lib().rfo_set_num_threads(C.c_int(int(n)))
+
+
+def autotune_threads(probe, candidates=None):
+    """Pick the OpenMP thread count that runs `probe()` fastest (containers often grant fewer
+    cores than os.cpu_count() reports).  Returns (threads, seconds)."""
+    import time
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if candidates is None:
+        candidates, c = [], 1
+        while c < ncpu:
+            candidates.append(c)
+            c *= 2
+        candidates.append(ncpu)
+    best = None
+    for th in candidates:
+        set_num_threads(th)
+        probe()
+        t0 = time.perf_counter()
+        probe()
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[1]:
+            best = (th, dt)
+    set_num_threads(best[0])
+    return best

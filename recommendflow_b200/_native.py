@@ -1,0 +1,85 @@
+"""ctypes binding of librf_b200.so (the C-ABI in include/rf_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, this module raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "librf_b200.so")
+
+RF_OK, RF_ERR_INVALID, RF_ERR_CUDA, RF_ERR_UNSUPPORTED = 0, -1, -2, -3
+COMBINER = {"sum": 0, "avg": 1, "min": 2, "max": 3}
+MASK_NONE, MASK_EMPTY_STRING, MASK_INT_VALUE = 0, 1, 2
+MAX_TABLES = 2
+
+
+class TableDesc(C.Structure):
+    _fields_ = [("weights", C.c_void_p), ("num_bins", C.c_int64), ("use_strong", C.c_int32),
+                ("reserved", C.c_int32), ("key0", C.c_uint64), ("key1", C.c_uint64)]
+
+
+class FieldDesc(C.Structure):
+    _fields_ = [("bytes", C.c_void_p), ("str_offsets", C.c_void_p), ("int_values", C.c_void_p),
+                ("ids", C.c_void_p), ("bag_offsets", C.c_void_p), ("n_items", C.c_int64),
+                ("bag_len", C.c_int32), ("n_tables", C.c_int32), ("tables", TableDesc * MAX_TABLES),
+                ("dim", C.c_int32), ("combiner", C.c_int32), ("mask_mode", C.c_int32), ("reserved", C.c_int32),
+                ("int_mask_value", C.c_int64), ("out", C.c_void_p), ("out_stride", C.c_int64),
+                ("ids_out", C.c_void_p)]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load librf_b200.so; raises if it has not been built (python -m recommendflow_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise NativeError(f"{SO_PATH} is missing: build it with `python -m recommendflow_b200.build` "
+                              "(nvcc, sm_100a). There is no CPU fallback.")
+        L = C.CDLL(SO_PATH)
+        L.rf_abi_version.restype = C.c_int
+        L.rf_last_error.restype = C.c_char_p
+        L.rf_launch_count.restype = C.c_int64
+        L.rf_debug_fastmod.restype = C.c_uint64
+        L.rf_debug_fastmod.argtypes = [C.c_uint64, C.c_uint64]
+        L.rf_hash_strings.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int,
+                                      C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.rf_hash_int64.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_int,
+                                    C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.rf_bag_forward.argtypes = [C.POINTER(FieldDesc), C.c_int, C.c_int64, C.c_void_p]
+        for name in ("rf_hash_strings", "rf_hash_int64", "rf_bag_forward"):
+            getattr(L, name).restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc == RF_OK:
+        return
+    msg = lib().rf_last_error().decode(errors="replace")
+    if rc == RF_ERR_INVALID:
+        raise ValueError(msg)
+    if rc == RF_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise NativeError(msg)
+
+
+def launch_count():
+    return int(lib().rf_launch_count())
+
+
+def salt_to_key(salt):
+    """Keras `Hashing(salt=...)`: None -> fast hash; int s -> key (s, s); [a, b] -> key (a, b)."""
+    if salt is None:
+        return 0, 0, 0
+    if isinstance(salt, int):
+        return 1, salt & (2**64 - 1), salt & (2**64 - 1)
+    if isinstance(salt, (tuple, list)) and len(salt) == 2:
+        return 1, int(salt[0]) & (2**64 - 1), int(salt[1]) & (2**64 - 1)
+    raise ValueError(f"`salt` should be a tuple or list of two strong hash keys or a single integer. Received: salt={salt}.")

@@ -1,0 +1,86 @@
+"""Layer factory: one preprocessing layer per working feature, keyed by feature name.
+
+Mirror of /root/reference/backend/utils/preprocess_utils.py:7-47 (`get_preprocess_layers`):
+same constructor arguments per deal (hashing -> DoubleHashingEmbedding(num_bins=vocab_size,
+output_dim=embedding_dim, seeds=hash_seeds, mask_value="", mask_zero=True, combiner=pooling,
+name="hashing_<feature>"), ...).  The returned mapping is a dict, so the reference's calling
+convention `layers[name](batch[name])` (models/matching/que2search.py:68,76-79) is unchanged;
+it additionally offers `forward_all(batch)`, which sends every pooled hashing feature of the
+batch through ONE kernel launch and hands back per-feature views of one [B, sum(2*D)] buffer.
+"""
+import torch
+
+from ..layers.preprocess_layers import (_POOLED, DiscreteEmbedding, DoubleHashingEmbedding, LookupEmbedding,
+                                        _batch_and_len, as_keys)
+from ...bag_ops import bag_forward
+
+
+class PreprocessLayers(dict):
+    """{feature name: layer}; plus a fused forward over all hashed features."""
+
+    def fused_names(self):
+        return [n for n, l in self.items() if isinstance(l, DoubleHashingEmbedding) and l.combiner in _POOLED]
+
+    def output_layout(self, names=None):
+        """{name: (column offset, width)} of the fused output buffer, in dict order."""
+        layout, col = {}, 0
+        for n in (names if names is not None else self.fused_names()):
+            width = 2 * self[n].output_dim
+            layout[n] = (col, width)
+            col += width
+        return layout, col
+
+    def forward_all(self, batch, names=None, out=None):
+        """batch: {feature name: StringColumn | int tensor | lists}.  Returns {name: tensor}.
+
+        Hashed, pooled features go through one fused launch; the rest are called one by one."""
+        names = list(names) if names is not None else [n for n in self if n in batch]
+        fused = [n for n in names if n in set(self.fused_names())]
+        result = {}
+        if fused:
+            layout, total = self.output_layout(fused)
+            keys = {n: as_keys(batch[n]) for n in fused}
+            B = _batch_and_len(keys[fused[0]])[0]
+            dev = keys[fused[0]].device
+            if out is None:
+                out = torch.empty(B, total, dtype=torch.float32, device=dev)
+            elif tuple(out.shape) != (B, total):
+                raise ValueError(f"out must be [{B}, {total}]")
+            calls = []
+            for n in fused:
+                layer = self[n].build(dev)
+                if _batch_and_len(keys[n])[0] != B:
+                    raise ValueError(f"feature {n}: batch size differs from the first feature's")
+                col, width = layout[n]
+                view = out[:, col:col + width]
+                if _batch_and_len(keys[n])[1] == 0:
+                    view.zero_()
+                else:
+                    calls.append(layer.field_call(keys[n], view))
+                result[n] = view
+            bag_forward(calls, B)
+            result["__fused__"] = out
+        for n in names:
+            if n not in result:
+                result[n] = self[n](batch[n])
+        return result
+
+
+def get_preprocess_layers(conf):
+    preprocess_layers = PreprocessLayers()
+    for feature in conf.train_features:
+        if feature.is_hashing():
+            preprocess_layers[feature.name] = DoubleHashingEmbedding(
+                num_bins=feature.vocab_size, output_dim=feature.embedding_dim, seeds=feature.hash_seeds,
+                mask_value="", mask_zero=True, combiner=feature.pooling.value, name=f"hashing_{feature.name}")
+        elif feature.is_lookup():
+            preprocess_layers[feature.name] = LookupEmbedding(
+                embedding_dim=feature.embedding_dim, dtype=feature.py_type, vocabs=feature.vocabs,
+                vocab_size=feature.vocab_size, pooling=feature.pooling.value, name=f"lookup_{feature.name}")
+        elif feature.is_discrete():
+            preprocess_layers[feature.name] = DiscreteEmbedding(
+                embedding_dim=feature.embedding_dim, vocabs=feature.vocabs, vocab_size=feature.vocab_size,
+                pooling=feature.pooling.value, name=f"discrete_{feature.name}")
+        elif feature.is_bert_encode():
+            raise NotImplementedError("bert_encode features need bert4keras tokenizers (out of scope, SURVEY.md §2 #17)")
+    return preprocess_layers

@@ -1,0 +1,177 @@
+"""Host-side launcher of the fused hash + gather + pool kernel (rf_bag_forward).
+
+PyTorch is plumbing here: it owns device memory and the current CUDA stream; every computation
+happens in librf_b200.so.  A `FieldCall` is one feature field of one batch; `bag_forward`
+sends any number of them through ONE kernel launch.
+"""
+import ctypes as C
+
+import torch
+
+from . import _native as nat
+from .strings import StringColumn
+
+
+class FieldCall(object):
+    """Inputs, tables and output slot of one field for one launch.
+
+    keys      StringColumn | int64 tensor [B, L] (hashed as decimal strings) | None
+    ids       int64 tensor [T, n_items] of pre-hashed row ids (instead of keys)
+    tables    list of (weights[N, D] fp32 cuda tensor or None, num_bins, salt)
+    out       fp32 cuda tensor view [B, T*D] (row stride free, columns contiguous) or None
+    ids_out   int64 tensor [T, n_items] or None
+    """
+
+    def __init__(self, tables, dim, combiner="sum", keys=None, ids=None, mask_mode=nat.MASK_NONE,
+                 int_mask_value=0, out=None, ids_out=None, bag_len=None, bag_offsets=None, n_items=None):
+        self.tables, self.dim, self.combiner = tables, dim, combiner
+        self.keys, self.ids = keys, ids
+        self.mask_mode, self.int_mask_value = mask_mode, int_mask_value
+        self.out, self.ids_out = out, ids_out
+        self.bag_len, self.bag_offsets, self.n_items = bag_len, bag_offsets, n_items
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise nat.NativeError(f"{what} must live on a CUDA device (got {t.device}); there is no CPU fallback")
+    return t
+
+
+def _fill(desc, call, batch):
+    keep = []
+    if call.combiner not in nat.COMBINER:
+        raise ValueError(f"Do not support combiner = '{call.combiner}', supported: [null, sum, min, max, avg, first, last]")
+    if len(call.tables) < 1 or len(call.tables) > nat.MAX_TABLES:
+        raise ValueError(f"a field takes 1..{nat.MAX_TABLES} tables")
+    bag_offsets = call.bag_offsets
+    if isinstance(call.keys, StringColumn):
+        col = call.keys
+        _require_cuda(col.data, "string arena")
+        desc.bytes = col.data.data_ptr()
+        desc.str_offsets = col.offsets.data_ptr()
+        keep += [col.data, col.offsets]
+        n_items = col.n_items
+        if bag_offsets is None:
+            bag_offsets = col.bag_offsets
+        bag_len = call.bag_len if call.bag_len is not None else col.shape[1]
+    elif call.keys is not None:
+        vals = _require_cuda(call.keys, "integer keys")
+        if vals.dtype != torch.int64:
+            raise ValueError(f"integer keys must be int64, got {vals.dtype}")
+        vals = vals.contiguous()
+        desc.int_values = vals.data_ptr()
+        keep.append(vals)
+        n_items = vals.numel()
+        bag_len = call.bag_len if call.bag_len is not None else (vals.shape[1] if vals.dim() == 2 else 1)
+    elif call.ids is not None:
+        ids = _require_cuda(call.ids, "ids")
+        if ids.dtype != torch.int64 or not ids.is_contiguous():
+            raise ValueError("ids must be a contiguous int64 tensor [n_tables, n_items]")
+        desc.ids = ids.data_ptr()
+        keep.append(ids)
+        n_items = ids.numel() // len(call.tables)
+        bag_len = call.bag_len
+    else:
+        raise ValueError("a field needs keys or ids")
+    if bag_offsets is not None:
+        _require_cuda(bag_offsets, "bag_offsets")
+        if bag_offsets.dtype != torch.int32 or bag_offsets.numel() != batch + 1:
+            raise ValueError("bag_offsets must be int32 [batch + 1]")
+        desc.bag_offsets = bag_offsets.data_ptr()
+        desc.n_items = n_items
+        keep.append(bag_offsets)
+        desc.bag_len = 0
+    else:
+        if bag_len is None or batch * bag_len != n_items:
+            raise ValueError(f"dense field: batch ({batch}) x bag_len ({bag_len}) != n_items ({n_items})")
+        desc.bag_len = bag_len
+        desc.n_items = n_items
+    desc.n_tables = len(call.tables)
+    for t, (w, num_bins, salt) in enumerate(call.tables):
+        if num_bins is None or num_bins <= 0:
+            raise ValueError("`num_bins` cannot be `None` or non-positive values.")
+        strong, k0, k1 = nat.salt_to_key(salt)
+        td = desc.tables[t]
+        td.num_bins, td.use_strong, td.key0, td.key1 = int(num_bins), strong, k0, k1
+        if w is not None:
+            _require_cuda(w, "embedding table")
+            if w.dtype != torch.float32 or not w.is_contiguous() or w.shape != (num_bins, call.dim):
+                raise ValueError(f"table {t} must be contiguous fp32 [{num_bins}, {call.dim}], got {tuple(w.shape)} {w.dtype}")
+            td.weights = w.data_ptr()
+            keep.append(w)
+    desc.dim = call.dim
+    desc.combiner = nat.COMBINER[call.combiner]
+    desc.mask_mode = call.mask_mode
+    desc.int_mask_value = int(call.int_mask_value)
+    if call.dim > 0:
+        out = _require_cuda(call.out, "output")
+        if out.dtype != torch.float32 or out.dim() != 2 or out.shape[0] != batch or \
+                out.shape[1] != call.dim * len(call.tables) or (out.shape[1] > 1 and out.stride(1) != 1):
+            raise ValueError(f"output must be fp32 [batch, n_tables*dim] with contiguous columns, got {tuple(out.shape)}")
+        desc.out = out.data_ptr()
+        desc.out_stride = out.stride(0) if batch > 1 else out.shape[1]
+        keep.append(out)
+    if call.ids_out is not None:
+        io = _require_cuda(call.ids_out, "ids_out")
+        if io.dtype != torch.int64 or not io.is_contiguous() or io.numel() != len(call.tables) * n_items:
+            raise ValueError("ids_out must be contiguous int64 [n_tables, n_items]")
+        desc.ids_out = io.data_ptr()
+        keep.append(io)
+    return keep
+
+
+def bag_forward(calls, batch, stream=None):
+    """Run every FieldCall of one batch through a single rf_bag_forward launch."""
+    if not calls or batch == 0:
+        return
+    descs = (nat.FieldDesc * len(calls))()
+    keep = []
+    for i, call in enumerate(calls):
+        keep += _fill(descs[i], call, batch)
+    dev = keep[0].device
+    if any(t.device != dev for t in keep):
+        raise ValueError("all tensors of one launch must be on the same device")
+    if stream is None:
+        stream = torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().rf_bag_forward(descs, len(calls), batch, C.c_void_p(stream.cuda_stream)))
+    return keep
+
+
+def hash_strings(col, num_bins, mask_value=None, salt=None):
+    """Keras `Hashing(num_bins, mask_value, salt)` on a StringColumn -> int64 ids shaped like it."""
+    if mask_value not in (None, ""):
+        raise NotImplementedError("only mask_value in (None, '') is supported for string keys "
+                                  "(get_preprocess_layers always passes '')")
+    _require_cuda(col.data, "string arena")
+    out = torch.empty(col.n_items, dtype=torch.int64, device=col.device)
+    strong, k0, k1 = nat.salt_to_key(salt)
+    mode = nat.MASK_NONE if mask_value is None else nat.MASK_EMPTY_STRING
+    if num_bins is None or num_bins <= 0:
+        raise ValueError("`num_bins` cannot be `None` or non-positive values.")
+    if col.n_items:
+        with torch.cuda.device(col.device):
+            nat.check(nat.lib().rf_hash_strings(col.data.data_ptr(), col.offsets.data_ptr(), col.n_items, int(num_bins),
+                                                mode, strong, k0, k1, out.data_ptr(),
+                                                C.c_void_p(torch.cuda.current_stream(col.device).cuda_stream)))
+    return out.view(col.shape) if col.shape[1] is not None else out
+
+
+def hash_ints(values, num_bins, mask_value=None, salt=None):
+    """Keras `Hashing` on an int64 tensor (values are hashed as their decimal strings)."""
+    _require_cuda(values, "integer keys")
+    if values.dtype != torch.int64:
+        raise ValueError(f"integer keys must be int64, got {values.dtype}")
+    if num_bins is None or num_bins <= 0:
+        raise ValueError("`num_bins` cannot be `None` or non-positive values.")
+    vals = values.contiguous()
+    out = torch.empty_like(vals)
+    strong, k0, k1 = nat.salt_to_key(salt)
+    mode = nat.MASK_NONE if mask_value is None else nat.MASK_INT_VALUE
+    if vals.numel():
+        with torch.cuda.device(vals.device):
+            nat.check(nat.lib().rf_hash_int64(vals.data_ptr(), vals.numel(), int(num_bins), mode,
+                                              int(mask_value) if mask_value is not None else 0, strong, k0, k1,
+                                              out.data_ptr(),
+                                              C.c_void_p(torch.cuda.current_stream(vals.device).cuda_stream)))
+    return out

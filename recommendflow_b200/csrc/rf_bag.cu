@@ -1,0 +1,670 @@
+// rf_bag.cu -- fused hash + gather + pool for sm_100a (B200), and its C-ABI.
+//
+// One launch covers every feature field of a batch.  It replaces, per field, the op chain
+//   Hashing x T -> Embedding gather x T -> reduce(axis=1) x T -> concat
+// of /root/reference/backend/layers/preprocess_layers.py:94-97 (DoubleHashingEmbedding.call,
+// T = 2) and :66-68 (EmbeddingBag.call), and, across fields, the per-feature Python loop of
+// models/matching/que2search.py:68,76-79.  The [B, L, D] gather result is never materialised.
+//
+// Work decomposition (HBM-bound byte/integer work -- no tensor cores on this path):
+//   tile  = (field, range of bags), ~kChunk keys; one CTA per tile, all fields in one grid.
+//   round = <= kChunk keys whose bags fit the round (a single bag longer than kChunk is
+//           walked in sub-rounds with the accumulators kept in registers).
+//   phase A: key offsets -> smem (coalesced), key bytes -> smem (16-byte vector copies of
+//            the tile's contiguous slice of the string arena).
+//   phase B: one key per thread: FarmHash64 / SipHash-2-4 out of shared memory, bucket via a
+//            multiply-high reciprocal, ids -> smem (and optionally to global as int64).
+//   phase C: one lane group per (bag, table): ids broadcast from smem, rows fetched with
+//            128-bit loads (4-8 rows in flight per lane), pooled in bag order in registers,
+//            one coalesced 128-bit store per lane.  Pooling is sequential in index order so
+//            fp32 results are bit-identical to the oracle's.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rf_b200.h"
+#include "rf_common.h"
+#include "rf_hash.cuh"
+
+namespace rf {
+
+constexpr int kThreads = 256;
+constexpr int kChunk = 1024;              // keys hashed per round
+constexpr int kStageBytes = 16 * 1024;    // key bytes staged per round
+constexpr int kMaxTileBags = 1024;        // bags per tile (jagged: CSR slice kept in smem)
+constexpr int kMaxFieldsSmem = 512;       // tile-prefix table kept in smem up to this many fields
+constexpr int kMaxDim = 512;
+
+struct DevTable {
+    const float *w;
+    uint64_t k0, k1;
+    FastMod mod;
+    uint32_t use_strong;
+    uint32_t masking;   // bucket 0 reserved for the mask value
+};
+
+struct DevField {
+    const uint8_t *bytes;
+    const int32_t *soffs;
+    const int64_t *ints;
+    const int64_t *ids_in;
+    const int32_t *boffs;
+    float *out;
+    int64_t *ids_out;
+    int64_t out_stride;
+    int64_t n_items;
+    int64_t int_mask;
+    int32_t batch;
+    int32_t bag_len;
+    int32_t dim;
+    int32_t n_tables;
+    int32_t combiner;
+    int32_t mask_mode;
+    int32_t bags_per_tile;
+    int32_t tile_begin;
+    int32_t vec_ok;      // 128-bit path usable (dim % 4 == 0, aligned pointers/strides)
+    int32_t pad_;
+    DevTable t[RF_MAX_TABLES_PER_FIELD];
+};
+
+// ------------------------------------------------------------------------------------------
+// pooling primitives
+// ------------------------------------------------------------------------------------------
+template <int OP>
+__device__ __forceinline__ float pool_init() {
+    return OP == RF_COMBINER_MIN ? __int_as_float(0x7f800000) : OP == RF_COMBINER_MAX ? __int_as_float(0xff800000) : 0.0f;
+}
+template <int OP>
+__device__ __forceinline__ float pool_op(float acc, float x) {
+    if (OP == RF_COMBINER_MIN) return x < acc ? x : acc;
+    if (OP == RF_COMBINER_MAX) return x > acc ? x : acc;
+    return acc + x;
+}
+template <int OP>
+__device__ __forceinline__ void pool_op4(float4 &a, const float4 &x) {
+    a.x = pool_op<OP>(a.x, x.x);
+    a.y = pool_op<OP>(a.y, x.y);
+    a.z = pool_op<OP>(a.z, x.z);
+    a.w = pool_op<OP>(a.w, x.w);
+}
+
+__device__ __forceinline__ float4 ldg_row(const float4 *p) { return __ldg(p); }
+
+// Accumulate `cnt` rows (ids in shared memory) into acc[], in index order.
+template <int NV, int OP>
+__device__ __forceinline__ void accumulate_vec(float4 (&acc)[NV], const float4 *__restrict__ W, uint32_t row_vecs,
+                                               uint32_t lg, uint32_t G, const uint32_t *sid, int cnt) {
+    constexpr int U = NV == 1 ? 8 : (NV == 2 ? 4 : 2);
+    int i = 0;
+    for (; i + U <= cnt; i += U) {
+        float4 r[U][NV];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float4 *row = W + (size_t)sid[i + u] * row_vecs;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const uint32_t c = lg + v * G;
+                r[u][v] = (NV == 1 || c < row_vecs) ? ldg_row(row + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int v = 0; v < NV; ++v) pool_op4<OP>(acc[v], r[u][v]);
+    }
+    if (U > 4 && i + 4 <= cnt) {
+        float4 r[4][NV];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float4 *row = W + (size_t)sid[i + u] * row_vecs;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) r[u][v] = ldg_row(row + lg + v * G);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < NV; ++v) pool_op4<OP>(acc[v], r[u][v]);
+        i += 4;
+    }
+    for (; i < cnt; ++i) {
+        const float4 *row = W + (size_t)sid[i] * row_vecs;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const uint32_t c = lg + v * G;
+            if (NV == 1 || c < row_vecs) pool_op4<OP>(acc[v], ldg_row(row + c));
+        }
+    }
+}
+
+struct Round {
+    int bag0, bag1;        // bags of this round, relative to the tile's first bag
+    int64_t item0;         // first key of the round (field-flat index)
+    int n_keys;            // keys hashed this round
+    bool partial;          // true: one long bag walked in sub-rounds
+    bool first_part, last_part;
+};
+
+// ------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------
+struct Smem {
+    uint32_t ids[RF_MAX_TABLES_PER_FIELD * kChunk];
+    int32_t soff[kChunk + 4];
+    uint32_t stage[kStageBytes / 4 + 8];
+    int32_t boff[kMaxTileBags + 4];
+    int32_t tile_begin[kMaxFieldsSmem + 1];
+    DevField field;   // this tile's descriptor, copied once per tile
+};
+static_assert(sizeof(DevField) % 4 == 0, "DevField is copied word-wise");
+
+template <class Src>
+__device__ __forceinline__ uint32_t bucket_of(const Src &src, uint32_t len, const DevTable &t, bool is_mask) {
+    const uint64_t h = t.use_strong ? siphash24(src, len, t.k0, t.k1) : fingerprint64(src, len);
+    uint32_t id = (uint32_t)fastmod(h, t.mod);
+    if (t.masking) id = is_mask ? 0u : id + 1u;
+    return id;
+}
+
+template <int NV, int OP>
+__device__ __forceinline__ void pool_round_vec(const DevField &F, const Smem &sm, const Round &R, int tile_bag0,
+                                               int64_t tile_item0, float4 *carry) {
+    const uint32_t row_vecs = (uint32_t)F.dim >> 2;
+    uint32_t G = 1;
+    while (G < row_vecs && G < 32) G <<= 1;
+    const uint32_t lg = threadIdx.x & (G - 1);
+    const uint32_t grp = threadIdx.x / G;
+    const uint32_t n_grp = kThreads / G;
+    const int T = F.n_tables;
+    const bool dense = F.boffs == nullptr;
+    const int n_work = (R.bag1 - R.bag0) * T;
+    for (int w = grp; w < n_work; w += n_grp) {
+        const int bl = R.bag0 + (T == 2 ? (w >> 1) : w);
+        const int t = T == 2 ? (w & 1) : 0;
+        int64_t lo, hi;   // field-flat key range of the bag
+        if (dense) {
+            lo = (int64_t)(tile_bag0 + bl) * F.bag_len;
+            hi = lo + F.bag_len;
+        } else {
+            lo = sm.boff[bl];
+            hi = sm.boff[bl + 1];
+        }
+        int rel = (int)(lo - R.item0), cnt = (int)(hi - lo);
+        if (R.partial) {   // the round holds a slice [item0, item0 + n_keys) of this one bag
+            rel = 0;
+            cnt = R.n_keys;
+        }
+        float4 acc[NV];
+        if (R.partial && !R.first_part) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) acc[v] = carry[v];
+        } else {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) acc[v] = make_float4(pool_init<OP>(), pool_init<OP>(), pool_init<OP>(), pool_init<OP>());
+        }
+        if (lg < row_vecs)
+            accumulate_vec<NV, OP>(acc, reinterpret_cast<const float4 *>(F.t[t].w), row_vecs, lg, G,
+                                   sm.ids + t * kChunk + rel, cnt);
+        if (R.partial && !R.last_part) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) carry[v] = acc[v];
+            continue;
+        }
+        const int64_t total = hi - lo;
+        if (total == 0) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (OP == RF_COMBINER_AVG) {
+            const float c = (float)total;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                acc[v].x = acc[v].x / c;
+                acc[v].y = acc[v].y / c;
+                acc[v].z = acc[v].z / c;
+                acc[v].w = acc[v].w / c;
+            }
+        }
+        float4 *o = reinterpret_cast<float4 *>(F.out + (int64_t)(tile_bag0 + bl) * F.out_stride + (int64_t)t * F.dim);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const uint32_t c = lg + v * G;
+            if (c < row_vecs) o[c] = acc[v];
+        }
+    }
+    (void)tile_item0;
+}
+
+// Generic-D path (dim % 4 != 0 or unaligned): one warp per (bag, table), one float per lane per
+// 32-column slab, same in-order accumulation.  Long bags carry kMaxDim/32 partial slabs.
+template <int OP>
+__device__ __forceinline__ void pool_round_scalar(const DevField &F, const Smem &sm, const Round &R, int tile_bag0,
+                                                  float (&carry)[kMaxDim / 32]) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warp = kThreads / 32;
+    const int T = F.n_tables;
+    const bool dense = F.boffs == nullptr;
+    const int n_work = (R.bag1 - R.bag0) * T;
+    const int D = F.dim;
+    for (int w = warp; w < n_work; w += n_warp) {
+        const int bl = R.bag0 + (T == 2 ? (w >> 1) : w);
+        const int t = T == 2 ? (w & 1) : 0;
+        int64_t lo, hi;
+        if (dense) {
+            lo = (int64_t)(tile_bag0 + bl) * F.bag_len;
+            hi = lo + F.bag_len;
+        } else {
+            lo = sm.boff[bl];
+            hi = sm.boff[bl + 1];
+        }
+        int rel = (int)(lo - R.item0), cnt = (int)(hi - lo);
+        if (R.partial) {
+            rel = 0;
+            cnt = R.n_keys;
+        }
+        const float *W = F.t[t].w;
+        const uint32_t *sid = sm.ids + t * kChunk + rel;
+        float *o = F.out + (int64_t)(tile_bag0 + bl) * F.out_stride + (int64_t)t * D;
+        const int64_t total = hi - lo;
+#pragma unroll
+        for (int s = 0; s < kMaxDim / 32; ++s) {
+            const int d = s * 32 + (int)lane;
+            if (s * 32 >= D) break;
+            float acc = (R.partial && !R.first_part) ? carry[s] : pool_init<OP>();
+            if (d < D)
+                for (int i = 0; i < cnt; ++i) acc = pool_op<OP>(acc, __ldg(W + (size_t)sid[i] * D + d));
+            if (R.partial && !R.last_part) {
+                carry[s] = acc;
+                continue;
+            }
+            if (total == 0) acc = 0.f;
+            else if (OP == RF_COMBINER_AVG) acc = acc / (float)total;
+            if (d < D) o[d] = acc;
+        }
+    }
+}
+
+template <int OP>
+__device__ __forceinline__ void pool_round(const DevField &F, const Smem &sm, const Round &R, int tile_bag0,
+                                           int64_t tile_item0, float4 (&cv)[4], float (&cs)[kMaxDim / 32]) {
+    if (F.vec_ok) {
+        const int row_vecs = F.dim >> 2;
+        if (row_vecs <= 32) {
+            pool_round_vec<1, OP>(F, sm, R, tile_bag0, tile_item0, cv);
+        } else if (row_vecs <= 64) {
+            pool_round_vec<2, OP>(F, sm, R, tile_bag0, tile_item0, cv);
+        } else {
+            pool_round_vec<4, OP>(F, sm, R, tile_bag0, tile_item0, cv);
+        }
+    } else {
+        pool_round_scalar<OP>(F, sm, R, tile_bag0, cs);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) bag_forward_kernel(const DevField *__restrict__ fields, int n_fields, int total_tiles) {
+    __shared__ Smem sm;
+    const int tid = threadIdx.x;
+
+    const bool prefix_in_smem = n_fields <= kMaxFieldsSmem;
+    if (prefix_in_smem) {
+        for (int i = tid; i < n_fields; i += kThreads) sm.tile_begin[i] = fields[i].tile_begin;
+        if (tid == 0) sm.tile_begin[n_fields] = total_tiles;
+        __syncthreads();
+    }
+
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        // ---- which field does this tile belong to (largest f with tile_begin[f] <= tile) -----
+        int f_lo = 0, f_hi = n_fields - 1;
+        while (f_lo < f_hi) {
+            const int mid = (f_lo + f_hi + 1) >> 1;
+            const int tb = prefix_in_smem ? sm.tile_begin[mid] : fields[mid].tile_begin;
+            if (tb <= tile) f_lo = mid; else f_hi = mid - 1;
+        }
+        // One round trip: every thread reads the few words it needs for the tile geometry
+        // straight from the (L2-resident) descriptor while the descriptor itself and the tile's
+        // CSR slice are copied into shared memory for the phases below.
+        const DevField &G = fields[f_lo];
+        const int tile_bag0 = (tile - G.tile_begin) * G.bags_per_tile;
+        const int tile_nbags = min(G.bags_per_tile, G.batch - tile_bag0);
+        const int32_t *g_boffs = G.boffs;
+        const bool dense = g_boffs == nullptr;
+        {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&G);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(&sm.field);
+            for (int i = tid; i < (int)(sizeof(DevField) / 4); i += kThreads) dst[i] = src[i];
+            if (!dense)
+                for (int i = tid; i <= tile_nbags; i += kThreads) sm.boff[i] = g_boffs[tile_bag0 + i];
+        }
+        __syncthreads();
+        const DevField &F = sm.field;
+        const int T = F.n_tables;
+        const int64_t tile_item0 = dense ? (int64_t)tile_bag0 * F.bag_len : (int64_t)sm.boff[0];
+
+        float4 carry_v[4];
+        float carry_s[kMaxDim / 32];
+
+        int bag = 0;            // next bag of the tile, relative
+        int64_t part_done = 0;  // keys of a long bag already consumed
+        while (bag < tile_nbags) {
+            // ---- carve the next round ------------------------------------------------------
+            Round R;
+            const int64_t b_lo = dense ? tile_item0 + (int64_t)bag * F.bag_len : (int64_t)sm.boff[bag];
+            const int64_t b_hi = dense ? b_lo + F.bag_len : (int64_t)sm.boff[bag + 1];
+            if (b_hi - b_lo > kChunk) {
+                R.partial = true;
+                R.bag0 = bag;
+                R.bag1 = bag + 1;
+                R.item0 = b_lo + part_done;
+                R.n_keys = (int)min((int64_t)kChunk, b_hi - R.item0);
+                R.first_part = part_done == 0;
+                R.last_part = R.item0 + R.n_keys == b_hi;
+            } else {
+                R.partial = false;
+                R.first_part = R.last_part = true;
+                R.bag0 = bag;
+                R.item0 = b_lo;
+                int end;
+                if (dense) {
+                    const int per = F.bag_len > 0 ? kChunk / F.bag_len : tile_nbags;
+                    end = min(tile_nbags, bag + max(per, 1));
+                } else {
+                    // largest end with boff[end] - b_lo <= kChunk (boff is non-decreasing)
+                    int lo = bag + 1, hi = tile_nbags;
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if ((int64_t)sm.boff[mid] - b_lo <= kChunk) lo = mid; else hi = mid - 1;
+                    }
+                    end = lo;
+                }
+                R.bag1 = end;
+                const int64_t e_hi = dense ? tile_item0 + (int64_t)end * F.bag_len : (int64_t)sm.boff[end];
+                R.n_keys = (int)(e_hi - b_lo);
+            }
+
+            // ---- phase A+B: keys -> bucket ids in shared memory -----------------------------
+            if (F.ids_in != nullptr) {
+                for (int j = tid; j < R.n_keys; j += kThreads)
+                    for (int t = 0; t < T; ++t)
+                        sm.ids[t * kChunk + j] = (uint32_t)F.ids_in[(int64_t)t * F.n_items + R.item0 + j];
+            } else if (F.ints != nullptr) {
+                uint32_t *scratch = sm.stage + tid * 6;
+                for (int j = tid; j < R.n_keys; j += kThreads) {
+                    const int64_t v = F.ints[R.item0 + j];
+                    const uint32_t len = format_int64(v, scratch);
+                    const WordSrcShared src{scratch, 0u};
+                    const bool is_mask = F.mask_mode == RF_MASK_INT_VALUE && v == F.int_mask;
+                    for (int t = 0; t < T; ++t) {
+                        const uint32_t id = bucket_of(src, len, F.t[t], is_mask);
+                        sm.ids[t * kChunk + j] = id;
+                        if (F.ids_out) F.ids_out[(int64_t)t * F.n_items + R.item0 + j] = (int64_t)id;
+                    }
+                }
+            } else {
+                for (int j = tid; j <= R.n_keys; j += kThreads) sm.soff[j] = F.soffs[R.item0 + j];
+                __syncthreads();
+                const int32_t byte0 = sm.soff[0];
+                const uint32_t n_bytes = (uint32_t)(sm.soff[R.n_keys] - byte0);
+                const uintptr_t addr0 = reinterpret_cast<uintptr_t>(F.bytes) + (uintptr_t)byte0;
+                const uint32_t shift = (uint32_t)(addr0 & 15u);
+                const bool staged = shift + n_bytes + 8u <= (uint32_t)kStageBytes;
+                if (staged) {
+                    const uint4 *g = reinterpret_cast<const uint4 *>(addr0 - shift);
+                    uint4 *s = reinterpret_cast<uint4 *>(sm.stage);
+                    const uint32_t n_vec = (shift + n_bytes + 8u + 15u) >> 4;
+                    for (uint32_t i = tid; i < n_vec; i += kThreads) s[i] = __ldg(g + i);
+                    __syncthreads();
+                }
+                for (int j = tid; j < R.n_keys; j += kThreads) {
+                    const int32_t o = sm.soff[j];
+                    const uint32_t len = (uint32_t)(sm.soff[j + 1] - o);
+                    const bool is_mask = F.mask_mode == RF_MASK_EMPTY_STRING && len == 0;
+                    for (int t = 0; t < T; ++t) {
+                        uint32_t id;
+                        if (staged) {
+                            const WordSrcShared src{sm.stage, shift + (uint32_t)(o - byte0)};
+                            id = bucket_of(src, len, F.t[t], is_mask);
+                        } else {
+                            const uintptr_t a = reinterpret_cast<uintptr_t>(F.bytes) + (uintptr_t)o;
+                            const WordSrcGlobal src{reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3), (uint32_t)(a & 3u)};
+                            id = bucket_of(src, len, F.t[t], is_mask);
+                        }
+                        sm.ids[t * kChunk + j] = id;
+                        if (F.ids_out) F.ids_out[(int64_t)t * F.n_items + R.item0 + j] = (int64_t)id;
+                    }
+                }
+            }
+            __syncthreads();
+
+            // ---- phase C: gather + pool -----------------------------------------------------
+            if (F.dim > 0) {
+                switch (F.combiner) {
+                    case RF_COMBINER_SUM: pool_round<RF_COMBINER_SUM>(F, sm, R, tile_bag0, tile_item0, carry_v, carry_s); break;
+                    case RF_COMBINER_AVG: pool_round<RF_COMBINER_AVG>(F, sm, R, tile_bag0, tile_item0, carry_v, carry_s); break;
+                    case RF_COMBINER_MIN: pool_round<RF_COMBINER_MIN>(F, sm, R, tile_bag0, tile_item0, carry_v, carry_s); break;
+                    default: pool_round<RF_COMBINER_MAX>(F, sm, R, tile_bag0, tile_item0, carry_v, carry_s); break;
+                }
+            }
+            __syncthreads();
+
+            if (R.partial) {
+                part_done += R.n_keys;
+                if (R.last_part) {
+                    part_done = 0;
+                    bag += 1;
+                }
+            } else {
+                bag = R.bag1;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: descriptor ring + launch
+// ------------------------------------------------------------------------------------------
+static std::atomic<int64_t> g_launches{0};
+
+struct DescSlot {
+    void *host = nullptr;
+    void *dev = nullptr;
+    size_t cap = 0;
+    cudaEvent_t done = nullptr;
+    bool used = false;
+};
+
+struct DeviceState {
+    DescSlot slots[8];
+    int next = 0;
+    int sm_count = 0;
+    std::mutex mu;
+};
+
+static DeviceState *device_state(int dev) {
+    static std::mutex mu;
+    static std::vector<DeviceState *> states;
+    std::lock_guard<std::mutex> lk(mu);
+    if ((int)states.size() <= dev) states.resize(dev + 1, nullptr);
+    if (!states[dev]) states[dev] = new DeviceState();
+    return states[dev];
+}
+
+static int launch_fields(std::vector<DevField> &dev_fields, cudaStream_t stream) {
+    int dev = 0;
+    RF_CUDA(cudaGetDevice(&dev));
+    DeviceState *st = device_state(dev);
+    std::lock_guard<std::mutex> lk(st->mu);
+    if (st->sm_count == 0) RF_CUDA(cudaDeviceGetAttribute(&st->sm_count, cudaDevAttrMultiProcessorCount, dev));
+
+    // tile sizing: ~kChunk keys per tile, smaller when the whole launch would not fill the GPU
+    int64_t total_keys = 0;
+    for (auto &f : dev_fields) total_keys += f.n_items;
+    int64_t target = total_keys / ((int64_t)st->sm_count * 8);
+    if (target < 128) target = 128;
+    if (target > kChunk) target = kChunk;
+    int64_t tiles = 0;
+    for (auto &f : dev_fields) {
+        int64_t avg = f.batch > 0 ? (f.n_items + f.batch - 1) / f.batch : 1;
+        if (avg < 1) avg = 1;
+        int64_t bpt = target / avg;
+        if (bpt < 1) bpt = 1;
+        if (bpt > kMaxTileBags) bpt = kMaxTileBags;
+        f.bags_per_tile = (int32_t)bpt;
+        if (tiles > INT32_MAX) return set_error(RF_ERR_UNSUPPORTED, "too many tiles in one launch");
+        f.tile_begin = (int32_t)tiles;
+        tiles += (f.batch + bpt - 1) / bpt;
+    }
+    if (tiles == 0) return RF_OK;
+    if (tiles > INT32_MAX) return set_error(RF_ERR_UNSUPPORTED, "too many tiles in one launch");
+
+    DescSlot &slot = st->slots[st->next];
+    st->next = (st->next + 1) % 8;
+    const size_t bytes = dev_fields.size() * sizeof(DevField);
+    if (slot.used) RF_CUDA(cudaEventSynchronize(slot.done));
+    if (slot.cap < bytes) {
+        if (slot.host) cudaFreeHost(slot.host);
+        if (slot.dev) cudaFree(slot.dev);
+        slot.host = slot.dev = nullptr;
+        size_t cap = bytes < 65536 ? 65536 : bytes * 2;
+        RF_CUDA(cudaMallocHost(&slot.host, cap));
+        RF_CUDA(cudaMalloc(&slot.dev, cap));
+        slot.cap = cap;
+    }
+    if (!slot.done) RF_CUDA(cudaEventCreateWithFlags(&slot.done, cudaEventDisableTiming));
+    memcpy(slot.host, dev_fields.data(), bytes);
+    RF_CUDA(cudaMemcpyAsync(slot.dev, slot.host, bytes, cudaMemcpyHostToDevice, stream));
+    bag_forward_kernel<<<(unsigned)tiles, kThreads, 0, stream>>>(static_cast<const DevField *>(slot.dev),
+                                                               (int)dev_fields.size(), (int)tiles);
+    RF_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    RF_CUDA(cudaEventRecord(slot.done, stream));
+    slot.used = true;
+    return RF_OK;
+}
+
+static int fill_table(DevTable &dt, const rf_table_desc &t, int mask_mode, bool need_weights, int fi, int ti) {
+    if (t.num_bins <= 0) return set_error(RF_ERR_INVALID, "`num_bins` cannot be `None` or non-positive values.");
+    if (t.num_bins > 0xffffffffLL) return set_error(RF_ERR_UNSUPPORTED, "num_bins above 2^32-1 is not supported");
+    if (need_weights && t.weights == nullptr)
+        return set_error(RF_ERR_INVALID, "field %d table %d: weights pointer is NULL", fi, ti);
+    dt.w = t.weights;
+    dt.k0 = t.key0;
+    dt.k1 = t.key1;
+    dt.use_strong = t.use_strong ? 1u : 0u;
+    dt.masking = (mask_mode != RF_MASK_NONE && t.num_bins > 1) ? 1u : 0u;
+    dt.mod = make_fastmod((uint64_t)t.num_bins - (dt.masking ? 1u : 0u));
+    return RF_OK;
+}
+
+static int build_field(DevField &d, const rf_field_desc &f, int64_t batch, int fi) {
+    memset(&d, 0, sizeof(d));
+    const int n_src = (f.bytes != nullptr) + (f.int_values != nullptr) + (f.ids != nullptr);
+    if (n_src != 1) return set_error(RF_ERR_INVALID, "field %d: exactly one of bytes / int_values / ids must be set", fi);
+    if (f.bytes && !f.str_offsets) return set_error(RF_ERR_INVALID, "field %d: bytes given without str_offsets", fi);
+    if (f.n_tables < 1 || f.n_tables > RF_MAX_TABLES_PER_FIELD)
+        return set_error(RF_ERR_INVALID, "field %d: n_tables must be 1..%d", fi, RF_MAX_TABLES_PER_FIELD);
+    if (batch < 0 || batch > INT32_MAX) return set_error(RF_ERR_INVALID, "batch out of range");
+    if (f.dim < 0 || f.dim > kMaxDim) return set_error(RF_ERR_UNSUPPORTED, "field %d: dim must be in [0, %d]", fi, kMaxDim);
+    if (f.dim == 0 && !f.ids_out) return set_error(RF_ERR_INVALID, "field %d: dim == 0 (hash only) needs ids_out", fi);
+    if (f.dim > 0 && !f.out) return set_error(RF_ERR_INVALID, "field %d: out pointer is NULL", fi);
+    if (f.combiner < RF_COMBINER_SUM || f.combiner > RF_COMBINER_MAX)
+        return set_error(RF_ERR_INVALID, "field %d: Do not support combiner = %d", fi, f.combiner);
+    if (f.mask_mode < RF_MASK_NONE || f.mask_mode > RF_MASK_INT_VALUE)
+        return set_error(RF_ERR_INVALID, "field %d: bad mask_mode", fi);
+    if (f.bytes && f.mask_mode == RF_MASK_INT_VALUE) return set_error(RF_ERR_INVALID, "field %d: integer mask on string keys", fi);
+    if (f.int_values && f.mask_mode == RF_MASK_EMPTY_STRING) return set_error(RF_ERR_INVALID, "field %d: string mask on integer keys", fi);
+    if (!f.bag_offsets && f.bag_len < 0) return set_error(RF_ERR_INVALID, "field %d: negative bag_len", fi);
+    d.bytes = f.bytes;
+    d.soffs = f.str_offsets;
+    d.ints = f.int_values;
+    d.ids_in = f.ids;
+    d.boffs = f.bag_offsets;
+    d.out = f.out;
+    d.ids_out = f.ids_out;
+    d.out_stride = f.out_stride;
+    d.batch = (int32_t)batch;
+    d.bag_len = f.bag_offsets ? 0 : f.bag_len;
+    d.n_items = f.bag_offsets ? f.n_items : batch * (int64_t)f.bag_len;
+    if (d.n_items < 0) return set_error(RF_ERR_INVALID, "field %d: negative n_items", fi);
+    d.int_mask = f.int_mask_value;
+    d.dim = f.dim;
+    d.n_tables = f.n_tables;
+    d.combiner = f.combiner;
+    d.mask_mode = f.mask_mode;
+    bool aligned = (f.dim % 4 == 0) && (reinterpret_cast<uintptr_t>(f.out) % 16 == 0) && (f.out_stride % 4 == 0);
+    for (int t = 0; t < f.n_tables; ++t) {
+        int rc = fill_table(d.t[t], f.tables[t], f.mask_mode, f.dim > 0, fi, t);
+        if (rc != RF_OK) return rc;
+        aligned = aligned && (reinterpret_cast<uintptr_t>(f.tables[t].weights) % 16 == 0);
+    }
+    d.vec_ok = aligned ? 1 : 0;
+    return RF_OK;
+}
+
+}  // namespace rf
+
+using namespace rf;
+
+extern "C" {
+
+int rf_abi_version(void) { return RF_B200_ABI_VERSION; }
+
+int64_t rf_launch_count(void) { return g_launches.load(); }
+
+uint64_t rf_debug_fastmod(uint64_t x, uint64_t d) {
+    const FastMod m = make_fastmod(d);
+    return fastmod(x, m);
+}
+
+int rf_bag_forward(const rf_field_desc *fields, int n_fields, int64_t batch, void *stream) {
+    if (n_fields < 0 || (n_fields > 0 && !fields)) return set_error(RF_ERR_INVALID, "bad fields array");
+    if (n_fields == 0 || batch == 0) return RF_OK;
+    std::vector<DevField> dev(n_fields);
+    for (int i = 0; i < n_fields; ++i) {
+        int rc = build_field(dev[i], fields[i], batch, i);
+        if (rc != RF_OK) return rc;
+    }
+    return launch_fields(dev, static_cast<cudaStream_t>(stream));
+}
+
+static int hash_only(rf_field_desc &f, int64_t n_items, int64_t num_bins, int mask_mode, int use_strong, uint64_t key0,
+                     uint64_t key1, int64_t *d_ids_out, void *stream) {
+    if (n_items < 0 || n_items > INT32_MAX) return set_error(RF_ERR_INVALID, "n_items out of range");
+    if (n_items == 0) return RF_OK;
+    if (!d_ids_out) return set_error(RF_ERR_INVALID, "ids_out is NULL");
+    f.bag_len = 1;
+    f.n_tables = 1;
+    f.tables[0].num_bins = num_bins;
+    f.tables[0].use_strong = use_strong;
+    f.tables[0].key0 = key0;
+    f.tables[0].key1 = key1;
+    f.dim = 0;
+    f.combiner = RF_COMBINER_SUM;
+    f.mask_mode = mask_mode;
+    f.ids_out = d_ids_out;
+    return rf_bag_forward(&f, 1, n_items, stream);
+}
+
+int rf_hash_strings(const uint8_t *d_bytes, const int32_t *d_str_offsets, int64_t n_items, int64_t num_bins, int mask_mode,
+                    int use_strong, uint64_t key0, uint64_t key1, int64_t *d_ids_out, void *stream) {
+    rf_field_desc f;
+    memset(&f, 0, sizeof(f));
+    if (n_items > 0 && (!d_bytes || !d_str_offsets)) return set_error(RF_ERR_INVALID, "bytes / str_offsets is NULL");
+    f.bytes = d_bytes;
+    f.str_offsets = d_str_offsets;
+    return hash_only(f, n_items, num_bins, mask_mode, use_strong, key0, key1, d_ids_out, stream);
+}
+
+int rf_hash_int64(const int64_t *d_values, int64_t n_items, int64_t num_bins, int mask_mode, int64_t int_mask_value,
+                  int use_strong, uint64_t key0, uint64_t key1, int64_t *d_ids_out, void *stream) {
+    rf_field_desc f;
+    memset(&f, 0, sizeof(f));
+    if (n_items > 0 && !d_values) return set_error(RF_ERR_INVALID, "values is NULL");
+    f.int_values = d_values;
+    f.int_mask_value = int_mask_value;
+    return hash_only(f, n_items, num_bins, mask_mode, use_strong, key0, key1, d_ids_out, stream);
+}
+
+}  // extern "C"

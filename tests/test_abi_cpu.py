@@ -1,0 +1,65 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/rf_b200.h
+declares, and its host-side helpers are right.  No compute entry point is called here."""
+import ctypes
+import os
+import random
+import re
+
+import pytest
+
+from recommendflow_b200 import _native as nat
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "rf_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = nat.lib()
+    names = declared_symbols()
+    assert "rf_bag_forward" in names and "rf_hash_strings" in names and len(names) >= 7
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/rf_b200.h but not exported"
+    assert lib.rf_abi_version() == 1
+
+
+def test_struct_layout_matches_header_sizes():
+    # rf_table_desc: ptr + i64 + 2*i32 + 2*u64 = 40 bytes; rf_field_desc packs without surprises
+    assert ctypes.sizeof(nat.TableDesc) == 40
+    assert ctypes.sizeof(nat.FieldDesc) == 5 * 8 + 8 + 8 + 2 * 40 + 16 + 8 + 8 + 8 + 8
+    assert nat.FieldDesc.tables.offset == 56 and nat.FieldDesc.out.offset == 160
+
+
+def test_fastmod_equals_modulo():
+    lib = nat.lib()
+    rng = random.Random(7)
+    divisors = [1, 2, 3, 7, 10, 255, 256, 999, 2999, 99999, 999999, 1000000, 2**31 - 1, 2**31, 2**32 - 2,
+                2**32 - 1, 2**32, 2**40 + 17, 2**63 - 25, 2**63, 2**64 - 1] + [rng.getrandbits(rng.randint(2, 64)) | 1 for _ in range(200)]
+    edge = [0, 1, 2, 2**32 - 1, 2**32, 2**63 - 1, 2**63, 2**64 - 2, 2**64 - 1]
+    for d in divisors:
+        for x in edge + [rng.getrandbits(64) for _ in range(200)] + [d - 1, d, d + 1 if d < 2**64 - 1 else d, (2**64 - 1) // d * d]:
+            x &= 2**64 - 1
+            assert lib.rf_debug_fastmod(x, d) == x % d, (x, d)
+
+
+def test_bad_arguments_fail_before_touching_the_gpu():
+    lib = nat.lib()
+    f = (nat.FieldDesc * 1)()
+    rc = lib.rf_bag_forward(f, 1, 4, None)          # no key source set
+    assert rc == nat.RF_ERR_INVALID and b"exactly one of" in lib.rf_last_error()
+    with pytest.raises(ValueError):
+        nat.check(rc)
+    assert lib.rf_bag_forward(f, 0, 4, None) == nat.RF_OK    # nothing to do
+    assert lib.rf_hash_strings(None, None, 0, 10, 0, 0, 0, 0, None, None) == nat.RF_OK
+
+
+def test_salt_rules():
+    assert nat.salt_to_key(None) == (0, 0, 0)
+    assert nat.salt_to_key(133) == (1, 133, 133)
+    assert nat.salt_to_key([2022, 2023]) == (1, 2022, 2023)
+    with pytest.raises(ValueError):
+        nat.salt_to_key([1, 2, 3])

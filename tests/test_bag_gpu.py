@@ -1,0 +1,213 @@
+"""Fused hash + gather + pool kernel (through the C-ABI and the reference-named layers) vs the
+CPU oracle.  Integer results (ids) and fp32 pooled outputs are compared BIT-EXACT: the kernel
+pools sequentially in index order, like the oracle (and divides `avg` with an IEEE fp32 divide).
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from recommendflow_b200 import _native as nat
+from recommendflow_b200.bag_ops import FieldCall, bag_forward
+from recommendflow_b200.backend.layers.preprocess_layers import DoubleHashingEmbedding, EmbeddingBag
+from recommendflow_b200.backend.utils.preprocess_utils import PreprocessLayers
+from tests.gpu_util import column, random_strings, tables, to_dev
+
+pytestmark = pytest.mark.gpu
+ALNUM = b"abcdefghijklmnopqrstuvwxyz0123456789_"
+
+
+def run_field(arena, offs, B, L, ws, num_bins, salts, combiner, mask_mode=nat.MASK_EMPTY_STRING, bag_offsets=None,
+              want_ids=False):
+    T, D = len(ws), ws[0].shape[1]
+    col = column(arena, offs, (B, L if bag_offsets is None else None), bag_offsets)
+    out = torch.full((B, T * D), float("nan"), dtype=torch.float32, device="cuda")
+    ids_out = torch.empty(T, len(offs) - 1, dtype=torch.int64, device="cuda") if want_ids else None
+    dev_w = to_dev(ws)
+    bag_forward([FieldCall([(dev_w[t], num_bins, salts[t]) for t in range(T)], D, combiner, keys=col,
+                           mask_mode=mask_mode, out=out, ids_out=ids_out, bag_len=None if bag_offsets is not None else L)], B)
+    torch.cuda.synchronize()
+    return out.cpu().numpy(), None if ids_out is None else ids_out.cpu().numpy()
+
+
+@pytest.mark.parametrize("combiner", ["sum", "avg", "min", "max"])
+@pytest.mark.parametrize("D,L,T", [(64, 4, 1), (64, 4, 2), (8, 1, 2), (16, 7, 2), (128, 50, 1), (256, 3, 2),
+                                   (512, 2, 1), (12, 5, 2), (6, 3, 1), (100, 9, 2), (48, 4, 1)])
+def test_dense_bags_bit_exact(combiner, D, L, T):
+    rng = np.random.default_rng(1000 + D + L)
+    B, N = 777, 5003
+    arena, offs = random_strings(rng, B * L, max_len=20, alphabet=ALNUM, empty_frac=0.3)
+    ws = tables(rng, T, N, D)
+    salts = [None, [2023, 2023]][:T] if D % 8 else [[2022, 2022], [2023, 2023]][:T]
+    want = oracle.hashed_bag_forward(arena, offs, B, L, ws, [N] * T, salts, combiner)
+    got, ids = run_field(arena, offs, B, L, ws, N, salts, combiner, want_ids=True)
+    for t in range(T):
+        assert np.array_equal(ids[t], oracle.hash_strings(arena, offs, N, "", salts[t]))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("combiner", ["sum", "avg", "max"])
+@pytest.mark.parametrize("D,T", [(128, 1), (64, 2), (20, 1)])
+def test_jagged_bags_bit_exact(combiner, D, T):
+    rng = np.random.default_rng(4242)
+    B, N = 600, 100003
+    lens = rng.integers(0, 201, size=B)           # includes empty bags
+    lens[5] = 0
+    bag = np.zeros(B + 1, dtype=np.int32)
+    bag[1:] = np.cumsum(lens)
+    n = int(bag[-1])
+    arena, offs = random_strings(rng, n, max_len=16, alphabet=ALNUM)
+    ws = tables(rng, T, N, D)
+    salts = [None, [5, 6]][:T]
+    want = oracle.hashed_bag_forward(arena, offs, B, 0, ws, [N] * T, salts, combiner, bag_offsets=bag)
+    got, _ = run_field(arena, offs, B, 0, ws, N, salts, combiner, bag_offsets=bag)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("D", [64, 256, 10])
+def test_bags_longer_than_a_round_carry_accumulators(D):
+    rng = np.random.default_rng(99)
+    lens = np.array([2500, 3, 1024, 1025, 0, 4096, 1], dtype=np.int64)
+    bag = np.zeros(len(lens) + 1, dtype=np.int32)
+    bag[1:] = np.cumsum(lens)
+    arena, offs = random_strings(rng, int(bag[-1]), max_len=12, alphabet=ALNUM)
+    ws = tables(rng, 2, 9973, D)
+    for combiner in ("sum", "avg", "min"):
+        want = oracle.hashed_bag_forward(arena, offs, len(lens), 0, ws, [9973] * 2, [[1, 2], None], combiner, bag_offsets=bag)
+        got, _ = run_field(arena, offs, len(lens), 0, ws, 9973, [[1, 2], None], combiner, bag_offsets=bag)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # dense, one very long bag per sample
+    B, L = 3, 1500
+    arena, offs = random_strings(rng, B * L, max_len=10, alphabet=ALNUM, empty_frac=0.2)
+    want = oracle.hashed_bag_forward(arena, offs, B, L, ws, [9973] * 2, [[1, 2], None], "avg")
+    got, _ = run_field(arena, offs, B, L, ws, 9973, [[1, 2], None], "avg")
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_double_hashing_layer_matches_reference_semantics():
+    # base_conf.yaml's one working hashed feature: app_id, N=3000, D=16, sum, seeds [2022, 2023]
+    rng = np.random.default_rng(11)
+    rows = [["com.app.%d" % rng.integers(0, 500) for _ in range(rng.integers(0, 4))] for _ in range(257)]
+    layer = DoubleHashingEmbedding(num_bins=3000, output_dim=16, seeds=[2022, 2023], mask_value="", mask_zero=True,
+                                   combiner="sum", name="hashing_app_id")
+    ws = tables(rng, 2, 3000, 16)
+    layer.set_weights(ws)
+    got = layer(rows)
+    L = max(len(r) for r in rows)
+    flat = [x for r in rows for x in (r + [""] * (L - len(r)))]
+    arena, offs = oracle.encode_strings(flat)
+    want = oracle.hashed_bag_forward(arena, offs, len(rows), L, ws, [3000, 3000], [2022, 2023], "sum")
+    assert got.shape == (257, 32)
+    assert np.array_equal(got.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    # pads are pooled in as row 0 (reference quirk): an all-pad sample equals L * W[0]
+    empty = [i for i, r in enumerate(rows) if not r][0]
+    acc = np.zeros(16, np.float32)
+    for _ in range(L):
+        acc = acc + ws[0][0]
+    assert np.array_equal(got[empty, :16].cpu().numpy(), acc)
+    for w_got, w_set in zip(layer.get_weights(), ws):
+        assert np.array_equal(w_got, w_set)
+
+
+def test_null_first_last_combiners():
+    rng = np.random.default_rng(12)
+    B, L, D, N = 9, 5, 8, 101
+    arena, offs = random_strings(rng, B * L, max_len=6, alphabet=ALNUM, empty_frac=0.2)
+    ws = tables(rng, 2, N, D)
+    ids = [oracle.hash_strings(arena, offs, N, "", s).reshape(B, L) for s in (2022, 2023)]
+    E = [w[i] for w, i in zip(ws, ids)]                                  # [B, L, D] each
+    col = column(arena, offs, (B, L))
+    for combiner, want in [("null", np.concatenate(E, axis=1)), ("first", np.concatenate([E[0][0], E[1][0]], axis=1)),
+                           ("last", np.concatenate([E[0][-1], E[1][-1]], axis=1))]:
+        layer = DoubleHashingEmbedding(N, D, [2022, 2023], combiner, mask_value="", name="h")
+        layer.set_weights(ws)
+        got = layer(col).cpu().numpy()
+        assert got.shape == want.shape and np.array_equal(got, want), combiner
+
+
+def test_embedding_bag_on_ids_and_int_keys():
+    rng = np.random.default_rng(13)
+    B, L, D, N = 300, 6, 32, 1000
+    (w,) = tables(rng, 1, N, D)
+    ids = rng.integers(0, N, size=(B, L), dtype=np.int64)
+    for combiner in ("sum", "avg", "min", "max"):
+        bag = EmbeddingBag(N, D, combiner=combiner, name="bag")
+        bag.set_weights([w])
+        got = bag(torch.from_numpy(ids).cuda()).cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), oracle.bag_pool(ids, w, combiner, L=L).view(np.uint32))
+    # integer feature through DoubleHashingEmbedding: values hashed as decimal strings, mask_value=0
+    vals = rng.integers(0, 50, size=(B, L), dtype=np.int64)
+    layer = DoubleHashingEmbedding(N, D, [2022, 2023], "sum", mask_value=0, name="hi")
+    ws = tables(rng, 2, N, D)
+    layer.set_weights(ws)
+    got = layer(torch.from_numpy(vals).cuda()).cpu().numpy()
+    want = np.concatenate([oracle.bag_pool(oracle.hash_ints(vals, N, 0, s), w_, "sum", L=L) for s, w_ in zip((2022, 2023), ws)], axis=1)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_fused_multi_field_launch_equals_per_layer_calls():
+    rng = np.random.default_rng(14)
+    B = 1500
+    specs = {"f_a": (50000, 64, 4, "sum"), "f_b": (3000, 16, 1, "avg"), "f_c": (100000, 8, 9, "max"),
+             "f_d": (777, 128, 2, "sum"), "f_e": (1000000, 64, 4, "min")}
+    layers, batch, want = PreprocessLayers(), {}, {}
+    for name, (N, D, L, comb) in specs.items():
+        layer = DoubleHashingEmbedding(N, D, [2022, 2023], comb, mask_value="", mask_zero=True, name=f"hashing_{name}")
+        ws = tables(rng, 2, N, D)
+        layer.set_weights(ws)
+        arena, offs = random_strings(rng, B * L, max_len=14, alphabet=ALNUM, empty_frac=0.25)
+        layers[name] = layer
+        batch[name] = column(arena, offs, (B, L))
+        want[name] = oracle.hashed_bag_forward(arena, offs, B, L, ws, [N, N], [2022, 2023], comb)
+    before = nat.launch_count()
+    res = layers.forward_all(batch)
+    assert nat.launch_count() == before + 1                      # ONE launch for all five fields
+    layout, total = layers.output_layout()
+    assert res["__fused__"].shape == (B, total)
+    for name in specs:
+        assert np.array_equal(res[name].cpu().numpy().view(np.uint32), want[name].view(np.uint32)), name
+        single = layers[name](batch[name])
+        assert torch.equal(single, res[name])
+
+
+def test_many_fields_exceeding_the_smem_prefix_table():
+    rng = np.random.default_rng(15)
+    B, F = 64, 600
+    calls, wants, outs = [], [], []
+    ws = tables(rng, 1, 997, 8)
+    dev_w = to_dev(ws)
+    for f in range(F):
+        arena, offs = random_strings(rng, B, max_len=8, alphabet=ALNUM)
+        out = torch.empty(B, 8, device="cuda")
+        calls.append(FieldCall([(dev_w[0], 997, [f, f + 1])], 8, "sum", keys=column(arena, offs, (B, 1)),
+                               mask_mode=nat.MASK_EMPTY_STRING, out=out, bag_len=1))
+        wants.append(oracle.hashed_bag_forward(arena, offs, B, 1, ws, [997], [[f, f + 1]], "sum"))
+        outs.append(out)
+    bag_forward(calls, B)
+    for out, want in zip(outs, wants):
+        assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_large_batch_linearity_property():
+    # size-independent property at C2's full batch: pooling with sum is additive in the tables,
+    # sum(W1 + W2)[ids] == sum(W1)[ids] + sum(W2)[ids] when W2 = 0, and ids are in range.
+    rng = np.random.default_rng(16)
+    B, L, N, D = 65536, 4, 1000000, 64
+    v = rng.integers(0, 10**7, size=B * L)
+    digits = np.char.mod("f07_%d", v)
+    arena, offs = oracle.encode_strings(digits.tolist())
+    col = column(arena, offs, (B, L))
+    w = torch.empty(N, D, device="cuda").uniform_(-0.05, 0.05)
+    out = torch.empty(B, D, device="cuda")
+    ids_out = torch.empty(1, B * L, dtype=torch.int64, device="cuda")
+    bag_forward([FieldCall([(w, N, None)], D, "sum", keys=col, mask_mode=nat.MASK_EMPTY_STRING, out=out, ids_out=ids_out,
+                           bag_len=L)], B)
+    ids = ids_out.view(B, L)
+    assert int(ids.min()) >= 1 and int(ids.max()) <= N - 1
+    ref = w[ids[:, 0]]
+    for l in range(1, L):
+        ref = ref + w[ids[:, l]]                                   # same left-to-right order
+    assert torch.equal(out, ref)
+    sample = rng.integers(0, B * L, size=4096)
+    want = oracle.hash_strings(arena, offs, N, "", None)[sample]
+    assert np.array_equal(ids_out.view(-1).cpu().numpy()[sample], want)
