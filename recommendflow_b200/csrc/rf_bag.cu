@@ -20,6 +20,7 @@
 //            fp32 results are bit-identical to the oracle's.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -74,32 +75,54 @@ struct DevField {
 };
 
 // ------------------------------------------------------------------------------------------
-// pooling primitives
+// pooling primitives.  Two code shapes only: ADD (sum / avg) and SELECT (min / max, picked by a
+// launch-uniform flag) -- fewer template instances keeps the fused kernel small.
 // ------------------------------------------------------------------------------------------
-template <int OP>
-__device__ __forceinline__ float pool_init() {
-    return OP == RF_COMBINER_MIN ? __int_as_float(0x7f800000) : OP == RF_COMBINER_MAX ? __int_as_float(0xff800000) : 0.0f;
-}
-template <int OP>
-__device__ __forceinline__ float pool_op(float acc, float x) {
-    if (OP == RF_COMBINER_MIN) return x < acc ? x : acc;
-    if (OP == RF_COMBINER_MAX) return x > acc ? x : acc;
-    return acc + x;
-}
-template <int OP>
-__device__ __forceinline__ void pool_op4(float4 &a, const float4 &x) {
-    a.x = pool_op<OP>(a.x, x.x);
-    a.y = pool_op<OP>(a.y, x.y);
-    a.z = pool_op<OP>(a.z, x.z);
-    a.w = pool_op<OP>(a.w, x.w);
-}
+constexpr int kAdd = 0, kSelect = 1;
+
+struct PoolOp {
+    int combiner;
+    __device__ __forceinline__ bool is_max() const { return combiner == RF_COMBINER_MAX; }
+    __device__ __forceinline__ bool is_avg() const { return combiner == RF_COMBINER_AVG; }
+    template <int K>
+    __device__ __forceinline__ float init() const {
+        if (K == kAdd) return 0.0f;
+        return is_max() ? __int_as_float(0xff800000) : __int_as_float(0x7f800000);
+    }
+    template <int K>
+    __device__ __forceinline__ float apply(float acc, float x) const {
+        if (K == kAdd) return acc + x;
+        const bool take = is_max() ? (x > acc) : (x < acc);     // same select as the oracle
+        return take ? x : acc;
+    }
+    template <int K>
+    __device__ __forceinline__ void apply4(float4 &a, const float4 &x) const {
+        a.x = apply<K>(a.x, x.x);
+        a.y = apply<K>(a.y, x.y);
+        a.z = apply<K>(a.z, x.z);
+        a.w = apply<K>(a.w, x.w);
+    }
+    template <int K>
+    __device__ __forceinline__ float finish(float acc, int64_t count) const {
+        if (count == 0) return 0.0f;
+        if (K == kAdd && is_avg()) return acc / (float)count;    // IEEE fp32 divide, like sum / L
+        return acc;
+    }
+    template <int K>
+    __device__ __forceinline__ void finish4(float4 &a, int64_t count) const {
+        a.x = finish<K>(a.x, count);
+        a.y = finish<K>(a.y, count);
+        a.z = finish<K>(a.z, count);
+        a.w = finish<K>(a.w, count);
+    }
+};
 
 __device__ __forceinline__ float4 ldg_row(const float4 *p) { return __ldg(p); }
 
-// Accumulate `cnt` rows (ids in shared memory) into acc[], in index order.
-template <int NV, int OP>
-__device__ __forceinline__ void accumulate_vec(float4 (&acc)[NV], const float4 *__restrict__ W, uint32_t row_vecs,
-                                               uint32_t lg, uint32_t G, const uint32_t *sid, int cnt) {
+// Accumulate `cnt` rows (ids in shared memory) into acc[], in index order, U rows in flight.
+template <int NV, int K>
+__device__ __forceinline__ void accumulate_vec(const PoolOp &op, float4 (&acc)[NV], const float4 *__restrict__ W,
+                                               uint32_t row_vecs, uint32_t lg, uint32_t G, const uint32_t *sid, int cnt) {
     constexpr int U = NV == 1 ? 8 : (NV == 2 ? 4 : 2);
     int i = 0;
     for (; i + U <= cnt; i += U) {
@@ -116,28 +139,14 @@ __device__ __forceinline__ void accumulate_vec(float4 (&acc)[NV], const float4 *
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
-            for (int v = 0; v < NV; ++v) pool_op4<OP>(acc[v], r[u][v]);
-    }
-    if (U > 4 && i + 4 <= cnt) {
-        float4 r[4][NV];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const float4 *row = W + (size_t)sid[i + u] * row_vecs;
-#pragma unroll
-            for (int v = 0; v < NV; ++v) r[u][v] = ldg_row(row + lg + v * G);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int v = 0; v < NV; ++v) pool_op4<OP>(acc[v], r[u][v]);
-        i += 4;
+            for (int v = 0; v < NV; ++v) op.apply4<K>(acc[v], r[u][v]);
     }
     for (; i < cnt; ++i) {
         const float4 *row = W + (size_t)sid[i] * row_vecs;
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             const uint32_t c = lg + v * G;
-            if (NV == 1 || c < row_vecs) pool_op4<OP>(acc[v], ldg_row(row + c));
+            if (NV == 1 || c < row_vecs) op.apply4<K>(acc[v], ldg_row(row + c));
         }
     }
 }
@@ -160,8 +169,11 @@ struct Smem {
     int32_t boff[kMaxTileBags + 4];
     int32_t tile_begin[kMaxFieldsSmem + 1];
     DevField field;   // this tile's descriptor, copied once per tile
+    // partial pools of a bag longer than one round (only lane groups 0..T-1 are active then):
+    // vec path float4[(t*32 + lane)*4 + v]; scalar path float[(t*32 + lane)*16 + slab]
+    float4 carry[RF_MAX_TABLES_PER_FIELD * 32 * 4];
 };
-static_assert(sizeof(DevField) % 4 == 0, "DevField is copied word-wise");
+static_assert(kMaxDim / 32 == 16 && sizeof(DevField) % 4 == 0, "DevField is copied word-wise");
 
 template <class Src>
 __device__ __forceinline__ uint32_t bucket_of(const Src &src, uint32_t len, const DevTable &t, bool is_mask) {
@@ -171,9 +183,9 @@ __device__ __forceinline__ uint32_t bucket_of(const Src &src, uint32_t len, cons
     return id;
 }
 
-template <int NV, int OP>
-__device__ __forceinline__ void pool_round_vec(const DevField &F, const Smem &sm, const Round &R, int tile_bag0,
-                                               int64_t tile_item0, float4 *carry) {
+template <int NV, int K>
+__device__ __forceinline__ void pool_round_vec(const PoolOp &op, const DevField &F, Smem &sm, const Round &R,
+                                               int tile_bag0) {
     const uint32_t row_vecs = (uint32_t)F.dim >> 2;
     uint32_t G = 1;
     while (G < row_vecs && G < 32) G <<= 1;
@@ -200,50 +212,93 @@ __device__ __forceinline__ void pool_round_vec(const DevField &F, const Smem &sm
             cnt = R.n_keys;
         }
         float4 acc[NV];
+        float4 *carry = sm.carry + (t * 32 + lg) * 4;
         if (R.partial && !R.first_part) {
 #pragma unroll
             for (int v = 0; v < NV; ++v) acc[v] = carry[v];
         } else {
+            const float z = op.init<K>();
 #pragma unroll
-            for (int v = 0; v < NV; ++v) acc[v] = make_float4(pool_init<OP>(), pool_init<OP>(), pool_init<OP>(), pool_init<OP>());
+            for (int v = 0; v < NV; ++v) acc[v] = make_float4(z, z, z, z);
         }
         if (lg < row_vecs)
-            accumulate_vec<NV, OP>(acc, reinterpret_cast<const float4 *>(F.t[t].w), row_vecs, lg, G,
-                                   sm.ids + t * kChunk + rel, cnt);
+            accumulate_vec<NV, K>(op, acc, reinterpret_cast<const float4 *>(F.t[t].w), row_vecs, lg, G,
+                                  sm.ids + t * kChunk + rel, cnt);
         if (R.partial && !R.last_part) {
 #pragma unroll
             for (int v = 0; v < NV; ++v) carry[v] = acc[v];
             continue;
         }
-        const int64_t total = hi - lo;
-        if (total == 0) {
-#pragma unroll
-            for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else if (OP == RF_COMBINER_AVG) {
-            const float c = (float)total;
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                acc[v].x = acc[v].x / c;
-                acc[v].y = acc[v].y / c;
-                acc[v].z = acc[v].z / c;
-                acc[v].w = acc[v].w / c;
-            }
-        }
         float4 *o = reinterpret_cast<float4 *>(F.out + (int64_t)(tile_bag0 + bl) * F.out_stride + (int64_t)t * F.dim);
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             const uint32_t c = lg + v * G;
+            op.finish4<K>(acc[v], hi - lo);
             if (c < row_vecs) o[c] = acc[v];
         }
     }
-    (void)tile_item0;
+}
+
+// Dense bags of exactly L keys (L in {1,2,3,4}), D <= 128: a lane group fetches NB bags together,
+// keeping NB * L (6..8) independent 128-bit row loads in flight per lane instead of L, because
+// this phase is bound by DRAM latency x dependent rounds.  Same in-order pooling per bag.
+// With T == 2 the table index of a lane group never changes (its work items keep their parity).
+template <int K, int NB, int L>
+__device__ __forceinline__ void pool_round_short(const PoolOp &op, const DevField &F, const Smem &sm, const Round &R,
+                                                 int tile_bag0) {
+    const uint32_t row_vecs = (uint32_t)F.dim >> 2;
+    uint32_t G = 1;
+    while (G < row_vecs) G <<= 1;
+    const uint32_t lg = threadIdx.x & (G - 1);
+    if (lg >= row_vecs) return;
+    const int grp = threadIdx.x / G;
+    const int n_grp = kThreads / G;                       // even: the parity of w is the parity of grp
+    const int T = F.n_tables;
+    const int n_work = (R.bag1 - R.bag0) * T;
+    const int t = T == 2 ? (grp & 1) : 0;
+    const int wshift = T == 2 ? 1 : 0;
+    const float4 *__restrict__ W = reinterpret_cast<const float4 *>(F.t[t].w) + lg;
+    const uint32_t *sid_base = sm.ids + t * kChunk;
+    float *out_base = F.out + (int64_t)(tile_bag0 + R.bag0) * F.out_stride + (int64_t)t * F.dim + lg * 4;
+    const int64_t ostride = F.out_stride;
+    int w = grp;
+    for (; w + (NB - 1) * n_grp < n_work; w += NB * n_grp) {
+        float4 r[NB][L];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const uint32_t *sid = sid_base + ((w + b * n_grp) >> wshift) * L;
+#pragma unroll
+            for (int u = 0; u < L; ++u) r[b][u] = ldg_row(W + (size_t)sid[u] * row_vecs);
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const float z = op.init<K>();
+            float4 acc = make_float4(z, z, z, z);
+#pragma unroll
+            for (int u = 0; u < L; ++u) op.apply4<K>(acc, r[b][u]);
+            op.finish4<K>(acc, L);
+            *reinterpret_cast<float4 *>(out_base + (int64_t)((w + b * n_grp) >> wshift) * ostride) = acc;
+        }
+    }
+    for (; w < n_work; w += n_grp) {
+        const uint32_t *sid = sid_base + (w >> wshift) * L;
+        float4 r[L];
+#pragma unroll
+        for (int u = 0; u < L; ++u) r[u] = ldg_row(W + (size_t)sid[u] * row_vecs);
+        const float z = op.init<K>();
+        float4 acc = make_float4(z, z, z, z);
+#pragma unroll
+        for (int u = 0; u < L; ++u) op.apply4<K>(acc, r[u]);
+        op.finish4<K>(acc, L);
+        *reinterpret_cast<float4 *>(out_base + (int64_t)(w >> wshift) * ostride) = acc;
+    }
 }
 
 // Generic-D path (dim % 4 != 0 or unaligned): one warp per (bag, table), one float per lane per
 // 32-column slab, same in-order accumulation.  Long bags carry kMaxDim/32 partial slabs.
-template <int OP>
-__device__ __forceinline__ void pool_round_scalar(const DevField &F, const Smem &sm, const Round &R, int tile_bag0,
-                                                  float (&carry)[kMaxDim / 32]) {
+template <int K>
+__device__ __forceinline__ void pool_round_scalar(const PoolOp &op, const DevField &F, Smem &sm, const Round &R,
+                                                  int tile_bag0) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warp = kThreads / 32;
     const int T = F.n_tables;
     const bool dense = F.boffs == nullptr;
@@ -268,43 +323,43 @@ __device__ __forceinline__ void pool_round_scalar(const DevField &F, const Smem 
         const float *W = F.t[t].w;
         const uint32_t *sid = sm.ids + t * kChunk + rel;
         float *o = F.out + (int64_t)(tile_bag0 + bl) * F.out_stride + (int64_t)t * D;
-        const int64_t total = hi - lo;
-#pragma unroll
-        for (int s = 0; s < kMaxDim / 32; ++s) {
+        float *carry = reinterpret_cast<float *>(sm.carry) + (t * 32 + lane) * (kMaxDim / 32);
+        for (int s = 0; s * 32 < D; ++s) {
             const int d = s * 32 + (int)lane;
-            if (s * 32 >= D) break;
-            float acc = (R.partial && !R.first_part) ? carry[s] : pool_init<OP>();
+            float acc = (R.partial && !R.first_part) ? carry[s] : op.init<K>();
             if (d < D)
-                for (int i = 0; i < cnt; ++i) acc = pool_op<OP>(acc, __ldg(W + (size_t)sid[i] * D + d));
+                for (int i = 0; i < cnt; ++i) acc = op.apply<K>(acc, __ldg(W + (size_t)sid[i] * D + d));
             if (R.partial && !R.last_part) {
                 carry[s] = acc;
                 continue;
             }
-            if (total == 0) acc = 0.f;
-            else if (OP == RF_COMBINER_AVG) acc = acc / (float)total;
-            if (d < D) o[d] = acc;
+            if (d < D) o[d] = op.finish<K>(acc, hi - lo);
         }
     }
 }
 
-template <int OP>
-__device__ __forceinline__ void pool_round(const DevField &F, const Smem &sm, const Round &R, int tile_bag0,
-                                           int64_t tile_item0, float4 (&cv)[4], float (&cs)[kMaxDim / 32]) {
+template <int K>
+__device__ __forceinline__ void pool_round(const PoolOp &op, const DevField &F, Smem &sm, const Round &R, int tile_bag0) {
     if (F.vec_ok) {
         const int row_vecs = F.dim >> 2;
-        if (row_vecs <= 32) {
-            pool_round_vec<1, OP>(F, sm, R, tile_bag0, tile_item0, cv);
+        if (row_vecs <= 32 && !R.partial && F.boffs == nullptr && F.bag_len >= 1 && F.bag_len <= 4) {
+            if (F.bag_len == 1) pool_round_short<K, 8, 1>(op, F, sm, R, tile_bag0);
+            else if (F.bag_len == 2) pool_round_short<K, 4, 2>(op, F, sm, R, tile_bag0);
+            else if (F.bag_len == 3) pool_round_short<K, 2, 3>(op, F, sm, R, tile_bag0);
+            else pool_round_short<K, 2, 4>(op, F, sm, R, tile_bag0);
+        } else if (row_vecs <= 32) {
+            pool_round_vec<1, K>(op, F, sm, R, tile_bag0);
         } else if (row_vecs <= 64) {
-            pool_round_vec<2, OP>(F, sm, R, tile_bag0, tile_item0, cv);
+            pool_round_vec<2, K>(op, F, sm, R, tile_bag0);
         } else {
-            pool_round_vec<4, OP>(F, sm, R, tile_bag0, tile_item0, cv);
+            pool_round_vec<4, K>(op, F, sm, R, tile_bag0);
         }
     } else {
-        pool_round_scalar<OP>(F, sm, R, tile_bag0, cs);
+        pool_round_scalar<K>(op, F, sm, R, tile_bag0);
     }
 }
 
-__global__ void __launch_bounds__(kThreads) bag_forward_kernel(const DevField *__restrict__ fields, int n_fields, int total_tiles) {
+__device__ __forceinline__ void bag_forward_body(const DevField *__restrict__ fields, int n_fields, int total_tiles) {
     __shared__ Smem sm;
     const int tid = threadIdx.x;
 
@@ -342,9 +397,6 @@ __global__ void __launch_bounds__(kThreads) bag_forward_kernel(const DevField *_
         const DevField &F = sm.field;
         const int T = F.n_tables;
         const int64_t tile_item0 = dense ? (int64_t)tile_bag0 * F.bag_len : (int64_t)sm.boff[0];
-
-        float4 carry_v[4];
-        float carry_s[kMaxDim / 32];
 
         int bag = 0;            // next bag of the tile, relative
         int64_t part_done = 0;  // keys of a long bag already consumed
@@ -440,12 +492,9 @@ __global__ void __launch_bounds__(kThreads) bag_forward_kernel(const DevField *_
 
             // ---- phase C: gather + pool -----------------------------------------------------
             if (F.dim > 0) {
-                switch (F.combiner) {
-                    case RF_COMBINER_SUM: pool_round<RF_COMBINER_SUM>(F, sm, R, tile_bag0, tile_item0, carry_v, carry_s); break;
-                    case RF_COMBINER_AVG: pool_round<RF_COMBINER_AVG>(F, sm, R, tile_bag0, tile_item0, carry_v, carry_s); break;
-                    case RF_COMBINER_MIN: pool_round<RF_COMBINER_MIN>(F, sm, R, tile_bag0, tile_item0, carry_v, carry_s); break;
-                    default: pool_round<RF_COMBINER_MAX>(F, sm, R, tile_bag0, tile_item0, carry_v, carry_s); break;
-                }
+                const PoolOp op{F.combiner};
+                if (F.combiner <= RF_COMBINER_AVG) pool_round<kAdd>(op, F, sm, R, tile_bag0);
+                else pool_round<kSelect>(op, F, sm, R, tile_bag0);
             }
             __syncthreads();
 
@@ -460,6 +509,12 @@ __global__ void __launch_bounds__(kThreads) bag_forward_kernel(const DevField *_
             }
         }
     }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) bag_forward_kernel(const DevField *__restrict__ fields, int n_fields,
+                                                                     int total_tiles) {
+    bag_forward_body(fields, n_fields, total_tiles);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -535,8 +590,17 @@ static int launch_fields(std::vector<DevField> &dev_fields, cudaStream_t stream)
     if (!slot.done) RF_CUDA(cudaEventCreateWithFlags(&slot.done, cudaEventDisableTiming));
     memcpy(slot.host, dev_fields.data(), bytes);
     RF_CUDA(cudaMemcpyAsync(slot.dev, slot.host, bytes, cudaMemcpyHostToDevice, stream));
-    bag_forward_kernel<<<(unsigned)tiles, kThreads, 0, stream>>>(static_cast<const DevField *>(slot.dev),
-                                                               (int)dev_fields.size(), (int)tiles);
+    // CTAs per SM the kernel is compiled for (register cap): 3 measured best on B200 for C2
+    // (0.385 ms vs 0.437 @2, 0.410 @4, 0.520 @5); RF_BAG_MINB overrides for experiments.
+    static const int cfg = getenv("RF_BAG_MINB") ? atoi(getenv("RF_BAG_MINB")) : 3;
+    const DevField *dptr = static_cast<const DevField *>(slot.dev);
+    const int nf = (int)dev_fields.size();
+    switch (cfg) {
+        case 4: bag_forward_kernel<4><<<(unsigned)tiles, kThreads, 0, stream>>>(dptr, nf, (int)tiles); break;
+        case 5: bag_forward_kernel<5><<<(unsigned)tiles, kThreads, 0, stream>>>(dptr, nf, (int)tiles); break;
+        case 2: bag_forward_kernel<2><<<(unsigned)tiles, kThreads, 0, stream>>>(dptr, nf, (int)tiles); break;
+        default: bag_forward_kernel<3><<<(unsigned)tiles, kThreads, 0, stream>>>(dptr, nf, (int)tiles); break;
+    }
     RF_CUDA(cudaGetLastError());
     g_launches.fetch_add(1);
     RF_CUDA(cudaEventRecord(slot.done, stream));
