@@ -116,7 +116,7 @@ class ClockSampler(object):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.001)
 
     def __enter__(self):
         if self.nv is not None:
@@ -364,6 +364,12 @@ def run_ours(args):
                 "frac": achieved / peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                 "frac_of_nominal_8TBs": achieved / 8000.0, "algorithmic_bytes_per_sample": bps,
                 "algorithmic_bytes_per_launch": bps * B, "kernel_ms": kern_ms, "traffic": None}
+    try:      # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", f"traffic_{name}.json")))
+        roofline["traffic"] = tr["traffic_bytes_per_launch"]
+        roofline["traffic_source"] = tr["source"]
+    except Exception:
+        pass
 
     # ---- CPU baseline beside it (rank 0, N == 1 only) ------------------------------------------
     cpu, parity = None, None
