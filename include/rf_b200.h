@@ -59,6 +59,9 @@ typedef struct rf_table_desc {
 } rf_table_desc;
 
 #define RF_MAX_TABLES_PER_FIELD 2
+/* rf_field_desc.flags: this launch produces PARTIAL pools (row-sharded tables): an empty bag    */
+/* yields the combiner's identity (+/-inf for min/max) instead of 0.                             */
+#define RF_FIELD_PARTIAL 1
 
 /* One feature field of one batch: replaces `DoubleHashingEmbedding.call`
  * (preprocess_layers.py:94-97; n_tables == 2) or `EmbeddingBag.call` (:66-68; pre-hashed
@@ -80,7 +83,7 @@ typedef struct rf_field_desc {
     int32_t dim;                 /* embedding dim D; 0 = hash only (needs ids_out)             */
     int32_t combiner;            /* rf_combiner                                                 */
     int32_t mask_mode;           /* rf_mask_mode                                                */
-    int32_t reserved;
+    int32_t flags;               /* RF_FIELD_* bits                                             */
     int64_t int_mask_value;      /* RF_MASK_INT_VALUE only                                      */
     /* --- outputs ----------------------------------------------------------------------------- */
     float *out;                  /* device; bag b, table t -> out[b*out_stride + t*dim .. +dim] */
@@ -105,6 +108,22 @@ int rf_hash_int64(const int64_t *d_values, int64_t n_items, int64_t num_bins, in
 /* (models/matching/que2search.py:68,76-79) over the layers built by get_preprocess_layers     */
 /* (backend/utils/preprocess_utils.py:7-20).                                                   */
 int rf_bag_forward(const rf_field_desc *fields, int n_fields, int64_t batch, void *stream);
+
+/* ---- row-sharded tables (new design; the reference only replicates tables,   */
+/* backend/utils/gpu_utils.py:13-14).  Row id lives on rank id % world as local row id / world. */
+/* rf_shard_route partitions the hashed ids of one field by owner, keeping bag order: for every */
+/* owner g it writes a CSR offsets[batch+1] through h_offsets_dst[g] (may be NULL) and the      */
+/* owner-local rows through h_rows_dst[g] (int64, capacity >= this rank's key count).  The      */
+/* h_* arrays are HOST arrays of `world` DEVICE pointers -- peer-mapped NVLink pointers in the  */
+/* fused path, local send buffers in the NCCL path.  d_counts_ws: int32[world*batch] scratch;   */
+/* d_offsets_local: int32[world*(batch+1)] receives the same CSR locally.                       */
+int rf_shard_route(const int64_t *d_ids, const int32_t *d_bag_offsets, int32_t bag_len, int64_t batch,
+                   int world, int32_t *d_counts_ws, int32_t *d_offsets_local,
+                   int32_t *const *h_offsets_dst, int64_t *const *h_rows_dst, void *stream);
+/* out[b] = reduce_{g<world, in rank order} partials[g][b][:]; avg divides by the bag's key count */
+int rf_combine_partials(const float *d_partials, int world, int64_t batch, int32_t dim, int combiner,
+                        int32_t bag_len, const int32_t *d_bag_offsets, float *d_out, int64_t out_stride,
+                        void *stream);
 
 /* Number of kernels launched by this library since load (bench.py's gpu_launches counter).   */
 int64_t rf_launch_count(void);

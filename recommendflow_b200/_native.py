@@ -12,6 +12,7 @@ RF_OK, RF_ERR_INVALID, RF_ERR_CUDA, RF_ERR_UNSUPPORTED = 0, -1, -2, -3
 COMBINER = {"sum": 0, "avg": 1, "min": 2, "max": 3}
 MASK_NONE, MASK_EMPTY_STRING, MASK_INT_VALUE = 0, 1, 2
 MAX_TABLES = 2
+FIELD_PARTIAL = 1
 
 
 class TableDesc(C.Structure):
@@ -23,7 +24,7 @@ class FieldDesc(C.Structure):
     _fields_ = [("bytes", C.c_void_p), ("str_offsets", C.c_void_p), ("int_values", C.c_void_p),
                 ("ids", C.c_void_p), ("bag_offsets", C.c_void_p), ("n_items", C.c_int64),
                 ("bag_len", C.c_int32), ("n_tables", C.c_int32), ("tables", TableDesc * MAX_TABLES),
-                ("dim", C.c_int32), ("combiner", C.c_int32), ("mask_mode", C.c_int32), ("reserved", C.c_int32),
+                ("dim", C.c_int32), ("combiner", C.c_int32), ("mask_mode", C.c_int32), ("flags", C.c_int32),
                 ("int_mask_value", C.c_int64), ("out", C.c_void_p), ("out_stride", C.c_int64),
                 ("ids_out", C.c_void_p)]
 
@@ -53,7 +54,11 @@ def lib():
         L.rf_hash_int64.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_int,
                                     C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
         L.rf_bag_forward.argtypes = [C.POINTER(FieldDesc), C.c_int, C.c_int64, C.c_void_p]
-        for name in ("rf_hash_strings", "rf_hash_int64", "rf_bag_forward"):
+        L.rf_shard_route.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
+        L.rf_combine_partials.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int, C.c_int32, C.c_void_p,
+                                          C.c_void_p, C.c_int64, C.c_void_p]
+        for name in ("rf_hash_strings", "rf_hash_int64", "rf_bag_forward", "rf_shard_route", "rf_combine_partials"):
             getattr(L, name).restype = C.c_int
         _lib = L
     return _lib

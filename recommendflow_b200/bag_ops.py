@@ -23,12 +23,13 @@ class FieldCall(object):
     """
 
     def __init__(self, tables, dim, combiner="sum", keys=None, ids=None, mask_mode=nat.MASK_NONE,
-                 int_mask_value=0, out=None, ids_out=None, bag_len=None, bag_offsets=None, n_items=None):
+                 int_mask_value=0, out=None, ids_out=None, bag_len=None, bag_offsets=None, n_items=None, flags=0):
         self.tables, self.dim, self.combiner = tables, dim, combiner
         self.keys, self.ids = keys, ids
         self.mask_mode, self.int_mask_value = mask_mode, int_mask_value
         self.out, self.ids_out = out, ids_out
         self.bag_len, self.bag_offsets, self.n_items = bag_len, bag_offsets, n_items
+        self.flags = flags
 
 
 def _require_cuda(t, what):
@@ -69,7 +70,9 @@ def _fill(desc, call, batch):
             raise ValueError("ids must be a contiguous int64 tensor [n_tables, n_items]")
         desc.ids = ids.data_ptr()
         keep.append(ids)
-        n_items = ids.numel() // len(call.tables)
+        # n_items may be an estimate when the true count only exists on the device (sharded path):
+        # with one table it only steers tile sizing
+        n_items = call.n_items if call.n_items is not None else ids.numel() // len(call.tables)
         bag_len = call.bag_len
     else:
         raise ValueError("a field needs keys or ids")
@@ -102,6 +105,7 @@ def _fill(desc, call, batch):
     desc.dim = call.dim
     desc.combiner = nat.COMBINER[call.combiner]
     desc.mask_mode = call.mask_mode
+    desc.flags = call.flags
     desc.int_mask_value = int(call.int_mask_value)
     if call.dim > 0:
         out = _require_cuda(call.out, "output")

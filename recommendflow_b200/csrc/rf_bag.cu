@@ -70,7 +70,7 @@ struct DevField {
     int32_t bags_per_tile;
     int32_t tile_begin;
     int32_t vec_ok;      // 128-bit path usable (dim % 4 == 0, aligned pointers/strides)
-    int32_t pad_;
+    int32_t flags;
     DevTable t[RF_MAX_TABLES_PER_FIELD];
 };
 
@@ -82,6 +82,7 @@ constexpr int kAdd = 0, kSelect = 1;
 
 struct PoolOp {
     int combiner;
+    int partial;   // RF_FIELD_PARTIAL: an empty bag yields the combiner's identity, not 0
     __device__ __forceinline__ bool is_max() const { return combiner == RF_COMBINER_MAX; }
     __device__ __forceinline__ bool is_avg() const { return combiner == RF_COMBINER_AVG; }
     template <int K>
@@ -104,7 +105,7 @@ struct PoolOp {
     }
     template <int K>
     __device__ __forceinline__ float finish(float acc, int64_t count) const {
-        if (count == 0) return 0.0f;
+        if (count == 0) return (K == kSelect && partial) ? acc : 0.0f;
         if (K == kAdd && is_avg()) return acc / (float)count;    // IEEE fp32 divide, like sum / L
         return acc;
     }
@@ -492,7 +493,7 @@ __device__ __forceinline__ void bag_forward_body(const DevField *__restrict__ fi
 
             // ---- phase C: gather + pool -----------------------------------------------------
             if (F.dim > 0) {
-                const PoolOp op{F.combiner};
+                const PoolOp op{F.combiner, F.flags & RF_FIELD_PARTIAL};
                 if (F.combiner <= RF_COMBINER_AVG) pool_round<kAdd>(op, F, sm, R, tile_bag0);
                 else pool_round<kSelect>(op, F, sm, R, tile_bag0);
             }
@@ -520,7 +521,7 @@ __global__ void __launch_bounds__(kThreads, MINB) bag_forward_kernel(const DevFi
 // ------------------------------------------------------------------------------------------
 // host side: descriptor ring + launch
 // ------------------------------------------------------------------------------------------
-static std::atomic<int64_t> g_launches{0};
+std::atomic<int64_t> g_launches{0};
 
 struct DescSlot {
     void *host = nullptr;
@@ -657,6 +658,7 @@ static int build_field(DevField &d, const rf_field_desc &f, int64_t batch, int f
     d.n_tables = f.n_tables;
     d.combiner = f.combiner;
     d.mask_mode = f.mask_mode;
+    d.flags = f.flags;
     bool aligned = (f.dim % 4 == 0) && (reinterpret_cast<uintptr_t>(f.out) % 16 == 0) && (f.out_stride % 4 == 0);
     for (int t = 0; t < f.n_tables; ++t) {
         int rc = fill_table(d.t[t], f.tables[t], f.mask_mode, f.dim > 0, fi, t);

@@ -1,0 +1,267 @@
+// rf_shard.cu -- routing and combining kernels for ROW-SHARDED embedding tables.
+//
+// The reference replicates every table on every GPU (tf.distribute.MirroredStrategy,
+// /root/reference/backend/utils/gpu_utils.py:13-14); row sharding is the new design that
+// north_star asks for once a table no longer belongs on one GPU.  Row `id` of a table lives on
+// rank `id % world` as local row `id / world`.  Per step and per rank:
+//
+//   1. hash the local keys (rf_hash_strings)                                    -> ids[n]
+//   2. rf_shard_route: count / scan / scatter the ids by owner, keeping bag order ->
+//        for every owner g: CSR offsets[batch+1] + local rows[], written THROUGH THE POINTERS
+//        THE CALLER GIVES -- peer-mapped NVLink pointers in the fused path, local send buffers
+//        in the NCCL path.
+//   3. on the owner: rf_bag_forward over the received (rows, offsets) with `out` pointing at the
+//        source rank's partial buffer (peer pointer => the pooled vector crosses NVLink as the
+//        kernel produces it; no separate all-to-all).
+//   4. rf_combine_partials on the source: reduce the `world` partial vectors in rank order.
+//
+// Everything here is integer routing and streaming adds: HBM / NVLink bound, no tensor cores.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "../../include/rf_b200.h"
+#include "rf_common.h"
+
+namespace rf {
+
+constexpr int kMaxWorld = 16;
+extern std::atomic<int64_t> g_launches;
+
+struct PtrTable {
+    void *p[kMaxWorld];
+};
+
+__device__ __forceinline__ void bag_range(const int32_t *boffs, int bag_len, int64_t b, int64_t &lo, int64_t &hi) {
+    if (boffs) {
+        lo = boffs[b];
+        hi = boffs[b + 1];
+    } else {
+        lo = b * bag_len;
+        hi = lo + bag_len;
+    }
+}
+
+// counts[g * batch + b] = #keys of bag b owned by rank g.  One warp per bag.
+__global__ void __launch_bounds__(256) shard_count_kernel(const int64_t *__restrict__ ids, const int32_t *__restrict__ boffs,
+                                                          int bag_len, int64_t batch, int world, int32_t *__restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = warp0; b < batch; b += n_warps) {
+        int64_t lo, hi;
+        bag_range(boffs, bag_len, b, lo, hi);
+        int mine = 0;   // lane g accumulates the count for owner g
+        for (int64_t i = lo; i < hi; i += 32) {
+            const bool on = i + lane < hi;
+            const int owner = on ? (int)((uint64_t)ids[i + lane] % (uint32_t)world) : -1;
+            for (int g = 0; g < world; ++g) {
+                const unsigned m = __ballot_sync(0xffffffffu, owner == g);
+                if (lane == g) mine += __popc(m);
+            }
+        }
+        if (lane < world) counts[(int64_t)lane * batch + b] = mine;
+    }
+}
+
+// One CTA per owner g: exclusive scan of counts[g][0..batch) -> offsets (batch + 1 entries), written
+// to the local copy and through dst.p[g] (the owner's receive buffer for this source).
+__global__ void __launch_bounds__(1024) shard_scan_kernel(const int32_t *__restrict__ counts, int64_t batch,
+                                                          int32_t *__restrict__ offs_local, PtrTable dst) {
+    __shared__ int32_t warp_sums[32];
+    __shared__ int32_t carry_s;
+    const int g = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int32_t *c = counts + (int64_t)g * batch;
+    int32_t *ol = offs_local + (int64_t)g * (batch + 1);
+    int32_t *od = static_cast<int32_t *>(dst.p[g]);
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < batch; base += 1024) {
+        const int64_t i = base + tid;
+        const int32_t v = i < batch ? c[i] : 0;
+        int32_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int32_t y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) warp_sums[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int32_t s = warp_sums[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int32_t y = __shfl_up_sync(0xffffffffu, s, d);
+                if (lane >= d) s += y;
+            }
+            warp_sums[lane] = s;
+        }
+        __syncthreads();
+        const int32_t carry = carry_s;
+        const int32_t excl = carry + (wid ? warp_sums[wid - 1] : 0) + x - v;
+        if (i < batch) {
+            ol[i] = excl;
+            if (od) od[i] = excl;
+        }
+        __syncthreads();
+        if (tid == 1023) carry_s = carry + warp_sums[31];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        ol[batch] = carry_s;
+        if (od) od[batch] = carry_s;
+    }
+}
+
+// One warp per bag: key k of bag b owned by g goes to rows_dst[g][offs[g][b] + (rank of k among the
+// bag's keys owned by g)] as the owner-local row id / world.  Order inside (owner, bag) is kept.
+__global__ void __launch_bounds__(256) shard_scatter_kernel(const int64_t *__restrict__ ids, const int32_t *__restrict__ boffs,
+                                                            int bag_len, int64_t batch, int world,
+                                                            const int32_t *__restrict__ offs_local, PtrTable rows_dst) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int64_t b = warp0; b < batch; b += n_warps) {
+        int64_t lo, hi;
+        bag_range(boffs, bag_len, b, lo, hi);
+        // lane g tracks the next free slot of owner g for this bag
+        int next = lane < world ? offs_local[(int64_t)lane * (batch + 1) + b] : 0;
+        for (int64_t i = lo; i < hi; i += 32) {
+            const bool on = i + lane < hi;
+            const uint64_t id = on ? (uint64_t)ids[i + lane] : 0;
+            const int owner = on ? (int)(id % (uint32_t)world) : -1;
+            int pos = 0;
+            for (int g = 0; g < world; ++g) {
+                const unsigned m = __ballot_sync(0xffffffffu, owner == g);
+                const int base = __shfl_sync(0xffffffffu, next, g);
+                if (owner == g) pos = base + __popc(m & lt);
+                if (lane == g) next += __popc(m);
+            }
+            if (on) static_cast<int64_t *>(rows_dst.p[owner])[pos] = (int64_t)(id / (uint32_t)world);
+        }
+    }
+}
+
+// out[b] = reduce over g = 0..world-1 (in that order) of partials[g][b]; avg divides by the bag's
+// key count.  One float4 (or float) per thread.
+template <bool VEC>
+__global__ void __launch_bounds__(256) combine_partials_kernel(const float *__restrict__ partials, int world, int64_t batch,
+                                                               int dim, int combiner, int bag_len,
+                                                               const int32_t *__restrict__ boffs, float *__restrict__ out,
+                                                               int64_t out_stride) {
+    const int per_row = VEC ? dim >> 2 : dim;
+    const int64_t total = batch * per_row;
+    const int64_t plane = batch * (int64_t)dim;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = e / per_row;
+        const int c = (int)(e - b * per_row);
+        const int64_t cnt = boffs ? (int64_t)(boffs[b + 1] - boffs[b]) : (int64_t)bag_len;
+        if (VEC) {
+            const float4 *p = reinterpret_cast<const float4 *>(partials + b * dim) + c;
+            float4 acc = __ldg(p);
+            for (int g = 1; g < world; ++g) {
+                const float4 x = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p) + g * plane));
+                if (combiner <= RF_COMBINER_AVG) {
+                    acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+                } else if (combiner == RF_COMBINER_MIN) {
+                    acc.x = x.x < acc.x ? x.x : acc.x; acc.y = x.y < acc.y ? x.y : acc.y;
+                    acc.z = x.z < acc.z ? x.z : acc.z; acc.w = x.w < acc.w ? x.w : acc.w;
+                } else {
+                    acc.x = x.x > acc.x ? x.x : acc.x; acc.y = x.y > acc.y ? x.y : acc.y;
+                    acc.z = x.z > acc.z ? x.z : acc.z; acc.w = x.w > acc.w ? x.w : acc.w;
+                }
+            }
+            if (cnt == 0) acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            else if (combiner == RF_COMBINER_AVG) {
+                const float d = (float)cnt;
+                acc.x = acc.x / d; acc.y = acc.y / d; acc.z = acc.z / d; acc.w = acc.w / d;
+            }
+            reinterpret_cast<float4 *>(out + b * out_stride)[c] = acc;
+        } else {
+            const float *p = partials + b * dim + c;
+            float acc = __ldg(p);
+            for (int g = 1; g < world; ++g) {
+                const float x = __ldg(p + g * plane);
+                if (combiner <= RF_COMBINER_AVG) acc += x;
+                else if (combiner == RF_COMBINER_MIN) acc = x < acc ? x : acc;
+                else acc = x > acc ? x : acc;
+            }
+            if (cnt == 0) acc = 0.f;
+            else if (combiner == RF_COMBINER_AVG) acc = acc / (float)cnt;
+            out[b * out_stride + c] = acc;
+        }
+    }
+}
+
+static int grid_for(int64_t work_items, int per_block, int dev_sms) {
+    int64_t blocks = (work_items + per_block - 1) / per_block;
+    const int64_t cap = (int64_t)dev_sms * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace rf
+
+using namespace rf;
+
+extern "C" {
+
+int rf_shard_route(const int64_t *d_ids, const int32_t *d_bag_offsets, int32_t bag_len, int64_t batch, int world,
+                   int32_t *d_counts_ws, int32_t *d_offsets_local, int32_t *const *h_offsets_dst,
+                   int64_t *const *h_rows_dst, void *stream) {
+    if (world < 1 || world > kMaxWorld) return set_error(RF_ERR_INVALID, "world must be in [1, %d]", kMaxWorld);
+    if (batch < 0 || batch > INT32_MAX) return set_error(RF_ERR_INVALID, "batch out of range");
+    if (batch == 0) return RF_OK;
+    if (!d_ids || !d_counts_ws || !d_offsets_local || !h_rows_dst)
+        return set_error(RF_ERR_INVALID, "rf_shard_route: NULL buffer");
+    if (!d_bag_offsets && bag_len < 0) return set_error(RF_ERR_INVALID, "negative bag_len");
+    int dev = 0, sms = 0;
+    RF_CUDA(cudaGetDevice(&dev));
+    RF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PtrTable offs{}, rows{};
+    for (int g = 0; g < world; ++g) {
+        offs.p[g] = h_offsets_dst ? h_offsets_dst[g] : nullptr;
+        rows.p[g] = h_rows_dst[g];
+        if (!rows.p[g]) return set_error(RF_ERR_INVALID, "rf_shard_route: rows_dst[%d] is NULL", g);
+    }
+    const int grid = grid_for(batch, 8, sms);   // 8 warps (bags) per 256-thread block
+    shard_count_kernel<<<grid, 256, 0, st>>>(d_ids, d_bag_offsets, bag_len, batch, world, d_counts_ws);
+    shard_scan_kernel<<<world, 1024, 0, st>>>(d_counts_ws, batch, d_offsets_local, offs);
+    shard_scatter_kernel<<<grid, 256, 0, st>>>(d_ids, d_bag_offsets, bag_len, batch, world, d_offsets_local, rows);
+    RF_CUDA(cudaGetLastError());
+    g_launches.fetch_add(3);
+    return RF_OK;
+}
+
+int rf_combine_partials(const float *d_partials, int world, int64_t batch, int32_t dim, int combiner, int32_t bag_len,
+                        const int32_t *d_bag_offsets, float *d_out, int64_t out_stride, void *stream) {
+    if (world < 1 || world > kMaxWorld) return set_error(RF_ERR_INVALID, "world must be in [1, %d]", kMaxWorld);
+    if (batch < 0 || dim <= 0) return set_error(RF_ERR_INVALID, "bad batch / dim");
+    if (combiner < RF_COMBINER_SUM || combiner > RF_COMBINER_MAX) return set_error(RF_ERR_INVALID, "bad combiner");
+    if (batch == 0) return RF_OK;
+    if (!d_partials || !d_out) return set_error(RF_ERR_INVALID, "rf_combine_partials: NULL buffer");
+    int dev = 0, sms = 0;
+    RF_CUDA(cudaGetDevice(&dev));
+    RF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool vec = dim % 4 == 0 && out_stride % 4 == 0 && reinterpret_cast<uintptr_t>(d_partials) % 16 == 0 &&
+                     reinterpret_cast<uintptr_t>(d_out) % 16 == 0;
+    const int64_t work = batch * (vec ? dim / 4 : dim);
+    const int grid = grid_for(work, 256, sms);
+    if (vec)
+        combine_partials_kernel<true><<<grid, 256, 0, st>>>(d_partials, world, batch, dim, combiner, bag_len, d_bag_offsets,
+                                                           d_out, out_stride);
+    else
+        combine_partials_kernel<false><<<grid, 256, 0, st>>>(d_partials, world, batch, dim, combiner, bag_len,
+                                                            d_bag_offsets, d_out, out_stride);
+    RF_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return RF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,182 @@
+"""Row-sharded embedding bag: one hashed feature whose table is split across the GPUs of a box.
+
+New design asked for by north_star (the reference only replicates tables under
+tf.distribute.MirroredStrategy, /root/reference/backend/utils/gpu_utils.py:13-14).  Row `id`
+of the [num_bins, D] table lives on rank `id % world` as local row `id // world`; the batch stays
+data-parallel (every rank brings its own bags).  One forward step per rank:
+
+    hash local keys -> route ids to their owners (count / scan / scatter, bag order kept)
+      -> owners pool the rows they hold per (source, bag)  -> partial vectors go back
+      -> source combines the `world` partials in rank order (avg divides by the bag's key count)
+
+Two transports:
+  * "p2p"  (product path): receive buffers live in symmetric memory; the routing kernel writes
+    ids/offsets straight into the owner's buffers and the owner's fused gather+pool kernel writes
+    each pooled vector straight into the SOURCE rank's buffer through NVLink peer pointers, so the
+    "all-to-all" of partials happens inside the compute kernel, tile by tile; only two stream-
+    ordered barriers remain.  No host synchronisation anywhere in the step.
+  * "nccl" (baseline): the same kernels on local buffers + torch.distributed all_to_all.
+Numerics: partial pools are accumulated in key order per owner and combined in rank order, so the
+result differs from the single-GPU sequential sum by fp32 rounding only (tests state the bound).
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _native as nat
+from .bag_ops import FieldCall, bag_forward, hash_ints, hash_strings
+from .strings import StringColumn
+
+
+class CudaShardOps(object):
+    """The compute steps of the sharded forward, on the CUDA kernels of librf_b200.so."""
+
+    def hash(self, keys, num_bins, mask_value, salt):
+        if isinstance(keys, StringColumn):
+            return hash_strings(keys, num_bins, mask_value, salt).reshape(-1)
+        return hash_ints(keys, num_bins, mask_value, salt).reshape(-1)
+
+    def route(self, ids, bag_offsets, bag_len, batch, world, counts_ws, offs_local, offs_dst_ptrs, rows_dst_ptrs):
+        arr_o = (C.c_void_p * world)(*offs_dst_ptrs) if offs_dst_ptrs is not None else None
+        arr_r = (C.c_void_p * world)(*rows_dst_ptrs)
+        with torch.cuda.device(ids.device):
+            nat.check(nat.lib().rf_shard_route(ids.data_ptr(), None if bag_offsets is None else bag_offsets.data_ptr(),
+                                               bag_len or 0, batch, world, counts_ws.data_ptr(), offs_local.data_ptr(),
+                                               arr_o, arr_r, C.c_void_p(torch.cuda.current_stream(ids.device).cuda_stream)))
+
+    def pool(self, shard, rows_per_src, offs_per_src, outs_per_src, batch, combiner, est_items):
+        calls = [FieldCall([(shard, shard.shape[0], None)], shard.shape[1], combiner, ids=rows.view(1, -1),
+                           bag_offsets=offs, out=out, flags=nat.FIELD_PARTIAL, n_items=est_items)
+                 for rows, offs, out in zip(rows_per_src, offs_per_src, outs_per_src)]
+        bag_forward(calls, batch)
+
+    def combine(self, partials, world, batch, dim, combiner, bag_len, bag_offsets, out):
+        with torch.cuda.device(out.device):
+            nat.check(nat.lib().rf_combine_partials(partials.data_ptr(), world, batch, dim, nat.COMBINER[combiner], bag_len or 0,
+                                                    None if bag_offsets is None else bag_offsets.data_ptr(), out.data_ptr(),
+                                                    out.stride(0), C.c_void_p(torch.cuda.current_stream(out.device).cuda_stream)))
+
+
+def shard_rows(num_bins, rank, world):
+    """Number of table rows rank `rank` holds (ids rank, rank + world, ...)."""
+    return (num_bins - rank + world - 1) // world if num_bins > rank else 0
+
+
+class ShardedEmbeddingBag(torch.nn.Module):
+    def __init__(self, num_bins, output_dim, combiner="sum", salt=None, mask_value="", group=None, transport="p2p",
+                 max_batch=8192, max_keys=None, device=None, name="sharded_bag", ops=None):
+        super().__init__()
+        if num_bins is None or num_bins <= 0:
+            raise ValueError("`num_bins` cannot be `None` or non-positive values.")
+        if combiner not in ("sum", "avg", "min", "max"):
+            raise ValueError(f"Do not support combiner = '{combiner}', supported: [sum, min, max, avg]")
+        if transport not in ("p2p", "nccl"):
+            raise ValueError("transport must be 'p2p' or 'nccl'")
+        self._name = name
+        self.num_bins, self.output_dim, self.combiner = int(num_bins), int(output_dim), combiner
+        self.salt, self.mask_value = salt, mask_value
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        if self.world > 16:
+            raise NotImplementedError("at most 16 ranks (one NVSwitch box)")
+        self.transport = transport
+        self.max_batch = int(max_batch)
+        self.max_keys = int(max_keys if max_keys is not None else max_batch * 200)
+        self.ops = ops if ops is not None else CudaShardOps()
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        rows = shard_rows(self.num_bins, self.rank, self.world)
+        self.shard = torch.nn.Parameter(torch.empty(max(rows, 1), self.output_dim, dtype=torch.float32,
+                                                    device=self.device).uniform_(-0.05, 0.05), requires_grad=False)
+        self._bufs = None
+
+    @property
+    def name(self):
+        return self._name
+
+    # ---- weights ---------------------------------------------------------------------------------
+    def set_full_weights(self, full):
+        """Load this rank's rows (rank::world) of a full [num_bins, D] table."""
+        full = torch.as_tensor(full, dtype=torch.float32)
+        if tuple(full.shape) != (self.num_bins, self.output_dim):
+            raise ValueError(f"expected a [{self.num_bins}, {self.output_dim}] table, got {tuple(full.shape)}")
+        mine = full[self.rank::self.world].contiguous()
+        if mine.shape[0] == 0:
+            mine = torch.zeros(1, self.output_dim)
+        self.shard = torch.nn.Parameter(mine.to(self.device), requires_grad=False)
+
+    # ---- buffers ---------------------------------------------------------------------------------
+    def _alloc(self):
+        W, B, K, D = self.world, self.max_batch, self.max_keys, self.output_dim
+        dev = self.device
+        b = {"counts": torch.empty(W * B, dtype=torch.int32, device=dev),
+             "offs_local": torch.empty(W * (B + 1), dtype=torch.int32, device=dev)}
+        if self.transport == "p2p":
+            import torch.distributed._symmetric_memory as symm
+            rows_bytes, offs_bytes, part_bytes = W * K * 8, W * (B + 1) * 4, W * B * D * 4
+            offs_bytes = (offs_bytes + 15) // 16 * 16
+            total = rows_bytes + offs_bytes + part_bytes
+            raw = symm.empty(total, dtype=torch.uint8, device=dev)
+            hdl = symm.rendezvous(raw, self.group)
+            b.update(raw=raw, hdl=hdl, rows_off=0, offs_off=rows_bytes, part_off=rows_bytes + offs_bytes)
+            b["rows_recv"] = raw[:rows_bytes].view(torch.int64).view(W, K)
+            b["offs_recv"] = raw[rows_bytes:rows_bytes + W * (B + 1) * 4].view(torch.int32).view(W, B + 1)
+            b["partials"] = raw[rows_bytes + offs_bytes:].view(torch.float32).view(W, B, D)
+            b["peer_partials"] = [hdl.get_buffer(r, (W, B, D), torch.float32, (rows_bytes + offs_bytes) // 4)
+                                  for r in range(W)]
+            b["peer_ptr"] = [int(p) for p in hdl.buffer_ptrs]
+        else:
+            b["rows_send"] = torch.empty(W, K, dtype=torch.int64, device=dev)
+            b["rows_recv"] = torch.empty(W, K, dtype=torch.int64, device=dev)
+            b["offs_send"] = torch.empty(W, B + 1, dtype=torch.int32, device=dev)
+            b["offs_recv"] = torch.empty(W, B + 1, dtype=torch.int32, device=dev)
+            b["part_send"] = torch.empty(W, B, D, dtype=torch.float32, device=dev)
+            b["partials"] = torch.empty(W, B, D, dtype=torch.float32, device=dev)
+        self._bufs = b
+        return b
+
+    # ---- forward ---------------------------------------------------------------------------------
+    def forward(self, keys, out=None):
+        """keys: StringColumn (dense [B, L] or jagged) or int64 [B, L] tensor, on this rank's device.
+        Every rank must call with the same batch size.  Returns [B, D] fp32."""
+        b = self._bufs or self._alloc()
+        W, D, me = self.world, self.output_dim, self.rank
+        if isinstance(keys, StringColumn):
+            B, L, bag_offsets, n_keys = keys.shape[0], keys.shape[1], keys.bag_offsets, keys.n_items
+        else:
+            B, L, bag_offsets, n_keys = keys.shape[0], keys.shape[1], None, keys.numel()
+        if B != self.max_batch:
+            raise ValueError(f"batch {B} != max_batch {self.max_batch} the exchange buffers were sized for")
+        if n_keys > self.max_keys:
+            raise ValueError(f"{n_keys} keys exceed max_keys={self.max_keys}")
+        if out is None:
+            out = torch.empty(B, D, dtype=torch.float32, device=self.device)
+        ids = self.ops.hash(keys, self.num_bins, self.mask_value, self.salt)
+        partial_op = "sum" if self.combiner == "avg" else self.combiner
+        est = max(1, n_keys // W)
+
+        if self.transport == "p2p":
+            K, hdl = self.max_keys, b["hdl"]
+            rows_dst = [b["peer_ptr"][g] + b["rows_off"] + me * K * 8 for g in range(W)]
+            offs_dst = [b["peer_ptr"][g] + b["offs_off"] + me * (B + 1) * 4 for g in range(W)]
+            self.ops.route(ids, bag_offsets, L, B, W, b["counts"], b["offs_local"], offs_dst, rows_dst)
+            hdl.barrier(channel=0)                       # every source's ids/offsets have landed here
+            self.ops.pool(self.shard.data, [b["rows_recv"][s] for s in range(W)], [b["offs_recv"][s] for s in range(W)],
+                          [b["peer_partials"][s][me] for s in range(W)], B, partial_op, est)
+            hdl.barrier(channel=1)                       # every owner's partials have landed here
+        else:
+            rows_dst = [b["rows_send"][g].data_ptr() for g in range(W)]
+            offs_dst = [b["offs_send"][g].data_ptr() for g in range(W)]
+            self.ops.route(ids, bag_offsets, L, B, W, b["counts"], b["offs_local"], offs_dst, rows_dst)
+            dist.all_to_all_single(b["offs_recv"], b["offs_send"], group=self.group)
+            send_tot = b["offs_send"][:, B].tolist()     # host sync: NCCL needs the split sizes
+            recv_tot = b["offs_recv"][:, B].tolist()
+            send_flat = torch.cat([b["rows_send"][g, :send_tot[g]] for g in range(W)])
+            recv_flat = torch.empty(sum(recv_tot), dtype=torch.int64, device=self.device)
+            dist.all_to_all_single(recv_flat, send_flat, recv_tot, send_tot, group=self.group)
+            rows_in = list(torch.split(recv_flat, recv_tot))
+            self.ops.pool(self.shard.data, rows_in, [b["offs_recv"][s] for s in range(W)],
+                          [b["part_send"][s] for s in range(W)], B, partial_op, est)
+            dist.all_to_all_single(b["partials"], b["part_send"], group=self.group)
+        self.ops.combine(b["partials"], W, B, D, self.combiner, L, bag_offsets, out)
+        return out

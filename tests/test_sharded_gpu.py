@@ -1,0 +1,81 @@
+"""Row-sharded forward on >= 2 real GPUs (NCCL + NVLink peer memory), both transports, vs the
+numpy restatement of the sharded algorithm (bit-exact) and vs the sequential oracle (tolerance).
+Skipped on a single-GPU box; run with `gpurun --gpus 2 -- python -m pytest tests/test_sharded_gpu.py -m gpu`."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from tests.shard_util import rank_batch, sharded_reference
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from recommendflow_b200.sharded import ShardedEmbeddingBag
+        from recommendflow_b200.strings import StringColumn
+        N, D, B = 100003, 128, 512
+        full = np.random.default_rng(1).uniform(-0.05, 0.05, size=(N, D)).astype(np.float32)
+        arena, offs, bag = rank_batch(rank, B, 200)
+        col = StringColumn.from_arena(arena, offs, (B, None), bag).to(f"cuda:{rank}")
+        ids = oracle.hash_strings(arena, offs, N, "", None)
+        out = {}
+        for combiner in ("avg", "sum", "max"):
+            want = sharded_reference(ids, bag, full, world, combiner)
+            seq = oracle.bag_pool(ids, full, combiner, bag_offsets=bag)
+            for transport in ("p2p", "nccl"):
+                layer = ShardedEmbeddingBag(N, D, combiner=combiner, salt=None, mask_value="", transport=transport,
+                                            max_batch=B, max_keys=B * 200)
+                layer.set_full_weights(full)
+                for _ in range(3):                       # repeated steps reuse the exchange buffers
+                    got = layer(col)
+                torch.cuda.synchronize()
+                got = got.cpu().numpy()
+                out[(combiner, transport)] = (bool(np.array_equal(got, want)), float(np.abs(got - seq).max()))
+        # dense [B, L] padded input (reference semantics: pads pool row 0 of owner 0)
+        L = 6
+        a2, o2 = oracle.encode_strings([f"k{rank}_{i % 37}" if i % 5 else "" for i in range(B * L)])
+        col2 = StringColumn.from_arena(a2, o2, (B, L)).to(f"cuda:{rank}")
+        layer = ShardedEmbeddingBag(N, D, combiner="avg", salt=[2022, 2022], mask_value="", max_batch=B, max_keys=B * L)
+        layer.set_full_weights(full)
+        got = layer(col2).cpu().numpy()
+        ids2 = oracle.hash_strings(a2, o2, N, "", [2022, 2022])
+        want2 = sharded_reference(ids2, np.arange(B + 1) * L, full, world, "avg")
+        out[("dense", "p2p")] = (bool(np.array_equal(got, want2)), 0.0)
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_sharded_forward_multi_gpu(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, out in res:
+        for key, (exact, err) in out.items():
+            assert exact, f"rank {rank} {key}: differs from the sharded restatement"
+            assert err <= 200 * 0.05 * 2.0 ** -21, (rank, key, err)     # fp32 re-association of <= 200 adds

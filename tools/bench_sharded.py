@@ -1,0 +1,125 @@
+#!/usr/bin/env python
+"""C4: jagged behaviour sequences (1..max_len keys), mean pooling, one
+rows x dim fp32 table row-sharded (id % world) across the GPUs of one box.
+
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/bench_sharded.py [...]
+    python tools/bench_sharded.py            # N = 1: the unsharded fused kernel on the whole table
+
+Prints one JSON line (rank 0): samples/s over all ranks (max-over-ranks device time), the
+achieved HBM GB/s per GPU, and both transports when --transport both.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def jagged_keys(rank, B, max_len, batch_index=0):
+    from recommendflow_b200.synth import decimal_keys
+    rng = np.random.default_rng(4242 + rank + 1000 * batch_index)
+    lens = rng.integers(1, max_len + 1, size=B)
+    bag = np.zeros(B + 1, dtype=np.int32)
+    bag[1:] = np.cumsum(lens)
+    v = rng.integers(0, 10**9, size=int(bag[-1]))
+    arena, offs = decimal_keys(b"item_", v)
+    return arena, offs, bag
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows", type=int, default=100_000_000)
+    ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--max-len", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--transport", default="both", choices=["p2p", "nccl", "both"])
+    ap.add_argument("--pipeline", type=int, default=1, help="streams used to overlap consecutive steps")
+    args = ap.parse_args()
+
+    import torch
+    import torch.distributed as dist
+    from recommendflow_b200 import _native as nat
+    from recommendflow_b200.bag_ops import FieldCall, bag_forward
+    from recommendflow_b200.sharded import ShardedEmbeddingBag
+    from recommendflow_b200.strings import StringColumn
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, N, D, K, W = args.batch, args.rows, args.dim, args.steps, max(args.warmup, 3)
+    NB = 4
+    batches = []
+    for bi in range(NB):
+        arena, offs, bag = jagged_keys(rank, B, args.max_len, bi)
+        batches.append(StringColumn.from_arena(arena, offs, (B, None), bag).to(dev))
+    max_keys = max(c.n_items for c in batches)
+    mean_len = float(np.mean([c.n_items for c in batches])) / B
+    key_bytes = float(np.mean([c.nbytes for c in batches])) / B
+    # algorithmic bytes per sample (bag): rows + key bytes + offsets + output
+    bps = mean_len * 4 * D + key_bytes + mean_len * 4 + 4 * D
+
+    def timed(step_fn):
+        for i in range(W):
+            step_fn(i)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            step_fn(W + i)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / K
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    results = {}
+    if world == 1:
+        table = torch.empty(N, D, dtype=torch.float32, device=dev).uniform_(-0.05, 0.05)
+        out = torch.empty(B, D, dtype=torch.float32, device=dev)
+        calls = [[FieldCall([(table, N, None)], D, "avg", keys=c, mask_mode=nat.MASK_EMPTY_STRING, out=out)] for c in batches]
+        ms = timed(lambda i: bag_forward(calls[i % NB], B))
+        results["single_gpu_fused"] = ms
+    else:
+        transports = ["p2p", "nccl"] if args.transport == "both" else [args.transport]
+        outs = {}
+        for tr in transports:
+            layer = ShardedEmbeddingBag(N, D, combiner="avg", salt=None, mask_value="", transport=tr, max_batch=B,
+                                        max_keys=max_keys)
+            out = torch.empty(B, D, dtype=torch.float32, device=dev)
+            ms = timed(lambda i: layer(batches[i % NB], out=out))
+            results[tr] = ms
+            outs[tr] = layer(batches[0]).clone()
+            del layer
+        if len(outs) == 2:
+            results["p2p_equals_nccl"] = bool(torch.equal(outs["p2p"], outs["nccl"]))
+    if rank == 0:
+        best = min(v for k, v in results.items() if isinstance(v, float))
+        line = {"metric": "lookup+pool samples/sec", "workload": f"c4: jagged 1..{args.max_len} keys/bag (mean {mean_len:.1f}), avg pooling, "
+                          f"{N}-row x {D}-dim fp32 table row-sharded id % {world}, batch {B}/GPU",
+                "n_gpus": world, "value": world * B / (best / 1e3), "unit": "samples/s", "ms_per_step": results,
+                "steps": K, "warmup": W, "algorithmic_bytes_per_sample": bps,
+                "hbm_gbs_per_gpu": bps * B / (best / 1e3) / 1e9, "gpu_launches": nat.launch_count()}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
