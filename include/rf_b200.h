@@ -120,6 +120,13 @@ int rf_bag_forward(const rf_field_desc *fields, int n_fields, int64_t batch, voi
 int rf_shard_route(const int64_t *d_ids, const int32_t *d_bag_offsets, int32_t bag_len, int64_t batch,
                    int world, int32_t *d_counts_ws, int32_t *d_offsets_local,
                    int32_t *const *h_offsets_dst, int64_t *const *h_rows_dst, void *stream);
+/* Same, fused with the hashing of string keys (no separate pass over the batch): d_ids_ws       */
+/* (int64[n_keys]) receives the bucket ids.                                                      */
+int rf_shard_route_keys(const uint8_t *d_bytes, const int32_t *d_str_offsets, int64_t num_bins, int mask_mode,
+                        int use_strong, uint64_t key0, uint64_t key1, int64_t *d_ids_ws,
+                        const int32_t *d_bag_offsets, int32_t bag_len, int64_t batch, int world,
+                        int32_t *d_counts_ws, int32_t *d_offsets_local, int32_t *const *h_offsets_dst,
+                        int64_t *const *h_rows_dst, void *stream);
 /* out[b] = reduce_{g<world, in rank order} partials[g][b][:]; avg divides by the bag's key count */
 int rf_combine_partials(const float *d_partials, int world, int64_t batch, int32_t dim, int combiner,
                         int32_t bag_len, const int32_t *d_bag_offsets, float *d_out, int64_t out_stride,

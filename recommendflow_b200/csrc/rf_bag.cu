@@ -36,18 +36,16 @@
 namespace rf {
 
 constexpr int kThreads = 256;
-constexpr int kChunk = 1024;              // keys hashed per round
-constexpr int kStageBytes = 16 * 1024;    // key bytes staged per round
+constexpr int kChunk = 2048;              // keys (bucket ids) held per round
+constexpr int kSub = 1024;                // keys hashed per sub-chunk of a round (offsets + staged bytes)
+constexpr int kStageBytes = 16 * 1024;    // key bytes staged per sub-chunk
 constexpr int kMaxTileBags = 1024;        // bags per tile (jagged: CSR slice kept in smem)
 constexpr int kMaxFieldsSmem = 512;       // tile-prefix table kept in smem up to this many fields
 constexpr int kMaxDim = 512;
 
 struct DevTable {
     const float *w;
-    uint64_t k0, k1;
-    FastMod mod;
-    uint32_t use_strong;
-    uint32_t masking;   // bucket 0 reserved for the mask value
+    HashSpec h;
 };
 
 struct DevField {
@@ -120,34 +118,32 @@ struct PoolOp {
 
 __device__ __forceinline__ float4 ldg_row(const float4 *p) { return __ldg(p); }
 
-// Accumulate `cnt` rows (ids in shared memory) into acc[], in index order, U rows in flight.
+// Accumulate `cnt` rows (ids in shared memory) into acc[], in index order.  Every trip issues up
+// to U independent 128-bit row loads before the first add, also on the last (partial) trip: a
+// bag's time is ceil(cnt / U) DRAM latencies, never one latency per leftover key.
 template <int NV, int K>
 __device__ __forceinline__ void accumulate_vec(const PoolOp &op, float4 (&acc)[NV], const float4 *__restrict__ W,
                                                uint32_t row_vecs, uint32_t lg, uint32_t G, const uint32_t *sid, int cnt) {
     constexpr int U = NV == 1 ? 8 : (NV == 2 ? 4 : 2);
-    int i = 0;
-    for (; i + U <= cnt; i += U) {
+    for (int i = 0; i < cnt; i += U) {
         float4 r[U][NV];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const float4 *row = W + (size_t)sid[i + u] * row_vecs;
+            // past the end: re-read the trip's first row (an L1 hit) so that every load is
+            // unconditional and independent; only the pooling below is predicated
+            const float4 *row = W + (size_t)sid[i + u < cnt ? i + u : i] * row_vecs;
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
                 const uint32_t c = lg + v * G;
-                r[u][v] = (NV == 1 || c < row_vecs) ? ldg_row(row + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                r[u][v] = ldg_row(row + ((NV == 1 || c < row_vecs) ? c : lg));
             }
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u)
+        for (int u = 0; u < U; ++u) {
+            if (i + u < cnt) {
 #pragma unroll
-            for (int v = 0; v < NV; ++v) op.apply4<K>(acc[v], r[u][v]);
-    }
-    for (; i < cnt; ++i) {
-        const float4 *row = W + (size_t)sid[i] * row_vecs;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            const uint32_t c = lg + v * G;
-            if (NV == 1 || c < row_vecs) op.apply4<K>(acc[v], ldg_row(row + c));
+                for (int v = 0; v < NV; ++v) op.apply4<K>(acc[v], r[u][v]);
+            }
         }
     }
 }
@@ -165,7 +161,7 @@ struct Round {
 // ------------------------------------------------------------------------------------------
 struct Smem {
     uint32_t ids[RF_MAX_TABLES_PER_FIELD * kChunk];
-    int32_t soff[kChunk + 4];
+    int32_t soff[kSub + 4];
     uint32_t stage[kStageBytes / 4 + 8];
     int32_t boff[kMaxTileBags + 4];
     int32_t tile_begin[kMaxFieldsSmem + 1];
@@ -173,16 +169,10 @@ struct Smem {
     // partial pools of a bag longer than one round (only lane groups 0..T-1 are active then):
     // vec path float4[(t*32 + lane)*4 + v]; scalar path float[(t*32 + lane)*16 + slab]
     float4 carry[RF_MAX_TABLES_PER_FIELD * 32 * 4];
+    int next_work;    // phase C: lane groups pull (bag, table) work items from here (jagged balance)
 };
+static_assert(sizeof(Smem) <= 48 * 1024, "static shared memory limit");
 static_assert(kMaxDim / 32 == 16 && sizeof(DevField) % 4 == 0, "DevField is copied word-wise");
-
-template <class Src>
-__device__ __forceinline__ uint32_t bucket_of(const Src &src, uint32_t len, const DevTable &t, bool is_mask) {
-    const uint64_t h = t.use_strong ? siphash24(src, len, t.k0, t.k1) : fingerprint64(src, len);
-    uint32_t id = (uint32_t)fastmod(h, t.mod);
-    if (t.masking) id = is_mask ? 0u : id + 1u;
-    return id;
-}
 
 template <int NV, int K>
 __device__ __forceinline__ void pool_round_vec(const PoolOp &op, const DevField &F, Smem &sm, const Round &R,
@@ -196,7 +186,15 @@ __device__ __forceinline__ void pool_round_vec(const PoolOp &op, const DevField 
     const int T = F.n_tables;
     const bool dense = F.boffs == nullptr;
     const int n_work = (R.bag1 - R.bag0) * T;
-    for (int w = grp; w < n_work; w += n_grp) {
+    // bags differ in length, so lane groups pull work items instead of striding over them
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31u) & ~(G - 1)));
+    (void)grp;
+    (void)n_grp;
+    for (;;) {
+        int w = 0;
+        if (lg == 0) w = atomicAdd(&sm.next_work, 1);
+        w = __shfl_sync(gmask, w, 0, G);
+        if (w >= n_work) break;
         const int bl = R.bag0 + (T == 2 ? (w >> 1) : w);
         const int t = T == 2 ? (w & 1) : 0;
         int64_t lo, hi;   // field-flat key range of the bag
@@ -340,7 +338,7 @@ __device__ __forceinline__ void pool_round_scalar(const PoolOp &op, const DevFie
 }
 
 template <int K>
-__device__ __forceinline__ void pool_round(const PoolOp &op, const DevField &F, Smem &sm, const Round &R, int tile_bag0) {
+__device__ __noinline__ void pool_round(const PoolOp &op, const DevField &F, Smem &sm, const Round &R, int tile_bag0) {
     if (F.vec_ok) {
         const int row_vecs = F.dim >> 2;
         if (row_vecs <= 32 && !R.partial && F.boffs == nullptr && F.bag_len >= 1 && F.bag_len <= 4) {
@@ -361,7 +359,7 @@ __device__ __forceinline__ void pool_round(const PoolOp &op, const DevField &F, 
 }
 
 __device__ __forceinline__ void bag_forward_body(const DevField *__restrict__ fields, int n_fields, int total_tiles) {
-    __shared__ Smem sm;
+    __shared__ Smem sm;      // 46.4 KB static: 3 CTAs/SM leave most of the 228 KB carve-out to L1
     const int tid = threadIdx.x;
 
     const bool prefix_in_smem = n_fields <= kMaxFieldsSmem;
@@ -450,45 +448,51 @@ __device__ __forceinline__ void bag_forward_body(const DevField *__restrict__ fi
                     const WordSrcShared src{scratch, 0u};
                     const bool is_mask = F.mask_mode == RF_MASK_INT_VALUE && v == F.int_mask;
                     for (int t = 0; t < T; ++t) {
-                        const uint32_t id = bucket_of(src, len, F.t[t], is_mask);
+                        const uint32_t id = bucket_of(src, len, F.t[t].h, is_mask);
                         sm.ids[t * kChunk + j] = id;
                         if (F.ids_out) F.ids_out[(int64_t)t * F.n_items + R.item0 + j] = (int64_t)id;
                     }
                 }
             } else {
-                for (int j = tid; j <= R.n_keys; j += kThreads) sm.soff[j] = F.soffs[R.item0 + j];
-                __syncthreads();
-                const int32_t byte0 = sm.soff[0];
-                const uint32_t n_bytes = (uint32_t)(sm.soff[R.n_keys] - byte0);
-                const uintptr_t addr0 = reinterpret_cast<uintptr_t>(F.bytes) + (uintptr_t)byte0;
-                const uint32_t shift = (uint32_t)(addr0 & 15u);
-                const bool staged = shift + n_bytes + 8u <= (uint32_t)kStageBytes;
-                if (staged) {
-                    const uint4 *g = reinterpret_cast<const uint4 *>(addr0 - shift);
-                    uint4 *s = reinterpret_cast<uint4 *>(sm.stage);
-                    const uint32_t n_vec = (shift + n_bytes + 8u + 15u) >> 4;
-                    for (uint32_t i = tid; i < n_vec; i += kThreads) s[i] = __ldg(g + i);
+                for (int sub0 = 0; sub0 < R.n_keys; sub0 += kSub) {
+                    const int n_sub = min(kSub, R.n_keys - sub0);
+                    const int64_t key0 = R.item0 + sub0;
+                    if (sub0) __syncthreads();          // previous sub-chunk's offsets / bytes are consumed
+                    for (int j = tid; j <= n_sub; j += kThreads) sm.soff[j] = F.soffs[key0 + j];
                     __syncthreads();
-                }
-                for (int j = tid; j < R.n_keys; j += kThreads) {
-                    const int32_t o = sm.soff[j];
-                    const uint32_t len = (uint32_t)(sm.soff[j + 1] - o);
-                    const bool is_mask = F.mask_mode == RF_MASK_EMPTY_STRING && len == 0;
-                    for (int t = 0; t < T; ++t) {
-                        uint32_t id;
-                        if (staged) {
-                            const WordSrcShared src{sm.stage, shift + (uint32_t)(o - byte0)};
-                            id = bucket_of(src, len, F.t[t], is_mask);
-                        } else {
-                            const uintptr_t a = reinterpret_cast<uintptr_t>(F.bytes) + (uintptr_t)o;
-                            const WordSrcGlobal src{reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3), (uint32_t)(a & 3u)};
-                            id = bucket_of(src, len, F.t[t], is_mask);
+                    const int32_t byte0 = sm.soff[0];
+                    const uint32_t n_bytes = (uint32_t)(sm.soff[n_sub] - byte0);
+                    const uintptr_t addr0 = reinterpret_cast<uintptr_t>(F.bytes) + (uintptr_t)byte0;
+                    const uint32_t shift = (uint32_t)(addr0 & 15u);
+                    const bool staged = shift + n_bytes + 8u <= (uint32_t)kStageBytes;
+                    if (staged) {
+                        const uint4 *g = reinterpret_cast<const uint4 *>(addr0 - shift);
+                        uint4 *s = reinterpret_cast<uint4 *>(sm.stage);
+                        const uint32_t n_vec = (shift + n_bytes + 8u + 15u) >> 4;
+                        for (uint32_t i = tid; i < n_vec; i += kThreads) s[i] = __ldg(g + i);
+                        __syncthreads();
+                    }
+                    for (int j = tid; j < n_sub; j += kThreads) {
+                        const int32_t o = sm.soff[j];
+                        const uint32_t len = (uint32_t)(sm.soff[j + 1] - o);
+                        const bool is_mask = F.mask_mode == RF_MASK_EMPTY_STRING && len == 0;
+                        for (int t = 0; t < T; ++t) {
+                            uint32_t id;
+                            if (staged) {
+                                const WordSrcShared src{sm.stage, shift + (uint32_t)(o - byte0)};
+                                id = bucket_of(src, len, F.t[t].h, is_mask);
+                            } else {
+                                const uintptr_t a = reinterpret_cast<uintptr_t>(F.bytes) + (uintptr_t)o;
+                                const WordSrcGlobal src{reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3), (uint32_t)(a & 3u)};
+                                id = bucket_of(src, len, F.t[t].h, is_mask);
+                            }
+                            sm.ids[t * kChunk + sub0 + j] = id;
+                            if (F.ids_out) F.ids_out[(int64_t)t * F.n_items + key0 + j] = (int64_t)id;
                         }
-                        sm.ids[t * kChunk + j] = id;
-                        if (F.ids_out) F.ids_out[(int64_t)t * F.n_items + R.item0 + j] = (int64_t)id;
                     }
                 }
             }
+            if (tid == 0) sm.next_work = 0;
             __syncthreads();
 
             // ---- phase C: gather + pool -----------------------------------------------------
@@ -531,9 +535,18 @@ struct DescSlot {
     bool used = false;
 };
 
+constexpr int kGraphSlots = 256;          // descriptor slots reserved for launches recorded into CUDA graphs
+constexpr size_t kGraphSlotBytes = 32 * 1024;
+
 struct DeviceState {
     DescSlot slots[8];
     int next = 0;
+    // A launch captured into a CUDA graph replays its descriptor upload from the same pinned host
+    // bytes every time, so it gets a slot of its own that is never rewritten.  The pool is
+    // allocated outside capture (cudaMalloc is not capturable).
+    char *graph_host = nullptr;
+    char *graph_dev = nullptr;
+    int graph_used = 0;
     int sm_count = 0;
     std::mutex mu;
 };
@@ -547,6 +560,22 @@ static DeviceState *device_state(int dev) {
     return states[dev];
 }
 
+static int launch_kernel(const DevField *dptr, int nf, int tiles_i, cudaStream_t stream) {
+    const int64_t tiles = tiles_i;
+    // CTAs per SM the kernel is compiled for (register cap): 4 (64 registers) measured best on
+    // B200 for C2 (0.383 ms vs 0.401 @3); RF_BAG_MINB overrides for experiments.
+    static const int cfg = getenv("RF_BAG_MINB") ? atoi(getenv("RF_BAG_MINB")) : 4;
+    switch (cfg) {
+        case 2: bag_forward_kernel<2><<<(unsigned)tiles, kThreads, 0, stream>>>(dptr, nf, (int)tiles); break;
+        case 3: bag_forward_kernel<3><<<(unsigned)tiles, kThreads, 0, stream>>>(dptr, nf, (int)tiles); break;
+        case 5: bag_forward_kernel<5><<<(unsigned)tiles, kThreads, 0, stream>>>(dptr, nf, (int)tiles); break;
+        default: bag_forward_kernel<4><<<(unsigned)tiles, kThreads, 0, stream>>>(dptr, nf, (int)tiles); break;
+    }
+    RF_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return RF_OK;
+}
+
 static int launch_fields(std::vector<DevField> &dev_fields, cudaStream_t stream) {
     int dev = 0;
     RF_CUDA(cudaGetDevice(&dev));
@@ -554,16 +583,19 @@ static int launch_fields(std::vector<DevField> &dev_fields, cudaStream_t stream)
     std::lock_guard<std::mutex> lk(st->mu);
     if (st->sm_count == 0) RF_CUDA(cudaDeviceGetAttribute(&st->sm_count, cudaDevAttrMultiProcessorCount, dev));
 
-    // tile sizing: ~kChunk keys per tile, smaller when the whole launch would not fill the GPU
+    // tile sizing: ~1024 keys per tile for short bags, a full round (kChunk keys, i.e. many bags
+    // to balance over the CTA's lane groups) for long ones; smaller when the launch would not
+    // fill the GPU
     int64_t total_keys = 0;
     for (auto &f : dev_fields) total_keys += f.n_items;
-    int64_t target = total_keys / ((int64_t)st->sm_count * 8);
-    if (target < 128) target = 128;
-    if (target > kChunk) target = kChunk;
+    int64_t fill = total_keys / ((int64_t)st->sm_count * 8);
+    if (fill < 128) fill = 128;
     int64_t tiles = 0;
     for (auto &f : dev_fields) {
         int64_t avg = f.batch > 0 ? (f.n_items + f.batch - 1) / f.batch : 1;
         if (avg < 1) avg = 1;
+        int64_t target = avg >= 32 ? kChunk : kSub;
+        if (target > fill) target = fill;
         int64_t bpt = target / avg;
         if (bpt < 1) bpt = 1;
         if (bpt > kMaxTileBags) bpt = kMaxTileBags;
@@ -575,9 +607,26 @@ static int launch_fields(std::vector<DevField> &dev_fields, cudaStream_t stream)
     if (tiles == 0) return RF_OK;
     if (tiles > INT32_MAX) return set_error(RF_ERR_UNSUPPORTED, "too many tiles in one launch");
 
+    const size_t bytes = dev_fields.size() * sizeof(DevField);
+    cudaStreamCaptureStatus capture = cudaStreamCaptureStatusNone;
+    RF_CUDA(cudaStreamIsCapturing(stream, &capture));
+    if (capture != cudaStreamCaptureStatusNone) {
+        if (!st->graph_host) return set_error(RF_ERR_CUDA, "run rf_bag_forward once outside stream capture before capturing it");
+        if (bytes > kGraphSlotBytes) return set_error(RF_ERR_UNSUPPORTED, "too many fields for a captured launch");
+        if (st->graph_used >= kGraphSlots) return set_error(RF_ERR_UNSUPPORTED, "more than %d captured launches", kGraphSlots);
+        char *h = st->graph_host + (size_t)st->graph_used * kGraphSlotBytes;
+        char *d = st->graph_dev + (size_t)st->graph_used * kGraphSlotBytes;
+        st->graph_used++;
+        memcpy(h, dev_fields.data(), bytes);
+        RF_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream));
+        return launch_kernel(reinterpret_cast<const DevField *>(d), (int)dev_fields.size(), (int)tiles, stream);
+    }
+    if (!st->graph_host) {
+        RF_CUDA(cudaMallocHost(reinterpret_cast<void **>(&st->graph_host), kGraphSlots * kGraphSlotBytes));
+        RF_CUDA(cudaMalloc(reinterpret_cast<void **>(&st->graph_dev), kGraphSlots * kGraphSlotBytes));
+    }
     DescSlot &slot = st->slots[st->next];
     st->next = (st->next + 1) % 8;
-    const size_t bytes = dev_fields.size() * sizeof(DevField);
     if (slot.used) RF_CUDA(cudaEventSynchronize(slot.done));
     if (slot.cap < bytes) {
         if (slot.host) cudaFreeHost(slot.host);
@@ -591,19 +640,10 @@ static int launch_fields(std::vector<DevField> &dev_fields, cudaStream_t stream)
     if (!slot.done) RF_CUDA(cudaEventCreateWithFlags(&slot.done, cudaEventDisableTiming));
     memcpy(slot.host, dev_fields.data(), bytes);
     RF_CUDA(cudaMemcpyAsync(slot.dev, slot.host, bytes, cudaMemcpyHostToDevice, stream));
-    // CTAs per SM the kernel is compiled for (register cap): 3 measured best on B200 for C2
-    // (0.385 ms vs 0.437 @2, 0.410 @4, 0.520 @5); RF_BAG_MINB overrides for experiments.
-    static const int cfg = getenv("RF_BAG_MINB") ? atoi(getenv("RF_BAG_MINB")) : 3;
-    const DevField *dptr = static_cast<const DevField *>(slot.dev);
-    const int nf = (int)dev_fields.size();
-    switch (cfg) {
-        case 4: bag_forward_kernel<4><<<(unsigned)tiles, kThreads, 0, stream>>>(dptr, nf, (int)tiles); break;
-        case 5: bag_forward_kernel<5><<<(unsigned)tiles, kThreads, 0, stream>>>(dptr, nf, (int)tiles); break;
-        case 2: bag_forward_kernel<2><<<(unsigned)tiles, kThreads, 0, stream>>>(dptr, nf, (int)tiles); break;
-        default: bag_forward_kernel<3><<<(unsigned)tiles, kThreads, 0, stream>>>(dptr, nf, (int)tiles); break;
+    {
+        int rc = launch_kernel(static_cast<const DevField *>(slot.dev), (int)dev_fields.size(), (int)tiles, stream);
+        if (rc != RF_OK) return rc;
     }
-    RF_CUDA(cudaGetLastError());
-    g_launches.fetch_add(1);
     RF_CUDA(cudaEventRecord(slot.done, stream));
     slot.used = true;
     return RF_OK;
@@ -615,11 +655,7 @@ static int fill_table(DevTable &dt, const rf_table_desc &t, int mask_mode, bool 
     if (need_weights && t.weights == nullptr)
         return set_error(RF_ERR_INVALID, "field %d table %d: weights pointer is NULL", fi, ti);
     dt.w = t.weights;
-    dt.k0 = t.key0;
-    dt.k1 = t.key1;
-    dt.use_strong = t.use_strong ? 1u : 0u;
-    dt.masking = (mask_mode != RF_MASK_NONE && t.num_bins > 1) ? 1u : 0u;
-    dt.mod = make_fastmod((uint64_t)t.num_bins - (dt.masking ? 1u : 0u));
+    dt.h = make_hash_spec(t.num_bins, mask_mode != RF_MASK_NONE, t.use_strong, t.key0, t.key1);
     return RF_OK;
 }
 

@@ -69,6 +69,24 @@ RF_HD uint64_t fastmod(uint64_t x, const FastMod &m) {
     return x - q * m.d;
 }
 
+// Everything Keras `Hashing` needs to turn one key into a bucket id.
+struct HashSpec {
+    uint64_t k0, k1;      // SipHash key (use_strong)
+    FastMod mod;          // divisor = num_bins, or num_bins - 1 when bucket 0 is reserved
+    uint32_t use_strong;  // 1: SipHash-2-4, 0: FarmHash Fingerprint64
+    uint32_t masking;     // 1: bucket 0 is reserved for the mask value (mask given and num_bins > 1)
+};
+
+inline HashSpec make_hash_spec(int64_t num_bins, bool has_mask, int use_strong, uint64_t k0, uint64_t k1) {
+    HashSpec h;
+    h.k0 = k0;
+    h.k1 = k1;
+    h.use_strong = use_strong ? 1u : 0u;
+    h.masking = (has_mask && num_bins > 1) ? 1u : 0u;
+    h.mod = make_fastmod((uint64_t)num_bins - (h.masking ? 1u : 0u));
+    return h;
+}
+
 #if defined(__CUDACC__)
 // ------------------------------------------------------------------------------------------
 // Byte sources: `words` is 4-byte aligned, the key starts `off` bytes into it.  Fetches read
@@ -282,6 +300,15 @@ __device__ __forceinline__ uint64_t siphash24(const Src &s, uint32_t n, uint64_t
     RF_SIPROUND();
     RF_SIPROUND();
     return v0 ^ v1 ^ v2 ^ v3;
+}
+
+// Keras Hashing._hash_values_to_bins for one key
+template <class Src>
+__device__ __forceinline__ uint32_t bucket_of(const Src &src, uint32_t len, const HashSpec &h, bool is_mask) {
+    const uint64_t x = h.use_strong ? siphash24(src, len, h.k0, h.k1) : fingerprint64(src, len);
+    uint32_t id = (uint32_t)fastmod(x, h.mod);
+    if (h.masking) id = is_mask ? 0u : id + 1u;
+    return id;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -23,6 +23,7 @@
 
 #include "../../include/rf_b200.h"
 #include "rf_common.h"
+#include "rf_hash.cuh"
 
 namespace rf {
 
@@ -43,8 +44,14 @@ __device__ __forceinline__ void bag_range(const int32_t *boffs, int bag_len, int
     }
 }
 
-// counts[g * batch + b] = #keys of bag b owned by rank g.  One warp per bag.
-__global__ void __launch_bounds__(256) shard_count_kernel(const int64_t *__restrict__ ids, const int32_t *__restrict__ boffs,
+// counts[g * batch + b] = #keys of bag b owned by rank g.  One warp per bag.  With HASH the keys
+// are still strings: each lane hashes its key straight from global memory (the loads of the
+// other warps hide the latency) and leaves the bucket id in ids_ws for the scatter pass, so the
+// sharded path needs no separate hashing pass over the batch.
+template <bool HASH>
+__global__ void __launch_bounds__(256) shard_count_kernel(const int64_t *__restrict__ ids, const uint8_t *__restrict__ bytes,
+                                                          const int32_t *__restrict__ soffs, HashSpec spec, int mask_empty,
+                                                          int64_t *__restrict__ ids_ws, const int32_t *__restrict__ boffs,
                                                           int bag_len, int64_t batch, int world, int32_t *__restrict__ counts) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -55,7 +62,20 @@ __global__ void __launch_bounds__(256) shard_count_kernel(const int64_t *__restr
         int mine = 0;   // lane g accumulates the count for owner g
         for (int64_t i = lo; i < hi; i += 32) {
             const bool on = i + lane < hi;
-            const int owner = on ? (int)((uint64_t)ids[i + lane] % (uint32_t)world) : -1;
+            uint64_t id = 0;
+            if (on) {
+                if (HASH) {
+                    const int32_t o = soffs[i + lane];
+                    const uint32_t len = (uint32_t)(soffs[i + lane + 1] - o);
+                    const uintptr_t a = reinterpret_cast<uintptr_t>(bytes) + (uintptr_t)o;
+                    const WordSrcGlobal src{reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3), (uint32_t)(a & 3u)};
+                    id = bucket_of(src, len, spec, mask_empty && len == 0);
+                    ids_ws[i + lane] = (int64_t)id;
+                } else {
+                    id = (uint64_t)ids[i + lane];
+                }
+            }
+            const int owner = on ? (int)(id % (uint32_t)world) : -1;
             for (int g = 0; g < world; ++g) {
                 const unsigned m = __ballot_sync(0xffffffffu, owner == g);
                 if (lane == g) mine += __popc(m);
@@ -210,14 +230,14 @@ using namespace rf;
 
 extern "C" {
 
-int rf_shard_route(const int64_t *d_ids, const int32_t *d_bag_offsets, int32_t bag_len, int64_t batch, int world,
-                   int32_t *d_counts_ws, int32_t *d_offsets_local, int32_t *const *h_offsets_dst,
-                   int64_t *const *h_rows_dst, void *stream) {
+static int route_impl(const int64_t *d_ids, const uint8_t *d_bytes, const int32_t *d_str_offsets, const HashSpec *spec,
+                      int mask_empty, int64_t *d_ids_ws, const int32_t *d_bag_offsets, int32_t bag_len, int64_t batch,
+                      int world, int32_t *d_counts_ws, int32_t *d_offsets_local, int32_t *const *h_offsets_dst,
+                      int64_t *const *h_rows_dst, void *stream) {
     if (world < 1 || world > kMaxWorld) return set_error(RF_ERR_INVALID, "world must be in [1, %d]", kMaxWorld);
     if (batch < 0 || batch > INT32_MAX) return set_error(RF_ERR_INVALID, "batch out of range");
     if (batch == 0) return RF_OK;
-    if (!d_ids || !d_counts_ws || !d_offsets_local || !h_rows_dst)
-        return set_error(RF_ERR_INVALID, "rf_shard_route: NULL buffer");
+    if (!d_counts_ws || !d_offsets_local || !h_rows_dst) return set_error(RF_ERR_INVALID, "rf_shard_route: NULL buffer");
     if (!d_bag_offsets && bag_len < 0) return set_error(RF_ERR_INVALID, "negative bag_len");
     int dev = 0, sms = 0;
     RF_CUDA(cudaGetDevice(&dev));
@@ -230,12 +250,41 @@ int rf_shard_route(const int64_t *d_ids, const int32_t *d_bag_offsets, int32_t b
         if (!rows.p[g]) return set_error(RF_ERR_INVALID, "rf_shard_route: rows_dst[%d] is NULL", g);
     }
     const int grid = grid_for(batch, 8, sms);   // 8 warps (bags) per 256-thread block
-    shard_count_kernel<<<grid, 256, 0, st>>>(d_ids, d_bag_offsets, bag_len, batch, world, d_counts_ws);
+    if (spec)
+        shard_count_kernel<true><<<grid, 256, 0, st>>>(nullptr, d_bytes, d_str_offsets, *spec, mask_empty, d_ids_ws,
+                                                       d_bag_offsets, bag_len, batch, world, d_counts_ws);
+    else
+        shard_count_kernel<false><<<grid, 256, 0, st>>>(d_ids, nullptr, nullptr, HashSpec{}, 0, nullptr, d_bag_offsets,
+                                                        bag_len, batch, world, d_counts_ws);
     shard_scan_kernel<<<world, 1024, 0, st>>>(d_counts_ws, batch, d_offsets_local, offs);
-    shard_scatter_kernel<<<grid, 256, 0, st>>>(d_ids, d_bag_offsets, bag_len, batch, world, d_offsets_local, rows);
+    shard_scatter_kernel<<<grid, 256, 0, st>>>(spec ? d_ids_ws : d_ids, d_bag_offsets, bag_len, batch, world,
+                                               d_offsets_local, rows);
     RF_CUDA(cudaGetLastError());
     g_launches.fetch_add(3);
     return RF_OK;
+}
+
+int rf_shard_route(const int64_t *d_ids, const int32_t *d_bag_offsets, int32_t bag_len, int64_t batch, int world,
+                   int32_t *d_counts_ws, int32_t *d_offsets_local, int32_t *const *h_offsets_dst,
+                   int64_t *const *h_rows_dst, void *stream) {
+    if (batch > 0 && !d_ids) return set_error(RF_ERR_INVALID, "rf_shard_route: ids is NULL");
+    return route_impl(d_ids, nullptr, nullptr, nullptr, 0, nullptr, d_bag_offsets, bag_len, batch, world, d_counts_ws,
+                      d_offsets_local, h_offsets_dst, h_rows_dst, stream);
+}
+
+int rf_shard_route_keys(const uint8_t *d_bytes, const int32_t *d_str_offsets, int64_t num_bins, int mask_mode,
+                        int use_strong, uint64_t key0, uint64_t key1, int64_t *d_ids_ws, const int32_t *d_bag_offsets,
+                        int32_t bag_len, int64_t batch, int world, int32_t *d_counts_ws, int32_t *d_offsets_local,
+                        int32_t *const *h_offsets_dst, int64_t *const *h_rows_dst, void *stream) {
+    if (batch > 0 && (!d_bytes || !d_str_offsets || !d_ids_ws))
+        return set_error(RF_ERR_INVALID, "rf_shard_route_keys: NULL key buffer");
+    if (num_bins <= 0) return set_error(RF_ERR_INVALID, "`num_bins` cannot be `None` or non-positive values.");
+    if (num_bins > 0xffffffffLL) return set_error(RF_ERR_UNSUPPORTED, "num_bins above 2^32-1 is not supported");
+    if (mask_mode != RF_MASK_NONE && mask_mode != RF_MASK_EMPTY_STRING)
+        return set_error(RF_ERR_INVALID, "string keys take RF_MASK_NONE or RF_MASK_EMPTY_STRING");
+    const HashSpec spec = make_hash_spec(num_bins, mask_mode != RF_MASK_NONE, use_strong, key0, key1);
+    return route_impl(nullptr, d_bytes, d_str_offsets, &spec, mask_mode == RF_MASK_EMPTY_STRING, d_ids_ws, d_bag_offsets,
+                      bag_len, batch, world, d_counts_ws, d_offsets_local, h_offsets_dst, h_rows_dst, stream);
 }
 
 int rf_combine_partials(const float *d_partials, int world, int64_t batch, int32_t dim, int combiner, int32_t bag_len,

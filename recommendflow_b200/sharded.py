@@ -37,6 +37,21 @@ class CudaShardOps(object):
             return hash_strings(keys, num_bins, mask_value, salt).reshape(-1)
         return hash_ints(keys, num_bins, mask_value, salt).reshape(-1)
 
+    def route_keys(self, keys, num_bins, mask_value, salt, ids_ws, bag_offsets, bag_len, batch, world, counts_ws,
+                   offs_local, offs_dst_ptrs, rows_dst_ptrs):
+        """Hash + route in one pass (string keys); ids_ws receives the bucket ids."""
+        if mask_value not in (None, ""):
+            raise NotImplementedError("only mask_value in (None, '') is supported for string keys")
+        strong, k0, k1 = nat.salt_to_key(salt)
+        arr_o = (C.c_void_p * world)(*offs_dst_ptrs) if offs_dst_ptrs is not None else None
+        arr_r = (C.c_void_p * world)(*rows_dst_ptrs)
+        with torch.cuda.device(keys.device):
+            nat.check(nat.lib().rf_shard_route_keys(
+                keys.data.data_ptr(), keys.offsets.data_ptr(), int(num_bins),
+                nat.MASK_NONE if mask_value is None else nat.MASK_EMPTY_STRING, strong, k0, k1, ids_ws.data_ptr(),
+                None if bag_offsets is None else bag_offsets.data_ptr(), bag_len or 0, batch, world, counts_ws.data_ptr(),
+                offs_local.data_ptr(), arr_o, arr_r, C.c_void_p(torch.cuda.current_stream(keys.device).cuda_stream)))
+
     def route(self, ids, bag_offsets, bag_len, batch, world, counts_ws, offs_local, offs_dst_ptrs, rows_dst_ptrs):
         arr_o = (C.c_void_p * world)(*offs_dst_ptrs) if offs_dst_ptrs is not None else None
         arr_r = (C.c_void_p * world)(*rows_dst_ptrs)
@@ -89,6 +104,13 @@ class ShardedEmbeddingBag(torch.nn.Module):
         self.shard = torch.nn.Parameter(torch.empty(max(rows, 1), self.output_dim, dtype=torch.float32,
                                                     device=self.device).uniform_(-0.05, 0.05), requires_grad=False)
         self._bufs = None
+        self.profile = None      # set to [] to collect (phase name, cuda event) pairs per forward
+
+    def _tick(self, phase):
+        if self.profile is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.profile.append((phase, ev))
 
     @property
     def name(self):
@@ -107,8 +129,12 @@ class ShardedEmbeddingBag(torch.nn.Module):
 
     # ---- buffers ---------------------------------------------------------------------------------
     def _alloc(self):
-        W, B, K, D = self.world, self.max_batch, self.max_keys, self.output_dim
         dev = self.device
+        if self.world > 1:       # symmetric buffers must have one size on every rank
+            t = torch.tensor([self.max_keys], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            self.max_keys = int(t.item())
+        W, B, K, D = self.world, self.max_batch, self.max_keys, self.output_dim
         b = {"counts": torch.empty(W * B, dtype=torch.int32, device=dev),
              "offs_local": torch.empty(W * (B + 1), dtype=torch.int32, device=dev)}
         if self.transport == "p2p":
@@ -151,7 +177,21 @@ class ShardedEmbeddingBag(torch.nn.Module):
             raise ValueError(f"{n_keys} keys exceed max_keys={self.max_keys}")
         if out is None:
             out = torch.empty(B, D, dtype=torch.float32, device=self.device)
-        ids = self.ops.hash(keys, self.num_bins, self.mask_value, self.salt)
+        self._tick("start")
+        fused_hash = isinstance(keys, StringColumn) and hasattr(self.ops, "route_keys")
+        if fused_hash:
+            if b.get("ids_ws") is None:
+                b["ids_ws"] = torch.empty(self.max_keys, dtype=torch.int64, device=self.device)
+
+            def route(offs_dst, rows_dst):
+                self.ops.route_keys(keys, self.num_bins, self.mask_value, self.salt, b["ids_ws"], bag_offsets, L, B, W,
+                                    b["counts"], b["offs_local"], offs_dst, rows_dst)
+        else:
+            ids = self.ops.hash(keys, self.num_bins, self.mask_value, self.salt)
+            self._tick("hash")
+
+            def route(offs_dst, rows_dst):
+                self.ops.route(ids, bag_offsets, L, B, W, b["counts"], b["offs_local"], offs_dst, rows_dst)
         partial_op = "sum" if self.combiner == "avg" else self.combiner
         est = max(1, n_keys // W)
 
@@ -159,15 +199,19 @@ class ShardedEmbeddingBag(torch.nn.Module):
             K, hdl = self.max_keys, b["hdl"]
             rows_dst = [b["peer_ptr"][g] + b["rows_off"] + me * K * 8 for g in range(W)]
             offs_dst = [b["peer_ptr"][g] + b["offs_off"] + me * (B + 1) * 4 for g in range(W)]
-            self.ops.route(ids, bag_offsets, L, B, W, b["counts"], b["offs_local"], offs_dst, rows_dst)
+            route(offs_dst, rows_dst)
+            self._tick("route")
             hdl.barrier(channel=0)                       # every source's ids/offsets have landed here
+            self._tick("barrier0")
             self.ops.pool(self.shard.data, [b["rows_recv"][s] for s in range(W)], [b["offs_recv"][s] for s in range(W)],
                           [b["peer_partials"][s][me] for s in range(W)], B, partial_op, est)
+            self._tick("pool")
             hdl.barrier(channel=1)                       # every owner's partials have landed here
+            self._tick("barrier1")
         else:
             rows_dst = [b["rows_send"][g].data_ptr() for g in range(W)]
             offs_dst = [b["offs_send"][g].data_ptr() for g in range(W)]
-            self.ops.route(ids, bag_offsets, L, B, W, b["counts"], b["offs_local"], offs_dst, rows_dst)
+            route(offs_dst, rows_dst)
             dist.all_to_all_single(b["offs_recv"], b["offs_send"], group=self.group)
             send_tot = b["offs_send"][:, B].tolist()     # host sync: NCCL needs the split sizes
             recv_tot = b["offs_recv"][:, B].tolist()
@@ -179,4 +223,5 @@ class ShardedEmbeddingBag(torch.nn.Module):
                           [b["part_send"][s] for s in range(W)], B, partial_op, est)
             dist.all_to_all_single(b["partials"], b["part_send"], group=self.group)
         self.ops.combine(b["partials"], W, B, D, self.combiner, L, bag_offsets, out)
+        self._tick("combine")
         return out

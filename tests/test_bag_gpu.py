@@ -211,3 +211,40 @@ def test_large_batch_linearity_property():
     sample = rng.integers(0, B * L, size=4096)
     want = oracle.hash_strings(arena, offs, N, "", None)[sample]
     assert np.array_equal(ids_out.view(-1).cpu().numpy()[sample], want)
+
+
+def test_cuda_graph_capture_and_replay_with_new_keys():
+    # A captured launch owns its descriptor slot; replaying after the key BUFFERS were refilled must
+    # use the new keys (descriptors hold pointers, not data).
+    rng = np.random.default_rng(17)
+    B, L, N, D = 4096, 4, 50021, 64
+    ws = tables(rng, 2, N, D)
+    dev_w = to_dev(ws)
+    arenas = [random_strings(rng, B * L, max_len=10, alphabet=ALNUM) for _ in range(2)]
+    cap_bytes = max(a.size for a, _ in arenas) + 16
+    data = torch.zeros(cap_bytes, dtype=torch.uint8, device="cuda")
+    offs = torch.zeros(B * L + 1, dtype=torch.int32, device="cuda")
+    from recommendflow_b200.strings import StringColumn
+    col = StringColumn(data, offs, (B, L))
+    out = torch.empty(B, 2 * D, device="cuda")
+    call = [FieldCall([(dev_w[0], N, [2022, 2022]), (dev_w[1], N, [2023, 2023])], D, "sum", keys=col,
+                      mask_mode=nat.MASK_EMPTY_STRING, out=out, bag_len=L)]
+
+    def load(i):
+        a, o = arenas[i]
+        data[:a.size].copy_(torch.from_numpy(a))
+        offs.copy_(torch.from_numpy(o))
+
+    load(0)
+    bag_forward(call, B)                      # warm-up outside capture (allocates the slot pool)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        bag_forward(call, B)
+    for i in (1, 0, 1):
+        load(i)
+        g.replay()
+        torch.cuda.synchronize()
+        a, o = arenas[i]
+        want = oracle.hashed_bag_forward(a, o, B, L, ws, [N, N], [[2022, 2022], [2023, 2023]], "sum")
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32)), i

@@ -39,7 +39,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--transport", default="both", choices=["p2p", "nccl", "both"])
-    ap.add_argument("--pipeline", type=int, default=1, help="streams used to overlap consecutive steps")
+    ap.add_argument("--graph", action="store_true", help="capture each step (p2p transport) in a CUDA graph and replay")
     args = ap.parse_args()
 
     import torch
@@ -98,14 +98,47 @@ def main():
         results["single_gpu_fused"] = ms
     else:
         transports = ["p2p", "nccl"] if args.transport == "both" else [args.transport]
-        outs = {}
+        outs, shard = {}, None
         for tr in transports:
             layer = ShardedEmbeddingBag(N, D, combiner="avg", salt=None, mask_value="", transport=tr, max_batch=B,
                                         max_keys=max_keys)
+            if shard is None:
+                shard = layer.shard
+            else:
+                layer.shard = shard                     # same table for both transports
             out = torch.empty(B, D, dtype=torch.float32, device=dev)
             ms = timed(lambda i: layer(batches[i % NB], out=out))
             results[tr] = ms
+            if tr == "p2p" and args.graph:
+                # the p2p step has no host synchronisation, so the whole step (route kernels, symmetric-
+                # memory barriers, fused gather+pool into peer memory, combine) replays as one graph launch
+                graphs = []
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for c in batches:
+                        layer(c, out=out)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                dist.barrier()
+                for c in batches:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        layer(c, out=out)
+                    graphs.append(g)
+                results["p2p_graph"] = timed(lambda i: graphs[i % NB].replay())
+                results["p2p_graph_equals_eager"] = bool(torch.equal(out, layer(batches[(W + K - 1) % NB]).clone()))
             outs[tr] = layer(batches[0]).clone()
+            if tr == "p2p":                             # per-phase device times of a few steps (rank 0 reports)
+                acc = {}
+                for i in range(5):
+                    layer.profile = []
+                    layer(batches[i % NB], out=out)
+                    torch.cuda.synchronize()
+                    for (n0, e0), (n1, e1) in zip(layer.profile[:-1], layer.profile[1:]):
+                        acc[n1] = acc.get(n1, 0.0) + e0.elapsed_time(e1) / 5
+                layer.profile = None
+                results["p2p_phases_ms"] = {k: round(v, 4) for k, v in acc.items()}
             del layer
         if len(outs) == 2:
             results["p2p_equals_nccl"] = bool(torch.equal(outs["p2p"], outs["nccl"]))
