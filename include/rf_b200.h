@@ -115,8 +115,8 @@ int rf_bag_forward(const rf_field_desc *fields, int n_fields, int64_t batch, voi
 /* owner g it writes a CSR offsets[batch+1] through h_offsets_dst[g] (may be NULL) and the      */
 /* owner-local rows through h_rows_dst[g] (int64, capacity >= this rank's key count).  The      */
 /* h_* arrays are HOST arrays of `world` DEVICE pointers -- peer-mapped NVLink pointers in the  */
-/* fused path, local send buffers in the NCCL path.  d_counts_ws: int32[world*batch] scratch;   */
-/* d_offsets_local: int32[world*(batch+1)] receives the same CSR locally.                       */
+/* fused path, local send buffers in the NCCL path.  Scratch: d_counts_ws int32[world*batch],   */
+/* d_offsets_local int32[world*(batch + 1 + ceil(batch/1024))] (in-chunk scans + chunk totals). */
 int rf_shard_route(const int64_t *d_ids, const int32_t *d_bag_offsets, int32_t bag_len, int64_t batch,
                    int world, int32_t *d_counts_ws, int32_t *d_offsets_local,
                    int32_t *const *h_offsets_dst, int64_t *const *h_rows_dst, void *stream);

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) shard_count_kernel(const int64_t *__restr
         int mine = 0;   // lane g accumulates the count for owner g
         for (int64_t i = lo; i < hi; i += 32) {
             const bool on = i + lane < hi;
-            uint64_t id = 0;
+            uint32_t id = 0;           // bucket ids fit 32 bits (num_bins <= 2^32 - 1): 32-bit div/mod
             if (on) {
                 if (HASH) {
                     const int32_t o = soffs[i + lane];
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) shard_count_kernel(const int64_t *__restr
                     id = bucket_of(src, len, spec, mask_empty && len == 0);
                     ids_ws[i + lane] = (int64_t)id;
                 } else {
-                    id = (uint64_t)ids[i + lane];
+                    id = (uint32_t)ids[i + lane];
                 }
             }
             const int owner = on ? (int)(id % (uint32_t)world) : -1;
@@ -85,22 +85,54 @@ __global__ void __launch_bounds__(256) shard_count_kernel(const int64_t *__restr
     }
 }
 
-// One CTA per owner g: exclusive scan of counts[g][0..batch) -> offsets (batch + 1 entries), written
-// to the local copy and through dst.p[g] (the owner's receive buffer for this source).
-__global__ void __launch_bounds__(1024) shard_scan_kernel(const int32_t *__restrict__ counts, int64_t batch,
-                                                          int32_t *__restrict__ offs_local, PtrTable dst) {
+constexpr int kScanChunk = 1024;   // bags per scan chunk
+
+// Grid (chunks, world): exclusive scan of counts[g][chunk*1024 ..] inside the chunk ->
+// excl[g][b] (chunk-relative) and chunk_tot[g][chunk].  The chunk bases are summed on the fly by
+// the scatter pass, so the whole scan is two fully parallel kernels instead of a serial one.
+__global__ void __launch_bounds__(kScanChunk) shard_scan_kernel(const int32_t *__restrict__ counts, int64_t batch,
+                                                                int n_chunks, int32_t *__restrict__ excl,
+                                                                int32_t *__restrict__ chunk_tot) {
+    __shared__ int32_t warp_sums[32];
+    const int g = blockIdx.y, chunk = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t i = (int64_t)chunk * kScanChunk + tid;
+    const int32_t v = i < batch ? counts[(int64_t)g * batch + i] : 0;
+    int32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int32_t y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        int32_t t = warp_sums[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int32_t y = __shfl_up_sync(0xffffffffu, t, d);
+            if (lane >= d) t += y;
+        }
+        warp_sums[lane] = t;
+    }
+    __syncthreads();
+    if (i < batch) excl[(int64_t)g * batch + i] = (wid ? warp_sums[wid - 1] : 0) + x - v;
+    if (tid == kScanChunk - 1) chunk_tot[(int64_t)g * n_chunks + chunk] = warp_sums[31];
+}
+
+// One CTA per owner: chunk_tot[g][0..n_chunks) -> exclusive chunk bases in place; the grand total
+// closes the owner's CSR (offs_dst[g][batch]).
+__global__ void __launch_bounds__(1024) shard_chunk_base_kernel(int32_t *__restrict__ chunk_tot, int n_chunks, int64_t batch,
+                                                                PtrTable offs_dst) {
     __shared__ int32_t warp_sums[32];
     __shared__ int32_t carry_s;
-    const int g = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int32_t *c = counts + (int64_t)g * batch;
-    int32_t *ol = offs_local + (int64_t)g * (batch + 1);
-    int32_t *od = static_cast<int32_t *>(dst.p[g]);
+    const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int32_t *ct = chunk_tot + (int64_t)g * n_chunks;
     if (tid == 0) carry_s = 0;
     __syncthreads();
-    for (int64_t base = 0; base < batch; base += 1024) {
-        const int64_t i = base + tid;
-        const int32_t v = i < batch ? c[i] : 0;
+    for (int base = 0; base < n_chunks; base += 1024) {
+        const int i = base + tid;
+        const int32_t v = i < n_chunks ? ct[i] : 0;
         int32_t x = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -110,36 +142,32 @@ __global__ void __launch_bounds__(1024) shard_scan_kernel(const int32_t *__restr
         if (lane == 31) warp_sums[wid] = x;
         __syncthreads();
         if (wid == 0) {
-            int32_t s = warp_sums[lane];
+            int32_t t = warp_sums[lane];
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const int32_t y = __shfl_up_sync(0xffffffffu, s, d);
-                if (lane >= d) s += y;
+                const int32_t y = __shfl_up_sync(0xffffffffu, t, d);
+                if (lane >= d) t += y;
             }
-            warp_sums[lane] = s;
+            warp_sums[lane] = t;
         }
         __syncthreads();
         const int32_t carry = carry_s;
-        const int32_t excl = carry + (wid ? warp_sums[wid - 1] : 0) + x - v;
-        if (i < batch) {
-            ol[i] = excl;
-            if (od) od[i] = excl;
-        }
+        if (i < n_chunks) ct[i] = carry + (wid ? warp_sums[wid - 1] : 0) + x - v;
         __syncthreads();
         if (tid == 1023) carry_s = carry + warp_sums[31];
         __syncthreads();
     }
-    if (tid == 0) {
-        ol[batch] = carry_s;
-        if (od) od[batch] = carry_s;
-    }
+    if (tid == 0 && offs_dst.p[g]) static_cast<int32_t *>(offs_dst.p[g])[batch] = carry_s;
 }
 
 // One warp per bag: key k of bag b owned by g goes to rows_dst[g][offs[g][b] + (rank of k among the
 // bag's keys owned by g)] as the owner-local row id / world.  Order inside (owner, bag) is kept.
+// offs[g][b] = chunk base + excl[g][b]; lane g also publishes it as the owner's CSR (offs_dst[g][b]).
 __global__ void __launch_bounds__(256) shard_scatter_kernel(const int64_t *__restrict__ ids, const int32_t *__restrict__ boffs,
-                                                            int bag_len, int64_t batch, int world,
-                                                            const int32_t *__restrict__ offs_local, PtrTable rows_dst) {
+                                                            int bag_len, int64_t batch, int world, int n_chunks,
+                                                            const int32_t *__restrict__ excl,
+                                                            const int32_t *__restrict__ chunk_tot, PtrTable offs_dst,
+                                                            PtrTable rows_dst) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -147,12 +175,19 @@ __global__ void __launch_bounds__(256) shard_scatter_kernel(const int64_t *__res
     for (int64_t b = warp0; b < batch; b += n_warps) {
         int64_t lo, hi;
         bag_range(boffs, bag_len, b, lo, hi);
-        // lane g tracks the next free slot of owner g for this bag
-        int next = lane < world ? offs_local[(int64_t)lane * (batch + 1) + b] : 0;
+        const int chunk = (int)(b / kScanChunk);
+        // lane g: base of owner g = chunk totals before this chunk + in-chunk exclusive offset
+        int next = 0;
+        if (lane < world) {
+            next = chunk_tot[(int64_t)lane * n_chunks + chunk] + excl[(int64_t)lane * batch + b];
+            int32_t *od = static_cast<int32_t *>(offs_dst.p[lane]);
+            if (od) od[b] = next;
+        }
         for (int64_t i = lo; i < hi; i += 32) {
             const bool on = i + lane < hi;
-            const uint64_t id = on ? (uint64_t)ids[i + lane] : 0;
-            const int owner = on ? (int)(id % (uint32_t)world) : -1;
+            const uint32_t id = on ? (uint32_t)ids[i + lane] : 0u;
+            const uint32_t row = id / (uint32_t)world;
+            const int owner = on ? (int)(id - row * (uint32_t)world) : -1;
             int pos = 0;
             for (int g = 0; g < world; ++g) {
                 const unsigned m = __ballot_sync(0xffffffffu, owner == g);
@@ -160,7 +195,7 @@ __global__ void __launch_bounds__(256) shard_scatter_kernel(const int64_t *__res
                 if (owner == g) pos = base + __popc(m & lt);
                 if (lane == g) next += __popc(m);
             }
-            if (on) static_cast<int64_t *>(rows_dst.p[owner])[pos] = (int64_t)(id / (uint32_t)world);
+            if (on) static_cast<int64_t *>(rows_dst.p[owner])[pos] = (int64_t)row;
         }
     }
 }
@@ -237,7 +272,8 @@ static int route_impl(const int64_t *d_ids, const uint8_t *d_bytes, const int32_
     if (world < 1 || world > kMaxWorld) return set_error(RF_ERR_INVALID, "world must be in [1, %d]", kMaxWorld);
     if (batch < 0 || batch > INT32_MAX) return set_error(RF_ERR_INVALID, "batch out of range");
     if (batch == 0) return RF_OK;
-    if (!d_counts_ws || !d_offsets_local || !h_rows_dst) return set_error(RF_ERR_INVALID, "rf_shard_route: NULL buffer");
+    if (!d_counts_ws || !d_offsets_local || !h_rows_dst || !h_offsets_dst)
+        return set_error(RF_ERR_INVALID, "rf_shard_route: NULL buffer");
     if (!d_bag_offsets && bag_len < 0) return set_error(RF_ERR_INVALID, "negative bag_len");
     int dev = 0, sms = 0;
     RF_CUDA(cudaGetDevice(&dev));
@@ -256,11 +292,15 @@ static int route_impl(const int64_t *d_ids, const uint8_t *d_bytes, const int32_
     else
         shard_count_kernel<false><<<grid, 256, 0, st>>>(d_ids, nullptr, nullptr, HashSpec{}, 0, nullptr, d_bag_offsets,
                                                         bag_len, batch, world, d_counts_ws);
-    shard_scan_kernel<<<world, 1024, 0, st>>>(d_counts_ws, batch, d_offsets_local, offs);
-    shard_scatter_kernel<<<grid, 256, 0, st>>>(spec ? d_ids_ws : d_ids, d_bag_offsets, bag_len, batch, world,
-                                               d_offsets_local, rows);
+    const int n_chunks = (int)((batch + kScanChunk - 1) / kScanChunk);
+    int32_t *excl = d_offsets_local;                         // [world][batch]
+    int32_t *chunk_tot = d_offsets_local + (int64_t)world * batch;   // [world][n_chunks]
+    shard_scan_kernel<<<dim3(n_chunks, world), kScanChunk, 0, st>>>(d_counts_ws, batch, n_chunks, excl, chunk_tot);
+    shard_chunk_base_kernel<<<world, 1024, 0, st>>>(chunk_tot, n_chunks, batch, offs);
+    shard_scatter_kernel<<<grid, 256, 0, st>>>(spec ? d_ids_ws : d_ids, d_bag_offsets, bag_len, batch, world, n_chunks,
+                                               excl, chunk_tot, offs, rows);
     RF_CUDA(cudaGetLastError());
-    g_launches.fetch_add(3);
+    g_launches.fetch_add(4);
     return RF_OK;
 }
 

@@ -128,6 +128,8 @@ class ShardedEmbeddingBag(torch.nn.Module):
         self.shard = torch.nn.Parameter(mine.to(self.device), requires_grad=False)
 
     # ---- buffers ---------------------------------------------------------------------------------
+    N_SETS = 2      # receive-buffer sets: routing of step i+1 may overlap pooling of step i
+
     def _alloc(self):
         dev = self.device
         if self.world > 1:       # symmetric buffers must have one size on every rank
@@ -136,37 +138,36 @@ class ShardedEmbeddingBag(torch.nn.Module):
             self.max_keys = int(t.item())
         W, B, K, D = self.world, self.max_batch, self.max_keys, self.output_dim
         b = {"counts": torch.empty(W * B, dtype=torch.int32, device=dev),
-             "offs_local": torch.empty(W * (B + 1), dtype=torch.int32, device=dev)}
+             "offs_local": torch.empty(W * (B + 1 + (B + 1023) // 1024), dtype=torch.int32, device=dev),
+             "ids_ws": None, "step": 0, "free_ev": [None] * self.N_SETS}
         if self.transport == "p2p":
             import torch.distributed._symmetric_memory as symm
-            rows_bytes, offs_bytes, part_bytes = W * K * 8, W * (B + 1) * 4, W * B * D * 4
-            offs_bytes = (offs_bytes + 15) // 16 * 16
-            total = rows_bytes + offs_bytes + part_bytes
-            raw = symm.empty(total, dtype=torch.uint8, device=dev)
+            rows_bytes = W * K * 8
+            offs_bytes = (W * (B + 1) * 4 + 15) // 16 * 16
+            set_bytes = rows_bytes + offs_bytes
+            part_off = self.N_SETS * set_bytes
+            raw = symm.empty(part_off + W * B * D * 4, dtype=torch.uint8, device=dev)
             hdl = symm.rendezvous(raw, self.group)
-            b.update(raw=raw, hdl=hdl, rows_off=0, offs_off=rows_bytes, part_off=rows_bytes + offs_bytes)
-            b["rows_recv"] = raw[:rows_bytes].view(torch.int64).view(W, K)
-            b["offs_recv"] = raw[rows_bytes:rows_bytes + W * (B + 1) * 4].view(torch.int32).view(W, B + 1)
-            b["partials"] = raw[rows_bytes + offs_bytes:].view(torch.float32).view(W, B, D)
-            b["peer_partials"] = [hdl.get_buffer(r, (W, B, D), torch.float32, (rows_bytes + offs_bytes) // 4)
-                                  for r in range(W)]
+            b.update(raw=raw, hdl=hdl, set_bytes=set_bytes, rows_bytes=rows_bytes, part_off=part_off)
+            b["rows_recv"] = [raw[j * set_bytes:j * set_bytes + rows_bytes].view(torch.int64).view(W, K)
+                              for j in range(self.N_SETS)]
+            b["offs_recv"] = [raw[j * set_bytes + rows_bytes:j * set_bytes + rows_bytes + W * (B + 1) * 4]
+                              .view(torch.int32).view(W, B + 1) for j in range(self.N_SETS)]
+            b["partials"] = raw[part_off:].view(torch.float32).view(W, B, D)
+            b["peer_partials"] = [hdl.get_buffer(r, (W, B, D), torch.float32, part_off // 4) for r in range(W)]
             b["peer_ptr"] = [int(p) for p in hdl.buffer_ptrs]
+            b["side"] = torch.cuda.Stream(device=dev)
         else:
             b["rows_send"] = torch.empty(W, K, dtype=torch.int64, device=dev)
-            b["rows_recv"] = torch.empty(W, K, dtype=torch.int64, device=dev)
             b["offs_send"] = torch.empty(W, B + 1, dtype=torch.int32, device=dev)
-            b["offs_recv"] = torch.empty(W, B + 1, dtype=torch.int32, device=dev)
+            b["offs_recv"] = [torch.empty(W, B + 1, dtype=torch.int32, device=dev)]
             b["part_send"] = torch.empty(W, B, D, dtype=torch.float32, device=dev)
             b["partials"] = torch.empty(W, B, D, dtype=torch.float32, device=dev)
         self._bufs = b
         return b
 
     # ---- forward ---------------------------------------------------------------------------------
-    def forward(self, keys, out=None):
-        """keys: StringColumn (dense [B, L] or jagged) or int64 [B, L] tensor, on this rank's device.
-        Every rank must call with the same batch size.  Returns [B, D] fp32."""
-        b = self._bufs or self._alloc()
-        W, D, me = self.world, self.output_dim, self.rank
+    def _describe(self, keys):
         if isinstance(keys, StringColumn):
             B, L, bag_offsets, n_keys = keys.shape[0], keys.shape[1], keys.bag_offsets, keys.n_items
         else:
@@ -175,53 +176,106 @@ class ShardedEmbeddingBag(torch.nn.Module):
             raise ValueError(f"batch {B} != max_batch {self.max_batch} the exchange buffers were sized for")
         if n_keys > self.max_keys:
             raise ValueError(f"{n_keys} keys exceed max_keys={self.max_keys}")
-        if out is None:
-            out = torch.empty(B, D, dtype=torch.float32, device=self.device)
-        self._tick("start")
-        fused_hash = isinstance(keys, StringColumn) and hasattr(self.ops, "route_keys")
-        if fused_hash:
-            if b.get("ids_ws") is None:
-                b["ids_ws"] = torch.empty(self.max_keys, dtype=torch.int64, device=self.device)
+        return B, L, bag_offsets, n_keys
 
-            def route(offs_dst, rows_dst):
-                self.ops.route_keys(keys, self.num_bins, self.mask_value, self.salt, b["ids_ws"], bag_offsets, L, B, W,
-                                    b["counts"], b["offs_local"], offs_dst, rows_dst)
+    def _route(self, keys, B, L, bag_offsets, offs_dst, rows_dst):
+        b, W = self._bufs, self.world
+        if isinstance(keys, StringColumn) and hasattr(self.ops, "route_keys"):      # hashing fused into routing
+            if b["ids_ws"] is None:
+                b["ids_ws"] = torch.empty(self.max_keys, dtype=torch.int64, device=self.device)
+            self.ops.route_keys(keys, self.num_bins, self.mask_value, self.salt, b["ids_ws"], bag_offsets, L, B, W,
+                                b["counts"], b["offs_local"], offs_dst, rows_dst)
         else:
             ids = self.ops.hash(keys, self.num_bins, self.mask_value, self.salt)
             self._tick("hash")
+            self.ops.route(ids, bag_offsets, L, B, W, b["counts"], b["offs_local"], offs_dst, rows_dst)
 
-            def route(offs_dst, rows_dst):
-                self.ops.route(ids, bag_offsets, L, B, W, b["counts"], b["offs_local"], offs_dst, rows_dst)
-        partial_op = "sum" if self.combiner == "avg" else self.combiner
-        est = max(1, n_keys // W)
-
-        if self.transport == "p2p":
-            K, hdl = self.max_keys, b["hdl"]
-            rows_dst = [b["peer_ptr"][g] + b["rows_off"] + me * K * 8 for g in range(W)]
-            offs_dst = [b["peer_ptr"][g] + b["offs_off"] + me * (B + 1) * 4 for g in range(W)]
-            route(offs_dst, rows_dst)
+    def prepare(self, keys, overlap=True):
+        """p2p transport: hash + route this rank's keys into the owners' receive buffers.  With
+        overlap=True it runs on a side stream, so it can proceed while the previous step's
+        gather+pool kernel is still running (the routing is latency-bound, the pooling HBM-bound).
+        Returns a ticket for finish()."""
+        if self.transport != "p2p":
+            raise ValueError("prepare()/finish() pipelining needs the p2p transport")
+        b = self._bufs or self._alloc()
+        B, L, bag_offsets, n_keys = self._describe(keys)
+        W, K, me = self.world, self.max_keys, self.rank
+        j = b["step"] % self.N_SETS
+        b["step"] += 1
+        base = [b["peer_ptr"][g] + j * b["set_bytes"] for g in range(W)]
+        rows_dst = [base[g] + me * K * 8 for g in range(W)]
+        offs_dst = [base[g] + b["rows_bytes"] + me * (B + 1) * 4 for g in range(W)]
+        cur = torch.cuda.current_stream(self.device)
+        stream = b["side"] if overlap else cur
+        if overlap:
+            stream.wait_stream(cur)                       # the keys were produced on the caller's stream
+        routed = None
+        with torch.cuda.stream(stream):
+            if overlap and b["free_ev"][j] is not None:
+                stream.wait_event(b["free_ev"][j])        # every owner is done pooling out of set j
+            self._tick("start")
+            self._route(keys, B, L, bag_offsets, offs_dst, rows_dst)
             self._tick("route")
-            hdl.barrier(channel=0)                       # every source's ids/offsets have landed here
-            self._tick("barrier0")
-            self.ops.pool(self.shard.data, [b["rows_recv"][s] for s in range(W)], [b["offs_recv"][s] for s in range(W)],
-                          [b["peer_partials"][s][me] for s in range(W)], B, partial_op, est)
-            self._tick("pool")
-            hdl.barrier(channel=1)                       # every owner's partials have landed here
-            self._tick("barrier1")
+            if overlap:
+                routed = torch.cuda.Event()
+                routed.record(stream)
+        return {"set": j, "routed": routed, "B": B, "L": L, "bag_offsets": bag_offsets, "n_keys": n_keys}
+
+    def finish(self, ticket, out=None):
+        """Barrier, fused gather+pool into the sources' buffers over NVLink, barrier, combine."""
+        b, W, D, me = self._bufs, self.world, self.output_dim, self.rank
+        B, L, bag_offsets, j = ticket["B"], ticket["L"], ticket["bag_offsets"], ticket["set"]
+        if out is None:
+            out = torch.empty(B, D, dtype=torch.float32, device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        if ticket["routed"] is not None:
+            cur.wait_event(ticket["routed"])
+        hdl = b["hdl"]
+        # all ranks: routing of this step has landed here AND the previous step's combine is over
+        hdl.barrier(channel=0)
+        self._tick("barrier0")
+        partial_op = "sum" if self.combiner == "avg" else self.combiner
+        self.ops.pool(self.shard.data, [b["rows_recv"][j][s] for s in range(W)], [b["offs_recv"][j][s] for s in range(W)],
+                      [b["peer_partials"][s][me] for s in range(W)], B, partial_op, max(1, ticket["n_keys"] // W))
+        self._tick("pool")
+        hdl.barrier(channel=1)                            # every owner's partials have landed here
+        self._tick("barrier1")
+        if torch.cuda.is_current_stream_capturing():
+            b["free_ev"][j] = None                        # a captured step is strictly stream-ordered
         else:
-            rows_dst = [b["rows_send"][g].data_ptr() for g in range(W)]
-            offs_dst = [b["offs_send"][g].data_ptr() for g in range(W)]
-            route(offs_dst, rows_dst)
-            dist.all_to_all_single(b["offs_recv"], b["offs_send"], group=self.group)
-            send_tot = b["offs_send"][:, B].tolist()     # host sync: NCCL needs the split sizes
-            recv_tot = b["offs_recv"][:, B].tolist()
-            send_flat = torch.cat([b["rows_send"][g, :send_tot[g]] for g in range(W)])
-            recv_flat = torch.empty(sum(recv_tot), dtype=torch.int64, device=self.device)
-            dist.all_to_all_single(recv_flat, send_flat, recv_tot, send_tot, group=self.group)
-            rows_in = list(torch.split(recv_flat, recv_tot))
-            self.ops.pool(self.shard.data, rows_in, [b["offs_recv"][s] for s in range(W)],
-                          [b["part_send"][s] for s in range(W)], B, partial_op, est)
-            dist.all_to_all_single(b["partials"], b["part_send"], group=self.group)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            b["free_ev"][j] = ev
+        self.ops.combine(b["partials"], W, B, D, self.combiner, L, bag_offsets, out)
+        self._tick("combine")
+        return out
+
+    def forward(self, keys, out=None):
+        """keys: StringColumn (dense [B, L] or jagged) or int64 [B, L] tensor, on this rank's device.
+        Every rank must call with the same batch size.  Returns [B, D] fp32."""
+        if self.transport == "p2p":
+            return self.finish(self.prepare(keys, overlap=False), out)
+        b = self._bufs or self._alloc()
+        B, L, bag_offsets, n_keys = self._describe(keys)
+        W, D = self.world, self.output_dim
+        if out is None:
+            out = torch.empty(B, D, dtype=torch.float32, device=self.device)
+        self._tick("start")
+        rows_dst = [b["rows_send"][g].data_ptr() for g in range(W)]
+        offs_dst = [b["offs_send"][g].data_ptr() for g in range(W)]
+        self._route(keys, B, L, bag_offsets, offs_dst, rows_dst)
+        offs_recv = b["offs_recv"][0]
+        dist.all_to_all_single(offs_recv, b["offs_send"], group=self.group)
+        send_tot = b["offs_send"][:, B].tolist()         # host sync: NCCL needs the split sizes
+        recv_tot = offs_recv[:, B].tolist()
+        send_flat = torch.cat([b["rows_send"][g, :send_tot[g]] for g in range(W)])
+        recv_flat = torch.empty(sum(recv_tot), dtype=torch.int64, device=self.device)
+        dist.all_to_all_single(recv_flat, send_flat, recv_tot, send_tot, group=self.group)
+        rows_in = list(torch.split(recv_flat, recv_tot))
+        partial_op = "sum" if self.combiner == "avg" else self.combiner
+        self.ops.pool(self.shard.data, rows_in, [offs_recv[s] for s in range(W)],
+                      [b["part_send"][s] for s in range(W)], B, partial_op, max(1, n_keys // W))
+        dist.all_to_all_single(b["partials"], b["part_send"], group=self.group)
         self.ops.combine(b["partials"], W, B, D, self.combiner, L, bag_offsets, out)
         self._tick("combine")
         return out

@@ -65,7 +65,6 @@ class OracleShardOps(object):
             counts = np.bincount(bag_of[sel], minlength=batch).astype(np.int32)
             offs = np.zeros(batch + 1, dtype=np.int32)
             offs[1:] = np.cumsum(counts)
-            offs_local.view(world, batch + 1)[g] = torch.from_numpy(offs)
             _write(offs_dst_ptrs[g], offs)
             _write(rows_dst_ptrs[g], (ids[sel] // world).astype(np.int64))     # stable: key order kept
 

@@ -109,6 +109,20 @@ def main():
             out = torch.empty(B, D, dtype=torch.float32, device=dev)
             ms = timed(lambda i: layer(batches[i % NB], out=out))
             results[tr] = ms
+            if tr == "p2p":
+                # steady-state pipelining: routing of step i+1 (side stream) overlaps pooling of step i
+                state = {"ticket": None}
+
+                def piped(i):
+                    if state["ticket"] is None:
+                        state["ticket"] = layer.prepare(batches[i % NB])
+                    nxt = layer.prepare(batches[(i + 1) % NB])
+                    layer.finish(state["ticket"], out=out)
+                    state["ticket"] = nxt
+                results["p2p_pipelined"] = timed(piped)
+                layer.finish(state["ticket"], out=out)          # drain
+                torch.cuda.synchronize()
+                results["p2p_pipelined_equals_eager"] = bool(torch.equal(out, layer(batches[(W + K) % NB]).clone()))
             if tr == "p2p" and args.graph:
                 # the p2p step has no host synchronisation, so the whole step (route kernels, symmetric-
                 # memory barriers, fused gather+pool into peer memory, combine) replays as one graph launch
