@@ -128,7 +128,7 @@ class ShardedEmbeddingBag(torch.nn.Module):
         self.shard = torch.nn.Parameter(mine.to(self.device), requires_grad=False)
 
     # ---- buffers ---------------------------------------------------------------------------------
-    N_SETS = 2      # receive-buffer sets: routing of step i+1 may overlap pooling of step i
+    N_SETS = 2      # buffer sets: route(i+1), pool(i) and the NVLink drain + combine of (i-1) overlap
 
     def _alloc(self):
         dev = self.device
@@ -139,30 +139,32 @@ class ShardedEmbeddingBag(torch.nn.Module):
         W, B, K, D = self.world, self.max_batch, self.max_keys, self.output_dim
         b = {"counts": torch.empty(W * B, dtype=torch.int32, device=dev),
              "offs_local": torch.empty(W * (B + 1 + (B + 1023) // 1024), dtype=torch.int32, device=dev),
-             "ids_ws": None, "step": 0, "free_ev": [None] * self.N_SETS}
+             "ids_ws": None, "step": 0, "rows_free": [None] * self.N_SETS, "combined": [None] * self.N_SETS}
         if self.transport == "p2p":
             import torch.distributed._symmetric_memory as symm
             rows_bytes = W * K * 8
             offs_bytes = (W * (B + 1) * 4 + 15) // 16 * 16
-            set_bytes = rows_bytes + offs_bytes
-            part_off = self.N_SETS * set_bytes
-            raw = symm.empty(part_off + W * B * D * 4, dtype=torch.uint8, device=dev)
+            part_bytes = W * B * D * 4
+            set_bytes = rows_bytes + offs_bytes + part_bytes
+            raw = symm.empty(self.N_SETS * set_bytes, dtype=torch.uint8, device=dev)
             hdl = symm.rendezvous(raw, self.group)
-            b.update(raw=raw, hdl=hdl, set_bytes=set_bytes, rows_bytes=rows_bytes, part_off=part_off)
-            b["rows_recv"] = [raw[j * set_bytes:j * set_bytes + rows_bytes].view(torch.int64).view(W, K)
-                              for j in range(self.N_SETS)]
-            b["offs_recv"] = [raw[j * set_bytes + rows_bytes:j * set_bytes + rows_bytes + W * (B + 1) * 4]
-                              .view(torch.int32).view(W, B + 1) for j in range(self.N_SETS)]
-            b["partials"] = raw[part_off:].view(torch.float32).view(W, B, D)
-            b["peer_partials"] = [hdl.get_buffer(r, (W, B, D), torch.float32, part_off // 4) for r in range(W)]
+            b.update(raw=raw, hdl=hdl, set_bytes=set_bytes, rows_bytes=rows_bytes)
+            b["rows_recv"], b["offs_recv"], b["partials"], b["peer_partials"] = [], [], [], []
+            for j in range(self.N_SETS):
+                o = j * set_bytes
+                b["rows_recv"].append(raw[o:o + rows_bytes].view(torch.int64).view(W, K))
+                b["offs_recv"].append(raw[o + rows_bytes:o + rows_bytes + W * (B + 1) * 4].view(torch.int32).view(W, B + 1))
+                po = o + rows_bytes + offs_bytes
+                b["partials"].append(raw[po:po + part_bytes].view(torch.float32).view(W, B, D))
+                b["peer_partials"].append([hdl.get_buffer(r, (W, B, D), torch.float32, po // 4) for r in range(W)])
             b["peer_ptr"] = [int(p) for p in hdl.buffer_ptrs]
-            b["side"] = torch.cuda.Stream(device=dev)
+            b["sR"], b["sP"], b["sC"] = (torch.cuda.Stream(device=dev) for _ in range(3))
         else:
             b["rows_send"] = torch.empty(W, K, dtype=torch.int64, device=dev)
             b["offs_send"] = torch.empty(W, B + 1, dtype=torch.int32, device=dev)
             b["offs_recv"] = [torch.empty(W, B + 1, dtype=torch.int32, device=dev)]
             b["part_send"] = torch.empty(W, B, D, dtype=torch.float32, device=dev)
-            b["partials"] = torch.empty(W, B, D, dtype=torch.float32, device=dev)
+            b["partials"] = [torch.empty(W, B, D, dtype=torch.float32, device=dev)]
         self._bufs = b
         return b
 
@@ -191,10 +193,12 @@ class ShardedEmbeddingBag(torch.nn.Module):
             self.ops.route(ids, bag_offsets, L, B, W, b["counts"], b["offs_local"], offs_dst, rows_dst)
 
     def prepare(self, keys, overlap=True):
-        """p2p transport: hash + route this rank's keys into the owners' receive buffers.  With
-        overlap=True it runs on a side stream, so it can proceed while the previous step's
-        gather+pool kernel is still running (the routing is latency-bound, the pooling HBM-bound).
-        Returns a ticket for finish()."""
+        """p2p transport, stage 1: hash + route this rank's keys into the owners' receive buffers.
+
+        With overlap=True the three stages of a step run on three streams -- route | fused gather+pool
+        into peer memory | NVLink drain + combine -- so that in a loop `t = prepare(next); finish(prev)`
+        the latency-bound routing of step i+1, the HBM-bound pooling of step i and the NVLink-bound
+        drain of step i-1 proceed concurrently (double-buffered exchange sets).  Returns a ticket."""
         if self.transport != "p2p":
             raise ValueError("prepare()/finish() pipelining needs the p2p transport")
         b = self._bufs or self._alloc()
@@ -206,48 +210,68 @@ class ShardedEmbeddingBag(torch.nn.Module):
         rows_dst = [base[g] + me * K * 8 for g in range(W)]
         offs_dst = [base[g] + b["rows_bytes"] + me * (B + 1) * 4 for g in range(W)]
         cur = torch.cuda.current_stream(self.device)
-        stream = b["side"] if overlap else cur
+        stream = b["sR"] if overlap else cur
+        routed = None
         if overlap:
             stream.wait_stream(cur)                       # the keys were produced on the caller's stream
-        routed = None
         with torch.cuda.stream(stream):
-            if overlap and b["free_ev"][j] is not None:
-                stream.wait_event(b["free_ev"][j])        # every owner is done pooling out of set j
+            if overlap and b["rows_free"][j] is not None:
+                stream.wait_event(b["rows_free"][j])      # every owner is done pooling out of set j
             self._tick("start")
             self._route(keys, B, L, bag_offsets, offs_dst, rows_dst)
             self._tick("route")
             if overlap:
                 routed = torch.cuda.Event()
                 routed.record(stream)
-        return {"set": j, "routed": routed, "B": B, "L": L, "bag_offsets": bag_offsets, "n_keys": n_keys}
+        return {"set": j, "routed": routed, "B": B, "L": L, "bag_offsets": bag_offsets, "n_keys": n_keys,
+                "overlap": overlap}
 
     def finish(self, ticket, out=None):
-        """Barrier, fused gather+pool into the sources' buffers over NVLink, barrier, combine."""
+        """Stages 2 and 3: barrier, fused gather+pool writing each pooled vector into the SOURCE rank's
+        buffer over NVLink, barrier (drain), combine.  The caller's stream waits for the result."""
         b, W, D, me = self._bufs, self.world, self.output_dim, self.rank
-        B, L, bag_offsets, j = ticket["B"], ticket["L"], ticket["bag_offsets"], ticket["set"]
+        B, L, bag_offsets, j, overlap = ticket["B"], ticket["L"], ticket["bag_offsets"], ticket["set"], ticket["overlap"]
         if out is None:
             out = torch.empty(B, D, dtype=torch.float32, device=self.device)
         cur = torch.cuda.current_stream(self.device)
-        if ticket["routed"] is not None:
-            cur.wait_event(ticket["routed"])
         hdl = b["hdl"]
-        # all ranks: routing of this step has landed here AND the previous step's combine is over
-        hdl.barrier(channel=0)
-        self._tick("barrier0")
+        sP = b["sP"] if overlap else cur
+        sC = b["sC"] if overlap else cur
         partial_op = "sum" if self.combiner == "avg" else self.combiner
-        self.ops.pool(self.shard.data, [b["rows_recv"][j][s] for s in range(W)], [b["offs_recv"][j][s] for s in range(W)],
-                      [b["peer_partials"][s][me] for s in range(W)], B, partial_op, max(1, ticket["n_keys"] // W))
-        self._tick("pool")
-        hdl.barrier(channel=1)                            # every owner's partials have landed here
-        self._tick("barrier1")
-        if torch.cuda.is_current_stream_capturing():
-            b["free_ev"][j] = None                        # a captured step is strictly stream-ordered
-        else:
-            ev = torch.cuda.Event()
-            ev.record(cur)
-            b["free_ev"][j] = ev
-        self.ops.combine(b["partials"], W, B, D, self.combiner, L, bag_offsets, out)
-        self._tick("combine")
+        with torch.cuda.stream(sP):
+            if overlap:
+                sP.wait_event(ticket["routed"])
+                if b["combined"][j] is not None:
+                    sP.wait_event(b["combined"][j])       # this rank consumed partial set j (two steps ago)
+            # after this barrier: every source's routing of this step has landed here, and every rank
+            # is past the combine that last read partial set j
+            hdl.barrier(channel=0)
+            self._tick("barrier0")
+            self.ops.pool(self.shard.data, [b["rows_recv"][j][s] for s in range(W)],
+                          [b["offs_recv"][j][s] for s in range(W)], [b["peer_partials"][j][s][me] for s in range(W)],
+                          B, partial_op, max(1, ticket["n_keys"] // W))
+            self._tick("pool")
+            pooled = None
+            if overlap:
+                pooled = torch.cuda.Event()
+                pooled.record(sP)
+        with torch.cuda.stream(sC):
+            if overlap:
+                sC.wait_event(pooled)
+                sC.wait_stream(cur)                       # `out` may still be read by the caller's stream
+            hdl.barrier(channel=1)                        # every owner's partials have landed (NVLink drained)
+            self._tick("barrier1")
+            if overlap:
+                ev = torch.cuda.Event()
+                ev.record(sC)
+                b["rows_free"][j] = ev
+            self.ops.combine(b["partials"][j], W, B, D, self.combiner, L, bag_offsets, out)
+            self._tick("combine")
+            if overlap:
+                done = torch.cuda.Event()
+                done.record(sC)
+                b["combined"][j] = done
+                cur.wait_event(done)
         return out
 
     def forward(self, keys, out=None):
@@ -275,7 +299,7 @@ class ShardedEmbeddingBag(torch.nn.Module):
         partial_op = "sum" if self.combiner == "avg" else self.combiner
         self.ops.pool(self.shard.data, rows_in, [offs_recv[s] for s in range(W)],
                       [b["part_send"][s] for s in range(W)], B, partial_op, max(1, n_keys // W))
-        dist.all_to_all_single(b["partials"], b["part_send"], group=self.group)
-        self.ops.combine(b["partials"], W, B, D, self.combiner, L, bag_offsets, out)
+        dist.all_to_all_single(b["partials"][0], b["part_send"], group=self.group)
+        self.ops.combine(b["partials"][0], W, B, D, self.combiner, L, bag_offsets, out)
         self._tick("combine")
         return out
