@@ -247,8 +247,11 @@ class ShardedEmbeddingBag(torch.nn.Module):
             # is past the combine that last read partial set j
             hdl.barrier(channel=0)
             self._tick("barrier0")
-            self.ops.pool(self.shard.data, [b["rows_recv"][j][s] for s in range(W)],
-                          [b["offs_recv"][j][s] for s in range(W)], [b["peer_partials"][j][s][me] for s in range(W)],
+            # sources in rotated order (me, me+1, ...): at any moment the W owners write their pooled
+            # vectors to W different ranks -- a permutation, not an incast on one rank's NVLink port
+            order = [(me + k) % W for k in range(W)]
+            self.ops.pool(self.shard.data, [b["rows_recv"][j][s] for s in order],
+                          [b["offs_recv"][j][s] for s in order], [b["peer_partials"][j][s][me] for s in order],
                           B, partial_op, max(1, ticket["n_keys"] // W))
             self._tick("pool")
             pooled = None
