@@ -18,6 +18,7 @@
 // Everything here is integer routing and streaming adds: HBM / NVLink bound, no tensor cores.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(1024) shard_chunk_base_kernel(int32_t *__restr
 // One warp per bag: key k of bag b owned by g goes to rows_dst[g][offs[g][b] + (rank of k among the
 // bag's keys owned by g)] as the owner-local row id / world.  Order inside (owner, bag) is kept.
 // offs[g][b] = chunk base + excl[g][b]; lane g also publishes it as the owner's CSR (offs_dst[g][b]).
-__global__ void __launch_bounds__(256) shard_scatter_kernel(const int64_t *__restrict__ ids, const int32_t *__restrict__ boffs,
+__global__ void __launch_bounds__(256) shard_scatter_warp_kernel(const int64_t *__restrict__ ids, const int32_t *__restrict__ boffs,
                                                             int bag_len, int64_t batch, int world, int n_chunks,
                                                             const int32_t *__restrict__ excl,
                                                             const int32_t *__restrict__ chunk_tot, PtrTable offs_dst,
@@ -196,6 +197,108 @@ __global__ void __launch_bounds__(256) shard_scatter_kernel(const int64_t *__res
                 if (lane == g) next += __popc(m);
             }
             if (on) static_cast<int64_t *>(rows_dst.p[owner])[pos] = (int64_t)row;
+        }
+    }
+}
+
+// Scatter, tiled: a CTA takes a run of consecutive bags.  Because every owner's CSR is in bag order,
+// the tile's keys for owner g form ONE contiguous range of g's receive buffer; the CTA assembles
+// the W ranges in shared memory (warp per bag, ballot ranks keep key order) and then streams each
+// range out with fully coalesced stores -- long contiguous writes are what NVLink moves
+// efficiently (8-byte scattered remote stores cost 2x the whole routing pass at 8 GPUs).
+// The owners' CSR entries of the tile's bags are written the same way.
+constexpr int kScatCap = 4096;     // keys staged per round
+constexpr int kScatThreads = 256;
+
+__device__ __forceinline__ int owner_offset(const int32_t *excl, const int32_t *chunk_tot, const int32_t *counts, int g,
+                                            int64_t b, int64_t batch, int n_chunks) {
+    if (b < batch) return chunk_tot[(int64_t)g * n_chunks + (int)(b / kScanChunk)] + excl[(int64_t)g * batch + b];
+    const int64_t l = batch - 1;
+    return chunk_tot[(int64_t)g * n_chunks + (int)(l / kScanChunk)] + excl[(int64_t)g * batch + l] + counts[(int64_t)g * batch + l];
+}
+
+__global__ void __launch_bounds__(kScatThreads) shard_scatter_kernel(const int64_t *__restrict__ ids,
+                                                                     const int32_t *__restrict__ boffs, int bag_len,
+                                                                     int64_t batch, int world, int n_chunks, int tile_bags,
+                                                                     const int32_t *__restrict__ excl,
+                                                                     const int32_t *__restrict__ chunk_tot,
+                                                                     const int32_t *__restrict__ counts, PtrTable offs_dst,
+                                                                     PtrTable rows_dst) {
+    __shared__ uint32_t srow[kScatCap];
+    __shared__ int seg_first[kMaxWorld], seg_len[kMaxWorld], seg_base[kMaxWorld + 1];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const int64_t n_tiles = (batch + tile_bags - 1) / tile_bags;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t t0 = tile * tile_bags, t1 = min(batch, t0 + tile_bags);
+        int64_t r0 = t0;
+        while (r0 < t1) {
+            // ---- carve a round [r0, r1) of whole bags with <= kScatCap keys (uniform across the CTA) ----
+            int64_t k0, dummy;
+            bag_range(boffs, bag_len, r0, k0, dummy);
+            int64_t r1 = r0;
+            int64_t k1 = k0;
+            while (r1 < t1) {
+                int64_t lo, hi;
+                bag_range(boffs, bag_len, r1, lo, hi);
+                if (hi - k0 > kScatCap && r1 > r0) break;
+                k1 = hi;
+                ++r1;
+                if (hi - k0 > kScatCap) break;      // a single oversized bag: handled unstaged below
+            }
+            const bool staged = k1 - k0 <= kScatCap;
+            if (tid < world) {
+                seg_first[tid] = owner_offset(excl, chunk_tot, counts, tid, r0, batch, n_chunks);
+                seg_len[tid] = owner_offset(excl, chunk_tot, counts, tid, r1, batch, n_chunks) - seg_first[tid];
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int acc = 0;
+                for (int g = 0; g < world; ++g) {
+                    seg_base[g] = acc;
+                    acc += seg_len[g];
+                }
+                seg_base[world] = acc;
+            }
+            __syncthreads();
+            // ---- warp per bag: rank every key inside its (owner, bag) run ----
+            for (int64_t b = r0 + wid; b < r1; b += kScatThreads / 32) {
+                int64_t lo, hi;
+                bag_range(boffs, bag_len, b, lo, hi);
+                int next = lane < world ? owner_offset(excl, chunk_tot, counts, lane, b, batch, n_chunks) : 0;
+                for (int64_t i = lo; i < hi; i += 32) {
+                    const bool on = i + lane < hi;
+                    const uint32_t id = on ? (uint32_t)ids[i + lane] : 0u;
+                    const uint32_t row = id / (uint32_t)world;
+                    const int owner = on ? (int)(id - row * (uint32_t)world) : -1;
+                    int pos = 0;
+                    for (int g = 0; g < world; ++g) {
+                        const unsigned m = __ballot_sync(0xffffffffu, owner == g);
+                        const int base = __shfl_sync(0xffffffffu, next, g);
+                        if (owner == g) pos = base + __popc(m & lt);
+                        if (lane == g) next += __popc(m);
+                    }
+                    if (on) {
+                        if (staged) srow[seg_base[owner] + (pos - seg_first[owner])] = row;
+                        else static_cast<int64_t *>(rows_dst.p[owner])[pos] = (int64_t)row;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- stream the W contiguous ranges (and the CSR entries) out, coalesced ----
+            for (int g = 0; g < world; ++g) {
+                if (staged) {
+                    int64_t *dst = static_cast<int64_t *>(rows_dst.p[g]) + seg_first[g];
+                    const uint32_t *src = srow + seg_base[g];
+                    for (int i = tid; i < seg_len[g]; i += kScatThreads) dst[i] = (int64_t)src[i];
+                }
+                int32_t *od = static_cast<int32_t *>(offs_dst.p[g]);
+                if (od)
+                    for (int64_t bb = r0 + tid; bb < r1; bb += kScatThreads)
+                        od[bb] = owner_offset(excl, chunk_tot, counts, g, bb, batch, n_chunks);
+            }
+            __syncthreads();
+            r0 = r1;
         }
     }
 }
@@ -297,8 +400,20 @@ static int route_impl(const int64_t *d_ids, const uint8_t *d_bytes, const int32_
     int32_t *chunk_tot = d_offsets_local + (int64_t)world * batch;   // [world][n_chunks]
     shard_scan_kernel<<<dim3(n_chunks, world), kScanChunk, 0, st>>>(d_counts_ws, batch, n_chunks, excl, chunk_tot);
     shard_chunk_base_kernel<<<world, 1024, 0, st>>>(chunk_tot, n_chunks, batch, offs);
-    shard_scatter_kernel<<<grid, 256, 0, st>>>(spec ? d_ids_ws : d_ids, d_bag_offsets, bag_len, batch, world, n_chunks,
-                                               excl, chunk_tot, offs, rows);
+    // scatter tiles: ~kScatCap keys of consecutive bags per CTA round (the mean bag length is only
+    // known on the device in jagged mode: size tiles for 128 keys/bag there, rounds adapt)
+    const int64_t per_bag = d_bag_offsets ? 128 : (bag_len > 0 ? bag_len : 1);
+    int64_t tile_bags = kScatCap / per_bag;
+    if (tile_bags < 8) tile_bags = 8;
+    if (tile_bags > 512) tile_bags = 512;
+    const int sgrid = grid_for((batch + tile_bags - 1) / tile_bags, 1, sms);
+    static const bool tiled = !(getenv("RF_SCATTER_TILED") && atoi(getenv("RF_SCATTER_TILED")) == 0);
+    if (tiled)
+        shard_scatter_kernel<<<sgrid, kScatThreads, 0, st>>>(spec ? d_ids_ws : d_ids, d_bag_offsets, bag_len, batch, world,
+                                                             n_chunks, (int)tile_bags, excl, chunk_tot, d_counts_ws, offs, rows);
+    else
+        shard_scatter_warp_kernel<<<grid, 256, 0, st>>>(spec ? d_ids_ws : d_ids, d_bag_offsets, bag_len, batch, world,
+                                                        n_chunks, excl, chunk_tot, offs, rows);
     RF_CUDA(cudaGetLastError());
     g_launches.fetch_add(4);
     return RF_OK;

@@ -158,7 +158,11 @@ class ShardedEmbeddingBag(torch.nn.Module):
                 b["partials"].append(raw[po:po + part_bytes].view(torch.float32).view(W, B, D))
                 b["peer_partials"].append([hdl.get_buffer(r, (W, B, D), torch.float32, po // 4) for r in range(W)])
             b["peer_ptr"] = [int(p) for p in hdl.buffer_ptrs]
-            b["sR"], b["sP"], b["sC"] = (torch.cuda.Stream(device=dev) for _ in range(3))
+            # routing and combine are short, latency-bound kernels: give their streams priority so their
+            # CTAs slot in between the CTAs of the long HBM-bound pooling kernel instead of queueing behind it
+            b["sR"] = torch.cuda.Stream(device=dev, priority=-1)
+            b["sP"] = torch.cuda.Stream(device=dev, priority=0)
+            b["sC"] = torch.cuda.Stream(device=dev, priority=-1)
         else:
             b["rows_send"] = torch.empty(W, K, dtype=torch.int64, device=dev)
             b["offs_send"] = torch.empty(W, B + 1, dtype=torch.int32, device=dev)
