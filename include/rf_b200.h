@@ -109,6 +109,28 @@ int rf_hash_int64(const int64_t *d_values, int64_t n_items, int64_t num_bins, in
 /* (backend/utils/preprocess_utils.py:7-20).                                                   */
 int rf_bag_forward(const rf_field_desc *fields, int n_fields, int64_t batch, void *stream);
 
+/* ---- scaled_dot_product_attention (backend/layers/layer_utils.py:4-24), exact fp32 ------------ */
+/* q, k, v, out: device [n_batch_heads, seq_len, head_dim] fp32; mask: device [n_batch_heads,    */
+/* seq_len] fp32 or NULL.  mask[i] == 0 fills QUERY row i of the logits with -4294967295 (the    */
+/* reference's [..., S, 1] mask broadcasts over keys); scale 1/sqrt(head_dim); softmax over keys. */
+int rf_sdpa_forward(const float *d_q, const float *d_k, const float *d_v, const float *d_mask,
+                    int64_t n_batch_heads, int32_t seq_len, int32_t head_dim, float *d_out, void *stream);
+
+/* ---- in-batch two-tower logits S = query . doc^T, reduced per row without ever storing S ------ */
+/* (backend/lossess/match_losses.py:119-226 all start from tf.matmul(query, tf.transpose(doc))).   */
+/* Per row i (any output pointer may be NULL):                                                     */
+/*   lse[i]    = log sum_j exp(scale * S_ij)       diag[i] = S_ii                                 */
+/*   hinge[i]  = sum_j clip(S_ij - S_ii + margin, 0, 1e14) * (col_weight ? col_weight[j] : 1)      */
+/*   maxoff[i] = max_j (j == i ? 0 : S_ij)                                                         */
+/*   *loss     = mean_i( -(scale * S_ii - lse[i]) * y[i] )   = batch_neg_sample_scaled_multi_class */
+/*               _ce_loss (:150-165), evaluated with max-subtraction (same value, no overflow).    */
+/* d_workspace: rf_inbatch_workspace_bytes(batch) bytes of device scratch.                        */
+int64_t rf_inbatch_workspace_bytes(int64_t batch);
+int rf_inbatch_rowstats(const float *d_query, const float *d_doc, const float *d_y, const float *d_col_weight,
+                        int64_t batch, int32_t dim, float scale, float margin, void *d_workspace,
+                        float *d_lse, float *d_diag, float *d_hinge, float *d_maxoff, float *d_loss,
+                        void *stream);
+
 /* ---- row-sharded tables (new design; the reference only replicates tables,   */
 /* backend/utils/gpu_utils.py:13-14).  Row id lives on rank id % world as local row id / world. */
 /* rf_shard_route partitions the hashed ids of one field by owner, keeping bag order: for every */

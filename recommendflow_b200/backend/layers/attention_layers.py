@@ -1,0 +1,108 @@
+"""`MultiHeadAttention` and `SelfAttention` with the reference's constructor and call surface
+(/root/reference/backend/layers/attention_layers.py:137-168 and :83-134).
+
+The attention core runs in rf_sdpa_forward (hand-written CUDA); the Dense q/k/v projections are
+plain library GEMMs (cuBLAS through torch.nn.functional.linear), as the task allows.  Keras
+`Dense` defaults are kept: glorot-uniform kernel, zero bias, no activation, no output projection.
+"""
+import math
+
+import numpy as np
+import torch
+
+from .layer_utils import scaled_dot_product_attention, split_heads
+from .preprocess_layers import Layer
+
+
+class Dense(Layer):
+    """Keras Dense(units, activation=None): y = x W + b, W: [in, units] built on first call."""
+
+    def __init__(self, units, activation=None, name=None):
+        super().__init__(name=name)
+        self.units, self.activation = units, activation
+        self.kernel = self.bias = None
+
+    def build(self, in_dim, device):
+        if self.kernel is None:
+            limit = math.sqrt(6.0 / (in_dim + self.units))          # glorot_uniform
+            self.kernel = torch.nn.Parameter(torch.empty(in_dim, self.units, device=device).uniform_(-limit, limit),
+                                             requires_grad=False)
+            self.bias = torch.nn.Parameter(torch.zeros(self.units, device=device), requires_grad=False)
+        return self
+
+    def set_weights(self, weights):
+        k, b = weights
+        k = torch.as_tensor(np.asarray(k), dtype=torch.float32)
+        dev = self.kernel.device if self.kernel is not None else torch.device("cuda", torch.cuda.current_device())
+        self.kernel = torch.nn.Parameter(k.to(dev), requires_grad=False)
+        self.bias = torch.nn.Parameter(torch.as_tensor(np.asarray(b), dtype=torch.float32).to(dev), requires_grad=False)
+        self.units = k.shape[1]
+
+    def get_weights(self):
+        return [self.kernel.detach().cpu().numpy(), self.bias.detach().cpu().numpy()]
+
+    def call(self, x):
+        self.build(x.shape[-1], x.device)
+        y = torch.matmul(x, self.kernel) + self.bias
+        return torch.relu(y) if self.activation == "relu" else y
+
+
+class MultiHeadAttention(Layer):
+    def __init__(self, d_model, num_heads):
+        super().__init__(name="multi_head_attention")
+        self.d_model = d_model
+        self.num_heads = num_heads
+        self.wq = Dense(d_model, activation=None)
+        self.wk = Dense(d_model, activation=None)
+        self.wv = Dense(d_model, activation=None)
+
+    def call(self, q, k, v, mask):
+        q, k, v = self.wq(q), self.wk(k), self.wv(v)                       # (B, S, d_model)
+        seq_len, d_model = q.shape[1], q.shape[2]
+        depth = d_model // self.num_heads
+        q = split_heads(q, seq_len, self.num_heads, depth)                 # (B, H, S, depth)
+        k = split_heads(k, seq_len, self.num_heads, depth)
+        v = split_heads(v, seq_len, self.num_heads, depth)
+        mask = mask.unsqueeze(1).expand(-1, self.num_heads, -1, -1)        # (B, H, S, 1)
+        att = scaled_dot_product_attention(q, k, v, mask)                  # (B, H, S, depth)
+        return att.permute(0, 2, 1, 3).reshape(-1, seq_len, d_model)       # no output projection (as the reference)
+
+    def forward(self, q, k, v, mask):
+        return self.call(q, k, v, mask)
+
+
+class SelfAttention(Layer):
+    """Shared-weight relu projections, sinusoidal positions, key... QUERY-row mask, mean over the sequence."""
+
+    def __init__(self, add_pos=True):
+        super().__init__(name="self_attention")
+        self.add_pos = add_pos
+        self.W = None
+
+    def build(self, dim, device):
+        if self.W is None:
+            self.dim = dim
+            self.W = torch.nn.Parameter(torch.empty(dim, dim, device=device).normal_(0.0, 0.05), requires_grad=False)
+        return self
+
+    @staticmethod
+    def get_angles(pos, i, d_model):
+        return pos * (1 / np.power(10000, (2 * (i // 2)) / np.float32(d_model)))
+
+    def positional_encoding(self, qk):
+        ang = self.get_angles(np.arange(qk.shape[1])[:, np.newaxis], np.arange(self.dim)[np.newaxis, :], self.dim)
+        ang[:, 0::2] = np.sin(ang[:, 0::2])
+        ang[:, 1::2] = np.cos(ang[:, 1::2])
+        return torch.as_tensor(ang[np.newaxis, ...], dtype=torch.float32, device=qk.device)
+
+    def call(self, inputs, **kwargs):
+        q, k, v, mask = inputs
+        self.build(q.shape[-1], q.device)
+        if self.add_pos:
+            k = k + self.positional_encoding(k)
+            q = q + self.positional_encoding(q)
+        q = torch.relu(torch.matmul(q, self.W))
+        k = torch.relu(torch.matmul(k, self.W))
+        # the reference scales by sqrt(self.dim) == sqrt(k.shape[-1]) and tiles the [B, S, 1] mask over keys
+        out = scaled_dot_product_attention(q, k, v, mask)
+        return out.mean(dim=1)

@@ -1,0 +1,124 @@
+"""SDPA, MultiHeadAttention and the in-batch two-tower losses (CUDA, through the C-ABI) vs the oracle.
+
+Floating point: the kernels accumulate in fp32, the oracle in float64.  Tolerances (stated per test)
+cover fp32 rounding of length-D dot products: |err| <~ D * 2^-24 * |q||k| on a logit, times the
+temperature (20) inside the exponent for the losses."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from recommendflow_b200.backend.layers.attention_layers import MultiHeadAttention, SelfAttention
+from recommendflow_b200.backend.layers.layer_utils import scaled_dot_product_attention, split_heads
+from recommendflow_b200.backend.lossess import match_losses, match_zipped_losses
+from recommendflow_b200.dense_ops import inbatch_rowstats
+from recommendflow_b200.utils.str_parser import str2loss
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("shape", [(7, 50, 64), (3, 4, 50, 16), (2, 1, 1), (5, 2, 33, 8), (4, 200, 32), (16, 50, 128)])
+def test_sdpa_matches_oracle(shape):
+    rng = np.random.default_rng(sum(shape))
+    q, k, v = (rng.standard_normal(shape).astype(np.float32) for _ in range(3))
+    mask = (rng.uniform(size=shape[:-1] + (1,)) > 0.3).astype(np.float32)
+    mask[0, ..., :, :] = 0                                   # a fully masked sequence -> uniform attention
+    want = oracle.sdpa(q, k, v, mask)
+    got = scaled_dot_product_attention(*(torch.from_numpy(x).cuda() for x in (q, k, v, mask))).cpu().numpy()
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-6)           # fp32 vs float64 accumulation
+    no_mask = scaled_dot_product_attention(*(torch.from_numpy(x).cuda() for x in (q, k, v)), None).cpu().numpy()
+    np.testing.assert_allclose(no_mask, oracle.sdpa(q, k, v, None), rtol=2e-5, atol=2e-6)
+    # masked query rows attend uniformly: output = mean over keys of v
+    np.testing.assert_allclose(got[0], np.broadcast_to(v[0].mean(axis=-2, keepdims=True), v[0].shape), rtol=1e-5, atol=1e-6)
+
+
+def test_multi_head_attention_layer_matches_reference_semantics():
+    rng = np.random.default_rng(9)
+    B, S, d_model, H = 6, 50, 64, 4
+    x = rng.standard_normal((B, S, d_model)).astype(np.float32)
+    mask = (np.arange(S)[None, :, None] < rng.integers(1, S + 1, size=(B, 1, 1))).astype(np.float32)
+    layer = MultiHeadAttention(d_model, H)
+    ws = []
+    for dense in (layer.wq, layer.wk, layer.wv):
+        w = (rng.standard_normal((d_model, d_model)) * 0.1).astype(np.float32)
+        b = (rng.standard_normal(d_model) * 0.1).astype(np.float32)
+        dense.set_weights([w, b])
+        ws.append((w, b))
+    xt, mt = torch.from_numpy(x).cuda(), torch.from_numpy(mask).cuda()
+    got = layer(xt, xt, xt, mt).cpu().numpy()
+    proj = [(x.astype(np.float64) @ w + b).astype(np.float32) for w, b in ws]
+    heads = [p.reshape(B, S, H, d_model // H).transpose(0, 2, 1, 3) for p in proj]
+    att = oracle.sdpa(*heads, np.broadcast_to(mask[:, None], (B, H, S, 1)))
+    want = att.transpose(0, 2, 1, 3).reshape(B, S, d_model)
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5)          # + fp32 cuBLAS projections
+    assert split_heads(xt, S, H, d_model // H).shape == (B, H, S, d_model // H)
+    sa = SelfAttention(add_pos=True)
+    assert sa([xt, xt, xt, mt]).shape == (B, d_model)
+
+
+def _pairs(rng, B, D):
+    q = rng.standard_normal((B, D)).astype(np.float32)
+    d = (0.7 * q + 0.7 * rng.standard_normal((B, D))).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    y = (rng.uniform(size=B) > 0.2).astype(np.float32)
+    return q, d, y
+
+
+@pytest.mark.parametrize("B,D", [(1000, 256), (64, 16), (777, 100), (129, 8), (4096, 256)])
+def test_scaled_inbatch_softmax_loss_matches_oracle(B, D):
+    rng = np.random.default_rng(B + D)
+    q, d, y = _pairs(rng, B, D)
+    want, lse, diag = oracle.inbatch_softmax_ce(y, q, d, 20.0)
+    qt, dt, yt = (torch.from_numpy(a).cuda() for a in (q, d, y))
+    got = match_losses.batch_neg_sample_scaled_multi_class_ce_loss(yt, qt, dt)
+    r = inbatch_rowstats(qt, dt, scale=20.0, want=("lse", "diag"))
+    # |S| <= 1, fp32 dot of <= 256 terms: ~1e-6 on a logit, x 20 in the exponent
+    np.testing.assert_allclose(r["diag"].cpu().numpy(), diag, atol=2e-6)
+    np.testing.assert_allclose(r["lse"].cpu().numpy(), lse, atol=1e-4)
+    assert abs(float(got) - want) <= 1e-4
+    z = match_zipped_losses.batch_neg_sample_scaled_multi_class_ce_loss(
+        yt[:, None], match_zipped_losses.zip_embedding(qt * 3.0, dt * 0.5))       # wrapper re-normalises
+    assert abs(float(z) - want) <= 1e-4
+    sym = match_losses.batch_neg_sample_symmetrical_scaled_multi_class_ce_loss(yt, qt, dt, scale=3)
+    want_sym, _, _ = oracle.inbatch_softmax_ce(y, q, d, 9.0)             # reference applies `scale` twice
+    assert abs(float(sym) - want_sym) <= 1e-4
+
+
+def test_margin_rank_losses_match_numpy():
+    rng = np.random.default_rng(21)
+    B, D = 513, 64
+    q, d, y = _pairs(rng, B, D)
+    S = q.astype(np.float64) @ d.astype(np.float64).T
+    qt, dt, yt = (torch.from_numpy(a).cuda() for a in (q, d, y))
+    want = (np.clip(-(np.diag(S)[:, None] - S) + 0.1, 0, 1e14) * y[None, :]).sum()      # y broadcasts over columns
+    got = float(match_losses.batch_neg_sample_margin_rank_loss(yt, qt, dt, margin=0.1))
+    assert abs(got - want) <= 1e-3 * max(1.0, abs(want))
+    neg = (S - np.diag(np.diag(S))).max(axis=-1)
+    want_h = (np.clip(-(np.diag(S) - neg) + 0.1, 0, 1e14) * y).sum()
+    got_h = float(match_losses.batch_hard_neg_sample_margin_rank_loss(yt, qt, dt, margin=0.1))
+    assert abs(got_h - want_h) <= 1e-4 * max(1.0, abs(want_h))
+    mse = float(match_losses.mean_squared_error(yt, qt, dt))
+    assert abs(mse - np.mean((y - np.diag(S)) ** 2)) <= 1e-5
+
+
+def test_loss_lookup_by_dotted_name_and_initials():
+    f = str2loss("backend.losses.match_losses.bnssmccl")
+    assert f is match_losses.batch_neg_sample_scaled_multi_class_ce_loss
+    assert str2loss("backend.lossess.match_losses.cosent_loss") is match_losses.cosent_loss
+
+
+def test_full_size_logits_properties():
+    # C3 size: B = 8192, Dt = 256.  Property: with doc == query (unit rows) S_ii = 1 is each row's max, so
+    # lse_i >= 20 and the loss is >= 0; swapping two docs changes exactly the losses of those rows.
+    torch.manual_seed(0)
+    B, D = 8192, 256
+    q = torch.nn.functional.normalize(torch.randn(B, D, device="cuda"), dim=1)
+    y = torch.ones(B, device="cuda")
+    r = inbatch_rowstats(q, q, y_true=y, scale=20.0, want=("lse", "diag"))
+    assert torch.allclose(r["diag"], torch.ones(B, device="cuda"), atol=1e-5)
+    assert float(r["lse"].min()) >= 20.0 - 1e-4 and float(r["loss"]) >= 0
+    rows = torch.randint(0, B, (256,), device="cuda")
+    ref = torch.logsumexp(20.0 * (q[rows].double() @ q.double().T), dim=1)
+    assert torch.allclose(r["lse"][rows].double(), ref, atol=1e-4)
