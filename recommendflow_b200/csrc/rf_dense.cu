@@ -192,55 +192,63 @@ __global__ void __launch_bounds__(1024) inbatch_finalize_kernel(const RowStat *_
 // [..., S, 1] mask broadcasts over keys: mask[i] == 0 replaces the whole QUERY row i of the logits
 // by -4294967295 -> uniform attention).  One CTA per (batch x head); everything in shared memory.
 // ------------------------------------------------------------------------------------------
+constexpr int kSdpaRows = 32;     // query rows per pass: the S x S score matrix never has to fit at once
+
 __global__ void __launch_bounds__(128) sdpa_kernel(const float *__restrict__ q, const float *__restrict__ k,
                                                    const float *__restrict__ v, const float *__restrict__ mask, int S, int dh,
                                                    float inv_sqrt_dk, float *__restrict__ out) {
     extern __shared__ float sm[];
     const int dp = dh + 1;                      // padded row stride: conflict-free column walks
+    const int sp = S + 1;
     float *ks = sm;                             // [S][dp]
     float *vs = ks + S * dp;                    // [S][dp]
-    float *qs = vs + S * dp;                    // [S][dp]
-    float *ps = qs + S * dp;                    // [S][S + 1]
-    const int sp = S + 1;
+    float *qs = vs + S * dp;                    // [kSdpaRows][dp]
+    float *ps = qs + kSdpaRows * dp;            // [kSdpaRows][sp]
     const size_t base = (size_t)blockIdx.x * S * dh;
     for (int e = threadIdx.x; e < S * dh; e += blockDim.x) {
         const int r = e / dh, c = e - r * dh;
         ks[r * dp + c] = k[base + e];
         vs[r * dp + c] = v[base + e];
-        qs[r * dp + c] = q[base + e];
     }
-    __syncthreads();
-    for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
-        const int i = e / S, j = e - i * S;
-        float acc = 0.f;
-        for (int c = 0; c < dh; ++c) acc = fmaf(qs[i * dp + c], ks[j * dp + c], acc);
-        float logit = acc * inv_sqrt_dk;
-        if (mask && mask[(size_t)blockIdx.x * S + i] == 0.f) logit = -4294967295.0f;
-        ps[i * sp + j] = logit;
-    }
-    __syncthreads();
-    // softmax per row: one warp per row
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warp = blockDim.x >> 5;
-    for (int i = warp; i < S; i += n_warp) {
-        float mx = -INFINITY;
-        for (int j = lane; j < S; j += 32) mx = fmaxf(mx, ps[i * sp + j]);
-        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        float sum = 0.f;
-        for (int j = lane; j < S; j += 32) {
-            const float p = expf(ps[i * sp + j] - mx);
-            ps[i * sp + j] = p;
-            sum += p;
+    for (int i0 = 0; i0 < S; i0 += kSdpaRows) {
+        const int rows = min(kSdpaRows, S - i0);
+        __syncthreads();                        // K/V staged; previous pass's qs/ps consumed
+        for (int e = threadIdx.x; e < rows * dh; e += blockDim.x) {
+            const int r = e / dh, c = e - r * dh;
+            qs[r * dp + c] = q[base + (size_t)(i0 + r) * dh + c];
         }
-        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        const float inv = 1.f / sum;
-        for (int j = lane; j < S; j += 32) ps[i * sp + j] *= inv;
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < S * dh; e += blockDim.x) {
-        const int i = e / dh, c = e - i * dh;
-        float acc = 0.f;
-        for (int j = 0; j < S; ++j) acc = fmaf(ps[i * sp + j], vs[j * dp + c], acc);
-        out[base + e] = acc;
+        __syncthreads();
+        for (int e = threadIdx.x; e < rows * S; e += blockDim.x) {
+            const int i = e / S, j = e - i * S;
+            float acc = 0.f;
+            for (int c = 0; c < dh; ++c) acc = fmaf(qs[i * dp + c], ks[j * dp + c], acc);
+            float logit = acc * inv_sqrt_dk;
+            if (mask && mask[(size_t)blockIdx.x * S + i0 + i] == 0.f) logit = -4294967295.0f;
+            ps[i * sp + j] = logit;
+        }
+        __syncthreads();
+        for (int i = warp; i < rows; i += n_warp) {          // softmax per row: one warp per row
+            float mx = -INFINITY;
+            for (int j = lane; j < S; j += 32) mx = fmaxf(mx, ps[i * sp + j]);
+            for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            float sum = 0.f;
+            for (int j = lane; j < S; j += 32) {
+                const float p = expf(ps[i * sp + j] - mx);
+                ps[i * sp + j] = p;
+                sum += p;
+            }
+            for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float inv = 1.f / sum;
+            for (int j = lane; j < S; j += 32) ps[i * sp + j] *= inv;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < rows * dh; e += blockDim.x) {
+            const int i = e / dh, c = e - i * dh;
+            float acc = 0.f;
+            for (int j = 0; j < S; ++j) acc = fmaf(ps[i * sp + j], vs[j * dp + c], acc);
+            out[base + (size_t)(i0 + i) * dh + c] = acc;
+        }
     }
 }
 
@@ -255,7 +263,7 @@ int rf_sdpa_forward(const float *d_q, const float *d_k, const float *d_v, const 
     if (n_batch_heads < 0 || seq_len <= 0 || head_dim <= 0) return set_error(RF_ERR_INVALID, "bad SDPA shape");
     if (n_batch_heads == 0) return RF_OK;
     if (!d_q || !d_k || !d_v || !d_out) return set_error(RF_ERR_INVALID, "rf_sdpa_forward: NULL buffer");
-    const size_t smem = sizeof(float) * ((size_t)3 * seq_len * (head_dim + 1) + (size_t)seq_len * (seq_len + 1));
+    const size_t smem = sizeof(float) * ((size_t)(2 * seq_len + kSdpaRows) * (head_dim + 1) + (size_t)kSdpaRows * (seq_len + 1));
     if (smem > 200 * 1024) return set_error(RF_ERR_UNSUPPORTED, "SDPA tile (S=%d, dh=%d) exceeds shared memory", seq_len, head_dim);
     if (n_batch_heads > INT32_MAX) return set_error(RF_ERR_INVALID, "too many batch x heads");
     RF_CUDA(cudaFuncSetAttribute(sdpa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
