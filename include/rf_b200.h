@@ -131,6 +131,17 @@ int rf_inbatch_rowstats(const float *d_query, const float *d_doc, const float *d
                         float *d_lse, float *d_diag, float *d_hinge, float *d_maxoff, float *d_loss,
                         void *stream);
 
+/* Same contract on the tensor cores: tcgen05.mma kind::tf32 (fp32 operands read as TF32, fp32   */
+/* accumulators in TMEM, TMA-fed 128x256x32 tiles, reductions fused into the TMEM epilogue).     */
+/* Operands are first rounded to nearest TF32 (unbiased) into the workspace; the diagonal S_ii   */
+/* stays an exact fp32 dot product.  Needs dim % 4 == 0 and                                      */
+/* rf_inbatch_workspace_bytes_tc(batch, dim) bytes of workspace.                                 */
+int64_t rf_inbatch_workspace_bytes_tc(int64_t batch, int32_t dim);
+int rf_inbatch_rowstats_tc(const float *d_query, const float *d_doc, const float *d_y, const float *d_col_weight,
+                           int64_t batch, int32_t dim, float scale, float margin, void *d_workspace,
+                           float *d_lse, float *d_diag, float *d_hinge, float *d_maxoff, float *d_loss,
+                           void *stream);
+
 /* ---- row-sharded tables (new design; the reference only replicates tables,   */
 /* backend/utils/gpu_utils.py:13-14).  Row id lives on rank id % world as local row id / world. */
 /* rf_shard_route partitions the hashed ids of one field by owner, keeping bag order: for every */

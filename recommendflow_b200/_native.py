@@ -61,6 +61,9 @@ def lib():
         L.rf_inbatch_rowstats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float,
                                           C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p]
+        L.rf_inbatch_rowstats_tc.argtypes = L.rf_inbatch_rowstats.argtypes
+        L.rf_inbatch_workspace_bytes_tc.restype = C.c_int64
+        L.rf_inbatch_workspace_bytes_tc.argtypes = [C.c_int64, C.c_int32]
         L.rf_shard_route.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
         L.rf_shard_route_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
@@ -68,7 +71,7 @@ def lib():
                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
         L.rf_combine_partials.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int, C.c_int32, C.c_void_p,
                                           C.c_void_p, C.c_int64, C.c_void_p]
-        for name in ("rf_hash_strings", "rf_hash_int64", "rf_bag_forward", "rf_shard_route", "rf_shard_route_keys", "rf_sdpa_forward", "rf_inbatch_rowstats",
+        for name in ("rf_hash_strings", "rf_hash_int64", "rf_bag_forward", "rf_shard_route", "rf_shard_route_keys", "rf_sdpa_forward", "rf_inbatch_rowstats", "rf_inbatch_rowstats_tc",
                      "rf_combine_partials"):
             getattr(L, name).restype = C.c_int
         _lib = L

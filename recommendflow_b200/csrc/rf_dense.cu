@@ -12,6 +12,7 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <atomic>
 
 #include "../../include/rf_b200.h"
@@ -20,6 +21,10 @@
 namespace rf {
 
 extern std::atomic<int64_t> g_launches;
+
+struct RowStat;
+int launch_logits_tc(const float *q, const float *d, const float *diag, const float *colw, int B, int Dt, float scale,
+                     float margin, bool full_stats, RowStat *part, int max_splits, int *splits, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------
 // In-batch row statistics.  For S = q d^T (q, d: [B, Dt] fp32 row-major), per row i:
@@ -134,6 +139,17 @@ __global__ void __launch_bounds__(256) inbatch_rowstats_kernel(const float *__re
             x = fmaxf(x, s.maxoff);
         }
         if (r < B) part[(size_t)blockIdx.y * B + r] = RowStat{m, l, h, x};
+    }
+}
+
+// Round fp32 to the nearest TF32 value (cvt.rna), kept in fp32 storage.  The tensor core truncates
+// whatever it is given to TF32; rounding first makes the operand error unbiased (2^-11 relative,
+// random sign) instead of a systematic 2^-10 shrink of every product.
+__global__ void __launch_bounds__(256) round_tf32_kernel(const float *__restrict__ in, float *__restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t r;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(in[i]));
+        out[i] = __uint_as_float(r);
     }
 }
 
@@ -281,6 +297,48 @@ int64_t rf_inbatch_workspace_bytes(int64_t batch) {
     if (splits < 1) splits = 1;
     if (splits > 64) splits = 64;
     return splits * batch * (int64_t)sizeof(RowStat) + batch * (int64_t)sizeof(float);
+}
+
+int64_t rf_inbatch_workspace_bytes_tc(int64_t batch, int32_t dim) {
+    if (batch <= 0 || dim <= 0) return 0;
+    return rf_inbatch_workspace_bytes(batch) + 512 + 2 * (((int64_t)batch * dim + 63) & ~(int64_t)63) * (int64_t)sizeof(float);
+}
+
+int rf_inbatch_rowstats_tc(const float *d_query, const float *d_doc, const float *d_y, const float *d_col_weight, int64_t batch,
+                           int32_t dim, float scale, float margin, void *d_workspace, float *d_lse, float *d_diag,
+                           float *d_hinge, float *d_maxoff, float *d_loss, void *stream) {
+    if (batch < 0 || dim <= 0) return set_error(RF_ERR_INVALID, "bad in-batch shape");
+    if (batch == 0) return RF_OK;
+    if (batch > (1 << 24)) return set_error(RF_ERR_UNSUPPORTED, "batch too large");
+    if (!d_query || !d_doc || !d_workspace) return set_error(RF_ERR_INVALID, "rf_inbatch_rowstats_tc: NULL buffer");
+    if (d_loss && !d_y) return set_error(RF_ERR_INVALID, "loss requested without y_true");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int B = (int)batch;
+    // workspace layout as in rf_inbatch_rowstats: [splits <= 64][B] RowStat, then B floats for the diagonal
+    const int64_t row_tiles = (batch + kTM - 1) / kTM;
+    int64_t max_splits = (148 * 4 + row_tiles - 1) / row_tiles;
+    if (max_splits < 1) max_splits = 1;
+    if (max_splits > 64) max_splits = 64;
+    RowStat *part = static_cast<RowStat *>(d_workspace);
+    float *diag_ws = reinterpret_cast<float *>(part + (size_t)max_splits * B);
+    float *diag = d_diag ? d_diag : diag_ws;
+    // TF32-rounded operand copies live after the statistics in the workspace, 256-byte aligned
+    uintptr_t p = (reinterpret_cast<uintptr_t>(diag_ws + B) + 255) & ~(uintptr_t)255;
+    float *q32 = reinterpret_cast<float *>(p);
+    float *d32 = q32 + (((size_t)B * dim + 63) & ~(size_t)63);
+    const int64_t n = (int64_t)B * dim;
+    const int rgrid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    round_tf32_kernel<<<rgrid, 256, 0, st>>>(d_query, q32, n);
+    round_tf32_kernel<<<rgrid, 256, 0, st>>>(d_doc, d32, n);
+    rowdot_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(d_query, d_doc, B, dim, diag);   // exact fp32 diagonal
+    int splits = 0;
+    const bool full = d_hinge != nullptr || d_maxoff != nullptr;
+    int rc = launch_logits_tc(q32, d32, diag, d_col_weight, B, dim, scale, margin, full, part, (int)max_splits, &splits, st);
+    if (rc != RF_OK) return rc;
+    inbatch_finalize_kernel<<<1, 1024, 0, st>>>(part, splits, B, diag, d_y, scale, d_lse, d_hinge, d_maxoff, d_loss);
+    RF_CUDA(cudaGetLastError());
+    g_launches.fetch_add(4);
+    return RF_OK;
 }
 
 int rf_inbatch_rowstats(const float *d_query, const float *d_doc, const float *d_y, const float *d_col_weight, int64_t batch,

@@ -1,0 +1,331 @@
+// rf_logits_tc.cu -- the B x B in-batch logits S = query . doc^T on the 5th-gen tensor cores
+// (tcgen05 + TMEM + TMA, sm_100a), with the row reductions of the two-tower losses fused into the
+// epilogue so that S never exists in memory.
+//
+// Replaces tf.matmul(query, tf.transpose(doc)) + tf.exp + tf.reduce_sum + tf.linalg.diag_part of
+// /root/reference/backend/lossess/match_losses.py:160-165 (and the same contraction of :119-226).
+//
+//   operands   fp32 in HBM, read as TF32 (kind::tf32: the tensor core uses the top 19 bits; this is
+//              what TensorFlow itself does for fp32 matmuls on Ampere+ GPUs), fp32 accumulate.
+//   tile       128 (query rows) x 256 (docs) x 32 (K, one 128-byte swizzle atom) per stage,
+//              4-stage TMA -> smem ring, 4 x tcgen05.mma (K = 8) per stage, accumulator 128 lanes x
+//              256 columns of TMEM.
+//   warps      0: TMA producer (one elected lane)   1: TMEM alloc + MMA issue (one elected lane)
+//              2-5: epilogue -- each thread owns one query row (= one TMEM lane), pulls 32 columns at
+//              a time with tcgen05.ld and keeps running (max, sum exp, hinge, max-off-diagonal).
+//   grid       (row tiles, column groups); a CTA walks `tiles_per_cta` column tiles and writes one
+//              partial RowStat per row; rf_dense.cu's finalize kernel merges the column groups.
+//
+// Every mbarrier wait is bounded and traps instead of hanging if the pipeline is ever wedged.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "../../include/rf_b200.h"
+#include "rf_common.h"
+
+namespace rf {
+
+extern std::atomic<int64_t> g_launches;
+
+struct RowStat {
+    float m, l, hinge, maxoff;
+};
+
+constexpr int kBM = 128, kBN = 256, kBK = 32;       // tile; kBK fp32 = 128 bytes = one SW128 atom row
+constexpr int kUmmaK = 8;                           // tf32: 32 bytes per MMA along K
+constexpr int kStages = 4;
+constexpr int kABytes = kBM * kBK * 4;              // 16 KiB
+constexpr int kBBytes = kBN * kBK * 4;              // 32 KiB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kTmemCols = 256;
+constexpr int kTcThreads = 192;
+constexpr size_t kTcSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// ---- PTX helpers --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 26)) __trap();            // a wedged pipeline must fail, not hang the GPU
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major operand tile in shared memory, 128-byte swizzle: rows at a 128-byte pitch, 8-row groups
+// 1024 bytes apart (SBO), LBO = 1 (unused for swizzled K-major), descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);        // start address  [0,14)
+    d |= (uint64_t)1 << 16;                              // leading byte offset (>>4) [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;                    // stride byte offset (>>4)  [32,46)
+    d |= (uint64_t)1 << 46;                              // version                   [46,48)
+    d |= (uint64_t)2 << 61;                              // layout: SWIZZLE_128B      [61,64)
+    return d;
+}
+
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 256
+constexpr uint32_t kInstrDesc = (1u << 4)                 // c_format = F32
+                                | (2u << 7)               // a_format = TF32
+                                | (2u << 10)              // b_format = TF32
+                                | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+
+template <bool FULL_STATS>
+__global__ void __launch_bounds__(kTcThreads, 1)
+logits_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_d,
+                 const float *__restrict__ diag, const float *__restrict__ colw, int B, int Dt, float scale, float margin,
+                 int n_tiles, int tiles_per_cta, RowStat *__restrict__ part) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SW128 atoms need 1024-byte alignment
+    const uint32_t bars = smem_base + kStages * kStageBytes;                    // full[4], empty[4], tmem_full, tmem_empty
+    const uint32_t full0 = bars, empty0 = bars + 8 * kStages, tmem_full = bars + 16 * kStages, tmem_empty = tmem_full + 8;
+    const uint32_t tmem_slot = tmem_empty + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x;
+    const int tile0 = blockIdx.y * tiles_per_cta;
+    const int tile1 = min(n_tiles, tile0 + tiles_per_cta);
+    const int n_kb = (Dt + kBK - 1) / kBK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);                  // one arrive per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {                                // whole warp: allocate the accumulator columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int tile = tile0; tile < tile1; ++tile) {
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    const uint32_t a_dst = smem_base + stage * kStageBytes;
+                    mbar_expect_tx(full0 + 8 * stage, kStageBytes);
+                    tma_load_2d(a_dst, &map_q, full0 + 8 * stage, kb * kBK, m_tile * kBM);
+                    tma_load_2d(a_dst + kABytes, &map_d, full0 + 8 * stage, kb * kBK, tile * kBN);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            int local = 0;
+            for (int tile = tile0; tile < tile1; ++tile, ++local) {
+                mbar_wait(tmem_empty, (local & 1) ^ 1);          // epilogue has drained the accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = smem_base + stage * kStageBytes;
+                    const uint64_t adesc = umma_desc_sw128(a_addr);
+                    const uint64_t bdesc = umma_desc_sw128(a_addr + kABytes);
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        // step 32 bytes along K inside the swizzle atom: +2 in the (>>4) address field
+                        umma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kInstrDesc,
+                                  (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty0 + 8 * stage);            // frees the smem stage when these MMAs retire
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(tmem_full);                         // accumulator complete
+            }
+        }
+    } else {
+        // ===== epilogue: thread <-> query row (TMEM lane); warp w may touch lanes 32*(w % 4) .. +31 =====
+        const int quarter = warp & 3;
+        const int row_in_tile = quarter * 32 + lane;
+        const int row = m_tile * kBM + row_in_tile;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const float rdiag = (FULL_STATS && row < B) ? diag[row] : 0.f;
+        float rm = -INFINITY, rl = 0.f, rh = 0.f, rx = -INFINITY;
+        int local = 0;
+        for (int tile = tile0; tile < tile1; ++tile, ++local) {
+            mbar_wait(tmem_full, local & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int col_tile0 = tile * kBN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < kBN; c0 += 32) {
+                float v[32];
+                tmem_ld32(lane_addr + (uint32_t)c0, v);
+                const int col0 = col_tile0 + c0;
+                if (col0 >= B) continue;
+                const int n_valid = min(32, B - col0);
+                float cmax = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float x = scale * v[j];
+                    if (j < n_valid) cmax = fmaxf(cmax, x);
+                }
+                if (cmax > rm) {
+                    rl *= __expf(rm - cmax);
+                    rm = cmax;
+                }
+                float add = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < n_valid) add += __expf(scale * v[j] - rm);
+                rl += add;
+                if (FULL_STATS) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (j < n_valid) {
+                            const int c = col0 + j;
+                            const float h = v[j] - rdiag + margin;
+                            rh += fminf(fmaxf(h, 0.f), 1e14f) * (colw ? __ldg(colw + c) : 1.f);
+                            rx = fmaxf(rx, c == row ? 0.f : v[j]);
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+        }
+        if (row < B) part[(size_t)blockIdx.y * B + row] = RowStat{rm, rl, rh, rx};
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---- host ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return (EncodeTiledFn) nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+static int make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return set_error(RF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(RF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return RF_OK;
+}
+
+// Launches the tensor-core partial-statistics kernel.  Returns the number of column groups in *splits.
+int launch_logits_tc(const float *q, const float *d, const float *diag, const float *colw, int B, int Dt, float scale,
+                     float margin, bool full_stats, RowStat *part, int max_splits, int *splits, cudaStream_t st) {
+    if (Dt % 4 != 0 || (reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(d) & 15))
+        return set_error(RF_ERR_UNSUPPORTED, "tensor-core logits need dim %% 4 == 0 and 16-byte aligned operands");
+    CUtensorMap mq, md;
+    int rc = make_map(&mq, q, B, Dt, kBM);
+    if (rc != RF_OK) return rc;
+    rc = make_map(&md, d, B, Dt, kBN);
+    if (rc != RF_OK) return rc;
+    const int m_tiles = (B + kBM - 1) / kBM;
+    const int n_tiles = (B + kBN - 1) / kBN;
+    int groups = (2 * 148 + m_tiles - 1) / m_tiles;        // aim at >= 2 CTAs per SM overall
+    if (groups < 1) groups = 1;
+    if (groups > n_tiles) groups = n_tiles;
+    if (groups > max_splits) groups = max_splits;
+    const int tiles_per_cta = (n_tiles + groups - 1) / groups;
+    groups = (n_tiles + tiles_per_cta - 1) / tiles_per_cta;
+    *splits = groups;
+    if (full_stats) {
+        RF_CUDA(cudaFuncSetAttribute(logits_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+        logits_tc_kernel<true><<<dim3(m_tiles, groups), kTcThreads, kTcSmemBytes, st>>>(mq, md, diag, colw, B, Dt, scale, margin,
+                                                                                        n_tiles, tiles_per_cta, part);
+    } else {
+        RF_CUDA(cudaFuncSetAttribute(logits_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+        logits_tc_kernel<false><<<dim3(m_tiles, groups), kTcThreads, kTcSmemBytes, st>>>(mq, md, diag, colw, B, Dt, scale, margin,
+                                                                                         n_tiles, tiles_per_cta, part);
+    }
+    RF_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return RF_OK;
+}
+
+}  // namespace rf

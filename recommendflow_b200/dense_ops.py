@@ -38,9 +38,19 @@ def sdpa(q, k, v, mask=None):
     return out
 
 
-def inbatch_rowstats(query, doc, y_true=None, col_weight=None, scale=20.0, margin=0.0, want=("lse", "diag")):
+# "tf32": tcgen05 tensor cores, fp32 operands read as TF32 (what TensorFlow does for fp32 matmuls on
+# Ampere and later GPUs); "fp32": exact CUDA-core accumulation.  Shapes the tensor-core kernel does
+# not take (dim % 4 != 0) use the fp32 kernel.
+DEFAULT_PRECISION = "tf32"
+
+
+def inbatch_rowstats(query, doc, y_true=None, col_weight=None, scale=20.0, margin=0.0, want=("lse", "diag"),
+                     precision=None):
     """Row statistics of S = query . doc^T without materialising S.  Returns a dict with the
     requested [B] vectors among lse / diag / hinge / maxoff, plus "loss" when y_true is given."""
+    precision = precision or DEFAULT_PRECISION
+    if precision not in ("tf32", "fp32"):
+        raise ValueError("precision must be 'tf32' or 'fp32'")
     q, d = _f32(query, "query"), _f32(doc, "doc")
     if q.dim() != 2 or q.shape != d.shape:
         raise ValueError(f"query and doc must both be [B, D], got {tuple(q.shape)} and {tuple(d.shape)}")
@@ -50,14 +60,17 @@ def inbatch_rowstats(query, doc, y_true=None, col_weight=None, scale=20.0, margi
     cw = None if col_weight is None else _f32(col_weight, "col_weight").reshape(-1)
     if y is not None and y.numel() != B:
         raise ValueError("y_true must have one entry per row")
-    ws = torch.empty(max(1, nat.lib().rf_inbatch_workspace_bytes(B)), dtype=torch.uint8, device=dev)
+    use_tc = precision == "tf32" and D % 4 == 0
+    ws_bytes = nat.lib().rf_inbatch_workspace_bytes_tc(B, D) if use_tc else nat.lib().rf_inbatch_workspace_bytes(B)
+    ws = torch.empty(max(1, ws_bytes), dtype=torch.uint8, device=dev)
     res = {k: torch.empty(B, dtype=torch.float32, device=dev) for k in want}
     loss = torch.zeros((), dtype=torch.float32, device=dev) if y is not None else None
     ptr = lambda t: None if t is None else t.data_ptr()
+    fn = nat.lib().rf_inbatch_rowstats_tc if use_tc else nat.lib().rf_inbatch_rowstats
     with torch.cuda.device(dev):
-        nat.check(nat.lib().rf_inbatch_rowstats(q.data_ptr(), d.data_ptr(), ptr(y), ptr(cw), B, D, float(scale), float(margin),
-                                                ws.data_ptr(), ptr(res.get("lse")), ptr(res.get("diag")), ptr(res.get("hinge")),
-                                                ptr(res.get("maxoff")), ptr(loss), _stream(dev)))
+        nat.check(fn(q.data_ptr(), d.data_ptr(), ptr(y), ptr(cw), B, D, float(scale), float(margin),
+                     ws.data_ptr(), ptr(res.get("lse")), ptr(res.get("diag")), ptr(res.get("hinge")),
+                     ptr(res.get("maxoff")), ptr(loss), _stream(dev)))
     if loss is not None:
         res["loss"] = loss
     return res
