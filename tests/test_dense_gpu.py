@@ -67,9 +67,10 @@ def _pairs(rng, B, D):
 
 
 # fp32: |S| <= 1, fp32 dot of <= 256 terms: ~1e-6 on a logit, x 20 in the exponent -> 1e-4.
-# tf32 (tcgen05): operands rounded to nearest TF32 (2^-11 relative, unbiased): a length-256 dot of unit
-# vectors moves by <~ 1e-4, x 20 in the exponent -> 4e-3 on lse and on the loss.
-TOL = {"fp32": 1e-4, "tf32": 4e-3}
+# tf32 (tcgen05): operands rounded to nearest TF32 (2^-11 relative each, unbiased): |dS| <= 2 * 2^-11 *
+# sum_k |q_k d_k| <= 1e-3 for unit vectors (worst case, all errors aligned), x 20 in the exponent ->
+# 2e-2 bound on a row's lse; observed ~4e-3 at D = 16 and ~1e-3 at D = 256.
+TOL = {"fp32": 1e-4, "tf32": 2e-2}
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32"])
