@@ -36,6 +36,7 @@ WORKLOADS = {
     "small": (4, 3000, 16, 2048, 4, 2),
 }
 N_KEY_BATCHES = 4
+E2E_CHUNKS = 4
 
 
 def parse_args():
@@ -47,6 +48,7 @@ def parse_args():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the row-sharded C4 measurement appended to the line")
     return ap.parse_args()
 
 
@@ -317,29 +319,54 @@ def run_ours(args):
     # ---- end to end: host key buffers in, pooled vectors out to host, every step ---------------
     e2e = None
     if not args.no_e2e:
-        # device staging buffers sized for the largest batch
-        max_b = max(int(h.data.numel()) for h in host_packed)
-        max_o = max(int(h.offsets.numel()) for h in host_packed)
-        stage = PackedBatch(torch.empty(max_b, dtype=torch.uint8, device=dev),
-                            torch.empty(max_o, dtype=torch.int32, device=dev), None)
+        # The batch crosses PCIe in E2E_CHUNKS row chunks on two streams, so the D2H of one chunk's pooled
+        # vectors overlaps the H2D + kernel of the next (PCIe is full duplex); every step still moves all
+        # key bytes in and all pooled vectors out, and the host result is complete at the end of the step.
+        n_chunks = E2E_CHUNKS if B % E2E_CHUNKS == 0 and B >= 4096 else 1
+        rows = B // n_chunks
+        host_chunks = []                                   # [batch][chunk] -> pinned PackedBatch of `rows` samples
+        for kb in key_batches:
+            per = []
+            for c in range(n_chunks):
+                fields = {}
+                for fname, (arena, offs, _) in kb.items():
+                    lo, hi = c * rows * L, (c + 1) * rows * L
+                    o = offs[lo:hi + 1]
+                    fields[fname] = (arena[o[0]:o[-1]], (o - o[0]).astype(np.int32), (rows, L))
+                per.append(PackedBatch.pack(fields, pin=True))
+            host_chunks.append(per)
+        max_b = max(int(h.data.numel()) for per in host_chunks for h in per)
+        max_o = max(int(h.offsets.numel()) for per in host_chunks for h in per)
+        streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        stages = [PackedBatch(torch.empty(max_b, dtype=torch.uint8, device=dev),
+                              torch.empty(max_o, dtype=torch.int32, device=dev), None) for _ in range(2)]
         host_out = torch.empty(B, F * T * D, dtype=torch.float32).pin_memory()
 
         def e2e_step(i):
-            hp = host_packed[i % N_KEY_BATCHES]
-            stage.data[:hp.data.numel()].copy_(hp.data, non_blocking=True)
-            stage.offsets[:hp.offsets.numel()].copy_(hp.offsets, non_blocking=True)
-            stage.layout = hp.layout
-            bag_forward(calls_for(stage.columns()), B)
-            host_out.copy_(out, non_blocking=True)
+            per = host_chunks[i % N_KEY_BATCHES]
+            for c, hp in enumerate(per):
+                st, stage = streams[c % 2], stages[c % 2]
+                with torch.cuda.stream(st):
+                    stage.data[:hp.data.numel()].copy_(hp.data, non_blocking=True)
+                    stage.offsets[:hp.offsets.numel()].copy_(hp.offsets, non_blocking=True)
+                    stage.layout = hp.layout
+                    cols = stage.columns()
+                    o = out[c * rows:(c + 1) * rows]
+                    bag_forward([FieldCall([(tables[f][t], N, salts[t]) for t in range(T)], D, "sum", keys=cols[n],
+                                           mask_mode=nat.MASK_EMPTY_STRING, out=o[:, f * T * D:(f + 1) * T * D], bag_len=L)
+                                 for f, n in enumerate(names)], rows)
+                    host_out[c * rows:(c + 1) * rows].copy_(o, non_blocking=True)
 
+        torch.cuda.synchronize()
         for i in range(3):
             e2e_step(i)
         barrier()
         ke = max(3, min(K, 20))
+        launches_e2e0 = nat.launch_count()
         t0 = time.perf_counter()
         for i in range(ke):
             e2e_step(i)
-            torch.cuda.synchronize()          # the caller consumes the host result every step
+            torch.cuda.synchronize()          # the caller consumes the complete host result every step
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / ke
         if world > 1:
@@ -347,9 +374,11 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_ms = float(t.item())
         e2e = {"value": world * B / (e2e_ms / 1e3), "unit": UNIT,
-               "h2d_bytes_per_step": int(np.mean([h.nbytes for h in host_packed])),
+               "h2d_bytes_per_step": int(np.mean([sum(h.nbytes for h in per) for per in host_chunks])),
                "d2h_bytes_per_step": int(host_out.numel() * 4), "ms_per_step": e2e_ms, "steps": ke,
-               "path": "pinned host key arena+offsets -> H2D -> rf_bag_forward -> D2H of the pooled [B, sum(T*D)] fp32"}
+               "gpu_launches": int(nat.launch_count() - launches_e2e0),
+               "path": f"pinned host key arena+offsets -> H2D -> rf_bag_forward -> D2H of the pooled [B, sum(T*D)] fp32, "
+                       f"{n_chunks} row chunks on 2 streams (copy/compute overlap)"}
 
     # ---- roofline of the one kernel ------------------------------------------------------------
     peaks = {}
@@ -383,12 +412,21 @@ def run_ours(args):
         if not same:
             raise SystemExit("bench: " + parity)
 
+    # ---- C4: jagged bags, mean pooling, 100M x 128 table: one GPU = the fused kernel on
+    # the whole table; N > 1 = the table row-sharded id % N with the p2p (NVLink peer memory) exchange.
+    c4 = None
+    if not args.no_c4 and name == "c2":
+        del tables, all_calls, dev_cols, dev_packed, out
+        torch.cuda.empty_cache()
+        from tools.bench_sharded import parse as c4_parse, run as c4_run
+        c4 = c4_run(c4_parse(["--batch", "65536", "--steps", "20", "--warmup", "5", "--transport", "p2p"]), world, rank, dev)
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 pooling / u64 hashing", "data": "synthetic", "config": workload_config(name),
                 "gpu_launches": int(launches), "clocks": clocks.summary(), "e2e": e2e, "roofline": roofline,
-                "cpu_baseline": cpu, "parity_check": parity}
+                "cpu_baseline": cpu, "parity_check": parity, "sharded_c4": c4}
         line["config"]["parallelism"] = f"dp{world} (replicated tables, no data-path collective)"
         print(json.dumps(line))
     if world > 1:

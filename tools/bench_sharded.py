@@ -30,7 +30,7 @@ def jagged_keys(rank, B, max_len, batch_index=0):
     return arena, offs, bag
 
 
-def main():
+def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=100_000_000)
     ap.add_argument("--dim", type=int, default=128)
@@ -40,8 +40,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--transport", default="both", choices=["p2p", "nccl", "both"])
     ap.add_argument("--graph", action="store_true", help="capture each step (p2p transport) in a CUDA graph and replay")
-    args = ap.parse_args()
+    return ap.parse_args(argv)
 
+
+def run(args, world, rank, dev):
+    """Measure C4 on an already initialised process group; returns the result dict (rank 0) or None."""
     import torch
     import torch.distributed as dist
     from recommendflow_b200 import _native as nat
@@ -49,13 +52,6 @@ def main():
     from recommendflow_b200.sharded import ShardedEmbeddingBag
     from recommendflow_b200.strings import StringColumn
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     B, N, D, K, W = args.batch, args.rows, args.dim, args.steps, max(args.warmup, 3)
     NB = 4
     batches = []
@@ -156,6 +152,7 @@ def main():
             del layer
         if len(outs) == 2:
             results["p2p_equals_nccl"] = bool(torch.equal(outs["p2p"], outs["nccl"]))
+    line = None
     if rank == 0:
         best = min(v for k, v in results.items() if isinstance(v, float))
         line = {"metric": "lookup+pool samples/sec", "workload": f"c4: jagged 1..{args.max_len} keys/bag (mean {mean_len:.1f}), avg pooling, "
@@ -163,6 +160,22 @@ def main():
                 "n_gpus": world, "value": world * B / (best / 1e3), "unit": "samples/s", "ms_per_step": results,
                 "steps": K, "warmup": W, "algorithmic_bytes_per_sample": bps,
                 "hbm_gbs_per_gpu": bps * B / (best / 1e3) / 1e9, "gpu_launches": nat.launch_count()}
+    return line
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    line = run(args, world, rank, dev)
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
