@@ -116,6 +116,12 @@ int rf_bag_forward(const rf_field_desc *fields, int n_fields, int64_t batch, voi
 int rf_sdpa_forward(const float *d_q, const float *d_k, const float *d_v, const float *d_mask,
                     int64_t n_batch_heads, int32_t seq_len, int32_t head_dim, float *d_out, void *stream);
 
+/* Same contract on the tensor cores (tcgen05.mma kind::tf32, TMEM accumulators, TMA): pairs of   */
+/* sequences share one 128-row tile; seq_len <= 64, head_dim in {32, 64, 96}; otherwise           */
+/* RF_ERR_UNSUPPORTED (use rf_sdpa_forward).  fp32 operands are read as TF32.                     */
+int rf_sdpa_forward_tc(const float *d_q, const float *d_k, const float *d_v, const float *d_mask,
+                       int64_t n_batch_heads, int32_t seq_len, int32_t head_dim, float *d_out, void *stream);
+
 /* ---- in-batch two-tower logits S = query . doc^T, reduced per row without ever storing S ------ */
 /* (backend/lossess/match_losses.py:119-226 all start from tf.matmul(query, tf.transpose(doc))).   */
 /* Per row i (any output pointer may be NULL):                                                     */

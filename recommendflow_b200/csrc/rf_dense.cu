@@ -22,6 +22,9 @@ namespace rf {
 
 extern std::atomic<int64_t> g_launches;
 
+bool sdpa_tc_supported(int64_t n_seq, int S, int dh, const float *q, const float *k, const float *v, const float *out);
+int launch_sdpa_tc(const float *q, const float *k, const float *v, const float *mask, int64_t n_seq, int S, int dh, float *out,
+                   cudaStream_t st);
 struct RowStat;
 int launch_logits_tc(const float *q, const float *d, const float *diag, const float *colw, int B, int Dt, float scale,
                      float margin, bool full_stats, RowStat *part, int max_splits, int *splits, cudaStream_t st);
@@ -166,15 +169,22 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const float *__restrict__ q
     if (lane == 0) diag[row] = acc;
 }
 
-// merge the column splits; lse_i = m + log(l); loss = mean_i( -(scale * diag_i - lse_i) * y_i )
-__global__ void __launch_bounds__(1024) inbatch_finalize_kernel(const RowStat *__restrict__ part, int splits, int B,
-                                                                const float *__restrict__ diag, const float *__restrict__ y,
-                                                                float scale, float *__restrict__ lse_out,
-                                                                float *__restrict__ hinge_out, float *__restrict__ maxoff_out,
-                                                                float *__restrict__ loss_out) {
-    __shared__ double wsum[32];
+// merge the column splits; lse_i = m + log(l); loss = mean_i( -(scale * diag_i - lse_i) * y_i ).
+// Many CTAs; each leaves a float64 partial of the loss, and the last one to finish (ticket counter)
+// adds the partials in block order, so the scalar is deterministic.
+constexpr int kFinThreads = 256;
+
+__global__ void __launch_bounds__(kFinThreads) inbatch_finalize_kernel(const RowStat *__restrict__ part, int splits, int B,
+                                                                       const float *__restrict__ diag,
+                                                                       const float *__restrict__ y, float scale,
+                                                                       float *__restrict__ lse_out, float *__restrict__ hinge_out,
+                                                                       float *__restrict__ maxoff_out, float *__restrict__ loss_out,
+                                                                       double *__restrict__ block_sums, unsigned int *ticket) {
+    __shared__ double wsum[kFinThreads / 32];
+    __shared__ bool last;
     double local = 0.0;
-    for (int r = threadIdx.x; r < B; r += blockDim.x) {
+    const int r = blockIdx.x * kFinThreads + threadIdx.x;
+    if (r < B) {
         float m = -INFINITY, l = 0.f, h = 0.f, x = -INFINITY;
         for (int s = 0; s < splits; ++s) {
             const RowStat p = part[(size_t)s * B + r];
@@ -191,17 +201,41 @@ __global__ void __launch_bounds__(1024) inbatch_finalize_kernel(const RowStat *_
         if (lse_out) lse_out[r] = lse;
         if (hinge_out) hinge_out[r] = h;
         if (maxoff_out) maxoff_out[r] = x;
-        if (y) local += (double)(-(scale * diag[r] - lse) * y[r]);
+        if (y) local = (double)(-(scale * diag[r] - lse) * y[r]);
     }
+    if (!loss_out) return;
     for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
     if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = local;
     __syncthreads();
-    if (threadIdx.x == 0 && loss_out) {
+    if (threadIdx.x == 0) {
         double t = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += wsum[w];
+        for (int w = 0; w < kFinThreads / 32; ++w) t += wsum[w];
+        block_sums[blockIdx.x] = t;
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        double t = 0.0;
+        for (unsigned int i = 0; i < gridDim.x; ++i) t += block_sums[i];
         *loss_out = (float)(t / (double)B);
+        *ticket = 0;                                 // ready for the next call
     }
 }
+
+static int launch_finalize(const RowStat *part, int splits, int B, const float *diag, const float *y, float scale, float *lse,
+                           float *hinge, float *maxoff, float *loss, void *fin_ws, cudaStream_t st) {
+    const int blocks = (B + kFinThreads - 1) / kFinThreads;
+    double *block_sums = static_cast<double *>(fin_ws);
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(block_sums + blocks);
+    if (loss) RF_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st));
+    inbatch_finalize_kernel<<<blocks, kFinThreads, 0, st>>>(part, splits, B, diag, y, scale, lse, hinge, maxoff, loss,
+                                                           block_sums, ticket);
+    return RF_OK;
+}
+
+static int64_t finalize_ws_bytes(int64_t batch) { return ((batch + kFinThreads - 1) / kFinThreads) * 8 + 64; }
 
 // ------------------------------------------------------------------------------------------
 // scaled_dot_product_attention.  q, k, v: [NB, S, dh] fp32; mask: [NB, S] or NULL (the reference's
@@ -290,13 +324,24 @@ int rf_sdpa_forward(const float *d_q, const float *d_k, const float *d_v, const 
     return RF_OK;
 }
 
+int rf_sdpa_forward_tc(const float *d_q, const float *d_k, const float *d_v, const float *d_mask, int64_t n_batch_heads,
+                       int32_t seq_len, int32_t head_dim, float *d_out, void *stream) {
+    if (n_batch_heads < 0 || seq_len <= 0 || head_dim <= 0) return set_error(RF_ERR_INVALID, "bad SDPA shape");
+    if (n_batch_heads == 0) return RF_OK;
+    if (!d_q || !d_k || !d_v || !d_out) return set_error(RF_ERR_INVALID, "rf_sdpa_forward_tc: NULL buffer");
+    if (!sdpa_tc_supported(n_batch_heads, seq_len, head_dim, d_q, d_k, d_v, d_out))
+        return set_error(RF_ERR_UNSUPPORTED, "tensor-core SDPA takes seq_len <= 64 and head_dim in {32, 64, 96}, 16-byte aligned");
+    return launch_sdpa_tc(d_q, d_k, d_v, d_mask, n_batch_heads, seq_len, head_dim, d_out, static_cast<cudaStream_t>(stream));
+}
+
 int64_t rf_inbatch_workspace_bytes(int64_t batch) {
     if (batch <= 0) return 0;
     const int64_t row_tiles = (batch + kTM - 1) / kTM;
     int64_t splits = (148 * 4 + row_tiles - 1) / row_tiles;
     if (splits < 1) splits = 1;
     if (splits > 64) splits = 64;
-    return splits * batch * (int64_t)sizeof(RowStat) + batch * (int64_t)sizeof(float);
+    return splits * batch * (int64_t)sizeof(RowStat) + ((batch * (int64_t)sizeof(float) + 15) & ~(int64_t)15) +
+           finalize_ws_bytes(batch);
 }
 
 int64_t rf_inbatch_workspace_bytes_tc(int64_t batch, int32_t dim) {
@@ -322,8 +367,9 @@ int rf_inbatch_rowstats_tc(const float *d_query, const float *d_doc, const float
     RowStat *part = static_cast<RowStat *>(d_workspace);
     float *diag_ws = reinterpret_cast<float *>(part + (size_t)max_splits * B);
     float *diag = d_diag ? d_diag : diag_ws;
+    void *fin_ws = reinterpret_cast<char *>(diag_ws) + (((size_t)B * sizeof(float) + 15) & ~(size_t)15);
     // TF32-rounded operand copies live after the statistics in the workspace, 256-byte aligned
-    uintptr_t p = (reinterpret_cast<uintptr_t>(diag_ws + B) + 255) & ~(uintptr_t)255;
+    uintptr_t p = (reinterpret_cast<uintptr_t>(fin_ws) + finalize_ws_bytes(B) + 255) & ~(uintptr_t)255;
     float *q32 = reinterpret_cast<float *>(p);
     float *d32 = q32 + (((size_t)B * dim + 63) & ~(size_t)63);
     const int64_t n = (int64_t)B * dim;
@@ -335,7 +381,8 @@ int rf_inbatch_rowstats_tc(const float *d_query, const float *d_doc, const float
     const bool full = d_hinge != nullptr || d_maxoff != nullptr;
     int rc = launch_logits_tc(q32, d32, diag, d_col_weight, B, dim, scale, margin, full, part, (int)max_splits, &splits, st);
     if (rc != RF_OK) return rc;
-    inbatch_finalize_kernel<<<1, 1024, 0, st>>>(part, splits, B, diag, d_y, scale, d_lse, d_hinge, d_maxoff, d_loss);
+    rc = launch_finalize(part, splits, B, diag, d_y, scale, d_lse, d_hinge, d_maxoff, d_loss, fin_ws, st);
+    if (rc != RF_OK) return rc;
     RF_CUDA(cudaGetLastError());
     g_launches.fetch_add(4);
     return RF_OK;
@@ -355,15 +402,21 @@ int rf_inbatch_rowstats(const float *d_query, const float *d_doc, const float *d
     int splits = (148 * 4 + row_tiles - 1) / row_tiles;
     if (splits < 1) splits = 1;
     if (splits > 64) splits = 64;
+    const int max_splits = splits;              // the workspace is laid out for this many
     int cols = (B + splits - 1) / splits;
     cols = (cols + kTN - 1) / kTN * kTN;
     splits = (B + cols - 1) / cols;
     RowStat *part = static_cast<RowStat *>(d_workspace);
-    float *diag = d_diag ? d_diag : reinterpret_cast<float *>(part + (size_t)splits * B);
+    float *diag_ws = reinterpret_cast<float *>(part + (size_t)max_splits * B);
+    float *diag = d_diag ? d_diag : diag_ws;
+    void *fin_ws = reinterpret_cast<char *>(diag_ws) + (((size_t)B * sizeof(float) + 15) & ~(size_t)15);
     rowdot_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(d_query, d_doc, B, dim, diag);
     inbatch_rowstats_kernel<<<dim3(row_tiles, splits), 256, 0, st>>>(d_query, d_doc, diag, d_col_weight, B, dim, scale, margin,
                                                                      cols, part);
-    inbatch_finalize_kernel<<<1, 1024, 0, st>>>(part, splits, B, diag, d_y, scale, d_lse, d_hinge, d_maxoff, d_loss);
+    {
+        int rc = launch_finalize(part, splits, B, diag, d_y, scale, d_lse, d_hinge, d_maxoff, d_loss, fin_ws, st);
+        if (rc != RF_OK) return rc;
+    }
     RF_CUDA(cudaGetLastError());
     g_launches.fetch_add(3);
     return RF_OK;

@@ -1,0 +1,342 @@
+// rf_sdpa_tc.cu -- scaled_dot_product_attention on the 5th-gen tensor cores (tcgen05 + TMEM + TMA).
+//
+// Replaces the two BatchMatMul + Softmax + Select of /root/reference/backend/layers/layer_utils.py:4-24
+// for the behaviour-sequence shape (S <= 64 keys, head_dim 32, 64 or 96 -- what fits one SM's smem).
+//
+// One CTA works on PAIRS of (batch x head) sequences: the two sequences fill the 128 rows of one
+// UMMA tile (rows 0-63 / 64-127; S is padded to 64 by simply letting the 64-row TMA box run into
+// the next sequence -- those rows/keys are masked out below).  Per pair:
+//   TMA     Q, K, V of both sequences -> smem (128-byte swizzle), head_dim in blocks of 32 floats
+//   GEMM 1  logits[128 x 128] = Qpair . Kpair^T      tcgen05.mma kind::tf32, K-major A and B
+//           (only the two diagonal 64 x 64 blocks are meaningful)
+//   softmax thread = query row = TMEM lane: tcgen05.ld its 64 logits, scale 1/sqrt(dh), the
+//           reference's QUERY-row mask (mask == 0 -> every logit = -4294967295 -> uniform), keys
+//           >= S dropped, exp / sum in registers, probabilities rounded to TF32 and written into a
+//           K-major swizzled smem tile P[128 x 128] that is block-diagonal (off-diagonal blocks
+//           stay zero), fence.proxy.async
+//   GEMM 2  out[128 x dh] = P . Vpair               A = P (K-major), B = V (MN-major: V is [keys][dh])
+//   store   thread = row: tcgen05.ld dh columns -> global
+// fp32 operands are read by the tensor core as TF32 (truncated), accumulation is fp32.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "../../include/rf_b200.h"
+#include "rf_common.h"
+
+namespace rf {
+
+extern std::atomic<int64_t> g_launches;
+
+namespace sdpa_tc {
+
+constexpr int kRows = 128;            // UMMA M: two sequences of up to 64 rows
+constexpr int kSeqPad = 64;
+constexpr int kKB = 32;               // fp32 elements per 128-byte swizzle row
+constexpr int kThreads = 160;         // warps 0-3: rows; warp 4: TMA + MMA issue
+constexpr int kTmemCols = 256;        // logits: columns [0,128), output: [128, 128 + dh)
+constexpr int kBlkBytes = kRows * 128;   // one [128 rows x 128 B] swizzled block = 16 KiB
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 26)) __trap();            // fail instead of hanging the GPU
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 128-byte-swizzled operand descriptors (version 1).  K-major: rows at 128 B, 8-row atoms 1024 B apart
+// (SBO), LBO unused (=1).  MN-major: 32 contiguous MN elements per 128-B row, successive K at +128 B,
+// 8-K atoms 1024 B apart (SBO), next 32 MN elements `lbo_bytes` further.
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) {
+    return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t addr, uint32_t lbo_bytes) {
+    return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+struct Params {
+    const float *mask;     // [n_seq, S] or NULL
+    float *out;            // [n_seq, S, dh]
+    int n_seq, S, dh;
+    float inv_sqrt_dk;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+               const __grid_constant__ CUtensorMap map_v, Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const int n_db = p.dh / kKB;                                    // head_dim blocks of 32 floats
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t q_s = base;                                      // n_db blocks [128 x 128 B]   (A of GEMM 1, K-major)
+    const uint32_t k_s = q_s + n_db * kBlkBytes;                    // n_db blocks                  (B of GEMM 1, K-major)
+    const uint32_t v_s = k_s + n_db * kBlkBytes;                    // n_db blocks [128 keys x 128B] (B of GEMM 2, MN-major)
+    const uint32_t p_s = v_s + n_db * kBlkBytes;                    // 4 blocks [128 x 128 B]        (A of GEMM 2, K-major)
+    const uint32_t bars = p_s + 4 * kBlkBytes;
+    const uint32_t ld_full = bars, mma1_done = bars + 8, p_ready = bars + 16, mma2_done = bars + 24, tmem_slot = bars + 32;
+    uint8_t *smem_gen = smem_raw + (base - smem_u32(smem_raw));    // generic pointer to `base`
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(ld_full, 1);
+        mbar_init(mma1_done, 1);
+        mbar_init(p_ready, 128);
+        mbar_init(mma2_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // the off-diagonal blocks of P are zero forever: rows 0-63 never write key blocks 2,3; rows 64-127 never 0,1
+    {
+        uint4 *pz = reinterpret_cast<uint4 *>(smem_gen + (p_s - base));
+        for (int i = threadIdx.x; i < 4 * kBlkBytes / 16; i += kThreads) pz[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zero fill must be visible to the MMA proxy
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int n_pairs = (p.n_seq + 1) / 2;
+    // GEMM 1: M128 N128, both K-major.  GEMM 2: M128 N=dh, A K-major, B MN-major (bit 16).
+    const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(p.dh >> 3) << 17) |
+                            ((uint32_t)(kRows >> 4) << 24);
+    const uint32_t load_bytes = 3u * n_db * kBlkBytes;
+
+    uint32_t ph = 0;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ph ^= 1) {
+        const int seq0 = 2 * pair;
+        if (warp == 4) {
+            if (lane == 0) {
+                // ---- TMA: both sequences of Q, K, V; 64-row boxes (rows past S spill into the next sequence) ----
+                mbar_expect_tx(ld_full, load_bytes);
+                for (int db = 0; db < n_db; ++db) {
+                    for (int h = 0; h < 2; ++h) {
+                        const int row = (seq0 + h) * p.S;
+                        const uint32_t off = db * kBlkBytes + h * (kSeqPad * 128);
+                        tma_load_2d(q_s + off, &map_q, ld_full, db * kKB, row);
+                        tma_load_2d(k_s + off, &map_k, ld_full, db * kKB, row);
+                        tma_load_2d(v_s + off, &map_v, ld_full, db * kKB, row);
+                    }
+                }
+                mbar_wait(ld_full, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // ---- GEMM 1: logits = Q K^T, K = dh in steps of 8 ----
+                for (int db = 0; db < n_db; ++db) {
+                    const uint64_t a = desc_kmajor(q_s + db * kBlkBytes), b = desc_kmajor(k_s + db * kBlkBytes);
+#pragma unroll
+                    for (int k = 0; k < kKB / 8; ++k) umma_tf32(tmem_base, a + (uint64_t)(2 * k), b + (uint64_t)(2 * k), idesc1, (db | k) ? 1u : 0u);
+                }
+                umma_commit(mma1_done);
+                // ---- GEMM 2: out = P V, K = 128 keys in steps of 8 (one 1024-byte atom of V each) ----
+                mbar_wait(p_ready, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int kb = 0; kb < 4; ++kb) {
+                    const uint64_t a = desc_kmajor(p_s + kb * kBlkBytes);
+#pragma unroll
+                    for (int k = 0; k < kKB / 8; ++k) {
+                        const uint64_t b = desc_mnmajor(v_s + (uint32_t)(kb * 4 + k) * 1024u, (uint32_t)kBlkBytes);
+                        umma_tf32(tmem_base + 128u, a + (uint64_t)(2 * k), b, idesc2, (kb | k) ? 1u : 0u);
+                    }
+                }
+                umma_commit(mma2_done);
+                mbar_wait(mma2_done, ph);          // Q/K/V/P smem is free again before the next pair's TMA
+            }
+            __syncwarp();
+        } else {
+            // ---- softmax: thread = row of the pair tile ----
+            const int r = threadIdx.x;                  // 0..127
+            const int half = r >> 6, i = r & 63;        // sequence of the pair, query index
+            const int seq = seq0 + half;
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+            mbar_wait(mma1_done, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float x[64];
+            {
+                float v0[32], v1[32];
+                tmem_ld32(lane_addr + (uint32_t)(half * 64), v0);
+                tmem_ld32(lane_addr + (uint32_t)(half * 64 + 32), v1);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    x[j] = v0[j];
+                    x[32 + j] = v1[j];
+                }
+            }
+            const bool row_ok = seq < p.n_seq && i < p.S;
+            const bool masked = row_ok && p.mask && p.mask[(size_t)seq * p.S + i] == 0.f;
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                float l = masked ? -4294967295.0f : x[j] * p.inv_sqrt_dk;
+                l = (j < p.S) ? l : -INFINITY;                       // padded keys take no probability
+                x[j] = l;
+                mx = fmaxf(mx, l);
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                const float e = (j < p.S) ? __expf(x[j] - mx) : 0.f;
+                x[j] = e;
+                sum += e;
+            }
+            const float inv = row_ok ? 1.f / sum : 0.f;               // rows that are padding produce zeros
+            // write P[r][half*64 + j] (TF32) into the swizzled K-major tile: key block kb = half*2 + (j / 32)
+            uint8_t *prow = smem_gen + (p_s - base) + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {                            // 16 chunks of 4 keys
+                uint4 w;
+                w.x = to_tf32(x[c * 4 + 0] * inv);
+                w.y = to_tf32(x[c * 4 + 1] * inv);
+                w.z = to_tf32(x[c * 4 + 2] * inv);
+                w.w = to_tf32(x[c * 4 + 3] * inv);
+                const int kb = half * 2 + (c >> 3), cc = c & 7;
+                *reinterpret_cast<uint4 *>(prow + kb * kBlkBytes + ((cc ^ (r & 7)) << 4)) = w;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(p_ready);
+            // ---- output: thread = row, dh columns at TMEM column 128 ----
+            mbar_wait(mma2_done, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float *orow = p.out + ((size_t)seq * p.S + i) * p.dh;
+            for (int c0 = 0; c0 < p.dh; c0 += 32) {
+                float o[32];
+                tmem_ld32(lane_addr + 128u + (uint32_t)c0, o);
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4 *>(orow + c0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int64_t cols) {
+    static EncodeTiledFn fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) return (EncodeTiledFn) nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    if (!fn) return set_error(RF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)kKB, (cuuint32_t)kSeqPad};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(RF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return RF_OK;
+}
+
+}  // namespace sdpa_tc
+
+bool sdpa_tc_supported(int64_t n_seq, int S, int dh, const float *q, const float *k, const float *v, const float *out) {
+    const uintptr_t al = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+                         reinterpret_cast<uintptr_t>(out);
+    return n_seq > 0 && S >= 1 && S <= sdpa_tc::kSeqPad && dh >= 32 && dh <= 96 && dh % 32 == 0 && (al & 15) == 0 &&
+           n_seq * (int64_t)S < INT32_MAX;
+}
+
+int launch_sdpa_tc(const float *q, const float *k, const float *v, const float *mask, int64_t n_seq, int S, int dh, float *out,
+                   cudaStream_t st) {
+    using namespace sdpa_tc;
+    CUtensorMap mq, mk, mv;
+    int rc;
+    if ((rc = make_map(&mq, q, n_seq * S, dh)) != RF_OK) return rc;
+    if ((rc = make_map(&mk, k, n_seq * S, dh)) != RF_OK) return rc;
+    if ((rc = make_map(&mv, v, n_seq * S, dh)) != RF_OK) return rc;
+    const int n_db = dh / kKB;
+    const size_t smem = (size_t)(3 * n_db + 4) * kBlkBytes + 1024 + 128;
+    int dev = 0, sms = 0;
+    RF_CUDA(cudaGetDevice(&dev));
+    RF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    RF_CUDA(cudaFuncSetAttribute(sdpa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int n_pairs = (int)((n_seq + 1) / 2);
+    const int ctas_per_sm = smem <= 110 * 1024 ? 2 : 1;
+    const int grid = n_pairs < sms * ctas_per_sm ? n_pairs : sms * ctas_per_sm;
+    Params p{mask, out, (int)n_seq, S, dh, 1.0f / sqrtf((float)dh)};
+    sdpa_tc_kernel<<<grid, kThreads, smem, st>>>(mq, mk, mv, p);
+    RF_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return RF_OK;
+}
+
+}  // namespace rf

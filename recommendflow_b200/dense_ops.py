@@ -6,6 +6,12 @@ import torch
 from . import _native as nat
 
 
+# "tf32": tcgen05 tensor cores, fp32 operands read as TF32 (what TensorFlow does for fp32 matmuls on
+# Ampere and later GPUs); "fp32": exact CUDA-core accumulation.  Shapes the tensor-core kernels do
+# not take use the fp32 kernels.
+DEFAULT_PRECISION = "tf32"
+
+
 def _f32(t, what):
     if not isinstance(t, torch.Tensor):
         t = torch.as_tensor(t)
@@ -18,8 +24,16 @@ def _stream(dev):
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
-def sdpa(q, k, v, mask=None):
-    """q, k, v: [..., S, dh]; mask: [..., S, 1] (or [..., S]) of 0/1 -- the reference's query-row mask."""
+def sdpa_tc_shape_ok(S, dh):
+    return 1 <= S <= 64 and dh in (32, 64, 96)
+
+
+def sdpa(q, k, v, mask=None, precision=None):
+    """q, k, v: [..., S, dh]; mask: [..., S, 1] (or [..., S]) of 0/1 -- the reference's query-row mask.
+    precision "tf32" runs on the tensor cores when the shape allows (S <= 64, dh in 32/64/96)."""
+    precision = precision or DEFAULT_PRECISION
+    if precision not in ("tf32", "fp32"):
+        raise ValueError("precision must be 'tf32' or 'fp32'")
     q, k, v = _f32(q, "q"), _f32(k, "k"), _f32(v, "v")
     if q.shape != k.shape or q.shape != v.shape:
         raise ValueError(f"q, k, v must share one shape, got {tuple(q.shape)}, {tuple(k.shape)}, {tuple(v.shape)}")
@@ -32,16 +46,11 @@ def sdpa(q, k, v, mask=None):
             m = m[..., 0]
         m = m.expand(q.shape[:-1]).contiguous()
     out = torch.empty_like(q)
+    fn = nat.lib().rf_sdpa_forward_tc if (precision == "tf32" and sdpa_tc_shape_ok(S, dh)) else nat.lib().rf_sdpa_forward
     with torch.cuda.device(q.device):
-        nat.check(nat.lib().rf_sdpa_forward(q.data_ptr(), k.data_ptr(), v.data_ptr(), None if m is None else m.data_ptr(),
-                                            nb, S, dh, out.data_ptr(), _stream(q.device)))
+        nat.check(fn(q.data_ptr(), k.data_ptr(), v.data_ptr(), None if m is None else m.data_ptr(),
+                     nb, S, dh, out.data_ptr(), _stream(q.device)))
     return out
-
-
-# "tf32": tcgen05 tensor cores, fp32 operands read as TF32 (what TensorFlow does for fp32 matmuls on
-# Ampere and later GPUs); "fp32": exact CUDA-core accumulation.  Shapes the tensor-core kernel does
-# not take (dim % 4 != 0) use the fp32 kernel.
-DEFAULT_PRECISION = "tf32"
 
 
 def inbatch_rowstats(query, doc, y_true=None, col_weight=None, scale=20.0, margin=0.0, want=("lse", "diag"),
