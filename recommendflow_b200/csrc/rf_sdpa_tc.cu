@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -98,15 +99,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 // 128-byte-swizzled operand descriptors (version 1).  K-major: rows at 128 B, 8-row atoms 1024 B apart
-// (SBO), LBO unused (=1).  MN-major: 32 contiguous MN elements per 128-B row, successive K at +128 B,
-// 8-K atoms 1024 B apart (SBO), next 32 MN elements `lbo_bytes` further.
+// (SBO), LBO unused (=1), layout SWIZZLE_128B.  MN-major TF32 operands only exist in the 32-byte-base
+// flavour (SWIZZLE_128B_BASE32B = TMA's 128B_ATOM_32B: 32-byte chunks XOR-ed with the row index mod 4):
+// 32 contiguous MN elements per 128-B row, successive K at +128 B, 4-K atoms 512 B apart (SBO), next
+// 32 MN elements `lbo_bytes` further.
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) {
     return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)2 << 61);
 }
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t addr, uint32_t lbo_bytes) {
-    return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
-           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
 }
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
@@ -120,6 +123,7 @@ struct Params {
     float *out;            // [n_seq, S, dh]
     int n_seq, S, dh;
     float inv_sqrt_dk;
+    int debug;             // RF_SDPA_DEBUG: 1 = write the probabilities, 2 = write the raw logits, instead of the output
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -195,6 +199,20 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 // ---- GEMM 2: out = P V, K = 128 keys in steps of 8 (one 1024-byte atom of V each) ----
                 mbar_wait(p_ready, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (p.debug == 3) {            // D2 = P . P^T  (is P readable as an operand?)
+                    for (int kb = 0; kb < 4; ++kb) {
+                        const uint64_t a = desc_kmajor(p_s + kb * kBlkBytes);
+                        for (int k = 0; k < kKB / 8; ++k) umma_tf32(tmem_base + 128u, a + (uint64_t)(2 * k), a + (uint64_t)(2 * k), idesc1, (kb | k) ? 1u : 0u);
+                    }
+                } else if (p.debug == 4) {     // D2 = Qpair[128 x dh] . V[first dh keys][dh]  (is MN-major V readable?)
+                    for (int db = 0; db < n_db; ++db) {
+                        const uint64_t a = desc_kmajor(q_s + db * kBlkBytes);
+                        for (int k = 0; k < kKB / 8; ++k) {
+                            const uint64_t b = desc_mnmajor(v_s + (uint32_t)(db * 4 + k) * 1024u, (uint32_t)kBlkBytes);
+                            umma_tf32(tmem_base + 128u, a + (uint64_t)(2 * k), b, idesc2, (db | k) ? 1u : 0u);
+                        }
+                    }
+                } else
                 for (int kb = 0; kb < 4; ++kb) {
                     const uint64_t a = desc_kmajor(p_s + kb * kBlkBytes);
 #pragma unroll
@@ -265,7 +283,11 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             float *orow = p.out + ((size_t)seq * p.S + i) * p.dh;
             for (int c0 = 0; c0 < p.dh; c0 += 32) {
                 float o[32];
-                tmem_ld32(lane_addr + 128u + (uint32_t)c0, o);
+                tmem_ld32(lane_addr + (p.debug == 2 ? (uint32_t)(half * 64) : 128u) + (uint32_t)c0, o);
+                if (p.debug == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) o[j] = (c0 + j < 64) ? x[(c0 + j) & 63] * inv : 0.f;
+                }
                 if (row_ok) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
@@ -287,7 +309,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int64_t cols) {
+static int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int64_t cols, CUtensorMapSwizzle swizzle) {
     static EncodeTiledFn fn = [] {
         void *f = nullptr;
         cudaDriverEntryPointQueryResult q;
@@ -300,7 +322,7 @@ static int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int64_t co
     const cuuint32_t box[2] = {(cuuint32_t)kKB, (cuuint32_t)kSeqPad};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(RF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return RF_OK;
@@ -320,9 +342,9 @@ int launch_sdpa_tc(const float *q, const float *k, const float *v, const float *
     using namespace sdpa_tc;
     CUtensorMap mq, mk, mv;
     int rc;
-    if ((rc = make_map(&mq, q, n_seq * S, dh)) != RF_OK) return rc;
-    if ((rc = make_map(&mk, k, n_seq * S, dh)) != RF_OK) return rc;
-    if ((rc = make_map(&mv, v, n_seq * S, dh)) != RF_OK) return rc;
+    if ((rc = make_map(&mq, q, n_seq * S, dh, CU_TENSOR_MAP_SWIZZLE_128B)) != RF_OK) return rc;
+    if ((rc = make_map(&mk, k, n_seq * S, dh, CU_TENSOR_MAP_SWIZZLE_128B)) != RF_OK) return rc;
+    if ((rc = make_map(&mv, v, n_seq * S, dh, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != RF_OK) return rc;   // MN-major TF32 operand
     const int n_db = dh / kKB;
     const size_t smem = (size_t)(3 * n_db + 4) * kBlkBytes + 1024 + 128;
     int dev = 0, sms = 0;
@@ -332,7 +354,8 @@ int launch_sdpa_tc(const float *q, const float *k, const float *v, const float *
     const int n_pairs = (int)((n_seq + 1) / 2);
     const int ctas_per_sm = smem <= 110 * 1024 ? 2 : 1;
     const int grid = n_pairs < sms * ctas_per_sm ? n_pairs : sms * ctas_per_sm;
-    Params p{mask, out, (int)n_seq, S, dh, 1.0f / sqrtf((float)dh)};
+    static const int debug = getenv("RF_SDPA_DEBUG") ? atoi(getenv("RF_SDPA_DEBUG")) : 0;
+    Params p{mask, out, (int)n_seq, S, dh, 1.0f / sqrtf((float)dh), debug};
     sdpa_tc_kernel<<<grid, kThreads, smem, st>>>(mq, mk, mv, p);
     RF_CUDA(cudaGetLastError());
     g_launches.fetch_add(1);
