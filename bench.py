@@ -33,6 +33,8 @@ WORKLOADS = {
     #        fields rows     dim  batch  L  tables/field
     "c2":   (26, 1_000_000, 64, 65536, 4, 1),
     "c2x2": (26, 1_000_000, 64, 65536, 4, 2),     # reference-faithful double SipHash variant
+    # C3's embedding side: the normalised base_recall_sdpa plan -- 228 hashed fields x 2 tables of 100000 x 8
+    "c3":   (228, 100_000, 8, 8192, 1, 2),
     "small": (4, 3000, 16, 2048, 4, 2),
 }
 N_KEY_BATCHES = 4

@@ -123,7 +123,6 @@ struct Params {
     float *out;            // [n_seq, S, dh]
     int n_seq, S, dh;
     float inv_sqrt_dk;
-    int debug;             // RF_SDPA_DEBUG: 1 = write the probabilities, 2 = write the raw logits, instead of the output
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -199,20 +198,6 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 // ---- GEMM 2: out = P V, K = 128 keys in steps of 8 (one 1024-byte atom of V each) ----
                 mbar_wait(p_ready, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (p.debug == 3) {            // D2 = P . P^T  (is P readable as an operand?)
-                    for (int kb = 0; kb < 4; ++kb) {
-                        const uint64_t a = desc_kmajor(p_s + kb * kBlkBytes);
-                        for (int k = 0; k < kKB / 8; ++k) umma_tf32(tmem_base + 128u, a + (uint64_t)(2 * k), a + (uint64_t)(2 * k), idesc1, (kb | k) ? 1u : 0u);
-                    }
-                } else if (p.debug == 4) {     // D2 = Qpair[128 x dh] . V[first dh keys][dh]  (is MN-major V readable?)
-                    for (int db = 0; db < n_db; ++db) {
-                        const uint64_t a = desc_kmajor(q_s + db * kBlkBytes);
-                        for (int k = 0; k < kKB / 8; ++k) {
-                            const uint64_t b = desc_mnmajor(v_s + (uint32_t)(db * 4 + k) * 1024u, (uint32_t)kBlkBytes);
-                            umma_tf32(tmem_base + 128u, a + (uint64_t)(2 * k), b, idesc2, (db | k) ? 1u : 0u);
-                        }
-                    }
-                } else
                 for (int kb = 0; kb < 4; ++kb) {
                     const uint64_t a = desc_kmajor(p_s + kb * kBlkBytes);
 #pragma unroll
@@ -283,11 +268,7 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             float *orow = p.out + ((size_t)seq * p.S + i) * p.dh;
             for (int c0 = 0; c0 < p.dh; c0 += 32) {
                 float o[32];
-                tmem_ld32(lane_addr + (p.debug == 2 ? (uint32_t)(half * 64) : 128u) + (uint32_t)c0, o);
-                if (p.debug == 1) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) o[j] = (c0 + j < 64) ? x[(c0 + j) & 63] * inv : 0.f;
-                }
+                tmem_ld32(lane_addr + 128u + (uint32_t)c0, o);
                 if (row_ok) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
@@ -354,8 +335,7 @@ int launch_sdpa_tc(const float *q, const float *k, const float *v, const float *
     const int n_pairs = (int)((n_seq + 1) / 2);
     const int ctas_per_sm = smem <= 110 * 1024 ? 2 : 1;
     const int grid = n_pairs < sms * ctas_per_sm ? n_pairs : sms * ctas_per_sm;
-    static const int debug = getenv("RF_SDPA_DEBUG") ? atoi(getenv("RF_SDPA_DEBUG")) : 0;
-    Params p{mask, out, (int)n_seq, S, dh, 1.0f / sqrtf((float)dh), debug};
+    Params p{mask, out, (int)n_seq, S, dh, 1.0f / sqrtf((float)dh)};
     sdpa_tc_kernel<<<grid, kThreads, smem, st>>>(mq, mk, mv, p);
     RF_CUDA(cudaGetLastError());
     g_launches.fetch_add(1);
