@@ -124,22 +124,38 @@ def _fill(desc, call, batch):
     return keep
 
 
+class BagPlan(object):
+    """The C descriptors of one fused launch, built once.  Re-launching a plan costs one C call: use it
+    when the same buffers are refilled every step (static key / output buffers), e.g. with hundreds of
+    fields where building the descriptors in Python would dominate the step."""
+
+    def __init__(self, calls, batch):
+        self.batch = batch
+        self.n = len(calls)
+        self.descs = (nat.FieldDesc * max(self.n, 1))()
+        self.keep = []
+        for i, call in enumerate(calls):
+            self.keep += _fill(self.descs[i], call, batch)
+        self.device = self.keep[0].device if self.keep else None
+        if any(t.device != self.device for t in self.keep):
+            raise ValueError("all tensors of one launch must be on the same device")
+
+    def launch(self, stream=None):
+        if self.n == 0 or self.batch == 0:
+            return
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().rf_bag_forward(self.descs, self.n, self.batch, C.c_void_p(stream.cuda_stream)))
+
+
 def bag_forward(calls, batch, stream=None):
     """Run every FieldCall of one batch through a single rf_bag_forward launch."""
     if not calls or batch == 0:
         return
-    descs = (nat.FieldDesc * len(calls))()
-    keep = []
-    for i, call in enumerate(calls):
-        keep += _fill(descs[i], call, batch)
-    dev = keep[0].device
-    if any(t.device != dev for t in keep):
-        raise ValueError("all tensors of one launch must be on the same device")
-    if stream is None:
-        stream = torch.cuda.current_stream(dev)
-    with torch.cuda.device(dev):
-        nat.check(nat.lib().rf_bag_forward(descs, len(calls), batch, C.c_void_p(stream.cuda_stream)))
-    return keep
+    plan = BagPlan(calls, batch)
+    plan.launch(stream)
+    return plan.keep
 
 
 def hash_strings(col, num_bins, mask_value=None, salt=None):
