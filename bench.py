@@ -247,6 +247,11 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    # NCCL prints its version banner on stdout; the contract is ONE JSON line there, so everything but
+    # the final line goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -442,7 +447,9 @@ def run_ours(args):
                 "gpu_launches": int(launches), "clocks": clocks.summary(), "e2e": e2e, "roofline": roofline,
                 "cpu_baseline": cpu, "parity_check": parity, "sharded_c4": c4}
         line["config"]["parallelism"] = f"dp{world} (replicated tables, no data-path collective)"
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
