@@ -171,6 +171,10 @@ int rf_combine_partials(const float *d_partials, int world, int64_t batch, int32
                         int32_t bag_len, const int32_t *d_bag_offsets, float *d_out, int64_t out_stride,
                         void *stream);
 
+/* Cap the fused kernel's grid at ctas_per_sm x #SMs (0 = no cap; it then walks its tiles            */
+/* grid-stride).  Leaves room on every SM for kernels of other streams (the sharded pipeline).     */
+int rf_set_bag_grid_limit(int ctas_per_sm);
+
 /* Number of kernels launched by this library since load (bench.py's gpu_launches counter).   */
 int64_t rf_launch_count(void);
 

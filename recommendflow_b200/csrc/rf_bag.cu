@@ -560,16 +560,29 @@ static DeviceState *device_state(int dev) {
     return states[dev];
 }
 
+// Optional cap on resident CTAs per SM (0 = none): the kernel walks its tiles grid-stride, so a
+// smaller grid leaves registers / CTA slots on every SM for kernels of OTHER streams -- used by the
+// sharded pipeline so that the routing of the next step really runs under the pooling of this one.
+static std::atomic<int> g_grid_ctas_per_sm{0};
+
 static int launch_kernel(const DevField *dptr, int nf, int tiles_i, cudaStream_t stream) {
-    const int64_t tiles = tiles_i;
+    int64_t tiles = tiles_i;
+    const int cap = g_grid_ctas_per_sm.load();
+    if (cap > 0) {
+        int dev = 0, sms = 0;
+        RF_CUDA(cudaGetDevice(&dev));
+        RF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (tiles > (int64_t)cap * sms) tiles = (int64_t)cap * sms;
+    }
+    const int total_tiles = tiles_i;
     // CTAs per SM the kernel is compiled for (register cap): 4 (64 registers) measured best on
     // B200 for C2 (0.383 ms vs 0.401 @3); RF_BAG_MINB overrides for experiments.
     static const int cfg = getenv("RF_BAG_MINB") ? atoi(getenv("RF_BAG_MINB")) : 4;
     switch (cfg) {
-        case 2: bag_forward_kernel<2><<<(unsigned)tiles, kThreads, 0, stream>>>(dptr, nf, (int)tiles); break;
-        case 3: bag_forward_kernel<3><<<(unsigned)tiles, kThreads, 0, stream>>>(dptr, nf, (int)tiles); break;
-        case 5: bag_forward_kernel<5><<<(unsigned)tiles, kThreads, 0, stream>>>(dptr, nf, (int)tiles); break;
-        default: bag_forward_kernel<4><<<(unsigned)tiles, kThreads, 0, stream>>>(dptr, nf, (int)tiles); break;
+        case 2: bag_forward_kernel<2><<<(unsigned)tiles, kThreads, 0, stream>>>(dptr, nf, total_tiles); break;
+        case 3: bag_forward_kernel<3><<<(unsigned)tiles, kThreads, 0, stream>>>(dptr, nf, total_tiles); break;
+        case 5: bag_forward_kernel<5><<<(unsigned)tiles, kThreads, 0, stream>>>(dptr, nf, total_tiles); break;
+        default: bag_forward_kernel<4><<<(unsigned)tiles, kThreads, 0, stream>>>(dptr, nf, total_tiles); break;
     }
     RF_CUDA(cudaGetLastError());
     g_launches.fetch_add(1);
@@ -714,6 +727,12 @@ extern "C" {
 int rf_abi_version(void) { return RF_B200_ABI_VERSION; }
 
 int64_t rf_launch_count(void) { return g_launches.load(); }
+
+int rf_set_bag_grid_limit(int ctas_per_sm) {
+    if (ctas_per_sm < 0) return set_error(RF_ERR_INVALID, "ctas_per_sm must be >= 0");
+    g_grid_ctas_per_sm.store(ctas_per_sm);
+    return RF_OK;
+}
 
 uint64_t rf_debug_fastmod(uint64_t x, uint64_t d) {
     const FastMod m = make_fastmod(d);

@@ -1,0 +1,64 @@
+"""Two-tower recall forward: hashed features -> fused bags -> (SDPA behaviour-sequence encoder) ->
+tower MLPs -> l2-normalise -> in-batch softmax loss.
+
+This is the "recall-SDPA" forward that conf/base_recall_sdpa.yaml describes.  The reference's own
+model for that config, `models/matching/dssm.py:Dssm`, is an unfinished stub (its `call` never uses
+its preprocessor or towers, :38-60), so this class composes the reference's building blocks the way
+its working model does (`models/matching/que2search.py:68-79,114-140`: per-feature
+`self.preprocessor[name](batch[name])`, concat per tower, tower MLP, `self.loss(y, q, a)`), with
+Dssm's tower definition (`create_mlp([1024, 512, 256], 0.3, "selu", BatchNormalization(1e-6))`,
+dssm.py:25-26) and an optional `MultiHeadAttention` encoder (attention_layers.py:137-168) over a
+behaviour sequence, mean-pooled over the sequence, on the user side.
+
+What runs where: every hashed feature of a batch goes through ONE fused kernel launch
+(`forward_all`); SDPA and the B x B logits run on the tcgen05 kernels; tower GEMMs are cuBLAS.
+"""
+import torch
+
+from ...backend.blocks.mlp import BatchNormalization, create_mlp
+from ...backend.layers.attention_layers import MultiHeadAttention
+from ...backend.lossess import match_losses
+from ...backend.utils.preprocess_utils import get_preprocess_layers
+
+
+class RecallSdpa(torch.nn.Module):
+    def __init__(self, feature_conf, loss=None, tower_units=(1024, 512, 256), behaviour_dim=None, num_heads=1,
+                 global_l2_norm=False, name="recall_sdpa"):
+        super().__init__()
+        self._name = name
+        self.feature_conf = feature_conf
+        self.preprocessor = get_preprocess_layers(feature_conf)
+        self.user_cols = [f.name for f in feature_conf.features.get_features(tower="user") if f.name in self.preprocessor]
+        self.ad_cols = [f.name for f in feature_conf.features.get_features(tower="ad") if f.name in self.preprocessor]
+        self.user_dense = create_mlp(list(tower_units), 0.3, "selu", BatchNormalization(epsilon=1e-6), name="user_dense_tower")
+        self.ad_dense = create_mlp(list(tower_units), 0.3, "selu", BatchNormalization(epsilon=1e-6), name="ad_dense_tower")
+        self.seq_encoder = MultiHeadAttention(behaviour_dim, num_heads) if behaviour_dim else None
+        self.loss_fun = loss or match_losses.batch_neg_sample_scaled_multi_class_ce_loss
+        # Dssm.embedding_norm calls K.l2_normalize(x) with no axis = one norm over the whole batch
+        # (dssm.py:36); per-row normalisation is what the in-batch softmax needs, so it is the default
+        self.global_l2_norm = global_l2_norm
+
+    @property
+    def name(self):
+        return self._name
+
+    def embedding_norm(self, x):
+        if self.global_l2_norm:
+            return x / torch.sqrt(torch.clamp((x * x).sum(), min=1e-12))
+        return torch.nn.functional.normalize(x, dim=1, eps=1e-12)
+
+    def towers(self, batch, behaviour=None):
+        embs = self.preprocessor.forward_all(batch, names=self.user_cols + self.ad_cols)
+        user = [embs[n] for n in self.user_cols]
+        if self.seq_encoder is not None and behaviour is not None:
+            x, mask = behaviour
+            user.append(self.seq_encoder(x, x, x, mask).mean(dim=1))
+        u = torch.cat(user, dim=-1)
+        a = torch.cat([embs[n] for n in self.ad_cols], dim=-1)
+        return self.embedding_norm(self.user_dense(u)), self.embedding_norm(self.ad_dense(a))
+
+    def forward(self, batch, y_true=None, behaviour=None, training=False):
+        u, a = self.towers(batch, behaviour)
+        if training:
+            return self.loss_fun(y_true, u, a)
+        return {"user": u, "ad": a, "label": y_true}

@@ -104,6 +104,10 @@ class ShardedEmbeddingBag(torch.nn.Module):
         self.shard = torch.nn.Parameter(torch.empty(max(rows, 1), self.output_dim, dtype=torch.float32,
                                                     device=self.device).uniform_(-0.05, 0.05), requires_grad=False)
         self._bufs = None
+        # pipelined mode: resident CTAs per SM the pooling kernel may take (of 4), so that the routing
+        # kernels of the next step find room on every SM; 0 = no cap
+        import os
+        self.pool_ctas_per_sm = int(os.environ.get("RF_SHARD_POOL_CTAS", "3"))
         self.profile = None      # set to [] to collect (phase name, cuda event) pairs per forward
 
     def _tick(self, phase):
@@ -254,9 +258,15 @@ class ShardedEmbeddingBag(torch.nn.Module):
             # sources in rotated order (me, me+1, ...): at any moment the W owners write their pooled
             # vectors to W different ranks -- a permutation, not an incast on one rank's NVLink port
             order = [(me + k) % W for k in range(W)]
-            self.ops.pool(self.shard.data, [b["rows_recv"][j][s] for s in order],
-                          [b["offs_recv"][j][s] for s in order], [b["peer_partials"][j][s][me] for s in order],
-                          B, partial_op, max(1, ticket["n_keys"] // W))
+            if overlap and self.pool_ctas_per_sm:
+                nat.check(nat.lib().rf_set_bag_grid_limit(self.pool_ctas_per_sm))
+            try:
+                self.ops.pool(self.shard.data, [b["rows_recv"][j][s] for s in order],
+                              [b["offs_recv"][j][s] for s in order], [b["peer_partials"][j][s][me] for s in order],
+                              B, partial_op, max(1, ticket["n_keys"] // W))
+            finally:
+                if overlap and self.pool_ctas_per_sm:
+                    nat.lib().rf_set_bag_grid_limit(0)
             self._tick("pool")
             pooled = None
             if overlap:
