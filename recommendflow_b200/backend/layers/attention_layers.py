@@ -10,8 +10,20 @@ import math
 import numpy as np
 import torch
 
+from ... import dense_ops
 from .layer_utils import scaled_dot_product_attention, split_heads
 from .preprocess_layers import Layer
+
+
+def library_matmul(x, w):
+    """Plain library GEMM (cuBLAS).  In the default "tf32" mode fp32 operands go through the TF32 tensor-core
+    path, which is also TensorFlow's default for fp32 matmuls on Ampere-and-later GPUs."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = dense_ops.DEFAULT_PRECISION == "tf32"
+    try:
+        return torch.matmul(x, w)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
 
 
 class Dense(Layer):
@@ -43,7 +55,7 @@ class Dense(Layer):
 
     def call(self, x):
         self.build(x.shape[-1], x.device)
-        y = torch.matmul(x, self.kernel) + self.bias
+        y = library_matmul(x, self.kernel) + self.bias
         return torch.relu(y) if self.activation == "relu" else y
 
 
@@ -101,8 +113,8 @@ class SelfAttention(Layer):
         if self.add_pos:
             k = k + self.positional_encoding(k)
             q = q + self.positional_encoding(q)
-        q = torch.relu(torch.matmul(q, self.W))
-        k = torch.relu(torch.matmul(k, self.W))
+        q = torch.relu(library_matmul(q, self.W))
+        k = torch.relu(library_matmul(k, self.W))
         # the reference scales by sqrt(self.dim) == sqrt(k.shape[-1]) and tiles the [B, S, 1] mask over keys
         out = scaled_dot_product_attention(q, k, v, mask)
         return out.mean(dim=1)
