@@ -1,0 +1,295 @@
+"""TFRecord / tf.train.Example codec that emits the kernels' input layout directly.
+
+Host-side "next" row of SURVEY.md §8f: the reference writes its training data with
+`utils/make_tfrecord.py` (value encoding :26-41, Example building :87-119, GZIP TFRecordWriter
+:139-144) and reads it back with `tf.io.parse_example` through `build_feature_description`
+(`backend/core/dataloader.py:23-44`).  TensorFlow is not available here, so the wire formats are
+implemented from their public specifications:
+
+  TFRecord framing   u64 length | u32 masked_crc32c(length) | bytes | u32 masked_crc32c(bytes),
+                     masked = rotr(crc, 15) + 0xa282ead8, the whole file optionally GZIP-ed
+  tf.train.Example   Example{1: Features{1: map<string, Feature>}},
+                     Feature{oneof 1: BytesList{1: repeated bytes}, 2: FloatList{1: packed float},
+                                   3: Int64List{1: packed varint}}
+
+`parse_example` densifies like tf.io.parse_example does for the reference's feature description:
+sequence features are padded to the longest list of the BATCH with "" / 0, and string features come
+out as a `StringColumn` (arena + offsets), ready for rf_bag_forward -- no Python string objects
+on the way to the GPU.
+"""
+import gzip
+import struct
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from ..config_parser.config_proto import TYPE_INT, TYPE_STR, FeatureDeal
+from ..strings import StringColumn
+
+# ---- CRC32C (Castagnoli), table driven --------------------------------------------------------
+_CRC_TABLE = []
+for _i in range(256):
+    _c = _i
+    for _ in range(8):
+        _c = (_c >> 1) ^ 0x82F63B78 if _c & 1 else _c >> 1
+    _CRC_TABLE.append(_c)
+
+
+def crc32c(data: bytes) -> int:
+    crc = 0xFFFFFFFF
+    tab = _CRC_TABLE
+    for b in data:
+        crc = tab[(crc ^ b) & 0xFF] ^ (crc >> 8)
+    return crc ^ 0xFFFFFFFF
+
+
+def masked_crc32c(data: bytes) -> int:
+    crc = crc32c(data)
+    return ((((crc >> 15) | (crc << 17)) & 0xFFFFFFFF) + 0xA282EAD8) & 0xFFFFFFFF
+
+
+# ---- protobuf primitives ------------------------------------------------------------------------
+def _varint(n: int) -> bytes:
+    n &= (1 << 64) - 1
+    out = bytearray()
+    while True:
+        b = n & 0x7F
+        n >>= 7
+        if n:
+            out.append(b | 0x80)
+        else:
+            out.append(b)
+            return bytes(out)
+
+
+def _len_field(field_no: int, payload: bytes) -> bytes:
+    return _varint((field_no << 3) | 2) + _varint(len(payload)) + payload
+
+
+def _read_varint(buf, pos):
+    result, shift = 0, 0
+    while True:
+        b = buf[pos]
+        pos += 1
+        result |= (b & 0x7F) << shift
+        if not b & 0x80:
+            return result, pos
+        shift += 7
+
+
+# ---- value encoding of utils/make_tfrecord.py:26-41 ---------------------------------------------
+def _build_int_feature(data):
+    """'1,2,3' -> Int64List (make_tfrecord.py:26)."""
+    vals = [int(i) for i in str(data).split(",")]
+    return _len_field(3, _len_field(1, b"".join(_varint(v) for v in vals)))
+
+
+def _build_float_feature(data):
+    """'0.5,1' -> FloatList (make_tfrecord.py:31)."""
+    vals = [float(i) for i in str(data).split(",")]
+    return _len_field(2, _len_field(1, struct.pack(f"<{len(vals)}f", *vals)))
+
+
+def _build_str_feature(data):
+    """'a,b' -> BytesList; the missing-value marker "-1" becomes one empty string (make_tfrecord.py:36-41)."""
+    data = "" if data == "-1" else str(data)
+    return _len_field(1, b"".join(_len_field(1, i.encode()) for i in data.split(",")))
+
+
+def get_or_ignore_row_data(row, name, na="-1"):
+    return row[name] if name in row else na
+
+
+def build_tfrecord(row, conf):
+    """One row (mapping feature name -> TSV cell) -> serialized tf.train.Example (make_tfrecord.py:87-119).
+    Like the reference, EVERY feature of the config is written, working or not."""
+    entries = []
+    for feature in conf.features.features:
+        cell = get_or_ignore_row_data(row, feature.name)
+        if feature.is_numeric() or feature.is_discrete():
+            value = _build_float_feature(cell)
+        elif feature.is_hashing() or feature.is_bert_encode():
+            value = _build_str_feature(cell)
+        elif feature.is_lookup() and feature.py_type == TYPE_INT:
+            value = _build_int_feature(cell)
+        elif feature.is_lookup() and feature.py_type == TYPE_STR:
+            value = _build_str_feature(cell)
+        elif feature.is_token_id():
+            value = _build_int_feature(cell)
+        else:
+            raise Exception(f"Unsupported deal method feature: {feature}")
+        entry = _len_field(1, feature.name.encode()) + _len_field(2, value)          # map entry {key, value}
+        entries.append(_len_field(1, entry))
+    return _len_field(1, b"".join(entries))                                           # Example.features
+
+
+def dump_tfrecord_data(rows, out_file, conf, compression="GZIP"):
+    """Rows -> GZIP TFRecord file (make_tfrecord.py:139-144)."""
+    opener = gzip.open if compression == "GZIP" else open
+    with opener(out_file, "wb") as fh:
+        for row in rows:
+            rec = build_tfrecord(row, conf)
+            head = struct.pack("<Q", len(rec))
+            fh.write(head + struct.pack("<I", masked_crc32c(head)) + rec + struct.pack("<I", masked_crc32c(rec)))
+
+
+def read_tfrecord(path, compression="GZIP", verify_crc=False):
+    """Yield the serialized records of a (GZIP) TFRecord file."""
+    opener = gzip.open if compression == "GZIP" else open
+    with opener(path, "rb") as fh:
+        while True:
+            head = fh.read(12)
+            if not head:
+                return
+            if len(head) < 12:
+                raise IOError("truncated TFRecord header")
+            (length,), (hcrc,) = struct.unpack("<Q", head[:8]), struct.unpack("<I", head[8:])
+            body = fh.read(length + 4)
+            if len(body) < length + 4:
+                raise IOError("truncated TFRecord body")
+            rec = body[:length]
+            if verify_crc:
+                if masked_crc32c(head[:8]) != hcrc or masked_crc32c(rec) != struct.unpack("<I", body[length:])[0]:
+                    raise IOError("TFRecord CRC mismatch")
+            yield rec
+
+
+def decode_example(rec: bytes):
+    """Serialized Example -> {name: ("bytes", [bytes...]) | ("float", [..]) | ("int64", [..])}."""
+    out = {}
+    pos, end = 0, len(rec)
+    while pos < end:
+        tag, pos = _read_varint(rec, pos)
+        ln, pos = _read_varint(rec, pos)
+        if tag != 0x0A:                       # only Example.features (field 1, length-delimited) exists
+            pos += ln
+            continue
+        fpos, fend = pos, pos + ln
+        pos = fend
+        while fpos < fend:                    # Features.feature map entries
+            tag, fpos = _read_varint(rec, fpos)
+            ln, fpos = _read_varint(rec, fpos)
+            epos, eend = fpos, fpos + ln
+            fpos = eend
+            key, kind, values = None, None, []
+            while epos < eend:                # entry: 1 = key, 2 = Feature
+                tag, epos = _read_varint(rec, epos)
+                ln, epos = _read_varint(rec, epos)
+                if tag == 0x0A:
+                    key = rec[epos:epos + ln].decode()
+                elif tag == 0x12:
+                    vpos, vend = epos, epos + ln
+                    while vpos < vend:        # Feature oneof
+                        ftag, vpos = _read_varint(rec, vpos)
+                        fl, vpos = _read_varint(rec, vpos)
+                        lpos, lend = vpos, vpos + fl
+                        vpos = lend
+                        if ftag == 0x0A:      # BytesList
+                            kind = "bytes"
+                            while lpos < lend:
+                                _, lpos = _read_varint(rec, lpos)
+                                bl, lpos = _read_varint(rec, lpos)
+                                values.append(rec[lpos:lpos + bl])
+                                lpos += bl
+                        elif ftag == 0x12:    # FloatList (packed, or repeated fixed32)
+                            kind = "float"
+                            while lpos < lend:
+                                t, lpos = _read_varint(rec, lpos)
+                                if t == 0x0A:
+                                    pl, lpos = _read_varint(rec, lpos)
+                                    values.extend(struct.unpack(f"<{pl // 4}f", rec[lpos:lpos + pl]))
+                                    lpos += pl
+                                else:
+                                    values.append(struct.unpack("<f", rec[lpos:lpos + 4])[0])
+                                    lpos += 4
+                        elif ftag == 0x1A:    # Int64List (packed, or repeated varint)
+                            kind = "int64"
+                            while lpos < lend:
+                                t, lpos = _read_varint(rec, lpos)
+                                if t == 0x0A:
+                                    pl, lpos = _read_varint(rec, lpos)
+                                    pend = lpos + pl
+                                    while lpos < pend:
+                                        v, lpos = _read_varint(rec, lpos)
+                                        values.append(v - (1 << 64) if v >= (1 << 63) else v)
+                                else:
+                                    v, lpos = _read_varint(rec, lpos)
+                                    values.append(v - (1 << 64) if v >= (1 << 63) else v)
+                epos += ln
+            if key is not None:
+                out[key] = (kind, values)
+    return out
+
+
+# ---- feature description (backend/core/dataloader.py:23-44) and batch parsing ----------------------
+FixedLenFeature = namedtuple("FixedLenFeature", "shape dtype default_value")
+FixedLenSequenceFeature = namedtuple("FixedLenSequenceFeature", "shape dtype allow_missing default_value")
+
+
+def build_feature_description(conf):
+    desc = {}
+    for f in conf.train_features:
+        if f.deal == FeatureDeal.Numeric or f.deal == FeatureDeal.Null:
+            desc[f.name] = FixedLenFeature((), f.type, f.default)
+        elif f.deal in (FeatureDeal.Discrete, FeatureDeal.Hashing, FeatureDeal.Lookup):
+            desc[f.name] = FixedLenSequenceFeature((), f.type, True, f.default)
+        elif f.deal == FeatureDeal.TokenId:
+            desc[f.name] = FixedLenSequenceFeature((), conf.features.features[0].type.__class__("int64", "int64"), True, 0)
+        elif f.deal == FeatureDeal.BertEncode:
+            desc[f.name] = FixedLenFeature((1,), f.type, "")
+        elif f.deal in (FeatureDeal.Image, FeatureDeal.Embedding):
+            desc[f.name] = FixedLenFeature((), f.type, f.default)
+        else:
+            raise Exception(f"Unregister Feature: {f.name}")
+    return desc
+
+
+def parse_example(records, feature_description):
+    """tf.io.parse_example for the reference's description: a batch of serialized Examples -> dict of dense
+    batch tensors.  Sequence features pad to the batch's longest list with the default ("" / 0 / 0.0);
+    string features come out as StringColumn [B, Lmax]."""
+    decoded = [decode_example(r) for r in records]
+    B = len(decoded)
+    out = {}
+    for name, spec in feature_description.items():
+        is_str = spec.dtype.name == "string"
+        lists = []
+        for ex in decoded:
+            kind, vals = ex.get(name, (None, []))
+            lists.append(list(vals))
+        if isinstance(spec, FixedLenSequenceFeature):
+            L = max((len(v) for v in lists), default=0)
+            if is_str:
+                out[name] = StringColumn.from_lists([v + [b""] * (L - len(v)) for v in lists] if L else [[] for _ in lists])
+            else:
+                np_dtype = np.int64 if spec.dtype.name == "int64" else np.float32
+                arr = np.full((B, L), spec.default_value, dtype=np_dtype)
+                for i, v in enumerate(lists):
+                    arr[i, :len(v)] = v
+                out[name] = torch.from_numpy(arr)
+        else:
+            if is_str:
+                flat = [(v[0] if v else (spec.default_value.encode() if isinstance(spec.default_value, str) else b"")) for v in lists]
+                out[name] = StringColumn.from_lists([[x] for x in flat])
+            else:
+                np_dtype = np.int64 if spec.dtype.name == "int64" else np.float32
+                out[name] = torch.from_numpy(np.array([v[0] if v else spec.default_value for v in lists], dtype=np_dtype))
+    return out
+
+
+def load_tfrecord(paths, conf, batch_size, compression="GZIP", drop_remainder=False):
+    """Minimal `_get_tfrecord_dataset` (dataloader.py:541-578): batches of (features, labels) dicts."""
+    desc = build_feature_description(conf)
+    label_names = conf.features.label_names
+    buf = []
+    for path in ([paths] if isinstance(paths, str) else paths):
+        for rec in read_tfrecord(path, compression):
+            buf.append(rec)
+            if len(buf) == batch_size:
+                ex = parse_example(buf, desc)
+                yield ex, {n: ex[n] for n in label_names if n in ex}
+                buf = []
+    if buf and not drop_remainder:
+        ex = parse_example(buf, desc)
+        yield ex, {n: ex[n] for n in label_names if n in ex}
