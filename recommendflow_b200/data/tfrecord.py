@@ -24,7 +24,7 @@ from collections import namedtuple
 import numpy as np
 import torch
 
-from ..config_parser.config_proto import TYPE_INT, TYPE_STR, FeatureDeal
+from ..config_parser.config_proto import TYPE_INT, TYPE_STR, FeatureDeal, int64 as INT64
 from ..strings import StringColumn
 
 # ---- CRC32C (Castagnoli), table driven --------------------------------------------------------
@@ -235,7 +235,7 @@ def build_feature_description(conf):
         elif f.deal in (FeatureDeal.Discrete, FeatureDeal.Hashing, FeatureDeal.Lookup):
             desc[f.name] = FixedLenSequenceFeature((), f.type, True, f.default)
         elif f.deal == FeatureDeal.TokenId:
-            desc[f.name] = FixedLenSequenceFeature((), conf.features.features[0].type.__class__("int64", "int64"), True, 0)
+            desc[f.name] = FixedLenSequenceFeature((), INT64, True, 0)
         elif f.deal == FeatureDeal.BertEncode:
             desc[f.name] = FixedLenFeature((1,), f.type, "")
         elif f.deal in (FeatureDeal.Image, FeatureDeal.Embedding):
