@@ -7,9 +7,10 @@
 //
 //   operands   fp32 in HBM, read as TF32 (kind::tf32: the tensor core uses the top 19 bits; this is
 //              what TensorFlow itself does for fp32 matmuls on Ampere+ GPUs), fp32 accumulate.
-//   tile       128 (query rows) x 256 (docs) x 32 (K, one 128-byte swizzle atom) per stage,
-//              4-stage TMA -> smem ring, 4 x tcgen05.mma (K = 8) per stage, accumulator 128 lanes x
-//              256 columns of TMEM.
+//   tile       128 (query rows) x 256 (docs) x 32 (K, one 128-byte swizzle atom) per stage; for
+//              dim <= 256 the CTA's query tile is loaded ONCE and stays resident, only doc tiles stream
+//              (3-stage TMA -> smem ring); 4 x tcgen05.mma (K = 8) per stage; TWO 128-lane x 256-column
+//              TMEM accumulators, so the MMAs of tile i+1 run under the epilogue of tile i.
 //   warps      0: TMA producer (one elected lane)   1: TMEM alloc + MMA issue (one elected lane)
 //              2-5: epilogue -- each thread owns one query row (= one TMEM lane), pulls 32 columns at
 //              a time with tcgen05.ld and keeps running (max, sum exp, hinge, max-off-diagonal).
@@ -37,13 +38,21 @@ struct RowStat {
 
 constexpr int kBM = 128, kBN = 256, kBK = 32;       // tile; kBK fp32 = 128 bytes = one SW128 atom row
 constexpr int kUmmaK = 8;                           // tf32: 32 bytes per MMA along K
-constexpr int kStages = 4;
 constexpr int kABytes = kBM * kBK * 4;              // 16 KiB
 constexpr int kBBytes = kBN * kBK * 4;              // 32 KiB
-constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kTmemCols = 256;
+// A_RES = true (dim <= 256): the CTA's query tile stays in shared memory for all of its column tiles
+// (8 x 16 KiB) and only doc tiles stream through a 3-stage ring -- L2 -> SM traffic per tile drops from
+// 384 KiB to 256 KiB, which is what bounds this fp32-operand kernel.  A_RES = false: both stream, 4 stages.
+constexpr int kMaxResidentKB = 8;
+constexpr int kTmemCols = 512;                      // two 128 x 256 fp32 accumulators: MMA(i+1) overlaps epilogue(i)
 constexpr int kTcThreads = 192;
-constexpr size_t kTcSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+template <bool A_RES> struct TcCfg {
+    static constexpr int kStages = A_RES ? 3 : 4;
+    static constexpr int kStageBytes = A_RES ? kBBytes : kABytes + kBBytes;
+    static constexpr size_t smem_bytes(int n_kb) {
+        return (size_t)(A_RES ? n_kb * kABytes : 0) + (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    }
+};
 
 // ---- PTX helpers --------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -122,29 +131,37 @@ constexpr uint32_t kInstrDesc = (1u << 4)                 // c_format = F32
                                 | (2u << 10)              // b_format = TF32
                                 | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 
-template <bool FULL_STATS>
+template <bool FULL_STATS, bool A_RES>
 __global__ void __launch_bounds__(kTcThreads, 1)
 logits_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_d,
                  const float *__restrict__ diag, const float *__restrict__ colw, int B, int Dt, float scale, float margin,
                  int n_tiles, int tiles_per_cta, RowStat *__restrict__ part) {
     extern __shared__ uint8_t smem_raw[];
+    constexpr int kStages = TcCfg<A_RES>::kStages;
+    constexpr int kStageBytes = TcCfg<A_RES>::kStageBytes;
+    const int n_kb = (Dt + kBK - 1) / kBK;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SW128 atoms need 1024-byte alignment
-    const uint32_t bars = smem_base + kStages * kStageBytes;                    // full[4], empty[4], tmem_full, tmem_empty
-    const uint32_t full0 = bars, empty0 = bars + 8 * kStages, tmem_full = bars + 16 * kStages, tmem_empty = tmem_full + 8;
-    const uint32_t tmem_slot = tmem_empty + 8;
+    const uint32_t a_res = smem_base;                                           // A_RES: n_kb resident query blocks
+    const uint32_t ring = smem_base + (A_RES ? n_kb * kABytes : 0);
+    const uint32_t bars = ring + kStages * kStageBytes;
+    const uint32_t full0 = bars, empty0 = bars + 8 * kStages;                   // full[s], empty[s]
+    const uint32_t tmem_full0 = bars + 16 * kStages, tmem_empty0 = tmem_full0 + 16;   // [2] each
+    const uint32_t a_full = tmem_empty0 + 16, tmem_slot = a_full + 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tile = blockIdx.x;
     const int tile0 = blockIdx.y * tiles_per_cta;
     const int tile1 = min(n_tiles, tile0 + tiles_per_cta);
-    const int n_kb = (Dt + kBK - 1) / kBK;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full0 + 8 * s, 1);
             mbar_init(empty0 + 8 * s, 1);
         }
-        mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 4);                  // one arrive per epilogue warp
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full0 + 8 * a, 1);
+            mbar_init(tmem_empty0 + 8 * a, 4);     // one arrive per epilogue warp
+        }
+        mbar_init(a_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {                                // whole warp: allocate the accumulator columns
@@ -161,13 +178,17 @@ logits_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
+            if (A_RES && tile0 < tile1) {
+                mbar_expect_tx(a_full, (uint32_t)(n_kb * kABytes));
+                for (int kb = 0; kb < n_kb; ++kb) tma_load_2d(a_res + kb * kABytes, &map_q, a_full, kb * kBK, m_tile * kBM);
+            }
             for (int tile = tile0; tile < tile1; ++tile) {
                 for (int kb = 0; kb < n_kb; ++kb) {
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                    const uint32_t a_dst = smem_base + stage * kStageBytes;
+                    const uint32_t dst = ring + stage * kStageBytes;
                     mbar_expect_tx(full0 + 8 * stage, kStageBytes);
-                    tma_load_2d(a_dst, &map_q, full0 + 8 * stage, kb * kBK, m_tile * kBM);
-                    tma_load_2d(a_dst + kABytes, &map_d, full0 + 8 * stage, kb * kBK, tile * kBN);
+                    if (!A_RES) tma_load_2d(dst, &map_q, full0 + 8 * stage, kb * kBK, m_tile * kBM);
+                    tma_load_2d(dst + (A_RES ? 0 : kABytes), &map_d, full0 + 8 * stage, kb * kBK, tile * kBN);
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -180,19 +201,21 @@ logits_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             int local = 0;
+            if (A_RES && tile0 < tile1) mbar_wait(a_full, 0);
             for (int tile = tile0; tile < tile1; ++tile, ++local) {
-                mbar_wait(tmem_empty, (local & 1) ^ 1);          // epilogue has drained the accumulator
+                const uint32_t acc = (uint32_t)(local & 1);
+                mbar_wait(tmem_empty0 + 8 * acc, ((uint32_t)(local >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int kb = 0; kb < n_kb; ++kb) {
                     mbar_wait(full0 + 8 * stage, phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_addr = smem_base + stage * kStageBytes;
-                    const uint64_t adesc = umma_desc_sw128(a_addr);
-                    const uint64_t bdesc = umma_desc_sw128(a_addr + kABytes);
+                    const uint32_t st_addr = ring + stage * kStageBytes;
+                    const uint64_t adesc = umma_desc_sw128(A_RES ? a_res + kb * kABytes : st_addr);
+                    const uint64_t bdesc = umma_desc_sw128(A_RES ? st_addr : st_addr + kABytes);
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
                         // step 32 bytes along K inside the swizzle atom: +2 in the (>>4) address field
-                        umma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kInstrDesc,
+                        umma_tf32(tmem_base + acc * (uint32_t)kBN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kInstrDesc,
                                   (kb | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(empty0 + 8 * stage);            // frees the smem stage when these MMAs retire
@@ -201,7 +224,7 @@ logits_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         phase ^= 1;
                     }
                 }
-                umma_commit(tmem_full);                         // accumulator complete
+                umma_commit(tmem_full0 + 8 * acc);              // accumulator complete
             }
         }
     } else {
@@ -214,13 +237,14 @@ logits_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         float rm = -INFINITY, rl = 0.f, rh = 0.f, rx = -INFINITY;
         int local = 0;
         for (int tile = tile0; tile < tile1; ++tile, ++local) {
-            mbar_wait(tmem_full, local & 1);
+            const uint32_t acc = (uint32_t)(local & 1);
+            mbar_wait(tmem_full0 + 8 * acc, (uint32_t)(local >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int col_tile0 = tile * kBN;
 #pragma unroll 1
             for (int c0 = 0; c0 < kBN; c0 += 32) {
                 float v[32];
-                tmem_ld32(lane_addr + (uint32_t)c0, v);
+                tmem_ld32(lane_addr + acc * (uint32_t)kBN + (uint32_t)c0, v);
                 const int col0 = col_tile0 + c0;
                 if (col0 >= B) continue;
                 const int n_valid = min(32, B - col0);
@@ -253,7 +277,7 @@ logits_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty);
+            if (lane == 0) mbar_arrive(tmem_empty0 + 8 * acc);
         }
         if (row < B) part[(size_t)blockIdx.y * B + row] = RowStat{rm, rl, rh, rx};
     }
@@ -307,22 +331,41 @@ int launch_logits_tc(const float *q, const float *d, const float *diag, const fl
     if (rc != RF_OK) return rc;
     const int m_tiles = (B + kBM - 1) / kBM;
     const int n_tiles = (B + kBN - 1) / kBN;
-    int groups = (2 * 148 + m_tiles - 1) / m_tiles;        // aim at >= 2 CTAs per SM overall
-    if (groups < 1) groups = 1;
-    if (groups > n_tiles) groups = n_tiles;
-    if (groups > max_splits) groups = max_splits;
+    const int n_kb = (Dt + kBK - 1) / kBK;
+    const bool a_res = n_kb <= kMaxResidentKB;
+    // column groups: one CTA per SM is resident, so choose the split that minimises
+    // waves x (tiles per CTA + the one-off query-tile load)
+    int dev = 0, sms = 148;
+    RF_CUDA(cudaGetDevice(&dev));
+    RF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int groups = 1;
+    double best = 1e30;
+    for (int g = 1; g <= n_tiles && g <= max_splits; ++g) {
+        const int tpc = (n_tiles + g - 1) / g;
+        const int g_eff = (n_tiles + tpc - 1) / tpc;
+        const double waves = (double)(((int64_t)m_tiles * g_eff + sms - 1) / sms);
+        const double cost = waves * (tpc + 0.5);
+        if (cost < best - 1e-9) {
+            best = cost;
+            groups = g_eff;
+        }
+    }
     const int tiles_per_cta = (n_tiles + groups - 1) / groups;
     groups = (n_tiles + tiles_per_cta - 1) / tiles_per_cta;
     *splits = groups;
-    if (full_stats) {
-        RF_CUDA(cudaFuncSetAttribute(logits_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-        logits_tc_kernel<true><<<dim3(m_tiles, groups), kTcThreads, kTcSmemBytes, st>>>(mq, md, diag, colw, B, Dt, scale, margin,
-                                                                                        n_tiles, tiles_per_cta, part);
-    } else {
-        RF_CUDA(cudaFuncSetAttribute(logits_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-        logits_tc_kernel<false><<<dim3(m_tiles, groups), kTcThreads, kTcSmemBytes, st>>>(mq, md, diag, colw, B, Dt, scale, margin,
-                                                                                         n_tiles, tiles_per_cta, part);
-    }
+    const dim3 grid(m_tiles, groups);
+#define RF_LAUNCH_TC(FULL, ARES)                                                                                          \
+    do {                                                                                                                  \
+        const size_t smem = TcCfg<ARES>::smem_bytes(n_kb);                                                                \
+        RF_CUDA(cudaFuncSetAttribute(logits_tc_kernel<FULL, ARES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        logits_tc_kernel<FULL, ARES><<<grid, kTcThreads, smem, st>>>(mq, md, diag, colw, B, Dt, scale, margin, n_tiles,     \
+                                                                    tiles_per_cta, part);                                 \
+    } while (0)
+    if (full_stats && a_res) RF_LAUNCH_TC(true, true);
+    else if (full_stats) RF_LAUNCH_TC(true, false);
+    else if (a_res) RF_LAUNCH_TC(false, true);
+    else RF_LAUNCH_TC(false, false);
+#undef RF_LAUNCH_TC
     RF_CUDA(cudaGetLastError());
     g_launches.fetch_add(1);
     return RF_OK;
