@@ -171,6 +171,14 @@ int rf_combine_partials(const float *d_partials, int world, int64_t batch, int32
                         int32_t bag_len, const int32_t *d_bag_offsets, float *d_out, int64_t out_stride,
                         void *stream);
 
+/* ---- backward of a pooled bag, fused with the row update ("next" row) ------------ */
+/* W[ids[k]] += alpha * grad_out[bag(k)] (x 1/count for avg) for every key k; alpha = -lr is the    */
+/* SGD step of the reference's Embedding variables (pads included: row 0 collects their gradient). */
+/* d_ids: the bucket ids the forward produced (rf_field_desc.ids_out, one table's slice).           */
+int rf_bag_backward(const int64_t *d_ids, int64_t n_keys, const int32_t *d_bag_offsets, int32_t bag_len,
+                    int64_t batch, const float *d_grad_out, int64_t grad_stride, int32_t dim, int combiner,
+                    float alpha, float *d_table, void *stream);
+
 /* Cap the fused kernel's grid at ctas_per_sm x #SMs (0 = no cap; it then walks its tiles            */
 /* grid-stride).  Leaves room on every SM for kernels of other streams (the sharded pipeline).     */
 int rf_set_bag_grid_limit(int ctas_per_sm);

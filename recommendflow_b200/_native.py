@@ -54,6 +54,8 @@ def lib():
         L.rf_hash_int64.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_int,
                                     C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
         L.rf_bag_forward.argtypes = [C.POINTER(FieldDesc), C.c_int, C.c_int64, C.c_void_p]
+        L.rf_bag_backward.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
+                                      C.c_int, C.c_float, C.c_void_p, C.c_void_p]
         L.rf_sdpa_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                       C.c_void_p, C.c_void_p]
         L.rf_sdpa_forward_tc.argtypes = L.rf_sdpa_forward.argtypes
@@ -72,7 +74,7 @@ def lib():
                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
         L.rf_combine_partials.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int, C.c_int32, C.c_void_p,
                                           C.c_void_p, C.c_int64, C.c_void_p]
-        for name in ("rf_hash_strings", "rf_hash_int64", "rf_bag_forward", "rf_shard_route", "rf_shard_route_keys", "rf_set_bag_grid_limit", "rf_sdpa_forward", "rf_sdpa_forward_tc", "rf_inbatch_rowstats", "rf_inbatch_rowstats_tc",
+        for name in ("rf_hash_strings", "rf_hash_int64", "rf_bag_forward", "rf_shard_route", "rf_shard_route_keys", "rf_set_bag_grid_limit", "rf_bag_backward", "rf_sdpa_forward", "rf_sdpa_forward_tc", "rf_inbatch_rowstats", "rf_inbatch_rowstats_tc",
                      "rf_combine_partials"):
             getattr(L, name).restype = C.c_int
         _lib = L

@@ -195,3 +195,22 @@ def hash_ints(values, num_bins, mask_value=None, salt=None):
                                               out.data_ptr(),
                                               C.c_void_p(torch.cuda.current_stream(vals.device).cuda_stream)))
     return out
+
+
+def bag_backward(ids, table, grad_out, alpha, combiner="sum", bag_len=None, bag_offsets=None):
+    """table[ids[k]] += alpha * grad_out[bag(k)] (x 1/count for "avg"), in place.  `ids`: the int64 bucket ids
+    of ONE table as the forward wrote them (ids_out[t]); alpha = -lr fuses the SGD step."""
+    ids = _require_cuda(ids, "ids").contiguous().view(-1)
+    _require_cuda(table, "table")
+    g = _require_cuda(grad_out, "grad_out")
+    if g.dtype != torch.float32 or g.dim() != 2 or g.stride(1) != 1 or g.shape[1] != table.shape[1]:
+        raise ValueError("grad_out must be fp32 [batch, dim] with contiguous columns")
+    if table.dtype != torch.float32 or not table.is_contiguous():
+        raise ValueError("table must be contiguous fp32")
+    batch = g.shape[0]
+    with torch.cuda.device(table.device):
+        nat.check(nat.lib().rf_bag_backward(ids.data_ptr(), ids.numel(), None if bag_offsets is None else bag_offsets.data_ptr(),
+                                            bag_len or 0, batch, g.data_ptr(), g.stride(0), table.shape[1],
+                                            nat.COMBINER[combiner], float(alpha), table.data_ptr(),
+                                            C.c_void_p(torch.cuda.current_stream(table.device).cuda_stream)))
+    return table

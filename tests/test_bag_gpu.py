@@ -248,3 +248,41 @@ def test_cuda_graph_capture_and_replay_with_new_keys():
         a, o = arenas[i]
         want = oracle.hashed_bag_forward(a, o, B, L, ws, [N, N], [[2022, 2022], [2023, 2023]], "sum")
         assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32)), i
+
+
+@pytest.mark.parametrize("combiner,D", [("sum", 64), ("avg", 16), ("sum", 6)])
+def test_backward_sgd_matches_numpy(combiner, D):
+    # gradient of the pooled bag w.r.t. every gathered row (pads included), fused with W -= lr * g.
+    # Atomics make the add order free: compare within fp32 re-association of the duplicates.
+    from recommendflow_b200.bag_ops import bag_backward
+    rng = np.random.default_rng(18)
+    B, L, N = 700, 5, 997
+    arena, offs = random_strings(rng, B * L, max_len=6, alphabet=ALNUM, empty_frac=0.3)
+    (w,) = tables(rng, 1, N, D)
+    ids = oracle.hash_strings(arena, offs, N, "", [2022, 2022])
+    g = rng.standard_normal((B, D)).astype(np.float32)
+    lr = 0.1
+    want = w.astype(np.float64).copy()
+    np.add.at(want, ids, -lr * np.repeat(g.astype(np.float64), L, axis=0) / (L if combiner == "avg" else 1))
+    col = column(arena, offs, (B, L))
+    dev_w = torch.from_numpy(w).cuda()
+    out = torch.empty(B, D, device="cuda")
+    ids_out = torch.empty(1, B * L, dtype=torch.int64, device="cuda")
+    bag_forward([FieldCall([(dev_w, N, [2022, 2022])], D, combiner, keys=col, mask_mode=nat.MASK_EMPTY_STRING, out=out,
+                           ids_out=ids_out, bag_len=L)], B)
+    assert np.array_equal(ids_out.cpu().numpy().ravel(), ids)
+    bag_backward(ids_out[0], dev_w, torch.from_numpy(g).cuda(), -lr, combiner, bag_len=L)
+    np.testing.assert_allclose(dev_w.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+    # jagged bags
+    lens = rng.integers(0, 9, size=B)
+    bag = np.zeros(B + 1, dtype=np.int32)
+    bag[1:] = np.cumsum(lens)
+    n = int(bag[-1])
+    jid = rng.integers(0, N, size=n)
+    want = w.astype(np.float64).copy()
+    scale = np.repeat(1.0 / np.maximum(lens, 1), lens) if combiner == "avg" else np.ones(n)
+    np.add.at(want, jid, 0.5 * np.repeat(g.astype(np.float64), lens, axis=0) * scale[:, None])
+    dev_w = torch.from_numpy(w).cuda()
+    bag_backward(torch.from_numpy(jid).cuda(), dev_w, torch.from_numpy(g).cuda(), 0.5, combiner,
+                 bag_offsets=torch.from_numpy(bag).cuda())
+    np.testing.assert_allclose(dev_w.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
