@@ -45,44 +45,85 @@ __device__ __forceinline__ void bag_range(const int32_t *boffs, int bag_len, int
     }
 }
 
-// counts[g * batch + b] = #keys of bag b owned by rank g.  One warp per bag.  With HASH the keys
-// are still strings: each lane hashes its key straight from global memory (the loads of the
-// other warps hide the latency) and leaves the bucket id in ids_ws for the scatter pass, so the
-// sharded path needs no separate hashing pass over the batch.
+// counts[g * batch + b] = #keys of bag b owned by rank g.
+// A CTA takes a run of consecutive bags (~kCntCap keys).  Pass 1 -- one key per thread, every lane
+// busy, coalesced offsets and neighbouring key bytes: hash the key (strings, straight from global
+// memory) or fetch its id, keep it in shared memory and (HASH) leave it in ids_ws for the scatter
+// pass.  Pass 2 -- one warp per bag counts owners out of shared memory with ballots.  A bag longer
+// than the staging capacity is counted by one warp directly from global memory.
+constexpr int kCntCap = 4096;
+constexpr int kCntThreads = 256;
+
 template <bool HASH>
-__global__ void __launch_bounds__(256) shard_count_kernel(const int64_t *__restrict__ ids, const uint8_t *__restrict__ bytes,
-                                                          const int32_t *__restrict__ soffs, HashSpec spec, int mask_empty,
-                                                          int64_t *__restrict__ ids_ws, const int32_t *__restrict__ boffs,
-                                                          int bag_len, int64_t batch, int world, int32_t *__restrict__ counts) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t b = warp0; b < batch; b += n_warps) {
-        int64_t lo, hi;
-        bag_range(boffs, bag_len, b, lo, hi);
-        int mine = 0;   // lane g accumulates the count for owner g
-        for (int64_t i = lo; i < hi; i += 32) {
-            const bool on = i + lane < hi;
-            uint32_t id = 0;           // bucket ids fit 32 bits (num_bins <= 2^32 - 1): 32-bit div/mod
-            if (on) {
-                if (HASH) {
-                    const int32_t o = soffs[i + lane];
-                    const uint32_t len = (uint32_t)(soffs[i + lane + 1] - o);
-                    const uintptr_t a = reinterpret_cast<uintptr_t>(bytes) + (uintptr_t)o;
-                    const WordSrcGlobal src{reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3), (uint32_t)(a & 3u)};
-                    id = bucket_of(src, len, spec, mask_empty && len == 0);
-                    ids_ws[i + lane] = (int64_t)id;
-                } else {
-                    id = (uint32_t)ids[i + lane];
+__device__ __forceinline__ uint32_t key_id(int64_t k, const int64_t *ids, const uint8_t *bytes, const int32_t *soffs,
+                                           const HashSpec &spec, int mask_empty) {
+    if (!HASH) return (uint32_t)ids[k];
+    const int32_t o = soffs[k];
+    const uint32_t len = (uint32_t)(soffs[k + 1] - o);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(bytes) + (uintptr_t)o;
+    const WordSrcGlobal src{reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3), (uint32_t)(a & 3u)};
+    return bucket_of(src, len, spec, mask_empty && len == 0);
+}
+
+template <bool HASH>
+__global__ void __launch_bounds__(kCntThreads) shard_count_kernel(const int64_t *__restrict__ ids, const uint8_t *__restrict__ bytes,
+                                                                  const int32_t *__restrict__ soffs, HashSpec spec, int mask_empty,
+                                                                  int64_t *__restrict__ ids_ws, const int32_t *__restrict__ boffs,
+                                                                  int bag_len, int64_t batch, int world, int tile_bags,
+                                                                  int32_t *__restrict__ counts) {
+    __shared__ uint32_t sid[kCntCap];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t n_tiles = (batch + tile_bags - 1) / tile_bags;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t t0 = tile * tile_bags, t1 = min(batch, t0 + tile_bags);
+        int64_t r0 = t0;
+        while (r0 < t1) {
+            int64_t k0, dummy;
+            bag_range(boffs, bag_len, r0, k0, dummy);
+            int64_t r1 = r0, k1 = k0;
+            while (r1 < t1) {                           // whole bags, <= kCntCap keys (uniform across the CTA)
+                int64_t lo, hi;
+                bag_range(boffs, bag_len, r1, lo, hi);
+                if (hi - k0 > kCntCap && r1 > r0) break;
+                k1 = hi;
+                ++r1;
+                if (hi - k0 > kCntCap) break;
+            }
+            const bool staged = k1 - k0 <= kCntCap;
+            if (staged) {
+                for (int64_t k = k0 + tid; k < k1; k += kCntThreads) {
+                    const uint32_t id = key_id<HASH>(k, ids, bytes, soffs, spec, mask_empty);
+                    sid[k - k0] = id;
+                    if (HASH) ids_ws[k] = (int64_t)id;
                 }
+                __syncthreads();
             }
-            const int owner = on ? (int)(id % (uint32_t)world) : -1;
-            for (int g = 0; g < world; ++g) {
-                const unsigned m = __ballot_sync(0xffffffffu, owner == g);
-                if (lane == g) mine += __popc(m);
+            for (int64_t b = r0 + wid; b < r1; b += kCntThreads / 32) {
+                int64_t lo, hi;
+                bag_range(boffs, bag_len, b, lo, hi);
+                int mine = 0;                           // lane g accumulates the count of owner g
+                for (int64_t i = lo; i < hi; i += 32) {
+                    const bool on = i + lane < hi;
+                    uint32_t id = 0;
+                    if (on) {
+                        if (staged) {
+                            id = sid[i + lane - k0];
+                        } else {
+                            id = key_id<HASH>(i + lane, ids, bytes, soffs, spec, mask_empty);
+                            if (HASH) ids_ws[i + lane] = (int64_t)id;
+                        }
+                    }
+                    const int owner = on ? (int)(id % (uint32_t)world) : -1;
+                    for (int g = 0; g < world; ++g) {
+                        const unsigned m = __ballot_sync(0xffffffffu, owner == g);
+                        if (lane == g) mine += __popc(m);
+                    }
+                }
+                if (lane < world) counts[(int64_t)lane * batch + b] = mine;
             }
+            __syncthreads();
+            r0 = r1;
         }
-        if (lane < world) counts[(int64_t)lane * batch + b] = mine;
     }
 }
 
@@ -389,24 +430,24 @@ static int route_impl(const int64_t *d_ids, const uint8_t *d_bytes, const int32_
         if (!rows.p[g]) return set_error(RF_ERR_INVALID, "rf_shard_route: rows_dst[%d] is NULL", g);
     }
     const int grid = grid_for(batch, 8, sms);   // 8 warps (bags) per 256-thread block
-    if (spec)
-        shard_count_kernel<true><<<grid, 256, 0, st>>>(nullptr, d_bytes, d_str_offsets, *spec, mask_empty, d_ids_ws,
-                                                       d_bag_offsets, bag_len, batch, world, d_counts_ws);
-    else
-        shard_count_kernel<false><<<grid, 256, 0, st>>>(d_ids, nullptr, nullptr, HashSpec{}, 0, nullptr, d_bag_offsets,
-                                                        bag_len, batch, world, d_counts_ws);
-    const int n_chunks = (int)((batch + kScanChunk - 1) / kScanChunk);
-    int32_t *excl = d_offsets_local;                         // [world][batch]
-    int32_t *chunk_tot = d_offsets_local + (int64_t)world * batch;   // [world][n_chunks]
-    shard_scan_kernel<<<dim3(n_chunks, world), kScanChunk, 0, st>>>(d_counts_ws, batch, n_chunks, excl, chunk_tot);
-    shard_chunk_base_kernel<<<world, 1024, 0, st>>>(chunk_tot, n_chunks, batch, offs);
-    // scatter tiles: ~kScatCap keys of consecutive bags per CTA round (the mean bag length is only
-    // known on the device in jagged mode: size tiles for 128 keys/bag there, rounds adapt)
+    // tiles of consecutive bags: ~4096 keys per CTA round (jagged: sized for 128 keys/bag, rounds adapt)
     const int64_t per_bag = d_bag_offsets ? 128 : (bag_len > 0 ? bag_len : 1);
     int64_t tile_bags = kScatCap / per_bag;
     if (tile_bags < 8) tile_bags = 8;
     if (tile_bags > 512) tile_bags = 512;
     const int sgrid = grid_for((batch + tile_bags - 1) / tile_bags, 1, sms);
+    if (spec)
+        shard_count_kernel<true><<<sgrid, kCntThreads, 0, st>>>(nullptr, d_bytes, d_str_offsets, *spec, mask_empty, d_ids_ws,
+                                                                d_bag_offsets, bag_len, batch, world, (int)tile_bags, d_counts_ws);
+    else
+        shard_count_kernel<false><<<sgrid, kCntThreads, 0, st>>>(d_ids, nullptr, nullptr, HashSpec{}, 0, nullptr, d_bag_offsets,
+                                                                 bag_len, batch, world, (int)tile_bags, d_counts_ws);
+    const int n_chunks = (int)((batch + kScanChunk - 1) / kScanChunk);
+    int32_t *excl = d_offsets_local;                         // [world][batch]
+    int32_t *chunk_tot = d_offsets_local + (int64_t)world * batch;   // [world][n_chunks]
+    shard_scan_kernel<<<dim3(n_chunks, world), kScanChunk, 0, st>>>(d_counts_ws, batch, n_chunks, excl, chunk_tot);
+    shard_chunk_base_kernel<<<world, 1024, 0, st>>>(chunk_tot, n_chunks, batch, offs);
+    // the scatter pass walks the same tiles
     static const bool tiled = !(getenv("RF_SCATTER_TILED") && atoi(getenv("RF_SCATTER_TILED")) == 0);
     if (tiled)
         shard_scatter_kernel<<<sgrid, kScatThreads, 0, st>>>(spec ? d_ids_ws : d_ids, d_bag_offsets, bag_len, batch, world,
