@@ -74,6 +74,9 @@ typedef struct rf_field_desc {
     const int64_t *ids;          /* device [n_tables][n_items] pre-hashed row ids (no hashing) */
     /* --- bags -------------------------------------------------------------------------------- */
     const int32_t *bag_offsets;  /* device [batch + 1] CSR over items (jagged mode), or NULL   */
+    const int32_t *bag_ends;     /* optional device [batch]: bag b = [bag_offsets[b],          */
+                                 /* bag_ends[b]) -- bags in order but with gaps between them   */
+                                 /* (then bag_offsets needs only [batch] entries)              */
     int64_t n_items;             /* jagged mode: total items (= bag_offsets[batch]); dense     */
                                  /* mode derives batch * bag_len and ignores this              */
     int32_t bag_len;             /* dense mode (bag_offsets == NULL): items per bag, pads      */
@@ -166,6 +169,17 @@ int rf_shard_route_keys(const uint8_t *d_bytes, const int32_t *d_str_offsets, in
                         const int32_t *d_bag_offsets, int32_t bag_len, int64_t batch, int world,
                         int32_t *d_counts_ws, int32_t *d_offsets_local, int32_t *const *h_offsets_dst,
                         int64_t *const *h_rows_dst, void *stream);
+/* Single-pass routing into the "tile" layout (no global scan, one kernel): for every owner g the */
+/* owner-local rows of this source's keys k0..k1 land in [k0, k0 + n_g) of h_rows_dst[g] (int64,  */
+/* capacity = this rank's key count; the rest of each range stays unused) and bag b's run is      */
+/* [h_begin_dst[g][b], h_end_dst[g][b]) -- feed them to rf_bag_forward as ids / bag_offsets /     */
+/* bag_ends.  Keys are strings (d_bytes + d_str_offsets, hashed on the fly; d_ids_ws receives the */
+/* ids) or pre-hashed d_ids.                                                                       */
+int rf_shard_route_tiles(const uint8_t *d_bytes, const int32_t *d_str_offsets, const int64_t *d_ids,
+                         int64_t num_bins, int mask_mode, int use_strong, uint64_t key0, uint64_t key1,
+                         int64_t *d_ids_ws, const int32_t *d_bag_offsets, int32_t bag_len, int64_t batch,
+                         int world, int64_t *const *h_rows_dst, int32_t *const *h_begin_dst,
+                         int32_t *const *h_end_dst, void *stream);
 /* out[b] = reduce_{g<world, in rank order} partials[g][b][:]; avg divides by the bag's key count */
 int rf_combine_partials(const float *d_partials, int world, int64_t batch, int32_t dim, int combiner,
                         int32_t bag_len, const int32_t *d_bag_offsets, float *d_out, int64_t out_stride,

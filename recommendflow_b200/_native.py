@@ -22,7 +22,7 @@ class TableDesc(C.Structure):
 
 class FieldDesc(C.Structure):
     _fields_ = [("bytes", C.c_void_p), ("str_offsets", C.c_void_p), ("int_values", C.c_void_p),
-                ("ids", C.c_void_p), ("bag_offsets", C.c_void_p), ("n_items", C.c_int64),
+                ("ids", C.c_void_p), ("bag_offsets", C.c_void_p), ("bag_ends", C.c_void_p), ("n_items", C.c_int64),
                 ("bag_len", C.c_int32), ("n_tables", C.c_int32), ("tables", TableDesc * MAX_TABLES),
                 ("dim", C.c_int32), ("combiner", C.c_int32), ("mask_mode", C.c_int32), ("flags", C.c_int32),
                 ("int_mask_value", C.c_int64), ("out", C.c_void_p), ("out_stride", C.c_int64),
@@ -72,9 +72,12 @@ def lib():
         L.rf_shard_route_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
                                           C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
+        L.rf_shard_route_tiles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_uint64,
+                                           C.c_uint64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int,
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
         L.rf_combine_partials.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int, C.c_int32, C.c_void_p,
                                           C.c_void_p, C.c_int64, C.c_void_p]
-        for name in ("rf_hash_strings", "rf_hash_int64", "rf_bag_forward", "rf_shard_route", "rf_shard_route_keys", "rf_set_bag_grid_limit", "rf_bag_backward", "rf_sdpa_forward", "rf_sdpa_forward_tc", "rf_inbatch_rowstats", "rf_inbatch_rowstats_tc",
+        for name in ("rf_hash_strings", "rf_hash_int64", "rf_bag_forward", "rf_shard_route", "rf_shard_route_keys", "rf_shard_route_tiles", "rf_set_bag_grid_limit", "rf_bag_backward", "rf_sdpa_forward", "rf_sdpa_forward_tc", "rf_inbatch_rowstats", "rf_inbatch_rowstats_tc",
                      "rf_combine_partials"):
             getattr(L, name).restype = C.c_int
         _lib = L

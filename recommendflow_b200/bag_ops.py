@@ -23,13 +23,15 @@ class FieldCall(object):
     """
 
     def __init__(self, tables, dim, combiner="sum", keys=None, ids=None, mask_mode=nat.MASK_NONE,
-                 int_mask_value=0, out=None, ids_out=None, bag_len=None, bag_offsets=None, n_items=None, flags=0):
+                 int_mask_value=0, out=None, ids_out=None, bag_len=None, bag_offsets=None, n_items=None, flags=0,
+                 bag_ends=None):
         self.tables, self.dim, self.combiner = tables, dim, combiner
         self.keys, self.ids = keys, ids
         self.mask_mode, self.int_mask_value = mask_mode, int_mask_value
         self.out, self.ids_out = out, ids_out
         self.bag_len, self.bag_offsets, self.n_items = bag_len, bag_offsets, n_items
         self.flags = flags
+        self.bag_ends = bag_ends
 
 
 def _require_cuda(t, what):
@@ -78,9 +80,16 @@ def _fill(desc, call, batch):
         raise ValueError("a field needs keys or ids")
     if bag_offsets is not None:
         _require_cuda(bag_offsets, "bag_offsets")
-        if bag_offsets.dtype != torch.int32 or bag_offsets.numel() != batch + 1:
-            raise ValueError("bag_offsets must be int32 [batch + 1]")
+        ends = call.bag_ends
+        if bag_offsets.dtype != torch.int32 or bag_offsets.numel() < batch + (0 if ends is not None else 1):
+            raise ValueError("bag_offsets must be int32 [batch + 1] (or [batch] together with bag_ends)")
         desc.bag_offsets = bag_offsets.data_ptr()
+        if ends is not None:
+            _require_cuda(ends, "bag_ends")
+            if ends.dtype != torch.int32 or ends.numel() < batch:
+                raise ValueError("bag_ends must be int32 [batch]")
+            desc.bag_ends = ends.data_ptr()
+            keep.append(ends)
         desc.n_items = n_items
         keep.append(bag_offsets)
         desc.bag_len = 0

@@ -39,7 +39,7 @@ constexpr int kThreads = 256;
 constexpr int kChunk = 2048;              // keys (bucket ids) held per round
 constexpr int kSub = 1024;                // keys hashed per sub-chunk of a round (offsets + staged bytes)
 constexpr int kStageBytes = 16 * 1024;    // key bytes staged per sub-chunk
-constexpr int kMaxTileBags = 1024;        // bags per tile (jagged: CSR slice kept in smem)
+constexpr int kMaxTileBags = 512;         // bags per tile (jagged: begin / end of every bag kept in smem)
 constexpr int kMaxFieldsSmem = 512;       // tile-prefix table kept in smem up to this many fields
 constexpr int kMaxDim = 512;
 
@@ -54,6 +54,7 @@ struct DevField {
     const int64_t *ints;
     const int64_t *ids_in;
     const int32_t *boffs;
+    const int32_t *bends;   // optional: bag b = [boffs[b], bends[b]) instead of [boffs[b], boffs[b+1])
     float *out;
     int64_t *ids_out;
     int64_t out_stride;
@@ -163,7 +164,8 @@ struct Smem {
     uint32_t ids[RF_MAX_TABLES_PER_FIELD * kChunk];
     int32_t soff[kSub + 4];
     uint32_t stage[kStageBytes / 4 + 8];
-    int32_t boff[kMaxTileBags + 4];
+    int32_t bbeg[kMaxTileBags + 4];   // jagged mode: first key of each bag of the tile
+    int32_t bend[kMaxTileBags + 4];   // ... and one past its last key
     int32_t tile_begin[kMaxFieldsSmem + 1];
     DevField field;   // this tile's descriptor, copied once per tile
     // partial pools of a bag longer than one round (only lane groups 0..T-1 are active then):
@@ -202,8 +204,8 @@ __device__ __forceinline__ void pool_round_vec(const PoolOp &op, const DevField 
             lo = (int64_t)(tile_bag0 + bl) * F.bag_len;
             hi = lo + F.bag_len;
         } else {
-            lo = sm.boff[bl];
-            hi = sm.boff[bl + 1];
+            lo = sm.bbeg[bl];
+            hi = sm.bend[bl];
         }
         int rel = (int)(lo - R.item0), cnt = (int)(hi - lo);
         if (R.partial) {   // the round holds a slice [item0, item0 + n_keys) of this one bag
@@ -311,8 +313,8 @@ __device__ __forceinline__ void pool_round_scalar(const PoolOp &op, const DevFie
             lo = (int64_t)(tile_bag0 + bl) * F.bag_len;
             hi = lo + F.bag_len;
         } else {
-            lo = sm.boff[bl];
-            hi = sm.boff[bl + 1];
+            lo = sm.bbeg[bl];
+            hi = sm.bend[bl];
         }
         int rel = (int)(lo - R.item0), cnt = (int)(hi - lo);
         if (R.partial) {
@@ -384,26 +386,30 @@ __device__ __forceinline__ void bag_forward_body(const DevField *__restrict__ fi
         const int tile_bag0 = (tile - G.tile_begin) * G.bags_per_tile;
         const int tile_nbags = min(G.bags_per_tile, G.batch - tile_bag0);
         const int32_t *g_boffs = G.boffs;
+        const int32_t *g_bends = G.bends;
         const bool dense = g_boffs == nullptr;
         {
             const uint32_t *src = reinterpret_cast<const uint32_t *>(&G);
             uint32_t *dst = reinterpret_cast<uint32_t *>(&sm.field);
             for (int i = tid; i < (int)(sizeof(DevField) / 4); i += kThreads) dst[i] = src[i];
             if (!dense)
-                for (int i = tid; i <= tile_nbags; i += kThreads) sm.boff[i] = g_boffs[tile_bag0 + i];
+                for (int i = tid; i < tile_nbags; i += kThreads) {
+                    sm.bbeg[i] = g_boffs[tile_bag0 + i];
+                    sm.bend[i] = g_bends ? g_bends[tile_bag0 + i] : g_boffs[tile_bag0 + i + 1];
+                }
         }
         __syncthreads();
         const DevField &F = sm.field;
         const int T = F.n_tables;
-        const int64_t tile_item0 = dense ? (int64_t)tile_bag0 * F.bag_len : (int64_t)sm.boff[0];
+        const int64_t tile_item0 = dense ? (int64_t)tile_bag0 * F.bag_len : (int64_t)sm.bbeg[0];
 
         int bag = 0;            // next bag of the tile, relative
         int64_t part_done = 0;  // keys of a long bag already consumed
         while (bag < tile_nbags) {
             // ---- carve the next round ------------------------------------------------------
             Round R;
-            const int64_t b_lo = dense ? tile_item0 + (int64_t)bag * F.bag_len : (int64_t)sm.boff[bag];
-            const int64_t b_hi = dense ? b_lo + F.bag_len : (int64_t)sm.boff[bag + 1];
+            const int64_t b_lo = dense ? tile_item0 + (int64_t)bag * F.bag_len : (int64_t)sm.bbeg[bag];
+            const int64_t b_hi = dense ? b_lo + F.bag_len : (int64_t)sm.bend[bag];
             if (b_hi - b_lo > kChunk) {
                 R.partial = true;
                 R.bag0 = bag;
@@ -422,16 +428,17 @@ __device__ __forceinline__ void bag_forward_body(const DevField *__restrict__ fi
                     const int per = F.bag_len > 0 ? kChunk / F.bag_len : tile_nbags;
                     end = min(tile_nbags, bag + max(per, 1));
                 } else {
-                    // largest end with boff[end] - b_lo <= kChunk (boff is non-decreasing)
+                    // largest end with bend[end - 1] - b_lo <= kChunk (ends are non-decreasing; with explicit
+                    // ends there may be unused gaps between bags: they just count towards the round's span)
                     int lo = bag + 1, hi = tile_nbags;
                     while (lo < hi) {
                         const int mid = (lo + hi + 1) >> 1;
-                        if ((int64_t)sm.boff[mid] - b_lo <= kChunk) lo = mid; else hi = mid - 1;
+                        if ((int64_t)sm.bend[mid - 1] - b_lo <= kChunk) lo = mid; else hi = mid - 1;
                     }
                     end = lo;
                 }
                 R.bag1 = end;
-                const int64_t e_hi = dense ? tile_item0 + (int64_t)end * F.bag_len : (int64_t)sm.boff[end];
+                const int64_t e_hi = dense ? tile_item0 + (int64_t)end * F.bag_len : (int64_t)sm.bend[end - 1];
                 R.n_keys = (int)(e_hi - b_lo);
             }
 
@@ -690,11 +697,13 @@ static int build_field(DevField &d, const rf_field_desc &f, int64_t batch, int f
     if (f.bytes && f.mask_mode == RF_MASK_INT_VALUE) return set_error(RF_ERR_INVALID, "field %d: integer mask on string keys", fi);
     if (f.int_values && f.mask_mode == RF_MASK_EMPTY_STRING) return set_error(RF_ERR_INVALID, "field %d: string mask on integer keys", fi);
     if (!f.bag_offsets && f.bag_len < 0) return set_error(RF_ERR_INVALID, "field %d: negative bag_len", fi);
+    if (f.bag_ends && !f.bag_offsets) return set_error(RF_ERR_INVALID, "field %d: bag_ends given without bag_offsets", fi);
     d.bytes = f.bytes;
     d.soffs = f.str_offsets;
     d.ints = f.int_values;
     d.ids_in = f.ids;
     d.boffs = f.bag_offsets;
+    d.bends = f.bag_ends;
     d.out = f.out;
     d.ids_out = f.ids_out;
     d.out_stride = f.out_stride;

@@ -344,6 +344,191 @@ __global__ void __launch_bounds__(kScatThreads) shard_scatter_kernel(const int64
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Single-pass routing ("tile" layout).  The two-pass route above needs a global scan between its
+// count and scatter passes only because every owner's CSR must be gap-free.  If the owner accepts
+// bags with explicit [begin, end) and gaps between them (rf_field_desc.bag_ends), a CTA can finish
+// its run of bags on its own: keys k0 .. k1 of this source go to [k0, k0 + n_g) of owner g's
+// buffer (n_g <= k1 - k0 always fits; the rest of that range stays unused).  One pass over the keys,
+// no global scan, no second read of the ids, and all remote writes are long contiguous runs:
+//   1. one key per thread: hash (or fetch) the id                                   -> smem
+//   2. one warp per bag: owner of each key, rank inside its (bag, owner) run with match.any
+//      (one instruction instead of a ballot per owner), per-(bag, owner) counts    -> smem
+//   3. one warp per owner: exclusive scan of the counts over the round's bags       -> smem
+//   4. one key per thread: place the owner-local row at its slot of the staging tile
+//   5. stream each owner's run, and the bags' begin / end arrays, out with coalesced stores
+// ------------------------------------------------------------------------------------------
+constexpr int kTileCap = 4096;        // keys per round
+constexpr int kTileBags = 128;        // bags per round
+constexpr int kTileThreads = 256;
+
+struct TileSmem {
+    uint32_t sid[kTileCap];                   // bucket id of each key of the round
+    uint32_t meta[kTileCap + 8];              // rank (12) | owner (4) << 12 | bag (8) << 16; before that: key offsets
+    uint32_t srow[kTileCap];                  // staging: owner-local rows, grouped by owner
+    uint16_t cnt[kTileBags][kMaxWorld];       // keys of (bag, owner)
+    uint16_t beg[kTileBags][kMaxWorld];       // exclusive scan of cnt over the bags, per owner
+    int seg_len[kMaxWorld], seg_base[kMaxWorld + 1];
+};
+
+template <bool HASH>
+__global__ void __launch_bounds__(kTileThreads) shard_route_tile_kernel(
+    const int64_t *__restrict__ ids, const uint8_t *__restrict__ bytes, const int32_t *__restrict__ soffs, HashSpec spec,
+    int mask_empty, int64_t *__restrict__ ids_ws, const int32_t *__restrict__ boffs, int bag_len, int64_t batch, int world,
+    int tile_bags, PtrTable rows_dst, PtrTable begin_dst, PtrTable end_dst) {
+    extern __shared__ __align__(16) unsigned char tile_raw[];
+    TileSmem &sm = *reinterpret_cast<TileSmem *>(tile_raw);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const bool pow2 = (world & (world - 1)) == 0;
+    const int wshift = 31 - __clz(world);
+    const int64_t n_tiles = (batch + tile_bags - 1) / tile_bags;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t t0 = tile * tile_bags, t1 = min(batch, t0 + tile_bags);
+        int64_t r0 = t0;
+        while (r0 < t1) {
+            // ---- carve a round: whole bags, <= kTileCap keys, <= kTileBags bags ----
+            int64_t k0, dummy;
+            bag_range(boffs, bag_len, r0, k0, dummy);
+            int64_t r1 = r0, k1 = k0;
+            while (r1 < t1 && r1 - r0 < kTileBags) {
+                int64_t lo, hi;
+                bag_range(boffs, bag_len, r1, lo, hi);
+                if (hi - k0 > kTileCap) break;
+                k1 = hi;
+                ++r1;
+            }
+            const int nb = (int)(r1 - r0);
+            if (nb == 0) {
+                // one bag longer than a round: walk it in pieces of kTileCap keys; the pieces of one (bag, owner)
+                // run stay in key order because every piece starts at its own key index
+                int64_t lo, hi;
+                bag_range(boffs, bag_len, r0, lo, hi);
+                int run[kMaxWorld];                     // thread 0: keys of each owner placed so far
+                if (tid == 0)
+                    for (int g = 0; g < world; ++g) run[g] = 0;
+                // the simple layout cannot express a bag whose owner-run is split by gaps, so such bags are
+                // packed serially by one thread (rare: > 4096 keys in one bag)
+                if (tid == 0) {
+                    for (int64_t k = lo; k < hi; ++k) {
+                        const uint32_t id = key_id<HASH>(k, ids, bytes, soffs, spec, mask_empty);
+                        if (HASH) ids_ws[k] = (int64_t)id;
+                        const uint32_t row = id / (uint32_t)world, g = id - row * (uint32_t)world;
+                        static_cast<int64_t *>(rows_dst.p[g])[lo + run[g]] = (int64_t)row;
+                        ++run[g];
+                    }
+                    for (int g = 0; g < world; ++g) {
+                        static_cast<int32_t *>(begin_dst.p[g])[r0] = (int32_t)lo;
+                        static_cast<int32_t *>(end_dst.p[g])[r0] = (int32_t)(lo + run[g]);
+                    }
+                }
+                __syncthreads();
+                r0 += 1;
+                continue;
+            }
+            const int n_keys = (int)(k1 - k0);
+            // ---- 1. ids (string keys: the round's offsets are staged first, coalesced, so that hashing
+            //         costs one dependent global round trip per key instead of two) ----
+            if (HASH) {
+                int32_t *soff_s = reinterpret_cast<int32_t *>(sm.meta);
+                for (int j = tid; j <= n_keys; j += kTileThreads) soff_s[j] = soffs[k0 + j];
+                __syncthreads();
+                for (int j = tid; j < n_keys; j += kTileThreads) {
+                    const int32_t o = soff_s[j];
+                    const uint32_t len = (uint32_t)(soff_s[j + 1] - o);
+                    const uintptr_t a = reinterpret_cast<uintptr_t>(bytes) + (uintptr_t)o;
+                    const WordSrcGlobal src{reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3), (uint32_t)(a & 3u)};
+                    const uint32_t id = bucket_of(src, len, spec, mask_empty && len == 0);
+                    sm.sid[j] = id;
+                    ids_ws[k0 + j] = (int64_t)id;
+                }
+            } else {
+                for (int j = tid; j < n_keys; j += kTileThreads) sm.sid[j] = (uint32_t)ids[k0 + j];
+            }
+            for (int j = tid; j < nb * kMaxWorld; j += kTileThreads) (&sm.cnt[0][0])[j] = 0;
+            __syncthreads();
+            // ---- 2. owner, rank inside the (bag, owner) run ----
+            for (int bl = wid; bl < nb; bl += kTileThreads / 32) {
+                int64_t lo, hi;
+                bag_range(boffs, bag_len, r0 + bl, lo, hi);
+                const int j0 = (int)(lo - k0), j1 = (int)(hi - k0);
+                for (int j = j0; j < j1; j += 32) {
+                    const bool on = j + lane < j1;
+                    const uint32_t id = on ? sm.sid[j + lane] : 0u;
+                    const uint32_t owner = on ? (pow2 ? (id & (uint32_t)(world - 1)) : id % (uint32_t)world) : 0xffu;
+                    const unsigned grp = __match_any_sync(0xffffffffu, owner);
+                    const int leader = __ffs(grp) - 1;
+                    int base = 0;
+                    if (on && lane == leader) {
+                        base = sm.cnt[bl][owner];
+                        sm.cnt[bl][owner] = (uint16_t)(base + __popc(grp));
+                    }
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (on) sm.meta[j + lane] = (uint32_t)(base + __popc(grp & lt)) | (owner << 12) | ((uint32_t)bl << 16);
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+            // ---- 3. per owner: exclusive scan of the counts over the bags (one warp per owner) ----
+            for (int g = wid; g < world; g += kTileThreads / 32) {
+                int c[kTileBags / 32], sum = 0;
+#pragma unroll
+                for (int i = 0; i < kTileBags / 32; ++i) {
+                    const int bl = lane * (kTileBags / 32) + i;
+                    c[i] = bl < nb ? sm.cnt[bl][g] : 0;
+                    sum += c[i];
+                }
+                int incl = sum;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int y = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += y;
+                }
+                int run = incl - sum;
+#pragma unroll
+                for (int i = 0; i < kTileBags / 32; ++i) {
+                    const int bl = lane * (kTileBags / 32) + i;
+                    if (bl < nb) sm.beg[bl][g] = (uint16_t)run;
+                    run += c[i];
+                }
+                if (lane == 31) sm.seg_len[g] = incl;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int acc = 0;
+                for (int g = 0; g < world; ++g) {
+                    sm.seg_base[g] = acc;
+                    acc += sm.seg_len[g];
+                }
+                sm.seg_base[world] = acc;
+            }
+            __syncthreads();
+            // ---- 4. place every key's owner-local row ----
+            for (int j = tid; j < n_keys; j += kTileThreads) {
+                const uint32_t m = sm.meta[j], id = sm.sid[j];
+                const uint32_t rank = m & 0xfffu, owner = (m >> 12) & 0xfu, bl = m >> 16;
+                const uint32_t row = pow2 ? id >> wshift : id / (uint32_t)world;
+                sm.srow[sm.seg_base[owner] + sm.beg[bl][owner] + rank] = row;
+            }
+            __syncthreads();
+            // ---- 5. stream out: owner g's run goes to [k0, k0 + seg_len[g]) of its buffer for this source ----
+            for (int g = 0; g < world; ++g) {
+                int64_t *dst = static_cast<int64_t *>(rows_dst.p[g]) + k0;
+                const uint32_t *src = sm.srow + sm.seg_base[g];
+                for (int i = tid; i < sm.seg_len[g]; i += kTileThreads) dst[i] = (int64_t)src[i];
+                int32_t *bd = static_cast<int32_t *>(begin_dst.p[g]), *ed = static_cast<int32_t *>(end_dst.p[g]);
+                for (int bl = tid; bl < nb; bl += kTileThreads) {
+                    const int32_t b = (int32_t)k0 + sm.beg[bl][g];
+                    bd[r0 + bl] = b;
+                    ed[r0 + bl] = b + sm.cnt[bl][g];
+                }
+            }
+            __syncthreads();
+            r0 = r1;
+        }
+    }
+}
+
 // out[b] = reduce over g = 0..world-1 (in that order) of partials[g][b]; avg divides by the bag's
 // key count.  One float4 (or float) per thread.
 template <bool VEC>
@@ -457,6 +642,60 @@ static int route_impl(const int64_t *d_ids, const uint8_t *d_bytes, const int32_
                                                         n_chunks, excl, chunk_tot, offs, rows);
     RF_CUDA(cudaGetLastError());
     g_launches.fetch_add(4);
+    return RF_OK;
+}
+
+int rf_shard_route_tiles(const uint8_t *d_bytes, const int32_t *d_str_offsets, const int64_t *d_ids, int64_t num_bins,
+                         int mask_mode, int use_strong, uint64_t key0, uint64_t key1, int64_t *d_ids_ws,
+                         const int32_t *d_bag_offsets, int32_t bag_len, int64_t batch, int world, int64_t *const *h_rows_dst,
+                         int32_t *const *h_begin_dst, int32_t *const *h_end_dst, void *stream) {
+    if (world < 1 || world > kMaxWorld) return set_error(RF_ERR_INVALID, "world must be in [1, %d]", kMaxWorld);
+    if (batch < 0 || batch > INT32_MAX) return set_error(RF_ERR_INVALID, "batch out of range");
+    if (batch == 0) return RF_OK;
+    const bool hash = d_bytes != nullptr;
+    if (hash == (d_ids != nullptr)) return set_error(RF_ERR_INVALID, "rf_shard_route_tiles: give string keys or ids, not both");
+    if (hash && (!d_str_offsets || !d_ids_ws)) return set_error(RF_ERR_INVALID, "rf_shard_route_tiles: NULL key buffer");
+    if (!h_rows_dst || !h_begin_dst || !h_end_dst) return set_error(RF_ERR_INVALID, "rf_shard_route_tiles: NULL destination table");
+    if (!d_bag_offsets && bag_len < 0) return set_error(RF_ERR_INVALID, "negative bag_len");
+    HashSpec spec{};
+    if (hash) {
+        if (num_bins <= 0) return set_error(RF_ERR_INVALID, "`num_bins` cannot be `None` or non-positive values.");
+        if (num_bins > 0xffffffffLL) return set_error(RF_ERR_UNSUPPORTED, "num_bins above 2^32-1 is not supported");
+        if (mask_mode != RF_MASK_NONE && mask_mode != RF_MASK_EMPTY_STRING)
+            return set_error(RF_ERR_INVALID, "string keys take RF_MASK_NONE or RF_MASK_EMPTY_STRING");
+        spec = make_hash_spec(num_bins, mask_mode != RF_MASK_NONE, use_strong, key0, key1);
+    }
+    PtrTable rows{}, begs{}, ends{};
+    for (int g = 0; g < world; ++g) {
+        rows.p[g] = h_rows_dst[g];
+        begs.p[g] = h_begin_dst[g];
+        ends.p[g] = h_end_dst[g];
+        if (!rows.p[g] || !begs.p[g] || !ends.p[g]) return set_error(RF_ERR_INVALID, "rf_shard_route_tiles: destination %d is NULL", g);
+    }
+    int dev = 0, sms = 0;
+    RF_CUDA(cudaGetDevice(&dev));
+    RF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // a tile is about one round (<= 4096 keys, <= 128 bags); jagged bag lengths are only known on the
+    // device, so tiles are sized for 128 keys per bag there and the rounds adapt
+    const int64_t per_bag = d_bag_offsets ? 128 : (bag_len > 0 ? bag_len : 1);
+    int64_t tile_bags = kTileCap / per_bag;
+    if (tile_bags < 8) tile_bags = 8;
+    if (tile_bags > kTileBags) tile_bags = kTileBags;
+    const int grid = grid_for((batch + tile_bags - 1) / tile_bags, 1, sms);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t smem = sizeof(TileSmem);
+    if (hash) {
+        RF_CUDA(cudaFuncSetAttribute(shard_route_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        shard_route_tile_kernel<true><<<grid, kTileThreads, smem, st>>>(nullptr, d_bytes, d_str_offsets, spec,
+                                                                        mask_mode == RF_MASK_EMPTY_STRING, d_ids_ws, d_bag_offsets,
+                                                                        bag_len, batch, world, (int)tile_bags, rows, begs, ends);
+    } else {
+        RF_CUDA(cudaFuncSetAttribute(shard_route_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        shard_route_tile_kernel<false><<<grid, kTileThreads, smem, st>>>(d_ids, nullptr, nullptr, spec, 0, nullptr, d_bag_offsets,
+                                                                         bag_len, batch, world, (int)tile_bags, rows, begs, ends);
+    }
+    RF_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
     return RF_OK;
 }
 

@@ -52,6 +52,25 @@ class CudaShardOps(object):
                 None if bag_offsets is None else bag_offsets.data_ptr(), bag_len or 0, batch, world, counts_ws.data_ptr(),
                 offs_local.data_ptr(), arr_o, arr_r, C.c_void_p(torch.cuda.current_stream(keys.device).cuda_stream)))
 
+    def route_tiles(self, keys, num_bins, mask_value, salt, ids_ws, bag_offsets, bag_len, batch, world,
+                    rows_dst_ptrs, begin_dst_ptrs, end_dst_ptrs):
+        """Single-pass routing into the gapped "tile" layout (rf_shard_route_tiles)."""
+        arrs = [(C.c_void_p * world)(*p) for p in (rows_dst_ptrs, begin_dst_ptrs, end_dst_ptrs)]
+        if isinstance(keys, StringColumn):
+            if mask_value not in (None, ""):
+                raise NotImplementedError("only mask_value in (None, '') is supported for string keys")
+            strong, k0, k1 = nat.salt_to_key(salt)
+            args = (keys.data.data_ptr(), keys.offsets.data_ptr(), None, int(num_bins),
+                    nat.MASK_NONE if mask_value is None else nat.MASK_EMPTY_STRING, strong, k0, k1, ids_ws.data_ptr())
+            dev = keys.device
+        else:                                   # pre-hashed int64 ids
+            args = (None, None, keys.data_ptr(), 0, 0, 0, 0, 0, None)
+            dev = keys.device
+        with torch.cuda.device(dev):
+            nat.check(nat.lib().rf_shard_route_tiles(*args, None if bag_offsets is None else bag_offsets.data_ptr(),
+                                                     bag_len or 0, batch, world, *arrs,
+                                                     C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+
     def route(self, ids, bag_offsets, bag_len, batch, world, counts_ws, offs_local, offs_dst_ptrs, rows_dst_ptrs):
         arr_o = (C.c_void_p * world)(*offs_dst_ptrs) if offs_dst_ptrs is not None else None
         arr_r = (C.c_void_p * world)(*rows_dst_ptrs)
@@ -60,10 +79,11 @@ class CudaShardOps(object):
                                                bag_len or 0, batch, world, counts_ws.data_ptr(), offs_local.data_ptr(),
                                                arr_o, arr_r, C.c_void_p(torch.cuda.current_stream(ids.device).cuda_stream)))
 
-    def pool(self, shard, rows_per_src, offs_per_src, outs_per_src, batch, combiner, est_items):
+    def pool(self, shard, rows_per_src, offs_per_src, outs_per_src, batch, combiner, est_items, ends_per_src=None):
+        ends_per_src = ends_per_src or [None] * len(rows_per_src)
         calls = [FieldCall([(shard, shard.shape[0], None)], shard.shape[1], combiner, ids=rows.view(1, -1),
-                           bag_offsets=offs, out=out, flags=nat.FIELD_PARTIAL, n_items=est_items)
-                 for rows, offs, out in zip(rows_per_src, offs_per_src, outs_per_src)]
+                           bag_offsets=offs, bag_ends=ends, out=out, flags=nat.FIELD_PARTIAL, n_items=est_items)
+                 for rows, offs, ends, out in zip(rows_per_src, offs_per_src, ends_per_src, outs_per_src)]
         bag_forward(calls, batch)
 
     def combine(self, partials, world, batch, dim, combiner, bag_len, bag_offsets, out):
@@ -108,6 +128,9 @@ class ShardedEmbeddingBag(torch.nn.Module):
         # kernels of the next step find room on every SM; 0 = no cap
         import os
         self.pool_ctas_per_sm = int(os.environ.get("RF_SHARD_POOL_CTAS", "3"))
+        # p2p routing layout: "tiles" = single-pass routing into gapped per-bag [begin, end) runs;
+        # "csr" = count / scan / scatter into a gap-free CSR (what the nccl transport always uses)
+        self.route_layout = os.environ.get("RF_SHARD_ROUTE", "tiles")
         self.profile = None      # set to [] to collect (phase name, cuda event) pairs per forward
 
     def _tick(self, phase):
@@ -147,17 +170,19 @@ class ShardedEmbeddingBag(torch.nn.Module):
         if self.transport == "p2p":
             import torch.distributed._symmetric_memory as symm
             rows_bytes = W * K * 8
-            offs_bytes = (W * (B + 1) * 4 + 15) // 16 * 16
+            offs_bytes = (2 * W * (B + 1) * 4 + 15) // 16 * 16      # [2][W][B+1]: bag begins / ends (or one CSR)
             part_bytes = W * B * D * 4
             set_bytes = rows_bytes + offs_bytes + part_bytes
             raw = symm.empty(self.N_SETS * set_bytes, dtype=torch.uint8, device=dev)
             hdl = symm.rendezvous(raw, self.group)
             b.update(raw=raw, hdl=hdl, set_bytes=set_bytes, rows_bytes=rows_bytes)
-            b["rows_recv"], b["offs_recv"], b["partials"], b["peer_partials"] = [], [], [], []
+            b["rows_recv"], b["offs_recv"], b["ends_recv"], b["partials"], b["peer_partials"] = [], [], [], [], []
             for j in range(self.N_SETS):
                 o = j * set_bytes
                 b["rows_recv"].append(raw[o:o + rows_bytes].view(torch.int64).view(W, K))
                 b["offs_recv"].append(raw[o + rows_bytes:o + rows_bytes + W * (B + 1) * 4].view(torch.int32).view(W, B + 1))
+                e0 = o + rows_bytes + W * (B + 1) * 4
+                b["ends_recv"].append(raw[e0:e0 + W * (B + 1) * 4].view(torch.int32).view(W, B + 1))
                 po = o + rows_bytes + offs_bytes
                 b["partials"].append(raw[po:po + part_bytes].view(torch.float32).view(W, B, D))
                 b["peer_partials"].append([hdl.get_buffer(r, (W, B, D), torch.float32, po // 4) for r in range(W)])
@@ -217,6 +242,8 @@ class ShardedEmbeddingBag(torch.nn.Module):
         base = [b["peer_ptr"][g] + j * b["set_bytes"] for g in range(W)]
         rows_dst = [base[g] + me * K * 8 for g in range(W)]
         offs_dst = [base[g] + b["rows_bytes"] + me * (B + 1) * 4 for g in range(W)]
+        ends_dst = [base[g] + b["rows_bytes"] + (W + me) * (B + 1) * 4 for g in range(W)]
+        tiles = self.route_layout == "tiles" and hasattr(self.ops, "route_tiles")
         cur = torch.cuda.current_stream(self.device)
         stream = b["sR"] if overlap else cur
         routed = None
@@ -226,13 +253,22 @@ class ShardedEmbeddingBag(torch.nn.Module):
             if overlap and b["rows_free"][j] is not None:
                 stream.wait_event(b["rows_free"][j])      # every owner is done pooling out of set j
             self._tick("start")
-            self._route(keys, B, L, bag_offsets, offs_dst, rows_dst)
+            if tiles:
+                src = keys
+                if not isinstance(keys, StringColumn):
+                    src = self.ops.hash(keys, self.num_bins, self.mask_value, self.salt)
+                elif b["ids_ws"] is None:
+                    b["ids_ws"] = torch.empty(self.max_keys, dtype=torch.int64, device=self.device)
+                self.ops.route_tiles(src, self.num_bins, self.mask_value, self.salt, b["ids_ws"], bag_offsets, L, B, W,
+                                     rows_dst, offs_dst, ends_dst)
+            else:
+                self._route(keys, B, L, bag_offsets, offs_dst, rows_dst)
             self._tick("route")
             if overlap:
                 routed = torch.cuda.Event()
                 routed.record(stream)
         return {"set": j, "routed": routed, "B": B, "L": L, "bag_offsets": bag_offsets, "n_keys": n_keys,
-                "overlap": overlap}
+                "overlap": overlap, "tiles": tiles}
 
     def finish(self, ticket, out=None):
         """Stages 2 and 3: barrier, fused gather+pool writing each pooled vector into the SOURCE rank's
@@ -263,7 +299,8 @@ class ShardedEmbeddingBag(torch.nn.Module):
             try:
                 self.ops.pool(self.shard.data, [b["rows_recv"][j][s] for s in order],
                               [b["offs_recv"][j][s] for s in order], [b["peer_partials"][j][s][me] for s in order],
-                              B, partial_op, max(1, ticket["n_keys"] // W))
+                              B, partial_op, max(1, ticket["n_keys"] // W),
+                              [b["ends_recv"][j][s] for s in order] if ticket["tiles"] else None)
             finally:
                 if overlap and self.pool_ctas_per_sm:
                     nat.lib().rf_set_bag_grid_limit(0)

@@ -30,8 +30,8 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_header_sizes():
     # rf_table_desc: ptr + i64 + 2*i32 + 2*u64 = 40 bytes; rf_field_desc packs without surprises
     assert ctypes.sizeof(nat.TableDesc) == 40
-    assert ctypes.sizeof(nat.FieldDesc) == 5 * 8 + 8 + 8 + 2 * 40 + 16 + 8 + 8 + 8 + 8
-    assert nat.FieldDesc.tables.offset == 56 and nat.FieldDesc.out.offset == 160
+    assert ctypes.sizeof(nat.FieldDesc) == 6 * 8 + 8 + 8 + 2 * 40 + 16 + 8 + 8 + 8 + 8
+    assert nat.FieldDesc.tables.offset == 64 and nat.FieldDesc.out.offset == 168
 
 
 def test_fastmod_equals_modulo():

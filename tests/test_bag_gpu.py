@@ -286,3 +286,34 @@ def test_backward_sgd_matches_numpy(combiner, D):
     bag_backward(torch.from_numpy(jid).cuda(), dev_w, torch.from_numpy(g).cuda(), 0.5, combiner,
                  bag_offsets=torch.from_numpy(bag).cuda())
     np.testing.assert_allclose(dev_w.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+
+
+def test_gapped_bags_with_explicit_ends():
+    # bag_ends: bags in order but with unused gaps between them (the sharded "tile" routing layout);
+    # the gaps hold garbage ids that must never be dereferenced
+    rng = np.random.default_rng(19)
+    B, N, D = 900, 5003, 128
+    lens = rng.integers(0, 40, size=B)
+    gaps = rng.integers(0, 3000, size=B) * (rng.uniform(size=B) < 0.1)         # a big gap now and then
+    begin = np.zeros(B, dtype=np.int64)
+    pos = 0
+    for b in range(B):
+        pos += gaps[b]
+        begin[b] = pos
+        pos += lens[b]
+    ids = np.full(pos + 5, 2**40, dtype=np.int64)                               # garbage everywhere ...
+    real = rng.integers(0, N, size=int(lens.sum()))
+    off = 0
+    for b in range(B):
+        ids[begin[b]:begin[b] + lens[b]] = real[off:off + lens[b]]              # ... except inside the bags
+        off += lens[b]
+    (w,) = tables(rng, 1, N, D)
+    csr = np.zeros(B + 1, dtype=np.int32)
+    csr[1:] = np.cumsum(lens)
+    for combiner in ("sum", "avg", "max"):
+        want = oracle.bag_pool(real, w, combiner, bag_offsets=csr)
+        out = torch.full((B, D), float("nan"), device="cuda")
+        bag_forward([FieldCall([(to_dev([w])[0], N, None)], D, combiner, ids=torch.from_numpy(ids).cuda().view(1, -1),
+                               bag_offsets=torch.from_numpy(begin.astype(np.int32)).cuda(),
+                               bag_ends=torch.from_numpy((begin + lens).astype(np.int32)).cuda(), out=out, n_items=int(lens.sum()))], B)
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32)), combiner

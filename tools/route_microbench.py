@@ -52,6 +52,24 @@ def main():
     print(f"route_keys: B={B} world={W} keys={n}: {e0.elapsed_time(e1) / args.steps * 1e3:.1f} us/step")
     # sanity: CSR totals add up to the key count
     assert int(offs_dst[:, B].sum()) == n
+    # single-pass tile routing
+    begs = torch.empty(W, B, dtype=torch.int32, device="cuda")
+    ends = torch.empty(W, B, dtype=torch.int32, device="cuda")
+
+    def step2():
+        ops.route_tiles(col, 100_000_000, "", None, ids_ws, col.bag_offsets, 0, B, W, [rows[g].data_ptr() for g in range(W)],
+                        [begs[g].data_ptr() for g in range(W)], [ends[g].data_ptr() for g in range(W)])
+
+    for _ in range(3):
+        step2()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        step2()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"route_tiles: B={B} world={W} keys={n}: {e0.elapsed_time(e1) / args.steps * 1e3:.1f} us/step")
+    assert int((ends - begs).sum()) == n
 
 
 if __name__ == "__main__":
