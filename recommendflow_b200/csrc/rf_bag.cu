@@ -401,6 +401,40 @@ __device__ __forceinline__ void bag_forward_body(const DevField *__restrict__ fi
         __syncthreads();
         const DevField &F = sm.field;
         const int T = F.n_tables;
+        // Bags with explicit ends may have gaps between them (sharded "tile" routing).  Re-base them onto a
+        // virtual gap-free key space -- bbeg / bend become running counts -- so that rounds are carved by
+        // real key counts; the true begins move to `gbeg` (aliases soff, unused by the ids path) and are
+        // only needed when the ids are staged.
+        int32_t *gbeg = sm.soff;
+        const bool gapped = !dense && g_bends != nullptr;
+        if (gapped) {
+            if (tid < 32) {
+                constexpr int kPer = (kMaxTileBags + 31) / 32;
+                int sum = 0;
+                for (int i = 0; i < kPer; ++i) {
+                    const int b = tid * kPer + i;
+                    sum += b < tile_nbags ? sm.bend[b] - sm.bbeg[b] : 0;
+                }
+                int incl = sum;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int y = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (tid >= d) incl += y;
+                }
+                int run = incl - sum;
+                for (int i = 0; i < kPer; ++i) {
+                    const int b = tid * kPer + i;
+                    if (b < tile_nbags) {
+                        const int beg = sm.bbeg[b], cnt = sm.bend[b] - beg;
+                        gbeg[b] = beg;
+                        sm.bbeg[b] = run;
+                        sm.bend[b] = run + cnt;
+                        run += cnt;
+                    }
+                }
+            }
+            __syncthreads();
+        }
         const int64_t tile_item0 = dense ? (int64_t)tile_bag0 * F.bag_len : (int64_t)sm.bbeg[0];
 
         int bag = 0;            // next bag of the tile, relative
@@ -443,7 +477,18 @@ __device__ __forceinline__ void bag_forward_body(const DevField *__restrict__ fi
             }
 
             // ---- phase A+B: keys -> bucket ids in shared memory -----------------------------
-            if (F.ids_in != nullptr) {
+            if (F.ids_in != nullptr && gapped) {
+                // virtual key -> its bag (binary search over the round's bags) -> true position
+                for (int j = tid; j < R.n_keys; j += kThreads) {
+                    const int vk = (int)R.item0 + j;
+                    int lo = R.bag0, hi = R.bag1 - 1;
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (sm.bbeg[mid] <= vk) lo = mid; else hi = mid - 1;
+                    }
+                    sm.ids[j] = (uint32_t)F.ids_in[(int64_t)gbeg[lo] + (vk - sm.bbeg[lo])];
+                }
+            } else if (F.ids_in != nullptr) {
                 for (int j = tid; j < R.n_keys; j += kThreads)
                     for (int t = 0; t < T; ++t)
                         sm.ids[t * kChunk + j] = (uint32_t)F.ids_in[(int64_t)t * F.n_items + R.item0 + j];
@@ -698,6 +743,8 @@ static int build_field(DevField &d, const rf_field_desc &f, int64_t batch, int f
     if (f.int_values && f.mask_mode == RF_MASK_EMPTY_STRING) return set_error(RF_ERR_INVALID, "field %d: string mask on integer keys", fi);
     if (!f.bag_offsets && f.bag_len < 0) return set_error(RF_ERR_INVALID, "field %d: negative bag_len", fi);
     if (f.bag_ends && !f.bag_offsets) return set_error(RF_ERR_INVALID, "field %d: bag_ends given without bag_offsets", fi);
+    if (f.bag_ends && (!f.ids || f.n_tables != 1))
+        return set_error(RF_ERR_UNSUPPORTED, "field %d: bag_ends (gapped bags) takes pre-hashed ids and one table", fi);
     d.bytes = f.bytes;
     d.soffs = f.str_offsets;
     d.ints = f.int_values;

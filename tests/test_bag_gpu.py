@@ -317,3 +317,31 @@ def test_gapped_bags_with_explicit_ends():
                                bag_offsets=torch.from_numpy(begin.astype(np.int32)).cuda(),
                                bag_ends=torch.from_numpy((begin + lens).astype(np.int32)).cuda(), out=out, n_items=int(lens.sum()))], B)
         assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32)), combiner
+
+
+@pytest.mark.parametrize("seed,B,max_len", [(23, 3000, 12), (29, 700, 5000), (31, 1, 7000)])
+def test_gapped_bags_long_and_empty(seed, B, max_len):
+    # gapped bags longer than one round (carry across rounds), runs of empty bags, several tiles
+    rng = np.random.default_rng(seed)
+    N, D = 7919, 64
+    lens = rng.integers(0, max_len + 1, size=B) * (rng.uniform(size=B) < 0.7)
+    if B > 1:
+        lens[rng.integers(0, B)] = max_len
+    gaps = rng.integers(0, 500, size=B) * (rng.uniform(size=B) < 0.3)
+    begin = np.cumsum(gaps + np.concatenate([[0], lens[:-1]])).astype(np.int64)
+    total = int(begin[-1] + lens[-1])
+    ids = np.full(total + 5, 2**40, dtype=np.int64)
+    real = rng.integers(0, N, size=int(lens.sum()))
+    csr = np.zeros(B + 1, dtype=np.int32)
+    csr[1:] = np.cumsum(lens)
+    for b in range(B):
+        ids[begin[b]:begin[b] + lens[b]] = real[csr[b]:csr[b + 1]]
+    (w,) = tables(rng, 1, N, D)
+    for combiner in ("sum", "avg"):
+        want = oracle.bag_pool(real, w, combiner, bag_offsets=csr)
+        out = torch.full((B, D), float("nan"), device="cuda")
+        bag_forward([FieldCall([(to_dev([w])[0], N, None)], D, combiner, ids=torch.from_numpy(ids).cuda().view(1, -1),
+                               bag_offsets=torch.from_numpy(begin.astype(np.int32)).cuda(),
+                               bag_ends=torch.from_numpy((begin + lens).astype(np.int32)).cuda(), out=out,
+                               n_items=int(lens.sum()))], B)
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32)), combiner
