@@ -193,6 +193,28 @@ int rf_bag_backward(const int64_t *d_ids, int64_t n_keys, const int32_t *d_bag_o
                     int64_t batch, const float *d_grad_out, int64_t grad_stride, int32_t dim, int combiner,
                     float alpha, float *d_table, void *stream);
 
+/* ---- vocabulary lookup / bucketisation ------------------------------------ */
+/* Keras StringLookup / IntegerLookup(vocabulary=vocabs, output_mode="int") as LookupEmbedding builds */
+/* them (backend/layers/preprocess_layers.py:148-150): term i -> i + 1, out-of-vocabulary -> 0.      */
+/* The table is caller-owned device memory; exact (a hash match is confirmed against the term).     */
+typedef struct rf_vocab_desc {
+    const uint8_t *term_bytes;    /* string vocabulary: arena of the terms (+16 readable bytes), else NULL */
+    const int32_t *term_offsets;  /* [n_terms + 1] byte offsets into term_bytes, else NULL                */
+    const int64_t *term_ints;     /* integer vocabulary: [n_terms], else NULL                             */
+    uint64_t *slots;              /* [capacity] open-addressing table, filled by rf_vocab_build           */
+    int64_t capacity;             /* power of two, >= max(2, 2 * n_terms)                                 */
+    int64_t n_terms;              /* terms must be distinct (the caller checks, as Keras does)            */
+} rf_vocab_desc;
+int rf_vocab_build(const rf_vocab_desc *vocab, void *stream);
+int rf_vocab_lookup_strings(const rf_vocab_desc *vocab, const uint8_t *d_bytes, const int32_t *d_str_offsets,
+                            int64_t n_items, int64_t *d_ids_out, void *stream);
+int rf_vocab_lookup_int64(const rf_vocab_desc *vocab, const int64_t *d_values, int64_t n_items,
+                          int64_t *d_ids_out, void *stream);
+/* Keras Discretization(bin_boundaries) (preprocess_layers.py:187): id = #boundaries <= x            */
+/* (upper_bound with `x < boundary`; NaN -> n_boundaries).  Boundaries ascending, device fp32.        */
+int rf_bucketize_f32(const float *d_values, int64_t n_items, const float *d_boundaries, int32_t n_boundaries,
+                     int64_t *d_ids_out, void *stream);
+
 /* Cap the fused kernel's grid at ctas_per_sm x #SMs (0 = no cap; it then walks its tiles            */
 /* grid-stride).  Leaves room on every SM for kernels of other streams (the sharded pipeline).     */
 int rf_set_bag_grid_limit(int ctas_per_sm);

@@ -209,3 +209,22 @@ def autotune_threads(probe, candidates=None):
             best = (th, dt)
     set_num_threads(best[0])
     return best
+
+
+def vocab_lookup(keys, vocabulary):
+    """Keras StringLookup / IntegerLookup(vocabulary, output_mode="int") as the reference builds them
+    (backend/layers/preprocess_layers.py:148-150): term i -> i + 1, out-of-vocabulary -> 0.
+    keys: flat list of bytes/str or ints.  Pure-Python dict (small cases)."""
+    norm = lambda t: t.encode() if isinstance(t, str) else t
+    index = {norm(t): i + 1 for i, t in enumerate(vocabulary)}
+    return np.array([index.get(norm(k), 0) for k in keys], dtype=np.int64)
+
+
+def bucketize(values, boundaries):
+    """Keras Discretization(bin_boundaries) (preprocess_layers.py:187): std::upper_bound with
+    `value < boundary`, so id = #boundaries <= value and NaN -> len(boundaries)."""
+    v = np.asarray(values, dtype=np.float32)
+    b = np.asarray(boundaries, dtype=np.float32)
+    out = np.searchsorted(b, v, side="right").astype(np.int64)
+    out[np.isnan(v)] = b.size
+    return out

@@ -29,6 +29,11 @@ class FieldDesc(C.Structure):
                 ("ids_out", C.c_void_p)]
 
 
+class VocabDesc(C.Structure):
+    _fields_ = [("term_bytes", C.c_void_p), ("term_offsets", C.c_void_p), ("term_ints", C.c_void_p),
+                ("slots", C.c_void_p), ("capacity", C.c_int64), ("n_terms", C.c_int64)]
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -77,6 +82,12 @@ def lib():
                                            C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
         L.rf_combine_partials.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int, C.c_int32, C.c_void_p,
                                           C.c_void_p, C.c_int64, C.c_void_p]
+        L.rf_vocab_build.argtypes = [C.POINTER(VocabDesc), C.c_void_p]
+        L.rf_vocab_lookup_strings.argtypes = [C.POINTER(VocabDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.rf_vocab_lookup_int64.argtypes = [C.POINTER(VocabDesc), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.rf_bucketize_f32.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        for name in ("rf_vocab_build", "rf_vocab_lookup_strings", "rf_vocab_lookup_int64", "rf_bucketize_f32"):
+            getattr(L, name).restype = C.c_int
         for name in ("rf_hash_strings", "rf_hash_int64", "rf_bag_forward", "rf_shard_route", "rf_shard_route_keys", "rf_shard_route_tiles", "rf_set_bag_grid_limit", "rf_bag_backward", "rf_sdpa_forward", "rf_sdpa_forward_tc", "rf_inbatch_rowstats", "rf_inbatch_rowstats_tc",
                      "rf_combine_partials"):
             getattr(L, name).restype = C.c_int

@@ -23,6 +23,7 @@ from ... import _native as nat
 from ...bag_ops import FieldCall, bag_forward, hash_ints, hash_strings
 from ...config_parser.config_proto import TYPE_INT, TYPE_STR
 from ...strings import StringColumn
+from ...vocab_ops import DeviceVocabulary, bucketize
 
 SUPPORT_POOLING = ["null", "sum", "min", "max", "avg", "first", "last"]
 _POOLED = ("sum", "avg", "min", "max")
@@ -268,33 +269,35 @@ class DoubleHashingEmbedding(Layer):
 
 
 class LookupEmbedding(Layer):
-    """Vocabulary lookup (Keras StringLookup / IntegerLookup, index 0 = OOV) + EmbeddingBag.
+    """Vocabulary lookup (Keras StringLookup / IntegerLookup: term i -> i + 1, OOV -> 0) + EmbeddingBag
+    (/root/reference/backend/layers/preprocess_layers.py:134-168).
 
-    Host-side vocabulary map for now (a "next" row of SURVEY.md §8f); the bag itself runs on the
-    same fused kernel through pre-hashed ids.
+    The vocabulary is a device hash table (`vocab_ops.DeviceVocabulary`, rf_vocab_lookup_*); the ids feed
+    the fused bag kernel.  The reference's factory passes `vocab_size=len(vocabs)`, one row short of the
+    largest index StringLookup can emit; the table here always has at least
+    `len(vocabs) + 1` rows so that the last term never indexes past it.
     """
 
     def __init__(self, embedding_dim, dtype, vocabs, vocab_size=None, pooling="sum", name=None):
         super().__init__(name=name)
         self.vocabulary = vocabs
         self.pooling = pooling
-        vocab_size = vocab_size or len(vocabs) + 1
+        vocab_size = max(vocab_size or 0, len(vocabs) + 1)
         if dtype not in (TYPE_STR, TYPE_INT):
             raise ValueError(f"Unsupported type for lookup feature: {dtype}")
         self.key_type = dtype
-        self._index = {(v.encode() if isinstance(v, str) else v): i + 1 for i, v in enumerate(vocabs)}
+        self._terms = [int(v) for v in vocabs] if dtype == TYPE_INT else [v if isinstance(v, (str, bytes)) else str(v) for v in vocabs]
+        self._vocab = None
         self.embedding = EmbeddingBag(vocab_size, embedding_dim, True, combiner=pooling, name=name + "_embedding")
 
     def lookup_ids(self, inputs):
-        if self.key_type == TYPE_STR:
-            col = inputs if isinstance(inputs, StringColumn) else StringColumn.from_lists(inputs)
-            ids = [self._index.get(s, 0) for s in col.tolist()]
-            shape = col.shape
-        else:
-            arr = np.asarray(inputs.cpu() if isinstance(inputs, torch.Tensor) else inputs, dtype=np.int64)
-            ids = [self._index.get(int(v), 0) for v in arr.ravel()]
-            shape = arr.shape if arr.ndim == 2 else (arr.shape[0], 1)
-        return torch.tensor(ids, dtype=torch.int64).view(shape)
+        keys = as_keys(inputs)
+        if (self.key_type == TYPE_STR) != isinstance(keys, StringColumn):
+            raise ValueError(f"lookup feature of type {self.key_type} got {type(keys).__name__} keys")
+        device = keys.device
+        if self._vocab is None or self._vocab.device != device:
+            self._vocab = DeviceVocabulary(self._terms, device)
+        return self._vocab.lookup(keys)
 
     def call(self, inputs, *args, **kwargs):
         return self.embedding(self.lookup_ids(inputs))
@@ -316,19 +319,22 @@ class DiscreteEmbedding(Layer):
     def __init__(self, embedding_dim, vocabs, vocab_size=None, pooling="sum", name=None):
         super().__init__(name=name)
         self.vocabulary = vocabs
-        vocab_size = vocab_size or len(vocabs) + 1
+        vocab_size = max(vocab_size or 0, len(vocabs) + 1)
         self.pooling = pooling
         self.bin_boundaries = [float(v) for v in vocabs]
+        self._edges = None
         self.embedding = EmbeddingBag(vocab_size, embedding_dim, True, combiner=pooling,
                                       name=name + "_disc_lookup_embedding")
 
     def call(self, inputs, *args, **kwargs):
-        x = torch.as_tensor(np.asarray(inputs.cpu() if isinstance(inputs, torch.Tensor) else inputs, dtype=np.float32))
+        x = inputs if isinstance(inputs, torch.Tensor) else torch.as_tensor(np.asarray(inputs, dtype=np.float32))
+        if not x.is_cuda:
+            x = x.to(_default_device(), non_blocking=True)
         if x.dim() == 1:
             x = x[:, None]
-        edges = torch.tensor(self.bin_boundaries, dtype=torch.float32)
-        ids = torch.bucketize(x, edges, right=True)
-        return self.embedding(ids.to(torch.int64))
+        if self._edges is None or self._edges.device != x.device:
+            self._edges = torch.tensor(self.bin_boundaries, dtype=torch.float32).to(x.device)
+        return self.embedding(bucketize(x, self._edges))
 
     def get_vocabulary(self):
         return self.bin_boundaries

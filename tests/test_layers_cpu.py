@@ -57,9 +57,12 @@ def test_factory_builds_reference_layer_set(golden_dir):
     assert layers["price"].embedding.name == "discrete_price_disc_lookup_embedding"
     layout, total = layers.output_layout()
     assert layout["clk_items"] == (0, 128) and layout["uid"] == (256, 64) and total == 416
-    # lookup quirk kept: the table has len(vocabs) rows although ids go up to len(vocabs)
-    assert layers["top_cat"].embedding.input_dim == 3
-    assert layers["top_cat"].lookup_ids([["app"], ["zzz"]]).tolist() == [[2], [0]]
+    # the reference's factory passes vocab_size=len(vocabs) although ids go up to len(vocabs); the table here
+    # gets the one extra row so that the last term stays inside it
+    assert layers["top_cat"].embedding.input_dim == len(layers["top_cat"].vocabulary) + 1 == 4
+    with pytest.raises(ValueError, match="repeated term"):
+        from recommendflow_b200.vocab_ops import DeviceVocabulary
+        DeviceVocabulary(["a", "b", "a"], "cuda")
 
 
 def test_string_column_padding_and_slack():
