@@ -193,6 +193,26 @@ int rf_bag_backward(const int64_t *d_ids, int64_t n_keys, const int32_t *d_bag_o
                     int64_t batch, const float *d_grad_out, int64_t grad_stride, int32_t dim, int combiner,
                     float alpha, float *d_table, void *stream);
 
+/* Same gradient, fused with the Adam update the reference trains with: tf.keras.optimizers.Adam on   */
+/* the Embedding variables (example/ranking_search/train.py:97-104).  Keras semantics: duplicate ids */
+/* are summed first; then, with lazy == 0, EVERY row of the table decays its moments and moves       */
+/* (m = m*b1 [+ g*(1-b1)], v = v*b2 [+ g*g*(1-b2)], w -= lr_t * m / (sqrt(v) + eps),                  */
+/* lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t)); lazy == 1 touches only the gathered rows (LazyAdam, not  */
+/* the reference's semantics).  ids must be < table_rows <= 2^32 - 1; dim % 4 == 0; d_table, d_m, d_v */
+/* are [table_rows, dim] fp32, 16-byte aligned.  Workspace: device memory of                           */
+/* rf_bag_adam_workspace_bytes(n_keys, table_rows) bytes (-1 on bad arguments).                        */
+typedef struct rf_adam_params {
+    float lr, beta1, beta2, epsilon; /* Keras defaults: 1e-3, 0.9, 0.999, 1e-7 */
+    int64_t step;                    /* t >= 1: iterations + 1                  */
+    int32_t lazy;
+    int32_t reserved;
+} rf_adam_params;
+int64_t rf_bag_adam_workspace_bytes(int64_t n_keys, int64_t table_rows);
+int rf_bag_backward_adam(const int64_t *d_ids, int64_t n_keys, const int32_t *d_bag_offsets, int32_t bag_len,
+                         int64_t batch, const float *d_grad_out, int64_t grad_stride, int32_t dim, int combiner,
+                         const rf_adam_params *params, float *d_table, float *d_m, float *d_v,
+                         int64_t table_rows, void *d_workspace, int64_t workspace_bytes, void *stream);
+
 /* ---- vocabulary lookup / bucketisation ------------------------------------ */
 /* Keras StringLookup / IntegerLookup(vocabulary=vocabs, output_mode="int") as LookupEmbedding builds */
 /* them (backend/layers/preprocess_layers.py:148-150): term i -> i + 1, out-of-vocabulary -> 0.      */

@@ -228,3 +228,22 @@ def bucketize(values, boundaries):
     out = np.searchsorted(b, v, side="right").astype(np.int64)
     out[np.isnan(v)] = b.size
     return out
+
+
+def bag_backward_adam(ids, grad, W, M, V, step, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7, combiner="sum", L=None,
+                      bag_offsets=None, lazy=False):
+    """In-place Keras Adam step on (W, M, V) from the pooled bag's gradient; returns the touched mask."""
+    ids = np.ascontiguousarray(ids, dtype=np.int64).ravel()
+    grad = np.ascontiguousarray(grad, dtype=np.float32)
+    B, D = grad.shape
+    rows = W.shape[0]
+    for a in (W, M, V):
+        assert a.dtype == np.float32 and a.flags.c_contiguous and a.shape == (rows, D)
+    bo = None if bag_offsets is None else np.ascontiguousarray(bag_offsets, dtype=np.int32)
+    G = np.zeros((rows, D), dtype=np.float32)
+    touched = np.zeros(rows, dtype=np.uint8)
+    lib().rfo_bag_backward_adam(_p(ids), C.c_int64(ids.size), _p(bo), C.c_int64(L or 0), C.c_int64(B), _p(grad), C.c_int64(D),
+                                C.c_int(1 if combiner == "avg" else 0), C.c_float(lr), C.c_float(beta1), C.c_float(beta2),
+                                C.c_float(eps), C.c_int64(step), C.c_int(1 if lazy else 0), _p(W), _p(M), _p(V), C.c_int64(rows),
+                                _p(G), _p(touched))
+    return touched.astype(bool)

@@ -387,6 +387,56 @@ double rfo_inbatch_softmax_ce(const float *q, const float *d, const float *y, in
     return total / (double)B;
 }
 
+/* ------------------------------------------------------------------------------------ */
+/* Backward of the pooled bag + tf.keras.optimizers.Adam on the Embedding variable            */
+/* (example/ranking_search/train.py:97-104; Keras OptimizerV2 Adam._resource_apply_sparse     */
+/* after _deduplicate_indexed_slices): duplicate rows' gradients are summed (here in key      */
+/* order), then EVERY row decays its moments and moves; touched rows add the gradient terms.  */
+/* lazy != 0: touched rows only.  G: caller-zeroed scratch [rows, D]; touched: zeroed [rows]. */
+/* ------------------------------------------------------------------------------------ */
+void rfo_bag_backward_adam(const int64_t *ids, int64_t n_keys, const int32_t *bag_offs, int64_t bag_len,
+                           int64_t B, const float *grad, int64_t D, int avg, float lr, float beta1,
+                           float beta2, float eps, int64_t step, int lazy, float *W, float *M, float *V,
+                           int64_t rows, float *G, uint8_t *touched) {
+    int64_t b = 0;
+    for (int64_t k = 0; k < n_keys; ++k) {
+        float scale = 1.0f;
+        if (bag_offs) {
+            while (b + 1 < B && bag_offs[b + 1] <= k) ++b;
+            if (avg) scale = 1.0f / (float)(bag_offs[b + 1] - bag_offs[b]);
+        } else {
+            b = k / bag_len;
+            if (avg) scale = 1.0f / (float)bag_len;
+        }
+        float *g = G + ids[k] * D;
+        const float *src = grad + b * D;
+        if (!touched[ids[k]]) {
+            touched[ids[k]] = 1;
+            for (int64_t j = 0; j < D; ++j) g[j] = avg ? src[j] * scale : src[j];
+        } else {
+            for (int64_t j = 0; j < D; ++j) g[j] = g[j] + (avg ? src[j] * scale : src[j]);
+        }
+    }
+    const float b1p = powf(beta1, (float)step), b2p = powf(beta2, (float)step);
+    const float lr_t = lr * sqrtf(1.0f - b2p) / (1.0f - b1p);
+    const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
+    for (int64_t r = 0; r < rows; ++r) {
+        if (lazy && !touched[r]) continue;
+        for (int64_t j = 0; j < D; ++j) {
+            const int64_t at = r * D + j;
+            float m = M[at] * beta1, v = V[at] * beta2;
+            if (touched[r]) {
+                const float g = G[at];
+                m = m + g * omb1;
+                v = v + (g * g) * omb2;
+            }
+            M[at] = m;
+            V[at] = v;
+            W[at] = W[at] - (lr_t * m) / (sqrtf(v) + eps);
+        }
+    }
+}
+
 int rfo_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -34,6 +34,11 @@ class VocabDesc(C.Structure):
                 ("slots", C.c_void_p), ("capacity", C.c_int64), ("n_terms", C.c_int64)]
 
 
+class AdamParams(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("epsilon", C.c_float),
+                ("step", C.c_int64), ("lazy", C.c_int32), ("reserved", C.c_int32)]
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -82,6 +87,12 @@ def lib():
                                            C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
         L.rf_combine_partials.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int, C.c_int32, C.c_void_p,
                                           C.c_void_p, C.c_int64, C.c_void_p]
+        L.rf_bag_adam_workspace_bytes.restype = C.c_int64
+        L.rf_bag_adam_workspace_bytes.argtypes = [C.c_int64, C.c_int64]
+        L.rf_bag_backward_adam.restype = C.c_int
+        L.rf_bag_backward_adam.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
+                                           C.c_int, C.POINTER(AdamParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                           C.c_void_p, C.c_int64, C.c_void_p]
         L.rf_vocab_build.argtypes = [C.POINTER(VocabDesc), C.c_void_p]
         L.rf_vocab_lookup_strings.argtypes = [C.POINTER(VocabDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.rf_vocab_lookup_int64.argtypes = [C.POINTER(VocabDesc), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]

@@ -223,3 +223,50 @@ def bag_backward(ids, table, grad_out, alpha, combiner="sum", bag_len=None, bag_
                                             nat.COMBINER[combiner], float(alpha), table.data_ptr(),
                                             C.c_void_p(torch.cuda.current_stream(table.device).cuda_stream)))
     return table
+
+
+class BagAdam(object):
+    """tf.keras.optimizers.Adam for one embedding table, applied from the pooled bag's gradient
+    (rf_bag_backward_adam).  Reference: /root/reference/example/ranking_search/train.py:97-104.
+
+    Keras semantics by default: every row decays its moments and moves each step (`lazy=False`); `lazy=True`
+    updates only the gathered rows.  Owns the moment buffers `m`, `v` and the sort workspace."""
+
+    def __init__(self, table, learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7, lazy=False):
+        _require_cuda(table, "table")
+        if table.dtype != torch.float32 or not table.is_contiguous() or table.dim() != 2:
+            raise ValueError("table must be a contiguous fp32 [rows, dim] tensor")
+        self.table = table
+        self.m = torch.zeros_like(table)
+        self.v = torch.zeros_like(table)
+        self.learning_rate, self.beta_1, self.beta_2, self.epsilon, self.lazy = learning_rate, beta_1, beta_2, epsilon, lazy
+        self.iterations = 0
+        self._ws = None
+
+    def _workspace(self, n_keys):
+        need = int(nat.lib().rf_bag_adam_workspace_bytes(n_keys, self.table.shape[0]))
+        if need < 0:
+            nat.check(nat.RF_ERR_INVALID)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.table.device)
+        return self._ws
+
+    def apply(self, ids, grad_out, combiner="sum", bag_len=None, bag_offsets=None):
+        """One optimizer step.  ids: int64 bucket ids of this table as the forward wrote them (ids_out[t]);
+        grad_out: fp32 [batch, dim] gradient of the pooled output."""
+        ids = _require_cuda(ids, "ids").contiguous().view(-1)
+        g = _require_cuda(grad_out, "grad_out")
+        dim = self.table.shape[1]
+        if g.dtype != torch.float32 or g.dim() != 2 or g.stride(1) != 1 or g.shape[1] != dim:
+            raise ValueError("grad_out must be fp32 [batch, dim] with contiguous columns")
+        self.iterations += 1
+        p = nat.AdamParams(lr=self.learning_rate, beta1=self.beta_1, beta2=self.beta_2, epsilon=self.epsilon,
+                           step=self.iterations, lazy=1 if self.lazy else 0)
+        with torch.cuda.device(self.table.device):
+            ws = self._workspace(ids.numel())
+            nat.check(nat.lib().rf_bag_backward_adam(
+                ids.data_ptr(), ids.numel(), None if bag_offsets is None else bag_offsets.data_ptr(), bag_len or 0, g.shape[0],
+                g.data_ptr(), g.stride(0), dim, nat.COMBINER[combiner], C.byref(p), self.table.data_ptr(), self.m.data_ptr(),
+                self.v.data_ptr(), self.table.shape[0], ws.data_ptr(), ws.numel(),
+                C.c_void_p(torch.cuda.current_stream(self.table.device).cuda_stream)))
+        return self.table
