@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- lookup+pool samples/s of the fused hash + gather + pool path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c2x2|small]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c2x2|c2zipf|c2l1|c3|small]
 
 Workload (config.workload) at every N: SURVEY.md §8(d) "C2" = BASELINE.json configs[1]: 26 hashed
 sparse fields, 1M-row x 64-dim fp32 tables, batch 65536, sum pooling, 4 keys per bag, keys
@@ -33,10 +33,13 @@ WORKLOADS = {
     #        fields rows     dim  batch  L  tables/field
     "c2":   (26, 1_000_000, 64, 65536, 4, 1),
     "c2x2": (26, 1_000_000, 64, 65536, 4, 2),     # reference-faithful double SipHash variant
+    "c2zipf": (26, 1_000_000, 64, 65536, 4, 1),   # SURVEY.md §8(d) secondary run: key values ~ Zipf(1.05) (hot rows)
+    "c2l1": (26, 1_000_000, 64, 65536, 1, 1),     # SURVEY.md §8(d) corner run: one key per bag
     # C3's embedding side: the normalised base_recall_sdpa plan -- 228 hashed fields x 2 tables of 100000 x 8
     "c3":   (228, 100_000, 8, 8192, 1, 2),
     "small": (4, 3000, 16, 2048, 4, 2),
 }
+KEY_ZIPF = {"c2zipf": 1.05}
 N_KEY_BATCHES = 4
 E2E_CHUNKS = 4
 
@@ -58,7 +61,8 @@ def workload_config(name):
     F, N, D, B, L, T = WORKLOADS[name]
     return {"workload": f"{name}: {F} hashed fields x {T} table(s), {N}-row x {D}-dim fp32 tables, batch {B}, "
                         f"{L} keys/bag, sum pooling, {'SipHash-2-4 seeds [2022,2023]' if T == 2 else 'Fingerprint64'}"
-                        f" mod N, mask_value=''",
+                        f" mod N, mask_value='', key values ~ "
+                        f"{'Zipf(%g)' % KEY_ZIPF[name] if name in KEY_ZIPF else 'Uniform[0, 1e7)'}",
             "fields": F, "rows": N, "dim": D, "batch_per_gpu": B, "bag_len": L, "tables_per_field": T,
             "l2_policy": f"inputs larger than L2: {F * T * N * D * 4 / 1e9:.2f} GB of tables gathered at random rows; "
                          f"{N_KEY_BATCHES} distinct key batches rotate across steps"}
@@ -76,7 +80,7 @@ def make_keys(name, rank):
     for bi in range(N_KEY_BATCHES):
         fields = {}
         for f in range(F):
-            arena, offs = c2_field_keys(f, B, L, batch_index=bi + 16 * rank)
+            arena, offs = c2_field_keys(f, B, L, batch_index=bi + 16 * rank, zipf=KEY_ZIPF.get(name))
             fields[f"f{f:02d}"] = (arena, offs, (B, L))
         batches.append(fields)
     return batches
@@ -164,7 +168,7 @@ def tune_cpu_threads(name, key_batches, host_tables, out):
     return th
 
 
-def cpu_reference_run(name, key_batches, host_tables, budget_s=12.0, max_passes=4):
+def cpu_reference_run(name, key_batches, host_tables, budget_s=10.0, max_passes=400):
     """Times whole batches of the workload on all host threads; returns (record, last output, its batch index)."""
     import oracle
     F, N, D, B, L, T = WORKLOADS[name]
@@ -176,10 +180,17 @@ def cpu_reference_run(name, key_batches, host_tables, budget_s=12.0, max_passes=
         cpu_one_pass(name, key_batches[passes % len(key_batches)], host_tables, out)
         passes += 1
     dt = time.perf_counter() - t0
+    last = (passes - 1) % len(key_batches)
+    oracle.set_num_threads(1)                                     # also the single-thread figure
+    t1 = time.perf_counter()
+    cpu_one_pass(name, key_batches[last], host_tables, out)
+    dt1 = time.perf_counter() - t1
+    oracle.set_num_threads(threads)
     return {"value": passes * B / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "single_thread_value": B / dt1, "host_cpus": os.cpu_count(),
             "sample": f"{passes} full batch(es) of {B} samples x {F} fields through oracle/rf_oracle.c "
-                      f"(OpenMP, {threads} threads) in {dt:.2f} s; TensorFlow unavailable, so the reference's TF CPU "
-                      f"path is represented by its restated CPU port"}, out, (passes - 1) % len(key_batches)
+                      f"(OpenMP, {threads} threads) in {dt:.2f} s (+ 1 batch on 1 thread in {dt1:.2f} s); TensorFlow "
+                      f"unavailable, so the reference's TF CPU path is represented by its restated CPU port"}, out, last
 
 
 def host_tables_numpy(name, seed0=7):
@@ -411,6 +422,10 @@ def run_ours(args):
                 "frac": achieved / peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                 "frac_of_nominal_8TBs": achieved / 8000.0, "algorithmic_bytes_per_sample": bps,
                 "algorithmic_bytes_per_launch": bps * B, "kernel_ms": kern_ms, "traffic": None}
+    if name in KEY_ZIPF:
+        roofline["note"] = ("Zipf keys: the hot rows are served by L2, so the algorithmic bytes (every gathered row "
+                            "counted) exceed the HBM traffic and frac may exceed 1; the uniform-key workload c2 is the "
+                            "HBM-bound measurement")
     try:      # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
         tr = json.load(open(os.path.join(ROOT, "profiles", f"traffic_{name}.json")))
         roofline["traffic"] = tr["traffic_bytes_per_launch"]

@@ -253,7 +253,9 @@ def test_cuda_graph_capture_and_replay_with_new_keys():
 @pytest.mark.parametrize("combiner,D", [("sum", 64), ("avg", 16), ("sum", 6)])
 def test_backward_sgd_matches_numpy(combiner, D):
     # gradient of the pooled bag w.r.t. every gathered row (pads included), fused with W -= lr * g.
-    # Atomics make the add order free: compare within fp32 re-association of the duplicates.
+    # Atomics make the add order free: compare within fp32 re-association of the duplicates.  The pad row
+    # collects ~1000 addends of magnitude <= 0.5, so the order-dependent error is bounded by about
+    # n_dup * 2^-24 * max|partial sum| ~ 1000 * 6e-8 * 5 = 3e-4 (typically 1e-5): atol 5e-4.
     from recommendflow_b200.bag_ops import bag_backward
     rng = np.random.default_rng(18)
     B, L, N = 700, 5, 997
@@ -272,7 +274,7 @@ def test_backward_sgd_matches_numpy(combiner, D):
                            ids_out=ids_out, bag_len=L)], B)
     assert np.array_equal(ids_out.cpu().numpy().ravel(), ids)
     bag_backward(ids_out[0], dev_w, torch.from_numpy(g).cuda(), -lr, combiner, bag_len=L)
-    np.testing.assert_allclose(dev_w.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(dev_w.cpu().numpy(), want, rtol=1e-5, atol=5e-4)
     # jagged bags
     lens = rng.integers(0, 9, size=B)
     bag = np.zeros(B + 1, dtype=np.int32)
@@ -285,7 +287,7 @@ def test_backward_sgd_matches_numpy(combiner, D):
     dev_w = torch.from_numpy(w).cuda()
     bag_backward(torch.from_numpy(jid).cuda(), dev_w, torch.from_numpy(g).cuda(), 0.5, combiner,
                  bag_offsets=torch.from_numpy(bag).cuda())
-    np.testing.assert_allclose(dev_w.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(dev_w.cpu().numpy(), want, rtol=1e-5, atol=5e-4)
 
 
 def test_gapped_bags_with_explicit_ends():
