@@ -201,6 +201,13 @@ def _bags_forward(bags, combiner, B, L, keys=None, ids=None, salts=None, mask_mo
     return picked.reshape(L, T * D)                            # concat([L, D], [L, D], axis=1)
 
 
+def _ids_field_call(bag, ids, out):
+    """FieldCall of a single-table bag fed by ready-made ids [B, L] (LookupEmbedding / DiscreteEmbedding)."""
+    bag.build(ids.device)
+    return FieldCall([(bag.embeddings.data, bag.input_dim, None)], bag.output_dim, bag.combiner,
+                     ids=ids.reshape(1, -1).contiguous(), out=out, bag_len=ids.shape[1])
+
+
 class DoubleHashingEmbedding(Layer):
     """Two salted hashes of the same keys -> two tables -> pooled -> concatenated: [B, 2 * D]."""
 
@@ -302,6 +309,10 @@ class LookupEmbedding(Layer):
     def call(self, inputs, *args, **kwargs):
         return self.embedding(self.lookup_ids(inputs))
 
+    def field_call(self, inputs, out):
+        """This feature as one field of a fused launch (ids come from the vocabulary kernel)."""
+        return _ids_field_call(self.embedding, self.lookup_ids(inputs), out)
+
     def get_vocabulary(self):
         oov = "[UNK]" if self.key_type == TYPE_STR else -1
         return [oov] + list(self.vocabulary)
@@ -326,7 +337,7 @@ class DiscreteEmbedding(Layer):
         self.embedding = EmbeddingBag(vocab_size, embedding_dim, True, combiner=pooling,
                                       name=name + "_disc_lookup_embedding")
 
-    def call(self, inputs, *args, **kwargs):
+    def bucket_ids(self, inputs):
         x = inputs if isinstance(inputs, torch.Tensor) else torch.as_tensor(np.asarray(inputs, dtype=np.float32))
         if not x.is_cuda:
             x = x.to(_default_device(), non_blocking=True)
@@ -334,7 +345,13 @@ class DiscreteEmbedding(Layer):
             x = x[:, None]
         if self._edges is None or self._edges.device != x.device:
             self._edges = torch.tensor(self.bin_boundaries, dtype=torch.float32).to(x.device)
-        return self.embedding(bucketize(x, self._edges))
+        return bucketize(x, self._edges)
+
+    def call(self, inputs, *args, **kwargs):
+        return self.embedding(self.bucket_ids(inputs))
+
+    def field_call(self, inputs, out):
+        return _ids_field_call(self.embedding, self.bucket_ids(inputs), out)
 
     def get_vocabulary(self):
         return self.bin_boundaries

@@ -11,7 +11,7 @@ batch through ONE kernel launch and hands back per-feature views of one [B, sum(
 import torch
 
 from ..layers.preprocess_layers import (_POOLED, DiscreteEmbedding, DoubleHashingEmbedding, LookupEmbedding,
-                                        _batch_and_len, as_keys)
+                                        _batch_and_len, _default_device, as_keys)
 from ...bag_ops import bag_forward
 
 
@@ -19,13 +19,21 @@ class PreprocessLayers(dict):
     """{feature name: layer}; plus a fused forward over all hashed features."""
 
     def fused_names(self):
-        return [n for n, l in self.items() if isinstance(l, DoubleHashingEmbedding) and l.combiner in _POOLED]
+        """Features that join the fused launch: pooled hashing features, and pooled lookup / discrete
+        features (their ids come from the vocabulary / bucketize kernels first)."""
+        return [n for n, l in self.items()
+                if (isinstance(l, DoubleHashingEmbedding) and l.combiner in _POOLED)
+                or (isinstance(l, (LookupEmbedding, DiscreteEmbedding)) and l.pooling in _POOLED)]
+
+    def _width(self, name):
+        layer = self[name]
+        return 2 * layer.output_dim if isinstance(layer, DoubleHashingEmbedding) else layer.embedding.output_dim
 
     def output_layout(self, names=None):
         """{name: (column offset, width)} of the fused output buffer, in dict order."""
         layout, col = {}, 0
         for n in (names if names is not None else self.fused_names()):
-            width = 2 * self[n].output_dim
+            width = self._width(n)
             layout[n] = (col, width)
             col += width
         return layout, col
@@ -39,24 +47,37 @@ class PreprocessLayers(dict):
         result = {}
         if fused:
             layout, total = self.output_layout(fused)
-            keys = {n: as_keys(batch[n]) for n in fused}
-            B = _batch_and_len(keys[fused[0]])[0]
-            dev = keys[fused[0]].device
+            hashed = [n for n in fused if isinstance(self[n], DoubleHashingEmbedding)]
+            keys = {n: as_keys(batch[n]) for n in hashed}
+            if hashed:
+                B, dev = _batch_and_len(keys[hashed[0]])[0], keys[hashed[0]].device
+            else:
+                first = batch[fused[0]]
+                B, dev = (first.shape[0] if hasattr(first, "shape") else len(first)), None
             if out is None:
-                out = torch.empty(B, total, dtype=torch.float32, device=dev)
+                out = torch.empty(B, total, dtype=torch.float32, device=dev or _default_device())
             elif tuple(out.shape) != (B, total):
                 raise ValueError(f"out must be [{B}, {total}]")
             calls = []
             for n in fused:
-                layer = self[n].build(dev)
-                if _batch_and_len(keys[n])[0] != B:
-                    raise ValueError(f"feature {n}: batch size differs from the first feature's")
                 col, width = layout[n]
                 view = out[:, col:col + width]
-                if _batch_and_len(keys[n])[1] == 0:
-                    view.zero_()
-                else:
-                    calls.append(layer.field_call(keys[n], view))
+                if n in keys:
+                    layer = self[n].build(out.device)
+                    if _batch_and_len(keys[n])[0] != B:
+                        raise ValueError(f"feature {n}: batch size differs from the first feature's")
+                    if _batch_and_len(keys[n])[1] == 0:
+                        view.zero_()
+                    else:
+                        calls.append(layer.field_call(keys[n], view))
+                else:                                   # lookup / discrete: ids from their own small kernels
+                    call = self[n].field_call(batch[n], view)
+                    if call.ids.shape[1] != B * call.bag_len:
+                        raise ValueError(f"feature {n}: batch size differs from the first feature's")
+                    if call.bag_len == 0:
+                        view.zero_()
+                    else:
+                        calls.append(call)
                 result[n] = view
             bag_forward(calls, B)
             result["__fused__"] = out

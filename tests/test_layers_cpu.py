@@ -56,7 +56,9 @@ def test_factory_builds_reference_layer_set(golden_dir):
     assert isinstance(layers["price"], DiscreteEmbedding) and layers["price"].name == "discrete_price"
     assert layers["price"].embedding.name == "discrete_price_disc_lookup_embedding"
     layout, total = layers.output_layout()
-    assert layout["clk_items"] == (0, 128) and layout["uid"] == (256, 64) and total == 416
+    assert layout["clk_items"] == (0, 128) and layout["uid"] == (256, 64)
+    # pooled lookup / discrete features join the fused buffer after the hashed ones
+    assert layout["top_cat"] == (416, 8) and layout["city_level"] == (424, 4) and layout["avg_price"] == (436, 8) and total == 444
     # the reference's factory passes vocab_size=len(vocabs) although ids go up to len(vocabs); the table here
     # gets the one extra row so that the last term stays inside it
     assert layers["top_cat"].embedding.input_dim == len(layers["top_cat"].vocabulary) + 1 == 4

@@ -95,3 +95,33 @@ def test_lookup_and_discrete_layers_against_oracle():
     got = dlayer(torch.from_numpy(price)).cpu().numpy()
     want = oracle.bag_pool(oracle.bucketize(price.ravel(), edges), dlayer.embedding.get_weights()[0], "sum", L=1)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_forward_all_fuses_hashed_lookup_and_discrete_features():
+    from recommendflow_b200 import _native as nat
+    from recommendflow_b200.backend.layers.preprocess_layers import DoubleHashingEmbedding
+    from recommendflow_b200.backend.utils.preprocess_utils import PreprocessLayers
+    rng = np.random.default_rng(21)
+    B = 300
+    layers = PreprocessLayers()
+    layers["uid"] = DoubleHashingEmbedding(5000, 16, [2022, 2023], "sum", mask_value="", mask_zero=True, name="hashing_uid")
+    layers["top_cat"] = LookupEmbedding(8, "str", ["game", "app", "book"], vocab_size=3, pooling="sum", name="lookup_top_cat")
+    layers["city_level"] = LookupEmbedding(4, "int", [1, 2, 3, 4, 5], vocab_size=5, pooling="max", name="lookup_city_level")
+    layers["price"] = DiscreteEmbedding(8, [0.5, 10, 100.25, 1000], vocab_size=4, pooling="sum", name="discrete_price")
+    cats = ["game", "app", "book", "zzz", ""]
+    batch = {"uid": [[f"u{int(v)}", f"u{int(v) + 1}"] for v in rng.integers(0, 10**6, size=B)],
+             "top_cat": [[cats[int(i)] for i in rng.integers(0, 5, size=3)] for _ in range(B)],
+             "city_level": torch.from_numpy(rng.integers(0, 8, size=(B, 2))),
+             "price": torch.from_numpy(rng.uniform(0, 2000, size=(B, 1)).astype(np.float32))}
+    singles = {n: layers[n](batch[n]) for n in layers}
+    before = nat.launch_count()
+    res = layers.forward_all(batch)
+    assert nat.launch_count() == before + 4          # 2 vocabulary lookups + 1 bucketize + ONE fused gather/pool launch
+    layout, total = layers.output_layout()
+    assert total == 32 + 8 + 4 + 8 and res["__fused__"].shape == (B, total)
+    for n in layers:
+        assert torch.equal(res[n], singles[n]), n
+    # and the lookup path against the oracle
+    flat = [x for r in batch["top_cat"] for x in r]
+    want = oracle.bag_pool(oracle.vocab_lookup(flat, ["game", "app", "book"]), layers["top_cat"].embedding.get_weights()[0], "sum", L=3)
+    assert np.array_equal(res["top_cat"].cpu().numpy().view(np.uint32), want.view(np.uint32))
