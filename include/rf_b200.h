@@ -213,6 +213,20 @@ int rf_bag_backward_adam(const int64_t *d_ids, int64_t n_keys, const int32_t *d_
                          const rf_adam_params *params, float *d_table, float *d_m, float *d_v,
                          int64_t table_rows, void *d_workspace, int64_t workspace_bytes, void *stream);
 
+/* ---- backward of the dense contractions (CUDA-core fp32; what model.fit differentiates) -------- */
+/* Gradient of scaled_dot_product_attention (layer_utils.py:4-24) w.r.t. q, k, v given d_grad_out =   */
+/* dL/d(out); same layouts as rf_sdpa_forward.  A masked query row passes gradient to v only.        */
+/* seq_len <= 64, head_dim <= 128, else RF_ERR_UNSUPPORTED.                                           */
+int rf_sdpa_backward(const float *d_q, const float *d_k, const float *d_v, const float *d_mask,
+                     const float *d_grad_out, int64_t n_batch_heads, int32_t seq_len, int32_t head_dim,
+                     float *d_dq, float *d_dk, float *d_dv, void *stream);
+/* Gradient of batch_neg_sample_scaled_multi_class_ce_loss (match_losses.py:150-165) w.r.t. query   */
+/* and doc (either output may be NULL), times `upstream` (dL/d loss).  d_lse: the per-row            */
+/* log-sum-exp rf_inbatch_rowstats[_tc] produced for the same inputs.  dim <= 512.  Deterministic.   */
+int rf_inbatch_softmax_ce_backward(const float *d_query, const float *d_doc, const float *d_y,
+                                   const float *d_lse, int64_t batch, int32_t dim, float scale,
+                                   float upstream, float *d_grad_query, float *d_grad_doc, void *stream);
+
 /* ---- vocabulary lookup / bucketisation ------------------------------------ */
 /* Keras StringLookup / IntegerLookup(vocabulary=vocabs, output_mode="int") as LookupEmbedding builds */
 /* them (backend/layers/preprocess_layers.py:148-150): term i -> i + 1, out-of-vocabulary -> 0.      */

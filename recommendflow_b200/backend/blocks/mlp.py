@@ -5,7 +5,8 @@ Reference quirk kept: the SAME normalization layer instance is appended before e
 one BatchNormalization would be applied to inputs of different widths -- Keras builds it on the first
 width and fails on the second unless all widths are equal.  Here the shared instance keeps one set of
 statistics per distinct width (the only way the reference's towers [1024, 512, 256] can run at all).
-Dense layers are library GEMMs (cuBLAS via torch); inference mode (moving statistics, no dropout).
+Dense layers are library GEMMs (cuBLAS via torch).  Inference mode (moving statistics, no dropout) unless a
+training step switches `BatchNormalization.batch_stats` / `Dropout.active` on (recommendflow_b200/training.py).
 """
 import torch
 
@@ -24,10 +25,12 @@ _ACT = {None: lambda x: x, "linear": lambda x: x, "relu": torch.relu, "selu": _s
 class BatchNormalization(Layer):
     """Keras BatchNormalization at inference: gamma * (x - moving_mean) / sqrt(moving_var + eps) + beta."""
 
-    def __init__(self, epsilon=1e-3, name=None):
+    def __init__(self, epsilon=1e-3, momentum=0.99, name=None):
         super().__init__(name=name)
         self.epsilon = epsilon
+        self.momentum = momentum
         self.stats = {}          # width -> (gamma, beta, moving_mean, moving_var)
+        self.batch_stats = False  # True during a training step: normalise with the batch's own statistics
 
     def set_weights(self, weights):
         gamma, beta, mean, var = (torch.as_tensor(w, dtype=torch.float32) for w in weights)
@@ -38,8 +41,24 @@ class BatchNormalization(Layer):
         if d not in self.stats:
             self.stats[d] = (torch.ones(d), torch.zeros(d), torch.zeros(d), torch.ones(d))
         gamma, beta, mean, var = (t.to(x.device) for t in self.stats[d])
+        if self.batch_stats:     # Keras training=True: batch mean / biased variance, moving statistics updated
+            bmean, bvar = x.mean(dim=0), x.var(dim=0, unbiased=False)
+            with torch.no_grad():
+                mean = mean * self.momentum + bmean.detach() * (1 - self.momentum)
+                var = var * self.momentum + bvar.detach() * (1 - self.momentum)
+            self.stats[d] = (gamma, beta, mean, var)
+            return (x - bmean) * (gamma * torch.rsqrt(bvar + self.epsilon)) + beta
         self.stats[d] = (gamma, beta, mean, var)
         return (x - mean) * (gamma * torch.rsqrt(var + self.epsilon)) + beta
+
+    def trainable(self):
+        """gamma / beta of every width seen so far, as leaves that require grad."""
+        out = []
+        for d, (gamma, beta, mean, var) in list(self.stats.items()):
+            gamma, beta = gamma.detach().requires_grad_(True), beta.detach().requires_grad_(True)
+            self.stats[d] = (gamma, beta, mean, var)
+            out += [gamma, beta]
+        return out
 
 
 class Sequential(Layer):
@@ -68,10 +87,22 @@ class _Activated(Layer):
         return _ACT[self.activation](self.dense(x))
 
 
+class Dropout(Layer):
+    """Keras Dropout(rate): identity unless `active` (a training step), then inverted dropout."""
+
+    def __init__(self, rate, name=None):
+        super().__init__(name=name)
+        self.rate = rate
+        self.active = False
+
+    def call(self, x):
+        return torch.nn.functional.dropout(x, self.rate, training=True) if self.active and self.rate > 0 else x
+
+
 def create_mlp(hidden_units, dropout_rate, activation, normalization_layer, name=None):
     layers = []
     for units in hidden_units:
         layers.append(normalization_layer)
         layers.append(_Activated(units, activation))
-        # Dropout(dropout_rate): identity at inference
+        layers.append(Dropout(dropout_rate))
     return Sequential(layers, name=name)

@@ -1,14 +1,17 @@
 """Attention helpers with the reference's names (/root/reference/backend/layers/layer_utils.py)."""
 import torch
 
-from ...dense_ops import sdpa
+from ...dense_ops import sdpa, sdpa_autograd
 
 
 def scaled_dot_product_attention(q, k, v, mask):
     """softmax(where(mask == 0, -2**32 + 1, q k^T / sqrt(dk))) v   (layer_utils.py:4-24).
 
     q, k, v: [..., seq_len, dim] CUDA tensors; mask: [..., seq_len, 1] -- it broadcasts over KEYS, so a
-    zero masks a whole QUERY row (which then attends uniformly), exactly as in the reference."""
+    zero masks a whole QUERY row (which then attends uniformly), exactly as in the reference.
+    When an input requires grad the differentiable op (CUDA forward + CUDA backward) is recorded."""
+    if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in (q, k, v)):
+        return sdpa_autograd(q, k, v, mask)
     return sdpa(q, k, v, mask)
 
 

@@ -17,7 +17,7 @@ from functools import partial
 
 import torch
 
-from ...dense_ops import inbatch_rowstats
+from ...dense_ops import inbatch_rowstats, inbatch_softmax_ce_autograd
 
 
 def _vec(t, like):
@@ -61,7 +61,10 @@ def cosent_loss_v2(y_true, query, doc, scale=20):
 
 
 def batch_neg_sample_scaled_multi_class_ce_loss(y_true, query, doc, scale=20):
-    """mean_i( -log( exp(s S_ii) / sum_j exp(s S_ij) ) * y_i ),  S = query . doc^T   (:150-165)."""
+    """mean_i( -log( exp(s S_ii) / sum_j exp(s S_ij) ) * y_i ),  S = query . doc^T   (:150-165).
+    When query or doc requires grad the differentiable op (CUDA forward + CUDA backward) is recorded."""
+    if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in (query, doc)):
+        return inbatch_softmax_ce_autograd(_vec(y_true, query), query, doc, float(scale))
     return inbatch_rowstats(query, doc, y_true=y_true, scale=scale, want=("lse", "diag"))["loss"]
 
 

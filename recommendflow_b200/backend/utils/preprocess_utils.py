@@ -38,10 +38,12 @@ class PreprocessLayers(dict):
             col += width
         return layout, col
 
-    def forward_all(self, batch, names=None, out=None):
+    def forward_all(self, batch, names=None, out=None, keep_ids=None):
         """batch: {feature name: StringColumn | int tensor | lists}.  Returns {name: tensor}.
 
-        Hashed, pooled features go through one fused launch; the rest are called one by one."""
+        Hashed, pooled features go through one fused launch; the rest are called one by one.
+        keep_ids: optional dict that receives, per fused feature, the row ids the launch gathered
+        ([tables, B * L] int64) and the bag length -- what the backward / optimizer step needs."""
         names = list(names) if names is not None else [n for n in self if n in batch]
         fused = [n for n in names if n in set(self.fused_names())]
         result = {}
@@ -69,7 +71,12 @@ class PreprocessLayers(dict):
                     if _batch_and_len(keys[n])[1] == 0:
                         view.zero_()
                     else:
-                        calls.append(layer.field_call(keys[n], view))
+                        call = layer.field_call(keys[n], view)
+                        if keep_ids is not None:
+                            n_items = _batch_and_len(keys[n])[0] * _batch_and_len(keys[n])[1]
+                            call.ids_out = torch.empty(2, n_items, dtype=torch.int64, device=out.device)
+                            keep_ids[n] = (call.ids_out, _batch_and_len(keys[n])[1])
+                        calls.append(call)
                 else:                                   # lookup / discrete: ids from their own small kernels
                     call = self[n].field_call(batch[n], view)
                     if call.ids.shape[1] != B * call.bag_len:
@@ -78,6 +85,8 @@ class PreprocessLayers(dict):
                         view.zero_()
                     else:
                         calls.append(call)
+                        if keep_ids is not None:
+                            keep_ids[n] = (call.ids, call.bag_len)
                 result[n] = view
             bag_forward(calls, B)
             result["__fused__"] = out

@@ -1,0 +1,266 @@
+// rf_dense_bwd.cu -- backward of the two dense contractions of the path (SURVEY.md §8f rank 1:
+// what `model.fit` differentiates; first correct CUDA-core fp32 versions, tensor-core versions are
+// the follow-up):
+//
+//  * rf_sdpa_backward: gradient of scaled_dot_product_attention (backend/layers/layer_utils.py:4-24)
+//    w.r.t. q, k, v.  One CTA per (batch, head) slice, everything in shared memory: P is recomputed
+//    from q, k and the mask exactly like the forward (a masked QUERY row is filled with the constant
+//    -4294967295, so it becomes uniform attention and passes no gradient to q / k, only to v).
+//        dV = P^T dO;  dP = dO V^T;  dS = P o (dP - rowsum(P o dP));  dQ = dS K / sqrt(dh);
+//        dK = dS^T Q / sqrt(dh)
+//  * rf_inbatch_softmax_ce_backward: gradient of batch_neg_sample_scaled_multi_class_ce_loss
+//    (backend/lossess/match_losses.py:150-165) w.r.t. query and doc, from the per-row log-sum-exp
+//    the forward (rf_inbatch_rowstats*) already produced; the B x B matrix is never stored:
+//        C_ij = upstream * y_i * scale / B * (exp(scale * S_ij - lse_i) - [i == j])
+//        dQ = C D,   dD = C^T Q
+//    Two passes of one kernel (owner = query rows / owner = doc rows): a CTA owns 32 rows of its
+//    side, keeps their gradient in registers, streams 64-row tiles of the other side through
+//    shared memory, recomputes the S tile, forms C and accumulates.  No atomics: deterministic.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "../../include/rf_b200.h"
+#include "rf_common.h"
+
+namespace rf {
+
+extern std::atomic<int64_t> g_launches;
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// --------------------------------------------------------------------------------------------
+// SDPA backward
+// --------------------------------------------------------------------------------------------
+constexpr int kBwdMaxSeq = 64;
+constexpr int kBwdMaxHeadDim = 128;
+
+__global__ void __launch_bounds__(kThreads)
+sdpa_backward_kernel(const float *__restrict__ q, const float *__restrict__ k, const float *__restrict__ v,
+                     const float *__restrict__ mask, const float *__restrict__ grad_out, int S, int dh,
+                     float *__restrict__ dq, float *__restrict__ dk, float *__restrict__ dv) {
+    extern __shared__ float smem[];
+    const int ld = dh + 1, lp = S + 1;
+    float *Q = smem, *K = Q + S * ld, *V = K + S * ld, *G = V + S * ld;      // [S][dh + 1]
+    float *P = G + S * ld, *dS = P + S * lp;                                // [S][S + 1]
+    float *rowm = dS + S * lp;                                              // [S] mask flag per query row
+    const int64_t base = (int64_t)blockIdx.x * S * dh;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < S * dh; e += kThreads) {
+        const int i = e / dh, c = e - i * dh;
+        Q[i * ld + c] = q[base + e];
+        K[i * ld + c] = k[base + e];
+        V[i * ld + c] = v[base + e];
+        G[i * ld + c] = grad_out[base + e];
+    }
+    for (int i = tid; i < S; i += kThreads) rowm[i] = mask ? mask[(int64_t)blockIdx.x * S + i] : 1.0f;
+    __syncthreads();
+    const float scale = 1.0f / sqrtf((float)dh);
+    // logits (mask fill) and dP = dO V^T
+    for (int e = tid; e < S * S; e += kThreads) {
+        const int i = e / S, j = e - i * S;
+        float s = 0.f, dp = 0.f;
+        for (int c = 0; c < dh; ++c) {
+            s = fmaf(Q[i * ld + c], K[j * ld + c], s);
+            dp = fmaf(G[i * ld + c], V[j * ld + c], dp);
+        }
+        P[i * lp + j] = rowm[i] == 0.0f ? -4294967295.0f : s * scale;
+        dS[i * lp + j] = dp;
+    }
+    __syncthreads();
+    // row softmax, delta_i = sum_j P_ij dP_ij, dS = P o (dP - delta); one warp per row
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int i = warp; i < S; i += kThreads / 32) {
+        float mx = -INFINITY;
+        for (int j = lane; j < S; j += 32) mx = fmaxf(mx, P[i * lp + j]);
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float den = 0.f;
+        for (int j = lane; j < S; j += 32) {
+            const float p = expf(P[i * lp + j] - mx);
+            P[i * lp + j] = p;
+            den += p;
+        }
+        for (int o = 16; o; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+        const float inv = 1.0f / den;
+        float delta = 0.f;
+        for (int j = lane; j < S; j += 32) {
+            const float p = P[i * lp + j] * inv;
+            P[i * lp + j] = p;
+            delta = fmaf(p, dS[i * lp + j], delta);
+        }
+        for (int o = 16; o; o >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, o);
+        const bool masked = rowm[i] == 0.0f;      // constant logits: nothing flows to q / k from this row
+        for (int j = lane; j < S; j += 32) dS[i * lp + j] = masked ? 0.f : P[i * lp + j] * (dS[i * lp + j] - delta);
+    }
+    __syncthreads();
+    for (int e = tid; e < S * dh; e += kThreads) {
+        const int i = e / dh, c = e - i * dh;
+        float aq = 0.f, ak = 0.f, av = 0.f;
+        for (int j = 0; j < S; ++j) {
+            aq = fmaf(dS[i * lp + j], K[j * ld + c], aq);       // dQ_i = sum_j dS_ij K_j
+            ak = fmaf(dS[j * lp + i], Q[j * ld + c], ak);       // dK_i = sum_j dS_ji Q_j
+            av = fmaf(P[j * lp + i], G[j * ld + c], av);        // dV_i = sum_j P_ji dO_j
+        }
+        dq[base + e] = aq * scale;
+        dk[base + e] = ak * scale;
+        dv[base + e] = av;
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// in-batch softmax cross-entropy backward
+// --------------------------------------------------------------------------------------------
+constexpr int kOwn = 32;     // owner rows per CTA
+constexpr int kOth = 64;     // rows of the other side per tile
+
+// OWNER_IS_QUERY: own = query rows i, other = doc rows j, C_ij indexed (own, other);
+// else          : own = doc rows j,  other = query rows i, C_ij indexed (other, own).
+template <bool OWNER_IS_QUERY, int NV>
+__global__ void __launch_bounds__(kThreads)
+ce_backward_kernel(const float *__restrict__ own, const float *__restrict__ oth, const float *__restrict__ y,
+                   const float *__restrict__ lse, int64_t B, int dim, float scale, float coef, float *__restrict__ grad_own) {
+    extern __shared__ float smem[];
+    const int ld = dim + 1;
+    float *A = smem;                   // [kOwn][dim + 1] owner rows
+    float *T = A + kOwn * ld;          // [kOth][dim + 1] tile of the other side
+    float *C = T + kOth * ld;          // [kOwn][kOth + 1]
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int64_t own0 = (int64_t)blockIdx.x * kOwn;
+    for (int e = tid; e < kOwn * dim; e += kThreads) {
+        const int r = e / dim, c = e - r * dim;
+        A[r * ld + c] = own0 + r < B ? own[(own0 + r) * dim + c] : 0.f;
+    }
+    float acc[2][NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[0][v] = acc[1][v] = 0.f;
+    const int o0 = ty * 2, o1 = o0 + 1;
+    for (int64_t t0 = 0; t0 < B; t0 += kOth) {
+        __syncthreads();               // previous tile fully consumed (and A loaded, first time round)
+        for (int e = tid; e < kOth * dim; e += kThreads) {
+            const int r = e / dim, c = e - r * dim;
+            T[r * ld + c] = t0 + r < B ? oth[(t0 + r) * dim + c] : 0.f;
+        }
+        __syncthreads();
+        // S tile: this thread's 2 owner rows x 4 other rows (tx, tx + 16, tx + 32, tx + 48)
+        float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        for (int c = 0; c < dim; ++c) {
+            const float a0 = A[o0 * ld + c], a1 = A[o1 * ld + c];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float b = T[(tx + 16 * u) * ld + c];
+                s[0][u] = fmaf(a0, b, s[0][u]);
+                s[1][u] = fmaf(a1, b, s[1][u]);
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < 2; ++w)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t go = own0 + o0 + w, gt = t0 + tx + 16 * u;
+                float cv = 0.f;
+                if (go < B && gt < B) {
+                    const int64_t row = OWNER_IS_QUERY ? go : gt;       // the query index owns lse and y
+                    cv = coef * y[row] * (expf(scale * s[w][u] - lse[row]) - (go == gt ? 1.0f : 0.0f));
+                }
+                C[(o0 + w) * (kOth + 1) + tx + 16 * u] = cv;
+            }
+        __syncthreads();
+        // grad_own[o][c] += sum_t C[o][t] * T[t][c]; this thread: rows o0, o1, columns tx + 16 v
+        for (int t = 0; t < kOth; ++t) {
+            const float c0 = C[o0 * (kOth + 1) + t], c1 = C[o1 * (kOth + 1) + t];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const int col = tx + 16 * v;
+                if (col < dim) {
+                    const float b = T[t * ld + col];
+                    acc[0][v] = fmaf(c0, b, acc[0][v]);
+                    acc[1][v] = fmaf(c1, b, acc[1][v]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < 2; ++w)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const int col = tx + 16 * v;
+            const int64_t go = own0 + o0 + w;
+            if (col < dim && go < B) grad_own[go * dim + col] = acc[w][v];
+        }
+}
+
+template <bool OWNER_IS_QUERY>
+int launch_ce_pass(const float *own, const float *oth, const float *y, const float *lse, int64_t B, int dim, float scale,
+                   float coef, float *grad_own, cudaStream_t st) {
+    const size_t smem = sizeof(float) * ((size_t)(kOwn + kOth) * (dim + 1) + (size_t)kOwn * (kOth + 1));
+    const unsigned grid = (unsigned)((B + kOwn - 1) / kOwn);
+#define RF_CE_LAUNCH(NV)                                                                                              \
+    do {                                                                                                              \
+        auto fn = ce_backward_kernel<OWNER_IS_QUERY, NV>;                                                              \
+        RF_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
+        fn<<<grid, kThreads, smem, st>>>(own, oth, y, lse, B, dim, scale, coef, grad_own);                            \
+    } while (0)
+    if (dim <= 128) RF_CE_LAUNCH(8);
+    else if (dim <= 256) RF_CE_LAUNCH(16);
+    else RF_CE_LAUNCH(32);
+#undef RF_CE_LAUNCH
+    RF_CUDA(cudaGetLastError());
+    return RF_OK;
+}
+
+}  // namespace
+}  // namespace rf
+
+using namespace rf;
+
+extern "C" {
+
+int rf_sdpa_backward(const float *d_q, const float *d_k, const float *d_v, const float *d_mask, const float *d_grad_out,
+                     int64_t n_batch_heads, int32_t seq_len, int32_t head_dim, float *d_dq, float *d_dk, float *d_dv,
+                     void *stream) {
+    if (n_batch_heads < 0 || seq_len <= 0 || head_dim <= 0) return set_error(RF_ERR_INVALID, "bad sdpa shape");
+    if (seq_len > kBwdMaxSeq || head_dim > kBwdMaxHeadDim)
+        return set_error(RF_ERR_UNSUPPORTED, "rf_sdpa_backward handles seq_len <= %d and head_dim <= %d (got %d, %d)", kBwdMaxSeq,
+                         kBwdMaxHeadDim, seq_len, head_dim);
+    if (n_batch_heads == 0) return RF_OK;
+    if (n_batch_heads > INT32_MAX) return set_error(RF_ERR_INVALID, "too many (batch, head) slices");
+    if (!d_q || !d_k || !d_v || !d_grad_out || !d_dq || !d_dk || !d_dv) return set_error(RF_ERR_INVALID, "rf_sdpa_backward: NULL buffer");
+    const size_t smem = sizeof(float) * ((size_t)4 * seq_len * (head_dim + 1) + (size_t)2 * seq_len * (seq_len + 1) + seq_len);
+    RF_CUDA(cudaFuncSetAttribute(sdpa_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sdpa_backward_kernel<<<(unsigned)n_batch_heads, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        d_q, d_k, d_v, d_mask, d_grad_out, seq_len, head_dim, d_dq, d_dk, d_dv);
+    RF_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return RF_OK;
+}
+
+int rf_inbatch_softmax_ce_backward(const float *d_query, const float *d_doc, const float *d_y, const float *d_lse, int64_t batch,
+                                   int32_t dim, float scale, float upstream, float *d_grad_query, float *d_grad_doc,
+                                   void *stream) {
+    if (batch < 0 || dim <= 0) return set_error(RF_ERR_INVALID, "bad in-batch shape");
+    if (dim > 512) return set_error(RF_ERR_UNSUPPORTED, "rf_inbatch_softmax_ce_backward handles dim <= 512 (got %d)", dim);
+    if (batch == 0) return RF_OK;
+    if (!d_query || !d_doc || !d_y || !d_lse) return set_error(RF_ERR_INVALID, "rf_inbatch_softmax_ce_backward: NULL input");
+    if (!d_grad_query && !d_grad_doc) return set_error(RF_ERR_INVALID, "rf_inbatch_softmax_ce_backward: no output requested");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float coef = upstream * scale / (float)batch;
+    int launches = 0;
+    if (d_grad_query) {
+        int rc = launch_ce_pass<true>(d_query, d_doc, d_y, d_lse, batch, dim, scale, coef, d_grad_query, st);
+        if (rc != RF_OK) return rc;
+        ++launches;
+    }
+    if (d_grad_doc) {
+        int rc = launch_ce_pass<false>(d_doc, d_query, d_y, d_lse, batch, dim, scale, coef, d_grad_doc, st);
+        if (rc != RF_OK) return rc;
+        ++launches;
+    }
+    g_launches.fetch_add(launches);
+    return RF_OK;
+}
+
+}  // extern "C"

@@ -83,3 +83,89 @@ def inbatch_rowstats(query, doc, y_true=None, col_weight=None, scale=20.0, margi
     if loss is not None:
         res["loss"] = loss
     return res
+
+
+def _mask_rows(mask, q):
+    if mask is None:
+        return None
+    m = _f32(mask, "mask")
+    if m.dim() == q.dim() and m.shape[-1] == 1:
+        m = m[..., 0]
+    return m.expand(q.shape[:-1]).contiguous()
+
+
+def sdpa_backward(q, k, v, mask, grad_out):
+    """(dq, dk, dv) of `sdpa` given grad_out = dL/d(out) (rf_sdpa_backward, exact fp32)."""
+    q, k, v, g = _f32(q, "q"), _f32(k, "k"), _f32(v, "v"), _f32(grad_out, "grad_out")
+    if not (q.shape == k.shape == v.shape == g.shape):
+        raise ValueError("q, k, v and grad_out must share one shape")
+    S, dh = q.shape[-2], q.shape[-1]
+    nb = q.numel() // (S * dh) if S * dh else 0
+    m = _mask_rows(mask, q)
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+    with torch.cuda.device(q.device):
+        nat.check(nat.lib().rf_sdpa_backward(q.data_ptr(), k.data_ptr(), v.data_ptr(), None if m is None else m.data_ptr(),
+                                             g.data_ptr(), nb, S, dh, dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                             _stream(q.device)))
+    return dq, dk, dv
+
+
+def inbatch_softmax_ce_backward(query, doc, y_true, lse, scale=20.0, upstream=1.0, need_query=True, need_doc=True):
+    """(d loss / d query, d loss / d doc) of batch_neg_sample_scaled_multi_class_ce_loss, from the forward's lse."""
+    q, d = _f32(query, "query"), _f32(doc, "doc")
+    y, lse = _f32(y_true, "y_true").reshape(-1), _f32(lse, "lse").reshape(-1)
+    B, D = q.shape
+    if d.shape != q.shape or y.numel() != B or lse.numel() != B:
+        raise ValueError("query / doc must be [B, D]; y_true and lse one entry per row")
+    gq = torch.empty_like(q) if need_query else None
+    gd = torch.empty_like(d) if need_doc else None
+    with torch.cuda.device(q.device):
+        nat.check(nat.lib().rf_inbatch_softmax_ce_backward(q.data_ptr(), d.data_ptr(), y.data_ptr(), lse.data_ptr(), B, D,
+                                                           float(scale), float(upstream),
+                                                           None if gq is None else gq.data_ptr(),
+                                                           None if gd is None else gd.data_ptr(), _stream(q.device)))
+    return gq, gd
+
+
+class SdpaFunction(torch.autograd.Function):
+    """scaled_dot_product_attention with the CUDA forward (tensor cores when the shape allows) and the CUDA
+    backward, for training through torch.autograd."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, mask, precision):
+        ctx.save_for_backward(q, k, v, mask if mask is not None else torch.empty(0, device=q.device))
+        ctx.has_mask = mask is not None
+        return sdpa(q, k, v, mask, precision)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        q, k, v, mask = ctx.saved_tensors
+        dq, dk, dv = sdpa_backward(q, k, v, mask if ctx.has_mask else None, grad_out)
+        return dq.view_as(q), dk.view_as(k), dv.view_as(v), None, None
+
+
+class InbatchSoftmaxCeFunction(torch.autograd.Function):
+    """batch_neg_sample_scaled_multi_class_ce_loss(y_true, query, doc, scale) as one differentiable op: the
+    forward keeps only the per-row log-sum-exp, the backward recomputes the logits tile by tile."""
+
+    @staticmethod
+    def forward(ctx, y_true, query, doc, scale, precision):
+        res = inbatch_rowstats(query, doc, y_true=y_true, scale=scale, want=("lse",), precision=precision)
+        ctx.save_for_backward(y_true, query, doc, res["lse"])
+        ctx.scale = float(scale)
+        return res["loss"]
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        y, q, d, lse = ctx.saved_tensors
+        gq, gd = inbatch_softmax_ce_backward(q, d, y, lse, ctx.scale, float(grad_loss), ctx.needs_input_grad[1],
+                                             ctx.needs_input_grad[2])
+        return None, gq, gd, None, None
+
+
+def sdpa_autograd(q, k, v, mask=None, precision=None):
+    return SdpaFunction.apply(q, k, v, mask, precision)
+
+
+def inbatch_softmax_ce_autograd(y_true, query, doc, scale=20.0, precision=None):
+    return InbatchSoftmaxCeFunction.apply(y_true, query, doc, scale, precision)

@@ -49,6 +49,10 @@ class RecallSdpa(torch.nn.Module):
 
     def towers(self, batch, behaviour=None):
         embs = self.preprocessor.forward_all(batch, names=self.user_cols + self.ad_cols)
+        return self.towers_from_embeddings(embs, behaviour)
+
+    def towers_from_embeddings(self, embs, behaviour=None):
+        """The dense part: {feature name: pooled embedding} (+ behaviour sequence) -> normalised tower outputs."""
         user = [embs[n] for n in self.user_cols]
         if self.seq_encoder is not None and behaviour is not None:
             x, mask = behaviour

@@ -150,3 +150,61 @@ def test_full_size_logits_properties():
         assert torch.allclose(r["diag"], torch.ones(B, device="cuda"), atol=1e-5)
         assert float(r["lse"].min()) >= 20.0 - tol and float(r["loss"]) >= -tol
         assert torch.allclose(r["lse"][rows].double(), ref, atol=tol), precision
+
+
+# ---- backward of the dense contractions: CUDA kernels vs torch.autograd on a float64 restatement -----------
+def _ref_sdpa64(q, k, v, mask):
+    s = q @ k.transpose(-1, -2) / np.sqrt(q.shape[-1])
+    if mask is not None:
+        s = torch.where(mask == 0, torch.full_like(s, -4294967295.0), s)      # [..., S, 1] broadcasts over keys
+    return torch.softmax(s, dim=-1) @ v
+
+
+@pytest.mark.parametrize("shape", [(6, 50, 32), (3, 2, 50, 64), (2, 64, 128), (5, 1, 8), (4, 3, 17, 20)])
+def test_sdpa_backward_matches_autograd(shape):
+    from recommendflow_b200.dense_ops import sdpa_autograd
+    rng = np.random.default_rng(sum(shape) + 1)
+    q, k, v, g = (torch.from_numpy(rng.standard_normal(shape).astype(np.float32)).cuda() for _ in range(4))
+    mask = torch.from_numpy((rng.uniform(size=shape[:-1] + (1,)) > 0.3).astype(np.float32)).cuda()
+    mask[0] = 0                                                               # a fully masked sequence
+    for m in (mask, None):
+        q64, k64, v64 = (t.double().requires_grad_(True) for t in (q, k, v))
+        _ref_sdpa64(q64, k64, v64, None if m is None else m.double()).backward(g.double())
+        qg, kg, vg = (t.clone().requires_grad_(True) for t in (q, k, v))
+        out = sdpa_autograd(qg, kg, vg, m, "fp32")
+        out.backward(g)
+        for name, got, want in (("dq", qg.grad, q64.grad), ("dk", kg.grad, k64.grad), ("dv", vg.grad, v64.grad)):
+            # fp32 accumulation of <= 128-term dot products of N(0,1) values, chained three deep
+            np.testing.assert_allclose(got.cpu().numpy(), want.float().cpu().numpy(), rtol=2e-4, atol=2e-5, err_msg=name)
+        if m is not None:                                                     # masked query rows pass nothing to q
+            assert float(qg.grad[0].abs().max()) == 0.0
+    with pytest.raises(NotImplementedError):
+        big = torch.zeros(1, 65, 8, device="cuda", requires_grad=True)
+        sdpa_autograd(big, big, big, None, "fp32").sum().backward()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("B,D", [(300, 64), (1000, 256), (77, 20), (2048, 128), (130, 512)])
+def test_inbatch_softmax_ce_backward_matches_autograd(B, D, precision):
+    from recommendflow_b200.dense_ops import inbatch_softmax_ce_autograd
+    rng = np.random.default_rng(B + D)
+    q = torch.nn.functional.normalize(torch.from_numpy(rng.standard_normal((B, D)).astype(np.float32)), dim=1).cuda()
+    d = torch.nn.functional.normalize(torch.from_numpy(rng.standard_normal((B, D)).astype(np.float32)), dim=1).cuda()
+    y = torch.from_numpy((rng.uniform(size=B) > 0.3).astype(np.float32)).cuda()
+    q64, d64 = q.double().requires_grad_(True), d.double().requires_grad_(True)
+    s = 20.0 * (q64 @ d64.T)
+    ref = (-(torch.diagonal(s) - torch.logsumexp(s, dim=1)) * y.double()).mean()
+    (3.0 * ref).backward()
+    qg, dg = q.clone().requires_grad_(True), d.clone().requires_grad_(True)
+    loss = inbatch_softmax_ce_autograd(y, qg, dg, 20.0, precision)
+    (3.0 * loss).backward()
+    # the gradient is a softmax-weighted sum of unit vectors times 20 / B; in tf32 mode only the forward's lse
+    # carries TF32 error (|d lse| <~ 20 * 2^-10), the backward recomputes the logits in fp32
+    tol = dict(rtol=1e-3, atol=2e-6) if precision == "fp32" else dict(rtol=3e-2, atol=3e-2 * 60.0 / B)
+    assert abs(float(loss) - float(ref)) <= (1e-4 if precision == "fp32" else 3e-2)
+    np.testing.assert_allclose(qg.grad.cpu().numpy(), q64.grad.float().cpu().numpy(), **tol)
+    np.testing.assert_allclose(dg.grad.cpu().numpy(), d64.grad.float().cpu().numpy(), **tol)
+    # only one side requested
+    qh = q.clone().requires_grad_(True)
+    inbatch_softmax_ce_autograd(y, qh, d, 20.0, "fp32").backward()
+    np.testing.assert_allclose(qh.grad.cpu().numpy(), (q64.grad / 3.0).float().cpu().numpy(), rtol=1e-3, atol=2e-6)

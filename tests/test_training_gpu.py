@@ -1,0 +1,57 @@
+"""A few optimisation steps of the two-tower recall model (recommendflow_b200/training.py): CUDA forward,
+CUDA backward of the loss / SDPA / bags, Keras-Adam updates.  The task is learnable by construction (the ad's
+item id determines the user's clicked item), so the in-batch softmax loss must fall well below ln(B)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from recommendflow_b200.config_parser import Configuration
+from recommendflow_b200.models.matching.recall_sdpa import RecallSdpa
+from recommendflow_b200.strings import StringColumn
+from recommendflow_b200.training import RecallSdpaTrainer
+
+pytestmark = pytest.mark.gpu
+
+
+def test_recall_sdpa_training_steps_reduce_the_loss(golden_dir):
+    torch.manual_seed(3)
+    rng = np.random.default_rng(3)
+    conf = Configuration(os.path.join(golden_dir, "configs", "synth_recall_sdpa.yaml"),
+                         slot_map_path=os.path.join(golden_dir, "configs", "synth_recall_sdpa.feature.map"))
+    keep = set(conf.features.user_feature_names[:3] + conf.features.ad_feature_names[:2])
+    for f in conf.features.features:
+        if f.is_hashing() and f.name not in keep:
+            f.working = False
+    B, S, dm = 256, 10, 32
+    model = RecallSdpa(conf, tower_units=(64, 32), behaviour_dim=dm, num_heads=2)
+    trainer = RecallSdpaTrainer(model, learning_rate=5e-3)
+    n_items = 400
+
+    def make_batch():
+        item = rng.integers(0, n_items, size=B)
+        batch = {}
+        for i, name in enumerate(model.user_cols):           # user features: noisy functions of the item
+            batch[name] = StringColumn.from_lists([[f"u{i}_{v}", f"u{i}_{v % 7}"] for v in item]).to("cuda")
+        for i, name in enumerate(model.ad_cols):
+            batch[name] = StringColumn.from_lists([[f"a{i}_{v}"] for v in item]).to("cuda")
+        x = torch.from_numpy(rng.standard_normal((B, S, dm)).astype(np.float32)).cuda()
+        mask = torch.from_numpy((np.arange(S)[None, :, None] < rng.integers(1, S + 1, size=(B, 1, 1))).astype(np.float32)).cuda()
+        return batch, torch.ones(B, device="cuda"), (x, mask)
+
+    losses = []
+    for step in range(60):
+        batch, y, behaviour = make_batch()
+        losses.append(float(trainer.train_step(batch, y, behaviour)))
+    assert np.isfinite(losses).all()
+    head, tail = np.mean(losses[:5]), np.mean(losses[-5:])
+    # duplicates of an item inside a batch are indistinguishable positives, so the floor is above zero
+    assert head > 4.0 and tail < head - 1.0, (head, tail)
+    assert trainer.iterations == 60 and len(trainer.bag_opts) == 2 * 5
+    opt = next(iter(trainer.bag_opts.values()))
+    assert opt.iterations == 60 and float(opt.v.abs().sum()) > 0
+    # inference mode is restored after every step
+    assert all(not m.batch_stats for m in trainer._modules(type(model.user_dense.layers[0])))
+    out = model(batch, y_true=y, behaviour=behaviour, training=False)
+    assert out["user"].shape == (B, 32)
