@@ -207,6 +207,26 @@ typedef struct rf_adam_params {
     int32_t lazy;
     int32_t reserved;
 } rf_adam_params;
+/* One table of a multi-table update.  All tables of a call share `dim`; sum of table_rows <= 2^32 - 1, */
+/* sum of n_keys <= 2^31 - 1.  grad_out: [batch, dim] view with row stride grad_stride (floats).         */
+typedef struct rf_adam_field {
+    const int64_t *ids;         /* [n_keys] row ids gathered from this table (rf_field_desc.ids_out slice) */
+    const int32_t *bag_offsets; /* [batch + 1] jagged bags, or NULL for batch x bag_len                    */
+    int64_t n_keys;
+    int32_t bag_len;
+    int32_t combiner;           /* RF_COMBINER_SUM | RF_COMBINER_AVG                                        */
+    const float *grad_out;
+    int64_t grad_stride;
+    float *table, *m, *v;       /* [table_rows, dim] fp32                                                   */
+    int64_t table_rows;
+    int32_t dim;
+    int32_t reserved;
+} rf_adam_field;
+/* ONE sort / select / update pass over all the tables (instead of one per table).                     */
+int64_t rf_bag_adam_multi_workspace_bytes(const rf_adam_field *fields, int n_fields);
+int rf_bag_backward_adam_multi(const rf_adam_field *fields, int n_fields, int64_t batch,
+                               const rf_adam_params *params, void *d_workspace, int64_t workspace_bytes,
+                               void *stream);
 int64_t rf_bag_adam_workspace_bytes(int64_t n_keys, int64_t table_rows);
 int rf_bag_backward_adam(const int64_t *d_ids, int64_t n_keys, const int32_t *d_bag_offsets, int32_t bag_len,
                          int64_t batch, const float *d_grad_out, int64_t grad_stride, int32_t dim, int combiner,

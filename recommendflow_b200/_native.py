@@ -39,6 +39,12 @@ class AdamParams(C.Structure):
                 ("step", C.c_int64), ("lazy", C.c_int32), ("reserved", C.c_int32)]
 
 
+class AdamField(C.Structure):
+    _fields_ = [("ids", C.c_void_p), ("bag_offsets", C.c_void_p), ("n_keys", C.c_int64), ("bag_len", C.c_int32),
+                ("combiner", C.c_int32), ("grad_out", C.c_void_p), ("grad_stride", C.c_int64), ("table", C.c_void_p),
+                ("m", C.c_void_p), ("v", C.c_void_p), ("table_rows", C.c_int64), ("dim", C.c_int32), ("reserved", C.c_int32)]
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -93,6 +99,11 @@ def lib():
         L.rf_bag_backward_adam.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
                                            C.c_int, C.POINTER(AdamParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                            C.c_void_p, C.c_int64, C.c_void_p]
+        L.rf_bag_adam_multi_workspace_bytes.restype = C.c_int64
+        L.rf_bag_adam_multi_workspace_bytes.argtypes = [C.POINTER(AdamField), C.c_int]
+        L.rf_bag_backward_adam_multi.restype = C.c_int
+        L.rf_bag_backward_adam_multi.argtypes = [C.POINTER(AdamField), C.c_int, C.c_int64, C.POINTER(AdamParams), C.c_void_p,
+                                                 C.c_int64, C.c_void_p]
         L.rf_sdpa_backward.restype = C.c_int
         L.rf_sdpa_backward.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 4
         L.rf_inbatch_softmax_ce_backward.restype = C.c_int

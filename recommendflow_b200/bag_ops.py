@@ -270,3 +270,64 @@ class BagAdam(object):
                 self.v.data_ptr(), self.table.shape[0], ws.data_ptr(), ws.numel(),
                 C.c_void_p(torch.cuda.current_stream(self.table.device).cuda_stream)))
         return self.table
+
+
+class BagAdamGroup(object):
+    """tf.keras.optimizers.Adam for a set of embedding tables that share `dim`, applied in ONE pass per step
+    (rf_bag_backward_adam_multi): one sort / select / update for all tables instead of one per table.
+
+    tables: list of contiguous fp32 [rows_i, dim] CUDA tensors.  Same semantics as `BagAdam` (Keras by default:
+    every row of every table decays and moves; `lazy=True`: gathered rows only)."""
+
+    def __init__(self, tables, learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7, lazy=False):
+        if not tables:
+            raise ValueError("BagAdamGroup needs at least one table")
+        dim = tables[0].shape[1]
+        for t in tables:
+            _require_cuda(t, "table")
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.dim() != 2 or t.shape[1] != dim:
+                raise ValueError("tables must be contiguous fp32 [rows, dim] tensors sharing dim")
+        self.tables = list(tables)
+        self.m = [torch.zeros_like(t) for t in tables]
+        self.v = [torch.zeros_like(t) for t in tables]
+        self.learning_rate, self.beta_1, self.beta_2, self.epsilon, self.lazy = learning_rate, beta_1, beta_2, epsilon, lazy
+        self.iterations = 0
+        self._ws = None
+
+    def apply(self, updates, batch):
+        """updates: one (ids, grad_out, combiner, bag_len, bag_offsets) per table, in table order; `None` for a
+        table that received no gradient this step (it still decays under Keras semantics).  batch: rows of grad_out."""
+        if len(updates) != len(self.tables):
+            raise ValueError("one update (or None) per table")
+        dev = self.tables[0].device
+        dim = self.tables[0].shape[1]
+        arr = (nat.AdamField * len(self.tables))()
+        keep = []
+        for i, (table, upd) in enumerate(zip(self.tables, updates)):
+            f = arr[i]
+            f.table, f.m, f.v = table.data_ptr(), self.m[i].data_ptr(), self.v[i].data_ptr()
+            f.table_rows, f.dim = table.shape[0], dim
+            f.combiner = nat.COMBINER["sum"]
+            if upd is None:
+                continue
+            ids, g, combiner, bag_len, bag_offsets = upd
+            ids = _require_cuda(ids, "ids").contiguous().view(-1)
+            g = _require_cuda(g, "grad_out")
+            if g.dtype != torch.float32 or g.dim() != 2 or g.stride(1) != 1 or g.shape[1] != dim or g.shape[0] != batch:
+                raise ValueError("grad_out must be fp32 [batch, dim] with contiguous columns")
+            keep += [ids, g]
+            f.ids, f.n_keys, f.grad_out, f.grad_stride = ids.data_ptr(), ids.numel(), g.data_ptr(), g.stride(0)
+            f.combiner, f.bag_len = nat.COMBINER[combiner], bag_len or 0
+            f.bag_offsets = None if bag_offsets is None else bag_offsets.data_ptr()
+        self.iterations += 1
+        p = nat.AdamParams(lr=self.learning_rate, beta1=self.beta_1, beta2=self.beta_2, epsilon=self.epsilon,
+                           step=self.iterations, lazy=1 if self.lazy else 0)
+        with torch.cuda.device(dev):
+            need = int(nat.lib().rf_bag_adam_multi_workspace_bytes(arr, len(self.tables)))
+            if need < 0:
+                nat.check(nat.RF_ERR_INVALID)
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            nat.check(nat.lib().rf_bag_backward_adam_multi(arr, len(self.tables), batch, C.byref(p), self._ws.data_ptr(),
+                                                           self._ws.numel(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        return self.tables

@@ -23,13 +23,19 @@
 //      kHeavyRun (the pad row 0 of dense-padded batches) go to a list and are reduced by a whole
 //      CTA each (slot-strided partial sums + ordered combine),
 //   4. dense pass over rows whose bit is clear.
+// Any number of tables that share `dim` go through ONE such pass (rf_bag_backward_adam_multi): rows and keys
+// are numbered globally across the tables, so the sort, the select and the four kernels are launched once
+// per step instead of once per table (456 tables in the C3 plan).
 // All arithmetic uses the round-to-nearest intrinsics (no FMA contraction) so a plain C restatement
 // reproduces it bit for bit wherever the summation order is the same.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
 
+#include <string.h>
+
 #include <atomic>
+#include <vector>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
@@ -67,33 +73,62 @@ __device__ __forceinline__ void adam_vec(float4 &w, float4 &m, float4 &v, const 
     adam_scalar(w.w, m.w, v.w, g.w, touched, c);
 }
 
-struct GradSrc {
-    const float *grad;
-    int64_t stride;
+// One table of a (possibly multi-table) update, as the device sees it.  Tables of one call share `dim`; their
+// rows are numbered globally (rbase + row) so that ONE sort / select / update pass covers all of them, and
+// their keys are numbered globally (kbase + k) so that a sorted position leads back to its bag.
+struct DevAdamField {
+    const int64_t *ids;
     const int32_t *boffs;
-    int64_t batch;
-    int bag_len;
-    int avg;
+    const float *grad;
+    int64_t grad_stride;
+    float *w, *m, *v;
+    int64_t rows;
+    uint32_t rbase;
+    int32_t kbase;
+    int32_t n_keys;
+    int32_t bag_len;
+    int32_t avg;
+    int32_t pad;
 };
 
-// gradient that key `pos` receives for column group c: grad[bag(pos)] (x 1 / count for avg)
-__device__ __forceinline__ float4 key_grad(const GradSrc &s, int pos, int c) {
+struct Job {
+    const DevAdamField *fields;
+    int n_fields;
+    int per;              // dim / 4
+    int64_t batch;
+    uint32_t *bitmap;     // over the global rows; NULL in lazy mode
+};
+
+// last field whose first global row (BY_ROW) / first global key position is <= x
+template <bool BY_ROW>
+__device__ __forceinline__ int field_of(const Job &j, uint32_t x) {
+    int lo = 0, hi = j.n_fields - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        const uint32_t first = BY_ROW ? j.fields[mid].rbase : (uint32_t)j.fields[mid].kbase;
+        if (first <= x) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// gradient that (field-local) key `k` receives for column group c: grad[bag(k)] (x 1 / count for avg)
+__device__ __forceinline__ float4 key_grad(const DevAdamField &f, int64_t batch, int k, int c) {
     int64_t b;
     float scale = 1.0f;
-    if (s.boffs) {
-        int64_t lo = 0, hi = s.batch;
+    if (f.boffs) {
+        int64_t lo = 0, hi = batch;
         while (lo + 1 < hi) {
             const int64_t mid = (lo + hi) >> 1;
-            if (s.boffs[mid] <= pos) lo = mid; else hi = mid;
+            if (f.boffs[mid] <= k) lo = mid; else hi = mid;
         }
         b = lo;
-        if (s.avg) scale = __fdiv_rn(1.0f, (float)(s.boffs[b + 1] - s.boffs[b]));
+        if (f.avg) scale = __fdiv_rn(1.0f, (float)(f.boffs[b + 1] - f.boffs[b]));
     } else {
-        b = pos / s.bag_len;
-        if (s.avg) scale = __fdiv_rn(1.0f, (float)s.bag_len);
+        b = k / f.bag_len;
+        if (f.avg) scale = __fdiv_rn(1.0f, (float)f.bag_len);
     }
-    float4 g = __ldg(reinterpret_cast<const float4 *>(s.grad + b * s.stride) + c);
-    if (s.avg) {
+    float4 g = __ldg(reinterpret_cast<const float4 *>(f.grad + b * f.grad_stride) + c);
+    if (f.avg) {
         g.x = __fmul_rn(g.x, scale);
         g.y = __fmul_rn(g.y, scale);
         g.z = __fmul_rn(g.z, scale);
@@ -109,12 +144,13 @@ __device__ __forceinline__ void add4(float4 &a, const float4 &b) {
     a.w = __fadd_rn(a.w, b.w);
 }
 
-__global__ void __launch_bounds__(kAdamThreads) adam_prep_kernel(const int64_t *__restrict__ ids, int n, uint32_t *__restrict__ keys,
-                                                                 int32_t *__restrict__ pos, int32_t *__restrict__ counters) {
+__global__ void __launch_bounds__(kAdamThreads) adam_prep_kernel(Job j, int n, uint32_t *__restrict__ keys, int32_t *__restrict__ pos,
+                                                                 int32_t *__restrict__ counters) {
     const int i = blockIdx.x * kAdamThreads + threadIdx.x;
     if (i == 0) counters[0] = counters[1] = 0;
     if (i < n) {
-        keys[i] = (uint32_t)ids[i];
+        const DevAdamField &f = j.fields[field_of<false>(j, (uint32_t)i)];
+        keys[i] = f.rbase + (uint32_t)f.ids[i - f.kbase];
         pos[i] = i;
     }
 }
@@ -124,28 +160,22 @@ struct HeadPred {
     __device__ __forceinline__ bool operator()(int i) const { return i == 0 || keys[i] != keys[i - 1]; }
 };
 
-struct Tables {
-    float *w, *m, *v;
-    uint32_t *bitmap;   // NULL in lazy mode
-    int per;            // dim / 4
-};
-
-__device__ __forceinline__ void apply_row(const Tables &t, uint32_t row, int c, const float4 &g, const AdamC &k) {
-    const int64_t at = (int64_t)row * t.per + c;
-    float4 w = reinterpret_cast<float4 *>(t.w)[at], m = reinterpret_cast<float4 *>(t.m)[at], v = reinterpret_cast<float4 *>(t.v)[at];
+__device__ __forceinline__ void apply_row(const Job &j, const DevAdamField &f, uint32_t grow, int c, const float4 &g, const AdamC &k) {
+    const int64_t at = (int64_t)(grow - f.rbase) * j.per + c;
+    float4 w = reinterpret_cast<float4 *>(f.w)[at], m = reinterpret_cast<float4 *>(f.m)[at], v = reinterpret_cast<float4 *>(f.v)[at];
     adam_vec(w, m, v, g, true, k);
-    reinterpret_cast<float4 *>(t.w)[at] = w;
-    reinterpret_cast<float4 *>(t.m)[at] = m;
-    reinterpret_cast<float4 *>(t.v)[at] = v;
-    if (c == 0 && t.bitmap) atomicOr(t.bitmap + (row >> 5), 1u << (row & 31));
+    reinterpret_cast<float4 *>(f.w)[at] = w;
+    reinterpret_cast<float4 *>(f.m)[at] = m;
+    reinterpret_cast<float4 *>(f.v)[at] = v;
+    if (c == 0 && j.bitmap) atomicOr(j.bitmap + (grow >> 5), 1u << (grow & 31));
 }
 
 // one lane group per unique row; *n_unique is read from device memory (written by the select)
 __global__ void __launch_bounds__(kAdamThreads)
 adam_rows_kernel(const uint32_t *__restrict__ keys, const int32_t *__restrict__ pos, const int32_t *__restrict__ heads,
-                 int32_t *__restrict__ counters, int n_keys, int2 *__restrict__ heavy, GradSrc src, Tables t, AdamC k) {
-    const int groups = kAdamThreads / t.per;
-    const int grp = threadIdx.x / t.per, c = threadIdx.x - grp * t.per;
+                 int32_t *__restrict__ counters, int n_keys, int2 *__restrict__ heavy, Job j, AdamC k) {
+    const int groups = kAdamThreads / j.per;
+    const int grp = threadIdx.x / j.per, c = threadIdx.x - grp * j.per;
     if (grp >= groups) return;
     const int n_unique = counters[0];
     for (int u = blockIdx.x * groups + grp; u < n_unique; u += gridDim.x * groups) {
@@ -154,54 +184,60 @@ adam_rows_kernel(const uint32_t *__restrict__ keys, const int32_t *__restrict__ 
             if (c == 0) heavy[atomicAdd(counters + 1, 1)] = make_int2(begin, end);
             continue;
         }
-        float4 g = key_grad(src, pos[begin], c);
-        for (int i = begin + 1; i < end; ++i) add4(g, key_grad(src, pos[i], c));
-        apply_row(t, keys[begin], c, g, k);
+        const uint32_t grow = keys[begin];
+        const DevAdamField &f = j.fields[field_of<true>(j, grow)];
+        float4 g = key_grad(f, j.batch, pos[begin] - f.kbase, c);
+        for (int i = begin + 1; i < end; ++i) add4(g, key_grad(f, j.batch, pos[i] - f.kbase, c));
+        apply_row(j, f, grow, c, g, k);
     }
 }
 
 // one CTA per long run: slot s sums keys begin + s, begin + s + slots, ...; slots are combined in order
 __global__ void __launch_bounds__(kAdamThreads)
 adam_heavy_kernel(const uint32_t *__restrict__ keys, const int32_t *__restrict__ pos, const int32_t *__restrict__ counters,
-                  const int2 *__restrict__ heavy, GradSrc src, Tables t, AdamC k) {
+                  const int2 *__restrict__ heavy, Job j, AdamC k) {
     __shared__ float4 part[kAdamThreads];
-    const int slots = kAdamThreads / t.per;
-    const int s = threadIdx.x / t.per, c = threadIdx.x - s * t.per;
+    const int slots = kAdamThreads / j.per;
+    const int s = threadIdx.x / j.per, c = threadIdx.x - s * j.per;
     const int n_heavy = counters[1];
     for (int h = blockIdx.x; h < n_heavy; h += gridDim.x) {
         const int2 run = heavy[h];
+        const uint32_t grow = keys[run.x];
+        const DevAdamField &f = j.fields[field_of<true>(j, grow)];
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         if (s < slots)
-            for (int i = run.x + s; i < run.y; i += slots) add4(g, key_grad(src, pos[i], c));
+            for (int i = run.x + s; i < run.y; i += slots) add4(g, key_grad(f, j.batch, pos[i] - f.kbase, c));
         part[threadIdx.x] = g;
         __syncthreads();
         if (s == 0) {
-            for (int j = 1; j < slots; ++j) add4(g, part[j * t.per + c]);
-            apply_row(t, keys[run.x], c, g, k);
+            for (int q = 1; q < slots; ++q) add4(g, part[q * j.per + c]);
+            apply_row(j, f, grow, c, g, k);
         }
         __syncthreads();
     }
 }
 
-// every row whose bit is clear: decay the moments and move the row (Keras' non-lazy sparse Adam)
-__global__ void __launch_bounds__(kAdamThreads)
-adam_dense_kernel(Tables t, int64_t rows, AdamC k) {
-    const int64_t total = rows * t.per;
+// every row whose bit is clear: decay the moments and move the row (Keras' non-lazy sparse Adam);
+// blockIdx.y = table
+__global__ void __launch_bounds__(kAdamThreads) adam_dense_kernel(Job j, AdamC k) {
+    const DevAdamField &f = j.fields[blockIdx.y];
+    const int64_t total = f.rows * j.per;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int64_t e = (int64_t)blockIdx.x * kAdamThreads + threadIdx.x; e < total; e += (int64_t)gridDim.x * kAdamThreads) {
-        const int64_t row = e / t.per;
-        if ((__ldg(t.bitmap + (row >> 5)) >> (row & 31)) & 1u) continue;
-        float4 w = reinterpret_cast<float4 *>(t.w)[e], m = reinterpret_cast<float4 *>(t.m)[e], v = reinterpret_cast<float4 *>(t.v)[e];
+        const uint32_t grow = f.rbase + (uint32_t)(e / j.per);
+        if ((__ldg(j.bitmap + (grow >> 5)) >> (grow & 31)) & 1u) continue;
+        float4 w = reinterpret_cast<float4 *>(f.w)[e], m = reinterpret_cast<float4 *>(f.m)[e], v = reinterpret_cast<float4 *>(f.v)[e];
         adam_vec(w, m, v, zero, false, k);
-        reinterpret_cast<float4 *>(t.w)[e] = w;
-        reinterpret_cast<float4 *>(t.m)[e] = m;
-        reinterpret_cast<float4 *>(t.v)[e] = v;
+        reinterpret_cast<float4 *>(f.w)[e] = w;
+        reinterpret_cast<float4 *>(f.m)[e] = m;
+        reinterpret_cast<float4 *>(f.v)[e] = v;
     }
 }
 
 inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct Workspace {
+    DevAdamField *fields;
     uint32_t *keys_in, *keys_out;
     int32_t *pos_in, *pos_out, *heads, *counters;
     int2 *heavy;
@@ -216,7 +252,7 @@ int key_bits(int64_t rows) {
     return bits;
 }
 
-int carve(Workspace &ws, char *base, int64_t n_keys, int64_t rows) {
+int carve(Workspace &ws, char *base, int n_fields, int64_t n_keys, int64_t rows) {
     const int n = (int)n_keys;
     size_t sort_bytes = 0, select_bytes = 0;
     cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
@@ -231,6 +267,7 @@ int carve(Workspace &ws, char *base, int64_t n_keys, int64_t rows) {
         off += up256(bytes);
         return p;
     };
+    ws.fields = reinterpret_cast<DevAdamField *>(take(sizeof(DevAdamField) * (size_t)n_fields));
     ws.keys_in = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * n));
     ws.keys_out = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * n));
     ws.pos_in = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * n));
@@ -246,6 +283,23 @@ int carve(Workspace &ws, char *base, int64_t n_keys, int64_t rows) {
     return RF_OK;
 }
 
+// totals over the fields + argument checks shared by the size query and the launch
+int totals(const rf_adam_field *fields, int n_fields, int64_t &n_keys, int64_t &rows) {
+    if (n_fields <= 0 || !fields) return set_error(RF_ERR_INVALID, "rf_bag_backward_adam: no tables");
+    if (n_fields > 65535) return set_error(RF_ERR_INVALID, "rf_bag_backward_adam: at most 65535 tables per call");
+    n_keys = rows = 0;
+    for (int i = 0; i < n_fields; ++i) {
+        const rf_adam_field &f = fields[i];
+        if (f.n_keys < 0 || f.table_rows <= 0) return set_error(RF_ERR_INVALID, "table %d: bad n_keys / table_rows", i);
+        if (f.dim != fields[0].dim) return set_error(RF_ERR_INVALID, "table %d: all tables of one call share dim (%d != %d)", i, f.dim, fields[0].dim);
+        n_keys += f.n_keys;
+        rows += f.table_rows;
+    }
+    if (n_keys > INT32_MAX) return set_error(RF_ERR_INVALID, "rf_bag_backward_adam: %lld keys exceed 2^31 - 1", (long long)n_keys);
+    if (rows > (int64_t)UINT32_MAX) return set_error(RF_ERR_INVALID, "rf_bag_backward_adam: %lld rows in total exceed 2^32 - 1", (long long)rows);
+    return RF_OK;
+}
+
 }  // namespace
 }  // namespace rf
 
@@ -253,39 +307,61 @@ using namespace rf;
 
 extern "C" {
 
-int64_t rf_bag_adam_workspace_bytes(int64_t n_keys, int64_t table_rows) {
-    if (n_keys < 0 || n_keys > INT32_MAX || table_rows <= 0 || table_rows > (int64_t)UINT32_MAX) {
-        set_error(RF_ERR_INVALID, "rf_bag_adam_workspace_bytes: n_keys / table_rows out of range");
-        return -1;
-    }
+int64_t rf_bag_adam_multi_workspace_bytes(const rf_adam_field *fields, int n_fields) {
+    int64_t n_keys = 0, rows = 0;
+    if (totals(fields, n_fields, n_keys, rows) != RF_OK) return -1;
     Workspace ws;
-    if (carve(ws, nullptr, n_keys, table_rows) != RF_OK) return -1;
+    if (carve(ws, nullptr, n_fields, n_keys, rows) != RF_OK) return -1;
     return (int64_t)ws.total;
 }
 
-int rf_bag_backward_adam(const int64_t *d_ids, int64_t n_keys, const int32_t *d_bag_offsets, int32_t bag_len, int64_t batch,
-                         const float *d_grad_out, int64_t grad_stride, int32_t dim, int combiner, const rf_adam_params *params,
-                         float *d_table, float *d_m, float *d_v, int64_t table_rows, void *d_workspace, int64_t workspace_bytes,
-                         void *stream) {
+int rf_bag_backward_adam_multi(const rf_adam_field *fields, int n_fields, int64_t batch, const rf_adam_params *params,
+                               void *d_workspace, int64_t workspace_bytes, void *stream) {
     if (!params) return set_error(RF_ERR_INVALID, "rf_bag_backward_adam: params is NULL");
-    if (n_keys < 0 || n_keys > INT32_MAX || batch < 0 || dim <= 0 || table_rows <= 0 || table_rows > (int64_t)UINT32_MAX)
-        return set_error(RF_ERR_INVALID, "bad backward shape");
-    if (combiner != RF_COMBINER_SUM && combiner != RF_COMBINER_AVG)
-        return set_error(RF_ERR_UNSUPPORTED, "backward is implemented for the sum and avg combiners");
+    int64_t n_keys = 0, rows = 0;
+    int rc = totals(fields, n_fields, n_keys, rows);
+    if (rc != RF_OK) return rc;
+    const int dim = fields[0].dim;
+    if (batch < 0 || dim <= 0) return set_error(RF_ERR_INVALID, "bad backward shape");
     if (params->step < 1) return set_error(RF_ERR_INVALID, "Adam step must be >= 1, got %lld", (long long)params->step);
-    if (dim % 4 != 0 || dim > 4 * kAdamThreads || grad_stride % 4 != 0)
-        return set_error(RF_ERR_UNSUPPORTED, "rf_bag_backward_adam needs dim %% 4 == 0, dim <= %d and grad_stride %% 4 == 0", 4 * kAdamThreads);
-    if (!d_table || !d_m || !d_v) return set_error(RF_ERR_INVALID, "rf_bag_backward_adam: NULL table / moment buffer");
-    if (n_keys > 0 && (!d_ids || !d_grad_out)) return set_error(RF_ERR_INVALID, "rf_bag_backward_adam: NULL ids / grad_out");
-    if (n_keys > 0 && !d_bag_offsets && (bag_len <= 0 || batch * (int64_t)bag_len != n_keys))
-        return set_error(RF_ERR_INVALID, "dense backward: batch x bag_len != n_keys");
-    for (const void *p : {(const void *)d_table, (const void *)d_m, (const void *)d_v, (const void *)d_grad_out})
-        if (reinterpret_cast<uintptr_t>(p) % 16 != 0) return set_error(RF_ERR_INVALID, "rf_bag_backward_adam: buffers must be 16-byte aligned");
+    if (dim % 4 != 0 || dim > 4 * kAdamThreads)
+        return set_error(RF_ERR_UNSUPPORTED, "rf_bag_backward_adam needs dim %% 4 == 0 and dim <= %d", 4 * kAdamThreads);
+    std::vector<DevAdamField> dev(n_fields);
+    int64_t kbase = 0, rbase = 0;
+    for (int i = 0; i < n_fields; ++i) {
+        const rf_adam_field &f = fields[i];
+        if (f.combiner != RF_COMBINER_SUM && f.combiner != RF_COMBINER_AVG)
+            return set_error(RF_ERR_UNSUPPORTED, "table %d: backward is implemented for the sum and avg combiners", i);
+        if (!f.table || !f.m || !f.v) return set_error(RF_ERR_INVALID, "table %d: NULL table / moment buffer", i);
+        if (f.n_keys > 0 && (!f.ids || !f.grad_out)) return set_error(RF_ERR_INVALID, "table %d: NULL ids / grad_out", i);
+        if (f.n_keys > 0 && !f.bag_offsets && (f.bag_len <= 0 || batch * (int64_t)f.bag_len != f.n_keys))
+            return set_error(RF_ERR_INVALID, "table %d: dense backward needs batch x bag_len == n_keys", i);
+        if (f.grad_stride % 4 != 0) return set_error(RF_ERR_UNSUPPORTED, "table %d: grad_stride %% 4 != 0", i);
+        for (const void *p : {(const void *)f.table, (const void *)f.m, (const void *)f.v, (const void *)f.grad_out})
+            if (reinterpret_cast<uintptr_t>(p) % 16 != 0) return set_error(RF_ERR_INVALID, "table %d: buffers must be 16-byte aligned", i);
+        DevAdamField &d = dev[i];
+        d.ids = f.ids;
+        d.boffs = f.bag_offsets;
+        d.grad = f.grad_out;
+        d.grad_stride = f.grad_stride;
+        d.w = f.table;
+        d.m = f.m;
+        d.v = f.v;
+        d.rows = f.table_rows;
+        d.rbase = (uint32_t)rbase;
+        d.kbase = (int32_t)kbase;
+        d.n_keys = (int32_t)f.n_keys;
+        d.bag_len = f.bag_len;
+        d.avg = f.combiner == RF_COMBINER_AVG;
+        d.pad = 0;
+        kbase += f.n_keys;
+        rbase += f.table_rows;
+    }
     Workspace ws;
-    int rc = carve(ws, static_cast<char *>(d_workspace), n_keys, table_rows);
+    rc = carve(ws, static_cast<char *>(d_workspace), n_fields, n_keys, rows);
     if (rc != RF_OK) return rc;
     if (!d_workspace || workspace_bytes < (int64_t)ws.total)
-        return set_error(RF_ERR_INVALID, "workspace too small: %lld < %lld bytes (rf_bag_adam_workspace_bytes)",
+        return set_error(RF_ERR_INVALID, "workspace too small: %lld < %lld bytes (rf_bag_adam[_multi]_workspace_bytes)",
                          (long long)workspace_bytes, (long long)ws.total);
 
     // Keras: lr_t = lr * sqrt(1 - beta_2^t) / (1 - beta_1^t), all in fp32
@@ -298,45 +374,79 @@ int rf_bag_backward_adam(const int64_t *d_ids, int64_t n_keys, const int32_t *d_
     const float b1p = powf(params->beta1, (float)params->step), b2p = powf(params->beta2, (float)params->step);
     k.lr_t = params->lr * sqrtf(1.0f - b2p) / (1.0f - b1p);
 
-    int dev = 0, sms = 0;
-    RF_CUDA(cudaGetDevice(&dev));
-    RF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int devid = 0, sms = 0;
+    RF_CUDA(cudaGetDevice(&devid));
+    RF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devid));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool lazy = params->lazy != 0;
-    Tables t{d_table, d_m, d_v, lazy ? nullptr : ws.bitmap, dim / 4};
+    // the descriptors travel through a pageable staging copy: the driver snapshots `dev` before returning
+    RF_CUDA(cudaMemcpyAsync(ws.fields, dev.data(), sizeof(DevAdamField) * (size_t)n_fields, cudaMemcpyHostToDevice, st));
+    Job job{ws.fields, n_fields, dim / 4, batch, lazy ? nullptr : ws.bitmap};
     if (!lazy) RF_CUDA(cudaMemsetAsync(ws.bitmap, 0, ws.bitmap_bytes, st));
     int launches = 0;
     if (n_keys > 0) {
         const int n = (int)n_keys;
-        adam_prep_kernel<<<(n + kAdamThreads - 1) / kAdamThreads, kAdamThreads, 0, st>>>(d_ids, n, ws.keys_in, ws.pos_in, ws.counters);
+        adam_prep_kernel<<<(n + kAdamThreads - 1) / kAdamThreads, kAdamThreads, 0, st>>>(job, n, ws.keys_in, ws.pos_in, ws.counters);
         RF_CUDA(cudaGetLastError());
         size_t tmp = ws.cub_bytes;
-        RF_CUDA(cub::DeviceRadixSort::SortPairs(ws.cub_temp, tmp, ws.keys_in, ws.keys_out, ws.pos_in, ws.pos_out, n, 0,
-                                                key_bits(table_rows), st));
+        RF_CUDA(cub::DeviceRadixSort::SortPairs(ws.cub_temp, tmp, ws.keys_in, ws.keys_out, ws.pos_in, ws.pos_out, n, 0, key_bits(rows), st));
         thrust::counting_iterator<int> iota(0);
         tmp = ws.cub_bytes;
         RF_CUDA(cub::DeviceSelect::If(ws.cub_temp, tmp, iota, ws.heads, ws.counters, n, HeadPred{ws.keys_out}, st));
-        GradSrc src{d_grad_out, grad_stride, d_bag_offsets, batch, bag_len, combiner == RF_COMBINER_AVG};
-        const int groups = kAdamThreads / t.per;
+        const int groups = kAdamThreads / job.per;
         int64_t blocks = ((int64_t)n + groups - 1) / groups;
         if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
-        adam_rows_kernel<<<(unsigned)blocks, kAdamThreads, 0, st>>>(ws.keys_out, ws.pos_out, ws.heads, ws.counters, n, ws.heavy, src, t, k);
+        adam_rows_kernel<<<(unsigned)blocks, kAdamThreads, 0, st>>>(ws.keys_out, ws.pos_out, ws.heads, ws.counters, n, ws.heavy, job, k);
         RF_CUDA(cudaGetLastError());
         int64_t hblocks = (int64_t)n / kHeavyRun + 1;
         if (hblocks > (int64_t)sms * 4) hblocks = (int64_t)sms * 4;
-        adam_heavy_kernel<<<(unsigned)hblocks, kAdamThreads, 0, st>>>(ws.keys_out, ws.pos_out, ws.counters, ws.heavy, src, t, k);
+        adam_heavy_kernel<<<(unsigned)hblocks, kAdamThreads, 0, st>>>(ws.keys_out, ws.pos_out, ws.counters, ws.heavy, job, k);
         RF_CUDA(cudaGetLastError());
         launches += 3;
     }
     if (!lazy) {
-        int64_t blocks = (table_rows * t.per + kAdamThreads - 1) / kAdamThreads;
-        if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
-        adam_dense_kernel<<<(unsigned)blocks, kAdamThreads, 0, st>>>(t, table_rows, k);
+        int64_t max_rows = 0;
+        for (int i = 0; i < n_fields; ++i) max_rows = fields[i].table_rows > max_rows ? fields[i].table_rows : max_rows;
+        int64_t blocks = (max_rows * job.per + kAdamThreads - 1) / kAdamThreads;
+        const int64_t cap = ((int64_t)sms * 16 + n_fields - 1) / n_fields;
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        adam_dense_kernel<<<dim3((unsigned)blocks, (unsigned)n_fields), kAdamThreads, 0, st>>>(job, k);
         RF_CUDA(cudaGetLastError());
         ++launches;
     }
     g_launches.fetch_add(launches);
     return RF_OK;
+}
+
+int64_t rf_bag_adam_workspace_bytes(int64_t n_keys, int64_t table_rows) {
+    rf_adam_field f;
+    memset(&f, 0, sizeof f);
+    f.n_keys = n_keys;
+    f.table_rows = table_rows;
+    f.dim = 4;
+    return rf_bag_adam_multi_workspace_bytes(&f, 1);
+}
+
+int rf_bag_backward_adam(const int64_t *d_ids, int64_t n_keys, const int32_t *d_bag_offsets, int32_t bag_len, int64_t batch,
+                         const float *d_grad_out, int64_t grad_stride, int32_t dim, int combiner, const rf_adam_params *params,
+                         float *d_table, float *d_m, float *d_v, int64_t table_rows, void *d_workspace, int64_t workspace_bytes,
+                         void *stream) {
+    rf_adam_field f;
+    memset(&f, 0, sizeof f);
+    f.ids = d_ids;
+    f.bag_offsets = d_bag_offsets;
+    f.n_keys = n_keys;
+    f.bag_len = bag_len;
+    f.combiner = combiner;
+    f.grad_out = d_grad_out;
+    f.grad_stride = grad_stride;
+    f.table = d_table;
+    f.m = d_m;
+    f.v = d_v;
+    f.table_rows = table_rows;
+    f.dim = dim;
+    return rf_bag_backward_adam_multi(&f, 1, batch, params, d_workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -17,7 +17,7 @@ import torch
 
 from .backend.blocks.mlp import BatchNormalization, Dropout
 from .backend.layers.preprocess_layers import DoubleHashingEmbedding
-from .bag_ops import BagAdam
+from .bag_ops import BagAdamGroup
 
 
 class RecallSdpaTrainer(object):
@@ -55,11 +55,20 @@ class RecallSdpaTrainer(object):
                 seen.add(id(bn))
         return params
 
-    def _bag_adam(self, table):
-        key = table.data_ptr()
-        if key not in self.bag_opts:
-            self.bag_opts[key] = BagAdam(table, learning_rate=self.learning_rate, lazy=self.lazy)
-        return self.bag_opts[key]
+    def _bag_groups(self, layout):
+        """One BagAdamGroup per embedding width: every table of that width is updated in ONE pass per step."""
+        if not self.bag_opts:
+            by_dim = {}
+            for name, (col, width) in layout.items():
+                layer = self.model.preprocessor[name]
+                bags = (layer.emb1, layer.emb2) if isinstance(layer, DoubleHashingEmbedding) else (layer.embedding,)
+                for t, bag in enumerate(bags):
+                    by_dim.setdefault(bag.output_dim, []).append((name, t, bag))
+            for dim, members in by_dim.items():
+                group = BagAdamGroup([bag.embeddings.data for _, _, bag in members], learning_rate=self.learning_rate,
+                                     lazy=self.lazy)
+                self.bag_opts[dim] = (group, members)
+        return self.bag_opts
 
     def _forward(self, batch, y_true, behaviour, ids):
         names = self.model.user_cols + self.model.ad_cols
@@ -90,18 +99,16 @@ class RecallSdpaTrainer(object):
             self._set_training(False)
         self.dense_opt.step()
         grad = leaf.grad
-        for name, (col, width) in layout.items():
-            layer = self.model.preprocessor[name]
-            rows, bag_len = ids[name]
-            if isinstance(layer, DoubleHashingEmbedding):
-                bags, combiner = (layer.emb1, layer.emb2), layer.combiner
-            else:
-                bags, combiner = (layer.embedding,), layer.pooling
-            if combiner not in ("sum", "avg"):
-                raise NotImplementedError(f"feature {name}: backward is implemented for sum / avg pooling, not {combiner}")
-            D = width // len(bags)
-            for t, bag in enumerate(bags):
-                self._bag_adam(bag.embeddings.data).apply(rows[t], grad[:, col + t * D:col + (t + 1) * D], combiner,
-                                                          bag_len=bag_len)
+        for dim, (group, members) in self._bag_groups(layout).items():
+            updates = []
+            for name, t, bag in members:
+                layer = self.model.preprocessor[name]
+                combiner = layer.combiner if isinstance(layer, DoubleHashingEmbedding) else layer.pooling
+                if combiner not in ("sum", "avg"):
+                    raise NotImplementedError(f"feature {name}: backward is implemented for sum / avg pooling, not {combiner}")
+                rows, bag_len = ids[name]
+                col = layout[name][0] + t * dim
+                updates.append((rows[t], grad[:, col:col + dim], combiner, bag_len, None))
+            group.apply(updates, grad.shape[0])
         self.iterations += 1
         return loss.detach()

@@ -387,3 +387,53 @@ def test_backward_adam_matches_keras_semantics(combiner, jagged, lazy):
             assert np.array_equal(got[exact].view(np.uint32), want[exact].view(np.uint32)), (name, step)
             np.testing.assert_allclose(got[~exact], want[~exact], rtol=2e-4, atol=1e-6, err_msg=f"{name} step {step}")
             want[~exact] = got[~exact]                                             # carry the device's rounding forward
+
+
+@pytest.mark.parametrize("lazy", [False, True])
+def test_backward_adam_multi_table_single_pass(lazy):
+    # several tables of one width updated in ONE pass (global row / key numbering): each must come out exactly
+    # as the single-table oracle says, including a table that received no gradient this step (Keras: it still
+    # decays; lazy: untouched)
+    from recommendflow_b200.bag_ops import BagAdamGroup
+    rng = np.random.default_rng(41)
+    D, B = 16, 300
+    sizes = [1009, 17, 5003, 64]
+    host = [tables(rng, 1, n, D)[0] for n in sizes]
+    ms, vs = [np.zeros_like(w) for w in host], [np.zeros_like(w) for w in host]
+    devs = [torch.from_numpy(w.copy()).cuda() for w in host]
+    group = BagAdamGroup(devs, learning_rate=3e-3, lazy=lazy)
+    before = nat.launch_count()
+    for step in (1, 2, 3):
+        g_all = rng.normal(size=(B, 4 * D)).astype(np.float32)              # one fused gradient buffer, 4 column slices
+        dev_g = torch.from_numpy(g_all).cuda()
+        updates, exact = [], []
+        for i, n in enumerate(sizes):
+            if i == 3 and step != 2:                                          # table 3 is only touched at step 2
+                updates.append(None)
+                oracle.bag_backward_adam(np.zeros(0, dtype=np.int64), np.zeros((B, D), dtype=np.float32), host[i], ms[i], vs[i],
+                                         step, lr=3e-3, L=1, lazy=lazy)
+                exact.append(np.ones(n, dtype=bool))
+                continue
+            if i % 2 == 0:                                                    # dense bags
+                L, bag = 3, None
+                ids = rng.integers(0, n, size=B * L)
+            else:                                                             # jagged bags
+                lens = rng.integers(0, 6, size=B)
+                bag = np.zeros(B + 1, dtype=np.int32)
+                bag[1:] = np.cumsum(lens)
+                L, ids = None, rng.integers(0, n, size=int(bag[-1]))
+            comb = "avg" if i == 1 else "sum"
+            g = np.ascontiguousarray(g_all[:, i * D:(i + 1) * D])
+            oracle.bag_backward_adam(ids, g, host[i], ms[i], vs[i], step, lr=3e-3, combiner=comb, L=L, bag_offsets=bag, lazy=lazy)
+            updates.append((torch.from_numpy(ids).cuda(), dev_g[:, i * D:(i + 1) * D], comb, L,
+                            None if bag is None else torch.from_numpy(bag).cuda()))
+            exact.append(np.bincount(ids, minlength=n) <= 128)
+        group.apply(updates, B)
+        for i in range(len(sizes)):
+            for name, got, want in (("w", devs[i], host[i]), ("m", group.m[i], ms[i]), ("v", group.v[i], vs[i])):
+                got = got.cpu().numpy()
+                ok = exact[i]
+                assert np.array_equal(got[ok].view(np.uint32), want[ok].view(np.uint32)), (name, i, step)
+                np.testing.assert_allclose(got[~ok], want[~ok], rtol=2e-4, atol=1e-6, err_msg=f"{name} table {i} step {step}")
+                want[~ok] = got[~ok]
+    assert nat.launch_count() - before == 3 * (3 if lazy else 4)              # per step: prep, rows, heavy (+ dense)

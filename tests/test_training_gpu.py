@@ -48,9 +48,9 @@ def test_recall_sdpa_training_steps_reduce_the_loss(golden_dir):
     head, tail = np.mean(losses[:5]), np.mean(losses[-5:])
     # duplicates of an item inside a batch are indistinguishable positives, so the floor is above zero
     assert head > 4.0 and tail < head - 1.0, (head, tail)
-    assert trainer.iterations == 60 and len(trainer.bag_opts) == 2 * 5
-    opt = next(iter(trainer.bag_opts.values()))
-    assert opt.iterations == 60 and float(opt.v.abs().sum()) > 0
+    assert trainer.iterations == 60 and len(trainer.bag_opts) == 1          # one group: all ten tables are 8 wide
+    group, members = next(iter(trainer.bag_opts.values()))
+    assert len(members) == 2 * 5 and group.iterations == 60 and all(float(v.abs().sum()) > 0 for v in group.v)
     # inference mode is restored after every step
     assert all(not m.batch_stats for m in trainer._modules(type(model.user_dense.layers[0])))
     out = model(batch, y_true=y, behaviour=behaviour, training=False)

@@ -1,0 +1,75 @@
+#!/usr/bin/env python
+"""Device timing of the backward kernels and of one full training step of the recall-SDPA model at the C3
+shape (batch 8192, 228 hashed features x 2 tables of 100000 x 8, [B, 50, 64] behaviour sequence, towers
+[1024, 512, 256]) on one B200.  Prints one JSON line.  STEPS / LAZY env vars."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def timed(fn, steps, warmup=3):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def main():
+    import torch
+    from recommendflow_b200 import _native as nat
+    from recommendflow_b200.config_parser import Configuration
+    from recommendflow_b200.dense_ops import inbatch_rowstats, inbatch_softmax_ce_backward, sdpa_backward
+    from recommendflow_b200.models.matching.recall_sdpa import RecallSdpa
+    from recommendflow_b200.strings import StringColumn
+    from recommendflow_b200.synth import c2_field_keys
+    from recommendflow_b200.training import RecallSdpaTrainer
+
+    B, S, dm, steps = 8192, 50, 64, int(os.environ.get("STEPS", "10"))
+    out = {"batch": B, "steps": steps}
+    # kernels alone
+    q = torch.nn.functional.normalize(torch.randn(B, 256, device="cuda"), dim=1)
+    d = torch.nn.functional.normalize(torch.randn(B, 256, device="cuda"), dim=1)
+    y = torch.ones(B, device="cuda")
+    lse = inbatch_rowstats(q, d, y_true=y, want=("lse",))["lse"]
+    out["ce_backward_ms"] = timed(lambda: inbatch_softmax_ce_backward(q, d, y, lse), steps)
+    out["ce_backward_tflops"] = 4 * 2 * B * B * 256 / (out["ce_backward_ms"] / 1e3) / 1e12      # S twice + two products
+    x = torch.randn(B, S, dm, device="cuda")
+    g = torch.randn(B, S, dm, device="cuda")
+    mask = (torch.arange(S, device="cuda")[None, :, None] < torch.randint(1, S + 1, (B, 1, 1), device="cuda")).float()
+    out["sdpa_backward_ms"] = timed(lambda: sdpa_backward(x, x, x, mask, g), steps)
+    # the whole step
+    cfg = os.path.join(ROOT, "tests", "golden", "configs", "synth_recall_sdpa")
+    conf = Configuration(cfg + ".yaml", slot_map_path=cfg + ".feature.map")
+    model = RecallSdpa(conf, behaviour_dim=dm, num_heads=1)
+    trainer = RecallSdpaTrainer(model, learning_rate=1e-4, lazy_embedding_adam=os.environ.get("LAZY", "0") == "1")
+    names = model.user_cols + model.ad_cols
+    batch = {}
+    for i, n in enumerate(names):
+        arena, offs = c2_field_keys(i, B, 1)
+        batch[n] = StringColumn.from_arena(arena, offs, (B, 1)).to("cuda")
+    l0 = None
+
+    def step():
+        return trainer.train_step(batch, y, (x, mask))
+    step()
+    l0 = nat.launch_count()
+    out["train_step_ms"] = timed(step, steps, warmup=2)
+    out["train_samples_per_s"] = B / (out["train_step_ms"] / 1e3)
+    out["launches_per_step"] = (nat.launch_count() - l0) / (steps + 2)
+    out["embedding_adam"] = "lazy" if trainer.lazy else "keras (all rows decay)"
+    out["loss_after"] = float(step())
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
