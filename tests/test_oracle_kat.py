@@ -151,3 +151,39 @@ def test_sdpa_and_inbatch_loss_against_numpy():
     want = np.mean(-np.log(np.exp(np.diag(s)) / np.exp(s).sum(-1)) * y)
     loss, lse, diag = oracle.inbatch_softmax_ce(y, qq, dd, 20.0)
     assert abs(loss - want) < 1e-9
+
+
+# ---- "next" rows: vocabulary lookup, discretization, Keras Adam -- pinned by the examples in the Keras docs ----
+def test_lookup_and_discretization_keras_doc_examples():
+    # tf.keras.layers.StringLookup docstring: vocab [a, b, c, d], data [[a, c, d], [d, z, b]] -> [[1, 3, 4], [4, 0, 2]]
+    assert oracle.vocab_lookup(["a", "c", "d", "d", "z", "b"], ["a", "b", "c", "d"]).tolist() == [1, 3, 4, 4, 0, 2]
+    # tf.keras.layers.IntegerLookup docstring: vocab [12, 36, 1138, 42], data [[12, 1138, 42], [42, 1000, 36]]
+    assert oracle.vocab_lookup([12, 1138, 42, 42, 1000, 36], [12, 36, 1138, 42]).tolist() == [1, 3, 4, 4, 0, 2]
+    # tf.keras.layers.Discretization docstring: bin_boundaries [0., 1., 2.]
+    got = oracle.bucketize([-1.5, 1.0, 3.4, .5, 0.0, 3.0, 1.3, 0.0], [0., 1., 2.])
+    assert got.tolist() == [0, 2, 3, 1, 1, 3, 2, 1]
+    assert oracle.bucketize([np.nan, np.inf, -np.inf], [0., 1.]).tolist() == [2, 2, 0]
+
+
+def test_adam_keras_doc_example_and_sparse_semantics():
+    # tf.keras.optimizers.Adam docstring: lr 0.1, var 10.0, loss var^2 / 2 (grad = var): first step -> 9.9
+    w, m, v = (np.full((1, 4), x, dtype=np.float32) for x in (10.0, 0.0, 0.0))
+    oracle.bag_backward_adam([0], np.full((1, 4), 10.0, dtype=np.float32), w, m, v, step=1, lr=0.1, L=1)
+    np.testing.assert_allclose(w, 9.9, rtol=1e-6)
+    # Keras' sparse apply: duplicates are summed BEFORE squaring, untouched rows decay and keep moving
+    w, m, v = np.zeros((3, 4), np.float32), np.zeros((3, 4), np.float32), np.zeros((3, 4), np.float32)
+    m[2], v[2] = 0.5, 0.25                                                   # row 2: momentum left from earlier steps
+    g = np.array([[1.0] * 4, [2.0] * 4], dtype=np.float32)
+    touched = oracle.bag_backward_adam([1, 1], g, w, m, v, step=5, lr=0.01, L=1)
+    assert touched.tolist() == [False, True, False]
+    np.testing.assert_allclose(m[1], 0.1 * 3.0, rtol=1e-6)                   # (1 - b1) * (1 + 2)
+    np.testing.assert_allclose(v[1], 0.001 * 9.0, rtol=1e-4)                 # (1 - b2) * (1 + 2)^2, not 1 + 4 (fp32 1 - 0.999)
+    np.testing.assert_allclose(m[2], 0.45, rtol=1e-6)
+    np.testing.assert_allclose(v[2], 0.25 * 0.999, rtol=1e-6)
+    lr_t = 0.01 * np.sqrt(1 - 0.999 ** 5) / (1 - 0.9 ** 5)
+    np.testing.assert_allclose(w[2], -lr_t * 0.45 / (np.sqrt(0.25 * 0.999) + 1e-7), rtol=1e-5)
+    assert not w[0].any() and not m[0].any()
+    # lazy: row 2 is left alone
+    w2, m2, v2 = np.zeros((3, 4), np.float32), m.copy(), v.copy()
+    oracle.bag_backward_adam([1, 1], g, w2, m2, v2, step=6, lr=0.01, L=1, lazy=True)
+    assert not w2[2].any() and np.array_equal(m2[2], m[2])

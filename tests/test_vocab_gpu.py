@@ -125,3 +125,14 @@ def test_forward_all_fuses_hashed_lookup_and_discrete_features():
     flat = [x for r in batch["top_cat"] for x in r]
     want = oracle.bag_pool(oracle.vocab_lookup(flat, ["game", "app", "book"]), layers["top_cat"].embedding.get_weights()[0], "sum", L=3)
     assert np.array_equal(res["top_cat"].cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
+def test_keras_doc_examples_on_the_device():
+    # the examples of the StringLookup / IntegerLookup / Discretization docstrings (tests/test_oracle_kat.py pins the oracle on them)
+    sv = DeviceVocabulary(["a", "b", "c", "d"], "cuda")
+    col = StringColumn.from_lists([["a", "c", "d"], ["d", "z", "b"]]).to("cuda")
+    assert sv.lookup(col).tolist() == [[1, 3, 4], [4, 0, 2]]
+    iv = DeviceVocabulary([12, 36, 1138, 42], "cuda")
+    assert iv.lookup(torch.tensor([[12, 1138, 42], [42, 1000, 36]], device="cuda")).tolist() == [[1, 3, 4], [4, 0, 2]]
+    x = torch.tensor([[-1.5, 1.0, 3.4, .5], [0.0, 3.0, 1.3, 0.0]], device="cuda")
+    assert bucketize(x, torch.tensor([0., 1., 2.], device="cuda")).tolist() == [[0, 2, 3, 1], [1, 3, 2, 1]]
