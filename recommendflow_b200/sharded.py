@@ -93,6 +93,24 @@ class CudaShardOps(object):
                                                     out.stride(0), C.c_void_p(torch.cuda.current_stream(out.device).cuda_stream)))
 
 
+    def adam(self, shard, m, v, rows, offs_all, grads, state, params):
+        """Keras Adam on this rank's shard from the routed rows of every source (rf_bag_backward_adam):
+        rows [n] int64 local rows, offs_all [n_bags + 1] CSR over all (source, bag) pairs, grads [n_bags, D]."""
+        n_bags = grads.shape[0]
+        p = nat.AdamParams(lr=params["learning_rate"], beta1=params["beta_1"], beta2=params["beta_2"], epsilon=params["epsilon"],
+                           step=params["step"], lazy=1 if params["lazy"] else 0)
+        with torch.cuda.device(shard.device):
+            need = int(nat.lib().rf_bag_adam_workspace_bytes(rows.numel(), shard.shape[0]))
+            if need < 0:
+                nat.check(nat.RF_ERR_INVALID)
+            if state.get("ws") is None or state["ws"].numel() < need:
+                state["ws"] = torch.empty(need, dtype=torch.uint8, device=shard.device)
+            nat.check(nat.lib().rf_bag_backward_adam(
+                rows.data_ptr(), rows.numel(), offs_all.data_ptr(), 0, n_bags, grads.data_ptr(), grads.stride(0), shard.shape[1],
+                nat.COMBINER["sum"], C.byref(p), shard.data_ptr(), m.data_ptr(), v.data_ptr(), shard.shape[0],
+                state["ws"].data_ptr(), state["ws"].numel(), C.c_void_p(torch.cuda.current_stream(shard.device).cuda_stream)))
+
+
 def shard_rows(num_bins, rank, world):
     """Number of table rows rank `rank` holds (ids rank, rank + world, ...)."""
     return (num_bins - rank + world - 1) // world if num_bins > rank else 0
@@ -350,6 +368,8 @@ class ShardedEmbeddingBag(torch.nn.Module):
         recv_flat = torch.empty(sum(recv_tot), dtype=torch.int64, device=self.device)
         dist.all_to_all_single(recv_flat, send_flat, recv_tot, send_tot, group=self.group)
         rows_in = list(torch.split(recv_flat, recv_tot))
+        # what the backward needs: the routed local rows of every source, in (source, bag, key) order
+        self._saved = {"rows": recv_flat, "recv_tot": recv_tot, "offs_recv": offs_recv, "B": B, "L": L, "bag_offsets": bag_offsets}
         partial_op = "sum" if self.combiner == "avg" else self.combiner
         self.ops.pool(self.shard.data, rows_in, [offs_recv[s] for s in range(W)],
                       [b["part_send"][s] for s in range(W)], B, partial_op, max(1, n_keys // W))
@@ -357,3 +377,50 @@ class ShardedEmbeddingBag(torch.nn.Module):
         self.ops.combine(b["partials"][0], W, B, D, self.combiner, L, bag_offsets, out)
         self._tick("combine")
         return out
+
+    # ---- backward + optimizer (SURVEY.md §8f rank 1, row-sharded) -------------------------------------
+    def apply_adam(self, grad_out, learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7, lazy=False):
+        """Backward of the LAST forward fused with tf.keras.optimizers.Adam on this rank's rows.
+
+        grad_out: [B, D] gradient of this rank's pooled output.  The reverse exchange is one all-gather of
+        the (pre-scaled) gradients: every owner already holds, from the forward's routing, the local rows each
+        source gathered per bag, so it can scatter source s's bag gradients to its rows directly.  Rows owned
+        by this rank that no source touched decay and move like every Keras Adam variable (lazy=False).
+        nccl transport (the p2p transport's peer-pointer variant is not built); sum / avg combiners."""
+        if self.transport != "nccl":
+            raise NotImplementedError("apply_adam is implemented for the nccl transport")
+        if self.combiner not in ("sum", "avg"):
+            raise NotImplementedError(f"backward is implemented for sum / avg pooling, not {self.combiner}")
+        sv = getattr(self, "_saved", None)
+        if sv is None:
+            raise RuntimeError("apply_adam needs a preceding forward")
+        B, W, D = sv["B"], self.world, self.output_dim
+        g = grad_out.to(torch.float32)
+        if tuple(g.shape) != (B, D):
+            raise ValueError(f"grad_out must be [{B}, {D}]")
+        if self.combiner == "avg":     # the bag's TOTAL key count lives with the source: scale here, owners then sum
+            if sv["bag_offsets"] is not None:
+                cnt = (sv["bag_offsets"][1:] - sv["bag_offsets"][:-1]).clamp(min=1).to(torch.float32)
+                g = g / cnt[:, None]
+            else:
+                g = g / float(max(sv["L"], 1))
+        g = g.contiguous()
+        gathered = torch.empty(W, B, D, dtype=torch.float32, device=g.device)
+        dist.all_gather(list(gathered.unbind(0)), g, group=self.group)
+        # one CSR over all (source, bag) pairs: source s's offsets shifted by the keys of the sources before it
+        totals = [0]
+        for n in sv["recv_tot"]:
+            totals.append(totals[-1] + int(n))
+        base = torch.tensor(totals, dtype=torch.int64, device=g.device)
+        offs_all = (sv["offs_recv"][:, :B].to(torch.int64) + base[:W, None]).reshape(-1)
+        offs_all = torch.cat([offs_all, base[W:]]).to(torch.int32).contiguous()
+        st = getattr(self, "_adam", None)
+        if st is None:
+            st = self._adam = {"m": torch.zeros_like(self.shard.data), "v": torch.zeros_like(self.shard.data), "iterations": 0,
+                               "ws": None}
+        st["iterations"] += 1
+        params = {"learning_rate": learning_rate, "beta_1": beta_1, "beta_2": beta_2, "epsilon": epsilon,
+                  "step": st["iterations"], "lazy": lazy}
+        self.ops.adam(self.shard.data, st["m"], st["v"], sv["rows"], offs_all, gathered.view(W * B, D), st, params)
+        self._saved = None
+        return self.shard

@@ -88,6 +88,11 @@ class OracleShardOps(object):
         acc[cnt == 0] = 0
         out.copy_(torch.from_numpy(acc.astype(np.float32)))
 
+    def adam(self, shard, m, v, rows, offs_all, grads, state, params):
+        oracle.bag_backward_adam(rows.numpy(), grads.numpy(), shard.numpy(), m.numpy(), v.numpy(), params["step"],
+                                 lr=params["learning_rate"], beta1=params["beta_1"], beta2=params["beta_2"], eps=params["epsilon"],
+                                 combiner="sum", bag_offsets=offs_all.numpy(), lazy=params["lazy"])
+
 
 def rank_batch(rank, B, max_len, seed=4242, alphabet=b"abcdefghijklmnopqrstuvwxyz0123456789_"):
     """Jagged keys of one rank: lengths ~ U{0..max_len} (seed 4242 + rank)."""

@@ -79,3 +79,59 @@ def test_sharded_forward_multi_gpu(world):
         for key, (exact, err) in out.items():
             assert exact, f"rank {rank} {key}: differs from the sharded restatement"
             assert err <= 200 * 0.05 * 2.0 ** -21, (rank, key, err)     # fp32 re-association of <= 200 adds
+
+
+def _train_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from recommendflow_b200.sharded import ShardedEmbeddingBag
+        from recommendflow_b200.strings import StringColumn
+        N, D, B = 5003, 32, 256
+        full = np.random.default_rng(1).uniform(-0.05, 0.05, size=(N, D)).astype(np.float32)
+        layer = ShardedEmbeddingBag(N, D, combiner="avg", salt=None, mask_value="", transport="nccl", max_batch=B,
+                                    max_keys=B * 30)
+        layer.set_full_weights(full)
+        for step in (1, 2):
+            arena, offs, bag = rank_batch(rank, B, 30, seed=100 * step)
+            layer(StringColumn.from_arena(arena, offs, (B, None), bag).to(f"cuda:{rank}"))
+            g = np.random.default_rng(7 * step + rank).standard_normal((B, D)).astype(np.float32)
+            layer.apply_adam(torch.from_numpy(g).cuda(), learning_rate=1e-2)
+        torch.cuda.synchronize()
+        q.put((rank, layer.shard.detach().cpu().numpy(), layer._adam["m"].cpu().numpy(), layer._adam["v"].cpu().numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_backward_adam_multi_gpu():
+    # same construction as tests/test_sharded_cpu.py::test_two_rank_gloo_sharded_backward_adam, on the CUDA kernels
+    world, N, D, B = 2, 5003, 32, 256
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {r: (w, m, v) for r, w, m, v in (q.get(timeout=300) for _ in procs)}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = np.random.default_rng(1).uniform(-0.05, 0.05, size=(N, D)).astype(np.float32)
+    m, v = np.zeros_like(full), np.zeros_like(full)
+    for step in (1, 2):
+        ids_all, grads_all, offs_all = [], [], [0]
+        for rank in range(world):
+            arena, offs, bag = rank_batch(rank, B, 30, seed=100 * step)
+            g = np.random.default_rng(7 * step + rank).standard_normal((B, D)).astype(np.float32)
+            g = g / np.maximum(np.diff(bag), 1).astype(np.float32)[:, None]
+            ids_all.append(oracle.hash_strings(arena, offs, N, "", None))
+            grads_all.append(g)
+            base = offs_all[-1]
+            offs_all += (bag[1:].astype(np.int64) + base).tolist()
+        assert np.bincount(np.concatenate(ids_all), minlength=N).max() <= 128       # every run is summed in key order
+        oracle.bag_backward_adam(np.concatenate(ids_all), np.concatenate(grads_all), full, m, v, step, lr=1e-2,
+                                 combiner="sum", bag_offsets=np.asarray(offs_all, dtype=np.int32))
+    for rank in range(world):
+        for got, want in zip(res[rank], (full, m, v)):
+            assert np.array_equal(got.view(np.uint32), want[rank::world].view(np.uint32)), rank
