@@ -63,3 +63,34 @@ def test_salt_rules():
     assert nat.salt_to_key([2022, 2023]) == (1, 2022, 2023)
     with pytest.raises(ValueError):
         nat.salt_to_key([1, 2, 3])
+
+
+def test_header_is_plain_c_and_ctypes_structs_match_it(tmp_path):
+    # include/rf_b200.h must compile as C99 on its own (it is what a cgo / JNI / TF-op binding includes), and the
+    # ctypes mirrors in _native.py must have exactly the C compiler's sizes and member offsets
+    import subprocess
+    src = tmp_path / "layout.c"
+    checks = {"rf_table_desc": (nat.TableDesc, ["weights", "num_bins", "use_strong", "key0", "key1"]),
+              "rf_field_desc": (nat.FieldDesc, ["bytes", "str_offsets", "int_values", "ids", "bag_offsets", "bag_ends", "n_items",
+                                                "bag_len", "n_tables", "tables", "dim", "combiner", "mask_mode", "flags",
+                                                "int_mask_value", "out", "out_stride", "ids_out"]),
+              "rf_vocab_desc": (nat.VocabDesc, ["term_bytes", "term_offsets", "term_ints", "slots", "capacity", "n_terms"]),
+              "rf_adam_params": (nat.AdamParams, ["lr", "beta1", "beta2", "epsilon", "step", "lazy"]),
+              "rf_adam_field": (nat.AdamField, ["ids", "bag_offsets", "n_keys", "bag_len", "combiner", "grad_out", "grad_stride",
+                                                "table", "m", "v", "table_rows", "dim"])}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "rf_b200.h")}"', "int main(void) {"]
+    for cname, (_, members) in checks.items():
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for m in members:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {m}));')
+        lines.append('  printf("\\n");')
+    lines += ["  return 0;", "}"]
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True).strip().splitlines()
+    for line in out:
+        cname, size, *offs = line.split()
+        struct, members = checks[cname]
+        assert ctypes.sizeof(struct) == int(size), cname
+        assert [getattr(struct, m).offset for m in members] == [int(o) for o in offs], cname
