@@ -45,6 +45,15 @@ class AdamField(C.Structure):
                 ("m", C.c_void_p), ("v", C.c_void_p), ("table_rows", C.c_int64), ("dim", C.c_int32), ("reserved", C.c_int32)]
 
 
+class ExampleColumn(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("name_len", C.c_int32), ("kind", C.c_int32), ("n_values", C.c_int64),
+                ("n_bytes", C.c_int64), ("row_counts", C.c_void_p), ("bytes_out", C.c_void_p), ("value_offsets", C.c_void_p),
+                ("floats_out", C.c_void_p), ("ints_out", C.c_void_p)]
+
+
+TFR_BYTES, TFR_FLOAT, TFR_INT64 = 0, 1, 2
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -104,6 +113,14 @@ def lib():
         L.rf_bag_backward_adam_multi.restype = C.c_int
         L.rf_bag_backward_adam_multi.argtypes = [C.POINTER(AdamField), C.c_int, C.c_int64, C.POINTER(AdamParams), C.c_void_p,
                                                  C.c_int64, C.c_void_p]
+        L.rf_crc32c.restype = C.c_uint32
+        L.rf_crc32c.argtypes = [C.c_void_p, C.c_int64]
+        L.rf_masked_crc32c.restype = C.c_uint32
+        L.rf_masked_crc32c.argtypes = [C.c_void_p, C.c_int64]
+        L.rf_tfrecord_index.restype = C.c_int
+        L.rf_tfrecord_index.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
+        L.rf_example_parse_columns.restype = C.c_int
+        L.rf_example_parse_columns.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(ExampleColumn), C.c_int, C.c_int]
         L.rf_sdpa_backward.restype = C.c_int
         L.rf_sdpa_backward.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 4
         L.rf_inbatch_softmax_ce_backward.restype = C.c_int

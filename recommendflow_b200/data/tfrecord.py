@@ -24,7 +24,7 @@ from collections import namedtuple
 import numpy as np
 import torch
 
-from ..config_parser.config_proto import TYPE_INT, TYPE_STR, FeatureDeal, int64 as INT64
+from ..config_parser.config_proto import TYPE_INT, TYPE_STR, FeatureDeal, float32 as TFFloat, int64 as INT64, string as TFString
 from ..strings import StringColumn
 
 # ---- CRC32C (Castagnoli), table driven --------------------------------------------------------
@@ -278,10 +278,143 @@ def parse_example(records, feature_description):
     return out
 
 
-def load_tfrecord(paths, conf, batch_size, compression="GZIP", drop_remainder=False):
-    """Minimal `_get_tfrecord_dataset` (dataloader.py:541-578): batches of (features, labels) dicts."""
+# ---- native path: librf_b200.so's rf_tfrecord_index / rf_example_parse_columns (include/rf_tfrecord.h) ----------
+class RecordFile(object):
+    """The records of one (GZIP) TFRecord file, indexed by the native codec: the decompressed stream stays one
+    bytes object; `offsets` / `lengths` locate each serialized Example in it."""
+
+    def __init__(self, path, compression="GZIP", verify_crc=False):
+        import ctypes as C
+
+        from .. import _native as nat
+        opener = gzip.open if compression == "GZIP" else open
+        with opener(path, "rb") as fh:
+            self.data = np.frombuffer(fh.read(), dtype=np.uint8)
+        lib = nat.lib()
+        n = C.c_int64(0)
+        try:
+            nat.check(lib.rf_tfrecord_index(self.data.ctypes.data, self.data.size, 1 if verify_crc else 0, 0, None, None, C.byref(n)))
+            self.offsets = np.empty(n.value, dtype=np.int64)
+            self.lengths = np.empty(n.value, dtype=np.int64)
+            nat.check(lib.rf_tfrecord_index(self.data.ctypes.data, self.data.size, 0, n.value, self.offsets.ctypes.data,
+                                            self.lengths.ctypes.data, C.byref(n)))
+        except ValueError as e:
+            raise IOError(str(e)) from None
+
+    def __len__(self):
+        return int(self.offsets.size)
+
+
+def _pad_rows(counts, L):
+    """index [B, L] into the jagged value list: row r's l-th value, clamped to one past its last (a pad)."""
+    start = np.zeros(counts.size, dtype=np.int64)
+    np.cumsum(counts[:-1], out=start[1:])
+    return start[:, None] + np.minimum(np.arange(L, dtype=np.int64)[None, :], counts[:, None].astype(np.int64))
+
+
+def parse_example_native(rf, first, count, feature_description):
+    """tf.io.parse_example over records [first, first + count) of a RecordFile, decoded by the native codec straight
+    into arenas / flat arrays (no Python object per value), then densified exactly like `parse_example`."""
+    import ctypes as C
+
+    from .. import _native as nat
+    names = list(feature_description)
+    cols = (nat.ExampleColumn * len(names))()
+    keep = []
+    for c, name in zip(cols, names):
+        spec = feature_description[name]
+        raw = name.encode()
+        keep.append(raw)
+        c.name, c.name_len = raw, len(raw)
+        c.kind = {"string": nat.TFR_BYTES, "int64": nat.TFR_INT64}.get(spec.dtype.name, nat.TFR_FLOAT)
+        counts = np.empty(count, dtype=np.int32)
+        keep.append(counts)
+        c.row_counts = counts.ctypes.data
+    offs, lens = rf.offsets[first:first + count], rf.lengths[first:first + count]
+    lib = nat.lib()
+    args = (rf.data.ctypes.data, offs.ctypes.data, lens.ctypes.data, count, cols, len(names))
+    nat.check(lib.rf_example_parse_columns(*args, 0))
+    outs = []
+    for c in cols:
+        if c.kind == nat.TFR_BYTES:
+            arena = np.zeros(c.n_bytes, dtype=np.uint8)
+            voffs = np.empty(c.n_values + 1, dtype=np.int32)
+            c.bytes_out, c.value_offsets = arena.ctypes.data, voffs.ctypes.data
+            outs.append((arena, voffs))
+        elif c.kind == nat.TFR_FLOAT:
+            vals = np.empty(c.n_values, dtype=np.float32)
+            c.floats_out = vals.ctypes.data
+            outs.append((vals,))
+        else:
+            vals = np.empty(c.n_values, dtype=np.int64)
+            c.ints_out = vals.ctypes.data
+            outs.append((vals,))
+    nat.check(lib.rf_example_parse_columns(*args, 1))
+    batch = {}
+    for c, name, out in zip(cols, names, outs):
+        spec = feature_description[name]
+        counts = np.ctypeslib.as_array(C.cast(c.row_counts, C.POINTER(C.c_int32)), shape=(count,)).copy()
+        seq = isinstance(spec, FixedLenSequenceFeature)
+        L = int(counts.max()) if (seq and count) else 1
+        if c.kind == nat.TFR_BYTES:
+            arena, voffs = out
+            if not seq:                                 # FixedLenFeature: first value, or the default when absent
+                default = spec.default_value.encode() if isinstance(spec.default_value, str) else b""
+                if (counts == 0).any() and default:
+                    strs = [bytes(arena[voffs[i]:voffs[i + 1]]) for i in range(c.n_values)]
+                    start = np.concatenate([[0], np.cumsum(counts)[:-1]])
+                    batch[name] = StringColumn.from_lists([[strs[start[r]] if counts[r] else default] for r in range(count)])
+                    continue
+                counts = np.minimum(counts, 1) if (counts <= 1).all() else counts
+                idx = _pad_rows(counts, 1) if (counts <= 1).all() else None
+                if idx is None:                         # longer lists: keep the first value of each row
+                    start = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int64)
+                    first_end = np.where(counts > 0, voffs[np.minimum(start + 1, c.n_values)], voffs[np.minimum(start, c.n_values)])
+                    strs = [bytes(arena[voffs[min(start[r], c.n_values)]:first_end[r]]) for r in range(count)]
+                    batch[name] = StringColumn.from_lists([[x] for x in strs])
+                    continue
+            if L == 0:
+                batch[name] = StringColumn.from_lists([[] for _ in range(count)])
+                continue
+            idx = _pad_rows(counts, L)
+            padded = np.empty(count * L + 1, dtype=np.int32)
+            padded[:-1] = voffs[idx].ravel()
+            padded[-1] = c.n_bytes
+            batch[name] = StringColumn.from_arena(arena, padded, (count, L))
+        else:
+            (vals,) = out
+            np_dtype = np.int64 if c.kind == nat.TFR_INT64 else np.float32
+            if seq:
+                arr = np.full((count, L), spec.default_value, dtype=np_dtype)
+                mask = np.arange(L)[None, :] < counts[:, None]
+                arr[mask] = vals
+                batch[name] = torch.from_numpy(arr)
+            else:
+                start = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int64)
+                arr = np.full(count, spec.default_value, dtype=np_dtype)
+                has = counts > 0
+                arr[has] = vals[start[has]]
+                batch[name] = torch.from_numpy(arr)
+    return batch
+
+
+def load_tfrecord(paths, conf, batch_size, compression="GZIP", drop_remainder=False, native=True):
+    """Minimal `_get_tfrecord_dataset` (dataloader.py:541-578): batches of (features, labels) dicts.
+
+    native=True decodes with the C codec of librf_b200.so (batches do not span files, as with the reference's
+    per-file interleave + batch); native=False is the pure-Python decoder the tests check it against."""
     desc = build_feature_description(conf)
     label_names = conf.features.label_names
+    if native:
+        for path in ([paths] if isinstance(paths, str) else paths):
+            rf = RecordFile(path, compression)
+            for first in range(0, len(rf), batch_size):
+                count = min(batch_size, len(rf) - first)
+                if count < batch_size and drop_remainder:
+                    break
+                ex = parse_example_native(rf, first, count, desc)
+                yield ex, {n: ex[n] for n in label_names if n in ex}
+        return
     buf = []
     for path in ([paths] if isinstance(paths, str) else paths):
         for rec in read_tfrecord(path, compression):

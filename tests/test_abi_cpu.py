@@ -13,9 +13,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "rf_b200.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(rf_[a-z0-9_]+)\s*\(", text)))
+    names = set()
+    for header in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        text = open(os.path.join(ROOT, "include", header)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(rf_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
 
 
 def test_library_exports_every_declared_symbol():
@@ -76,9 +79,12 @@ def test_header_is_plain_c_and_ctypes_structs_match_it(tmp_path):
                                                 "int_mask_value", "out", "out_stride", "ids_out"]),
               "rf_vocab_desc": (nat.VocabDesc, ["term_bytes", "term_offsets", "term_ints", "slots", "capacity", "n_terms"]),
               "rf_adam_params": (nat.AdamParams, ["lr", "beta1", "beta2", "epsilon", "step", "lazy"]),
+              "rf_example_column": (nat.ExampleColumn, ["name", "name_len", "kind", "n_values", "n_bytes", "row_counts", "bytes_out",
+                                                        "value_offsets", "floats_out", "ints_out"]),
               "rf_adam_field": (nat.AdamField, ["ids", "bag_offsets", "n_keys", "bag_len", "combiner", "grad_out", "grad_stride",
                                                 "table", "m", "v", "table_rows", "dim"])}
-    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "rf_b200.h")}"', "int main(void) {"]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "rf_b200.h")}"', f'#include "{os.path.join(ROOT, "include", "rf_tfrecord.h")}"',
+             "int main(void) {"]
     for cname, (_, members) in checks.items():
         lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
         for m in members:
