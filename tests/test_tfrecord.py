@@ -207,3 +207,41 @@ def test_native_codec_on_protobuf_runtime_output(tmp_path):
     open(bad, "wb").write(bytes(raw[:-3]))
     with pytest.raises(IOError, match="truncated"):
         tfr.RecordFile(bad, compression=None)
+
+
+def test_native_codec_rejects_or_survives_corrupt_examples(golden_dir):
+    # bounds: every read in the native decoder is checked against the record's span; mutated records either parse or
+    # raise ValueError, they never crash
+    conf2 = Configuration(os.path.join(golden_dir, "configs", "synth_mixed.yaml"))
+    for f in conf2.features.features:
+        if f.name == "uid":
+            f.working = False
+    rng = np.random.default_rng(11)
+    recs = [tfr.build_tfrecord(r, conf2) for r in _random_rows(rng, 6)]
+    desc = tfr.build_feature_description(conf2)
+
+    class OneRecord(object):
+        pass
+    outcomes = {"ok": 0, "rejected": 0}
+    for it in range(1500):
+        rec = bytearray(recs[it % len(recs)])
+        for _ in range(int(rng.integers(1, 4))):
+            if len(rec) < 2:
+                break
+            mode = int(rng.integers(0, 3))
+            if mode == 0:
+                rec[int(rng.integers(0, len(rec)))] = int(rng.integers(0, 256))
+            elif mode == 1:
+                del rec[int(rng.integers(1, len(rec))):]
+            else:
+                a = int(rng.integers(0, len(rec)))
+                rec[a:a + int(rng.integers(0, 4))] = bytes(rng.integers(0, 256, size=int(rng.integers(0, 6)), dtype=np.uint8))
+        rf = OneRecord()
+        rf.data = np.frombuffer(bytes(rec), dtype=np.uint8).copy()
+        rf.offsets, rf.lengths = np.array([0], dtype=np.int64), np.array([len(rec)], dtype=np.int64)
+        try:
+            tfr.parse_example_native(rf, 0, 1, desc)
+            outcomes["ok"] += 1
+        except ValueError:
+            outcomes["rejected"] += 1
+    assert outcomes["rejected"] > 100 and outcomes["ok"] > 10
