@@ -426,3 +426,62 @@ def load_tfrecord(paths, conf, batch_size, compression="GZIP", drop_remainder=Fa
     if buf and not drop_remainder:
         ex = parse_example(buf, desc)
         yield ex, {n: ex[n] for n in label_names if n in ex}
+
+
+def get_tfrecord_dataset(paths, feature_description, label_names, batch_size, thread_num=4, compression_type="GZIP",
+                         prefetch_buffer_size=8, drop_remainder=False, pin_memory=False):
+    """`_get_tfrecord_dataset` (dataloader.py:541-578) on the native codec: `thread_num` host threads read, inflate and
+    decode files concurrently (zlib and the C decoder both run without the GIL), at most `prefetch_buffer_size` decoded
+    batches wait in the queue, and batches come out in file order (batches do not span files).  Yields
+    (features, labels) like the reference's parse_example (:77-89).  pin_memory=True page-locks every batch so that
+    the `.to(device, non_blocking=True)` of the layers overlaps with compute."""
+    import queue
+    import threading
+    paths = [paths] if isinstance(paths, str) else list(paths)
+    assert len(paths) > 0, "Paths must not be empty"
+    thread_num = max(1, min(int(thread_num), len(paths)))
+    slots = {i: queue.Queue(maxsize=max(1, prefetch_buffer_size // thread_num + 1)) for i in range(len(paths))}
+    stop = threading.Event()
+    END = object()
+
+    def put(q, item):
+        while not stop.is_set():
+            try:
+                q.put(item, timeout=0.1)
+                return True
+            except queue.Full:
+                continue
+        return False
+
+    def work(worker):
+        for fi in range(worker, len(paths), thread_num):
+            try:
+                rf = RecordFile(paths[fi], compression_type)
+                for first in range(0, len(rf), batch_size):
+                    count = min(batch_size, len(rf) - first)
+                    if count < batch_size and drop_remainder:
+                        break
+                    ex = parse_example_native(rf, first, count, feature_description)
+                    if pin_memory:
+                        ex = {k: v.pin_memory() for k, v in ex.items()}
+                    if not put(slots[fi], ex):
+                        return
+                put(slots[fi], END)
+            except BaseException as e:                     # surfaces in the consumer
+                put(slots[fi], e)
+                return
+
+    threads = [threading.Thread(target=work, args=(w,), daemon=True) for w in range(thread_num)]
+    for t in threads:
+        t.start()
+    try:
+        for fi in range(len(paths)):
+            while True:
+                item = slots[fi].get()
+                if item is END:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                yield item, {n: item[n] for n in label_names if n in item}
+    finally:
+        stop.set()

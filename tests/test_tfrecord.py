@@ -245,3 +245,31 @@ def test_native_codec_rejects_or_survives_corrupt_examples(golden_dir):
         except ValueError:
             outcomes["rejected"] += 1
     assert outcomes["rejected"] > 100 and outcomes["ok"] > 10
+
+
+def test_threaded_dataset_yields_every_file_in_order(golden_dir, tmp_path):
+    conf2 = Configuration(os.path.join(golden_dir, "configs", "synth_mixed.yaml"))
+    for f in conf2.features.features:
+        if f.name == "uid":
+            f.working = False
+    rng = np.random.default_rng(8)
+    paths, sizes = [], [37, 5, 64, 1, 20]
+    for i, n in enumerate(sizes):
+        paths.append(str(tmp_path / f"part-{i}.tfr.gz"))
+        tfr.dump_tfrecord_data(_random_rows(rng, n), paths[-1], conf2)
+    desc = tfr.build_feature_description(conf2)
+    for threads, drop in ((1, False), (3, False), (8, True)):
+        got = list(tfr.get_tfrecord_dataset(paths, desc, conf2.features.label_names, 16, thread_num=threads, drop_remainder=drop,
+                                            prefetch_buffer_size=2))
+        want = [b for p in paths for b in tfr.load_tfrecord(p, conf2, 16, drop_remainder=drop)]
+        assert len(got) == len(want) == sum((n // 16) if drop else -(-n // 16) for n in sizes)
+        for (gb, gl), (wb, wl) in zip(got, want):
+            _assert_same_batch(gb, wb)
+            assert np.array_equal(gl["label"].numpy(), wl["label"].numpy())
+    # a broken file surfaces as an exception in the consumer, and an abandoned iterator lets the workers stop
+    open(paths[2], "wb").write(b"not gzip")
+    with pytest.raises(Exception):
+        list(tfr.get_tfrecord_dataset(paths, desc, conf2.features.label_names, 16, thread_num=2))
+    it = tfr.get_tfrecord_dataset(paths[:2], desc, conf2.features.label_names, 4, thread_num=2, prefetch_buffer_size=1)
+    next(it)
+    it.close()
