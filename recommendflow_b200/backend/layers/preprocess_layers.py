@@ -41,6 +41,8 @@ def as_keys(inputs, device=None):
         if inputs.data.is_cuda:
             return inputs
         return inputs.to(device or _default_device(), non_blocking=True)
+    if not isinstance(inputs, (torch.Tensor, np.ndarray, list, tuple)) and hasattr(inputs, "__dlpack__"):
+        inputs = torch.from_dlpack(inputs)           # zero-copy hand-over from TensorFlow / CuPy / JAX (DLPack)
     if isinstance(inputs, torch.Tensor):
         if inputs.dtype not in (torch.int64, torch.int32):
             raise ValueError(f"tensor inputs must be integer keys, got {inputs.dtype}")

@@ -83,3 +83,23 @@ def test_no_cpu_fallback():
     layer = DoubleHashingEmbedding(100, 8, [1, 2], "sum", mask_value="", name="h")
     with pytest.raises(nat.NativeError, match="no CPU fallback"):
         layer([["a"], ["b"]])
+
+
+def test_integer_keys_arrive_through_dlpack():
+    # any producer that speaks DLPack (tf.experimental.dlpack, CuPy, JAX) can hand integer keys over without a copy
+    from recommendflow_b200.backend.layers.preprocess_layers import as_keys
+
+    class Foreign(object):
+        def __init__(self, t):
+            self._t = t
+
+        def __dlpack__(self, *args, **kwargs):
+            return self._t.__dlpack__(*args, **kwargs)
+
+        def __dlpack_device__(self):
+            return self._t.__dlpack_device__()
+    src = torch.arange(12, dtype=torch.int64).reshape(3, 4)
+    got = as_keys(Foreign(src), device="cpu")
+    assert got.dtype == torch.int64 and got.shape == (3, 4) and got.data_ptr() == src.data_ptr()
+    with pytest.raises(ValueError, match="integer keys"):
+        as_keys(Foreign(torch.zeros(2, 2)), device="cpu")
