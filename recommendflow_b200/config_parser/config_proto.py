@@ -29,36 +29,18 @@ float32 = DType("float32", "float32")
 string = DType("string", None)
 
 
-class FeatureTower(Enum):
-    Null = "null"
-    User = "user"
-    Ad = "ad"
-    Context = "context"
-    Label = "label"
+def _spec_enum(name, values):
+    """Enum whose member names are the CamelCase of their string values ("token_id" -> TokenId), which is the
+    naming the reference's enums follow (config_proto.py:5-33)."""
+    members = {"".join(part.capitalize() for part in v.split("_")): v for v in values}
+    return Enum(name, members, module=__name__)
 
 
-class FeatureDeal(Enum):
-    Null = "null"
-    Numeric = "numeric"
-    Discrete = "discrete"
-    Hashing = "hashing"
-    Lookup = "lookup"
-    Image = "image"
-    Embedding = "embedding"
-    TokenId = "token_id"
-    BertEncode = "bert_encode"
-
-
-class FeaturePooling(Enum):
-    # NB: no "cls" member -- conf/demo_conf.yaml therefore fails to parse, as in the reference.
-    Null = "null"
-    Avg = "avg"
-    Min = "min"
-    Max = "max"
-    Sum = "sum"
-    First = "first"
-    Last = "last"
-
+FeatureTower = _spec_enum("FeatureTower", ("null", "user", "ad", "context", "label"))
+FeatureDeal = _spec_enum("FeatureDeal", ("null", "numeric", "discrete", "hashing", "lookup", "image", "embedding",
+                                         "token_id", "bert_encode"))
+# NB: no "cls" pooling -- conf/demo_conf.yaml therefore fails to parse, as in the reference.
+FeaturePooling = _spec_enum("FeaturePooling", ("null", "avg", "min", "max", "sum", "first", "last"))
 
 TYPE_INT = "int"
 TYPE_FLOAT = "float"
