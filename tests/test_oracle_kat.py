@@ -187,3 +187,42 @@ def test_adam_keras_doc_example_and_sparse_semantics():
     w2, m2, v2 = np.zeros((3, 4), np.float32), m.copy(), v.copy()
     oracle.bag_backward_adam([1, 1], g, w2, m2, v2, step=6, lr=0.01, L=1, lazy=True)
     assert not w2[2].any() and np.array_equal(m2[2], m[2])
+
+
+# ---- property tests (hypothesis): the C oracle and the independent pure-Python restatement never disagree ----
+try:
+    from hypothesis import given, settings, strategies as st
+    HAVE_HYPOTHESIS = True
+except Exception:                                   # pragma: no cover
+    HAVE_HYPOTHESIS = False
+
+if HAVE_HYPOTHESIS:
+    @settings(max_examples=300, deadline=None)
+    @given(st.binary(min_size=0, max_size=300), st.integers(0, 2**64 - 1), st.integers(0, 2**64 - 1))
+    def test_property_hashes_agree_between_restatements(data, k0, k1):
+        assert oracle.fingerprint64(data) == pyhash.fingerprint64(data)
+        assert oracle.siphash24(k0, k1, data) == pyhash.siphash24(k0, k1, data)
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.binary(min_size=0, max_size=40), min_size=1, max_size=20), st.integers(2, 2**32 - 1),
+           st.sampled_from([None, 7, [2022, 2023]]))
+    def test_property_keras_bucket_rule(values, num_bins, salt):
+        arena, offs = oracle.encode_strings(values)
+        masked = oracle.hash_strings(arena, offs, num_bins, "", salt)
+        plain = oracle.hash_strings(arena, offs, num_bins, None, salt)
+        for v, m, p in zip(values, masked.tolist(), plain.tolist()):
+            assert 0 <= p < num_bins
+            if v == b"":
+                assert m == 0                                  # mask_value "" -> bucket 0 ...
+            else:
+                assert 1 <= m <= num_bins - 1                  # ... everything else in [1, N - 1]
+                k = (salt, salt) if isinstance(salt, int) else salt
+                h = pyhash.fingerprint64(v) if salt is None else pyhash.siphash24(k[0], k[1], v)
+                assert m == 1 + h % (num_bins - 1) and p == h % num_bins
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.integers(-2**63, 2**63 - 1), min_size=1, max_size=16), st.integers(2, 10**6))
+    def test_property_ints_hash_as_their_decimal_strings(values, num_bins):
+        got = oracle.hash_ints(np.array(values, dtype=np.int64), num_bins, None, None).tolist()
+        arena, offs = oracle.encode_strings([str(v) for v in values])
+        assert got == oracle.hash_strings(arena, offs, num_bins, None, None).tolist()
