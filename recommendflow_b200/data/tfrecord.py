@@ -428,6 +428,24 @@ def load_tfrecord(paths, conf, batch_size, compression="GZIP", drop_remainder=Fa
         yield ex, {n: ex[n] for n in label_names if n in ex}
 
 
+_LIVE_DATASETS = []     # (stop event, worker threads) of iterators that have not been closed yet
+
+
+def _stop_live_datasets():
+    """atexit: worker threads must not run into interpreter shutdown (a daemon thread that is inside torch / numpy
+    when the interpreter finalises takes the whole process down with std::terminate)."""
+    for stop, threads in list(_LIVE_DATASETS):
+        stop.set()
+    for stop, threads in list(_LIVE_DATASETS):
+        for t in threads:
+            t.join(timeout=10)
+
+
+import atexit  # noqa: E402
+
+atexit.register(_stop_live_datasets)
+
+
 def get_tfrecord_dataset(paths, feature_description, label_names, batch_size, thread_num=4, compression_type="GZIP",
                          prefetch_buffer_size=8, drop_remainder=False, pin_memory=False):
     """`_get_tfrecord_dataset` (dataloader.py:541-578) on the native codec: `thread_num` host threads read, inflate and
@@ -472,6 +490,8 @@ def get_tfrecord_dataset(paths, feature_description, label_names, batch_size, th
                 return
 
     threads = [threading.Thread(target=work, args=(w,), daemon=True) for w in range(thread_num)]
+    live, registry = (stop, threads), _LIVE_DATASETS       # local name: module globals are gone during shutdown
+    registry.append(live)
     for t in threads:
         t.start()
     try:
@@ -485,3 +505,7 @@ def get_tfrecord_dataset(paths, feature_description, label_names, batch_size, th
                 yield item, {n: item[n] for n in label_names if n in item}
     finally:
         stop.set()
+        for t in threads:                                  # never leave a worker running into interpreter shutdown
+            t.join(timeout=10)
+        if live in registry:
+            registry.remove(live)
