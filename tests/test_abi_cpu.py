@@ -100,3 +100,20 @@ def test_header_is_plain_c_and_ctypes_structs_match_it(tmp_path):
         struct, members = checks[cname]
         assert ctypes.sizeof(struct) == int(size), cname
         assert [getattr(struct, m).offset for m in members] == [int(o) for o in offs], cname
+
+
+def test_plain_c_program_links_against_the_library(tmp_path):
+    # examples/c_abi_demo.c uses the boundary from C99 with nothing but the CUDA runtime: it must compile, link against
+    # librf_b200.so and start.  Without a GPU it reports that and exits 77 (no CPU fallback); on a GPU box it checks a
+    # Keras Hashing known answer and a gather through rf_bag_forward and exits 0.
+    import subprocess
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    exe = str(tmp_path / "c_abi_demo")
+    libdir = os.path.join(ROOT, "recommendflow_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+                           os.path.join(ROOT, "examples", "c_abi_demo.c"), "-L", libdir, "-lrf_b200", "-L", os.path.join(cuda, "lib64"),
+                           "-lcudart", f"-Wl,-rpath,{libdir}", "-o", exe])
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode in (0, 77), res.stdout + res.stderr
+    if res.returncode == 77:
+        assert "no CPU fallback" in res.stderr
