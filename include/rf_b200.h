@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define RF_B200_ABI_VERSION 1
+#define RF_B200_ABI_VERSION 2
 
 typedef enum rf_status {
     RF_OK = 0,
@@ -44,8 +44,12 @@ typedef enum rf_mask_mode {
     RF_MASK_NONE = 0,        /* mask_value=None: ids in [0, num_bins)                          */
     RF_MASK_EMPTY_STRING = 1,/* mask_value="" (what get_preprocess_layers passes,             */
                              /* backend/utils/preprocess_utils.py:15): "" -> 0, else 1+h%(N-1) */
-    RF_MASK_INT_VALUE = 2    /* integer inputs: value == int_mask_value -> 0                  */
+    RF_MASK_INT_VALUE = 2,   /* integer inputs: value == int_mask_value -> 0                  */
+    RF_MASK_STRING_VALUE = 3 /* mask_value="<any string>": keys whose bytes equal                  */
+                             /* rf_field_desc.mask_bytes[0 .. mask_len) -> 0 (Keras compares the   */
+                             /* raw strings before hashing); at most RF_MAX_MASK_BYTES bytes        */
 } rf_mask_mode;
+#define RF_MAX_MASK_BYTES 32
 
 /* One embedding table + the hash that feeds it: replaces one Keras `Hashing` + `Embedding`
  * pair (preprocess_layers.py:89-92, :31-39). */
@@ -92,6 +96,10 @@ typedef struct rf_field_desc {
     float *out;                  /* device; bag b, table t -> out[b*out_stride + t*dim .. +dim] */
     int64_t out_stride;          /* floats between consecutive bags' rows                       */
     int64_t *ids_out;            /* optional device [n_tables][n_items]: the bucket ids         */
+    /* --- RF_MASK_STRING_VALUE only (host bytes, copied into the launch descriptor) ------------ */
+    uint8_t mask_bytes[RF_MAX_MASK_BYTES];
+    int32_t mask_len;
+    int32_t reserved;
 } rf_field_desc;
 
 /* ---- library ------------------------------------------------------------------------------ */
@@ -105,6 +113,11 @@ int rf_hash_strings(const uint8_t *d_bytes, const int32_t *d_str_offsets, int64_
 int rf_hash_int64(const int64_t *d_values, int64_t n_items, int64_t num_bins, int mask_mode,
                   int64_t int_mask_value, int use_strong, uint64_t key0, uint64_t key1,
                   int64_t *d_ids_out, void *stream);
+/* Keras `Hashing(num_bins, mask_value="<string>")`: keys equal to the mask string go to bucket 0. */
+/* h_mask_value: HOST bytes, mask_len <= RF_MAX_MASK_BYTES (mask_len == 0 is mask_value="").       */
+int rf_hash_strings_masked(const uint8_t *d_bytes, const int32_t *d_str_offsets, int64_t n_items,
+                           int64_t num_bins, const uint8_t *h_mask_value, int32_t mask_len, int use_strong,
+                           uint64_t key0, uint64_t key1, int64_t *d_ids_out, void *stream);
 
 /* ---- fused hash + gather + pool over n_fields fields of one batch, ONE kernel launch ------- */
 /* Replaces the per-feature loop `self.preprocessor[name](batch[name])`                        */

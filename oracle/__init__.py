@@ -187,6 +187,26 @@ def set_num_threads(n):
     lib().rfo_set_num_threads(C.c_int(int(n)))
 
 
+def host_threads(cap=64):
+    """A FIXED thread count for the CPU arms of bench.py: the cores this process may actually use --
+    min(scheduler affinity, cgroup CPU quota, cap) -- so that the reference arm's denominator does not
+    depend on a timing probe (round 1: the auto-tuned count moved the baseline by +-25 % between runs)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:                                   # cgroup v2: "<quota> <period>" or "max <period>"
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        try:                               # cgroup v1
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return max(1, min(n, cap))
+
+
 def autotune_threads(probe, candidates=None):
     """Pick the OpenMP thread count that runs `probe()` fastest (containers often grant fewer
     cores than os.cpu_count() reports).  Returns (threads, seconds)."""

@@ -10,7 +10,8 @@ SO_PATH = os.path.join(_HERE, "librf_b200.so")
 
 RF_OK, RF_ERR_INVALID, RF_ERR_CUDA, RF_ERR_UNSUPPORTED = 0, -1, -2, -3
 COMBINER = {"sum": 0, "avg": 1, "min": 2, "max": 3}
-MASK_NONE, MASK_EMPTY_STRING, MASK_INT_VALUE = 0, 1, 2
+MASK_NONE, MASK_EMPTY_STRING, MASK_INT_VALUE, MASK_STRING_VALUE = 0, 1, 2, 3
+MAX_MASK_BYTES = 32
 MAX_TABLES = 2
 FIELD_PARTIAL = 1
 
@@ -26,7 +27,8 @@ class FieldDesc(C.Structure):
                 ("bag_len", C.c_int32), ("n_tables", C.c_int32), ("tables", TableDesc * MAX_TABLES),
                 ("dim", C.c_int32), ("combiner", C.c_int32), ("mask_mode", C.c_int32), ("flags", C.c_int32),
                 ("int_mask_value", C.c_int64), ("out", C.c_void_p), ("out_stride", C.c_int64),
-                ("ids_out", C.c_void_p)]
+                ("ids_out", C.c_void_p), ("mask_bytes", C.c_uint8 * MAX_MASK_BYTES), ("mask_len", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class VocabDesc(C.Structure):
@@ -76,6 +78,9 @@ def lib():
         L.rf_debug_fastmod.argtypes = [C.c_uint64, C.c_uint64]
         L.rf_hash_strings.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                       C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.rf_hash_strings_masked.restype = C.c_int
+        L.rf_hash_strings_masked.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_char_p, C.c_int32, C.c_int,
+                                             C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
         L.rf_hash_int64.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_int,
                                     C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
         L.rf_bag_forward.argtypes = [C.POINTER(FieldDesc), C.c_int, C.c_int64, C.c_void_p]
@@ -147,6 +152,18 @@ def check(rc):
     if rc == RF_ERR_UNSUPPORTED:
         raise NotImplementedError(msg)
     raise NativeError(msg)
+
+
+def string_mask(mask_value):
+    """Keras `Hashing(mask_value=...)` for string keys -> (rf_mask_mode, mask bytes)."""
+    if mask_value is None:
+        return MASK_NONE, b""
+    raw = mask_value if isinstance(mask_value, bytes) else str(mask_value).encode("utf-8")
+    if len(raw) == 0:
+        return MASK_EMPTY_STRING, b""
+    if len(raw) > MAX_MASK_BYTES:
+        raise NotImplementedError(f"a string mask_value takes at most {MAX_MASK_BYTES} bytes, got {len(raw)}")
+    return MASK_STRING_VALUE, raw
 
 
 def launch_count():

@@ -178,7 +178,7 @@ class EmbeddingBag(Layer):
 
 
 def _bags_forward(bags, combiner, B, L, keys=None, ids=None, salts=None, mask_mode=nat.MASK_NONE,
-                  int_mask_value=0, out=None):
+                  int_mask_value=0, out=None, mask_bytes=b""):
     """Shared body of EmbeddingBag.call / DoubleHashingEmbedding.call for every combiner."""
     T, D = len(bags), bags[0].output_dim
     dev = bags[0].embeddings.device
@@ -189,13 +189,13 @@ def _bags_forward(bags, combiner, B, L, keys=None, ids=None, salts=None, mask_mo
         if L == 0 or B == 0:
             return out.zero_()
         bag_forward([FieldCall(tables, D, combiner, keys=keys, ids=ids, mask_mode=mask_mode,
-                               int_mask_value=int_mask_value, out=out, bag_len=L)], B)
+                               int_mask_value=int_mask_value, out=out, bag_len=L, mask_bytes=mask_bytes)], B)
         return out
     # null / first / last: a plain gather -- every item is its own bag
     rows = torch.empty(B * L, T * D, dtype=torch.float32, device=dev)
     if B * L:
         bag_forward([FieldCall(tables, D, "sum", keys=keys, ids=ids, mask_mode=mask_mode,
-                               int_mask_value=int_mask_value, out=rows, bag_len=1)], B * L)
+                               int_mask_value=int_mask_value, out=rows, bag_len=1, mask_bytes=mask_bytes)], B * L)
     rows = rows.view(B, L, T, D)
     if combiner == "null":          # concat([E1, E2], axis=1) of two [B, L, D] tensors
         return rows.permute(0, 2, 1, 3).reshape(B, T * L, D)
@@ -236,31 +236,31 @@ class DoubleHashingEmbedding(Layer):
 
     def field_call(self, keys, out):
         """The FieldCall of this layer for a fused multi-field launch (pooled combiners only)."""
-        mode, imask = self._mask(keys)
+        mode, imask, raw = self._mask(keys)
         tables = [(self.emb1.embeddings.data, self.num_bins, self.hash1.salt),
                   (self.emb2.embeddings.data, self.num_bins, self.hash2.salt)]
         return FieldCall(tables, self.output_dim, self.combiner, keys=keys, mask_mode=mode, int_mask_value=imask,
-                         out=out, bag_len=_batch_and_len(keys)[1])
+                         out=out, bag_len=_batch_and_len(keys)[1], mask_bytes=raw)
 
     def _mask(self, keys):
+        """(rf_mask_mode, integer mask value, mask string bytes) for these keys."""
         if self.mask_value is None:
-            return nat.MASK_NONE, 0
+            return nat.MASK_NONE, 0, b""
         if isinstance(keys, StringColumn):
-            if self.mask_value != "":
-                raise NotImplementedError("string keys support mask_value '' only (what get_preprocess_layers passes)")
-            return nat.MASK_EMPTY_STRING, 0
+            mode, raw = nat.string_mask(self.mask_value)
+            return mode, 0, raw
         if isinstance(self.mask_value, str):
             raise ValueError(f"integer keys cannot be compared with the string mask_value {self.mask_value!r}")
-        return nat.MASK_INT_VALUE, int(self.mask_value)
+        return nat.MASK_INT_VALUE, int(self.mask_value), b""
 
     def call(self, inputs, *args, **kwargs):
         self.emb1._check_combiner()
         keys = as_keys(inputs)
         self.build(keys.device)
-        mode, imask = self._mask(keys)
+        mode, imask, raw = self._mask(keys)
         B, L = _batch_and_len(keys)
         return _bags_forward([self.emb1, self.emb2], self.combiner, B, L, keys=keys,
-                             salts=[self.hash1.salt, self.hash2.salt], mask_mode=mode, int_mask_value=imask)
+                             salts=[self.hash1.salt, self.hash2.salt], mask_mode=mode, int_mask_value=imask, mask_bytes=raw)
 
     def get_weights(self):
         return self.emb1.get_weights() + self.emb2.get_weights()

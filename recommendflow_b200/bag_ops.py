@@ -24,7 +24,7 @@ class FieldCall(object):
 
     def __init__(self, tables, dim, combiner="sum", keys=None, ids=None, mask_mode=nat.MASK_NONE,
                  int_mask_value=0, out=None, ids_out=None, bag_len=None, bag_offsets=None, n_items=None, flags=0,
-                 bag_ends=None):
+                 bag_ends=None, mask_bytes=b""):
         self.tables, self.dim, self.combiner = tables, dim, combiner
         self.keys, self.ids = keys, ids
         self.mask_mode, self.int_mask_value = mask_mode, int_mask_value
@@ -32,6 +32,7 @@ class FieldCall(object):
         self.bag_len, self.bag_offsets, self.n_items = bag_len, bag_offsets, n_items
         self.flags = flags
         self.bag_ends = bag_ends
+        self.mask_bytes = mask_bytes      # MASK_STRING_VALUE: the mask string (Keras Hashing(mask_value="..."))
 
 
 def _require_cuda(t, what):
@@ -114,6 +115,12 @@ def _fill(desc, call, batch):
     desc.dim = call.dim
     desc.combiner = nat.COMBINER[call.combiner]
     desc.mask_mode = call.mask_mode
+    if call.mask_mode == nat.MASK_STRING_VALUE:
+        raw = bytes(call.mask_bytes)
+        if len(raw) > nat.MAX_MASK_BYTES:
+            raise NotImplementedError(f"a string mask_value takes at most {nat.MAX_MASK_BYTES} bytes")
+        C.memmove(desc.mask_bytes, raw, len(raw))
+        desc.mask_len = len(raw)
     desc.flags = call.flags
     desc.int_mask_value = int(call.int_mask_value)
     if call.dim > 0:
@@ -169,20 +176,21 @@ def bag_forward(calls, batch, stream=None):
 
 def hash_strings(col, num_bins, mask_value=None, salt=None):
     """Keras `Hashing(num_bins, mask_value, salt)` on a StringColumn -> int64 ids shaped like it."""
-    if mask_value not in (None, ""):
-        raise NotImplementedError("only mask_value in (None, '') is supported for string keys "
-                                  "(get_preprocess_layers always passes '')")
+    mode, raw = nat.string_mask(mask_value)
     _require_cuda(col.data, "string arena")
     out = torch.empty(col.n_items, dtype=torch.int64, device=col.device)
     strong, k0, k1 = nat.salt_to_key(salt)
-    mode = nat.MASK_NONE if mask_value is None else nat.MASK_EMPTY_STRING
     if num_bins is None or num_bins <= 0:
         raise ValueError("`num_bins` cannot be `None` or non-positive values.")
     if col.n_items:
+        stream = C.c_void_p(torch.cuda.current_stream(col.device).cuda_stream)
         with torch.cuda.device(col.device):
-            nat.check(nat.lib().rf_hash_strings(col.data.data_ptr(), col.offsets.data_ptr(), col.n_items, int(num_bins),
-                                                mode, strong, k0, k1, out.data_ptr(),
-                                                C.c_void_p(torch.cuda.current_stream(col.device).cuda_stream)))
+            if mode == nat.MASK_STRING_VALUE:     # any other string: the kernel compares the key bytes with it
+                nat.check(nat.lib().rf_hash_strings_masked(col.data.data_ptr(), col.offsets.data_ptr(), col.n_items,
+                                                           int(num_bins), raw, len(raw), strong, k0, k1, out.data_ptr(), stream))
+            else:
+                nat.check(nat.lib().rf_hash_strings(col.data.data_ptr(), col.offsets.data_ptr(), col.n_items, int(num_bins),
+                                                    mode, strong, k0, k1, out.data_ptr(), stream))
     return out.view(col.shape) if col.shape[1] is not None else out
 
 

@@ -70,8 +70,23 @@ struct DevField {
     int32_t tile_begin;
     int32_t vec_ok;      // 128-bit path usable (dim % 4 == 0, aligned pointers/strides)
     int32_t flags;
+    uint32_t mask_words[RF_MAX_MASK_BYTES / 4];   // RF_MASK_STRING_VALUE: the mask string, zero padded
+    int32_t mask_len;
+    int32_t pad_;
     DevTable t[RF_MAX_TABLES_PER_FIELD];
 };
+
+// key == mask string?  (RF_MASK_STRING_VALUE; lengths already equal)
+template <class Src>
+__device__ __forceinline__ bool equals_mask(const Src &src, uint32_t len, const uint32_t *mask_words) {
+    bool same = true;
+    for (uint32_t p = 0; p < len; p += 4) {
+        const uint32_t rem = len - p;
+        const uint32_t keep = rem >= 4 ? 0xffffffffu : ((1u << (rem * 8)) - 1u);
+        same = same && ((fetch32(src, p) & keep) == (mask_words[p >> 2] & keep));
+    }
+    return same;
+}
 
 // ------------------------------------------------------------------------------------------
 // pooling primitives.  Two code shapes only: ADD (sum / avg) and SELECT (min / max, picked by a
@@ -527,7 +542,16 @@ __device__ __forceinline__ void bag_forward_body(const DevField *__restrict__ fi
                     for (int j = tid; j < n_sub; j += kThreads) {
                         const int32_t o = sm.soff[j];
                         const uint32_t len = (uint32_t)(sm.soff[j + 1] - o);
-                        const bool is_mask = F.mask_mode == RF_MASK_EMPTY_STRING && len == 0;
+                        bool is_mask = F.mask_mode == RF_MASK_EMPTY_STRING && len == 0;
+                        if (F.mask_mode == RF_MASK_STRING_VALUE && len == (uint32_t)F.mask_len) {
+                            if (staged) {
+                                is_mask = equals_mask(WordSrcShared{sm.stage, shift + (uint32_t)(o - byte0)}, len, F.mask_words);
+                            } else {
+                                const uintptr_t a = reinterpret_cast<uintptr_t>(F.bytes) + (uintptr_t)o;
+                                is_mask = equals_mask(WordSrcGlobal{reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3), (uint32_t)(a & 3u)},
+                                                      len, F.mask_words);
+                            }
+                        }
                         for (int t = 0; t < T; ++t) {
                             uint32_t id;
                             if (staged) {
@@ -737,10 +761,13 @@ static int build_field(DevField &d, const rf_field_desc &f, int64_t batch, int f
     if (f.dim > 0 && !f.out) return set_error(RF_ERR_INVALID, "field %d: out pointer is NULL", fi);
     if (f.combiner < RF_COMBINER_SUM || f.combiner > RF_COMBINER_MAX)
         return set_error(RF_ERR_INVALID, "field %d: Do not support combiner = %d", fi, f.combiner);
-    if (f.mask_mode < RF_MASK_NONE || f.mask_mode > RF_MASK_INT_VALUE)
+    if (f.mask_mode < RF_MASK_NONE || f.mask_mode > RF_MASK_STRING_VALUE)
         return set_error(RF_ERR_INVALID, "field %d: bad mask_mode", fi);
     if (f.bytes && f.mask_mode == RF_MASK_INT_VALUE) return set_error(RF_ERR_INVALID, "field %d: integer mask on string keys", fi);
-    if (f.int_values && f.mask_mode == RF_MASK_EMPTY_STRING) return set_error(RF_ERR_INVALID, "field %d: string mask on integer keys", fi);
+    if (f.int_values && (f.mask_mode == RF_MASK_EMPTY_STRING || f.mask_mode == RF_MASK_STRING_VALUE))
+        return set_error(RF_ERR_INVALID, "field %d: string mask on integer keys", fi);
+    if (f.mask_mode == RF_MASK_STRING_VALUE && (f.mask_len < 0 || f.mask_len > RF_MAX_MASK_BYTES))
+        return set_error(RF_ERR_UNSUPPORTED, "field %d: a string mask_value takes at most %d bytes", fi, RF_MAX_MASK_BYTES);
     if (!f.bag_offsets && f.bag_len < 0) return set_error(RF_ERR_INVALID, "field %d: negative bag_len", fi);
     if (f.bag_ends && !f.bag_offsets) return set_error(RF_ERR_INVALID, "field %d: bag_ends given without bag_offsets", fi);
     if (f.bag_ends && (!f.ids || f.n_tables != 1))
@@ -763,6 +790,14 @@ static int build_field(DevField &d, const rf_field_desc &f, int64_t batch, int f
     d.n_tables = f.n_tables;
     d.combiner = f.combiner;
     d.mask_mode = f.mask_mode;
+    if (f.mask_mode == RF_MASK_STRING_VALUE) {
+        if (f.mask_len == 0) {
+            d.mask_mode = RF_MASK_EMPTY_STRING;      // mask_value="" is the length test alone
+        } else {
+            memcpy(d.mask_words, f.mask_bytes, (size_t)f.mask_len);
+            d.mask_len = f.mask_len;
+        }
+    }
     d.flags = f.flags;
     bool aligned = (f.dim % 4 == 0) && (reinterpret_cast<uintptr_t>(f.out) % 16 == 0) && (f.out_stride % 4 == 0);
     for (int t = 0; t < f.n_tables; ++t) {
@@ -832,6 +867,22 @@ int rf_hash_strings(const uint8_t *d_bytes, const int32_t *d_str_offsets, int64_
     f.bytes = d_bytes;
     f.str_offsets = d_str_offsets;
     return hash_only(f, n_items, num_bins, mask_mode, use_strong, key0, key1, d_ids_out, stream);
+}
+
+int rf_hash_strings_masked(const uint8_t *d_bytes, const int32_t *d_str_offsets, int64_t n_items, int64_t num_bins,
+                           const uint8_t *h_mask_value, int32_t mask_len, int use_strong, uint64_t key0, uint64_t key1,
+                           int64_t *d_ids_out, void *stream) {
+    rf_field_desc f;
+    memset(&f, 0, sizeof(f));
+    if (n_items > 0 && (!d_bytes || !d_str_offsets)) return set_error(RF_ERR_INVALID, "bytes / str_offsets is NULL");
+    if (mask_len < 0 || mask_len > RF_MAX_MASK_BYTES)
+        return set_error(RF_ERR_UNSUPPORTED, "a string mask_value takes at most %d bytes", RF_MAX_MASK_BYTES);
+    if (mask_len > 0 && !h_mask_value) return set_error(RF_ERR_INVALID, "mask_value is NULL");
+    f.bytes = d_bytes;
+    f.str_offsets = d_str_offsets;
+    if (mask_len > 0) memcpy(f.mask_bytes, h_mask_value, (size_t)mask_len);
+    f.mask_len = mask_len;
+    return hash_only(f, n_items, num_bins, RF_MASK_STRING_VALUE, use_strong, key0, key1, d_ids_out, stream);
 }
 
 int rf_hash_int64(const int64_t *d_values, int64_t n_items, int64_t num_bins, int mask_mode, int64_t int_mask_value,

@@ -10,6 +10,7 @@ from . import _native as nat
 # Ampere and later GPUs); "fp32": exact CUDA-core accumulation.  Shapes the tensor-core kernels do
 # not take use the fp32 kernels.
 DEFAULT_PRECISION = "tf32"
+TC_PRECISIONS = ("tf32",)          # operand formats the tensor-core kernels take
 
 
 def _f32(t, what):

@@ -27,13 +27,13 @@ def test_library_exports_every_declared_symbol():
     assert "rf_bag_forward" in names and "rf_hash_strings" in names and len(names) >= 7
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/rf_b200.h but not exported"
-    assert lib.rf_abi_version() == 1
+    assert lib.rf_abi_version() == 2
 
 
 def test_struct_layout_matches_header_sizes():
     # rf_table_desc: ptr + i64 + 2*i32 + 2*u64 = 40 bytes; rf_field_desc packs without surprises
     assert ctypes.sizeof(nat.TableDesc) == 40
-    assert ctypes.sizeof(nat.FieldDesc) == 6 * 8 + 8 + 8 + 2 * 40 + 16 + 8 + 8 + 8 + 8
+    assert ctypes.sizeof(nat.FieldDesc) == 6 * 8 + 8 + 8 + 2 * 40 + 16 + 8 + 8 + 8 + 8 + 32 + 8
     assert nat.FieldDesc.tables.offset == 64 and nat.FieldDesc.out.offset == 168
 
 
@@ -76,7 +76,7 @@ def test_header_is_plain_c_and_ctypes_structs_match_it(tmp_path):
     checks = {"rf_table_desc": (nat.TableDesc, ["weights", "num_bins", "use_strong", "key0", "key1"]),
               "rf_field_desc": (nat.FieldDesc, ["bytes", "str_offsets", "int_values", "ids", "bag_offsets", "bag_ends", "n_items",
                                                 "bag_len", "n_tables", "tables", "dim", "combiner", "mask_mode", "flags",
-                                                "int_mask_value", "out", "out_stride", "ids_out"]),
+                                                "int_mask_value", "out", "out_stride", "ids_out", "mask_bytes", "mask_len"]),
               "rf_vocab_desc": (nat.VocabDesc, ["term_bytes", "term_offsets", "term_ints", "slots", "capacity", "n_terms"]),
               "rf_adam_params": (nat.AdamParams, ["lr", "beta1", "beta2", "epsilon", "step", "lazy"]),
               "rf_example_column": (nat.ExampleColumn, ["name", "name_len", "kind", "n_values", "n_bytes", "row_counts", "bytes_out",

@@ -208,3 +208,115 @@ def test_inbatch_softmax_ce_backward_matches_autograd(B, D, precision):
     qh = q.clone().requires_grad_(True)
     inbatch_softmax_ce_autograd(y, qh, d, 20.0, "fp32").backward()
     np.testing.assert_allclose(qh.grad.cpu().numpy(), (q64.grad / 3.0).float().cpu().numpy(), rtol=1e-3, atol=2e-6)
+
+
+# ---- every two-tower loss is connected to the autograd graph (only the scaled CE was) ---------------
+def _ref_losses64():
+    """float64 torch restatements of /root/reference/backend/lossess/match_losses.py (B x B materialised)."""
+    def S(q, d):
+        return q @ d.t()
+
+    def pairwise(s, y, positive_only):
+        diff = s[:, None] - s[None, :]
+        keep = y[:, None] < y[None, :]
+        if positive_only:
+            keep = keep & (diff > 0)
+        flat = torch.where(keep, diff, torch.full_like(diff, -1e12)).reshape(-1)
+        return torch.logsumexp(torch.cat([torch.zeros(1, dtype=s.dtype, device=s.device), flat]), dim=0)
+
+    def ce(y, q, d):
+        s = S(q, d)
+        p = torch.clamp(torch.diagonal(s) / s.sum(dim=1), 1e-7, 1 - 1e-7)
+        return torch.mean(-y * torch.log(p) * y)
+
+    def sym_ce(y, q, d):
+        s = S(q, d)
+        p1 = torch.clamp(torch.diagonal(s) / s.sum(dim=1), 1e-7, 1 - 1e-7)
+        p2 = torch.clamp(torch.diagonal(s) / s.sum(dim=0), 1e-7, 1 - 1e-7)
+        return torch.mean(0.5 * (-y * torch.log(p1) - y * torch.log(p2)) * y)
+
+    def scaled(y, q, d, scale=20.0):
+        s = S(q, d) * scale
+        return torch.mean(-(torch.diagonal(s) - torch.logsumexp(s, dim=1)) * y)
+
+    def margin_rank(y, q, d, margin=0.1):
+        s = S(q, d)
+        return (torch.clamp(s - torch.diagonal(s)[:, None] + margin, 0, 1e14) * y[None, :]).sum()
+
+    def hard_rank(y, q, d, margin=0.1):
+        s = S(q, d)
+        neg = s - torch.diag(torch.diagonal(s))
+        return (torch.clamp(neg.max(dim=1).values - torch.diagonal(s) + margin, 0, 1e14) * y).sum()
+
+    diag = lambda q, d: (q * d).sum(dim=1)
+    return {
+        "mean_squared_error": lambda y, q, d: torch.mean((y - diag(q, d)) ** 2),
+        "binary_cross_entropy": lambda y, q, d: (-(y * torch.log(torch.clamp(diag(q, d), 1e-7, 1 - 1e-7)) + (1 - y) * torch.log(
+            1 - torch.clamp(diag(q, d), 1e-7, 1 - 1e-7)))).sum(),
+        "cosent_loss": lambda y, q, d: pairwise(diag(q, d) * 20, y, False),
+        "cosent_loss_v2": lambda y, q, d: pairwise(diag(q, d) * 20, y, True),
+        "batch_neg_sample_ce_loss": ce,
+        "batch_neg_sample_symmetrical_ce_loss": sym_ce,
+        "batch_neg_sample_scaled_multi_class_ce_loss": scaled,
+        "batch_neg_sample_symmetrical_scaled_multi_class_ce_loss": lambda y, q, d: scaled(y, q, d, 400.0),
+        "batch_neg_sample_margin_rank_loss": margin_rank,
+        "batch_hard_neg_sample_margin_rank_loss": hard_rank,
+    }
+
+
+@pytest.mark.parametrize("name", sorted(_ref_losses64()))
+def test_every_loss_value_and_gradient_match_float64_autograd(name):
+    """loss.backward() reaches query AND doc through every term of the loss (rtol 2e-3 on the gradients: fp32 / TF32
+    contractions against float64; the symmetric scaled loss runs at temperature 400, where TF32 logits move the
+    softmax visibly, so it is checked on the exact-fp32 kernel)."""
+    import recommendflow_b200.dense_ops as dense_ops
+    rng = np.random.default_rng(len(name))
+    B, D = 300, 64
+    q = rng.standard_normal((B, D)); d = rng.standard_normal((B, D))
+    if name in ("batch_neg_sample_ce_loss", "batch_neg_sample_symmetrical_ce_loss", "binary_cross_entropy"):
+        q, d = np.abs(q), np.abs(d)                      # keep the "probabilities" positive like trained towers would
+    q /= np.linalg.norm(q, axis=1, keepdims=True); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    y = (rng.uniform(size=B) > 0.4).astype(np.float64) if "cosent" not in name else rng.integers(0, 4, size=B).astype(np.float64)
+    q64 = torch.tensor(q, dtype=torch.float64, device="cuda", requires_grad=True)
+    d64 = torch.tensor(d, dtype=torch.float64, device="cuda", requires_grad=True)
+    want = _ref_losses64()[name](torch.tensor(y, device="cuda"), q64, d64)
+    want.backward()
+    q32 = torch.tensor(q, dtype=torch.float32, device="cuda", requires_grad=True)
+    d32 = torch.tensor(d, dtype=torch.float32, device="cuda", requires_grad=True)
+    old = dense_ops.DEFAULT_PRECISION
+    dense_ops.DEFAULT_PRECISION = "fp32"
+    try:
+        got = getattr(match_losses, name)(torch.tensor(y, dtype=torch.float32, device="cuda"), q32, d32)
+        if got.dim():                                     # binary_cross_entropy returns the per-row vector (:35-39)
+            got = got.sum()
+        got.backward()
+    finally:
+        dense_ops.DEFAULT_PRECISION = old
+    assert q32.grad is not None and d32.grad is not None, "loss is detached from query / doc"
+    np.testing.assert_allclose(got.item(), want.item(), rtol=2e-4, atol=1e-5)
+    scale = max(q64.grad.abs().max().item(), d64.grad.abs().max().item(), 1e-12)
+    np.testing.assert_allclose(q32.grad.double().cpu().numpy() / scale, q64.grad.cpu().numpy() / scale, rtol=0, atol=2e-3)
+    np.testing.assert_allclose(d32.grad.double().cpu().numpy() / scale, d64.grad.cpu().numpy() / scale, rtol=0, atol=2e-3)
+
+
+def test_aux_label_cosent_losses_match_reference_formula():
+    """aux_label_cosent_loss / pos_aux_label_cosent_loss (match_losses.py:72-116): cosent_v2 over the positive
+    (and negative) subsets of the batch, on the auxiliary label."""
+    rng = np.random.default_rng(77)
+    B, D = 64, 16
+    q = rng.standard_normal((B, D)); d = rng.standard_normal((B, D))
+    q /= np.linalg.norm(q, axis=1, keepdims=True); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    y = (rng.uniform(size=B) > 0.5).astype(np.float32)
+    aux = rng.uniform(size=B).astype(np.float32)
+
+    def v2(idx):
+        s = (q[idx] * d[idx]).sum(axis=1) * 20
+        diff = s[:, None] - s[None, :]
+        keep = (aux[idx][:, None] < aux[idx][None, :]) & (diff > 0)
+        return np.log(1.0 + np.exp(diff[keep]).sum())
+
+    pos, neg = np.nonzero(y == 1)[0], np.nonzero(y == 0)[0]
+    args = [torch.tensor(x, dtype=torch.float32, device="cuda") for x in (y, aux, q, d)]
+    np.testing.assert_allclose(match_losses.pos_aux_label_cosent_loss(*args).item(), v2(pos), rtol=1e-4)
+    np.testing.assert_allclose(match_losses.aux_label_cosent_loss(*args, alpha=0.3).item(), 0.7 * v2(pos) + 0.3 * v2(neg), rtol=1e-4)
+    assert match_losses.pos_aux_label_cosent_loss(torch.zeros(B, device="cuda"), *args[1:]).item() == 0.0

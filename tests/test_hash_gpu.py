@@ -13,7 +13,7 @@ from tests.test_oracle_kat import KERAS_KATS
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("values,num_bins,mask,salt,want", [k for k in KERAS_KATS if k[2] in (None, "")])
+@pytest.mark.parametrize("values,num_bins,mask,salt,want", KERAS_KATS)
 def test_public_kats_on_gpu(values, num_bins, mask, salt, want):
     layer = Hashing(num_bins, mask_value=mask, salt=salt)
     if isinstance(values[0], int):
@@ -32,6 +32,44 @@ def test_random_strings_every_length_branch(salt, num_bins, mask):
     want = oracle.hash_strings(arena, offs, num_bins, mask, salt)
     got = hash_strings(column(arena, offs, (6000, 1)), num_bins, mask, salt).view(-1).cpu().numpy()
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("salt", [None, [133, 137]])
+@pytest.mark.parametrize("mask", ["omar", "x", "0123456789abcdef0123456789abcdef", "ab\x00cd", "日本"])
+def test_arbitrary_string_mask_value(mask, salt):
+    """Keras Hashing(mask_value="<string>"): keys whose BYTES equal the mask go to bucket 0, everything else to
+    1 + h mod (N - 1) -- prefixes, extensions and same-length near misses of the mask included."""
+    rng = np.random.default_rng(len(mask))
+    raw = mask.encode("utf-8")
+    near = [raw, raw[:-1], raw + b"!", raw[:-1] + bytes([raw[-1] ^ 1]), b"", raw * 2, bytes([raw[0] ^ 0x20]) + raw[1:]]
+    vals = [near[i % len(near)] if i % 3 == 0 else bytes(rng.integers(1, 256, size=rng.integers(0, 40), dtype=np.uint8)) for i in range(4000)]
+    arena, offs = oracle.encode_strings(vals)
+    want = oracle.hash_strings(arena, offs, 1000, raw, salt)
+    assert (want == 0).sum() >= 4000 // 21
+    got = hash_strings(column(arena, offs, (4000, 1)), 1000, mask, salt).view(-1).cpu().numpy()
+    assert np.array_equal(got, want)
+    # the staged (shared-memory) and unstaged (global-memory) byte sources agree: long filler keys force the latter
+    vals2 = [v if i % 2 else v + b"#" * 600 for i, v in enumerate(vals)]
+    arena2, offs2 = oracle.encode_strings(vals2)
+    got2 = hash_strings(column(arena2, offs2, (4000, 1)), 1000, mask, salt).view(-1).cpu().numpy()
+    assert np.array_equal(got2, oracle.hash_strings(arena2, offs2, 1000, raw, salt))
+    with pytest.raises(NotImplementedError):
+        hash_strings(column(arena, offs, (4000, 1)), 1000, "m" * 33, salt)
+
+
+def test_double_hashing_layer_with_string_mask_value():
+    from recommendflow_b200.backend.layers.preprocess_layers import DoubleHashingEmbedding
+    rng = np.random.default_rng(5)
+    B, L, N, D = 64, 3, 500, 8
+    rows = [[("pad" if rng.uniform() < 0.3 else f"k{rng.integers(0, 1000)}") for _ in range(L)] for _ in range(B)]
+    layer = DoubleHashingEmbedding(num_bins=N, output_dim=D, seeds=[2022, 2023], combiner="avg", mask_value="pad", name="h")
+    ws = [rng.uniform(-0.05, 0.05, size=(N, D)).astype(np.float32) for _ in range(2)]
+    layer.set_weights(ws)
+    got = layer(rows).cpu().numpy()
+    arena, offs = oracle.encode_strings([x for r in rows for x in r])
+    want = np.concatenate([oracle.bag_pool(oracle.hash_strings(arena, offs, N, b"pad", s), w, "avg", L=L)
+                           for s, w in zip([2022, 2023], ws)], axis=1)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
 def test_long_keys_take_the_unstaged_path():
