@@ -66,6 +66,11 @@ typedef struct rf_table_desc {
 /* rf_field_desc.flags: this launch produces PARTIAL pools (row-sharded tables): an empty bag    */
 /* yields the combiner's identity (+/-inf for min/max) instead of 0.                             */
 #define RF_FIELD_PARTIAL 1
+/* The pooled vector is ADDED into `out` (red.global.add, also over NVLink peer pointers) instead of  */
+/* stored; empty bags add nothing.  sum / avg only; must be set on every field of a launch or none.  */
+/* `out` must be zeroed (or hold the running value) before the launch.  Summation order across       */
+/* concurrent launches / owners is free, i.e. results are not bit-reproducible.                       */
+#define RF_FIELD_ACCUMULATE 2
 
 /* One feature field of one batch: replaces `DoubleHashingEmbedding.call`
  * (preprocess_layers.py:94-97; n_tables == 2) or `EmbeddingBag.call` (:66-68; pre-hashed
@@ -124,6 +129,12 @@ int rf_hash_strings_masked(const uint8_t *d_bytes, const int32_t *d_str_offsets,
 /* (models/matching/que2search.py:68,76-79) over the layers built by get_preprocess_layers     */
 /* (backend/utils/preprocess_utils.py:7-20).                                                   */
 int rf_bag_forward(const rf_field_desc *fields, int n_fields, int64_t batch, void *stream);
+/* Same, with the grid capped at max_ctas_per_sm x #SMs for THIS launch (0 = no cap): the kernel then walks */
+/* its tiles grid-stride and leaves room on every SM for kernels of other streams (sharded pipeline).      */
+int rf_bag_forward_ex(const rf_field_desc *fields, int n_fields, int64_t batch, int max_ctas_per_sm, void *stream);
+/* Launches recorded into CUDA graphs keep a descriptor slot each (256 per device).  Call this after the   */
+/* graphs that hold them were destroyed to hand all slots back.                                             */
+int rf_release_captured_launches(void);
 
 /* ---- scaled_dot_product_attention (backend/layers/layer_utils.py:4-24), exact fp32 ------------ */
 /* q, k, v, out: device [n_batch_heads, seq_len, head_dim] fp32; mask: device [n_batch_heads,    */

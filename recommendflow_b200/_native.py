@@ -14,6 +14,7 @@ MASK_NONE, MASK_EMPTY_STRING, MASK_INT_VALUE, MASK_STRING_VALUE = 0, 1, 2, 3
 MAX_MASK_BYTES = 32
 MAX_TABLES = 2
 FIELD_PARTIAL = 1
+FIELD_ACCUMULATE = 2
 
 
 class TableDesc(C.Structure):
@@ -84,6 +85,9 @@ def lib():
         L.rf_hash_int64.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_int,
                                     C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
         L.rf_bag_forward.argtypes = [C.POINTER(FieldDesc), C.c_int, C.c_int64, C.c_void_p]
+        L.rf_bag_forward_ex.restype = C.c_int
+        L.rf_bag_forward_ex.argtypes = [C.POINTER(FieldDesc), C.c_int, C.c_int64, C.c_int, C.c_void_p]
+        L.rf_release_captured_launches.restype = C.c_int
         L.rf_bag_backward.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
                                       C.c_int, C.c_float, C.c_void_p, C.c_void_p]
         L.rf_sdpa_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,

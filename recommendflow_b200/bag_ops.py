@@ -156,21 +156,24 @@ class BagPlan(object):
         if any(t.device != self.device for t in self.keep):
             raise ValueError("all tensors of one launch must be on the same device")
 
-    def launch(self, stream=None):
+    def launch(self, stream=None, max_ctas_per_sm=0):
+        """max_ctas_per_sm > 0 caps this launch's grid (the kernel walks its tiles grid-stride), leaving room on
+        every SM for kernels of other streams."""
         if self.n == 0 or self.batch == 0:
             return
         if stream is None:
             stream = torch.cuda.current_stream(self.device)
         with torch.cuda.device(self.device):
-            nat.check(nat.lib().rf_bag_forward(self.descs, self.n, self.batch, C.c_void_p(stream.cuda_stream)))
+            nat.check(nat.lib().rf_bag_forward_ex(self.descs, self.n, self.batch, int(max_ctas_per_sm),
+                                                  C.c_void_p(stream.cuda_stream)))
 
 
-def bag_forward(calls, batch, stream=None):
+def bag_forward(calls, batch, stream=None, max_ctas_per_sm=0):
     """Run every FieldCall of one batch through a single rf_bag_forward launch."""
     if not calls or batch == 0:
         return
     plan = BagPlan(calls, batch)
-    plan.launch(stream)
+    plan.launch(stream, max_ctas_per_sm)
     return plan.keep
 
 

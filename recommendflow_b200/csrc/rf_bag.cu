@@ -134,6 +134,29 @@ struct PoolOp {
 
 __device__ __forceinline__ float4 ldg_row(const float4 *p) { return __ldg(p); }
 
+// Output of one pooled vector.  ACC = false: plain store.  ACC = true (RF_FIELD_ACCUMULATE): fire-and-forget
+// reduction into the destination (red.global.add: local HBM/L2, or a peer GPU's memory over NVLink) -- the
+// owners of a row-sharded table add their partial pools straight into the source rank's zeroed buffer, so no
+// per-owner partial buffers and no combine pass exist.  The order in which owners land is free: this mode is
+// not bit-reproducible (the ordered rf_combine_partials path stays the parity path).
+template <bool ACC>
+__device__ __forceinline__ void emit4(float4 *dst, const float4 &v, bool nonempty) {
+    if (ACC) {
+        if (nonempty)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    } else {
+        *dst = v;
+    }
+}
+template <bool ACC>
+__device__ __forceinline__ void emit1(float *dst, float v, bool nonempty) {
+    if (ACC) {
+        if (nonempty) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst), "f"(v) : "memory");
+    } else {
+        *dst = v;
+    }
+}
+
 // Accumulate `cnt` rows (ids in shared memory) into acc[], in index order.  Every trip issues up
 // to U independent 128-bit row loads before the first add, also on the last (partial) trip: a
 // bag's time is ceil(cnt / U) DRAM latencies, never one latency per leftover key.
@@ -191,7 +214,7 @@ struct Smem {
 static_assert(sizeof(Smem) <= 48 * 1024, "static shared memory limit");
 static_assert(kMaxDim / 32 == 16 && sizeof(DevField) % 4 == 0, "DevField is copied word-wise");
 
-template <int NV, int K>
+template <int NV, int K, bool ACC>
 __device__ __forceinline__ void pool_round_vec(const PoolOp &op, const DevField &F, Smem &sm, const Round &R,
                                                int tile_bag0) {
     const uint32_t row_vecs = (uint32_t)F.dim >> 2;
@@ -250,7 +273,7 @@ __device__ __forceinline__ void pool_round_vec(const PoolOp &op, const DevField 
         for (int v = 0; v < NV; ++v) {
             const uint32_t c = lg + v * G;
             op.finish4<K>(acc[v], hi - lo);
-            if (c < row_vecs) o[c] = acc[v];
+            if (c < row_vecs) emit4<ACC>(o + c, acc[v], hi > lo);
         }
     }
 }
@@ -259,7 +282,7 @@ __device__ __forceinline__ void pool_round_vec(const PoolOp &op, const DevField 
 // keeping NB * L (6..8) independent 128-bit row loads in flight per lane instead of L, because
 // this phase is bound by DRAM latency x dependent rounds.  Same in-order pooling per bag.
 // With T == 2 the table index of a lane group never changes (its work items keep their parity).
-template <int K, int NB, int L>
+template <int K, int NB, int L, bool ACC>
 __device__ __forceinline__ void pool_round_short(const PoolOp &op, const DevField &F, const Smem &sm, const Round &R,
                                                  int tile_bag0) {
     const uint32_t row_vecs = (uint32_t)F.dim >> 2;
@@ -293,7 +316,7 @@ __device__ __forceinline__ void pool_round_short(const PoolOp &op, const DevFiel
 #pragma unroll
             for (int u = 0; u < L; ++u) op.apply4<K>(acc, r[b][u]);
             op.finish4<K>(acc, L);
-            *reinterpret_cast<float4 *>(out_base + (int64_t)((w + b * n_grp) >> wshift) * ostride) = acc;
+            emit4<ACC>(reinterpret_cast<float4 *>(out_base + (int64_t)((w + b * n_grp) >> wshift) * ostride), acc, true);
         }
     }
     for (; w < n_work; w += n_grp) {
@@ -306,13 +329,13 @@ __device__ __forceinline__ void pool_round_short(const PoolOp &op, const DevFiel
 #pragma unroll
         for (int u = 0; u < L; ++u) op.apply4<K>(acc, r[u]);
         op.finish4<K>(acc, L);
-        *reinterpret_cast<float4 *>(out_base + (int64_t)(w >> wshift) * ostride) = acc;
+        emit4<ACC>(reinterpret_cast<float4 *>(out_base + (int64_t)(w >> wshift) * ostride), acc, true);
     }
 }
 
 // Generic-D path (dim % 4 != 0 or unaligned): one warp per (bag, table), one float per lane per
 // 32-column slab, same in-order accumulation.  Long bags carry kMaxDim/32 partial slabs.
-template <int K>
+template <int K, bool ACC>
 __device__ __forceinline__ void pool_round_scalar(const PoolOp &op, const DevField &F, Smem &sm, const Round &R,
                                                   int tile_bag0) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warp = kThreads / 32;
@@ -349,32 +372,33 @@ __device__ __forceinline__ void pool_round_scalar(const PoolOp &op, const DevFie
                 carry[s] = acc;
                 continue;
             }
-            if (d < D) o[d] = op.finish<K>(acc, hi - lo);
+            if (d < D) emit1<ACC>(o + d, op.finish<K>(acc, hi - lo), hi > lo);
         }
     }
 }
 
-template <int K>
+template <int K, bool ACC>
 __device__ __noinline__ void pool_round(const PoolOp &op, const DevField &F, Smem &sm, const Round &R, int tile_bag0) {
     if (F.vec_ok) {
         const int row_vecs = F.dim >> 2;
         if (row_vecs <= 32 && !R.partial && F.boffs == nullptr && F.bag_len >= 1 && F.bag_len <= 4) {
-            if (F.bag_len == 1) pool_round_short<K, 8, 1>(op, F, sm, R, tile_bag0);
-            else if (F.bag_len == 2) pool_round_short<K, 4, 2>(op, F, sm, R, tile_bag0);
-            else if (F.bag_len == 3) pool_round_short<K, 2, 3>(op, F, sm, R, tile_bag0);
-            else pool_round_short<K, 2, 4>(op, F, sm, R, tile_bag0);
+            if (F.bag_len == 1) pool_round_short<K, 8, 1, ACC>(op, F, sm, R, tile_bag0);
+            else if (F.bag_len == 2) pool_round_short<K, 4, 2, ACC>(op, F, sm, R, tile_bag0);
+            else if (F.bag_len == 3) pool_round_short<K, 2, 3, ACC>(op, F, sm, R, tile_bag0);
+            else pool_round_short<K, 2, 4, ACC>(op, F, sm, R, tile_bag0);
         } else if (row_vecs <= 32) {
-            pool_round_vec<1, K>(op, F, sm, R, tile_bag0);
+            pool_round_vec<1, K, ACC>(op, F, sm, R, tile_bag0);
         } else if (row_vecs <= 64) {
-            pool_round_vec<2, K>(op, F, sm, R, tile_bag0);
+            pool_round_vec<2, K, ACC>(op, F, sm, R, tile_bag0);
         } else {
-            pool_round_vec<4, K>(op, F, sm, R, tile_bag0);
+            pool_round_vec<4, K, ACC>(op, F, sm, R, tile_bag0);
         }
     } else {
-        pool_round_scalar<K>(op, F, sm, R, tile_bag0);
+        pool_round_scalar<K, ACC>(op, F, sm, R, tile_bag0);
     }
 }
 
+template <bool ACC>
 __device__ __forceinline__ void bag_forward_body(const DevField *__restrict__ fields, int n_fields, int total_tiles) {
     __shared__ Smem sm;      // 46.4 KB static: 3 CTAs/SM leave most of the 228 KB carve-out to L1
     const int tid = threadIdx.x;
@@ -574,8 +598,8 @@ __device__ __forceinline__ void bag_forward_body(const DevField *__restrict__ fi
             // ---- phase C: gather + pool -----------------------------------------------------
             if (F.dim > 0) {
                 const PoolOp op{F.combiner, F.flags & RF_FIELD_PARTIAL};
-                if (F.combiner <= RF_COMBINER_AVG) pool_round<kAdd>(op, F, sm, R, tile_bag0);
-                else pool_round<kSelect>(op, F, sm, R, tile_bag0);
+                if (F.combiner <= RF_COMBINER_AVG) pool_round<kAdd, ACC>(op, F, sm, R, tile_bag0);
+                else if (!ACC) pool_round<kSelect, false>(op, F, sm, R, tile_bag0);
             }
             __syncthreads();
 
@@ -595,7 +619,15 @@ __device__ __forceinline__ void bag_forward_body(const DevField *__restrict__ fi
 template <int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) bag_forward_kernel(const DevField *__restrict__ fields, int n_fields,
                                                                      int total_tiles) {
-    bag_forward_body(fields, n_fields, total_tiles);
+    bag_forward_body<false>(fields, n_fields, total_tiles);
+}
+
+// RF_FIELD_ACCUMULATE launches (every field of the launch carries the flag): same body, outputs reduced into
+// the destination.  A separate instance so that the store path above stays byte-identical.
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) bag_forward_acc_kernel(const DevField *__restrict__ fields, int n_fields,
+                                                                         int total_tiles) {
+    bag_forward_body<true>(fields, n_fields, total_tiles);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -641,9 +673,9 @@ static DeviceState *device_state(int dev) {
 // sharded pipeline so that the routing of the next step really runs under the pooling of this one.
 static std::atomic<int> g_grid_ctas_per_sm{0};
 
-static int launch_kernel(const DevField *dptr, int nf, int tiles_i, cudaStream_t stream) {
+static int launch_kernel(const DevField *dptr, int nf, int tiles_i, int ctas_per_sm, bool acc, cudaStream_t stream) {
     int64_t tiles = tiles_i;
-    const int cap = g_grid_ctas_per_sm.load();
+    const int cap = ctas_per_sm > 0 ? ctas_per_sm : g_grid_ctas_per_sm.load();
     if (cap > 0) {
         int dev = 0, sms = 0;
         RF_CUDA(cudaGetDevice(&dev));
@@ -654,6 +686,12 @@ static int launch_kernel(const DevField *dptr, int nf, int tiles_i, cudaStream_t
     // CTAs per SM the kernel is compiled for (register cap): 4 (64 registers) measured best on
     // B200 for C2 (0.383 ms vs 0.401 @3); RF_BAG_MINB overrides for experiments.
     static const int cfg = getenv("RF_BAG_MINB") ? atoi(getenv("RF_BAG_MINB")) : 4;
+    if (acc) {
+        bag_forward_acc_kernel<4><<<(unsigned)tiles, kThreads, 0, stream>>>(dptr, nf, total_tiles);
+        RF_CUDA(cudaGetLastError());
+        g_launches.fetch_add(1);
+        return RF_OK;
+    }
     switch (cfg) {
         case 2: bag_forward_kernel<2><<<(unsigned)tiles, kThreads, 0, stream>>>(dptr, nf, total_tiles); break;
         case 3: bag_forward_kernel<3><<<(unsigned)tiles, kThreads, 0, stream>>>(dptr, nf, total_tiles); break;
@@ -665,7 +703,7 @@ static int launch_kernel(const DevField *dptr, int nf, int tiles_i, cudaStream_t
     return RF_OK;
 }
 
-static int launch_fields(std::vector<DevField> &dev_fields, cudaStream_t stream) {
+static int launch_fields(std::vector<DevField> &dev_fields, int ctas_per_sm, cudaStream_t stream) {
     int dev = 0;
     RF_CUDA(cudaGetDevice(&dev));
     DeviceState *st = device_state(dev);
@@ -695,6 +733,11 @@ static int launch_fields(std::vector<DevField> &dev_fields, cudaStream_t stream)
     }
     if (tiles == 0) return RF_OK;
     if (tiles > INT32_MAX) return set_error(RF_ERR_UNSUPPORTED, "too many tiles in one launch");
+    int n_acc = 0;
+    for (auto &f : dev_fields) n_acc += (f.flags & RF_FIELD_ACCUMULATE) ? 1 : 0;
+    if (n_acc != 0 && n_acc != (int)dev_fields.size())
+        return set_error(RF_ERR_INVALID, "RF_FIELD_ACCUMULATE must be set on every field of a launch or on none");
+    const bool acc = n_acc != 0;
 
     const size_t bytes = dev_fields.size() * sizeof(DevField);
     cudaStreamCaptureStatus capture = cudaStreamCaptureStatusNone;
@@ -708,7 +751,7 @@ static int launch_fields(std::vector<DevField> &dev_fields, cudaStream_t stream)
         st->graph_used++;
         memcpy(h, dev_fields.data(), bytes);
         RF_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream));
-        return launch_kernel(reinterpret_cast<const DevField *>(d), (int)dev_fields.size(), (int)tiles, stream);
+        return launch_kernel(reinterpret_cast<const DevField *>(d), (int)dev_fields.size(), (int)tiles, ctas_per_sm, acc, stream);
     }
     if (!st->graph_host) {
         RF_CUDA(cudaMallocHost(reinterpret_cast<void **>(&st->graph_host), kGraphSlots * kGraphSlotBytes));
@@ -730,7 +773,7 @@ static int launch_fields(std::vector<DevField> &dev_fields, cudaStream_t stream)
     memcpy(slot.host, dev_fields.data(), bytes);
     RF_CUDA(cudaMemcpyAsync(slot.dev, slot.host, bytes, cudaMemcpyHostToDevice, stream));
     {
-        int rc = launch_kernel(static_cast<const DevField *>(slot.dev), (int)dev_fields.size(), (int)tiles, stream);
+        int rc = launch_kernel(static_cast<const DevField *>(slot.dev), (int)dev_fields.size(), (int)tiles, ctas_per_sm, acc, stream);
         if (rc != RF_OK) return rc;
     }
     RF_CUDA(cudaEventRecord(slot.done, stream));
@@ -772,6 +815,8 @@ static int build_field(DevField &d, const rf_field_desc &f, int64_t batch, int f
     if (f.bag_ends && !f.bag_offsets) return set_error(RF_ERR_INVALID, "field %d: bag_ends given without bag_offsets", fi);
     if (f.bag_ends && (!f.ids || f.n_tables != 1))
         return set_error(RF_ERR_UNSUPPORTED, "field %d: bag_ends (gapped bags) takes pre-hashed ids and one table", fi);
+    if ((f.flags & RF_FIELD_ACCUMULATE) && f.combiner > RF_COMBINER_AVG)
+        return set_error(RF_ERR_INVALID, "field %d: RF_FIELD_ACCUMULATE takes the sum / avg combiners", fi);
     d.bytes = f.bytes;
     d.soffs = f.str_offsets;
     d.ints = f.int_values;
@@ -830,15 +875,29 @@ uint64_t rf_debug_fastmod(uint64_t x, uint64_t d) {
     return fastmod(x, m);
 }
 
-int rf_bag_forward(const rf_field_desc *fields, int n_fields, int64_t batch, void *stream) {
+int rf_bag_forward_ex(const rf_field_desc *fields, int n_fields, int64_t batch, int max_ctas_per_sm, void *stream) {
     if (n_fields < 0 || (n_fields > 0 && !fields)) return set_error(RF_ERR_INVALID, "bad fields array");
+    if (max_ctas_per_sm < 0) return set_error(RF_ERR_INVALID, "max_ctas_per_sm must be >= 0");
     if (n_fields == 0 || batch == 0) return RF_OK;
     std::vector<DevField> dev(n_fields);
     for (int i = 0; i < n_fields; ++i) {
         int rc = build_field(dev[i], fields[i], batch, i);
         if (rc != RF_OK) return rc;
     }
-    return launch_fields(dev, static_cast<cudaStream_t>(stream));
+    return launch_fields(dev, max_ctas_per_sm, static_cast<cudaStream_t>(stream));
+}
+
+int rf_bag_forward(const rf_field_desc *fields, int n_fields, int64_t batch, void *stream) {
+    return rf_bag_forward_ex(fields, n_fields, batch, 0, stream);
+}
+
+int rf_release_captured_launches(void) {
+    int dev = 0;
+    RF_CUDA(cudaGetDevice(&dev));
+    DeviceState *st = device_state(dev);
+    std::lock_guard<std::mutex> lk(st->mu);
+    st->graph_used = 0;
+    return RF_OK;
 }
 
 static int hash_only(rf_field_desc &f, int64_t n_items, int64_t num_bins, int mask_mode, int use_strong, uint64_t key0,

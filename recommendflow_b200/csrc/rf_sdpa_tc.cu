@@ -126,7 +126,7 @@ struct Params {
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
-sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+sdpa_tc_kernel_v1(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                const __grid_constant__ CUtensorMap map_v, Params p) {
     extern __shared__ uint8_t smem_raw[];
     const int n_db = p.dh / kKB;                                    // head_dim blocks of 32 floats
@@ -286,6 +286,221 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// v2 (round 2): the same arithmetic, software-pipelined across pairs.  Round 1 ran load -> GEMM 1 -> softmax ->
+// GEMM 2 -> store strictly in series with one CTA per SM (ncu: 33 % of the op's HBM floor, 5 warps resident,
+// `long_scoreboard` + `wait`): every pair paid a full DRAM round trip with nothing else in flight.  Now
+//   warp 4 (one lane)  TMA of Q, K and GEMM 1.  Q/K smem is single-buffered but refilled for pair n+1 the moment
+//                      GEMM 1 of pair n retires, and GEMM 1 writes alternating TMEM logit buffers, so the loads
+//                      AND the first contraction of pair n+1 run under the softmax of pair n;
+//   warp 5 (one lane)  TMA of V (double-buffered when it fits) and GEMM 2;
+//   warps 0-3          softmax / P / output rows, exactly as before.
+// TMEM: logits[0] cols 0-127, logits[1] cols 128-255, output cols 256-(256+dh).  smem (dh = 64): Q 32 + K 32 +
+// V 2 x 32 + P 64 = 192 KiB, one CTA per SM.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kThreads2 = 192;
+constexpr int kTmemCols2 = 512;
+
+__global__ void __launch_bounds__(kThreads2, 1)
+sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+               const __grid_constant__ CUtensorMap map_v, Params p, int n_vbuf) {
+    extern __shared__ uint8_t smem_raw[];
+    const int n_db = p.dh / kKB;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t q_s = base;
+    const uint32_t k_s = q_s + n_db * kBlkBytes;
+    const uint32_t v_s = k_s + n_db * kBlkBytes;                     // n_vbuf buffers of n_db blocks
+    const uint32_t p_s = v_s + n_vbuf * n_db * kBlkBytes;            // 4 blocks
+    const uint32_t bars = p_s + 4 * kBlkBytes;
+    const uint32_t qk_full = bars, mma1_done0 = bars + 8, s_free0 = bars + 24, v_full0 = bars + 40, p_ready = bars + 56,
+                   mma2_done = bars + 64, tmem_slot = bars + 72;
+    uint8_t *smem_gen = smem_raw + (base - smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(qk_full, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(mma1_done0 + 8 * b, 1);
+            mbar_init(s_free0 + 8 * b, 128);
+            mbar_init(v_full0 + 8 * b, 1);
+        }
+        mbar_init(p_ready, 128);
+        mbar_init(mma2_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        uint4 *pz = reinterpret_cast<uint4 *>(smem_gen + (p_s - base));
+        for (int i = threadIdx.x; i < 4 * kBlkBytes / 16; i += kThreads2) pz[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols2) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int n_pairs = (p.n_seq + 1) / 2;
+    const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(p.dh >> 3) << 17) |
+                            ((uint32_t)(kRows >> 4) << 24);
+    const uint32_t qk_bytes = 2u * n_db * kBlkBytes, v_bytes = (uint32_t)n_db * kBlkBytes;
+    const int stride = gridDim.x;
+
+    if (warp == 4) {
+        // ===== Q / K loader + GEMM 1 =====
+        if (lane == 0) {
+            auto load_qk = [&](int pair) {
+                mbar_expect_tx(qk_full, qk_bytes);
+                for (int db = 0; db < n_db; ++db)
+                    for (int h = 0; h < 2; ++h) {
+                        const int row = (2 * pair + h) * p.S;
+                        const uint32_t off = db * kBlkBytes + h * (kSeqPad * 128);
+                        tma_load_2d(q_s + off, &map_q, qk_full, db * kKB, row);
+                        tma_load_2d(k_s + off, &map_k, qk_full, db * kKB, row);
+                    }
+            };
+            if ((int)blockIdx.x < n_pairs) load_qk(blockIdx.x);
+            uint32_t n = 0;
+            for (int pair = blockIdx.x; pair < n_pairs; pair += stride, ++n) {
+                const uint32_t b = n & 1u, use = (n >> 1) & 1u;
+                mbar_wait(qk_full, n & 1u);
+                mbar_wait(s_free0 + 8 * b, use ^ 1u);               // softmax of pair n-2 has read this logit buffer
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int db = 0; db < n_db; ++db) {
+                    const uint64_t a = desc_kmajor(q_s + db * kBlkBytes), bd = desc_kmajor(k_s + db * kBlkBytes);
+#pragma unroll
+                    for (int k = 0; k < kKB / 8; ++k)
+                        umma_tf32(tmem_base + b * 128u, a + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc1, (db | k) ? 1u : 0u);
+                }
+                umma_commit(mma1_done0 + 8 * b);
+                if (pair + stride < n_pairs) {
+                    mbar_wait(mma1_done0 + 8 * b, use);             // Q / K smem is free again
+                    load_qk(pair + stride);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        // ===== V loader + GEMM 2 =====
+        if (lane == 0) {
+            auto load_v = [&](int pair, int vb) {
+                mbar_expect_tx(v_full0 + 8 * vb, v_bytes);
+                for (int db = 0; db < n_db; ++db)
+                    for (int h = 0; h < 2; ++h)
+                        tma_load_2d(v_s + vb * n_db * kBlkBytes + db * kBlkBytes + h * (kSeqPad * 128), &map_v, v_full0 + 8 * vb,
+                                    db * kKB, (2 * pair + h) * p.S);
+            };
+            for (int j = 0; j < n_vbuf; ++j)
+                if ((int)blockIdx.x + j * stride < n_pairs) load_v(blockIdx.x + j * stride, j);
+            uint32_t n = 0;
+            for (int pair = blockIdx.x; pair < n_pairs; pair += stride, ++n) {
+                const uint32_t vb = n_vbuf == 2 ? (n & 1u) : 0u;
+                const uint32_t vuse = n_vbuf == 2 ? ((n >> 1) & 1u) : (n & 1u);
+                mbar_wait(p_ready, n & 1u);
+                mbar_wait(v_full0 + 8 * vb, vuse);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t vbase = v_s + vb * n_db * kBlkBytes;
+                for (int kb = 0; kb < 4; ++kb) {
+                    const uint64_t a = desc_kmajor(p_s + kb * kBlkBytes);
+#pragma unroll
+                    for (int k = 0; k < kKB / 8; ++k) {
+                        const uint64_t bd = desc_mnmajor(vbase + (uint32_t)(kb * 4 + k) * 1024u, (uint32_t)kBlkBytes);
+                        umma_tf32(tmem_base + 256u, a + (uint64_t)(2 * k), bd, idesc2, (kb | k) ? 1u : 0u);
+                    }
+                }
+                umma_commit(mma2_done);
+                const int nxt = pair + n_vbuf * stride;
+                if (nxt < n_pairs) {
+                    mbar_wait(mma2_done, n & 1u);                   // this V buffer has been consumed
+                    load_v(nxt, (int)vb);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== softmax: thread = row of the pair tile =====
+        const int r = threadIdx.x;
+        const int half = r >> 6, i = r & 63;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        uint32_t n = 0;
+        for (int pair = blockIdx.x; pair < n_pairs; pair += stride, ++n) {
+            const uint32_t b = n & 1u, use = (n >> 1) & 1u;
+            const int seq = 2 * pair + half;
+            mbar_wait(mma1_done0 + 8 * b, use);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float x[64];
+            {
+                float v0[32], v1[32];
+                tmem_ld32(lane_addr + b * 128u + (uint32_t)(half * 64), v0);
+                tmem_ld32(lane_addr + b * 128u + (uint32_t)(half * 64 + 32), v1);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    x[j] = v0[j];
+                    x[32 + j] = v1[j];
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(s_free0 + 8 * b);                           // GEMM 1 of pair n+2 may overwrite this buffer
+            const bool row_ok = seq < p.n_seq && i < p.S;
+            const bool masked = row_ok && p.mask && p.mask[(size_t)seq * p.S + i] == 0.f;
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                float l = masked ? -4294967295.0f : x[j] * p.inv_sqrt_dk;
+                l = (j < p.S) ? l : -INFINITY;
+                x[j] = l;
+                mx = fmaxf(mx, l);
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                const float e = (j < p.S) ? __expf(x[j] - mx) : 0.f;
+                x[j] = e;
+                sum += e;
+            }
+            const float inv = row_ok ? 1.f / sum : 0.f;
+            uint8_t *prow = smem_gen + (p_s - base) + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                uint4 w;
+                w.x = to_tf32(x[c * 4 + 0] * inv);
+                w.y = to_tf32(x[c * 4 + 1] * inv);
+                w.z = to_tf32(x[c * 4 + 2] * inv);
+                w.w = to_tf32(x[c * 4 + 3] * inv);
+                const int kb = half * 2 + (c >> 3), cc = c & 7;
+                *reinterpret_cast<uint4 *>(prow + kb * kBlkBytes + ((cc ^ (r & 7)) << 4)) = w;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(p_ready);
+            mbar_wait(mma2_done, n & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float *orow = p.out + ((size_t)seq * p.S + i) * p.dh;
+            for (int c0 = 0; c0 < p.dh; c0 += 32) {
+                float o[32];
+                tmem_ld32(lane_addr + 256u + (uint32_t)c0, o);
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4 *>(orow + c0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols2) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -327,16 +542,25 @@ int launch_sdpa_tc(const float *q, const float *k, const float *v, const float *
     if ((rc = make_map(&mk, k, n_seq * S, dh, CU_TENSOR_MAP_SWIZZLE_128B)) != RF_OK) return rc;
     if ((rc = make_map(&mv, v, n_seq * S, dh, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != RF_OK) return rc;   // MN-major TF32 operand
     const int n_db = dh / kKB;
-    const size_t smem = (size_t)(3 * n_db + 4) * kBlkBytes + 1024 + 128;
     int dev = 0, sms = 0;
     RF_CUDA(cudaGetDevice(&dev));
     RF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    RF_CUDA(cudaFuncSetAttribute(sdpa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int n_pairs = (int)((n_seq + 1) / 2);
-    const int ctas_per_sm = smem <= 110 * 1024 ? 2 : 1;
-    const int grid = n_pairs < sms * ctas_per_sm ? n_pairs : sms * ctas_per_sm;
     Params p{mask, out, (int)n_seq, S, dh, 1.0f / sqrtf((float)dh)};
-    sdpa_tc_kernel<<<grid, kThreads, smem, st>>>(mq, mk, mv, p);
+    static const bool v1 = getenv("RF_SDPA_V1") && atoi(getenv("RF_SDPA_V1")) != 0;
+    if (v1) {        // round-1 kernel (single-stage), kept for A/B measurements
+        const size_t smem = (size_t)(3 * n_db + 4) * kBlkBytes + 1024 + 128;
+        RF_CUDA(cudaFuncSetAttribute(sdpa_tc_kernel_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int ctas_per_sm = smem <= 110 * 1024 ? 2 : 1;
+        const int grid = n_pairs < sms * ctas_per_sm ? n_pairs : sms * ctas_per_sm;
+        sdpa_tc_kernel_v1<<<grid, kThreads, smem, st>>>(mq, mk, mv, p);
+    } else {
+        const int n_vbuf = n_db <= 2 ? 2 : 1;
+        const size_t smem = (size_t)((2 + n_vbuf) * n_db + 4) * kBlkBytes + 1024 + 128;
+        RF_CUDA(cudaFuncSetAttribute(sdpa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = n_pairs < sms ? n_pairs : sms;
+        sdpa_tc_kernel<<<grid, kThreads2, smem, st>>>(mq, mk, mv, p, n_vbuf);
+    }
     RF_CUDA(cudaGetLastError());
     g_launches.fetch_add(1);
     return RF_OK;

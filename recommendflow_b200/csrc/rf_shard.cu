@@ -369,15 +369,22 @@ struct TileSmem {
     uint16_t cnt[kTileBags][kMaxWorld];       // keys of (bag, owner)
     uint16_t beg[kTileBags][kMaxWorld];       // exclusive scan of cnt over the bags, per owner
     int seg_len[kMaxWorld], seg_base[kMaxWorld + 1];
+    int32_t tile_boffs[kTileBags + 4];        // STAGE: key offsets of the tile's bags (tile_bags <= kTileBags)
 };
+constexpr int kStageKeys = 1024;              // keys whose bytes are staged at a time (<= 16 KiB - slack, else unstaged)
 
-template <bool HASH>
-__global__ void __launch_bounds__(kTileThreads) shard_route_tile_kernel(
+// STAGE = true (default, RF_ROUTE_STAGE=0 selects the round-1 kernel): the tile's bag offsets and, 1024 keys at a
+// time, the contiguous slice of the string arena those keys occupy are copied into shared memory with coalesced
+// 16-byte loads first, so carving rounds and hashing never wait on a dependent global load (round 1: offset -> bytes
+// -> hash was one DRAM round trip per key with 16 keys per thread in series; the kernel ran at 11 % of HBM speed).
+template <bool HASH, bool STAGE>
+__global__ void __launch_bounds__(kTileThreads, 4) shard_route_tile_kernel(
     const int64_t *__restrict__ ids, const uint8_t *__restrict__ bytes, const int32_t *__restrict__ soffs, HashSpec spec,
     int mask_empty, int64_t *__restrict__ ids_ws, const int32_t *__restrict__ boffs, int bag_len, int64_t batch, int world,
     int tile_bags, PtrTable rows_dst, PtrTable begin_dst, PtrTable end_dst) {
     extern __shared__ __align__(16) unsigned char tile_raw[];
     TileSmem &sm = *reinterpret_cast<TileSmem *>(tile_raw);
+    int32_t *tb = reinterpret_cast<int32_t *>(sm.tile_boffs);      // STAGE: key offsets of the tile's bags
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
     const bool pow2 = (world & (world - 1)) == 0;
@@ -385,18 +392,38 @@ __global__ void __launch_bounds__(kTileThreads) shard_route_tile_kernel(
     const int64_t n_tiles = (batch + tile_bags - 1) / tile_bags;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t t0 = tile * tile_bags, t1 = min(batch, t0 + tile_bags);
+        if (STAGE) {
+            __syncthreads();                        // the previous tile's rounds are done with tb
+            for (int i = tid; i <= (int)(t1 - t0); i += kTileThreads)
+                tb[i] = boffs ? boffs[t0 + i] : (int32_t)((t0 + i) * bag_len);
+            __syncthreads();
+        }
         int64_t r0 = t0;
         while (r0 < t1) {
             // ---- carve a round: whole bags, <= kTileCap keys, <= kTileBags bags ----
-            int64_t k0, dummy;
-            bag_range(boffs, bag_len, r0, k0, dummy);
-            int64_t r1 = r0, k1 = k0;
-            while (r1 < t1 && r1 - r0 < kTileBags) {
-                int64_t lo, hi;
-                bag_range(boffs, bag_len, r1, lo, hi);
-                if (hi - k0 > kTileCap) break;
-                k1 = hi;
-                ++r1;
+            int64_t k0, k1, r1;
+            if (STAGE) {
+                // tb is non-decreasing: binary search for the last bag whose end still fits the round
+                k0 = tb[r0 - t0];
+                int lo = (int)(r0 - t0), hi = (int)min(t1 - t0, r0 - t0 + kTileBags);
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if ((int64_t)tb[mid] - k0 <= kTileCap) lo = mid; else hi = mid - 1;
+                }
+                r1 = t0 + lo;
+                k1 = tb[lo];
+            } else {
+                int64_t dummy;
+                bag_range(boffs, bag_len, r0, k0, dummy);
+                r1 = r0;
+                k1 = k0;
+                while (r1 < t1 && r1 - r0 < kTileBags) {
+                    int64_t lo, hi;
+                    bag_range(boffs, bag_len, r1, lo, hi);
+                    if (hi - k0 > kTileCap) break;
+                    k1 = hi;
+                    ++r1;
+                }
             }
             const int nb = (int)(r1 - r0);
             if (nb == 0) {
@@ -412,7 +439,7 @@ __global__ void __launch_bounds__(kTileThreads) shard_route_tile_kernel(
                 if (tid == 0) {
                     for (int64_t k = lo; k < hi; ++k) {
                         const uint32_t id = key_id<HASH>(k, ids, bytes, soffs, spec, mask_empty);
-                        if (HASH) ids_ws[k] = (int64_t)id;
+                        if (HASH && ids_ws) ids_ws[k] = (int64_t)id;
                         const uint32_t row = id / (uint32_t)world, g = id - row * (uint32_t)world;
                         static_cast<int64_t *>(rows_dst.p[g])[lo + run[g]] = (int64_t)row;
                         ++run[g];
@@ -429,7 +456,44 @@ __global__ void __launch_bounds__(kTileThreads) shard_route_tile_kernel(
             const int n_keys = (int)(k1 - k0);
             // ---- 1. ids (string keys: the round's offsets are staged first, coalesced, so that hashing
             //         costs one dependent global round trip per key instead of two) ----
-            if (HASH) {
+            if (HASH && STAGE) {
+                int32_t *soff_s = reinterpret_cast<int32_t *>(sm.meta);
+                for (int j = tid; j <= n_keys; j += kTileThreads) soff_s[j] = soffs[k0 + j];
+                __syncthreads();
+                // key bytes, kStageKeys keys at a time, into the staging area (srow is not live until step 4)
+                uint32_t *stage = sm.srow;
+                for (int sub0 = 0; sub0 < n_keys; sub0 += kStageKeys) {
+                    const int n_sub = min(kStageKeys, n_keys - sub0);
+                    const int32_t byte0 = soff_s[sub0];
+                    const uint32_t n_bytes = (uint32_t)(soff_s[sub0 + n_sub] - byte0);
+                    const uintptr_t addr0 = reinterpret_cast<uintptr_t>(bytes) + (uintptr_t)byte0;
+                    const uint32_t shift = (uint32_t)(addr0 & 15u);
+                    const bool staged = shift + n_bytes + 8u <= (uint32_t)(kTileCap * 4 - 32);
+                    if (sub0) __syncthreads();              // the previous slice has been hashed
+                    if (staged) {
+                        const uint4 *g = reinterpret_cast<const uint4 *>(addr0 - shift);
+                        uint4 *s4 = reinterpret_cast<uint4 *>(stage);
+                        const uint32_t n_vec = (shift + n_bytes + 8u + 15u) >> 4;
+                        for (uint32_t i = tid; i < n_vec; i += kTileThreads) s4[i] = __ldg(g + i);
+                        __syncthreads();
+                    }
+                    for (int j = sub0 + tid; j < sub0 + n_sub; j += kTileThreads) {
+                        const int32_t o = soff_s[j];
+                        const uint32_t len = (uint32_t)(soff_s[j + 1] - o);
+                        uint32_t id;
+                        if (staged) {
+                            const WordSrcShared src{stage, shift + (uint32_t)(o - byte0)};
+                            id = bucket_of(src, len, spec, mask_empty && len == 0);
+                        } else {
+                            const uintptr_t a = reinterpret_cast<uintptr_t>(bytes) + (uintptr_t)o;
+                            const WordSrcGlobal src{reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3), (uint32_t)(a & 3u)};
+                            id = bucket_of(src, len, spec, mask_empty && len == 0);
+                        }
+                        sm.sid[j] = id;
+                        if (ids_ws) ids_ws[k0 + j] = (int64_t)id;
+                    }
+                }
+            } else if (HASH) {
                 int32_t *soff_s = reinterpret_cast<int32_t *>(sm.meta);
                 for (int j = tid; j <= n_keys; j += kTileThreads) soff_s[j] = soffs[k0 + j];
                 __syncthreads();
@@ -440,7 +504,7 @@ __global__ void __launch_bounds__(kTileThreads) shard_route_tile_kernel(
                     const WordSrcGlobal src{reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3), (uint32_t)(a & 3u)};
                     const uint32_t id = bucket_of(src, len, spec, mask_empty && len == 0);
                     sm.sid[j] = id;
-                    ids_ws[k0 + j] = (int64_t)id;
+                    if (ids_ws) ids_ws[k0 + j] = (int64_t)id;
                 }
             } else {
                 for (int j = tid; j < n_keys; j += kTileThreads) sm.sid[j] = (uint32_t)ids[k0 + j];
@@ -450,7 +514,12 @@ __global__ void __launch_bounds__(kTileThreads) shard_route_tile_kernel(
             // ---- 2. owner, rank inside the (bag, owner) run ----
             for (int bl = wid; bl < nb; bl += kTileThreads / 32) {
                 int64_t lo, hi;
-                bag_range(boffs, bag_len, r0 + bl, lo, hi);
+                if (STAGE) {
+                    lo = tb[r0 - t0 + bl];
+                    hi = tb[r0 - t0 + bl + 1];
+                } else {
+                    bag_range(boffs, bag_len, r0 + bl, lo, hi);
+                }
                 const int j0 = (int)(lo - k0), j1 = (int)(hi - k0);
                 for (int j = j0; j < j1; j += 32) {
                     const bool on = j + lane < j1;
@@ -654,7 +723,7 @@ int rf_shard_route_tiles(const uint8_t *d_bytes, const int32_t *d_str_offsets, c
     if (batch == 0) return RF_OK;
     const bool hash = d_bytes != nullptr;
     if (hash == (d_ids != nullptr)) return set_error(RF_ERR_INVALID, "rf_shard_route_tiles: give string keys or ids, not both");
-    if (hash && (!d_str_offsets || !d_ids_ws)) return set_error(RF_ERR_INVALID, "rf_shard_route_tiles: NULL key buffer");
+    if (hash && !d_str_offsets) return set_error(RF_ERR_INVALID, "rf_shard_route_tiles: NULL key buffer");
     if (!h_rows_dst || !h_begin_dst || !h_end_dst) return set_error(RF_ERR_INVALID, "rf_shard_route_tiles: NULL destination table");
     if (!d_bag_offsets && bag_len < 0) return set_error(RF_ERR_INVALID, "negative bag_len");
     HashSpec spec{};
@@ -684,16 +753,25 @@ int rf_shard_route_tiles(const uint8_t *d_bytes, const int32_t *d_str_offsets, c
     const int grid = grid_for((batch + tile_bags - 1) / tile_bags, 1, sms);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t smem = sizeof(TileSmem);
-    if (hash) {
-        RF_CUDA(cudaFuncSetAttribute(shard_route_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        shard_route_tile_kernel<true><<<grid, kTileThreads, smem, st>>>(nullptr, d_bytes, d_str_offsets, spec,
-                                                                        mask_mode == RF_MASK_EMPTY_STRING, d_ids_ws, d_bag_offsets,
-                                                                        bag_len, batch, world, (int)tile_bags, rows, begs, ends);
-    } else {
-        RF_CUDA(cudaFuncSetAttribute(shard_route_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        shard_route_tile_kernel<false><<<grid, kTileThreads, smem, st>>>(d_ids, nullptr, nullptr, spec, 0, nullptr, d_bag_offsets,
-                                                                         bag_len, batch, world, (int)tile_bags, rows, begs, ends);
-    }
+    static const bool stage = !(getenv("RF_ROUTE_STAGE") && atoi(getenv("RF_ROUTE_STAGE")) == 0);
+#define RF_ROUTE_LAUNCH(H, S, ...)                                                                                      \
+    do {                                                                                                                \
+        RF_CUDA(cudaFuncSetAttribute(shard_route_tile_kernel<H, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        shard_route_tile_kernel<H, S><<<grid, kTileThreads, smem, st>>>(__VA_ARGS__);                                    \
+    } while (0)
+    if (hash && stage)
+        RF_ROUTE_LAUNCH(true, true, nullptr, d_bytes, d_str_offsets, spec, mask_mode == RF_MASK_EMPTY_STRING, d_ids_ws, d_bag_offsets,
+                        bag_len, batch, world, (int)tile_bags, rows, begs, ends);
+    else if (hash)
+        RF_ROUTE_LAUNCH(true, false, nullptr, d_bytes, d_str_offsets, spec, mask_mode == RF_MASK_EMPTY_STRING, d_ids_ws, d_bag_offsets,
+                        bag_len, batch, world, (int)tile_bags, rows, begs, ends);
+    else if (stage)
+        RF_ROUTE_LAUNCH(false, true, d_ids, nullptr, nullptr, spec, 0, nullptr, d_bag_offsets, bag_len, batch, world, (int)tile_bags,
+                        rows, begs, ends);
+    else
+        RF_ROUTE_LAUNCH(false, false, d_ids, nullptr, nullptr, spec, 0, nullptr, d_bag_offsets, bag_len, batch, world, (int)tile_bags,
+                        rows, begs, ends);
+#undef RF_ROUTE_LAUNCH
     RF_CUDA(cudaGetLastError());
     g_launches.fetch_add(1);
     return RF_OK;

@@ -29,6 +29,29 @@ from .bag_ops import FieldCall, bag_forward, hash_ints, hash_strings
 from .strings import StringColumn
 
 
+class BucketIds(object):
+    """Pre-hashed keys: int64 bucket ids in [0, num_bins) -- dense [B, L] or jagged (flat ids + int32 bag_offsets[B + 1]).
+    The "pre-hashed ids" path of SURVEY.md §8(d) C4: routing skips the hash and reads 8 bytes per key."""
+
+    def __init__(self, ids, bag_offsets=None):
+        if ids.dtype != torch.int64:
+            raise ValueError("bucket ids must be int64")
+        if bag_offsets is None and ids.dim() != 2:
+            raise ValueError("dense bucket ids must be [B, L]; pass bag_offsets for jagged bags")
+        self.ids = ids.contiguous()
+        self.bag_offsets = bag_offsets
+        B = ids.shape[0] if bag_offsets is None else bag_offsets.numel() - 1
+        self.shape = (B, ids.shape[1] if bag_offsets is None else None)
+
+    @property
+    def n_items(self):
+        return self.ids.numel()
+
+    @property
+    def device(self):
+        return self.ids.device
+
+
 class CudaShardOps(object):
     """The compute steps of the sharded forward, on the CUDA kernels of librf_b200.so."""
 
@@ -61,7 +84,8 @@ class CudaShardOps(object):
                 raise NotImplementedError("only mask_value in (None, '') is supported for string keys")
             strong, k0, k1 = nat.salt_to_key(salt)
             args = (keys.data.data_ptr(), keys.offsets.data_ptr(), None, int(num_bins),
-                    nat.MASK_NONE if mask_value is None else nat.MASK_EMPTY_STRING, strong, k0, k1, ids_ws.data_ptr())
+                    nat.MASK_NONE if mask_value is None else nat.MASK_EMPTY_STRING, strong, k0, k1,
+                    None if ids_ws is None else ids_ws.data_ptr())
             dev = keys.device
         else:                                   # pre-hashed int64 ids
             args = (None, None, keys.data_ptr(), 0, 0, 0, 0, 0, None)
@@ -79,12 +103,16 @@ class CudaShardOps(object):
                                                bag_len or 0, batch, world, counts_ws.data_ptr(), offs_local.data_ptr(),
                                                arr_o, arr_r, C.c_void_p(torch.cuda.current_stream(ids.device).cuda_stream)))
 
-    def pool(self, shard, rows_per_src, offs_per_src, outs_per_src, batch, combiner, est_items, ends_per_src=None):
+    def pool(self, shard, rows_per_src, offs_per_src, outs_per_src, batch, combiner, est_items, ends_per_src=None,
+             accumulate=False, max_ctas_per_sm=0):
+        """Owner side: pool the rows every source asked for.  accumulate=True adds each pooled vector into the
+        source's (zeroed) buffer with red.global.add instead of storing a per-owner partial."""
         ends_per_src = ends_per_src or [None] * len(rows_per_src)
+        flags = nat.FIELD_PARTIAL | (nat.FIELD_ACCUMULATE if accumulate else 0)
         calls = [FieldCall([(shard, shard.shape[0], None)], shard.shape[1], combiner, ids=rows.view(1, -1),
-                           bag_offsets=offs, bag_ends=ends, out=out, flags=nat.FIELD_PARTIAL, n_items=est_items)
+                           bag_offsets=offs, bag_ends=ends, out=out, flags=flags, n_items=est_items)
                  for rows, offs, ends, out in zip(rows_per_src, offs_per_src, ends_per_src, outs_per_src)]
-        bag_forward(calls, batch)
+        bag_forward(calls, batch, max_ctas_per_sm=max_ctas_per_sm)
 
     def combine(self, partials, world, batch, dim, combiner, bag_len, bag_offsets, out):
         with torch.cuda.device(out.device):
@@ -118,7 +146,8 @@ def shard_rows(num_bins, rank, world):
 
 class ShardedEmbeddingBag(torch.nn.Module):
     def __init__(self, num_bins, output_dim, combiner="sum", salt=None, mask_value="", group=None, transport="p2p",
-                 max_batch=8192, max_keys=None, device=None, name="sharded_bag", ops=None):
+                 max_batch=8192, max_keys=None, device=None, name="sharded_bag", ops=None, deterministic=True,
+                 keep_ids=True):
         super().__init__()
         if num_bins is None or num_bins <= 0:
             raise ValueError("`num_bins` cannot be `None` or non-positive values.")
@@ -134,6 +163,13 @@ class ShardedEmbeddingBag(torch.nn.Module):
         if self.world > 16:
             raise NotImplementedError("at most 16 ranks (one NVSwitch box)")
         self.transport = transport
+        # deterministic=False (p2p, sum / avg): the owners ADD their partial pools straight into the source rank's
+        # zeroed buffer over NVLink (red.global.add) -- no per-owner partial buffers, no combine pass; the price is
+        # a summation order across owners that changes from run to run (fp32 re-association, same bound as below)
+        self.deterministic = bool(deterministic)
+        if not self.deterministic and (transport != "p2p" or combiner not in ("sum", "avg")):
+            raise ValueError("deterministic=False needs the p2p transport and a sum / avg combiner")
+        self.keep_ids = bool(keep_ids)      # string keys: also leave the bucket ids in a workspace (the backward's input)
         self.max_batch = int(max_batch)
         self.max_keys = int(max_keys if max_keys is not None else max_batch * 200)
         self.ops = ops if ops is not None else CudaShardOps()
@@ -189,7 +225,7 @@ class ShardedEmbeddingBag(torch.nn.Module):
             import torch.distributed._symmetric_memory as symm
             rows_bytes = W * K * 8
             offs_bytes = (2 * W * (B + 1) * 4 + 15) // 16 * 16      # [2][W][B+1]: bag begins / ends (or one CSR)
-            part_bytes = W * B * D * 4
+            part_bytes = (W if self.deterministic else 1) * B * D * 4
             set_bytes = rows_bytes + offs_bytes + part_bytes
             raw = symm.empty(self.N_SETS * set_bytes, dtype=torch.uint8, device=dev)
             hdl = symm.rendezvous(raw, self.group)
@@ -202,8 +238,12 @@ class ShardedEmbeddingBag(torch.nn.Module):
                 e0 = o + rows_bytes + W * (B + 1) * 4
                 b["ends_recv"].append(raw[e0:e0 + W * (B + 1) * 4].view(torch.int32).view(W, B + 1))
                 po = o + rows_bytes + offs_bytes
-                b["partials"].append(raw[po:po + part_bytes].view(torch.float32).view(W, B, D))
-                b["peer_partials"].append([hdl.get_buffer(r, (W, B, D), torch.float32, po // 4) for r in range(W)])
+                if self.deterministic:
+                    b["partials"].append(raw[po:po + part_bytes].view(torch.float32).view(W, B, D))
+                    b["peer_partials"].append([hdl.get_buffer(r, (W, B, D), torch.float32, po // 4) for r in range(W)])
+                else:       # one [B, D] accumulator per set; every owner reduces into it
+                    b["partials"].append(raw[po:po + part_bytes].view(torch.float32).view(1, B, D))
+                    b["peer_partials"].append([hdl.get_buffer(r, (1, B, D), torch.float32, po // 4) for r in range(W)])
             b["peer_ptr"] = [int(p) for p in hdl.buffer_ptrs]
             # routing and combine are short, latency-bound kernels: give their streams priority so their
             # CTAs slot in between the CTAs of the long HBM-bound pooling kernel instead of queueing behind it
@@ -221,7 +261,7 @@ class ShardedEmbeddingBag(torch.nn.Module):
 
     # ---- forward ---------------------------------------------------------------------------------
     def _describe(self, keys):
-        if isinstance(keys, StringColumn):
+        if isinstance(keys, (StringColumn, BucketIds)):
             B, L, bag_offsets, n_keys = keys.shape[0], keys.shape[1], keys.bag_offsets, keys.n_items
         else:
             B, L, bag_offsets, n_keys = keys.shape[0], keys.shape[1], None, keys.numel()
@@ -271,16 +311,26 @@ class ShardedEmbeddingBag(torch.nn.Module):
             if overlap and b["rows_free"][j] is not None:
                 stream.wait_event(b["rows_free"][j])      # every owner is done pooling out of set j
             self._tick("start")
+            if isinstance(keys, BucketIds) and not tiles:
+                raise NotImplementedError("pre-hashed BucketIds take the tile routing layout")
             if tiles:
                 src = keys
-                if not isinstance(keys, StringColumn):
+                if isinstance(keys, BucketIds):
+                    src = keys.ids.view(-1)
+                elif not isinstance(keys, StringColumn):
                     src = self.ops.hash(keys, self.num_bins, self.mask_value, self.salt)
-                elif b["ids_ws"] is None:
+                elif b["ids_ws"] is None and self.keep_ids:
                     b["ids_ws"] = torch.empty(self.max_keys, dtype=torch.int64, device=self.device)
                 self.ops.route_tiles(src, self.num_bins, self.mask_value, self.salt, b["ids_ws"], bag_offsets, L, B, W,
                                      rows_dst, offs_dst, ends_dst)
             else:
                 self._route(keys, B, L, bag_offsets, offs_dst, rows_dst)
+            if not self.deterministic:
+                # the accumulator of this set: its last reader (the finishing pass two steps ago) is ordered before
+                # this stream by the rows_free / combined events below; owners only add after the next barrier
+                if overlap and b["combined"][j] is not None:
+                    stream.wait_event(b["combined"][j])
+                b["partials"][j].zero_()
             self._tick("route")
             if overlap:
                 routed = torch.cuda.Event()
@@ -312,16 +362,13 @@ class ShardedEmbeddingBag(torch.nn.Module):
             # sources in rotated order (me, me+1, ...): at any moment the W owners write their pooled
             # vectors to W different ranks -- a permutation, not an incast on one rank's NVLink port
             order = [(me + k) % W for k in range(W)]
-            if overlap and self.pool_ctas_per_sm:
-                nat.check(nat.lib().rf_set_bag_grid_limit(self.pool_ctas_per_sm))
-            try:
-                self.ops.pool(self.shard.data, [b["rows_recv"][j][s] for s in order],
-                              [b["offs_recv"][j][s] for s in order], [b["peer_partials"][j][s][me] for s in order],
-                              B, partial_op, max(1, ticket["n_keys"] // W),
-                              [b["ends_recv"][j][s] for s in order] if ticket["tiles"] else None)
-            finally:
-                if overlap and self.pool_ctas_per_sm:
-                    nat.lib().rf_set_bag_grid_limit(0)
+            acc = not self.deterministic
+            self.ops.pool(self.shard.data, [b["rows_recv"][j][s] for s in order],
+                          [b["offs_recv"][j][s] for s in order],
+                          [b["peer_partials"][j][s][0 if acc else me] for s in order],
+                          B, partial_op, max(1, ticket["n_keys"] // W),
+                          [b["ends_recv"][j][s] for s in order] if ticket["tiles"] else None,
+                          accumulate=acc, max_ctas_per_sm=self.pool_ctas_per_sm if overlap else 0)
             self._tick("pool")
             pooled = None
             if overlap:
@@ -337,7 +384,9 @@ class ShardedEmbeddingBag(torch.nn.Module):
                 ev = torch.cuda.Event()
                 ev.record(sC)
                 b["rows_free"][j] = ev
-            self.ops.combine(b["partials"][j], W, B, D, self.combiner, L, bag_offsets, out)
+            # deterministic: reduce the W partials in rank order; else the single accumulator only needs the
+            # avg division (or a copy) on its way to `out` -- the same kernel with world = 1
+            self.ops.combine(b["partials"][j], W if self.deterministic else 1, B, D, self.combiner, L, bag_offsets, out)
             self._tick("combine")
             if overlap:
                 done = torch.cuda.Event()
@@ -347,7 +396,8 @@ class ShardedEmbeddingBag(torch.nn.Module):
         return out
 
     def forward(self, keys, out=None):
-        """keys: StringColumn (dense [B, L] or jagged) or int64 [B, L] tensor, on this rank's device.
+        """keys: StringColumn (dense [B, L] or jagged), int64 [B, L] tensor (hashed as decimal strings, like Keras
+        Hashing), or BucketIds (pre-hashed ids), on this rank's device.
         Every rank must call with the same batch size.  Returns [B, D] fp32."""
         if self.transport == "p2p":
             return self.finish(self.prepare(keys, overlap=False), out)

@@ -48,6 +48,30 @@ def _worker(rank, world, port, q):
                 torch.cuda.synchronize()
                 got = got.cpu().numpy()
                 out[(combiner, transport)] = (bool(np.array_equal(got, want)), float(np.abs(got - seq).max()))
+        # combine-free mode: the owners reduce into the source's buffer (red.global.add over NVLink); summation order
+        # across owners is free, so the check is the re-association bound against the sequential oracle
+        from recommendflow_b200.sharded import BucketIds
+        for combiner in ("avg", "sum"):
+            seq = oracle.bag_pool(ids, full, combiner, bag_offsets=bag)
+            layer = ShardedEmbeddingBag(N, D, combiner=combiner, salt=None, mask_value="", max_batch=B, max_keys=B * 200,
+                                        deterministic=False)
+            layer.set_full_weights(full)
+            for _ in range(3):
+                got = layer(col)
+            # pipelined prepare / finish on the three streams gives the same values
+            t0 = layer.prepare(col)
+            t1 = layer.prepare(col)
+            a = layer.finish(t0).clone()
+            b = layer.finish(t1).clone()
+            torch.cuda.synchronize()
+            err = max(float(np.abs(x.cpu().numpy() - seq).max()) for x in (got, a, b))
+            out[(combiner, "p2p-accumulate")] = (True, err)
+        # pre-hashed ids (SURVEY.md §8d C4 "pre-hashed path"): routing skips the hash
+        want = sharded_reference(ids, bag, full, world, "avg")
+        layer = ShardedEmbeddingBag(N, D, combiner="avg", salt=None, mask_value="", max_batch=B, max_keys=B * 200)
+        layer.set_full_weights(full)
+        got = layer(BucketIds(torch.from_numpy(ids).to(f"cuda:{rank}"), col.bag_offsets)).cpu().numpy()
+        out[("avg", "p2p-prehashed")] = (bool(np.array_equal(got, want)), 0.0)
         # dense [B, L] padded input (reference semantics: pads pool row 0 of owner 0)
         L = 6
         a2, o2 = oracle.encode_strings([f"k{rank}_{i % 37}" if i % 5 else "" for i in range(B * L)])
