@@ -61,6 +61,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-c4", action="store_true", help="skip the row-sharded C4 measurement appended to the line")
+    ap.add_argument("--no-c3", action="store_true", help="skip the C3 end-to-end forward appended to the line (N = 1)")
     return ap.parse_args()
 
 
@@ -258,6 +259,198 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------
+# host <-> device copy ceiling of this box, measured with every rank copying at once
+# ------------------------------------------------------------------------------------------
+def numa_node_of_gpu(index):
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        path = f"/sys/bus/pci/devices/{bus.lower()[-12:]}/numa_node"
+        return int(open(path).read())
+    except Exception:
+        return None
+
+
+def pcie_diagnostics(dev, world, rank, dist):
+    """Plain pinned-memory copies, all ranks at the same time: the D2H / H2D bandwidth each rank gets while the others
+    copy too.  It is the ceiling of the e2e number above (436 MB of pooled vectors leave the GPU every step) and shows
+    whether the multi-GPU e2e collapse is this box's host side (shared PCIe uplinks / one NUMA node) or ours."""
+    import torch
+    n = 256 << 20
+    d = torch.empty(n, dtype=torch.uint8, device=dev)
+    h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    res = {}
+    for name, (src, dst) in {"d2h": (d, h), "h2d": (h, d)}.items():
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(4):
+            dst.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        gbs = 4 * n / (e0.elapsed_time(e1) / 1e3) / 1e9
+        if dist is not None:
+            t = torch.tensor([gbs, gbs], dtype=torch.float64, device=dev)
+            tmin, tsum = t[:1].clone(), t[1:].clone()
+            dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            res[f"concurrent_{name}_gbs_per_rank_min"] = float(tmin.item())
+            res[f"concurrent_{name}_gbs_all_ranks"] = float(tsum.item())
+        else:
+            res[f"concurrent_{name}_gbs_per_rank_min"] = gbs
+            res[f"concurrent_{name}_gbs_all_ranks"] = gbs
+    res["gpu_numa_node"] = numa_node_of_gpu(dev.index or 0)
+    return res
+
+
+# ------------------------------------------------------------------------------------------
+# C3 end to end (BASELINE.json configs[2]): the full recall-SDPA forward, host keys in, loss out
+# ------------------------------------------------------------------------------------------
+def run_c3full(dev, steps, warmup, with_cpu=True):
+    """base_recall_sdpa two-tower forward at batch 8192 on one GPU: 228 hashed features (2 SipHash tables of 100000 x 8
+    each) -> ONE fused bag launch; a hashed behaviour SEQUENCE of up to 50 items -> [B, 50, 64] embeddings ->
+    MultiHeadAttention (tcgen05 Dense projections + tcgen05 SDPA) -> mean; towers [1024, 512, 256] (BatchNormalization
+    folded, selu, tcgen05 GEMMs, l2 norm in the last epilogue); in-batch softmax loss (tcgen05).  e2e: pinned host key
+    buffers -> H2D -> forward -> D2H of the loss, every step.  CPU baseline: the same forward through the oracle."""
+    import torch
+    from recommendflow_b200 import _native as nat
+    from recommendflow_b200.backend.layers.preprocess_layers import HashedEmbeddingBag
+    from recommendflow_b200.config_parser import Configuration
+    from recommendflow_b200.models.matching.recall_sdpa import RecallSdpa
+    from recommendflow_b200.strings import StringColumn
+    from recommendflow_b200.synth import PackedBatch, c2_field_keys, decimal_keys
+
+    B, S, dm, NBAT = 8192, 50, 64, 2
+    cfg = os.path.join(ROOT, "tests", "golden", "configs", "synth_recall_sdpa")
+    conf = Configuration(cfg + ".yaml", slot_map_path=cfg + ".feature.map")
+    torch.manual_seed(0)
+    model = RecallSdpa(conf, behaviour_dim=dm, num_heads=1)
+    names = model.user_cols + model.ad_cols
+    beh = HashedEmbeddingBag(100_000, dm, "null", salt=None, mask_value="", mask_zero=True, name="hashing_behaviour")
+    model.build(dev)
+    beh.build(dev)
+    host, devb = [], []
+    for bi in range(NBAT):
+        rng = np.random.default_rng(555 + bi)
+        fields = {}
+        for i, n in enumerate(names):
+            arena, offs = c2_field_keys(i, B, 1, batch_index=bi)
+            fields[n] = (arena, offs, (B, 1))
+        lens = rng.integers(1, S + 1, size=B)
+        valid = np.arange(S)[None, :] < lens[:, None]
+        arena, offs = decimal_keys(b"item_", rng.integers(0, 10**7, size=int(valid.sum())))
+        klen = np.zeros(B * S, dtype=np.int64)
+        klen[valid.reshape(-1)] = np.diff(offs)
+        boffs = np.zeros(B * S + 1, dtype=np.int32)
+        boffs[1:] = np.cumsum(klen)                                     # pads are empty strings, like the dataloader's ""
+        h = {"keys": PackedBatch.pack(fields, pin=True),
+             "beh": StringColumn.from_arena(arena, boffs, (B, S)).pin_memory(),
+             "mask": torch.from_numpy(valid.astype(np.float32)[:, :, None].copy()).pin_memory(),
+             "y": torch.ones(B).pin_memory(), "np": (fields, arena, boffs, valid)}
+        host.append(h)
+        devb.append({"keys": h["keys"].to(dev), "beh": h["beh"].to(dev), "mask": h["mask"].to(dev), "y": h["y"].to(dev)})
+
+    def forward(b):
+        with torch.no_grad():
+            embs = model.preprocessor.forward_all(b["keys"], names=names)
+            x = beh(b["beh"])                                           # [B, S, 64]: the behaviour sequence's embeddings
+            u, a = model.towers_from_embeddings(embs, (x, b["mask"]))
+            return model.loss_fun(b["y"], u, a)
+
+    def e2e_step(i):
+        h = host[i % NBAT]
+        b = {"keys": h["keys"], "beh": h["beh"].to(dev, non_blocking=True), "mask": h["mask"].to(dev, non_blocking=True),
+             "y": h["y"].to(dev, non_blocking=True)}
+        return float(forward(b).item())                                 # D2H of the scalar + sync: the step's result
+
+    for i in range(max(warmup, 3)):
+        forward(devb[i % NBAT])
+    torch.cuda.synchronize()
+    l0 = nat.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss = forward(devb[i % NBAT])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    launches = nat.launch_count() - l0
+    for i in range(3):
+        e2e_step(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        gpu_loss = e2e_step(i)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
+    h2d = int(host[0]["keys"].nbytes + host[0]["beh"].nbytes + 4 * host[0]["beh"].offsets.numel() + host[0]["mask"].numel() * 4 + B * 4)
+    res = {"workload": "c3full: base_recall_sdpa two-tower forward, batch 8192: 228 hashed features x 2 tables of 100000 x 8 "
+                       "(one fused launch), hashed behaviour sequence <= 50 x 64 -> MultiHeadAttention (tcgen05) -> mean, "
+                       "towers [1024, 512, 256] selu + BatchNormalization (tcgen05 Dense, folded), l2 norm, in-batch softmax (tcgen05)",
+           "metric": "recall-SDPA forward samples/sec", "unit": UNIT, "value": B / (ms / 1e3), "ms_per_step": ms, "steps": steps,
+           "gpu_launches_per_step": launches / steps,
+           "e2e": {"value": B / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                   "path": "pinned host key arenas (+ mask, labels) -> H2D -> forward_all / HashedEmbeddingBag / towers / loss -> "
+                           "D2H of the loss scalar"}}
+    if with_cpu:
+        import oracle
+        threads = cpu_threads()
+        W = {}
+        for n in names:
+            layer = model.preprocessor[n]
+            W[n] = [w for w in layer.get_weights()]
+        wb = beh.get_weights()[0]
+        att = model.seq_encoder
+        proj = [tuple(d.get_weights()) for d in (att.wq, att.wk, att.wv)]
+
+        def tower_stages(seq):
+            stages, d = [], None
+            for norm, act in seq._stages():
+                d = act.dense.kernel.shape[0]
+                gamma, beta, mean, var = (t.detach().cpu().numpy() for t in norm.state(d))
+                k, bias = act.dense.get_weights()
+                stages.append((gamma, beta, mean, var, k, bias, act.activation))
+            return stages
+        ustages, astages = tower_stages(model.user_dense), tower_stages(model.ad_dense)
+
+        def cpu_forward(h):
+            fields, arena, boffs, valid = h["np"]
+            cols = []
+            for n in names:
+                a, o, _ = fields[n]
+                cols.append(oracle.hashed_bag_forward(a, o, B, 1, W[n], [100_000, 100_000], [2022, 2023], "sum"))
+            ids = oracle.hash_strings(arena, boffs, 100_000, "", None)
+            x = oracle.gather_rows(ids, wb).reshape(B, S, dm)
+            seq = oracle.multi_head_attention(x, valid.astype(np.float32), *proj, 1).mean(axis=1)
+            nu = len(model.user_cols)
+            u = oracle.tower_mlp(np.concatenate(cols[:nu] + [seq], axis=1), ustages, eps=1e-6)
+            a_ = oracle.tower_mlp(np.concatenate(cols[nu:], axis=1), astages, eps=1e-6)
+            return oracle.inbatch_softmax_ce(np.ones(B, np.float32), u, a_, 20.0)[0]
+
+        cpu_loss = cpu_forward(host[(steps - 1) % NBAT])                # also the warm-up
+        t0, n = time.perf_counter(), 0
+        while n < 8 and (n == 0 or time.perf_counter() - t0 < 12.0):
+            cpu_forward(host[n % NBAT])
+            n += 1
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": n * B / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                               "sample": f"{n} full batch(es) of {B} samples through the oracle port of the same forward "
+                                         f"(oracle/rf_oracle.c: hashing, bags, Dense, SDPA, softmax CE; OpenMP, {threads} threads) "
+                                         f"in {dt:.2f} s"}
+        res["e2e_vs_cpu_baseline"] = res["e2e"]["value"] / res["cpu_baseline"]["value"]
+        rel = abs(gpu_loss - cpu_loss) / max(abs(cpu_loss), 1e-9)
+        res["parity_check"] = f"GPU loss {gpu_loss:.6f} vs oracle loss {cpu_loss:.6f} (rel. diff {rel:.2e}; TF32 tensor-core tolerance 2e-2)"
+        if not rel <= 2e-2:
+            raise SystemExit("bench c3full: " + res["parity_check"])
+    del model, beh, devb
+    torch.cuda.empty_cache()
+    return res
+
+
+# ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -351,12 +544,29 @@ def run_ours(args):
     ms_per_step = total_ms / K
     value = world * B / (ms_per_step / 1e3)
 
-    # ---- end to end: host key buffers in, pooled vectors out to host, every step ---------------
+    # ---- end to end THROUGH THE LAYER API: host key buffers in, pooled vectors out to host, every step ---------
     e2e = None
     if not args.no_e2e:
-        # The batch crosses PCIe in E2E_CHUNKS row chunks on two streams, so the D2H of one chunk's pooled
-        # vectors overlaps the H2D + kernel of the next (PCIe is full duplex); every step still moves all
-        # key bytes in and all pooled vectors out, and the host result is complete at the end of the step.
+        # The plugin call is `layers.forward_all(batch)` on the mapping get_preprocess_layers returns
+        # (backend/utils/preprocess_utils.py): here one HashedEmbeddingBag (T = 1) / DoubleHashingEmbedding (T = 2) per
+        # field holding the same tables.  The batch is a pinned host PackedBatch (one arena + one offsets buffer);
+        # forward_all copies it to the device (2 copies), builds the launch descriptors and launches the fused kernel.
+        # The batch crosses PCIe in E2E_CHUNKS row chunks on two streams so that the D2H of one chunk's pooled vectors
+        # overlaps the H2D + kernel of the next (PCIe is full duplex); every step still moves all key bytes in and all
+        # pooled vectors out, and the host result is complete at the end of the step.
+        from recommendflow_b200.backend.layers.preprocess_layers import HashedEmbeddingBag
+        from recommendflow_b200.backend.utils.preprocess_utils import PreprocessLayers
+        layers = PreprocessLayers()
+        for f, n in enumerate(names):
+            if T == 1:
+                layer = HashedEmbeddingBag(N, D, "sum", salt=None, mask_value="", mask_zero=True, name=f"hashing_{n}")
+                layer.emb.embeddings = torch.nn.Parameter(tables[f][0], requires_grad=False)
+            else:
+                layer = DoubleHashingEmbedding(num_bins=N, output_dim=D, seeds=[2022, 2023], combiner="sum", mask_value="",
+                                               mask_zero=True, name=f"hashing_{n}")
+                layer.emb1.embeddings = torch.nn.Parameter(tables[f][0], requires_grad=False)
+                layer.emb2.embeddings = torch.nn.Parameter(tables[f][1], requires_grad=False)
+            layers[n] = layer
         n_chunks = E2E_CHUNKS if B % E2E_CHUNKS == 0 and B >= 4096 else 1
         rows = B // n_chunks
         host_chunks = []                                   # [batch][chunk] -> pinned PackedBatch of `rows` samples
@@ -370,36 +580,14 @@ def run_ours(args):
                     fields[fname] = (arena[o[0]:o[-1]], (o - o[0]).astype(np.int32), (rows, L))
                 per.append(PackedBatch.pack(fields, pin=True))
             host_chunks.append(per)
-        max_b = max(int(h.data.numel()) for per in host_chunks for h in per)
-        max_o = max(int(h.offsets.numel()) for per in host_chunks for h in per)
         streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
-        stages = [PackedBatch(torch.empty(max_b, dtype=torch.uint8, device=dev),
-                              torch.empty(max_o, dtype=torch.int32, device=dev), None) for _ in range(2)]
         host_out = torch.empty(B, F * T * D, dtype=torch.float32).pin_memory()
-
-        # one launch plan per (key batch, chunk): the staging buffers and the output rows are static
-        e2e_plans = {}
-
-        def plan_for(bi, c, hp):
-            if (bi, c) not in e2e_plans:
-                stage = stages[c % 2]
-                stage.layout = hp.layout
-                cols = stage.columns()
-                o = out[c * rows:(c + 1) * rows]
-                e2e_plans[(bi, c)] = BagPlan(
-                    [FieldCall([(tables[f][t], N, salts[t]) for t in range(T)], D, "sum", keys=cols[n],
-                               mask_mode=nat.MASK_EMPTY_STRING, out=o[:, f * T * D:(f + 1) * T * D], bag_len=L)
-                     for f, n in enumerate(names)], rows)
-            return e2e_plans[(bi, c)]
 
         def e2e_step(i):
             bi = i % N_KEY_BATCHES
             for c, hp in enumerate(host_chunks[bi]):
-                st, stage = streams[c % 2], stages[c % 2]
-                with torch.cuda.stream(st):
-                    stage.data[:hp.data.numel()].copy_(hp.data, non_blocking=True)
-                    stage.offsets[:hp.offsets.numel()].copy_(hp.offsets, non_blocking=True)
-                    plan_for(bi, c, hp).launch()
+                with torch.cuda.stream(streams[c % 2]):
+                    layers.forward_all(hp, names=names, out=out[c * rows:(c + 1) * rows])
                     host_out[c * rows:(c + 1) * rows].copy_(out[c * rows:(c + 1) * rows], non_blocking=True)
 
         torch.cuda.synchronize()
@@ -414,6 +602,11 @@ def run_ours(args):
             torch.cuda.synchronize()          # the caller consumes the complete host result every step
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / ke
+        # the layer call's host result equals the kernel-only path's, bit for bit
+        step((ke - 1) % N_KEY_BATCHES)
+        torch.cuda.synchronize()
+        if not torch.equal(host_out, out.cpu()):
+            raise SystemExit("bench: e2e (forward_all) output differs from the BagPlan launch")
         if world > 1:
             t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -422,8 +615,11 @@ def run_ours(args):
                "h2d_bytes_per_step": int(np.mean([sum(h.nbytes for h in per) for per in host_chunks])),
                "d2h_bytes_per_step": int(host_out.numel() * 4), "ms_per_step": e2e_ms, "steps": ke,
                "gpu_launches": int(nat.launch_count() - launches_e2e0),
-               "path": f"pinned host key arena+offsets -> H2D -> rf_bag_forward -> D2H of the pooled [B, sum(T*D)] fp32, "
-                       f"{n_chunks} row chunks on 2 streams (copy/compute overlap)"}
+               "path": f"pinned host PackedBatch -> PreprocessLayers.forward_all (H2D of arena + offsets, descriptors, "
+                       f"rf_bag_forward) -> D2H of the pooled [B, sum(T*D)] fp32; {n_chunks} row chunks on 2 streams "
+                       f"(copy/compute overlap)"}
+        e2e.update(pcie_diagnostics(dev, world, rank, dist if world > 1 else None))
+        del layers
 
     # ---- roofline of the one kernel ------------------------------------------------------------
     peaks = {}
@@ -469,14 +665,19 @@ def run_ours(args):
         del tables, all_calls, dev_cols, dev_packed, out
         torch.cuda.empty_cache()
         from tools.bench_sharded import parse as c4_parse, run as c4_run
-        c4 = c4_run(c4_parse(["--batch", "65536", "--steps", "20", "--warmup", "5", "--transport", "p2p"]), world, rank, dev)
+        c4 = c4_run(c4_parse(["--steps", "20", "--warmup", "5"]), world, rank, dev)
+
+    # ---- C3 end to end (host keys -> bags -> SDPA -> towers -> loss -> host), rank 0 of a single-GPU run ----
+    c3 = None
+    if not args.no_c3 and name == "c2" and world == 1:
+        c3 = run_c3full(dev, 20, 5, with_cpu=not args.no_cpu_baseline)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 pooling / u64 hashing", "data": "synthetic", "config": workload_config(name, world),
                 "gpu_launches": int(launches), "clocks": clocks.summary(), "e2e": e2e, "roofline": roofline,
-                "cpu_baseline": cpu, "parity_check": parity, "sharded_c4": c4}
+                "cpu_baseline": cpu, "parity_check": parity, "sharded_c4": c4, "c3full": c3}
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)

@@ -175,6 +175,22 @@ int rf_inbatch_rowstats_tc(const float *d_query, const float *d_doc, const float
                            float *d_lse, float *d_diag, float *d_hinge, float *d_maxoff, float *d_loss,
                            void *stream);
 
+/* ---- Keras Dense on the tensor cores: out = activation(x . W + b) (+ optional row l2-normalisation) ---------- */
+/* The tower MLP of backend/blocks/mlp.py:4-15 ([norm, Dense(units, activation), Dropout] * n; models/matching/     */
+/* dssm.py:25-26: [1024, 512, 256], selu, BatchNormalization(1e-6)) and the Dense q/k/v projections of              */
+/* backend/layers/attention_layers.py:141-155.  x: device [rows, in_dim] fp32 with row pitch ldx (floats);           */
+/* weight_t: device [units, in_dim] fp32 = the TRANSPOSE of the Keras kernel [in_dim, units] (K-major for the       */
+/* tensor core); bias: device [units] or NULL; out: device [rows, units] with row pitch ldo.  Operands are read as  */
+/* TF32 (fp32 accumulate).  An inference-mode BatchNormalization in front of the Dense is folded into weight_t /    */
+/* bias by the caller.  l2_normalize != 0 divides every output row by max(||row||_2, 1e-12) in the same epilogue    */
+/* (units <= 256).  in_dim, units, ldx, ldo multiples of 4; 16-byte aligned buffers; else RF_ERR_UNSUPPORTED.        */
+typedef enum rf_activation {
+    RF_ACT_NONE = 0, RF_ACT_RELU = 1, RF_ACT_SELU = 2, RF_ACT_TANH = 3, RF_ACT_SIGMOID = 4, RF_ACT_GELU = 5
+} rf_activation;
+int rf_dense_forward_tc(const float *d_x, int64_t rows, int32_t in_dim, int64_t ldx, const float *d_weight_t,
+                        const float *d_bias, int32_t units, int activation, int l2_normalize, float *d_out,
+                        int64_t ldo, void *stream);
+
 /* ---- row-sharded tables (new design; the reference only replicates tables,   */
 /* backend/utils/gpu_utils.py:13-14).  Row id lives on rank id % world as local row id / world. */
 /* rf_shard_route partitions the hashed ids of one field by owner, keeping bag order: for every */

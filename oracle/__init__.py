@@ -179,6 +179,52 @@ def inbatch_softmax_ce(y_true, query, doc, scale=20.0):
     return float(loss), lse, diag
 
 
+ACTIVATIONS = {None: 0, "linear": 0, "relu": 1, "selu": 2, "tanh": 3, "sigmoid": 4, "gelu": 5}
+
+
+def dense(x, kernel, bias=None, activation=None):
+    """Keras Dense(units, activation): act(x @ kernel + bias); kernel [in, units] (backend/blocks/mlp.py:4-15)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1])
+    w = np.ascontiguousarray(kernel, dtype=np.float32)
+    b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+    out = np.empty((x2.shape[0], w.shape[1]), dtype=np.float32)
+    lib().rfo_dense(_p(x2), C.c_int64(x2.shape[0]), C.c_int64(x2.shape[1]), _p(w), _p(b), C.c_int64(w.shape[1]),
+                    C.c_int(ACTIVATIONS[activation]), _p(out))
+    return out.reshape(*lead, w.shape[1])
+
+
+def batchnorm_inference(x, gamma, beta, mean, var, eps):
+    """Keras BatchNormalization(training=False): gamma * (x - mean) / sqrt(var + eps) + beta."""
+    return ((x - mean) * (gamma / np.sqrt(var + np.float32(eps))) + beta).astype(np.float32)
+
+
+def tower_mlp(x, stages, eps=1e-6, l2_normalize=True):
+    """create_mlp([..], dropout, activation, BatchNormalization(eps)) at inference (mlp.py:4-15, dssm.py:25-26):
+    stages = [(gamma, beta, mean, var, kernel, bias, activation), ...]; then K.l2_normalize per row."""
+    h = np.ascontiguousarray(x, dtype=np.float32)
+    for gamma, beta, mean, var, kernel, bias, act in stages:
+        if gamma is not None:
+            h = batchnorm_inference(h, gamma, beta, mean, var, eps)
+        h = dense(h, kernel, bias, act)
+    if l2_normalize:
+        h = h / np.maximum(np.sqrt((h * h).sum(axis=1, keepdims=True)), np.float32(1e-12))
+    return h.astype(np.float32)
+
+
+def multi_head_attention(x, mask, wq, wk, wv, num_heads):
+    """MultiHeadAttention(d_model, num_heads).call(x, x, x, mask) (attention_layers.py:137-168): Dense q/k/v with
+    bias, split heads, scaled_dot_product_attention with the query-row mask, merge; no output projection."""
+    B, S, d = x.shape
+    q, k, v = (dense(x, w, b) for w, b in (wq, wk, wv))
+    depth = d // num_heads
+    split = lambda t: np.ascontiguousarray(t.reshape(B, S, num_heads, depth).transpose(0, 2, 1, 3))
+    m = np.broadcast_to(np.asarray(mask, dtype=np.float32).reshape(B, 1, S, 1), (B, num_heads, S, 1))
+    att = sdpa(split(q), split(k), split(v), m)
+    return att.transpose(0, 2, 1, 3).reshape(B, S, d)
+
+
 def num_threads():
     return int(lib().rfo_num_threads())
 

@@ -437,6 +437,43 @@ void rfo_bag_backward_adam(const int64_t *ids, int64_t n_keys, const int32_t *ba
     }
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* Keras Dense: out[M,N] = act(x[M,K] . W[K,N] + b[N]), W = the Keras kernel [in, units]        */
+/* (backend/blocks/mlp.py:4-15: keras.layers.Dense(units, activation); attention_layers.py:141). */
+/* fp32 accumulation in k order (what TF's CPU kernel class does), one output row at a time.     */
+/* act: 0 none, 1 relu, 2 selu, 3 tanh, 4 sigmoid, 5 gelu (erf form, the Keras default).         */
+/* ------------------------------------------------------------------------------------------ */
+void rfo_dense(const float *x, int64_t M, int64_t K, const float *W, const float *b, int64_t N, int act, float *out) {
+#pragma omp parallel
+    {
+        float *acc = (float *)malloc((size_t)N * sizeof(float));
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < M; ++i) {
+            for (int64_t j = 0; j < N; ++j) acc[j] = 0.0f;
+            const float *xi = x + i * K;
+            for (int64_t k = 0; k < K; ++k) {
+                const float a = xi[k];
+                const float *w = W + k * N;
+                for (int64_t j = 0; j < N; ++j) acc[j] += a * w[j];
+            }
+            float *o = out + i * N;
+            for (int64_t j = 0; j < N; ++j) {
+                float z = acc[j] + (b ? b[j] : 0.0f);
+                switch (act) {
+                    case 1: z = z > 0.0f ? z : 0.0f; break;
+                    case 2: z = z > 0.0f ? 1.0507009873554805f * z : 1.0507009873554805f * 1.6732632423543772f * expm1f(z); break;
+                    case 3: z = tanhf(z); break;
+                    case 4: z = 1.0f / (1.0f + expf(-z)); break;
+                    case 5: z = 0.5f * z * (1.0f + erff(z * 0.70710678118654752f)); break;
+                    default: break;
+                }
+                o[j] = z;
+            }
+        }
+        free(acc);
+    }
+}
+
 int rfo_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -12,6 +12,7 @@ RF_OK, RF_ERR_INVALID, RF_ERR_CUDA, RF_ERR_UNSUPPORTED = 0, -1, -2, -3
 COMBINER = {"sum": 0, "avg": 1, "min": 2, "max": 3}
 MASK_NONE, MASK_EMPTY_STRING, MASK_INT_VALUE, MASK_STRING_VALUE = 0, 1, 2, 3
 MAX_MASK_BYTES = 32
+ACTIVATION = {None: 0, "linear": 0, "relu": 1, "selu": 2, "tanh": 3, "sigmoid": 4, "gelu": 5}
 MAX_TABLES = 2
 FIELD_PARTIAL = 1
 FIELD_ACCUMULATE = 2
@@ -93,6 +94,9 @@ def lib():
         L.rf_sdpa_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                       C.c_void_p, C.c_void_p]
         L.rf_sdpa_forward_tc.argtypes = L.rf_sdpa_forward.argtypes
+        L.rf_dense_forward_tc.restype = C.c_int
+        L.rf_dense_forward_tc.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int,
+                                          C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
         L.rf_inbatch_workspace_bytes.restype = C.c_int64
         L.rf_inbatch_workspace_bytes.argtypes = [C.c_int64]
         L.rf_inbatch_rowstats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float,

@@ -5,12 +5,18 @@ Reference quirk kept: the SAME normalization layer instance is appended before e
 one BatchNormalization would be applied to inputs of different widths -- Keras builds it on the first
 width and fails on the second unless all widths are equal.  Here the shared instance keeps one set of
 statistics per distinct width (the only way the reference's towers [1024, 512, 256] can run at all).
-Dense layers are library GEMMs (cuBLAS via torch).  Inference mode (moving statistics, no dropout) unless a
-training step switches `BatchNormalization.batch_stats` / `Dropout.active` on (recommendflow_b200/training.py).
+
+Inference (no gradient being recorded, moving statistics, no dropout): every [norm, Dense, activation] stage is
+ONE launch of the tcgen05 GEMM rf_dense_forward_tc -- BatchNormalization is an affine map per input column there
+and is folded into the Dense kernel and bias (cached until a weight changes); the last stage can also l2-normalise
+its rows in the same epilogue.  Under autograd (recommendflow_b200/training.py: batch statistics, dropout) the stages
+run as library GEMMs + elementwise torch ops, whose backward torch provides.
+All learned state is registered (Parameters / buffers), so it is part of `state_dict()`.
 """
 import torch
 
-from ..layers.attention_layers import Dense
+from ... import dense_ops
+from ..layers.attention_layers import Dense, library_matmul
 from ..layers.preprocess_layers import Layer
 
 
@@ -23,56 +29,61 @@ _ACT = {None: lambda x: x, "linear": lambda x: x, "relu": torch.relu, "selu": _s
 
 
 class BatchNormalization(Layer):
-    """Keras BatchNormalization at inference: gamma * (x - moving_mean) / sqrt(moving_var + eps) + beta."""
+    """Keras BatchNormalization: gamma * (x - mean) / sqrt(var + eps) + beta, moving statistics at inference,
+    batch statistics (and a moving-average update) when `batch_stats` is on (Keras training=True)."""
 
     def __init__(self, epsilon=1e-3, momentum=0.99, name=None):
         super().__init__(name=name)
         self.epsilon = epsilon
         self.momentum = momentum
-        self.stats = {}          # width -> (gamma, beta, moving_mean, moving_var)
         self.batch_stats = False  # True during a training step: normalise with the batch's own statistics
+
+    # ---- per-width state: gamma_<d>, beta_<d> (Parameters), moving_mean_<d>, moving_var_<d> (buffers) --------------
+    def widths(self):
+        return sorted(int(k.split("_")[1]) for k in self._parameters if k.startswith("gamma_"))
+
+    def ensure(self, d, device=None):
+        if f"gamma_{d}" not in self._parameters:
+            self.register_parameter(f"gamma_{d}", torch.nn.Parameter(torch.ones(d, device=device), requires_grad=False))
+            self.register_parameter(f"beta_{d}", torch.nn.Parameter(torch.zeros(d, device=device), requires_grad=False))
+            self.register_buffer(f"moving_mean_{d}", torch.zeros(d, device=device))
+            self.register_buffer(f"moving_var_{d}", torch.ones(d, device=device))
+        return self
+
+    def state(self, d):
+        return (getattr(self, f"gamma_{d}"), getattr(self, f"beta_{d}"), getattr(self, f"moving_mean_{d}"),
+                getattr(self, f"moving_var_{d}"))
 
     def set_weights(self, weights):
         gamma, beta, mean, var = (torch.as_tensor(w, dtype=torch.float32) for w in weights)
-        self.stats[int(gamma.numel())] = (gamma, beta, mean, var)
+        d = int(gamma.numel())
+        dev = self.state(d)[0].device if f"gamma_{d}" in self._parameters else (
+            torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None)
+        self.ensure(d, dev)
+        with torch.no_grad():
+            for dst, src in zip(self.state(d), (gamma, beta, mean, var)):
+                dst.copy_(src.to(dst.device))
+
+    def affine(self, d):
+        """(scale, shift) of the inference-mode map x -> x * scale + shift for inputs of width d."""
+        gamma, beta, mean, var = self.state(d)
+        scale = gamma * torch.rsqrt(var + self.epsilon)
+        return scale, beta - mean * scale
+
+    def versions(self, d):
+        return tuple((t.data_ptr(), t._version) for t in self.state(d))
 
     def call(self, x):
         d = x.shape[-1]
-        if d not in self.stats:
-            self.stats[d] = (torch.ones(d), torch.zeros(d), torch.zeros(d), torch.ones(d))
-        gamma, beta, mean, var = (t.to(x.device) for t in self.stats[d])
+        self.ensure(d, x.device)
+        gamma, beta, mean, var = self.state(d)
         if self.batch_stats:     # Keras training=True: batch mean / biased variance, moving statistics updated
             bmean, bvar = x.mean(dim=0), x.var(dim=0, unbiased=False)
             with torch.no_grad():
-                mean = mean * self.momentum + bmean.detach() * (1 - self.momentum)
-                var = var * self.momentum + bvar.detach() * (1 - self.momentum)
-            self.stats[d] = (gamma, beta, mean, var)
+                mean.mul_(self.momentum).add_(bmean.detach() * (1 - self.momentum))
+                var.mul_(self.momentum).add_(bvar.detach() * (1 - self.momentum))
             return (x - bmean) * (gamma * torch.rsqrt(bvar + self.epsilon)) + beta
-        self.stats[d] = (gamma, beta, mean, var)
         return (x - mean) * (gamma * torch.rsqrt(var + self.epsilon)) + beta
-
-    def trainable(self):
-        """gamma / beta of every width seen so far, as leaves that require grad."""
-        out = []
-        for d, (gamma, beta, mean, var) in list(self.stats.items()):
-            gamma, beta = gamma.detach().requires_grad_(True), beta.detach().requires_grad_(True)
-            self.stats[d] = (gamma, beta, mean, var)
-            out += [gamma, beta]
-        return out
-
-
-class Sequential(Layer):
-    def __init__(self, layers, name=None):
-        super().__init__(name=name)
-        self.layers = list(layers)
-        for i, l in enumerate(self.layers):
-            if isinstance(l, torch.nn.Module):
-                self.add_module(f"l{i}", l)
-
-    def call(self, x):
-        for layer in self.layers:
-            x = layer(x)
-        return x
 
 
 class _Activated(Layer):
@@ -84,7 +95,11 @@ class _Activated(Layer):
         self.activation = activation
 
     def call(self, x):
-        return _ACT[self.activation](self.dense(x))
+        self.dense.build(x.shape[-1], x.device)
+        if (dense_ops.DEFAULT_PRECISION == "tf32" and not self.dense.recording_grad(x)
+                and dense_ops.dense_tc_ok(x, self.dense.kernel.shape[0], self.dense.units)):
+            return dense_ops.dense_forward(x, self.dense.kernel_t(), self.dense.bias, self.activation)
+        return _ACT[self.activation](library_matmul(x, self.dense.kernel) + self.dense.bias)
 
 
 class Dropout(Layer):
@@ -97,6 +112,83 @@ class Dropout(Layer):
 
     def call(self, x):
         return torch.nn.functional.dropout(x, self.rate, training=True) if self.active and self.rate > 0 else x
+
+
+class Sequential(Layer):
+    def __init__(self, layers, name=None):
+        super().__init__(name=name)
+        self.layers = list(layers)
+        for i, l in enumerate(self.layers):
+            if isinstance(l, torch.nn.Module):
+                self.add_module(f"l{i}", l)
+        self._folded = {}
+
+    # ---- inference: [BatchNormalization, Dense + activation, Dropout] = one tensor-core launch ------------------------
+    def _stages(self):
+        """Group the layer list into (norm or None, _Activated) stages; None if the list has another shape."""
+        stages, norm = [], None
+        for l in self.layers:
+            if isinstance(l, BatchNormalization) and norm is None:
+                norm = l
+            elif isinstance(l, _Activated):
+                stages.append((norm, l))
+                norm = None
+            elif isinstance(l, Dropout):
+                continue
+            else:
+                return None
+        return stages if norm is None else None
+
+    def _folded_weights(self, idx, norm, act, in_dim):
+        """(weight_t [units, in], bias [units]) of stage idx with the inference-mode normalisation folded in:
+        (x * s + t) W + b = x (diag(s) W) + (t W + b).  Cached until the kernel, bias or statistics change."""
+        dense = act.dense
+        key = (dense.kernel.data_ptr(), dense.kernel._version, dense.bias.data_ptr(), dense.bias._version,
+               norm.versions(in_dim) if norm is not None else None)
+        hit = self._folded.get(idx)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                if norm is None:
+                    wt, b = dense.kernel_t(), dense.bias.detach()
+                else:
+                    scale, shift = norm.affine(in_dim)
+                    wt = (dense.kernel.detach().t() * scale[None, :]).contiguous()
+                    b = dense.bias.detach() + shift @ dense.kernel.detach()
+            hit = (key, wt, b)
+            self._folded[idx] = hit
+        return hit[1], hit[2]
+
+    def _fusable(self, x, stages):
+        if stages is None or dense_ops.DEFAULT_PRECISION != "tf32" or not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2:
+            return False
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return False
+        for l in self.layers:
+            if (isinstance(l, BatchNormalization) and l.batch_stats) or (isinstance(l, Dropout) and l.active and l.rate > 0):
+                return False
+        d = x.shape[-1]
+        for norm, act in stages:
+            if d % 4 or act.dense.units % 4:
+                return False
+            d = act.dense.units
+        return True
+
+    def call(self, x, l2_normalize=False):
+        """l2_normalize: divide every output row by max(||row||, 1e-12) -- fused into the last stage's epilogue on
+        the tensor-core path (the towers' embedding_norm)."""
+        stages = self._stages()
+        if self._fusable(x, stages) and (not l2_normalize or stages[-1][1].dense.units <= 256):
+            for idx, (norm, act) in enumerate(stages):
+                d = x.shape[-1]
+                act.dense.build(d, x.device)
+                if norm is not None:
+                    norm.ensure(d, x.device)
+                wt, b = self._folded_weights(idx, norm, act, d)
+                x = dense_ops.dense_forward(x, wt, b, act.activation, l2_normalize and idx == len(stages) - 1)
+            return x
+        for layer in self.layers:
+            x = layer(x)
+        return torch.nn.functional.normalize(x, dim=1, eps=1e-12) if l2_normalize else x
 
 
 def create_mlp(hidden_units, dropout_rate, activation, normalization_layer, name=None):

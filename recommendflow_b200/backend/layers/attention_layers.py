@@ -1,9 +1,10 @@
 """`MultiHeadAttention` and `SelfAttention` with the reference's constructor and call surface
 (/root/reference/backend/layers/attention_layers.py:137-168 and :83-134).
 
-The attention core runs in rf_sdpa_forward (hand-written CUDA); the Dense q/k/v projections are
-plain library GEMMs (cuBLAS through torch.nn.functional.linear), as the task allows.  Keras
-`Dense` defaults are kept: glorot-uniform kernel, zero bias, no activation, no output projection.
+The attention core runs in rf_sdpa_forward[_tc]; the Dense q/k/v projections run in rf_dense_forward_tc (the
+tcgen05 GEMM with the bias / activation epilogue) whenever no gradient is being recorded -- under autograd (the
+training step) they are library GEMMs (cuBLAS through torch.matmul), whose backward torch provides.  Keras `Dense`
+defaults are kept: glorot-uniform kernel, zero bias, no activation, no output projection.
 """
 import math
 
@@ -53,8 +54,23 @@ class Dense(Layer):
     def get_weights(self):
         return [self.kernel.detach().cpu().numpy(), self.bias.detach().cpu().numpy()]
 
+    def kernel_t(self):
+        """[units, in] copy of the kernel (the K-major operand the tensor-core GEMM reads), refreshed when the
+        kernel tensor is replaced or updated in place."""
+        key = (self.kernel.data_ptr(), self.kernel._version)
+        if getattr(self, "_kt_key", None) != key:
+            self._kt = self.kernel.detach().t().contiguous()
+            self._kt_key = key
+        return self._kt
+
+    def recording_grad(self, x):
+        return torch.is_grad_enabled() and (x.requires_grad or self.kernel.requires_grad or self.bias.requires_grad)
+
     def call(self, x):
         self.build(x.shape[-1], x.device)
+        if (dense_ops.DEFAULT_PRECISION == "tf32" and not self.recording_grad(x) and self.activation in (None, "relu")
+                and dense_ops.dense_tc_ok(x, self.kernel.shape[0], self.units)):
+            return dense_ops.dense_forward(x, self.kernel_t(), self.bias, self.activation)
         y = library_matmul(x, self.kernel) + self.bias
         return torch.relu(y) if self.activation == "relu" else y
 

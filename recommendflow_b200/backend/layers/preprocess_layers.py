@@ -277,6 +277,53 @@ class DoubleHashingEmbedding(Layer):
         return cfg
 
 
+class HashedEmbeddingBag(Layer):
+    """Keras `Hashing(num_bins, mask_value, salt)` feeding ONE `EmbeddingBag`: the single-table form of
+    DoubleHashingEmbedding (same sub-layer naming, same pad semantics).  The reference only wires the double form
+    (preprocess_layers.py:79-106); this is the "hashed sparse field" of BASELINE.json's embedding microbenchmark
+    (salt=None: tf.strings.to_hash_bucket_fast = Fingerprint64 mod N) and, with combiner="null", the hashed
+    behaviour SEQUENCE whose [B, L, D] embeddings feed the SDPA encoder."""
+
+    def __init__(self, num_bins, output_dim, combiner="sum", salt=None, mask_value=None, mask_zero=False, name=""):
+        if num_bins is None or num_bins <= 0:
+            raise ValueError("`num_bins` cannot be `None` or non-positive values.")
+        super().__init__(name=name)
+        self.num_bins, self.output_dim, self.combiner, self.mask_value = num_bins, output_dim, combiner, mask_value
+        self.hash = Hashing(num_bins, mask_value=mask_value, name=f"{name}_hashing", salt=salt)
+        self.emb = EmbeddingBag(num_bins, output_dim, mask_zero, combiner=combiner, name=f"{name}_embedding_bag")
+
+    def build(self, device=None):
+        self.emb.build(device)
+        return self
+
+    _mask = DoubleHashingEmbedding._mask
+
+    def field_call(self, keys, out):
+        mode, imask, raw = self._mask(keys)
+        return FieldCall([(self.emb.embeddings.data, self.num_bins, self.hash.salt)], self.output_dim, self.combiner, keys=keys,
+                         mask_mode=mode, int_mask_value=imask, out=out, bag_len=_batch_and_len(keys)[1], mask_bytes=raw)
+
+    def call(self, inputs, *args, out=None, **kwargs):
+        self.emb._check_combiner()
+        keys = as_keys(inputs)
+        self.build(keys.device)
+        mode, imask, raw = self._mask(keys)
+        B, L = _batch_and_len(keys)
+        return _bags_forward([self.emb], self.combiner, B, L, keys=keys, salts=[self.hash.salt], mask_mode=mode,
+                             int_mask_value=imask, mask_bytes=raw, out=out)
+
+    def get_weights(self):
+        return self.emb.get_weights()
+
+    def set_weights(self, weights):
+        self.emb.set_weights(weights)
+
+    def get_config(self):
+        cfg = super().get_config()
+        cfg.update({"combiner": self.combiner, "num_bins": self.num_bins, "salt": self.hash.salt, "mask_value": self.mask_value})
+        return cfg
+
+
 class LookupEmbedding(Layer):
     """Vocabulary lookup (Keras StringLookup / IntegerLookup: term i -> i + 1, OOV -> 0) + EmbeddingBag
     (/root/reference/backend/layers/preprocess_layers.py:134-168).

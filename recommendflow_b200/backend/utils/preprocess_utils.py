@@ -10,8 +10,9 @@ batch through ONE kernel launch and hands back per-feature views of one [B, sum(
 """
 import torch
 
-from ..layers.preprocess_layers import (_POOLED, DiscreteEmbedding, DoubleHashingEmbedding, LookupEmbedding,
+from ..layers.preprocess_layers import (_POOLED, DiscreteEmbedding, DoubleHashingEmbedding, HashedEmbeddingBag, LookupEmbedding,
                                         _batch_and_len, _default_device, as_keys)
+from ...synth import PackedBatch
 from ...bag_ops import bag_forward
 
 
@@ -22,12 +23,14 @@ class PreprocessLayers(dict):
         """Features that join the fused launch: pooled hashing features, and pooled lookup / discrete
         features (their ids come from the vocabulary / bucketize kernels first)."""
         return [n for n, l in self.items()
-                if (isinstance(l, DoubleHashingEmbedding) and l.combiner in _POOLED)
+                if (isinstance(l, (DoubleHashingEmbedding, HashedEmbeddingBag)) and l.combiner in _POOLED)
                 or (isinstance(l, (LookupEmbedding, DiscreteEmbedding)) and l.pooling in _POOLED)]
 
     def _width(self, name):
         layer = self[name]
-        return 2 * layer.output_dim if isinstance(layer, DoubleHashingEmbedding) else layer.embedding.output_dim
+        if isinstance(layer, DoubleHashingEmbedding):
+            return 2 * layer.output_dim
+        return layer.output_dim if isinstance(layer, HashedEmbeddingBag) else layer.embedding.output_dim
 
     def output_layout(self, names=None):
         """{name: (column offset, width)} of the fused output buffer, in dict order."""
@@ -39,17 +42,23 @@ class PreprocessLayers(dict):
         return layout, col
 
     def forward_all(self, batch, names=None, out=None, keep_ids=None):
-        """batch: {feature name: StringColumn | int tensor | lists}.  Returns {name: tensor}.
+        """batch: {feature name: StringColumn | int tensor | lists}, or a `synth.PackedBatch` (all string features
+        of the batch in ONE arena + ONE offsets buffer; a host-side PackedBatch crosses PCIe as two copies).
+        Returns {name: tensor}.
 
         Hashed, pooled features go through one fused launch; the rest are called one by one.
         keep_ids: optional dict that receives, per fused feature, the row ids the launch gathered
         ([tables, B * L] int64) and the bag length -- what the backward / optimizer step needs."""
+        if isinstance(batch, PackedBatch):
+            if not batch.data.is_cuda:
+                batch = batch.to(_default_device(), non_blocking=True)
+            batch = batch.columns()
         names = list(names) if names is not None else [n for n in self if n in batch]
         fused = [n for n in names if n in set(self.fused_names())]
         result = {}
         if fused:
             layout, total = self.output_layout(fused)
-            hashed = [n for n in fused if isinstance(self[n], DoubleHashingEmbedding)]
+            hashed = [n for n in fused if isinstance(self[n], (DoubleHashingEmbedding, HashedEmbeddingBag))]
             keys = {n: as_keys(batch[n]) for n in hashed}
             if hashed:
                 B, dev = _batch_and_len(keys[hashed[0]])[0], keys[hashed[0]].device
@@ -74,7 +83,7 @@ class PreprocessLayers(dict):
                         call = layer.field_call(keys[n], view)
                         if keep_ids is not None:
                             n_items = _batch_and_len(keys[n])[0] * _batch_and_len(keys[n])[1]
-                            call.ids_out = torch.empty(2, n_items, dtype=torch.int64, device=out.device)
+                            call.ids_out = torch.empty(len(call.tables), n_items, dtype=torch.int64, device=out.device)
                             keep_ids[n] = (call.ids_out, _batch_and_len(keys[n])[1])
                         calls.append(call)
                 else:                                   # lookup / discrete: ids from their own small kernels

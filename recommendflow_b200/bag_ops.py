@@ -254,6 +254,14 @@ class BagAdam(object):
         self.iterations = 0
         self._ws = None
 
+    def state_dict(self):
+        return {"iterations": self.iterations, "m": self.m.clone(), "v": self.v.clone()}
+
+    def load_state_dict(self, state):
+        self.iterations = int(state["iterations"])
+        self.m.copy_(state["m"])
+        self.v.copy_(state["v"])
+
     def _workspace(self, n_keys):
         need = int(nat.lib().rf_bag_adam_workspace_bytes(n_keys, self.table.shape[0]))
         if need < 0:
@@ -304,6 +312,16 @@ class BagAdamGroup(object):
         self.learning_rate, self.beta_1, self.beta_2, self.epsilon, self.lazy = learning_rate, beta_1, beta_2, epsilon, lazy
         self.iterations = 0
         self._ws = None
+
+    def state_dict(self):
+        return {"iterations": self.iterations, "m": [t.clone() for t in self.m], "v": [t.clone() for t in self.v]}
+
+    def load_state_dict(self, state):
+        self.iterations = int(state["iterations"])
+        for dst, src in zip(self.m, state["m"]):
+            dst.copy_(src)
+        for dst, src in zip(self.v, state["v"]):
+            dst.copy_(src)
 
     def apply(self, updates, batch):
         """updates: one (ids, grad_out, combiner, bag_len, bag_offsets) per table, in table order; `None` for a

@@ -1,0 +1,382 @@
+// rf_gemm_tc.cu -- Keras Dense (y = activation(x W + b)) on the 5th-gen tensor cores (tcgen05 + TMEM + TMA).
+//
+// Replaces the tower MLP of /root/reference/backend/blocks/mlp.py:4-15 (create_mlp: [norm, Dense(units,
+// activation), Dropout] * n; models/matching/dssm.py:25-26 builds [1024, 512, 256], selu, BatchNormalization(1e-6))
+// and the Dense q / k / v projections of backend/layers/attention_layers.py:141-155.  At inference the
+// BatchNormalization in front of a Dense is an affine map per input column and is folded into W and b by the
+// host layer, so one launch of this kernel is a whole [norm, Dense, activation] stage; the last stage can also
+// l2-normalise its rows (dssm.py:36 / que2search.py embedding_norm) in the same epilogue.
+//
+//   operands   x [M, K] fp32 (row pitch ldx) and W^T [N, K] fp32, both K-major, read by TMA straight from HBM as
+//              TF32 (kind::tf32 -- what TensorFlow itself does for fp32 matmuls on Ampere and later), fp32 accumulate
+//   tile       128 x BN x 32 per stage (BN = 64 / 128 / 256 picked per shape), 4-6 stage TMA -> smem ring,
+//              4 x tcgen05.mma (K = 8) per stage, TWO 128-lane x BN-column TMEM accumulators so that the MMAs of
+//              tile i+1 run under the epilogue of tile i; persistent CTAs walk the tiles grid-stride
+//   warps      0: TMA producer   1: TMEM alloc + MMA issue   2-5: epilogue, thread = output row = TMEM lane:
+//              tcgen05.ld 32 columns, + bias, activation, (optional row l2-norm), then the warp's 32 x 32 block goes
+//              through a 128-byte-swizzled smem tile and leaves as ONE TMA store (UTMASTG): full 128-byte lines per
+//              row instead of 32 scattered 16-byte stores per instruction (first version: 0.2 ms for a 64 -> 64
+//              projection of 409 600 rows whose HBM floor is 32 us); TMA clips rows / columns past the edges
+// Every mbarrier wait is bounded and traps instead of hanging.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "../../include/rf_b200.h"
+#include "rf_common.h"
+
+namespace rf {
+
+extern std::atomic<int64_t> g_launches;
+
+namespace gemm_tc {
+
+constexpr int kBM = 128, kBK = 32, kUmmaK = 8;
+constexpr int kABytes = kBM * kBK * 4;              // 16 KiB
+constexpr int kThreads = 192;
+constexpr int kOutStage = 4 * 2 * 4096;             // per epilogue warp: two 32-row x 128-byte staging tiles for the TMA store
+
+template <int BN>
+struct Cfg {
+    static constexpr int kBBytes = BN * kBK * 4;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = BN == 256 ? 4 : 6;
+    static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + kOutStage + 1024 + 256;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// K-major operand tile, 128-byte swizzle: rows at a 128-byte pitch, 8-row groups 1024 bytes apart (SBO)
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+__device__ __forceinline__ float activate(float x, int act) {
+    switch (act) {
+        case RF_ACT_RELU: return fmaxf(x, 0.f);
+        case RF_ACT_SELU: return x > 0.f ? 1.0507009873554805f * x : 1.7580993408473766f * expm1f(x);   // scale * alpha
+        case RF_ACT_TANH: return tanhf(x);
+        case RF_ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
+        case RF_ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+        default: return x;
+    }
+}
+
+struct Params {
+    const float *bias;      // [N] or NULL
+    float *out;             // [M, N], row pitch ldo
+    int64_t ldo;
+    int M, N, K;
+    int act, l2norm;
+    int n_m_tiles, n_n_tiles;
+    float l2_eps;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const __grid_constant__ CUtensorMap map_o, Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    using C = Cfg<BN>;
+    constexpr int kStages = C::kStages;
+    constexpr int kStageBytes = C::kStageBytes;
+    constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+    const int n_kb = (p.K + kBK - 1) / kBK;
+    const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t out_stage = ring + kStages * kStageBytes;      // 1024-byte aligned (stage sizes are multiples of 1 KiB)
+    const uint32_t bars = out_stage + kOutStage;
+    const uint32_t full0 = bars, empty0 = bars + 8 * kStages;
+    const uint32_t tmem_full0 = bars + 16 * kStages, tmem_empty0 = tmem_full0 + 16, tmem_slot = tmem_empty0 + 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = p.n_m_tiles * p.n_n_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full0 + 8 * a, 1);
+            mbar_init(tmem_empty0 + 8 * a, 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int m_tile = t / p.n_n_tiles, n_tile = t - m_tile * p.n_n_tiles;
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    const uint32_t dst = ring + stage * kStageBytes;
+                    mbar_expect_tx(full0 + 8 * stage, kStageBytes);
+                    tma_load_2d(dst, &map_a, full0 + 8 * stage, kb * kBK, m_tile * kBM);
+                    tma_load_2d(dst + kABytes, &map_b, full0 + 8 * stage, kb * kBK, n_tile * BN);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            int local = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++local) {
+                const uint32_t acc = (uint32_t)(local & 1);
+                mbar_wait(tmem_empty0 + 8 * acc, ((uint32_t)(local >> 1) & 1u) ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st_addr = ring + stage * kStageBytes;
+                    const uint64_t adesc = desc_sw128(st_addr), bdesc = desc_sw128(st_addr + kABytes);
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k)
+                        umma_tf32(tmem_base + acc * (uint32_t)BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kIdesc,
+                                  (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(empty0 + 8 * stage);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(tmem_full0 + 8 * acc);
+            }
+        }
+    } else {
+        // ===== epilogue: thread <-> output row (TMEM lane); warp w may touch lanes 32 * (w % 4) .. + 31 =====
+        const int quarter = warp & 3;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        int local = 0;
+        uint32_t n_store = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++local) {
+            const int m_tile = t / p.n_n_tiles, n_tile = t - m_tile * p.n_n_tiles;
+            const uint32_t acc = (uint32_t)(local & 1);
+            mbar_wait(tmem_full0 + 8 * acc, (uint32_t)(local >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float inv = 1.f;
+            if (p.l2norm) {                     // pass 1: ||activation(x W + b)||^2 of this row (one column tile holds the row)
+                float ss = 0.f;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    if (n_tile * BN + c0 >= p.N) break;
+                    float v[32];
+                    tmem_ld32(lane_addr + acc * (uint32_t)BN + (uint32_t)c0, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = n_tile * BN + c0 + j;
+                        if (col < p.N) {
+                            const float y = activate(v[j] + (p.bias ? __ldg(p.bias + col) : 0.f), p.act);
+                            ss = fmaf(y, y, ss);
+                        }
+                    }
+                }
+                inv = 1.f / fmaxf(sqrtf(ss), p.l2_eps);
+            }
+            const int row0 = m_tile * kBM + quarter * 32;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int col0 = n_tile * BN + c0;
+                if (col0 >= p.N) break;
+                float v[32];
+                tmem_ld32(lane_addr + acc * (uint32_t)BN + (uint32_t)c0, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = col0 + j;
+                    const float b = (p.bias && col < p.N) ? __ldg(p.bias + col) : 0.f;
+                    v[j] = activate(v[j] + b, p.act) * inv;
+                }
+                // stage the warp's 32 rows x 32 columns (128 bytes per row, 16-byte chunks XOR-ed with row & 7 = the
+                // TMA 128-byte swizzle) and hand the tile to the TMA store engine
+                const uint32_t buf = out_stage + (uint32_t)(warp - 2) * 8192u + (uint32_t)(n_store & 1) * 4096u;
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // this buffer's previous store has read it
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(buf + (uint32_t)lane * 128u + (uint32_t)((c ^ (lane & 7)) << 4)),
+                                 "f"(v[4 * c]), "f"(v[4 * c + 1]), "f"(v[4 * c + 2]), "f"(v[4 * c + 3])
+                                 : "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) tma_store_2d(&map_o, buf, col0, row0);
+                ++n_store;
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty0 + 8 * acc);
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // every store has landed before the CTA exits
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B) {
+    static EncodeTiledFn fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) return (EncodeTiledFn) nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    if (!fn) return set_error(RF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(RF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return RF_OK;
+}
+
+template <int BN>
+static int launch(const float *x, int64_t ldx, const float *wt, int64_t ldw, Params p, int sms, cudaStream_t st) {
+    CUtensorMap ma, mb, mo;
+    int rc = make_map(&ma, x, p.M, p.K, ldx, kBM);
+    if (rc != RF_OK) return rc;
+    rc = make_map(&mb, wt, p.N, p.K, ldw, BN);
+    if (rc != RF_OK) return rc;
+    rc = make_map(&mo, p.out, p.M, p.N, p.ldo, 32, CU_TENSOR_MAP_L2_PROMOTION_NONE);     // 32 x 32 store boxes
+    if (rc != RF_OK) return rc;
+    p.n_m_tiles = (p.M + kBM - 1) / kBM;
+    p.n_n_tiles = (p.N + BN - 1) / BN;
+    const int tiles = p.n_m_tiles * p.n_n_tiles;
+    const int grid = tiles < sms ? tiles : sms;
+    RF_CUDA(cudaFuncSetAttribute(dense_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::kSmem));
+    dense_tc_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmem, st>>>(ma, mb, mo, p);
+    RF_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return RF_OK;
+}
+
+}  // namespace gemm_tc
+}  // namespace rf
+
+using namespace rf;
+
+extern "C" int rf_dense_forward_tc(const float *d_x, int64_t rows, int32_t in_dim, int64_t ldx, const float *d_weight_t,
+                                   const float *d_bias, int32_t units, int activation, int l2_normalize, float *d_out,
+                                   int64_t ldo, void *stream) {
+    using namespace gemm_tc;
+    if (rows < 0 || in_dim <= 0 || units <= 0) return set_error(RF_ERR_INVALID, "bad Dense shape");
+    if (activation < RF_ACT_NONE || activation > RF_ACT_GELU) return set_error(RF_ERR_INVALID, "Unknown activation function: %d", activation);
+    if (rows == 0) return RF_OK;
+    if (!d_x || !d_weight_t || !d_out) return set_error(RF_ERR_INVALID, "rf_dense_forward_tc: NULL buffer");
+    if (rows > INT32_MAX) return set_error(RF_ERR_UNSUPPORTED, "more than 2^31 - 1 rows");
+    const uintptr_t al = reinterpret_cast<uintptr_t>(d_x) | reinterpret_cast<uintptr_t>(d_weight_t) | reinterpret_cast<uintptr_t>(d_out);
+    if ((al & 15) || in_dim % 4 || units % 4 || ldx % 4 || ldo % 4 || ldx < in_dim || ldo < units)
+        return set_error(RF_ERR_UNSUPPORTED, "tensor-core Dense needs in_dim, units and both row pitches to be multiples of 4 "
+                                             "floats and 16-byte aligned buffers");
+    if (l2_normalize && units > 256) return set_error(RF_ERR_UNSUPPORTED, "fused row l2-normalisation handles units <= 256");
+    int dev = 0, sms = 148;
+    RF_CUDA(cudaGetDevice(&dev));
+    RF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    Params p{d_bias, d_out, ldo, (int)rows, units, in_dim, activation, l2_normalize ? 1 : 0, 0, 0, 1e-12f};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // column tile: the widest that keeps the persistent grid busy: cost = waves x tile width
+    const int64_t m_tiles = (rows + kBM - 1) / kBM;
+    int best_bn = 0;
+    int64_t best_cost = INT64_MAX;
+    for (int bn : {256, 128, 64}) {
+        if (l2_normalize && units > bn) continue;
+        if (bn > 64 && units <= bn / 2) continue;                      // a mostly empty column tile
+        const int64_t tiles = m_tiles * ((units + bn - 1) / bn);
+        const int64_t cost = ((tiles + sms - 1) / sms) * bn;
+        if (cost < best_cost) {
+            best_cost = cost;
+            best_bn = bn;
+        }
+    }
+    if (best_bn == 256) return launch<256>(d_x, ldx, d_weight_t, in_dim, p, sms, st);
+    if (best_bn == 128) return launch<128>(d_x, ldx, d_weight_t, in_dim, p, sms, st);
+    return launch<64>(d_x, ldx, d_weight_t, in_dim, p, sms, st);
+}

@@ -112,6 +112,11 @@ __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t addr, uint32_t lbo_byt
            ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
 }
 
+__device__ __forceinline__ float ex2(float x) {       // MUFU.EX2: 2^x, ex2(-inf) = +0
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ uint32_t to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -288,18 +293,22 @@ sdpa_tc_kernel_v1(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
 
 // ------------------------------------------------------------------------------------------------------------
-// v2 (round 2): the same arithmetic, software-pipelined across pairs.  Round 1 ran load -> GEMM 1 -> softmax ->
-// GEMM 2 -> store strictly in series with one CTA per SM (ncu: 33 % of the op's HBM floor, 5 warps resident,
-// `long_scoreboard` + `wait`): every pair paid a full DRAM round trip with nothing else in flight.  Now
-//   warp 4 (one lane)  TMA of Q, K and GEMM 1.  Q/K smem is single-buffered but refilled for pair n+1 the moment
-//                      GEMM 1 of pair n retires, and GEMM 1 writes alternating TMEM logit buffers, so the loads
-//                      AND the first contraction of pair n+1 run under the softmax of pair n;
-//   warp 5 (one lane)  TMA of V (double-buffered when it fits) and GEMM 2;
-//   warps 0-3          softmax / P / output rows, exactly as before.
+// Round-2 kernel: the same arithmetic, software-pipelined across pairs, softmax on 8 warps.
+// Round 1 ran load -> GEMM 1 -> softmax -> GEMM 2 -> store strictly in series with one CTA per SM (ncu: 33 % of the
+// op's HBM floor).  A first pipelined version (loads and GEMM 1 of pair n+1 under the softmax of pair n) only gained
+// 16 %: its profile showed the 4 softmax warps -- one per scheduler, ~1500 dependent instructions per row of 64
+// logits -- pacing the kernel at ~10 k cycles per pair (profiles/r2a_ncu_sdpa_pipelined_summary.csv).  Now
+//   warp 8 (one lane)  TMA of Q, K and GEMM 1.  Q/K smem is refilled for pair n+1 the moment GEMM 1 of pair n
+//                      retires, and GEMM 1 writes alternating TMEM logit buffers;
+//   warp 9 (one lane)  TMA of V (double-buffered when it fits) and GEMM 2;
+//   warps 0-7          softmax: TWO threads per query row (warps w and w+4 own the same TMEM lanes), 32 logits each:
+//                      local max / exp2 / sum, one (max, sum) exchange through shared memory, then P = e * factor;
+//                      2 warps per scheduler and ~400 instructions per thread.
 // TMEM: logits[0] cols 0-127, logits[1] cols 128-255, output cols 256-(256+dh).  smem (dh = 64): Q 32 + K 32 +
 // V 2 x 32 + P 64 = 192 KiB, one CTA per SM.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kThreads2 = 192;
+constexpr int kThreads2 = 320;
+constexpr int kSoftThreads = 256;
 constexpr int kTmemCols2 = 512;
 
 __global__ void __launch_bounds__(kThreads2, 1)
@@ -312,20 +321,22 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const uint32_t k_s = q_s + n_db * kBlkBytes;
     const uint32_t v_s = k_s + n_db * kBlkBytes;                     // n_vbuf buffers of n_db blocks
     const uint32_t p_s = v_s + n_vbuf * n_db * kBlkBytes;            // 4 blocks
-    const uint32_t bars = p_s + 4 * kBlkBytes;
+    const uint32_t xch_s = p_s + 4 * kBlkBytes;                      // float2 [2][128]: (local max, local sum) per half row
+    const uint32_t bars = xch_s + 2 * 128 * 8;
     const uint32_t qk_full = bars, mma1_done0 = bars + 8, s_free0 = bars + 24, v_full0 = bars + 40, p_ready = bars + 56,
                    mma2_done = bars + 64, tmem_slot = bars + 72;
     uint8_t *smem_gen = smem_raw + (base - smem_u32(smem_raw));
+    float2 *xch = reinterpret_cast<float2 *>(smem_gen + (xch_s - base));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         mbar_init(qk_full, 1);
         for (int b = 0; b < 2; ++b) {
             mbar_init(mma1_done0 + 8 * b, 1);
-            mbar_init(s_free0 + 8 * b, 128);
+            mbar_init(s_free0 + 8 * b, kSoftThreads);
             mbar_init(v_full0 + 8 * b, 1);
         }
-        mbar_init(p_ready, 128);
+        mbar_init(p_ready, kSoftThreads);
         mbar_init(mma2_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -333,7 +344,7 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         uint4 *pz = reinterpret_cast<uint4 *>(smem_gen + (p_s - base));
         for (int i = threadIdx.x; i < 4 * kBlkBytes / 16; i += kThreads2) pz[i] = make_uint4(0, 0, 0, 0);
     }
-    if (warp == 4) {
+    if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols2) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -351,7 +362,7 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const uint32_t qk_bytes = 2u * n_db * kBlkBytes, v_bytes = (uint32_t)n_db * kBlkBytes;
     const int stride = gridDim.x;
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ===== Q / K loader + GEMM 1 =====
         if (lane == 0) {
             auto load_qk = [&](int pair) {
@@ -385,7 +396,7 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             }
         }
         __syncwarp();
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // ===== V loader + GEMM 2 =====
         if (lane == 0) {
             auto load_v = [&](int pair, int vb) {
@@ -423,57 +434,58 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
         __syncwarp();
     } else {
-        // ===== softmax: thread = row of the pair tile =====
-        const int r = threadIdx.x;
-        const int half = r >> 6, i = r & 63;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        // ===== softmax: two threads per row of the pair tile (warps w and w + 4 share TMEM lanes 32 (w % 4) ..) =====
+        const int quarter = warp & 3, ch = warp >> 2;                // ch: which 32 of the row's 64 logits
+        const int r = quarter * 32 + lane;                          // row of the pair tile = TMEM lane
+        const int half = r >> 6, i = r & 63;                        // sequence of the pair, query index
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const float c2 = p.inv_sqrt_dk * 1.4426950408889634f;       // logits enter exp2 pre-multiplied by log2(e) / sqrt(dh)
+        const int nv = min(32, max(0, p.S - ch * 32));              // valid keys among this thread's 32
+        const int n32 = p.dh >> 5, o_lo = ch == 0 ? 0 : (n32 + 1) / 2, o_hi = ch == 0 ? (n32 + 1) / 2 : n32;
         uint32_t n = 0;
         for (int pair = blockIdx.x; pair < n_pairs; pair += stride, ++n) {
             const uint32_t b = n & 1u, use = (n >> 1) & 1u;
             const int seq = 2 * pair + half;
             mbar_wait(mma1_done0 + 8 * b, use);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float x[64];
-            {
-                float v0[32], v1[32];
-                tmem_ld32(lane_addr + b * 128u + (uint32_t)(half * 64), v0);
-                tmem_ld32(lane_addr + b * 128u + (uint32_t)(half * 64 + 32), v1);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    x[j] = v0[j];
-                    x[32 + j] = v1[j];
-                }
-            }
+            float x[32];
+            tmem_ld32(lane_addr + b * 128u + (uint32_t)(half * 64 + ch * 32), x);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(s_free0 + 8 * b);                           // GEMM 1 of pair n+2 may overwrite this buffer
             const bool row_ok = seq < p.n_seq && i < p.S;
+            // the reference's QUERY-row mask fills the whole row with one constant: uniform attention over the S keys
             const bool masked = row_ok && p.mask && p.mask[(size_t)seq * p.S + i] == 0.f;
             float mx = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                float l = masked ? -4294967295.0f : x[j] * p.inv_sqrt_dk;
-                l = (j < p.S) ? l : -INFINITY;
-                x[j] = l;
-                mx = fmaxf(mx, l);
+            for (int j = 0; j < 32; ++j) {
+                const float l = masked ? 0.f : x[j];
+                x[j] = j < nv ? l : -INFINITY;                      // padded keys: exp2(-inf) = 0
+                mx = fmaxf(mx, x[j]);
             }
+            const float mc = mx == -INFINITY ? 0.f : mx * c2;
             float sum = 0.f;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                const float e = (j < p.S) ? __expf(x[j] - mx) : 0.f;
-                x[j] = e;
-                sum += e;
+            for (int j = 0; j < 32; ++j) {
+                x[j] = ex2(fmaf(x[j], c2, -mc));
+                sum += x[j];
             }
-            const float inv = row_ok ? 1.f / sum : 0.f;
-            uint8_t *prow = smem_gen + (p_s - base) + (r >> 3) * 1024 + (r & 7) * 128;
+            xch[ch * 128 + r] = make_float2(mx, sum);
+            asm volatile("bar.sync 1, %0;" ::"n"(kSoftThreads) : "memory");
+            const float2 other = xch[(ch ^ 1) * 128 + r];
+            const float big = fmaxf(mx, other.x);                   // finite: every row has >= 1 valid key in one half
+            const float f_me = mx == -INFINITY ? 0.f : ex2((mx - big) * c2);
+            const float f_ot = other.x == -INFINITY ? 0.f : ex2((other.x - big) * c2);
+            const float total = sum * f_me + other.y * f_ot;
+            const float fac = row_ok ? f_me / total : 0.f;          // rows that are padding produce zeros
+            uint8_t *prow = smem_gen + (p_s - base) + (r >> 3) * 1024 + (r & 7) * 128 + (half * 2 + ch) * kBlkBytes;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
+            for (int c = 0; c < 8; ++c) {                             // 8 chunks of 4 keys
                 uint4 w;
-                w.x = to_tf32(x[c * 4 + 0] * inv);
-                w.y = to_tf32(x[c * 4 + 1] * inv);
-                w.z = to_tf32(x[c * 4 + 2] * inv);
-                w.w = to_tf32(x[c * 4 + 3] * inv);
-                const int kb = half * 2 + (c >> 3), cc = c & 7;
-                *reinterpret_cast<uint4 *>(prow + kb * kBlkBytes + ((cc ^ (r & 7)) << 4)) = w;
+                w.x = to_tf32(x[c * 4 + 0] * fac);
+                w.y = to_tf32(x[c * 4 + 1] * fac);
+                w.z = to_tf32(x[c * 4 + 2] * fac);
+                w.w = to_tf32(x[c * 4 + 3] * fac);
+                *reinterpret_cast<uint4 *>(prow + ((c ^ (r & 7)) << 4)) = w;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -481,13 +493,13 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             mbar_wait(mma2_done, n & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float *orow = p.out + ((size_t)seq * p.S + i) * p.dh;
-            for (int c0 = 0; c0 < p.dh; c0 += 32) {
+            for (int cb = o_lo; cb < o_hi; ++cb) {
                 float o[32];
-                tmem_ld32(lane_addr + 256u + (uint32_t)c0, o);
+                tmem_ld32(lane_addr + 256u + (uint32_t)(cb * 32), o);
                 if (row_ok) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4 *>(orow + c0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                        *reinterpret_cast<float4 *>(orow + cb * 32 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -495,7 +507,7 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols2) : "memory");
     }
@@ -556,7 +568,7 @@ int launch_sdpa_tc(const float *q, const float *k, const float *v, const float *
         sdpa_tc_kernel_v1<<<grid, kThreads, smem, st>>>(mq, mk, mv, p);
     } else {
         const int n_vbuf = n_db <= 2 ? 2 : 1;
-        const size_t smem = (size_t)((2 + n_vbuf) * n_db + 4) * kBlkBytes + 1024 + 128;
+        const size_t smem = (size_t)((2 + n_vbuf) * n_db + 4) * kBlkBytes + 2048 + 1024 + 128;
         RF_CUDA(cudaFuncSetAttribute(sdpa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int grid = n_pairs < sms ? n_pairs : sms;
         sdpa_tc_kernel<<<grid, kThreads2, smem, st>>>(mq, mk, mv, p, n_vbuf);

@@ -25,6 +25,46 @@ def _stream(dev):
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+def dense_tc_ok(x, in_dim, units, l2_normalize=False):
+    """Shapes / layouts rf_dense_forward_tc takes (everything else goes through the library GEMM)."""
+    return (x.is_cuda and x.dtype == torch.float32 and in_dim % 4 == 0 and units % 4 == 0 and x.stride(-1) == 1
+            and (not l2_normalize or units <= 256))
+
+
+def dense_forward(x, weight_t, bias=None, activation=None, l2_normalize=False, out=None):
+    """Keras Dense on the tensor cores: activation(x @ weight_t.T + bias) (then optionally l2-normalised rows).
+
+    x: [..., in_dim] fp32 CUDA (rows may be strided: any view whose last dim is contiguous and whose leading dims
+    collapse to one row pitch); weight_t: [units, in_dim] = the transposed Keras kernel; bias [units] or None.
+    One launch of rf_dense_forward_tc (tcgen05, TF32 operands, fp32 accumulate, fused epilogue)."""
+    if activation not in nat.ACTIVATION:
+        raise ValueError(f"Unknown activation function: {activation}")
+    w = _f32(weight_t, "weight_t")
+    units, in_dim = w.shape
+    if x.shape[-1] != in_dim:
+        raise ValueError(f"input has {x.shape[-1]} features, the layer expects {in_dim}")
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, in_dim) if x.dim() != 2 else x
+    if x2.dtype != torch.float32 or not x2.is_cuda:
+        x2 = _f32(x2, "x")
+    if x2.stride(1) != 1 or (x2.shape[0] > 1 and x2.stride(0) % 4) or x2.data_ptr() % 16:
+        x2 = x2.contiguous()
+    rows = x2.shape[0]
+    ldx = x2.stride(0) if rows > 1 else in_dim
+    if out is None:
+        out2 = torch.empty(rows, units, dtype=torch.float32, device=x2.device)
+    else:
+        out2 = out.reshape(-1, units) if out.dim() != 2 else out
+        if out2.dtype != torch.float32 or out2.shape[0] != rows or out2.stride(1) != 1:
+            raise ValueError("out must be an fp32 [rows, units] view with contiguous columns")
+    b = None if bias is None else _f32(bias, "bias")
+    with torch.cuda.device(x2.device):
+        nat.check(nat.lib().rf_dense_forward_tc(x2.data_ptr(), rows, in_dim, ldx, w.data_ptr(), None if b is None else b.data_ptr(),
+                                                units, nat.ACTIVATION[activation], 1 if l2_normalize else 0, out2.data_ptr(),
+                                                out2.stride(0) if rows > 1 else units, _stream(x2.device)))
+    return out2.view(*lead, units) if out is None else out
+
+
 def sdpa_tc_shape_ok(S, dh):
     return 1 <= S <= 64 and dh in (32, 64, 96)
 

@@ -28,6 +28,9 @@ class RecallSdpa(torch.nn.Module):
         self._name = name
         self.feature_conf = feature_conf
         self.preprocessor = get_preprocess_layers(feature_conf)
+        # the mapping above keeps the reference's `layers[name](batch[name])` convention; registering the same layers
+        # here makes every embedding table part of state_dict() / .to() (feature names may hold dots: keys are indexed)
+        self.preprocess_layers = torch.nn.ModuleList(list(self.preprocessor.values()))
         self.user_cols = [f.name for f in feature_conf.features.get_features(tower="user") if f.name in self.preprocessor]
         self.ad_cols = [f.name for f in feature_conf.features.get_features(tower="ad") if f.name in self.preprocessor]
         self.user_dense = create_mlp(list(tower_units), 0.3, "selu", BatchNormalization(epsilon=1e-6), name="user_dense_tower")
@@ -57,9 +60,39 @@ class RecallSdpa(torch.nn.Module):
         if self.seq_encoder is not None and behaviour is not None:
             x, mask = behaviour
             user.append(self.seq_encoder(x, x, x, mask).mean(dim=1))
-        u = torch.cat(user, dim=-1)
-        a = torch.cat([embs[n] for n in self.ad_cols], dim=-1)
-        return self.embedding_norm(self.user_dense(u)), self.embedding_norm(self.ad_dense(a))
+        u = torch.cat(user, dim=-1) if len(user) > 1 else user[0]
+        ad = [embs[n] for n in self.ad_cols]
+        a = self._adjacent_view(ad) if len(ad) > 1 else ad[0]
+        if self.global_l2_norm:
+            return self.embedding_norm(self.user_dense(u)), self.embedding_norm(self.ad_dense(a))
+        # per-row l2 normalisation rides in the last Dense's epilogue on the tensor-core path
+        return self.user_dense(u, l2_normalize=True), self.ad_dense(a, l2_normalize=True)
+
+    @staticmethod
+    def _adjacent_view(parts):
+        """Column views that sit side by side in one buffer (the fused bag output) are returned as ONE strided view
+        instead of being copied by torch.cat; anything else is concatenated."""
+        base = parts[0]
+        if any(p.requires_grad for p in parts):       # as_strided would cut the graph to parts[1:]
+            return torch.cat(parts, dim=-1)
+        if all(p.dim() == 2 and p.stride() == base.stride() and p.shape[0] == base.shape[0] for p in parts):
+            off, ok = base.storage_offset(), True
+            for p in parts:
+                ok = ok and p.untyped_storage().data_ptr() == base.untyped_storage().data_ptr() and p.storage_offset() == off
+                off += p.shape[1]
+            if ok:
+                return base.as_strided((base.shape[0], off - base.storage_offset()), base.stride(), base.storage_offset())
+        return torch.cat(parts, dim=-1)
+
+    def build(self, device=None):
+        """Create every embedding table now (Keras builds variables lazily at the first call): needed before
+        load_state_dict() on a fresh model."""
+        for layer in self.preprocessor.values():
+            if hasattr(layer, "build"):
+                layer.build(device)
+            elif hasattr(layer, "embedding"):
+                layer.embedding.build(device)
+        return self
 
     def forward(self, batch, y_true=None, behaviour=None, training=False):
         u, a = self.towers(batch, behaviour)

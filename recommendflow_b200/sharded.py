@@ -283,13 +283,17 @@ class ShardedEmbeddingBag(torch.nn.Module):
             self._tick("hash")
             self.ops.route(ids, bag_offsets, L, B, W, b["counts"], b["offs_local"], offs_dst, rows_dst)
 
-    def prepare(self, keys, overlap=True):
+    def prepare(self, keys, overlap=True, capturing=False):
         """p2p transport, stage 1: hash + route this rank's keys into the owners' receive buffers.
 
-        With overlap=True the three stages of a step run on three streams -- route | fused gather+pool
-        into peer memory | NVLink drain + combine -- so that in a loop `t = prepare(next); finish(prev)`
-        the latency-bound routing of step i+1, the HBM-bound pooling of step i and the NVLink-bound
-        drain of step i-1 proceed concurrently (double-buffered exchange sets).  Returns a ticket."""
+        With overlap=True the three stages of a step run on three streams -- route (+ the "routing has landed"
+        barrier) | fused gather+pool into peer memory | NVLink drain + combine -- so that in a loop
+        `t = prepare(next); finish(prev)` the latency-bound routing of step i+1, the HBM-bound pooling of step i
+        and the NVLink-bound drain of step i-1 proceed concurrently (double-buffered exchange sets); the pooling
+        stream then runs pooling kernels back to back (round 1 kept the first barrier on it: 13 us per step).
+        capturing=True: the call is being recorded into a CUDA graph together with the `finish` of the previous
+        step; dependencies on EARLIER steps are then carried by the order of graph launches, not by events (an
+        event recorded in another capture cannot be waited on).  Returns a ticket."""
         if self.transport != "p2p":
             raise ValueError("prepare()/finish() pipelining needs the p2p transport")
         b = self._bufs or self._alloc()
@@ -308,7 +312,7 @@ class ShardedEmbeddingBag(torch.nn.Module):
         if overlap:
             stream.wait_stream(cur)                       # the keys were produced on the caller's stream
         with torch.cuda.stream(stream):
-            if overlap and b["rows_free"][j] is not None:
+            if overlap and not capturing and b["rows_free"][j] is not None:
                 stream.wait_event(b["rows_free"][j])      # every owner is done pooling out of set j
             self._tick("start")
             if isinstance(keys, BucketIds) and not tiles:
@@ -328,15 +332,23 @@ class ShardedEmbeddingBag(torch.nn.Module):
             if not self.deterministic:
                 # the accumulator of this set: its last reader (the finishing pass two steps ago) is ordered before
                 # this stream by the rows_free / combined events below; owners only add after the next barrier
-                if overlap and b["combined"][j] is not None:
+                if overlap and not capturing and b["combined"][j] is not None:
                     stream.wait_event(b["combined"][j])
                 b["partials"][j].zero_()
             self._tick("route")
             if overlap:
+                # after this barrier: every source's routing of this step has landed at its owners, and every rank
+                # is past the combine that last read partial set j -- issued HERE, behind the routing, so that it
+                # completes under the previous step's pooling instead of delaying this step's
+                if not capturing and b["combined"][j] is not None:
+                    stream.wait_event(b["combined"][j])
+                b["hdl"].barrier(channel=0)
                 routed = torch.cuda.Event()
                 routed.record(stream)
+                if capturing:
+                    cur.wait_event(routed)                # join the side stream back into the capturing stream
         return {"set": j, "routed": routed, "B": B, "L": L, "bag_offsets": bag_offsets, "n_keys": n_keys,
-                "overlap": overlap, "tiles": tiles}
+                "overlap": overlap, "tiles": tiles, "capturing": capturing}
 
     def finish(self, ticket, out=None):
         """Stages 2 and 3: barrier, fused gather+pool writing each pooled vector into the SOURCE rank's
@@ -350,14 +362,16 @@ class ShardedEmbeddingBag(torch.nn.Module):
         sP = b["sP"] if overlap else cur
         sC = b["sC"] if overlap else cur
         partial_op = "sum" if self.combiner == "avg" else self.combiner
+        capturing = ticket.get("capturing", False) or torch.cuda.is_current_stream_capturing()
         with torch.cuda.stream(sP):
-            if overlap:
-                sP.wait_event(ticket["routed"])
-                if b["combined"][j] is not None:
-                    sP.wait_event(b["combined"][j])       # this rank consumed partial set j (two steps ago)
-            # after this barrier: every source's routing of this step has landed here, and every rank
-            # is past the combine that last read partial set j
-            hdl.barrier(channel=0)
+            if overlap and capturing:
+                sP.wait_stream(cur)                       # fork; the routing + barrier of this ticket ran in an earlier launch
+            elif overlap:
+                sP.wait_event(ticket["routed"])           # routing landed everywhere (the barrier is behind this event)
+            else:
+                # after this barrier: every source's routing of this step has landed here, and every rank
+                # is past the combine that last read partial set j
+                hdl.barrier(channel=0)
             self._tick("barrier0")
             # sources in rotated order (me, me+1, ...): at any moment the W owners write their pooled
             # vectors to W different ranks -- a permutation, not an incast on one rank's NVLink port
@@ -380,7 +394,7 @@ class ShardedEmbeddingBag(torch.nn.Module):
                 sC.wait_stream(cur)                       # `out` may still be read by the caller's stream
             hdl.barrier(channel=1)                        # every owner's partials have landed (NVLink drained)
             self._tick("barrier1")
-            if overlap:
+            if overlap and not capturing:
                 ev = torch.cuda.Event()
                 ev.record(sC)
                 b["rows_free"][j] = ev
@@ -391,7 +405,8 @@ class ShardedEmbeddingBag(torch.nn.Module):
             if overlap:
                 done = torch.cuda.Event()
                 done.record(sC)
-                b["combined"][j] = done
+                if not capturing:
+                    b["combined"][j] = done
                 cur.wait_event(done)
         return out
 
@@ -427,6 +442,20 @@ class ShardedEmbeddingBag(torch.nn.Module):
         self.ops.combine(b["partials"][0], W, B, D, self.combiner, L, bag_offsets, out)
         self._tick("combine")
         return out
+
+    def optimizer_state_dict(self):
+        """Adam moments of this rank's shard + the iteration counter (the shard itself is `self.shard`, a Parameter)."""
+        st = getattr(self, "_adam", None)
+        if st is None:
+            return {"iterations": 0, "m": None, "v": None}
+        return {"iterations": st["iterations"], "m": st["m"].clone(), "v": st["v"].clone()}
+
+    def load_optimizer_state_dict(self, state):
+        if state["m"] is None:
+            self._adam = None
+            return
+        self._adam = {"m": state["m"].to(self.shard.device).clone(), "v": state["v"].to(self.shard.device).clone(),
+                      "iterations": int(state["iterations"]), "ws": None}
 
     # ---- backward + optimizer (SURVEY.md §8f rank 1, row-sharded) -------------------------------------
     def apply_adam(self, grad_out, learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7, lazy=False):

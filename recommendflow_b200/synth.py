@@ -91,3 +91,39 @@ class PackedBatch(object):
         for name, (b0, o0, n, shape) in self.layout.items():
             cols[name] = StringColumn(self.data[b0:], self.offsets[o0:o0 + n + 1], shape)
         return cols
+
+
+# ---- closed-form table: any row can be rebuilt anywhere (host or device), bit for bit -----------------------------
+# w[r, c] = float32(h) * float32(0.1 / 2^24) - float32(0.05),  h = ((r * 2654435761 + c * 40503 + 12345) mod 2^32) >> 8
+# h < 2^24 converts to fp32 exactly; the multiply and the subtract are two separate IEEE fp32 operations on both
+# sides (no FMA contraction: separate torch kernels / separate numpy ufuncs), so the device table equals the host
+# rows bit for bit.  Used by the sharded benchmark's parity check: a rank checks its first bags against the oracle
+# without anyone ever holding the 51 GB table on the host.
+_CF_SCALE = np.float32(0.1 / 2 ** 24)
+_CF_SHIFT = np.float32(0.05)
+
+
+def closed_form_rows(row_ids, dim):
+    """numpy: the [len(row_ids), dim] fp32 rows of the closed-form table."""
+    r = np.asarray(row_ids, dtype=np.uint64).reshape(-1, 1)
+    c = np.arange(dim, dtype=np.uint64).reshape(1, -1)
+    h = ((r * np.uint64(2654435761) + c * np.uint64(40503) + np.uint64(12345)) & np.uint64(0xffffffff)) >> np.uint64(8)
+    w = h.astype(np.float32)
+    w *= _CF_SCALE
+    w -= _CF_SHIFT
+    return w
+
+
+def fill_closed_form(table, first_row=0, row_stride=1, chunk_rows=1 << 20):
+    """torch (any device): table[i] = closed-form row (first_row + i * row_stride); in place, chunked."""
+    n, dim = table.shape
+    c = torch.arange(dim, dtype=torch.int64, device=table.device).view(1, -1) * 40503 + 12345
+    for i0 in range(0, n, chunk_rows):
+        i1 = min(n, i0 + chunk_rows)
+        r = (torch.arange(i0, i1, dtype=torch.int64, device=table.device) * row_stride + first_row).view(-1, 1)
+        h = ((r * 2654435761 + c) & 0xffffffff) >> 8
+        w = h.to(torch.float32)
+        w.mul_(float(_CF_SCALE))
+        w.sub_(float(_CF_SHIFT))
+        table[i0:i1].copy_(w)
+    return table

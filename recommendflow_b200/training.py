@@ -7,8 +7,10 @@ What runs where:
     in-batch softmax loss on the CUDA kernels, tower GEMMs on cuBLAS;
   * backward: rf_inbatch_softmax_ce_backward and rf_sdpa_backward through torch.autograd Functions, the
     tower / projection GEMMs through torch's own autograd (library code);
-  * update: dense variables by torch.optim.Adam with Keras' hyper-parameters (eps = 1e-7), every embedding
-    table by rf_bag_backward_adam (Keras' sparse Adam: duplicates summed, all rows decay; `lazy=True`
+  * update: dense variables by `KerasAdam` below -- tf.keras.optimizers.Adam's exact update
+    w -= lr_t * m / (sqrt(v) + eps), lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t), the same form rf_bag_adam.cu applies to
+    the tables (torch.optim.Adam adds eps to sqrt(v_hat), a ~30x different effective eps at step 1) -- every
+    embedding table by rf_bag_backward_adam (Keras' sparse Adam: duplicates summed, all rows decay; `lazy=True`
     restricts the update to the gathered rows).
 BatchNormalization uses batch statistics and Dropout is active during the step, as with Keras training=True.
 Single GPU (replicated tables); the reverse exchange of the row-sharded path is not built yet.
@@ -18,6 +20,50 @@ import torch
 from .backend.blocks.mlp import BatchNormalization, Dropout
 from .backend.layers.preprocess_layers import DoubleHashingEmbedding
 from .bag_ops import BagAdamGroup
+
+
+class KerasAdam(object):
+    """tf.keras.optimizers.Adam on dense variables (foreach tensor ops; O(#parameters) glue, not a hot path).
+    m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  w -= lr * sqrt(1 - b2^t) / (1 - b1^t) * m / (sqrt(v) + eps)."""
+
+    def __init__(self, params, learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        self.params = [p for p in params]
+        self.learning_rate, self.beta_1, self.beta_2, self.epsilon = learning_rate, beta_1, beta_2, epsilon
+        self.iterations = 0
+        self.m = [torch.zeros_like(p) for p in self.params]
+        self.v = [torch.zeros_like(p) for p in self.params]
+
+    def zero_grad(self):
+        for p in self.params:
+            p.grad = None
+
+    @torch.no_grad()
+    def step(self):
+        self.iterations += 1
+        t = self.iterations
+        lr_t = self.learning_rate * (1.0 - self.beta_2 ** t) ** 0.5 / (1.0 - self.beta_1 ** t)
+        idx = [i for i, p in enumerate(self.params) if p.grad is not None]
+        if not idx:
+            return
+        ps, gs = [self.params[i] for i in idx], [self.params[i].grad for i in idx]
+        ms, vs = [self.m[i] for i in idx], [self.v[i] for i in idx]
+        torch._foreach_mul_(ms, self.beta_1)
+        torch._foreach_add_(ms, gs, alpha=1.0 - self.beta_1)
+        torch._foreach_mul_(vs, self.beta_2)
+        torch._foreach_addcmul_(vs, gs, gs, value=1.0 - self.beta_2)
+        den = torch._foreach_sqrt(vs)
+        torch._foreach_add_(den, self.epsilon)
+        torch._foreach_addcdiv_(ps, ms, den, value=-lr_t)
+
+    def state_dict(self):
+        return {"iterations": self.iterations, "m": [t.clone() for t in self.m], "v": [t.clone() for t in self.v]}
+
+    def load_state_dict(self, state):
+        self.iterations = int(state["iterations"])
+        for dst, src in zip(self.m, state["m"]):
+            dst.copy_(src)
+        for dst, src in zip(self.v, state["v"]):
+            dst.copy_(src)
 
 
 class RecallSdpaTrainer(object):
@@ -44,15 +90,18 @@ class RecallSdpaTrainer(object):
 
     def _dense_variables(self):
         """Every dense variable of the model (tower / projection kernels and biases, BatchNormalization gamma and
-        beta).  The embedding tables live in the preprocessing layers, outside `model.parameters()`."""
-        params = list(self.model.parameters())
-        for p in params:
+        beta).  The embedding tables are registered parameters too (state_dict), but they are updated by the fused
+        sparse Adam kernels, never by autograd."""
+        tables = set()
+        for layer in self.model.preprocessor.values():
+            tables.update(id(p) for p in layer.parameters())
+        params, seen = [], set()
+        for p in self.model.parameters():
+            if id(p) in tables or id(p) in seen:
+                continue
+            seen.add(id(p))
             p.requires_grad_(True)
-        seen = set()
-        for bn in self._modules(BatchNormalization):
-            if id(bn) not in seen:
-                params += bn.trainable()
-                seen.add(id(bn))
+            params.append(p)
         return params
 
     def _bag_groups(self, layout):
@@ -88,12 +137,12 @@ class RecallSdpaTrainer(object):
         if self.dense_opt is None:                      # variables are created lazily by the first forward
             with torch.no_grad():
                 self._forward(batch, y_true, behaviour, {})
-            self.dense_opt = torch.optim.Adam(self._dense_variables(), lr=self.learning_rate, betas=(0.9, 0.999), eps=1e-7)
+            self.dense_opt = KerasAdam(self._dense_variables(), learning_rate=self.learning_rate)
         self._set_training(True)
         try:
             ids = {}
             loss, leaf, layout = self._forward(batch, y_true, behaviour, ids)
-            self.dense_opt.zero_grad(set_to_none=True)
+            self.dense_opt.zero_grad()
             loss.backward()
         finally:
             self._set_training(False)
@@ -112,3 +161,31 @@ class RecallSdpaTrainer(object):
             group.apply(updates, grad.shape[0])
         self.iterations += 1
         return loss.detach()
+
+    # ---- checkpointing: model.state_dict() holds the variables; this holds the optimizer slots -------------------
+    def state_dict(self):
+        """Adam moments of every dense variable and every embedding table + the iteration counters (what
+        tf.keras' ModelCheckpoint(save_weights_only=False) keeps beside the weights)."""
+        return {"iterations": self.iterations,
+                "dense": None if self.dense_opt is None else self.dense_opt.state_dict(),
+                "bags": {dim: group.state_dict() for dim, (group, _) in self.bag_opts.items()}}
+
+    def load_state_dict(self, state, example_batch=None):
+        """Restore after the optimizers exist (they are created lazily by the first step: pass `example_batch` =
+        (batch, y_true, behaviour) to build them without taking a step)."""
+        if self.dense_opt is None:
+            if example_batch is None:
+                raise RuntimeError("the optimizers are built by the first step; pass example_batch to build them now")
+            batch, y_true, behaviour = example_batch
+            with torch.no_grad():
+                self._forward(batch, y_true, behaviour, {})
+            self.dense_opt = KerasAdam(self._dense_variables(), learning_rate=self.learning_rate)
+        if not self.bag_opts and state["bags"]:
+            names = self.model.user_cols + self.model.ad_cols
+            layout, _ = self.model.preprocessor.output_layout([n for n in names if n in set(self.model.preprocessor.fused_names())])
+            self._bag_groups(layout)
+        self.iterations = int(state["iterations"])
+        if state["dense"] is not None:
+            self.dense_opt.load_state_dict(state["dense"])
+        for dim, st in state["bags"].items():
+            self.bag_opts[dim][0].load_state_dict(st)

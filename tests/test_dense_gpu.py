@@ -320,3 +320,103 @@ def test_aux_label_cosent_losses_match_reference_formula():
     np.testing.assert_allclose(match_losses.pos_aux_label_cosent_loss(*args).item(), v2(pos), rtol=1e-4)
     np.testing.assert_allclose(match_losses.aux_label_cosent_loss(*args, alpha=0.3).item(), 0.7 * v2(pos) + 0.3 * v2(neg), rtol=1e-4)
     assert match_losses.pos_aux_label_cosent_loss(torch.zeros(B, device="cuda"), *args[1:]).item() == 0.0
+
+
+# ---- Keras Dense / tower MLP on the tcgen05 GEMM (rf_dense_forward_tc) ----------------------------------------------
+def _act64(name, z):
+    if name in (None, "linear"):
+        return z
+    if name == "relu":
+        return np.maximum(z, 0)
+    if name == "selu":
+        return 1.0507009873554805 * np.where(z > 0, z, 1.6732632423543772 * np.expm1(z))
+    if name == "tanh":
+        return np.tanh(z)
+    if name == "sigmoid":
+        return 1 / (1 + np.exp(-z))
+    if name == "gelu":
+        from math import erf
+        return 0.5 * z * (1 + np.vectorize(erf)(z / np.sqrt(2)))
+    raise AssertionError(name)
+
+
+# TF32 operands (the tensor core drops the low 13 mantissa bits of each fp32 operand, 2^-10 relative), fp32 accumulate:
+# |err| <~ 2^-10 * sum_k |x_k w_k|; for the sizes below that is a few 1e-3
+DENSE_TOL = dict(rtol=6e-3, atol=6e-3)
+
+
+@pytest.mark.parametrize("M,K,N,act", [(8192, 1664, 1024, "selu"), (300, 64, 64, None), (129, 512, 256, "relu"), (1000, 1024, 512, "tanh"),
+                                       (77, 36, 20, "sigmoid"), (4096, 256, 128, "gelu"), (1, 32, 4, None), (513, 100, 260, "selu")])
+def test_dense_forward_tc_matches_float64(M, K, N, act):
+    from recommendflow_b200.dense_ops import dense_forward
+    rng = np.random.default_rng(M + K + N)
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    w = rng.uniform(-0.05, 0.05, size=(K, N)).astype(np.float32)          # Keras kernel [in, units]
+    b = rng.uniform(-0.5, 0.5, size=N).astype(np.float32)
+    want = _act64(act, x.astype(np.float64) @ w.astype(np.float64) + b)
+    before = __import__("recommendflow_b200")._native.launch_count()
+    got = dense_forward(torch.from_numpy(x).cuda(), torch.from_numpy(np.ascontiguousarray(w.T)).cuda(), torch.from_numpy(b).cuda(), act)
+    assert __import__("recommendflow_b200")._native.launch_count() == before + 1
+    np.testing.assert_allclose(got.cpu().numpy(), want, **DENSE_TOL)
+    # no bias; rows l2-normalised in the epilogue (units <= 256)
+    if N <= 256:
+        z = _act64(act, x.astype(np.float64) @ w.astype(np.float64))
+        want_n = z / np.maximum(np.linalg.norm(z, axis=1, keepdims=True), 1e-12)
+        got_n = dense_forward(torch.from_numpy(x).cuda(), torch.from_numpy(np.ascontiguousarray(w.T)).cuda(), None, act, l2_normalize=True)
+        np.testing.assert_allclose(got_n.cpu().numpy(), want_n, rtol=6e-3, atol=2e-3)
+
+
+def test_dense_forward_tc_strided_input_and_output_slot():
+    """x may be a column window of a wider buffer (the fused bag output), out a column window of another."""
+    from recommendflow_b200.dense_ops import dense_forward
+    rng = np.random.default_rng(5)
+    M, K, N = 700, 96, 64
+    wide = rng.standard_normal((M, 256)).astype(np.float32)
+    w = rng.uniform(-0.1, 0.1, size=(K, N)).astype(np.float32)
+    xw = torch.from_numpy(wide).cuda()
+    outw = torch.full((M, 200), 7.0, device="cuda")
+    dense_forward(xw[:, 32:32 + K], torch.from_numpy(np.ascontiguousarray(w.T)).cuda(), None, "relu", out=outw[:, 100:100 + N])
+    want = np.maximum(wide[:, 32:32 + K].astype(np.float64) @ w, 0)
+    np.testing.assert_allclose(outw[:, 100:100 + N].cpu().numpy(), want, **DENSE_TOL)
+    assert torch.all(outw[:, :100] == 7.0) and torch.all(outw[:, 100 + N:] == 7.0)      # nothing outside the slot is touched
+
+
+def test_tower_mlp_fused_matches_layerwise_float64():
+    """create_mlp([1024, 512, 256], 0.3, "selu", BatchNormalization(1e-6)) (dssm.py:25-26) at inference: the fused path
+    (BN folded into each Dense, one tcgen05 launch per stage, l2 norm in the last epilogue) vs a float64 layer-by-layer
+    restatement of the Keras semantics."""
+    from recommendflow_b200 import _native as nat
+    from recommendflow_b200.backend.blocks.mlp import BatchNormalization, create_mlp
+    rng = np.random.default_rng(11)
+    B, d_in, units = 2048, 1664, [1024, 512, 256]
+    bn = BatchNormalization(epsilon=1e-6)
+    mlp = create_mlp(units, 0.3, "selu", bn, name="tower")
+    x = rng.standard_normal((B, d_in)).astype(np.float32) * 0.3
+    dims, h64 = [d_in] + units, x.astype(np.float64)
+    stage = 0
+    for layer in mlp.layers:
+        if hasattr(layer, "dense"):
+            d0, d1 = dims[stage], dims[stage + 1]
+            k = (rng.standard_normal((d0, d1)) / np.sqrt(d0)).astype(np.float32)
+            b = rng.uniform(-0.1, 0.1, size=d1).astype(np.float32)
+            layer.dense.set_weights([k, b])
+            gamma, beta = rng.uniform(0.5, 1.5, d0).astype(np.float32), rng.uniform(-0.2, 0.2, d0).astype(np.float32)
+            mean, var = rng.uniform(-0.3, 0.3, d0).astype(np.float32), rng.uniform(0.5, 2.0, d0).astype(np.float32)
+            bn.set_weights([gamma, beta, mean, var])
+            h64 = (h64 - mean) / np.sqrt(var.astype(np.float64) + 1e-6) * gamma + beta
+            h64 = _act64("selu", h64 @ k.astype(np.float64) + b)
+            stage += 1
+    want = h64 / np.maximum(np.linalg.norm(h64, axis=1, keepdims=True), 1e-12)
+    xt = torch.from_numpy(x).cuda()
+    before = nat.launch_count()
+    got = mlp(xt, l2_normalize=True)
+    assert nat.launch_count() == before + 3, "three stages = three tensor-core launches"
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=2e-2, atol=2e-3)
+    # every learned tensor is registered state
+    keys = set(mlp.state_dict().keys())
+    assert any("gamma_1664" in k for k in keys) and any("moving_var_512" in k for k in keys) and any("kernel" in k for k in keys)
+    # a weight update invalidates the folded cache
+    with torch.no_grad():
+        mlp.layers[1].dense.bias.add_(1.0)
+    got2 = mlp(xt, l2_normalize=True)
+    assert not torch.allclose(got, got2)
