@@ -357,9 +357,8 @@ def run_c3full(dev, steps, warmup, with_cpu=True):
 
     def forward(b):
         with torch.no_grad():
-            embs = model.preprocessor.forward_all(b["keys"], names=names)
             x = beh(b["beh"])                                           # [B, S, 64]: the behaviour sequence's embeddings
-            u, a = model.towers_from_embeddings(embs, (x, b["mask"]))
+            u, a = model.towers(b["keys"], (x, b["mask"]))              # fused bags + SDPA encoder + towers (l2-normalised)
             return model.loss_fun(b["y"], u, a)
 
     def e2e_step(i):
@@ -421,7 +420,8 @@ def run_c3full(dev, steps, warmup, with_cpu=True):
             cols = []
             for n in names:
                 a, o, _ = fields[n]
-                cols.append(oracle.hashed_bag_forward(a, o, B, 1, W[n], [100_000, 100_000], [2022, 2023], "sum"))
+                layer = model.preprocessor[n]
+                cols.append(oracle.hashed_bag_forward(a, o, B, 1, W[n], [layer.num_bins] * 2, list(layer.seeds), layer.combiner))
             ids = oracle.hash_strings(arena, boffs, 100_000, "", None)
             x = oracle.gather_rows(ids, wb).reshape(B, S, dm)
             seq = oracle.multi_head_attention(x, valid.astype(np.float32), *proj, 1).mean(axis=1)

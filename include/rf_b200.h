@@ -214,12 +214,47 @@ int rf_shard_route_keys(const uint8_t *d_bytes, const int32_t *d_str_offsets, in
 /* capacity = this rank's key count; the rest of each range stays unused) and bag b's run is      */
 /* [h_begin_dst[g][b], h_end_dst[g][b]) -- feed them to rf_bag_forward as ids / bag_offsets /     */
 /* bag_ends.  Keys are strings (d_bytes + d_str_offsets, hashed on the fly; d_ids_ws receives the */
-/* ids) or pre-hashed d_ids.                                                                       */
+/* ids; may be NULL when the caller does not need them) or pre-hashed d_ids.                       */
 int rf_shard_route_tiles(const uint8_t *d_bytes, const int32_t *d_str_offsets, const int64_t *d_ids,
                          int64_t num_bins, int mask_mode, int use_strong, uint64_t key0, uint64_t key1,
                          int64_t *d_ids_ws, const int32_t *d_bag_offsets, int32_t bag_len, int64_t batch,
                          int world, int64_t *const *h_rows_dst, int32_t *const *h_begin_dst,
                          int32_t *const *h_end_dst, void *stream);
+/* Same, with the routing kernel's grid capped at max_ctas_per_sm x #SMs (0 = no cap).  In the pipelined step the  */
+/* routing of batch i+1 runs under the HBM-bound pooling of batch i: 2 CTAs per SM measured best (more starve the  */
+/* pooling kernel of residency, fewer leave the routing latency-bound).                                            */
+int rf_shard_route_tiles_ex(const uint8_t *d_bytes, const int32_t *d_str_offsets, const int64_t *d_ids,
+                            int64_t num_bins, int mask_mode, int use_strong, uint64_t key0, uint64_t key1,
+                            int64_t *d_ids_ws, const int32_t *d_bag_offsets, int32_t bag_len, int64_t batch,
+                            int world, int64_t *const *h_rows_dst, int32_t *const *h_begin_dst,
+                            int32_t *const *h_end_dst, int max_ctas_per_sm, void *stream);
+
+/* ---- the whole row-sharded forward step as ONE call (rf_sharded_bag_forward) -------------------- */
+/* route -> barrier -> fused gather+pool into the SOURCE ranks' buffers over NVLink -> barrier -> combine, all stream  */
+/* ordered, no host synchronisation, no torch / NCCL types: the exchange runs on peer-mapped memory the binder         */
+/* provides (cudaMalloc + cudaIpc handles, cuMem fabric handles, an NCCL window, torch symmetric memory ...).          */
+/* Every rank allocates rf_shard_exchange_bytes(...) bytes + a signal pad of >= 2 * 16 uint32 (zero-initialised once), */
+/* maps every peer's two buffers, and fills the context with the pointers AS MAPPED INTO ITS OWN process.              */
+/* `step` counts 1, 2, 3, ... identically on every rank (the barriers compare it; no reset between steps).             */
+/* Keys: strings (d_bytes + d_str_offsets, hashed on the fly) or pre-hashed d_ids; bags: CSR d_bag_offsets or dense    */
+/* bag_len.  d_shard: this rank's rows (id % world == rank, local row id / world), [shard_rows, dim] fp32.             */
+/* Pads / semantics as rf_bag_forward; partial pools are summed in key order per owner and combined in rank order.     */
+typedef struct rf_shard_ctx {
+    int32_t rank, world;           /* world <= 16 (one NVSwitch box), one rank per GPU                         */
+    int64_t max_batch;             /* bags per rank per step the exchange buffers were sized for               */
+    int64_t max_keys;              /* keys per rank per step the exchange buffers were sized for               */
+    int32_t dim;
+    int32_t reserved;
+    void *peer_exchange[16];       /* [world] every rank's exchange buffer, mapped into this process           */
+    uint32_t *peer_signals[16];    /* [world] every rank's signal pad, mapped into this process                */
+} rf_shard_ctx;
+int64_t rf_shard_exchange_bytes(int world, int64_t max_batch, int64_t max_keys, int32_t dim);
+int rf_sharded_bag_forward(const rf_shard_ctx *ctx, const uint8_t *d_bytes, const int32_t *d_str_offsets,
+                           const int64_t *d_ids, int64_t num_bins, int mask_mode, int use_strong, uint64_t key0,
+                           uint64_t key1, const int32_t *d_bag_offsets, int32_t bag_len, int64_t batch,
+                           const float *d_shard, int64_t shard_rows, int combiner, uint64_t step, float *d_out,
+                           int64_t out_stride, void *stream);
+
 /* out[b] = reduce_{g<world, in rank order} partials[g][b][:]; avg divides by the bag's key count */
 int rf_combine_partials(const float *d_partials, int world, int64_t batch, int32_t dim, int combiner,
                         int32_t bag_len, const int32_t *d_bag_offsets, float *d_out, int64_t out_stride,

@@ -38,6 +38,11 @@ class VocabDesc(C.Structure):
                 ("slots", C.c_void_p), ("capacity", C.c_int64), ("n_terms", C.c_int64)]
 
 
+class ShardCtx(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("max_batch", C.c_int64), ("max_keys", C.c_int64), ("dim", C.c_int32),
+                ("reserved", C.c_int32), ("peer_exchange", C.c_void_p * 16), ("peer_signals", C.c_void_p * 16)]
+
+
 class AdamParams(C.Structure):
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("epsilon", C.c_float),
                 ("step", C.c_int64), ("lazy", C.c_int32), ("reserved", C.c_int32)]
@@ -113,6 +118,16 @@ def lib():
         L.rf_shard_route_tiles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_uint64,
                                            C.c_uint64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int,
                                            C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
+        L.rf_shard_exchange_bytes.restype = C.c_int64
+        L.rf_shard_exchange_bytes.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int32]
+        L.rf_sharded_bag_forward.restype = C.c_int
+        L.rf_sharded_bag_forward.argtypes = [C.POINTER(ShardCtx), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                             C.c_uint64, C.c_uint64, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int,
+                                             C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p]
+        L.rf_shard_route_tiles_ex.restype = C.c_int
+        L.rf_shard_route_tiles_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_uint64,
+                                              C.c_uint64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int,
+                                              C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
         L.rf_combine_partials.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int, C.c_int32, C.c_void_p,
                                           C.c_void_p, C.c_int64, C.c_void_p]
         L.rf_bag_adam_workspace_bytes.restype = C.c_int64

@@ -26,6 +26,8 @@ from ...strings import StringColumn
 from ...vocab_ops import DeviceVocabulary, bucketize
 
 SUPPORT_POOLING = ["null", "sum", "min", "max", "avg", "first", "last"]
+# bumped whenever any layer's table tensor is (re)created: cached launch plans hold raw table pointers
+TABLE_EPOCH = [0]
 _POOLED = ("sum", "avg", "min", "max")
 
 
@@ -143,6 +145,7 @@ class EmbeddingBag(Layer):
         if self.embeddings is None:
             self.embeddings = _new_table(self.input_dim, self.output_dim, self.embeddings_initializer,
                                          device or _default_device())
+            TABLE_EPOCH[0] += 1
         return self
 
     def get_weights(self):
@@ -157,6 +160,7 @@ class EmbeddingBag(Layer):
                              f"with provided weight shape {tuple(w.shape)}.")
         dev = self.embeddings.device if self.embeddings is not None else _default_device()
         self.embeddings = torch.nn.Parameter(w.to(dev).contiguous(), requires_grad=False)
+        TABLE_EPOCH[0] += 1
 
     def _check_combiner(self):
         if self.combiner not in self.support_pooling:

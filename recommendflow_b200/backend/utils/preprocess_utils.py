@@ -13,7 +13,8 @@ import torch
 from ..layers.preprocess_layers import (_POOLED, DiscreteEmbedding, DoubleHashingEmbedding, HashedEmbeddingBag, LookupEmbedding,
                                         _batch_and_len, _default_device, as_keys)
 from ...synth import PackedBatch
-from ...bag_ops import bag_forward
+from ...bag_ops import BagPlan, bag_forward
+from ..layers import preprocess_layers as _pl
 
 
 class PreprocessLayers(dict):
@@ -41,14 +42,52 @@ class PreprocessLayers(dict):
             col += width
         return layout, col
 
-    def forward_all(self, batch, names=None, out=None, keep_ids=None):
+    # ---- launch-plan cache (see forward_all) ---------------------------------------------------------------------
+    def _store_plan(self, key, plan, fused, keys, out):
+        cache = self.__dict__.setdefault("_plans", {})
+        if len(cache) >= 8:
+            cache.pop(next(iter(cache)))
+        sig = [(keys[n].data.data_ptr(), keys[n].offsets.data_ptr(), keys[n].shape, keys[n].bag_offsets is None) for n in fused]
+        cache[key] = {"plan": plan, "sig": sig, "out": (out.data_ptr(), out.stride(0)), "epoch": _pl.TABLE_EPOCH[0],
+                      "device": out.device}
+
+    def _launch_cached(self, key, fused, keys, layout, out, B):
+        ent = self.__dict__.get("_plans", {}).get(key)
+        if ent is None or ent["epoch"] != _pl.TABLE_EPOCH[0] or ent["device"] != out.device:
+            return False
+        plan, sig = ent["plan"], ent["sig"]
+        out_ptr, out_stride = out.data_ptr(), out.stride(0)
+        out_moved = (out_ptr, out_stride) != ent["out"]
+        keep = []
+        for i, n in enumerate(fused):
+            col = keys[n]
+            cur = (col.data.data_ptr(), col.offsets.data_ptr(), col.shape, col.bag_offsets is None)
+            if cur[2] != sig[i][2] or not cur[3] or not sig[i][3]:
+                return False                            # another bag length / a jagged column: rebuild
+            if cur != sig[i]:
+                desc = plan.descs[i]
+                desc.bytes, desc.str_offsets = cur[0], cur[1]
+                sig[i] = cur
+            if out_moved:
+                desc = plan.descs[i]
+                desc.out = out_ptr + 4 * layout[n][0]
+                desc.out_stride = out_stride if B > 1 else layout[n][1]
+            keep += [col.data, col.offsets]
+        ent["out"] = (out_ptr, out_stride)
+        ent["alive"] = (keep, out)                      # the launch reads these buffers: keep them referenced
+        plan.launch()
+        return True
+
+    def forward_all(self, batch, names=None, out=None, keep_ids=None, layout=None):
         """batch: {feature name: StringColumn | int tensor | lists}, or a `synth.PackedBatch` (all string features
         of the batch in ONE arena + ONE offsets buffer; a host-side PackedBatch crosses PCIe as two copies).
         Returns {name: tensor}.
 
         Hashed, pooled features go through one fused launch; the rest are called one by one.
         keep_ids: optional dict that receives, per fused feature, the row ids the launch gathered
-        ([tables, B * L] int64) and the bag length -- what the backward / optimizer step needs."""
+        ([tables, B * L] int64) and the bag length -- what the backward / optimizer step needs.
+        layout: optional {name: (column, width)} placing every fused feature inside a caller-owned `out` that may be
+        wider than the features (e.g. with a gap that another producer fills), instead of packing them side by side."""
         if isinstance(batch, PackedBatch):
             if not batch.data.is_cuda:
                 batch = batch.to(_default_device(), non_blocking=True)
@@ -57,7 +96,15 @@ class PreprocessLayers(dict):
         fused = [n for n in names if n in set(self.fused_names())]
         result = {}
         if fused:
-            layout, total = self.output_layout(fused)
+            if layout is None:
+                layout, total = self.output_layout(fused)
+            else:
+                if out is None:
+                    raise ValueError("a custom layout needs the caller's `out` buffer")
+                total = out.shape[1]
+                for n in fused:
+                    if n not in layout or layout[n][1] != self._width(n) or layout[n][0] + layout[n][1] > total:
+                        raise ValueError(f"layout of feature {n} does not fit `out`")
             hashed = [n for n in fused if isinstance(self[n], (DoubleHashingEmbedding, HashedEmbeddingBag))]
             keys = {n: as_keys(batch[n]) for n in hashed}
             if hashed:
@@ -69,36 +116,53 @@ class PreprocessLayers(dict):
                 out = torch.empty(B, total, dtype=torch.float32, device=dev or _default_device())
             elif tuple(out.shape) != (B, total):
                 raise ValueError(f"out must be [{B}, {total}]")
-            calls = []
-            for n in fused:
-                col, width = layout[n]
-                view = out[:, col:col + width]
-                if n in keys:
-                    layer = self[n].build(out.device)
-                    if _batch_and_len(keys[n])[0] != B:
-                        raise ValueError(f"feature {n}: batch size differs from the first feature's")
-                    if _batch_and_len(keys[n])[1] == 0:
-                        view.zero_()
-                    else:
-                        call = layer.field_call(keys[n], view)
-                        if keep_ids is not None:
-                            n_items = _batch_and_len(keys[n])[0] * _batch_and_len(keys[n])[1]
-                            call.ids_out = torch.empty(len(call.tables), n_items, dtype=torch.int64, device=out.device)
-                            keep_ids[n] = (call.ids_out, _batch_and_len(keys[n])[1])
-                        calls.append(call)
-                else:                                   # lookup / discrete: ids from their own small kernels
-                    call = self[n].field_call(batch[n], view)
-                    if call.ids.shape[1] != B * call.bag_len:
-                        raise ValueError(f"feature {n}: batch size differs from the first feature's")
-                    if call.bag_len == 0:
-                        view.zero_()
-                    else:
-                        calls.append(call)
-                        if keep_ids is not None:
-                            keep_ids[n] = (call.ids, call.bag_len)
-                result[n] = view
-            bag_forward(calls, B)
-            result["__fused__"] = out
+            # ---- cached launch plan: with hundreds of features, building the C descriptors in Python costs milliseconds
+            # per call (228 features: ~9 ms against a 0.17 ms kernel).  When the same features arrive with the same
+            # shapes -- every step of a loop -- the descriptors of the previous call are re-used; only pointers that
+            # moved (a freshly copied key arena, another output buffer) are patched in place.
+            cache_key = (tuple(fused), B, tuple(layout[n] for n in fused)) if (keep_ids is None and len(hashed) == len(fused)) else None
+            if cache_key is not None and self._launch_cached(cache_key, fused, keys, layout, out, B):
+                for n in fused:
+                    col, width = layout[n]
+                    result[n] = out[:, col:col + width]
+                result["__fused__"] = out
+                fused_done = True
+            else:
+                fused_done = False
+            if not fused_done:
+                calls = []
+                for n in fused:
+                    col, width = layout[n]
+                    view = out[:, col:col + width]
+                    if n in keys:
+                        layer = self[n].build(out.device)
+                        if _batch_and_len(keys[n])[0] != B:
+                            raise ValueError(f"feature {n}: batch size differs from the first feature's")
+                        if _batch_and_len(keys[n])[1] == 0:
+                            view.zero_()
+                        else:
+                            call = layer.field_call(keys[n], view)
+                            if keep_ids is not None:
+                                n_items = _batch_and_len(keys[n])[0] * _batch_and_len(keys[n])[1]
+                                call.ids_out = torch.empty(len(call.tables), n_items, dtype=torch.int64, device=out.device)
+                                keep_ids[n] = (call.ids_out, _batch_and_len(keys[n])[1])
+                            calls.append(call)
+                    else:                                   # lookup / discrete: ids from their own small kernels
+                        call = self[n].field_call(batch[n], view)
+                        if call.ids.shape[1] != B * call.bag_len:
+                            raise ValueError(f"feature {n}: batch size differs from the first feature's")
+                        if call.bag_len == 0:
+                            view.zero_()
+                        else:
+                            calls.append(call)
+                            if keep_ids is not None:
+                                keep_ids[n] = (call.ids, call.bag_len)
+                    result[n] = view
+                plan = BagPlan(calls, B)
+                plan.launch()
+                if cache_key is not None and len(calls) == len(fused):
+                    self._store_plan(cache_key, plan, fused, keys, out)
+                result["__fused__"] = out
         for n in names:
             if n not in result:
                 result[n] = self[n](batch[n])

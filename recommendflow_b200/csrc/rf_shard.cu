@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <atomic>
 
@@ -381,7 +382,8 @@ template <bool HASH, bool STAGE>
 __global__ void __launch_bounds__(kTileThreads, 4) shard_route_tile_kernel(
     const int64_t *__restrict__ ids, const uint8_t *__restrict__ bytes, const int32_t *__restrict__ soffs, HashSpec spec,
     int mask_empty, int64_t *__restrict__ ids_ws, const int32_t *__restrict__ boffs, int bag_len, int64_t batch, int world,
-    int tile_bags, PtrTable rows_dst, PtrTable begin_dst, PtrTable end_dst) {
+    int tile_bags, const __grid_constant__ PtrTable rows_dst, const __grid_constant__ PtrTable begin_dst,
+    const __grid_constant__ PtrTable end_dst) {
     extern __shared__ __align__(16) unsigned char tile_raw[];
     TileSmem &sm = *reinterpret_cast<TileSmem *>(tile_raw);
     int32_t *tb = reinterpret_cast<int32_t *>(sm.tile_boffs);      // STAGE: key offsets of the tile's bags
@@ -581,16 +583,19 @@ __global__ void __launch_bounds__(kTileThreads, 4) shard_route_tile_kernel(
             }
             __syncthreads();
             // ---- 5. stream out: owner g's run goes to [k0, k0 + seg_len[g]) of its buffer for this source ----
-            for (int g = 0; g < world; ++g) {
-                int64_t *dst = static_cast<int64_t *>(rows_dst.p[g]) + k0;
-                const uint32_t *src = sm.srow + sm.seg_base[g];
-                for (int i = tid; i < sm.seg_len[g]; i += kTileThreads) dst[i] = (int64_t)src[i];
-                int32_t *bd = static_cast<int32_t *>(begin_dst.p[g]), *ed = static_cast<int32_t *>(end_dst.p[g]);
-                for (int bl = tid; bl < nb; bl += kTileThreads) {
-                    const int32_t b = (int32_t)k0 + sm.beg[bl][g];
-                    bd[r0 + bl] = b;
-                    ed[r0 + bl] = b + sm.cnt[bl][g];
-                }
+            // one pass over the staged keys: key i belongs to the owner whose segment [seg_base[g], seg_base[g+1]) holds
+            // it; consecutive threads write consecutive slots of that owner's run (all 256 threads busy, instead of one
+            // short loop per owner)
+            for (int i = tid; i < n_keys; i += kTileThreads) {
+                int g = 0;
+                while (g + 1 < world && i >= sm.seg_base[g + 1]) ++g;
+                static_cast<int64_t *>(rows_dst.p[g])[k0 + (i - sm.seg_base[g])] = (int64_t)sm.srow[i];
+            }
+            for (int e = tid; e < nb * world; e += kTileThreads) {
+                const int g = e / nb, bl = e - g * nb;
+                const int32_t b = (int32_t)k0 + sm.beg[bl][g];
+                static_cast<int32_t *>(begin_dst.p[g])[r0 + bl] = b;
+                static_cast<int32_t *>(end_dst.p[g])[r0 + bl] = b + sm.cnt[bl][g];
             }
             __syncthreads();
             r0 = r1;
@@ -647,6 +652,27 @@ __global__ void __launch_bounds__(256) combine_partials_kernel(const float *__re
             out[b * out_stride + c] = acc;
         }
     }
+}
+
+// Cross-GPU barrier on peer-mapped signal pads (one CTA): thread t tells rank t "rank `me` has reached `value`" and
+// waits until rank t has told this rank the same.  Everything this stream wrote to peers before the barrier is
+// released with a system-scope fence first, so after the barrier every rank sees every other rank's earlier writes.
+// One rank per GPU (ranks sharing a GPU would wait on kernels that cannot be co-scheduled).  Bounded spin: traps.
+__global__ void __launch_bounds__(32) shard_barrier_kernel(const __grid_constant__ PtrTable signals, int me, int world, int slot,
+                                                           uint32_t value) {
+    const int t = threadIdx.x;
+    if (t >= world) return;
+    __threadfence_system();
+    uint32_t *remote = static_cast<uint32_t *>(signals.p[t]) + slot * kMaxWorld + me;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(value) : "memory");
+    const uint32_t *mine = static_cast<const uint32_t *>(signals.p[me]) + slot * kMaxWorld + t;
+    uint32_t seen = 0;
+    for (uint64_t spin = 0;; ++spin) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+        if ((int32_t)(seen - value) >= 0) break;
+        if (spin > (1ull << 31)) __trap();
+    }
+    __threadfence_system();
 }
 
 static int grid_for(int64_t work_items, int per_block, int dev_sms) {
@@ -714,10 +740,11 @@ static int route_impl(const int64_t *d_ids, const uint8_t *d_bytes, const int32_
     return RF_OK;
 }
 
-int rf_shard_route_tiles(const uint8_t *d_bytes, const int32_t *d_str_offsets, const int64_t *d_ids, int64_t num_bins,
-                         int mask_mode, int use_strong, uint64_t key0, uint64_t key1, int64_t *d_ids_ws,
-                         const int32_t *d_bag_offsets, int32_t bag_len, int64_t batch, int world, int64_t *const *h_rows_dst,
-                         int32_t *const *h_begin_dst, int32_t *const *h_end_dst, void *stream) {
+int rf_shard_route_tiles_ex(const uint8_t *d_bytes, const int32_t *d_str_offsets, const int64_t *d_ids, int64_t num_bins,
+                            int mask_mode, int use_strong, uint64_t key0, uint64_t key1, int64_t *d_ids_ws,
+                            const int32_t *d_bag_offsets, int32_t bag_len, int64_t batch, int world, int64_t *const *h_rows_dst,
+                            int32_t *const *h_begin_dst, int32_t *const *h_end_dst, int max_ctas_per_sm, void *stream) {
+    if (max_ctas_per_sm < 0) return set_error(RF_ERR_INVALID, "max_ctas_per_sm must be >= 0");
     if (world < 1 || world > kMaxWorld) return set_error(RF_ERR_INVALID, "world must be in [1, %d]", kMaxWorld);
     if (batch < 0 || batch > INT32_MAX) return set_error(RF_ERR_INVALID, "batch out of range");
     if (batch == 0) return RF_OK;
@@ -750,7 +777,12 @@ int rf_shard_route_tiles(const uint8_t *d_bytes, const int32_t *d_str_offsets, c
     int64_t tile_bags = kTileCap / per_bag;
     if (tile_bags < 8) tile_bags = 8;
     if (tile_bags > kTileBags) tile_bags = kTileBags;
-    const int grid = grid_for((batch + tile_bags - 1) / tile_bags, 1, sms);
+    int grid = grid_for((batch + tile_bags - 1) / tile_bags, 1, sms);
+    // experiments: RF_ROUTE_CTAS_PER_SM caps the grid (the kernel walks its tiles grid-stride), e.g. 1 leaves the
+    // rest of every SM to a concurrently running pooling kernel
+    static const int env_cap = getenv("RF_ROUTE_CTAS_PER_SM") ? atoi(getenv("RF_ROUTE_CTAS_PER_SM")) : -1;
+    const int route_cap = env_cap >= 0 ? env_cap : max_ctas_per_sm;
+    if (route_cap > 0 && grid > route_cap * sms) grid = route_cap * sms;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t smem = sizeof(TileSmem);
     static const bool stage = !(getenv("RF_ROUTE_STAGE") && atoi(getenv("RF_ROUTE_STAGE")) == 0);
@@ -775,6 +807,14 @@ int rf_shard_route_tiles(const uint8_t *d_bytes, const int32_t *d_str_offsets, c
     RF_CUDA(cudaGetLastError());
     g_launches.fetch_add(1);
     return RF_OK;
+}
+
+int rf_shard_route_tiles(const uint8_t *d_bytes, const int32_t *d_str_offsets, const int64_t *d_ids, int64_t num_bins,
+                         int mask_mode, int use_strong, uint64_t key0, uint64_t key1, int64_t *d_ids_ws,
+                         const int32_t *d_bag_offsets, int32_t bag_len, int64_t batch, int world, int64_t *const *h_rows_dst,
+                         int32_t *const *h_begin_dst, int32_t *const *h_end_dst, void *stream) {
+    return rf_shard_route_tiles_ex(d_bytes, d_str_offsets, d_ids, num_bins, mask_mode, use_strong, key0, key1, d_ids_ws, d_bag_offsets,
+                                   bag_len, batch, world, h_rows_dst, h_begin_dst, h_end_dst, 0, stream);
 }
 
 int rf_shard_route(const int64_t *d_ids, const int32_t *d_bag_offsets, int32_t bag_len, int64_t batch, int world,
@@ -824,6 +864,77 @@ int rf_combine_partials(const float *d_partials, int world, int64_t batch, int32
     RF_CUDA(cudaGetLastError());
     g_launches.fetch_add(1);
     return RF_OK;
+}
+
+
+int64_t rf_shard_exchange_bytes(int world, int64_t max_batch, int64_t max_keys, int32_t dim) {
+    if (world < 1 || world > kMaxWorld || max_batch <= 0 || max_keys <= 0 || dim <= 0) return -1;
+    const int64_t rows = (int64_t)world * max_keys * 8;
+    const int64_t bounds = ((2 * (int64_t)world * max_batch * 4 + 15) / 16) * 16;
+    return rows + bounds + (int64_t)world * max_batch * dim * 4;
+}
+
+int rf_sharded_bag_forward(const rf_shard_ctx *ctx, const uint8_t *d_bytes, const int32_t *d_str_offsets, const int64_t *d_ids,
+                           int64_t num_bins, int mask_mode, int use_strong, uint64_t key0, uint64_t key1,
+                           const int32_t *d_bag_offsets, int32_t bag_len, int64_t batch, const float *d_shard, int64_t shard_rows,
+                           int combiner, uint64_t step, float *d_out, int64_t out_stride, void *stream) {
+    if (!ctx) return set_error(RF_ERR_INVALID, "rf_sharded_bag_forward: NULL context");
+    const int W = ctx->world, me = ctx->rank;
+    if (W < 1 || W > kMaxWorld || me < 0 || me >= W) return set_error(RF_ERR_INVALID, "bad rank / world");
+    if (batch <= 0 || batch > ctx->max_batch) return set_error(RF_ERR_INVALID, "batch must be in [1, max_batch]");
+    if (step == 0 || step > 0x7fffffffull) return set_error(RF_ERR_INVALID, "step must count up from 1 (same value on every rank)");
+    if (combiner < RF_COMBINER_SUM || combiner > RF_COMBINER_MAX) return set_error(RF_ERR_INVALID, "bad combiner");
+    if (!d_shard || !d_out) return set_error(RF_ERR_INVALID, "rf_sharded_bag_forward: NULL shard / out");
+    const int64_t B = ctx->max_batch, K = ctx->max_keys, D = ctx->dim;
+    const int64_t rows_bytes = (int64_t)W * K * 8;
+    const int64_t bounds_bytes = ((2 * (int64_t)W * B * 4 + 15) / 16) * 16;
+    PtrTable sig{};
+    int64_t *rows_dst[kMaxWorld];
+    int32_t *beg_dst[kMaxWorld], *end_dst[kMaxWorld];
+    for (int g = 0; g < W; ++g) {
+        char *base = static_cast<char *>(ctx->peer_exchange[g]);
+        if (!base || !ctx->peer_signals[g]) return set_error(RF_ERR_INVALID, "rf_sharded_bag_forward: peer %d is not mapped", g);
+        rows_dst[g] = reinterpret_cast<int64_t *>(base) + (int64_t)me * K;                 // my slice of owner g's buffers
+        beg_dst[g] = reinterpret_cast<int32_t *>(base + rows_bytes) + (int64_t)me * B;
+        end_dst[g] = reinterpret_cast<int32_t *>(base + rows_bytes) + (int64_t)(W + me) * B;
+        sig.p[g] = ctx->peer_signals[g];
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // 1. route my keys to their owners (peer stores)
+    int rc = rf_shard_route_tiles(d_bytes, d_str_offsets, d_ids, num_bins, mask_mode, use_strong, key0, key1, nullptr, d_bag_offsets,
+                                  bag_len, batch, W, rows_dst, beg_dst, end_dst, stream);
+    if (rc != RF_OK) return rc;
+    // 2. every source's routing has landed
+    shard_barrier_kernel<<<1, 32, 0, st>>>(sig, me, W, 0, (uint32_t)step);
+    // 3. pool what each source asked of my shard, straight into that source's partial plane `me`
+    char *mine = static_cast<char *>(ctx->peer_exchange[me]);
+    rf_field_desc fields[kMaxWorld];
+    memset(fields, 0, sizeof(fields));
+    for (int k = 0; k < W; ++k) {
+        const int s = (me + k) % W;                    // rotated: at any moment the W owners write to W different ranks
+        rf_field_desc &f = fields[k];
+        f.ids = reinterpret_cast<const int64_t *>(mine) + (int64_t)s * K;
+        f.bag_offsets = reinterpret_cast<const int32_t *>(mine + rows_bytes) + (int64_t)s * B;
+        f.bag_ends = reinterpret_cast<const int32_t *>(mine + rows_bytes) + (int64_t)(W + s) * B;
+        f.n_items = K / W > 0 ? K / W : 1;             // an estimate only steers tile sizing
+        f.n_tables = 1;
+        f.tables[0].weights = d_shard;
+        f.tables[0].num_bins = shard_rows;
+        f.dim = (int32_t)D;
+        f.combiner = combiner == RF_COMBINER_AVG ? RF_COMBINER_SUM : combiner;
+        f.flags = RF_FIELD_PARTIAL;
+        f.out = reinterpret_cast<float *>(static_cast<char *>(ctx->peer_exchange[s]) + rows_bytes + bounds_bytes) + (int64_t)me * B * D;
+        f.out_stride = D;
+    }
+    rc = rf_bag_forward(fields, W, batch, stream);
+    if (rc != RF_OK) return rc;
+    // 4. every owner's partials have landed here
+    shard_barrier_kernel<<<1, 32, 0, st>>>(sig, me, W, 1, (uint32_t)step);
+    RF_CUDA(cudaGetLastError());
+    g_launches.fetch_add(2);
+    // 5. reduce the W partials in rank order (avg divides by the bag's key count)
+    return rf_combine_partials(reinterpret_cast<const float *>(mine + rows_bytes + bounds_bytes), W, batch, (int32_t)D, combiner,
+                               bag_len, d_bag_offsets, d_out, out_stride, stream);
 }
 
 }  // extern "C"

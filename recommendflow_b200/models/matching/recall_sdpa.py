@@ -51,8 +51,35 @@ class RecallSdpa(torch.nn.Module):
         return torch.nn.functional.normalize(x, dim=1, eps=1e-12)
 
     def towers(self, batch, behaviour=None):
-        embs = self.preprocessor.forward_all(batch, names=self.user_cols + self.ad_cols)
-        return self.towers_from_embeddings(embs, behaviour)
+        names = self.user_cols + self.ad_cols
+        fused = set(self.preprocessor.fused_names())
+        if (self.seq_encoder is None or behaviour is None or torch.is_grad_enabled() and behaviour[0].requires_grad
+                or not all(n in fused for n in names)):
+            embs = self.preprocessor.forward_all(batch, names=names)
+            return self.towers_from_embeddings(embs, behaviour)
+        # One buffer [user features | encoded behaviour sequence | ad features]: the fused bag launch writes the two
+        # outer parts in place, the sequence encoder's output drops into the gap, and each tower reads its part as
+        # a strided view -- no concatenation copy of the [B, ~1900] tower inputs.
+        x, mask = behaviour
+        d_seq = self.seq_encoder.d_model
+        layout, col = {}, 0
+        for n in self.user_cols:
+            w = self.preprocessor._width(n)
+            layout[n] = (col, w)
+            col += w
+        gap = col
+        col += d_seq
+        for n in self.ad_cols:
+            w = self.preprocessor._width(n)
+            layout[n] = (col, w)
+            col += w
+        big = torch.empty(x.shape[0], col, dtype=torch.float32, device=x.device)
+        self.preprocessor.forward_all(batch, names=names, out=big, layout=layout)
+        big[:, gap:gap + d_seq] = self.seq_encoder(x, x, x, mask).mean(dim=1)
+        u, a = big[:, :gap + d_seq], big[:, gap + d_seq:]
+        if self.global_l2_norm:
+            return self.embedding_norm(self.user_dense(u)), self.embedding_norm(self.ad_dense(a))
+        return self.user_dense(u, l2_normalize=True), self.ad_dense(a, l2_normalize=True)
 
     def towers_from_embeddings(self, embs, behaviour=None):
         """The dense part: {feature name: pooled embedding} (+ behaviour sequence) -> normalised tower outputs."""

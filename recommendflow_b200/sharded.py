@@ -76,7 +76,7 @@ class CudaShardOps(object):
                 offs_local.data_ptr(), arr_o, arr_r, C.c_void_p(torch.cuda.current_stream(keys.device).cuda_stream)))
 
     def route_tiles(self, keys, num_bins, mask_value, salt, ids_ws, bag_offsets, bag_len, batch, world,
-                    rows_dst_ptrs, begin_dst_ptrs, end_dst_ptrs):
+                    rows_dst_ptrs, begin_dst_ptrs, end_dst_ptrs, max_ctas_per_sm=0):
         """Single-pass routing into the gapped "tile" layout (rf_shard_route_tiles)."""
         arrs = [(C.c_void_p * world)(*p) for p in (rows_dst_ptrs, begin_dst_ptrs, end_dst_ptrs)]
         if isinstance(keys, StringColumn):
@@ -91,9 +91,9 @@ class CudaShardOps(object):
             args = (None, None, keys.data_ptr(), 0, 0, 0, 0, 0, None)
             dev = keys.device
         with torch.cuda.device(dev):
-            nat.check(nat.lib().rf_shard_route_tiles(*args, None if bag_offsets is None else bag_offsets.data_ptr(),
-                                                     bag_len or 0, batch, world, *arrs,
-                                                     C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+            nat.check(nat.lib().rf_shard_route_tiles_ex(*args, None if bag_offsets is None else bag_offsets.data_ptr(),
+                                                        bag_len or 0, batch, world, *arrs, int(max_ctas_per_sm),
+                                                        C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
 
     def route(self, ids, bag_offsets, bag_len, batch, world, counts_ws, offs_local, offs_dst_ptrs, rows_dst_ptrs):
         arr_o = (C.c_void_p * world)(*offs_dst_ptrs) if offs_dst_ptrs is not None else None
@@ -139,6 +139,52 @@ class CudaShardOps(object):
                 state["ws"].data_ptr(), state["ws"].numel(), C.c_void_p(torch.cuda.current_stream(shard.device).cuda_stream)))
 
 
+class CAbiShardedStep(object):
+    """The whole sharded forward step through ONE C call (rf_sharded_bag_forward): what a binder without torch would
+    use.  Here torch's symmetric memory only plays the part of "memory every peer can map"; the barriers are the
+    library's own (peer-mapped signal pads), no torch.distributed call happens in a step."""
+
+    def __init__(self, num_bins, dim, combiner, max_batch, max_keys, group=None, salt=None, mask_value=""):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.num_bins, self.dim, self.combiner, self.salt, self.mask_value = int(num_bins), int(dim), combiner, salt, mask_value
+        dev = torch.device("cuda", torch.cuda.current_device())
+        t = torch.tensor([max_keys], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        self.max_batch, self.max_keys = int(max_batch), int(t.item())
+        need = int(nat.lib().rf_shard_exchange_bytes(self.world, self.max_batch, self.max_keys, self.dim))
+        self.exchange_bytes = (need + 255) // 256 * 256
+        self.raw = symm.empty(self.exchange_bytes + 256, dtype=torch.uint8, device=dev)
+        self.hdl = symm.rendezvous(self.raw, self.group)
+        self.raw.zero_()                                   # the signal pads start at 0
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        self.ctx = nat.ShardCtx(rank=self.rank, world=self.world, max_batch=self.max_batch, max_keys=self.max_keys, dim=self.dim)
+        for g, p in enumerate(self.hdl.buffer_ptrs):
+            self.ctx.peer_exchange[g] = int(p)
+            self.ctx.peer_signals[g] = int(p) + self.exchange_bytes
+        self.step = 0
+
+    def __call__(self, keys, shard, out=None):
+        if isinstance(keys, StringColumn):
+            mode, _ = nat.string_mask(self.mask_value)
+            strong, k0, k1 = nat.salt_to_key(self.salt)
+            args = (keys.data.data_ptr(), keys.offsets.data_ptr(), None, self.num_bins, mode, strong, k0, k1)
+        else:                                              # BucketIds
+            args = (None, None, keys.ids.data_ptr(), 0, 0, 0, 0, 0)
+        B, L = keys.shape
+        if out is None:
+            out = torch.empty(B, self.dim, dtype=torch.float32, device=shard.device)
+        self.step += 1
+        with torch.cuda.device(shard.device):
+            nat.check(nat.lib().rf_sharded_bag_forward(
+                C.byref(self.ctx), *args, None if keys.bag_offsets is None else keys.bag_offsets.data_ptr(), L or 0, B,
+                shard.data_ptr(), shard.shape[0], nat.COMBINER[self.combiner], self.step, out.data_ptr(), out.stride(0),
+                C.c_void_p(torch.cuda.current_stream(shard.device).cuda_stream)))
+        return out
+
+
 def shard_rows(num_bins, rank, world):
     """Number of table rows rank `rank` holds (ids rank, rank + world, ...)."""
     return (num_bins - rank + world - 1) // world if num_bins > rank else 0
@@ -181,7 +227,12 @@ class ShardedEmbeddingBag(torch.nn.Module):
         # pipelined mode: resident CTAs per SM the pooling kernel may take (of 4), so that the routing
         # kernels of the next step find room on every SM; 0 = no cap
         import os
-        self.pool_ctas_per_sm = int(os.environ.get("RF_SHARD_POOL_CTAS", "3"))
+        self.pool_ctas_per_sm = int(os.environ.get("RF_SHARD_POOL_CTAS", "0"))
+        # ... and the routing kernel's own residency cap while it runs under the previous step's pooling: measured on the
+        # one-GPU emulation of the 8-way step (tools/emu_sharded.py, profiles/r2_emu_sharded.json): uncapped routing +
+        # uncapped pooling 0.761 ms, routing at 2 CTAs/SM 0.736, at 1 CTA/SM 0.750; capping the POOLING kernel instead
+        # (3 of 4 CTAs/SM, round 1's default) costs 0.09 ms because its tiles are then walked statically
+        self.route_ctas_per_sm = int(os.environ.get("RF_SHARD_ROUTE_CTAS", "2"))
         # p2p routing layout: "tiles" = single-pass routing into gapped per-bag [begin, end) runs;
         # "csr" = count / scan / scatter into a gap-free CSR (what the nccl transport always uses)
         self.route_layout = os.environ.get("RF_SHARD_ROUTE", "tiles")
@@ -326,7 +377,7 @@ class ShardedEmbeddingBag(torch.nn.Module):
                 elif b["ids_ws"] is None and self.keep_ids:
                     b["ids_ws"] = torch.empty(self.max_keys, dtype=torch.int64, device=self.device)
                 self.ops.route_tiles(src, self.num_bins, self.mask_value, self.salt, b["ids_ws"], bag_offsets, L, B, W,
-                                     rows_dst, offs_dst, ends_dst)
+                                     rows_dst, offs_dst, ends_dst, max_ctas_per_sm=self.route_ctas_per_sm if overlap else 0)
             else:
                 self._route(keys, B, L, bag_offsets, offs_dst, rows_dst)
             if not self.deterministic:

@@ -77,6 +77,7 @@ def test_header_is_plain_c_and_ctypes_structs_match_it(tmp_path):
               "rf_field_desc": (nat.FieldDesc, ["bytes", "str_offsets", "int_values", "ids", "bag_offsets", "bag_ends", "n_items",
                                                 "bag_len", "n_tables", "tables", "dim", "combiner", "mask_mode", "flags",
                                                 "int_mask_value", "out", "out_stride", "ids_out", "mask_bytes", "mask_len"]),
+              "rf_shard_ctx": (nat.ShardCtx, ["rank", "world", "max_batch", "max_keys", "dim", "peer_exchange", "peer_signals"]),
               "rf_vocab_desc": (nat.VocabDesc, ["term_bytes", "term_offsets", "term_ints", "slots", "capacity", "n_terms"]),
               "rf_adam_params": (nat.AdamParams, ["lr", "beta1", "beta2", "epsilon", "step", "lazy"]),
               "rf_example_column": (nat.ExampleColumn, ["name", "name_len", "kind", "n_values", "n_bytes", "row_counts", "bytes_out",

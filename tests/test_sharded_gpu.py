@@ -72,6 +72,20 @@ def _worker(rank, world, port, q):
         layer.set_full_weights(full)
         got = layer(BucketIds(torch.from_numpy(ids).to(f"cuda:{rank}"), col.bag_offsets)).cpu().numpy()
         out[("avg", "p2p-prehashed")] = (bool(np.array_equal(got, want)), 0.0)
+        # the whole step through the single C-ABI entry (rf_sharded_bag_forward: own barriers, no torch collective)
+        from recommendflow_b200.sharded import CAbiShardedStep, shard_rows
+        for combiner in ("avg", "max"):
+            stepper = CAbiShardedStep(N, D, combiner, B, B * 200)
+            mine = torch.from_numpy(np.ascontiguousarray(full[rank::world])).to(f"cuda:{rank}")
+            assert mine.shape[0] == shard_rows(N, rank, world)
+            for _ in range(3):
+                got = stepper(col, mine)
+            torch.cuda.synchronize()
+            want = sharded_reference(ids, bag, full, world, combiner)
+            out[(combiner, "c-abi")] = (bool(np.array_equal(got.cpu().numpy(), want)), 0.0)
+            got = stepper(BucketIds(torch.from_numpy(ids).to(f"cuda:{rank}"), col.bag_offsets), mine)
+            torch.cuda.synchronize()
+            out[(combiner, "c-abi-prehashed")] = (bool(np.array_equal(got.cpu().numpy(), want)), 0.0)
         # dense [B, L] padded input (reference semantics: pads pool row 0 of owner 0)
         L = 6
         a2, o2 = oracle.encode_strings([f"k{rank}_{i % 37}" if i % 5 else "" for i in range(B * L)])
