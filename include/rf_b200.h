@@ -322,6 +322,14 @@ int rf_inbatch_softmax_ce_backward(const float *d_query, const float *d_doc, con
                                    const float *d_lse, int64_t batch, int32_t dim, float scale,
                                    float upstream, float *d_grad_query, float *d_grad_doc, void *stream);
 
+/* One [batch x batch] BLOCK of a wider logits matrix (data-parallel towers: every rank's queries against the docs  */
+/* all-gathered from all ranks).  d_lse is the log-sum-exp over the WHOLE row (all blocks); the positives sit on the */
+/* diagonal only in the rank's own block (positives_on_diagonal = 1), other blocks hold negatives only (0).          */
+int rf_inbatch_softmax_ce_backward_block(const float *d_query, const float *d_doc, const float *d_y, const float *d_lse,
+                                         int64_t batch, int32_t dim, float scale, float upstream,
+                                         int positives_on_diagonal, float *d_grad_query, float *d_grad_doc,
+                                         void *stream);
+
 /* ---- vocabulary lookup / bucketisation ------------------------------------ */
 /* Keras StringLookup / IntegerLookup(vocabulary=vocabs, output_mode="int") as LookupEmbedding builds */
 /* them (backend/layers/preprocess_layers.py:148-150): term i -> i + 1, out-of-vocabulary -> 0.      */

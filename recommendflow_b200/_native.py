@@ -153,6 +153,8 @@ def lib():
         L.rf_sdpa_backward.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 4
         L.rf_inbatch_softmax_ce_backward.restype = C.c_int
         L.rf_inbatch_softmax_ce_backward.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_float, C.c_float] + [C.c_void_p] * 3
+        L.rf_inbatch_softmax_ce_backward_block.restype = C.c_int
+        L.rf_inbatch_softmax_ce_backward_block.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_int] + [C.c_void_p] * 3
         L.rf_vocab_build.argtypes = [C.POINTER(VocabDesc), C.c_void_p]
         L.rf_vocab_lookup_strings.argtypes = [C.POINTER(VocabDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.rf_vocab_lookup_int64.argtypes = [C.POINTER(VocabDesc), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]

@@ -194,7 +194,8 @@ class Sequential(Layer):
 def create_mlp(hidden_units, dropout_rate, activation, normalization_layer, name=None):
     layers = []
     for units in hidden_units:
-        layers.append(normalization_layer)
+        if normalization_layer is not None:
+            layers.append(normalization_layer)
         layers.append(_Activated(units, activation))
         layers.append(Dropout(dropout_rate))
     return Sequential(layers, name=name)

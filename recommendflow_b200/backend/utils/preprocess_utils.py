@@ -8,13 +8,22 @@ convention `layers[name](batch[name])` (models/matching/que2search.py:68,76-79) 
 it additionally offers `forward_all(batch)`, which sends every pooled hashing feature of the
 batch through ONE kernel launch and hands back per-feature views of one [B, sum(2*D)] buffer.
 """
+import ctypes as C
+
+import numpy as np
 import torch
 
 from ..layers.preprocess_layers import (_POOLED, DiscreteEmbedding, DoubleHashingEmbedding, HashedEmbeddingBag, LookupEmbedding,
                                         _batch_and_len, _default_device, as_keys)
 from ...synth import PackedBatch
+from ... import _native as nat
 from ...bag_ops import BagPlan, bag_forward
 from ..layers import preprocess_layers as _pl
+
+
+def np_u64(delta):
+    """A (possibly negative) pointer delta as the uint64 that adds to the same address modulo 2^64."""
+    return np.uint64(delta % (1 << 64))
 
 
 class PreprocessLayers(dict):
@@ -78,6 +87,45 @@ class PreprocessLayers(dict):
         plan.launch()
         return True
 
+    # Fast path for a PackedBatch (every string feature of the batch in one arena + one offsets buffer) whose field
+    # layout is the one of the previous call -- the steady state of a training / serving loop: the cached descriptors
+    # are re-based with two vector additions (key arena / offsets moved, output moved) and launched.  No per-feature
+    # Python work at all: 228 features cost ~20 us of host time instead of ~9 ms.
+    def _store_packed(self, packed, names, plan, layout, out):
+        words = C.sizeof(nat.FieldDesc) // 8
+        view = np.frombuffer(plan.descs, dtype=np.uint64).reshape(-1, words)
+        items = [packed.layout[n] for n in names]
+        self.__dict__["_packed_plan"] = {
+            "plan": plan, "view": view, "names": tuple(names), "shapes": tuple((it[2], it[3]) for it in items),
+            "layout": dict(layout), "layout_key": tuple(layout[n] for n in names),
+            "out_cols": np.array([4 * layout[n][0] for n in names], dtype=np.uint64),
+            "out_shape": (tuple(out.shape), out.stride(0)), "epoch": _pl.TABLE_EPOCH[0], "device": out.device,
+            "col_bytes": nat.FieldDesc.bytes.offset // 8, "col_offs": nat.FieldDesc.str_offsets.offset // 8,
+            "col_out": nat.FieldDesc.out.offset // 8}
+
+    def _launch_packed(self, packed, names, out, layout):
+        ent = self.__dict__.get("_packed_plan")
+        if (ent is None or ent["names"] != tuple(names) or ent["epoch"] != _pl.TABLE_EPOCH[0] or ent["device"] != out.device
+                or ent["out_shape"] != (tuple(out.shape), out.stride(0))
+                or (layout is not None and tuple(layout[n] for n in names) != ent["layout_key"])):
+            return False
+        try:
+            items = [packed.layout[n] for n in names]              # (byte offset, offsets index, n_items, shape)
+        except KeyError:
+            return False
+        if tuple((it[2], it[3]) for it in items) != ent["shapes"]:
+            return False
+        n = len(items)
+        b0 = np.fromiter((it[0] for it in items), dtype=np.uint64, count=n)
+        o0 = np.fromiter((it[1] for it in items), dtype=np.uint64, count=n)
+        view = ent["view"]
+        view[:, ent["col_bytes"]] = np.uint64(packed.data.data_ptr()) + b0
+        view[:, ent["col_offs"]] = np.uint64(packed.offsets.data_ptr()) + o0 * np.uint64(4)
+        view[:, ent["col_out"]] = np.uint64(out.data_ptr()) + ent["out_cols"]
+        ent["alive"] = (packed, out)
+        ent["plan"].launch()
+        return True
+
     def forward_all(self, batch, names=None, out=None, keep_ids=None, layout=None):
         """batch: {feature name: StringColumn | int tensor | lists}, or a `synth.PackedBatch` (all string features
         of the batch in ONE arena + ONE offsets buffer; a host-side PackedBatch crosses PCIe as two copies).
@@ -88,9 +136,15 @@ class PreprocessLayers(dict):
         ([tables, B * L] int64) and the bag length -- what the backward / optimizer step needs.
         layout: optional {name: (column, width)} placing every fused feature inside a caller-owned `out` that may be
         wider than the features (e.g. with a gap that another producer fills), instead of packing them side by side."""
+        packed = None
         if isinstance(batch, PackedBatch):
             if not batch.data.is_cuda:
                 batch = batch.to(_default_device(), non_blocking=True)
+            packed = batch
+            if keep_ids is None and out is not None and names is not None and self._launch_packed(packed, names, out, layout):
+                res = {n: out[:, c:c + w] for n, (c, w) in self.__dict__["_packed_plan"]["layout"].items()}
+                res["__fused__"] = out
+                return res
             batch = batch.columns()
         names = list(names) if names is not None else [n for n in self if n in batch]
         fused = [n for n in names if n in set(self.fused_names())]
@@ -162,6 +216,8 @@ class PreprocessLayers(dict):
                 plan.launch()
                 if cache_key is not None and len(calls) == len(fused):
                     self._store_plan(cache_key, plan, fused, keys, out)
+                    if packed is not None and len(fused) == len(names):
+                        self._store_packed(packed, names, plan, layout, out)
                 result["__fused__"] = out
         for n in names:
             if n not in result:

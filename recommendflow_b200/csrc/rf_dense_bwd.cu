@@ -122,7 +122,8 @@ constexpr int kOth = 64;     // rows of the other side per tile
 template <bool OWNER_IS_QUERY, int NV>
 __global__ void __launch_bounds__(kThreads)
 ce_backward_kernel(const float *__restrict__ own, const float *__restrict__ oth, const float *__restrict__ y,
-                   const float *__restrict__ lse, int64_t B, int dim, float scale, float coef, float *__restrict__ grad_own) {
+                   const float *__restrict__ lse, int64_t B, int dim, float scale, float coef, float diag_on,
+                   float *__restrict__ grad_own) {
     extern __shared__ float smem[];
     const int ld = dim + 1;
     float *A = smem;                   // [kOwn][dim + 1] owner rows
@@ -164,7 +165,7 @@ ce_backward_kernel(const float *__restrict__ own, const float *__restrict__ oth,
                 float cv = 0.f;
                 if (go < B && gt < B) {
                     const int64_t row = OWNER_IS_QUERY ? go : gt;       // the query index owns lse and y
-                    cv = coef * y[row] * (expf(scale * s[w][u] - lse[row]) - (go == gt ? 1.0f : 0.0f));
+                    cv = coef * y[row] * (expf(scale * s[w][u] - lse[row]) - (go == gt ? diag_on : 0.0f));
                 }
                 C[(o0 + w) * (kOth + 1) + tx + 16 * u] = cv;
             }
@@ -195,14 +196,14 @@ ce_backward_kernel(const float *__restrict__ own, const float *__restrict__ oth,
 
 template <bool OWNER_IS_QUERY>
 int launch_ce_pass(const float *own, const float *oth, const float *y, const float *lse, int64_t B, int dim, float scale,
-                   float coef, float *grad_own, cudaStream_t st) {
+                   float coef, float diag_on, float *grad_own, cudaStream_t st) {
     const size_t smem = sizeof(float) * ((size_t)(kOwn + kOth) * (dim + 1) + (size_t)kOwn * (kOth + 1));
     const unsigned grid = (unsigned)((B + kOwn - 1) / kOwn);
 #define RF_CE_LAUNCH(NV)                                                                                              \
     do {                                                                                                              \
         auto fn = ce_backward_kernel<OWNER_IS_QUERY, NV>;                                                              \
         RF_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
-        fn<<<grid, kThreads, smem, st>>>(own, oth, y, lse, B, dim, scale, coef, grad_own);                            \
+        fn<<<grid, kThreads, smem, st>>>(own, oth, y, lse, B, dim, scale, coef, diag_on, grad_own);                   \
     } while (0)
     if (dim <= 128) RF_CE_LAUNCH(8);
     else if (dim <= 256) RF_CE_LAUNCH(16);
@@ -238,9 +239,9 @@ int rf_sdpa_backward(const float *d_q, const float *d_k, const float *d_v, const
     return RF_OK;
 }
 
-int rf_inbatch_softmax_ce_backward(const float *d_query, const float *d_doc, const float *d_y, const float *d_lse, int64_t batch,
-                                   int32_t dim, float scale, float upstream, float *d_grad_query, float *d_grad_doc,
-                                   void *stream) {
+int rf_inbatch_softmax_ce_backward_block(const float *d_query, const float *d_doc, const float *d_y, const float *d_lse,
+                                         int64_t batch, int32_t dim, float scale, float upstream, int positives_on_diagonal,
+                                         float *d_grad_query, float *d_grad_doc, void *stream) {
     if (batch < 0 || dim <= 0) return set_error(RF_ERR_INVALID, "bad in-batch shape");
     if (dim > 512) return set_error(RF_ERR_UNSUPPORTED, "rf_inbatch_softmax_ce_backward handles dim <= 512 (got %d)", dim);
     if (batch == 0) return RF_OK;
@@ -248,19 +249,27 @@ int rf_inbatch_softmax_ce_backward(const float *d_query, const float *d_doc, con
     if (!d_grad_query && !d_grad_doc) return set_error(RF_ERR_INVALID, "rf_inbatch_softmax_ce_backward: no output requested");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float coef = upstream * scale / (float)batch;
+    const float diag_on = positives_on_diagonal ? 1.0f : 0.0f;
     int launches = 0;
     if (d_grad_query) {
-        int rc = launch_ce_pass<true>(d_query, d_doc, d_y, d_lse, batch, dim, scale, coef, d_grad_query, st);
+        int rc = launch_ce_pass<true>(d_query, d_doc, d_y, d_lse, batch, dim, scale, coef, diag_on, d_grad_query, st);
         if (rc != RF_OK) return rc;
         ++launches;
     }
     if (d_grad_doc) {
-        int rc = launch_ce_pass<false>(d_doc, d_query, d_y, d_lse, batch, dim, scale, coef, d_grad_doc, st);
+        int rc = launch_ce_pass<false>(d_doc, d_query, d_y, d_lse, batch, dim, scale, coef, diag_on, d_grad_doc, st);
         if (rc != RF_OK) return rc;
         ++launches;
     }
     g_launches.fetch_add(launches);
     return RF_OK;
+}
+
+int rf_inbatch_softmax_ce_backward(const float *d_query, const float *d_doc, const float *d_y, const float *d_lse, int64_t batch,
+                                   int32_t dim, float scale, float upstream, float *d_grad_query, float *d_grad_doc,
+                                   void *stream) {
+    return rf_inbatch_softmax_ce_backward_block(d_query, d_doc, d_y, d_lse, batch, dim, scale, upstream, 1, d_grad_query, d_grad_doc,
+                                                stream);
 }
 
 }  // extern "C"

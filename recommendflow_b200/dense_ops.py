@@ -151,8 +151,11 @@ def sdpa_backward(q, k, v, mask, grad_out):
     return dq, dk, dv
 
 
-def inbatch_softmax_ce_backward(query, doc, y_true, lse, scale=20.0, upstream=1.0, need_query=True, need_doc=True):
-    """(d loss / d query, d loss / d doc) of batch_neg_sample_scaled_multi_class_ce_loss, from the forward's lse."""
+def inbatch_softmax_ce_backward(query, doc, y_true, lse, scale=20.0, upstream=1.0, need_query=True, need_doc=True,
+                                positives_on_diagonal=True):
+    """(d loss / d query, d loss / d doc) of batch_neg_sample_scaled_multi_class_ce_loss, from the forward's lse.
+    positives_on_diagonal=False: `doc` is a block of negatives only (another rank's docs in the data-parallel step)
+    and `lse` is the log-sum-exp over the whole row of the all-gathered logits."""
     q, d = _f32(query, "query"), _f32(doc, "doc")
     y, lse = _f32(y_true, "y_true").reshape(-1), _f32(lse, "lse").reshape(-1)
     B, D = q.shape
@@ -161,10 +164,10 @@ def inbatch_softmax_ce_backward(query, doc, y_true, lse, scale=20.0, upstream=1.
     gq = torch.empty_like(q) if need_query else None
     gd = torch.empty_like(d) if need_doc else None
     with torch.cuda.device(q.device):
-        nat.check(nat.lib().rf_inbatch_softmax_ce_backward(q.data_ptr(), d.data_ptr(), y.data_ptr(), lse.data_ptr(), B, D,
-                                                           float(scale), float(upstream),
-                                                           None if gq is None else gq.data_ptr(),
-                                                           None if gd is None else gd.data_ptr(), _stream(q.device)))
+        nat.check(nat.lib().rf_inbatch_softmax_ce_backward_block(q.data_ptr(), d.data_ptr(), y.data_ptr(), lse.data_ptr(), B, D,
+                                                                 float(scale), float(upstream), 1 if positives_on_diagonal else 0,
+                                                                 None if gq is None else gq.data_ptr(),
+                                                                 None if gd is None else gd.data_ptr(), _stream(q.device)))
     return gq, gd
 
 

@@ -106,3 +106,21 @@ def rank_batch(rank, B, max_len, seed=4242, alphabet=b"abcdefghijklmnopqrstuvwxy
     offs[1:] = np.cumsum(klen)
     arena = np.frombuffer(alphabet, dtype=np.uint8)[rng.integers(0, len(alphabet), size=int(offs[-1]))]
     return arena.copy(), offs, bag
+
+
+class TorchLossOps(object):
+    """CPU stand-ins for training_sharded.CudaLossOps (tests only): the [B, B] block primitives in plain torch."""
+
+    def block_lse(self, q, a, scale):
+        return torch.logsumexp(scale * (q @ a.t()), dim=1)
+
+    def rowdot(self, q, a):
+        return (q * a).sum(dim=1)
+
+    def block_grads(self, q, a, y, lse, scale, upstream, own_block):
+        B = q.shape[0]
+        c = torch.exp(scale * (q @ a.t()) - lse[:, None])
+        if own_block:
+            c = c - torch.eye(B, dtype=q.dtype)
+        c = c * (upstream * scale / B) * y[:, None]
+        return c @ a, c.t() @ q

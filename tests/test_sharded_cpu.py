@@ -121,3 +121,106 @@ def test_two_rank_gloo_sharded_backward_adam(combiner):
         assert np.array_equal(w_r.view(np.uint32), full[rank::world].view(np.uint32)), rank
         assert np.array_equal(m_r.view(np.uint32), m[rank::world].view(np.uint32)), rank
         assert np.array_equal(v_r.view(np.uint32), v[rank::world].view(np.uint32)), rank
+
+
+# ---- C5: sharded tables + data-parallel towers + all-gathered in-batch softmax, under gloo -------------------------
+def _c5_setup(seed=5):
+    from recommendflow_b200.backend.blocks.mlp import create_mlp
+    torch.manual_seed(seed)
+    user_tower = create_mlp([16, 8], 0.0, "selu", None, name="user_tower")
+    ad_tower = create_mlp([16, 8], 0.0, "selu", None, name="ad_tower")
+    x = torch.zeros(2, 8)
+    user_tower(x), ad_tower(x)                     # builds the (seeded) dense variables on the CPU
+    return user_tower, ad_tower
+
+
+def _c5_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from recommendflow_b200.training_sharded import ShardedRecallTrainer
+        from tests.shard_util import TorchLossOps
+        N, D, B = 211, 8, 24
+        full = {n: np.random.default_rng(i).uniform(-0.05, 0.05, size=(N, D)).astype(np.float32) for i, n in enumerate(("u", "a"))}
+        bags = {}
+        for n in ("u", "a"):
+            bags[n] = ShardedEmbeddingBag(N, D, combiner="avg", salt=None, mask_value="", transport="nccl", max_batch=B,
+                                          max_keys=B * 6, device="cpu", ops=OracleShardOps())
+            bags[n].set_full_weights(full[n])
+        user_tower, ad_tower = _c5_setup()
+        trainer = ShardedRecallTrainer({"u": bags["u"]}, {"a": bags["a"]}, user_tower, ad_tower, learning_rate=1e-2,
+                                       loss_ops=TorchLossOps())
+        losses = []
+        for step in (1, 2, 3):
+            batch = {}
+            for i, n in enumerate(("u", "a")):
+                arena, offs, bag = rank_batch(rank, B, 6, seed=100 * step + 7 * i)
+                batch[n] = StringColumn.from_arena(arena, offs, (B, None), bag)
+            losses.append(float(trainer.train_step(batch, np.ones(B, np.float32))))
+        dense = [p.detach().numpy().copy() for p in trainer.dense_opt.params]
+        q.put((rank, losses, dense, {n: b.shard.detach().numpy().copy() for n, b in bags.items()}))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_c5_train_step_matches_single_process():
+    """3 steps of the C5 trainer on 2 ranks == 3 steps of ONE process holding the full tables and the global batch
+    (same towers, Keras Adam everywhere, in-batch softmax over all 2B docs): losses, dense variables and table shards
+    agree to fp32 re-association (the sharded forward sums partial pools per owner, gradients are all-reduced)."""
+    world, N, D, B = 2, 211, 8, 24
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_c5_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {r: (l, d, s) for r, l, d, s in (q.get(timeout=180) for _ in procs)}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # ---- single process: full tables, global batch, torch autograd + the oracle's sparse Keras Adam ----
+    from recommendflow_b200.training import KerasAdam
+    full = {n: np.random.default_rng(i).uniform(-0.05, 0.05, size=(N, D)).astype(np.float32) for i, n in enumerate(("u", "a"))}
+    mom = {n: (np.zeros_like(full[n]), np.zeros_like(full[n])) for n in full}
+    user_tower, ad_tower = _c5_setup()
+    params = []
+    for t in (user_tower, ad_tower):
+        for p in t.parameters():
+            p.requires_grad_(True)
+            params.append(p)
+    opt = KerasAdam(params, learning_rate=1e-2)
+    want_losses = []
+    for step in (1, 2, 3):
+        leaves, ids_all, bag_all = {}, {}, {}
+        for i, n in enumerate(("u", "a")):
+            pooled, ids_l, offs_l = [], [], [0]
+            for rank in range(world):
+                arena, offs, bag = rank_batch(rank, B, 6, seed=100 * step + 7 * i)
+                ids = oracle.hash_strings(arena, offs, N, "", None)
+                pooled.append(sharded_reference(ids, bag, full[n], world, "avg"))
+                ids_l.append(ids)
+                offs_l += (bag[1:].astype(np.int64) + offs_l[-1]).tolist()
+            leaves[n] = torch.from_numpy(np.concatenate(pooled)).requires_grad_(True)
+            ids_all[n], bag_all[n] = np.concatenate(ids_l), np.asarray(offs_l, dtype=np.int32)
+        u = torch.nn.functional.normalize(user_tower(leaves["u"]), dim=1, eps=1e-12)
+        a = torch.nn.functional.normalize(ad_tower(leaves["a"]), dim=1, eps=1e-12)
+        s = 20.0 * (u @ a.t())
+        loss = torch.mean(-(torch.diagonal(s) - torch.logsumexp(s, dim=1)))
+        opt.zero_grad()
+        loss.backward()
+        want_losses.append(float(loss))
+        opt.step()
+        for n in ("u", "a"):
+            cnt = np.maximum(np.diff(bag_all[n]), 1).astype(np.float32)[:, None]
+            oracle.bag_backward_adam(ids_all[n], leaves[n].grad.numpy() / cnt, full[n], mom[n][0], mom[n][1], step, lr=1e-2,
+                                     combiner="sum", bag_offsets=bag_all[n])
+    for rank in range(world):
+        losses, dense, shards = res[rank]
+        np.testing.assert_allclose(losses, want_losses, rtol=2e-5, atol=1e-6)
+        for got, p in zip(dense, params):
+            np.testing.assert_allclose(got, p.detach().numpy(), rtol=1e-4, atol=2e-6)
+        for n in ("u", "a"):
+            # Adam normalises the gradient (m / (sqrt(v) + eps)): where a row's gradient is ~1e-8, fp32 re-association of
+            # the gradient moves the update by a visible fraction of the step (lr = 1e-2): allow 0.5 % of one full step
+            np.testing.assert_allclose(shards[n], full[n][rank::world], rtol=1e-4, atol=5e-5)
+    assert want_losses[-1] < want_losses[0]

@@ -173,3 +173,107 @@ def test_sharded_backward_adam_multi_gpu():
     for rank in range(world):
         for got, want in zip(res[rank], (full, m, v)):
             assert np.array_equal(got.view(np.uint32), want[rank::world].view(np.uint32)), rank
+
+
+# ---- C5: sharded tables + data-parallel towers + all-gathered in-batch softmax on 2 GPUs ------------------------------
+def _c5_gpu_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import recommendflow_b200.dense_ops as dense_ops
+        from recommendflow_b200.backend.blocks.mlp import create_mlp
+        from recommendflow_b200.sharded import ShardedEmbeddingBag
+        from recommendflow_b200.strings import StringColumn
+        from recommendflow_b200.training_sharded import ShardedRecallTrainer
+        dense_ops.DEFAULT_PRECISION = "fp32"              # exact-fp32 loss kernels: the comparison below is tight
+        N, D, B = 2003, 16, 256
+        full = {n: np.random.default_rng(i).uniform(-0.05, 0.05, size=(N, D)).astype(np.float32) for i, n in enumerate(("u", "a"))}
+        bags = {}
+        for n in ("u", "a"):
+            bags[n] = ShardedEmbeddingBag(N, D, combiner="avg", salt=None, mask_value="", transport="nccl", max_batch=B, max_keys=B * 8)
+            bags[n].set_full_weights(full[n])
+        torch.manual_seed(5)
+        towers = [create_mlp([32, 16], 0.0, "selu", None, name=t) for t in ("user_tower", "ad_tower")]
+        x = torch.zeros(2, D)
+        for t in towers:
+            t(x)                                          # seeded CPU init, identical on every rank ...
+            t.to(dev)                                     # ... then moved
+        trainer = ShardedRecallTrainer({"u": bags["u"]}, {"a": bags["a"]}, towers[0], towers[1], learning_rate=1e-2)
+        losses = []
+        for step in (1, 2, 3):
+            batch = {}
+            for i, n in enumerate(("u", "a")):
+                arena, offs, bag = rank_batch(rank, B, 8, seed=100 * step + 7 * i)
+                batch[n] = StringColumn.from_arena(arena, offs, (B, None), bag).to(dev)
+            losses.append(float(trainer.train_step(batch, torch.ones(B, device=dev))))
+        torch.cuda.synchronize()
+        q.put((rank, losses, [p.detach().cpu().numpy() for p in trainer.dense_opt.params],
+               {n: b.shard.detach().cpu().numpy() for n, b in bags.items()}))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_c5_train_step_multi_gpu_matches_single_process():
+    """tests/test_sharded_cpu.py::test_two_rank_gloo_c5_train_step_matches_single_process on the CUDA kernels and NCCL:
+    3 steps on 2 GPUs vs ONE CPU process with the full tables and the global batch."""
+    from recommendflow_b200.backend.blocks.mlp import create_mlp
+    from recommendflow_b200.training import KerasAdam
+    world, N, D, B = 2, 2003, 16, 256
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_c5_gpu_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {r: (l, d, s) for r, l, d, s in (q.get(timeout=300) for _ in procs)}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = {n: np.random.default_rng(i).uniform(-0.05, 0.05, size=(N, D)).astype(np.float32) for i, n in enumerate(("u", "a"))}
+    mom = {n: (np.zeros_like(full[n]), np.zeros_like(full[n])) for n in full}
+    torch.manual_seed(5)
+    towers = [create_mlp([32, 16], 0.0, "selu", None, name=t) for t in ("user_tower", "ad_tower")]
+    x = torch.zeros(2, D)
+    params = []
+    for t in towers:
+        t(x)
+        for p in t.parameters():
+            p.requires_grad_(True)
+            params.append(p)
+    opt = KerasAdam(params, learning_rate=1e-2)
+    want_losses = []
+    for step in (1, 2, 3):
+        leaves, ids_all, bag_all = {}, {}, {}
+        for i, n in enumerate(("u", "a")):
+            pooled, ids_l, offs_l = [], [], [0]
+            for rank in range(world):
+                arena, offs, bag = rank_batch(rank, B, 8, seed=100 * step + 7 * i)
+                ids = oracle.hash_strings(arena, offs, N, "", None)
+                pooled.append(sharded_reference(ids, bag, full[n], world, "avg"))
+                ids_l.append(ids)
+                offs_l += (bag[1:].astype(np.int64) + offs_l[-1]).tolist()
+            leaves[n] = torch.from_numpy(np.concatenate(pooled)).requires_grad_(True)
+            ids_all[n], bag_all[n] = np.concatenate(ids_l), np.asarray(offs_l, dtype=np.int32)
+        u = torch.nn.functional.normalize(towers[0](leaves["u"]), dim=1, eps=1e-12)
+        a = torch.nn.functional.normalize(towers[1](leaves["a"]), dim=1, eps=1e-12)
+        s = 20.0 * (u @ a.t())
+        loss = torch.mean(-(torch.diagonal(s) - torch.logsumexp(s, dim=1)))
+        opt.zero_grad()
+        loss.backward()
+        want_losses.append(float(loss.detach()))
+        opt.step()
+        for n in ("u", "a"):
+            cnt = np.maximum(np.diff(bag_all[n]), 1).astype(np.float32)[:, None]
+            oracle.bag_backward_adam(ids_all[n], leaves[n].grad.numpy() / cnt, full[n], mom[n][0], mom[n][1], step, lr=1e-2,
+                                     combiner="sum", bag_offsets=bag_all[n])
+    for rank in range(world):
+        losses, dense, shards = res[rank]
+        np.testing.assert_allclose(losses, want_losses, rtol=1e-4, atol=1e-5)
+        # Adam normalises gradients: tiny-gradient elements move by a visible fraction of a step under fp32 reordering
+        for got, p in zip(dense, params):
+            np.testing.assert_allclose(got, p.detach().numpy(), rtol=2e-3, atol=2e-4)
+        for n in ("u", "a"):
+            np.testing.assert_allclose(shards[n], full[n][rank::world], rtol=2e-3, atol=2e-4)
+    assert want_losses[-1] < want_losses[0]

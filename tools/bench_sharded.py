@@ -48,6 +48,7 @@ def parse(argv=None):
     ap.add_argument("--nccl", action="store_true", help="also time the all_to_all (NCCL) transport baseline")
     ap.add_argument("--no-n1", action="store_true", help="skip the same-box single-GPU measurement on rank 0")
     ap.add_argument("--quick", action="store_true", help="string keys at the first batch size only")
+    ap.add_argument("--no-train", action="store_true", help="skip the C5 training-step measurement (N > 1)")
     return ap.parse_args(argv)
 
 
@@ -91,6 +92,62 @@ def check(got, ids, bag, world, dim, ordered, max_len):
         return ok, 0.0 if ok else float(np.abs(g - want).max())
     err = float(np.abs(g.astype(np.float64) - want).max())
     return err <= max_len * 0.05 * 2.0 ** -21, err
+
+
+def run_train_c5(world, rank, dev, barrier, steps=5):
+    """C5 (BASELINE.json configs[4]): full training step, 1 B table rows in total row-sharded over the ranks, dense
+    towers data-parallel, in-batch softmax over the global batch (recommendflow_b200/training_sharded.py).
+    4 features x 250 M rows x 16 dims (64 GB of tables + 128 GB of Adam moments over the box), Keras Adam on every row
+    (the reference's optimizer semantics), batch 8192 per GPU (the CUDA-core loss backward bounds the step today;
+    65 536 per GPU needs the tensor-core backward)."""
+    import torch
+    import torch.distributed as dist
+    from recommendflow_b200.backend.blocks.mlp import create_mlp
+    from recommendflow_b200.sharded import ShardedEmbeddingBag
+    from recommendflow_b200.strings import StringColumn
+    from recommendflow_b200.training_sharded import ShardedRecallTrainer
+    rows_total, n_feat, D, B, max_len = 1_000_000_000, 4, 16, 8192, 20
+    N = rows_total // n_feat
+    if N // world * D * 4 * 3 * n_feat > 150e9:
+        return {"skipped": f"1 B rows need more than {world} GPUs for tables + Adam moments"}
+    names = [f"user_{i}" for i in range(n_feat // 2)] + [f"ad_{i}" for i in range(n_feat // 2)]
+    bags = {n: ShardedEmbeddingBag(N, D, combiner="avg", salt=None, mask_value="", transport="nccl", max_batch=B, max_keys=B * max_len)
+            for n in names}
+    torch.manual_seed(11)
+    towers = [create_mlp([256, 128], 0.0, "selu", None, name=t) for t in ("user_tower", "ad_tower")]
+    x = torch.zeros(2, D * n_feat // 2)
+    for t in towers:
+        t(x)
+        t.to(dev)
+    trainer = ShardedRecallTrainer({n: bags[n] for n in names[:n_feat // 2]}, {n: bags[n] for n in names[n_feat // 2:]},
+                                   towers[0], towers[1], learning_rate=1e-3)
+    batches = []
+    for bi in range(2):
+        b = {}
+        for i, n in enumerate(names):
+            arena, offs, bag = jagged_keys(rank + 100 * i, B, max_len, bi)
+            b[n] = StringColumn.from_arena(arena, offs, (B, None), bag).to(dev)
+        batches.append(b)
+    y = torch.ones(B, device=dev)
+    losses = [float(trainer.train_step(batches[i % 2], y)) for i in range(2)]          # warm-up (builds optimizers)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        losses.append(float(trainer.train_step(batches[i % 2], y)))
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    del trainer, bags
+    torch.cuda.empty_cache()
+    return {"workload": f"c5: training step, {n_feat} features x {N} rows x {D} dims = {rows_total} table rows row-sharded id % {world} "
+                        f"(Keras Adam on every row), towers [256, 128] data-parallel, in-batch softmax over the global batch "
+                        f"{world} x {B}, jagged 1..{max_len} keys/bag",
+            "ms_per_step": ms, "samples_per_s": world * B / (ms / 1e3), "steps": steps, "losses": [round(v, 5) for v in losses],
+            "loss_fell": losses[-1] < losses[0]}
 
 
 def run(args, world, rank, dev):
@@ -271,6 +328,13 @@ def run(args, world, rank, dev):
                 results[f"nccl/B{B}/string"] = timed(lambda i: layer(d["string"][i % NB], out=out))
                 del layer
 
+    train_c5 = None
+    if world > 1 and not args.no_train and not args.quick:
+        try:
+            train_c5 = run_train_c5(world, rank, dev, barrier)
+        except Exception as exc:                      # the forward measurement above must survive a training-side failure
+            train_c5 = {"error": f"{type(exc).__name__}: {exc}"}
+
     line = None
     bad = [k for k, v in parity.items() if not all(x for x in v.values() if isinstance(x, bool))]
     if rank == 0:
@@ -307,7 +371,7 @@ def run(args, world, rank, dev):
                             f"string keys (Fingerprint64 on the fly) and pre-hashed int64 ids",
                 "n_gpus": world, "value": head["samples_per_s"], "unit": "samples/s", "summary": summary,
                 "speedup_vs_n1": head.get("speedup_vs_n1"), "ms_per_step": results, "steps": K, "warmup": W,
-                "parity_check": parity, "parity_ok": not bad, "limiter": limiter,
+                "parity_check": parity, "parity_ok": not bad, "limiter": limiter, "train_c5": train_c5,
                 "gpu_launches": nat.launch_count() - launches0}
     if bad:
         if rank == 0:
