@@ -191,6 +191,15 @@ int rf_dense_forward_tc(const float *d_x, int64_t rows, int32_t in_dim, int64_t 
                         const float *d_bias, int32_t units, int activation, int l2_normalize, float *d_out,
                         int64_t ldo, void *stream);
 
+/* Same contract with bf16 operands (kind::f16, fp32 accumulate): the TF32 kernel is bound by L2 -> SM operand   */
+/* traffic; here a CTA keeps 256 query rows resident and streams 2-byte doc tiles (4x less traffic per flop).     */
+/* Operands are rounded to nearest bf16 into the workspace (rf_inbatch_workspace_bytes_tc is enough); the         */
+/* diagonal stays exact fp32.  dim % 8 == 0 and dim <= 256, else RF_ERR_UNSUPPORTED.                               */
+int rf_inbatch_rowstats_bf16(const float *d_query, const float *d_doc, const float *d_y, const float *d_col_weight,
+                             int64_t batch, int32_t dim, float scale, float margin, void *d_workspace,
+                             float *d_lse, float *d_diag, float *d_hinge, float *d_maxoff, float *d_loss,
+                             void *stream);
+
 /* ---- row-sharded tables (new design; the reference only replicates tables,   */
 /* backend/utils/gpu_utils.py:13-14).  Row id lives on rank id % world as local row id / world. */
 /* rf_shard_route partitions the hashed ids of one field by owner, keeping bag order: for every */

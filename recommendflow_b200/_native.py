@@ -108,6 +108,8 @@ def lib():
                                           C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p]
         L.rf_inbatch_rowstats_tc.argtypes = L.rf_inbatch_rowstats.argtypes
+        L.rf_inbatch_rowstats_bf16.argtypes = L.rf_inbatch_rowstats.argtypes
+        L.rf_inbatch_rowstats_bf16.restype = C.c_int
         L.rf_inbatch_workspace_bytes_tc.restype = C.c_int64
         L.rf_inbatch_workspace_bytes_tc.argtypes = [C.c_int64, C.c_int32]
         L.rf_shard_route.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,

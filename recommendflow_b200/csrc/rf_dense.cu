@@ -28,6 +28,8 @@ int launch_sdpa_tc(const float *q, const float *k, const float *v, const float *
 struct RowStat;
 int launch_logits_tc(const float *q, const float *d, const float *diag, const float *colw, int B, int Dt, float scale,
                      float margin, bool full_stats, RowStat *part, int max_splits, int *splits, cudaStream_t st);
+int launch_logits_bf16(const void *q16, const void *d16, const float *diag, const float *colw, int B, int Dt, float scale,
+                       float margin, bool full_stats, RowStat *part, int max_splits, int *splits, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------
 // In-batch row statistics.  For S = q d^T (q, d: [B, Dt] fp32 row-major), per row i:
@@ -153,6 +155,15 @@ __global__ void __launch_bounds__(256) round_tf32_kernel(const float *__restrict
         uint32_t r;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(in[i]));
         out[i] = __uint_as_float(r);
+    }
+}
+
+// fp32 -> bf16, round to nearest even (the bf16 tensor-core variant's operand copies)
+__global__ void __launch_bounds__(256) to_bf16_kernel(const float *__restrict__ in, unsigned short *__restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        unsigned short r;
+        asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(r) : "f"(in[i]));
+        out[i] = r;
     }
 }
 
@@ -380,6 +391,45 @@ int rf_inbatch_rowstats_tc(const float *d_query, const float *d_doc, const float
     int splits = 0;
     const bool full = d_hinge != nullptr || d_maxoff != nullptr;
     int rc = launch_logits_tc(q32, d32, diag, d_col_weight, B, dim, scale, margin, full, part, (int)max_splits, &splits, st);
+    if (rc != RF_OK) return rc;
+    rc = launch_finalize(part, splits, B, diag, d_y, scale, d_lse, d_hinge, d_maxoff, d_loss, fin_ws, st);
+    if (rc != RF_OK) return rc;
+    RF_CUDA(cudaGetLastError());
+    g_launches.fetch_add(4);
+    return RF_OK;
+}
+
+int rf_inbatch_rowstats_bf16(const float *d_query, const float *d_doc, const float *d_y, const float *d_col_weight, int64_t batch,
+                             int32_t dim, float scale, float margin, void *d_workspace, float *d_lse, float *d_diag,
+                             float *d_hinge, float *d_maxoff, float *d_loss, void *stream) {
+    if (batch < 0 || dim <= 0) return set_error(RF_ERR_INVALID, "bad in-batch shape");
+    if (batch == 0) return RF_OK;
+    if (batch > (1 << 24)) return set_error(RF_ERR_UNSUPPORTED, "batch too large");
+    if (dim % 8 != 0 || dim > 256) return set_error(RF_ERR_UNSUPPORTED, "bf16 tensor-core logits need dim %% 8 == 0 and dim <= 256");
+    if (!d_query || !d_doc || !d_workspace) return set_error(RF_ERR_INVALID, "rf_inbatch_rowstats_bf16: NULL buffer");
+    if (d_loss && !d_y) return set_error(RF_ERR_INVALID, "loss requested without y_true");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int B = (int)batch;
+    // same workspace layout as rf_inbatch_rowstats_tc; the operand copies are bf16 here (half the reserved space)
+    const int64_t row_tiles = (batch + kTM - 1) / kTM;
+    int64_t max_splits = (148 * 4 + row_tiles - 1) / row_tiles;
+    if (max_splits < 1) max_splits = 1;
+    if (max_splits > 64) max_splits = 64;
+    RowStat *part = static_cast<RowStat *>(d_workspace);
+    float *diag_ws = reinterpret_cast<float *>(part + (size_t)max_splits * B);
+    float *diag = d_diag ? d_diag : diag_ws;
+    void *fin_ws = reinterpret_cast<char *>(diag_ws) + (((size_t)B * sizeof(float) + 15) & ~(size_t)15);
+    uintptr_t p = (reinterpret_cast<uintptr_t>(fin_ws) + finalize_ws_bytes(B) + 255) & ~(uintptr_t)255;
+    unsigned short *q16 = reinterpret_cast<unsigned short *>(p);
+    unsigned short *d16 = q16 + (((size_t)B * dim + 127) & ~(size_t)127);
+    const int64_t n = (int64_t)B * dim;
+    const int rgrid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    to_bf16_kernel<<<rgrid, 256, 0, st>>>(d_query, q16, n);
+    to_bf16_kernel<<<rgrid, 256, 0, st>>>(d_doc, d16, n);
+    rowdot_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(d_query, d_doc, B, dim, diag);   // exact fp32 diagonal
+    int splits = 0;
+    const bool full = d_hinge != nullptr || d_maxoff != nullptr;
+    int rc = launch_logits_bf16(q16, d16, diag, d_col_weight, B, dim, scale, margin, full, part, (int)max_splits, &splits, st);
     if (rc != RF_OK) return rc;
     rc = launch_finalize(part, splits, B, diag, d_y, scale, d_lse, d_hinge, d_maxoff, d_loss, fin_ws, st);
     if (rc != RF_OK) return rc;

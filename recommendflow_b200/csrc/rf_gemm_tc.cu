@@ -12,8 +12,13 @@
 //   tile       128 x BN x 32 per stage (BN = 64 / 128 / 256 picked per shape), 4-6 stage TMA -> smem ring,
 //              4 x tcgen05.mma (K = 8) per stage, TWO 128-lane x BN-column TMEM accumulators so that the MMAs of
 //              tile i+1 run under the epilogue of tile i; persistent CTAs walk the tiles grid-stride
-//   warps      0: TMA producer   1: TMEM alloc + MMA issue   2-5: epilogue, thread = output row = TMEM lane:
-//              tcgen05.ld 32 columns, + bias, activation, (optional row l2-norm), then the warp's 32 x 32 block goes
+//   warps      0: TMA producer   1: TMEM alloc + MMA issue   2-9: epilogue, thread = output row = TMEM lane, EIGHT
+//              warps (two per scheduler: warps w and w + 4 own the same TMEM lanes and take alternate 32-column
+//              chunks) -- the first version had four and its profile (profiles/r2b_ncu_dense_tc_summary.csv) showed
+//              the kernel paced by their instruction issue (tensor pipe 9 % active): a branchy activation with a
+//              bias load per element cost ~55 dependent instructions per output on one warp per scheduler.
+//              tcgen05.ld 32 columns, + bias (one coalesced load per chunk, broadcast by shuffles), branch-free
+//              activation chosen once per chunk, (optional row l2-norm), then the warp's 32 x 32 block goes
 //              through a 128-byte-swizzled smem tile and leaves as ONE TMA store (UTMASTG): full 128-byte lines per
 //              row instead of 32 scattered 16-byte stores per instruction (first version: 0.2 ms for a 64 -> 64
 //              projection of 409 600 rows whose HBM floor is 32 us); TMA clips rows / columns past the edges
@@ -36,16 +41,17 @@ namespace gemm_tc {
 
 constexpr int kBM = 128, kBK = 32, kUmmaK = 8;
 constexpr int kABytes = kBM * kBK * 4;              // 16 KiB
-constexpr int kThreads = 192;
-constexpr int kOutStage = 4 * 2 * 4096;             // per epilogue warp: two 32-row x 128-byte staging tiles for the TMA store
+constexpr int kThreads = 64 + 256;
+constexpr int kEpiWarps = 8;
+constexpr int kOutStage = kEpiWarps * 2 * 4096;     // per epilogue warp: two 32-row x 128-byte staging tiles for the TMA store
 
 template <int BN>
 struct Cfg {
     static constexpr int kBBytes = BN * kBK * 4;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = BN == 256 ? 4 : 6;
+    static constexpr int kStages = BN == 256 ? 3 : (BN == 128 ? 4 : 6);     // ring + 64 KiB of store staging <= 227 KiB
     static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
-    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + kOutStage + 1024 + 256;
+    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + kOutStage + 2048 + 1024 + 256;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -116,14 +122,33 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t sr
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
-__device__ __forceinline__ float activate(float x, int act) {
+template <int ACT>
+__device__ __forceinline__ float activate(float x) {
+    if (ACT == RF_ACT_RELU) return fmaxf(x, 0.f);
+    if (ACT == RF_ACT_SELU) {          // scale * (x > 0 ? x : alpha * (e^x - 1)), both sides evaluated, no branch
+        const float neg = 1.7580993408473766f * (__expf(fminf(x, 0.f)) - 1.f);
+        return x > 0.f ? 1.0507009873554805f * x : neg;
+    }
+    if (ACT == RF_ACT_TANH) return tanhf(x);
+    if (ACT == RF_ACT_SIGMOID) return __fdividef(1.f, 1.f + __expf(-x));
+    if (ACT == RF_ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+    return x;
+}
+
+// v[j] = activation(v[j] + bias[col0 + j]) for the 32 columns of one chunk; `bias_lane` = bias[col0 + lane] (or 0)
+template <int ACT>
+__device__ __forceinline__ void bias_act_chunk(float (&v)[32], float bias_lane) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = activate<ACT>(v[j] + __shfl_sync(0xffffffffu, bias_lane, j));
+}
+__device__ __forceinline__ void bias_act(float (&v)[32], float bias_lane, int act) {
     switch (act) {
-        case RF_ACT_RELU: return fmaxf(x, 0.f);
-        case RF_ACT_SELU: return x > 0.f ? 1.0507009873554805f * x : 1.7580993408473766f * expm1f(x);   // scale * alpha
-        case RF_ACT_TANH: return tanhf(x);
-        case RF_ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
-        case RF_ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
-        default: return x;
+        case RF_ACT_RELU: bias_act_chunk<RF_ACT_RELU>(v, bias_lane); break;
+        case RF_ACT_SELU: bias_act_chunk<RF_ACT_SELU>(v, bias_lane); break;
+        case RF_ACT_TANH: bias_act_chunk<RF_ACT_TANH>(v, bias_lane); break;
+        case RF_ACT_SIGMOID: bias_act_chunk<RF_ACT_SIGMOID>(v, bias_lane); break;
+        case RF_ACT_GELU: bias_act_chunk<RF_ACT_GELU>(v, bias_lane); break;
+        default: bias_act_chunk<RF_ACT_NONE>(v, bias_lane); break;
     }
 }
 
@@ -149,7 +174,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int n_kb = (p.K + kBK - 1) / kBK;
     const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t out_stage = ring + kStages * kStageBytes;      // 1024-byte aligned (stage sizes are multiples of 1 KiB)
-    const uint32_t bars = out_stage + kOutStage;
+    const uint32_t xch_s = out_stage + kOutStage;                 // float2 [2][128]: l2-norm partial sums of the two column halves
+    const uint32_t bars = xch_s + 2048;
     const uint32_t full0 = bars, empty0 = bars + 8 * kStages;
     const uint32_t tmem_full0 = bars + 16 * kStages, tmem_empty0 = tmem_full0 + 16, tmem_slot = tmem_empty0 + 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -162,7 +188,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full0 + 8 * a, 1);
-            mbar_init(tmem_empty0 + 8 * a, 4);
+            mbar_init(tmem_empty0 + 8 * a, kEpiWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -223,9 +249,11 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
         }
     } else {
-        // ===== epilogue: thread <-> output row (TMEM lane); warp w may touch lanes 32 * (w % 4) .. + 31 =====
-        const int quarter = warp & 3;
+        // ===== epilogue: thread <-> output row (TMEM lane); warp w may touch lanes 32 * (w % 4) .. + 31; warps w and
+        // w + 4 share those lanes and take alternate 32-column chunks =====
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        float2 *xch = reinterpret_cast<float2 *>(smem_raw + (xch_s - smem_u32(smem_raw)));
         int local = 0;
         uint32_t n_store = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++local) {
@@ -237,34 +265,34 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if (p.l2norm) {                     // pass 1: ||activation(x W + b)||^2 of this row (one column tile holds the row)
                 float ss = 0.f;
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    if (n_tile * BN + c0 >= p.N) break;
+                for (int c0 = half * 32; c0 < BN; c0 += 64) {
+                    const int col0 = n_tile * BN + c0;
+                    if (col0 >= p.N) break;
                     float v[32];
                     tmem_ld32(lane_addr + acc * (uint32_t)BN + (uint32_t)c0, v);
+                    const float bl = (p.bias && col0 + lane < p.N) ? __ldg(p.bias + col0 + lane) : 0.f;
+                    bias_act(v, bl, p.act);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = n_tile * BN + c0 + j;
-                        if (col < p.N) {
-                            const float y = activate(v[j] + (p.bias ? __ldg(p.bias + col) : 0.f), p.act);
-                            ss = fmaf(y, y, ss);
-                        }
-                    }
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < p.N) ss = fmaf(v[j], v[j], ss);
                 }
+                // the row's other half lives in the partner warp (w +- 4): exchange the partial sums through smem
+                const int r = quarter * 32 + lane;
+                xch[half * 128 + r].x = ss;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                ss += xch[(half ^ 1) * 128 + r].x;
+                asm volatile("bar.sync 1, 256;" ::: "memory");                       // before the next tile overwrites xch
                 inv = 1.f / fmaxf(sqrtf(ss), p.l2_eps);
             }
             const int row0 = m_tile * kBM + quarter * 32;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = half * 32; c0 < BN; c0 += 64) {
                 const int col0 = n_tile * BN + c0;
                 if (col0 >= p.N) break;
                 float v[32];
                 tmem_ld32(lane_addr + acc * (uint32_t)BN + (uint32_t)c0, v);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int col = col0 + j;
-                    const float b = (p.bias && col < p.N) ? __ldg(p.bias + col) : 0.f;
-                    v[j] = activate(v[j] + b, p.act) * inv;
-                }
+                const float bl = (p.bias && col0 + lane < p.N) ? __ldg(p.bias + col0 + lane) : 0.f;
+                bias_act(v, bl, p.act);
                 // stage the warp's 32 rows x 32 columns (128 bytes per row, 16-byte chunks XOR-ed with row & 7 = the
                 // TMA 128-byte swizzle) and hand the tile to the TMA store engine
                 const uint32_t buf = out_stage + (uint32_t)(warp - 2) * 8192u + (uint32_t)(n_store & 1) * 4096u;
@@ -273,7 +301,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
                 for (int c = 0; c < 8; ++c)
                     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(buf + (uint32_t)lane * 128u + (uint32_t)((c ^ (lane & 7)) << 4)),
-                                 "f"(v[4 * c]), "f"(v[4 * c + 1]), "f"(v[4 * c + 2]), "f"(v[4 * c + 3])
+                                 "f"(v[4 * c] * inv), "f"(v[4 * c + 1] * inv), "f"(v[4 * c + 2] * inv), "f"(v[4 * c + 3] * inv)
                                  : "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();

@@ -10,7 +10,7 @@ from . import _native as nat
 # Ampere and later GPUs); "fp32": exact CUDA-core accumulation.  Shapes the tensor-core kernels do
 # not take use the fp32 kernels.
 DEFAULT_PRECISION = "tf32"
-TC_PRECISIONS = ("tf32",)          # operand formats the tensor-core kernels take
+TC_PRECISIONS = ("tf32", "bf16")   # operand formats the tensor-core kernels take (bf16: the in-batch logits only)
 
 
 def _f32(t, what):
@@ -99,8 +99,8 @@ def inbatch_rowstats(query, doc, y_true=None, col_weight=None, scale=20.0, margi
     """Row statistics of S = query . doc^T without materialising S.  Returns a dict with the
     requested [B] vectors among lse / diag / hinge / maxoff, plus "loss" when y_true is given."""
     precision = precision or DEFAULT_PRECISION
-    if precision not in ("tf32", "fp32"):
-        raise ValueError("precision must be 'tf32' or 'fp32'")
+    if precision not in ("tf32", "fp32", "bf16"):
+        raise ValueError("precision must be 'tf32', 'bf16' or 'fp32'")
     q, d = _f32(query, "query"), _f32(doc, "doc")
     if q.dim() != 2 or q.shape != d.shape:
         raise ValueError(f"query and doc must both be [B, D], got {tuple(q.shape)} and {tuple(d.shape)}")
@@ -110,13 +110,14 @@ def inbatch_rowstats(query, doc, y_true=None, col_weight=None, scale=20.0, margi
     cw = None if col_weight is None else _f32(col_weight, "col_weight").reshape(-1)
     if y is not None and y.numel() != B:
         raise ValueError("y_true must have one entry per row")
-    use_tc = precision == "tf32" and D % 4 == 0
+    use_bf16 = precision == "bf16" and D % 8 == 0 and D <= 256
+    use_tc = use_bf16 or (precision in ("tf32", "bf16") and D % 4 == 0)
     ws_bytes = nat.lib().rf_inbatch_workspace_bytes_tc(B, D) if use_tc else nat.lib().rf_inbatch_workspace_bytes(B)
     ws = torch.empty(max(1, ws_bytes), dtype=torch.uint8, device=dev)
     res = {k: torch.empty(B, dtype=torch.float32, device=dev) for k in want}
     loss = torch.zeros((), dtype=torch.float32, device=dev) if y is not None else None
     ptr = lambda t: None if t is None else t.data_ptr()
-    fn = nat.lib().rf_inbatch_rowstats_tc if use_tc else nat.lib().rf_inbatch_rowstats
+    fn = nat.lib().rf_inbatch_rowstats_bf16 if use_bf16 else (nat.lib().rf_inbatch_rowstats_tc if use_tc else nat.lib().rf_inbatch_rowstats)
     with torch.cuda.device(dev):
         nat.check(fn(q.data_ptr(), d.data_ptr(), ptr(y), ptr(cw), B, D, float(scale), float(margin),
                      ws.data_ptr(), ptr(res.get("lse")), ptr(res.get("diag")), ptr(res.get("hinge")),

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--d-model", type=int, default=64)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--skip-fp32", action="store_true")
+    ap.add_argument("--big", action="store_true", help="also time B = 65536")
     args = ap.parse_args()
     import torch
     from recommendflow_b200 import _native as nat
@@ -45,9 +46,18 @@ def main():
 
     out = {"workload": f"in-batch softmax loss, B={B}, Dt={D}, scale 20 (match_losses.py:150-165)"}
     flops = 2.0 * B * B * D
-    for prec in (["tf32"] if args.skip_fp32 else ["tf32", "fp32"]):
+    for prec in (["tf32", "bf16"] if args.skip_fp32 else ["tf32", "bf16", "fp32"]):
         ms, r = timed(lambda: inbatch_rowstats(q, d, y_true=y, precision=prec), args.steps)
         out[prec] = {"ms": ms, "tflops": flops / ms / 1e9, "loss": float(r["loss"])}
+    if args.big:
+        Bb = 65536
+        qb = torch.nn.functional.normalize(torch.randn(Bb, D, device="cuda"), dim=1)
+        db = torch.nn.functional.normalize(0.7 * qb + 0.7 * torch.randn(Bb, D, device="cuda"), dim=1)
+        yb = torch.ones(Bb, device="cuda")
+        for prec in ("tf32", "bf16"):
+            ms, r = timed(lambda: inbatch_rowstats(qb, db, y_true=yb, precision=prec), 5)
+            out[f"{prec}_B65536"] = {"ms": ms, "tflops": 2.0 * Bb * Bb * D / ms / 1e9, "loss": float(r["loss"])}
+        del qb, db
     S, dm = args.seq, args.d_model
     qq, kk, vv = (torch.randn(B, S, dm, device="cuda") for _ in range(3))
     mask = (torch.arange(S, device="cuda")[None, :, None] < torch.randint(1, S + 1, (B, 1, 1), device="cuda")).float()
@@ -56,6 +66,7 @@ def main():
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         out["tf32"]["frac_of_measured_bf16_peak"] = out["tf32"]["tflops"] / peaks["bf16_tflops"]
+        out["bf16"]["frac_of_measured_bf16_peak"] = out["bf16"]["tflops"] / peaks["bf16_tflops"]
     except Exception:
         pass
     out["gpu_launches"] = nat.launch_count()
