@@ -149,6 +149,11 @@ int rf_sdpa_forward(const float *d_q, const float *d_k, const float *d_v, const 
 int rf_sdpa_forward_tc(const float *d_q, const float *d_k, const float *d_v, const float *d_mask,
                        int64_t n_batch_heads, int32_t seq_len, int32_t head_dim, float *d_out, void *stream);
 
+/* Same, with q / k / v rows `row_pitch` floats apart (out stays contiguous): q, k, v may be column windows of ONE    */
+/* fused projection output [rows, 3 * head_dim] (MultiHeadAttention with a single Dense for the three projections). */
+int rf_sdpa_forward_tc_strided(const float *d_q, const float *d_k, const float *d_v, int64_t row_pitch, const float *d_mask,
+                               int64_t n_batch_heads, int32_t seq_len, int32_t head_dim, float *d_out, void *stream);
+
 /* ---- in-batch two-tower logits S = query . doc^T, reduced per row without ever storing S ------ */
 /* (backend/lossess/match_losses.py:119-226 all start from tf.matmul(query, tf.transpose(doc))).   */
 /* Per row i (any output pointer may be NULL):                                                     */

@@ -99,6 +99,9 @@ def lib():
         L.rf_sdpa_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                       C.c_void_p, C.c_void_p]
         L.rf_sdpa_forward_tc.argtypes = L.rf_sdpa_forward.argtypes
+        L.rf_sdpa_forward_tc_strided.restype = C.c_int
+        L.rf_sdpa_forward_tc_strided.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
+                                                 C.c_int32, C.c_void_p, C.c_void_p]
         L.rf_dense_forward_tc.restype = C.c_int
         L.rf_dense_forward_tc.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int,
                                           C.c_int, C.c_void_p, C.c_int64, C.c_void_p]

@@ -84,7 +84,26 @@ class MultiHeadAttention(Layer):
         self.wk = Dense(d_model, activation=None)
         self.wv = Dense(d_model, activation=None)
 
+    def _fused_qkv_weights(self):
+        """[3 * d_model, in] weight and [3 * d_model] bias of ONE Dense producing q | k | v side by side."""
+        key = tuple((d.kernel.data_ptr(), d.kernel._version, d.bias.data_ptr(), d.bias._version) for d in (self.wq, self.wk, self.wv))
+        if getattr(self, "_qkv_key", None) != key:
+            self._qkv_w = torch.cat([d.kernel.detach().t() for d in (self.wq, self.wk, self.wv)], dim=0).contiguous()
+            self._qkv_b = torch.cat([d.bias.detach() for d in (self.wq, self.wk, self.wv)]).contiguous()
+            self._qkv_key = key
+        return self._qkv_w, self._qkv_b
+
     def call(self, q, k, v, mask):
+        if (q is k and k is v and self.num_heads == 1 and dense_ops.DEFAULT_PRECISION == "tf32" and q.dim() == 3 and q.is_cuda
+                and dense_ops.sdpa_tc_shape_ok(q.shape[1], self.d_model) and q.shape[-1] % 4 == 0):
+            for d in (self.wq, self.wk, self.wv):
+                d.build(q.shape[-1], q.device)
+            if not any(d.recording_grad(q) for d in (self.wq, self.wk, self.wv)):
+                # self-attention, one head, inference: ONE tensor-core Dense for the three projections (x is read once),
+                # and the attention kernel reads q, k, v as column windows of its output
+                w, b = self._fused_qkv_weights()
+                qkv = dense_ops.dense_forward(q, w, b, None)
+                return dense_ops.sdpa_fused_qkv(qkv, mask, self.d_model)
         q, k, v = self.wq(q), self.wk(k), self.wv(v)                       # (B, S, d_model)
         seq_len, d_model = q.shape[1], q.shape[2]
         depth = d_model // self.num_heads

@@ -576,6 +576,19 @@ __device__ __forceinline__ void bag_forward_body(const DevField *__restrict__ fi
                                                       len, F.mask_words);
                             }
                         }
+                        if (staged && T == 2 && F.t[0].h.use_strong && F.t[1].h.use_strong) {
+                            // both SipHashes of the key in lockstep (twice the instruction-level parallelism)
+                            const WordSrcShared src{sm.stage, shift + (uint32_t)(o - byte0)};
+                            uint32_t ida, idb;
+                            bucket_of_x2(src, len, F.t[0].h, F.t[1].h, is_mask, ida, idb);
+                            sm.ids[sub0 + j] = ida;
+                            sm.ids[kChunk + sub0 + j] = idb;
+                            if (F.ids_out) {
+                                F.ids_out[key0 + j] = (int64_t)ida;
+                                F.ids_out[F.n_items + key0 + j] = (int64_t)idb;
+                            }
+                            continue;
+                        }
                         for (int t = 0; t < T; ++t) {
                             uint32_t id;
                             if (staged) {

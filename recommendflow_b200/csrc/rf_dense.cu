@@ -24,7 +24,7 @@ extern std::atomic<int64_t> g_launches;
 
 bool sdpa_tc_supported(int64_t n_seq, int S, int dh, const float *q, const float *k, const float *v, const float *out);
 int launch_sdpa_tc(const float *q, const float *k, const float *v, const float *mask, int64_t n_seq, int S, int dh, float *out,
-                   cudaStream_t st);
+                   cudaStream_t st, int64_t ld = 0);
 struct RowStat;
 int launch_logits_tc(const float *q, const float *d, const float *diag, const float *colw, int B, int Dt, float scale,
                      float margin, bool full_stats, RowStat *part, int max_splits, int *splits, cudaStream_t st);
@@ -343,6 +343,17 @@ int rf_sdpa_forward_tc(const float *d_q, const float *d_k, const float *d_v, con
     if (!sdpa_tc_supported(n_batch_heads, seq_len, head_dim, d_q, d_k, d_v, d_out))
         return set_error(RF_ERR_UNSUPPORTED, "tensor-core SDPA takes seq_len <= 64 and head_dim in {32, 64, 96}, 16-byte aligned");
     return launch_sdpa_tc(d_q, d_k, d_v, d_mask, n_batch_heads, seq_len, head_dim, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int rf_sdpa_forward_tc_strided(const float *d_q, const float *d_k, const float *d_v, int64_t row_pitch, const float *d_mask,
+                               int64_t n_batch_heads, int32_t seq_len, int32_t head_dim, float *d_out, void *stream) {
+    if (n_batch_heads < 0 || seq_len <= 0 || head_dim <= 0) return set_error(RF_ERR_INVALID, "bad SDPA shape");
+    if (row_pitch < head_dim || row_pitch % 4) return set_error(RF_ERR_INVALID, "row_pitch must be >= head_dim and a multiple of 4 floats");
+    if (n_batch_heads == 0) return RF_OK;
+    if (!d_q || !d_k || !d_v || !d_out) return set_error(RF_ERR_INVALID, "rf_sdpa_forward_tc_strided: NULL buffer");
+    if (!sdpa_tc_supported(n_batch_heads, seq_len, head_dim, d_q, d_k, d_v, d_out))
+        return set_error(RF_ERR_UNSUPPORTED, "tensor-core SDPA takes seq_len <= 64 and head_dim in {32, 64, 96}, 16-byte aligned");
+    return launch_sdpa_tc(d_q, d_k, d_v, d_mask, n_batch_heads, seq_len, head_dim, d_out, static_cast<cudaStream_t>(stream), row_pitch);
 }
 
 int64_t rf_inbatch_workspace_bytes(int64_t batch) {

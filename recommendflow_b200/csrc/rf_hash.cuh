@@ -302,6 +302,71 @@ __device__ __forceinline__ uint64_t siphash24(const Src &s, uint32_t n, uint64_t
     return v0 ^ v1 ^ v2 ^ v3;
 }
 
+// Two SipHash-2-4 of the SAME message under two keys, in lockstep: DoubleHashingEmbedding hashes every key twice
+// (seeds[0], seeds[1]); one SipHash is a single dependent chain of 64-bit add / rotate / xor, so interleaving the two
+// states doubles the instruction-level parallelism (C3: 228 features x 2 SipHash tables, D = 8 -- that launch is bound
+// by hash issue latency, not by HBM).  Same arithmetic as siphash24, message words fetched once.
+#define RF_SIPROUND2()                                                 \
+    do {                                                               \
+        a0 += a1; b0 += b1;                                            \
+        a1 = rotl64(a1, 13); b1 = rotl64(b1, 13);                      \
+        a1 ^= a0; b1 ^= b0;                                            \
+        a0 = rotl64(a0, 32); b0 = rotl64(b0, 32);                      \
+        a2 += a3; b2 += b3;                                            \
+        a3 = rotl64(a3, 16); b3 = rotl64(b3, 16);                      \
+        a3 ^= a2; b3 ^= b2;                                            \
+        a0 += a3; b0 += b3;                                            \
+        a3 = rotl64(a3, 21); b3 = rotl64(b3, 21);                      \
+        a3 ^= a0; b3 ^= b0;                                            \
+        a2 += a1; b2 += b1;                                            \
+        a1 = rotl64(a1, 17); b1 = rotl64(b1, 17);                      \
+        a1 ^= a2; b1 ^= b2;                                            \
+        a2 = rotl64(a2, 32); b2 = rotl64(b2, 32);                      \
+    } while (0)
+
+template <class Src>
+__device__ __forceinline__ void siphash24_x2(const Src &s, uint32_t n, uint64_t ka0, uint64_t ka1, uint64_t kb0, uint64_t kb1,
+                                             uint64_t &ha, uint64_t &hb) {
+    uint64_t a0 = ka0 ^ 0x736f6d6570736575ULL, a1 = ka1 ^ 0x646f72616e646f6dULL;
+    uint64_t a2 = ka0 ^ 0x6c7967656e657261ULL, a3 = ka1 ^ 0x7465646279746573ULL;
+    uint64_t b0 = kb0 ^ 0x736f6d6570736575ULL, b1 = kb1 ^ 0x646f72616e646f6dULL;
+    uint64_t b2 = kb0 ^ 0x6c7967656e657261ULL, b3 = kb1 ^ 0x7465646279746573ULL;
+    const uint32_t full = n & ~7u;
+    for (uint32_t p = 0; p < full; p += 8) {
+        const uint64_t m = fetch64(s, p);
+        a3 ^= m; b3 ^= m;
+        RF_SIPROUND2();
+        RF_SIPROUND2();
+        a0 ^= m; b0 ^= m;
+    }
+    const uint32_t rem = n & 7u;
+    uint64_t m = (uint64_t)(n & 0xffu) << 56;
+    if (rem) m |= fetch64(s, full) & ((1ULL << (rem * 8)) - 1ULL);
+    a3 ^= m; b3 ^= m;
+    RF_SIPROUND2();
+    RF_SIPROUND2();
+    a0 ^= m; b0 ^= m;
+    a2 ^= 0xff; b2 ^= 0xff;
+    RF_SIPROUND2();
+    RF_SIPROUND2();
+    RF_SIPROUND2();
+    RF_SIPROUND2();
+    ha = a0 ^ a1 ^ a2 ^ a3;
+    hb = b0 ^ b1 ^ b2 ^ b3;
+}
+
+// Keras Hashing._hash_values_to_bins for one key under two strong hashes at once
+template <class Src>
+__device__ __forceinline__ void bucket_of_x2(const Src &src, uint32_t len, const HashSpec &ha, const HashSpec &hb, bool is_mask,
+                                             uint32_t &ida, uint32_t &idb) {
+    uint64_t xa, xb;
+    siphash24_x2(src, len, ha.k0, ha.k1, hb.k0, hb.k1, xa, xb);
+    ida = (uint32_t)fastmod(xa, ha.mod);
+    idb = (uint32_t)fastmod(xb, hb.mod);
+    if (ha.masking) ida = is_mask ? 0u : ida + 1u;
+    if (hb.masking) idb = is_mask ? 0u : idb + 1u;
+}
+
 // Keras Hashing._hash_values_to_bins for one key
 template <class Src>
 __device__ __forceinline__ uint32_t bucket_of(const Src &src, uint32_t len, const HashSpec &h, bool is_mask) {

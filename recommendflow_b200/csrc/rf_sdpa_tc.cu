@@ -517,7 +517,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int64_t cols, CUtensorMapSwizzle swizzle) {
+static int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int64_t cols, int64_t ld, CUtensorMapSwizzle swizzle) {
     static EncodeTiledFn fn = [] {
         void *f = nullptr;
         cudaDriverEntryPointQueryResult q;
@@ -526,7 +526,7 @@ static int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int64_t co
     }();
     if (!fn) return set_error(RF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
     const cuuint32_t box[2] = {(cuuint32_t)kKB, (cuuint32_t)kSeqPad};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
@@ -546,13 +546,14 @@ bool sdpa_tc_supported(int64_t n_seq, int S, int dh, const float *q, const float
 }
 
 int launch_sdpa_tc(const float *q, const float *k, const float *v, const float *mask, int64_t n_seq, int S, int dh, float *out,
-                   cudaStream_t st) {
+                   cudaStream_t st, int64_t ld) {
     using namespace sdpa_tc;
     CUtensorMap mq, mk, mv;
     int rc;
-    if ((rc = make_map(&mq, q, n_seq * S, dh, CU_TENSOR_MAP_SWIZZLE_128B)) != RF_OK) return rc;
-    if ((rc = make_map(&mk, k, n_seq * S, dh, CU_TENSOR_MAP_SWIZZLE_128B)) != RF_OK) return rc;
-    if ((rc = make_map(&mv, v, n_seq * S, dh, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != RF_OK) return rc;   // MN-major TF32 operand
+    if (ld <= 0) ld = dh;                      // rows of q / k / v are `ld` floats apart (contiguous by default)
+    if ((rc = make_map(&mq, q, n_seq * S, dh, ld, CU_TENSOR_MAP_SWIZZLE_128B)) != RF_OK) return rc;
+    if ((rc = make_map(&mk, k, n_seq * S, dh, ld, CU_TENSOR_MAP_SWIZZLE_128B)) != RF_OK) return rc;
+    if ((rc = make_map(&mv, v, n_seq * S, dh, ld, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != RF_OK) return rc;   // MN-major TF32 operand
     const int n_db = dh / kKB;
     int dev = 0, sms = 0;
     RF_CUDA(cudaGetDevice(&dev));

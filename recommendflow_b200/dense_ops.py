@@ -11,6 +11,10 @@ from . import _native as nat
 # not take use the fp32 kernels.
 DEFAULT_PRECISION = "tf32"
 TC_PRECISIONS = ("tf32", "bf16")   # operand formats the tensor-core kernels take (bf16: the in-batch logits only)
+# The B x B in-batch logits default to bf16 operands in tensor-core mode: the TF32 kernel is bound by operand traffic
+# (232 TFLOP/s at B = 8192, 319 at 65536), the bf16 kernel reaches 508 / 1121 TFLOP/s; the diagonal (the positives)
+# stays an exact fp32 dot product and the tolerance is stated in tests/test_dense_gpu.py.  "tf32" / "fp32" on request.
+DEFAULT_LOSS_PRECISION = "bf16"
 
 
 def _f32(t, what):
@@ -94,11 +98,34 @@ def sdpa(q, k, v, mask=None, precision=None):
     return out
 
 
+def sdpa_fused_qkv(qkv, mask, dh):
+    """scaled_dot_product_attention on q, k, v that sit side by side in ONE [..., S, 3 * dh] projection output
+    (rf_sdpa_forward_tc_strided: the TMA descriptors carry the row pitch; nothing is copied)."""
+    qkv = _f32(qkv, "qkv")
+    S = qkv.shape[-2]
+    if qkv.shape[-1] != 3 * dh or not sdpa_tc_shape_ok(S, dh):
+        raise ValueError("sdpa_fused_qkv takes [..., S, 3 * dh] with S <= 64 and dh in (32, 64, 96)")
+    nb = qkv.numel() // (S * 3 * dh)
+    flat = qkv.view(-1, 3 * dh)
+    m = None
+    if mask is not None:
+        m = _f32(mask, "mask")
+        if m.dim() == qkv.dim() and m.shape[-1] == 1:
+            m = m[..., 0]
+        m = m.expand(qkv.shape[:-1]).contiguous()
+    out = torch.empty(*qkv.shape[:-1], dh, dtype=torch.float32, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        nat.check(nat.lib().rf_sdpa_forward_tc_strided(flat.data_ptr(), flat.data_ptr() + 4 * dh, flat.data_ptr() + 8 * dh, 3 * dh,
+                                                       None if m is None else m.data_ptr(), nb, S, dh, out.data_ptr(),
+                                                       _stream(qkv.device)))
+    return out
+
+
 def inbatch_rowstats(query, doc, y_true=None, col_weight=None, scale=20.0, margin=0.0, want=("lse", "diag"),
                      precision=None):
     """Row statistics of S = query . doc^T without materialising S.  Returns a dict with the
     requested [B] vectors among lse / diag / hinge / maxoff, plus "loss" when y_true is given."""
-    precision = precision or DEFAULT_PRECISION
+    precision = precision or (DEFAULT_LOSS_PRECISION if DEFAULT_PRECISION == "tf32" else DEFAULT_PRECISION)
     if precision not in ("tf32", "fp32", "bf16"):
         raise ValueError("precision must be 'tf32', 'bf16' or 'fp32'")
     q, d = _f32(query, "query"), _f32(doc, "doc")

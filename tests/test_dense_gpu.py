@@ -92,7 +92,8 @@ TOL = {"fp32": 1e-4, "tf32": 2e-2, "bf16": 8e-2}
 @pytest.mark.parametrize("B,D", [(1000, 256), (64, 16), (777, 100), (129, 8), (4096, 256), (300, 36), (8192, 64), (255, 128), (257, 24)])
 def test_scaled_inbatch_softmax_loss_matches_oracle(B, D, precision, monkeypatch):
     import recommendflow_b200.dense_ops as dense_ops
-    monkeypatch.setattr(dense_ops, "DEFAULT_PRECISION", precision)
+    monkeypatch.setattr(dense_ops, "DEFAULT_PRECISION", "tf32" if precision == "bf16" else precision)
+    monkeypatch.setattr(dense_ops, "DEFAULT_LOSS_PRECISION", precision)
     rng = np.random.default_rng(B + D)
     q, d, y = _pairs(rng, B, D)
     want, lse, diag = oracle.inbatch_softmax_ce(y, q, d, 20.0)
@@ -115,7 +116,8 @@ def test_scaled_inbatch_softmax_loss_matches_oracle(B, D, precision, monkeypatch
 @pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
 def test_margin_rank_losses_match_numpy(precision, monkeypatch):
     import recommendflow_b200.dense_ops as dense_ops
-    monkeypatch.setattr(dense_ops, "DEFAULT_PRECISION", precision)
+    monkeypatch.setattr(dense_ops, "DEFAULT_PRECISION", "tf32" if precision == "bf16" else precision)
+    monkeypatch.setattr(dense_ops, "DEFAULT_LOSS_PRECISION", precision)
     rng = np.random.default_rng(21)
     B, D = 513, 64
     q, d, y = _pairs(rng, B, D)
@@ -423,3 +425,27 @@ def test_tower_mlp_fused_matches_layerwise_float64():
         mlp.layers[1].dense.bias.add_(1.0)
     got2 = mlp(xt, l2_normalize=True)
     assert not torch.allclose(got, got2)
+
+
+def test_multi_head_attention_fused_qkv_path_matches_oracle():
+    """Self-attention with one head at inference: one tcgen05 Dense produces q | k | v side by side and the tcgen05 SDPA
+    kernel reads them as column windows (row pitch in the TMA descriptors).  vs the float64/fp32 oracle, TF32 tolerance."""
+    from recommendflow_b200 import _native as nat
+    rng = np.random.default_rng(31)
+    B, S, d = 37, 50, 64
+    x = rng.standard_normal((B, S, d)).astype(np.float32)
+    lens = rng.integers(1, S + 1, size=B)
+    mask = (np.arange(S)[None, :] < lens[:, None]).astype(np.float32)
+    layer = MultiHeadAttention(d, 1)
+    ws = []
+    for dense in (layer.wq, layer.wk, layer.wv):
+        w = (rng.standard_normal((d, d)) * 0.15).astype(np.float32)
+        b = (rng.standard_normal(d) * 0.1).astype(np.float32)
+        dense.set_weights([w, b])
+        ws.append((w, b))
+    xt = torch.from_numpy(x).cuda()
+    before = nat.launch_count()
+    got = layer(xt, xt, xt, torch.from_numpy(mask[:, :, None]).cuda())
+    assert nat.launch_count() == before + 2, "one Dense launch + one SDPA launch"
+    want = oracle.multi_head_attention(x, mask, *ws, 1)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=2e-2, atol=2e-2)

@@ -61,8 +61,10 @@ def main():
     S, dm = args.seq, args.d_model
     qq, kk, vv = (torch.randn(B, S, dm, device="cuda") for _ in range(3))
     mask = (torch.arange(S, device="cuda")[None, :, None] < torch.randint(1, S + 1, (B, 1, 1), device="cuda")).float()
-    ms, _ = timed(lambda: sdpa(qq, kk, vv, mask), args.steps)
-    out["sdpa"] = {"shape": [B, S, dm], "ms": ms, "gflop": 4.0 * B * S * S * dm / 1e9, "hbm_gbs": 4 * B * S * dm * 4 / ms / 1e6}
+    runs = [timed(lambda: sdpa(qq, kk, vv, mask), args.steps)[0] for _ in range(5)]      # five back-to-back measurements
+    ms = min(runs)
+    out["sdpa"] = {"shape": [B, S, dm], "ms": ms, "runs_ms": [round(r, 4) for r in runs], "gflop": 4.0 * B * S * S * dm / 1e9,
+                   "hbm_gbs": 4 * B * S * dm * 4 / ms / 1e6}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         out["tf32"]["frac_of_measured_bf16_peak"] = out["tf32"]["tflops"] / peaks["bf16_tflops"]
