@@ -52,18 +52,22 @@ class PreprocessLayers(dict):
         return layout, col
 
     # ---- launch-plan cache (see forward_all) ---------------------------------------------------------------------
-    def _store_plan(self, key, plan, fused, keys, out):
+    def _store_plan(self, key, plan, fused, keys, out, keep_ids=None):
         cache = self.__dict__.setdefault("_plans", {})
         if len(cache) >= 8:
             cache.pop(next(iter(cache)))
         sig = [(keys[n].data.data_ptr(), keys[n].offsets.data_ptr(), keys[n].shape, keys[n].bag_offsets is None) for n in fused]
         cache[key] = {"plan": plan, "sig": sig, "out": (out.data_ptr(), out.stride(0)), "epoch": _pl.TABLE_EPOCH[0],
-                      "device": out.device}
+                      "device": out.device, "ids": None if keep_ids is None else dict(keep_ids)}
 
-    def _launch_cached(self, key, fused, keys, layout, out, B):
+    def _launch_cached(self, key, fused, keys, layout, out, B, keep_ids=None):
         ent = self.__dict__.get("_plans", {}).get(key)
         if ent is None or ent["epoch"] != _pl.TABLE_EPOCH[0] or ent["device"] != out.device:
             return False
+        if keep_ids is not None:
+            if ent["ids"] is None:
+                return False
+            keep_ids.update(ent["ids"])                 # the plan's own id buffers: this launch overwrites them in place
         plan, sig = ent["plan"], ent["sig"]
         out_ptr, out_stride = out.data_ptr(), out.stride(0)
         out_moved = (out_ptr, out_stride) != ent["out"]
@@ -174,8 +178,10 @@ class PreprocessLayers(dict):
             # per call (228 features: ~9 ms against a 0.17 ms kernel).  When the same features arrive with the same
             # shapes -- every step of a loop -- the descriptors of the previous call are re-used; only pointers that
             # moved (a freshly copied key arena, another output buffer) are patched in place.
-            cache_key = (tuple(fused), B, tuple(layout[n] for n in fused)) if (keep_ids is None and len(hashed) == len(fused)) else None
-            if cache_key is not None and self._launch_cached(cache_key, fused, keys, layout, out, B):
+            # (with keep_ids the cached plan also owns the ids_out buffers: the ids of step i live in the same memory as
+            # those of step i-1, which is what lets the optimizer keep ITS descriptors too)
+            cache_key = (tuple(fused), B, tuple(layout[n] for n in fused), keep_ids is not None) if len(hashed) == len(fused) else None
+            if cache_key is not None and self._launch_cached(cache_key, fused, keys, layout, out, B, keep_ids):
                 for n in fused:
                     col, width = layout[n]
                     result[n] = out[:, col:col + width]
@@ -215,8 +221,8 @@ class PreprocessLayers(dict):
                 plan = BagPlan(calls, B)
                 plan.launch()
                 if cache_key is not None and len(calls) == len(fused):
-                    self._store_plan(cache_key, plan, fused, keys, out)
-                    if packed is not None and len(fused) == len(names):
+                    self._store_plan(cache_key, plan, fused, keys, out, keep_ids)
+                    if packed is not None and len(fused) == len(names) and keep_ids is None:
                         self._store_packed(packed, names, plan, layout, out)
                 result["__fused__"] = out
         for n in names:

@@ -323,6 +323,56 @@ class BagAdamGroup(object):
         for dst, src in zip(self.v, state["v"]):
             dst.copy_(src)
 
+    def apply_fused(self, ids, grad, cols, combiners, bag_lens, batch):
+        """The training loop's form of `apply`: table i gathered the keys `ids[i]` (int64 [batch * bag_lens[i]], dense bags)
+        and its gradient is the column window grad[:, cols[i] : cols[i] + dim] of ONE [batch, total] gradient tensor.
+        The C descriptors are built once and kept: as long as the id buffers stay where they are (the forward's cached
+        plan keeps them), a step only re-bases the gradient pointers (one vector addition for all tables) -- the
+        round-1 step rebuilt 456 descriptors in Python (~7 ms) every time."""
+        import numpy as np
+        n = len(self.tables)
+        if not (len(ids) == len(cols) == len(combiners) == len(bag_lens) == n):
+            raise ValueError("one entry per table")
+        g = _require_cuda(grad, "grad")
+        dim = self.tables[0].shape[1]
+        if g.dtype != torch.float32 or g.dim() != 2 or g.stride(1) != 1 or g.shape[0] != batch or g.stride(0) % 4:
+            raise ValueError("grad must be fp32 [batch, total] with contiguous columns and a row pitch that is a multiple of 4")
+        sig = (tuple(t.data_ptr() for t in ids), tuple(cols), tuple(combiners), tuple(bag_lens), batch, g.stride(0))
+        if getattr(self, "_fused_sig", None) != sig:
+            arr = (nat.AdamField * n)()
+            for i, table in enumerate(self.tables):
+                f = arr[i]
+                t = _require_cuda(ids[i], "ids")
+                if t.dtype != torch.int64 or not t.is_contiguous() or t.numel() != batch * bag_lens[i]:
+                    raise ValueError("ids[i] must be contiguous int64 [batch * bag_len]")
+                f.table, f.m, f.v = table.data_ptr(), self.m[i].data_ptr(), self.v[i].data_ptr()
+                f.table_rows, f.dim = table.shape[0], dim
+                f.ids, f.n_keys, f.grad_stride = t.data_ptr(), t.numel(), g.stride(0)
+                f.combiner, f.bag_len = nat.COMBINER[combiners[i]], bag_lens[i]
+            words = C.sizeof(nat.AdamField) // 8
+            self._fused = {"arr": arr, "view": np.frombuffer(arr, dtype=np.uint64).reshape(-1, words),
+                           "col": nat.AdamField.grad_out.offset // 8, "cols4": np.asarray(cols, dtype=np.uint64) * np.uint64(4),
+                           "ids": list(ids)}
+            self._fused_sig = sig
+        fz = self._fused
+        fz["view"][:, fz["col"]] = np.uint64(g.data_ptr()) + fz["cols4"]
+        self.iterations += 1
+        p = nat.AdamParams(lr=self.learning_rate, beta1=self.beta_1, beta2=self.beta_2, epsilon=self.epsilon,
+                           step=self.iterations, lazy=1 if self.lazy else 0)
+        dev = self.tables[0].device
+        with torch.cuda.device(dev):
+            if getattr(self, "_fused_need", None) is None or self._fused_need[0] != sig:
+                need = int(nat.lib().rf_bag_adam_multi_workspace_bytes(fz["arr"], n))
+                if need < 0:
+                    nat.check(nat.RF_ERR_INVALID)
+                self._fused_need = (sig, need)
+            need = self._fused_need[1]
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            nat.check(nat.lib().rf_bag_backward_adam_multi(fz["arr"], n, batch, C.byref(p), self._ws.data_ptr(), self._ws.numel(),
+                                                           C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        return self.tables
+
     def apply(self, updates, batch):
         """updates: one (ids, grad_out, combiner, bag_len, bag_offsets) per table, in table order; `None` for a
         table that received no gradient this step (it still decays under Keras semantics).  batch: rows of grad_out."""

@@ -95,6 +95,16 @@ class RecallSdpa(torch.nn.Module):
         # per-row l2 normalisation rides in the last Dense's epilogue on the tensor-core path
         return self.user_dense(u, l2_normalize=True), self.ad_dense(a, l2_normalize=True)
 
+    def towers_from_fused(self, user_part, ad_part, behaviour=None):
+        """The dense part from the two column windows of the fused bag output (training path: differentiable)."""
+        u = user_part
+        if self.seq_encoder is not None and behaviour is not None:
+            x, mask = behaviour
+            u = torch.cat([u, self.seq_encoder(x, x, x, mask).mean(dim=1)], dim=-1)
+        if self.global_l2_norm:
+            return self.embedding_norm(self.user_dense(u)), self.embedding_norm(self.ad_dense(ad_part))
+        return self.user_dense(u, l2_normalize=True), self.ad_dense(ad_part, l2_normalize=True)
+
     @staticmethod
     def _adjacent_view(parts):
         """Column views that sit side by side in one buffer (the fused bag output) are returned as ONE strided view

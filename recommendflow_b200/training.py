@@ -127,8 +127,10 @@ class RecallSdpaTrainer(object):
             raise NotImplementedError(f"features {missing} do not pool (combiner null / first / last): no training path")
         leaf = embs["__fused__"].detach().requires_grad_(True)
         layout, _ = self.model.preprocessor.output_layout([n for n in names if n in set(self.model.preprocessor.fused_names())])
-        views = {n: leaf[:, col:col + width] for n, (col, width) in layout.items()}
-        u, a = self.model.towers_from_embeddings(views, behaviour)
+        # the fused buffer holds the user features first, then the ad features (names order): each tower's input is ONE
+        # column window of the leaf -- two slices on the autograd tape instead of one per feature
+        ucols = sum(layout[n][1] for n in self.model.user_cols)
+        u, a = self.model.towers_from_fused(leaf[:, :ucols], leaf[:, ucols:], behaviour)
         return self.model.loss_fun(y_true, u, a), leaf, layout
 
     # ---- the step --------------------------------------------------------------------------------
@@ -149,16 +151,18 @@ class RecallSdpaTrainer(object):
         self.dense_opt.step()
         grad = leaf.grad
         for dim, (group, members) in self._bag_groups(layout).items():
-            updates = []
+            id_list, cols, combs, lens = [], [], [], []
             for name, t, bag in members:
                 layer = self.model.preprocessor[name]
                 combiner = layer.combiner if isinstance(layer, DoubleHashingEmbedding) else layer.pooling
                 if combiner not in ("sum", "avg"):
                     raise NotImplementedError(f"feature {name}: backward is implemented for sum / avg pooling, not {combiner}")
                 rows, bag_len = ids[name]
-                col = layout[name][0] + t * dim
-                updates.append((rows[t], grad[:, col:col + dim], combiner, bag_len, None))
-            group.apply(updates, grad.shape[0])
+                id_list.append(rows[t])
+                cols.append(layout[name][0] + t * dim)
+                combs.append(combiner)
+                lens.append(bag_len)
+            group.apply_fused(id_list, grad, cols, combs, lens, grad.shape[0])
         self.iterations += 1
         return loss.detach()
 
