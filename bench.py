@@ -619,6 +619,14 @@ def run_ours(args):
                        f"rf_bag_forward) -> D2H of the pooled [B, sum(T*D)] fp32; {n_chunks} row chunks on 2 streams "
                        f"(copy/compute overlap)"}
         e2e.update(pcie_diagnostics(dev, world, rank, dist if world > 1 else None))
+        # the step cannot beat the slowest rank's share of the box's host links: all pooled vectors out + all keys in
+        floor_ms = (e2e["d2h_bytes_per_step"] / (e2e["concurrent_d2h_gbs_per_rank_min"] * 1e6)
+                    if e2e["concurrent_d2h_gbs_per_rank_min"] > 0 else None)
+        e2e["box_d2h_floor_ms_per_step"] = floor_ms
+        e2e["fraction_of_box_d2h_ceiling"] = None if not floor_ms else floor_ms / e2e_ms
+        e2e["note"] = ("bound by the D2H of the pooled vectors (436 MB per rank per step): the plain-copy bandwidth measured with "
+                       "all ranks copying at once is printed beside it (one GPU: ~57 GB/s = PCIe Gen5 x16; eight GPUs of this box "
+                       "share ~123 GB/s of D2H)")
         del layers
 
     # ---- roofline of the one kernel ------------------------------------------------------------

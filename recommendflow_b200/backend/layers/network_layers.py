@@ -8,14 +8,17 @@ num_heads)` (:331) although Keras' signature is `(num_heads, key_dim)` -- so the
 masks a whole QUERY row (Keras adds -1e9 to every logit of that row -> uniform attention), the same
 effect as the reference's own `scaled_dot_product_attention`.
 
-The attention core runs in rf_sdpa_forward (CUDA); projections, LayerNorm and the 1x1-conv FFN are
-library GEMMs / elementwise glue (cuBLAS through torch), as the task allows.  Dropout is identity at
-inference (the reference default is dropout=0.).
+The attention core runs in rf_sdpa_forward (CUDA).  At inference the q / k / v / output projections and the 1x1-conv
+FFN run on the tensor-core Dense kernel (rf_dense_forward_tc: the [in, N, H] einsum kernels are flattened to [in, N*H]);
+under autograd they are library GEMMs (torch provides the backward).  LayerNorm is elementwise glue.  Dropout is
+identity at inference (the reference default is dropout=0.).
 """
 import math
 
 import numpy as np
 import torch
+
+from ... import dense_ops
 
 from .attention_layers import Dense
 from .layer_utils import scaled_dot_product_attention
@@ -67,15 +70,29 @@ class KerasMultiHeadAttention(Layer):
         for n, w in zip(names, weights):
             setattr(self, n, torch.nn.Parameter(torch.as_tensor(np.asarray(w), dtype=torch.float32).to(dev), requires_grad=False))
 
+    def _project(self, x, w, b, tag):
+        """einsum("abc,cde->abde", x, w) + b.  At inference the [in, N, H] kernel is flattened to one [in, N*H] Dense
+        and runs on the tensor-core kernel (rf_dense_forward_tc); under autograd it stays the library einsum."""
+        n_out = w.shape[1] * w.shape[2]
+        recording = torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or b.requires_grad)
+        if (dense_ops.DEFAULT_PRECISION == "tf32" and not recording and dense_ops.dense_tc_ok(x, w.shape[0], n_out)):
+            key = (w.data_ptr(), w._version)
+            cache = self.__dict__.setdefault("_wt", {})
+            if cache.get(tag, (None,))[0] != key:
+                cache[tag] = (key, w.detach().reshape(w.shape[0], n_out).t().contiguous())
+            y = dense_ops.dense_forward(x, cache[tag][1], b.detach().reshape(-1), None)
+            return y.view(*x.shape[:-1], w.shape[1], w.shape[2])
+        return torch.einsum("abc,cde->abde", x, w) + b
+
     def call(self, query, value, key=None, attention_mask=None):
         key = value if key is None else key
         self.build(query.shape[-1], query.device)
         B, T, _ = query.shape
         S = key.shape[1]
         N, H = self.num_heads, self.key_dim
-        q = (torch.einsum("abc,cde->abde", query, self.wq) + self.bq).permute(0, 2, 1, 3).reshape(B * N, T, H)
-        k = (torch.einsum("abc,cde->abde", key, self.wk) + self.bk).permute(0, 2, 1, 3).reshape(B * N, S, H)
-        v = (torch.einsum("abc,cde->abde", value, self.wv) + self.bv).permute(0, 2, 1, 3).reshape(B * N, S, H)
+        q = self._project(query, self.wq, self.bq, "q").permute(0, 2, 1, 3).reshape(B * N, T, H)
+        k = self._project(key, self.wk, self.bk, "k").permute(0, 2, 1, 3).reshape(B * N, S, H)
+        v = self._project(value, self.wv, self.bv, "v").permute(0, 2, 1, 3).reshape(B * N, S, H)
         mask = None
         if attention_mask is not None:
             if attention_mask.dim() != 3 or attention_mask.shape[-1] != 1:
@@ -85,6 +102,14 @@ class KerasMultiHeadAttention(Layer):
             raise NotImplementedError("self-attention only (the reference calls mha(x, x, x, mask))")
         ctx = scaled_dot_product_attention(q, k, v, mask)                       # [B*N, T, H]
         ctx = ctx.reshape(B, N, T, H).permute(0, 2, 1, 3)                       # [B, T, N, H]
+        flat = ctx.reshape(B, T, N * H)
+        recording = torch.is_grad_enabled() and (flat.requires_grad or self.wo.requires_grad or self.bo.requires_grad)
+        if dense_ops.DEFAULT_PRECISION == "tf32" and not recording and dense_ops.dense_tc_ok(flat, N * H, self.wo.shape[-1]):
+            key = (self.wo.data_ptr(), self.wo._version)
+            cache = self.__dict__.setdefault("_wt", {})
+            if cache.get("o", (None,))[0] != key:
+                cache["o"] = (key, self.wo.detach().reshape(N * H, -1).t().contiguous())
+            return dense_ops.dense_forward(flat.contiguous(), cache["o"][1], self.bo.detach(), None)
         return torch.einsum("abcd,cde->abe", ctx, self.wo) + self.bo
 
 

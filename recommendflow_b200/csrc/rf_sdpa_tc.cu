@@ -313,25 +313,30 @@ constexpr int kTmemCols2 = 512;
 
 __global__ void __launch_bounds__(kThreads2, 1)
 sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-               const __grid_constant__ CUtensorMap map_v, Params p, int n_vbuf) {
-    extern __shared__ uint8_t smem_raw[];
+               const __grid_constant__ CUtensorMap map_v, Params p, int n_vbuf, int n_qkbuf) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int n_db = p.dh / kKB;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t q_s = base;
-    const uint32_t k_s = q_s + n_db * kBlkBytes;
-    const uint32_t v_s = k_s + n_db * kBlkBytes;                     // n_vbuf buffers of n_db blocks
+    const uint32_t q_s = base;                                       // n_qkbuf buffers of n_db blocks
+    const uint32_t k_s = q_s + n_qkbuf * n_db * kBlkBytes;           // n_qkbuf buffers of n_db blocks
+    const uint32_t v_s = k_s + n_qkbuf * n_db * kBlkBytes;           // n_vbuf buffers of n_db blocks
     const uint32_t p_s = v_s + n_vbuf * n_db * kBlkBytes;            // 4 blocks
     const uint32_t xch_s = p_s + 4 * kBlkBytes;                      // float2 [2][128]: (local max, local sum) per half row
     const uint32_t bars = xch_s + 2 * 128 * 8;
-    const uint32_t qk_full = bars, mma1_done0 = bars + 8, s_free0 = bars + 24, v_full0 = bars + 40, p_ready = bars + 56,
-                   mma2_done = bars + 64, tmem_slot = bars + 72;
+    const uint32_t qk_full0 = bars, mma1_done0 = bars + 16, s_free0 = bars + 32, v_full0 = bars + 48, p_ready = bars + 64,
+                   mma2_done = bars + 72, tmem_slot = bars + 80;
     uint8_t *smem_gen = smem_raw + (base - smem_u32(smem_raw));
     float2 *xch = reinterpret_cast<float2 *>(smem_gen + (xch_s - base));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    {   // the carve-up must fit the launch's dynamic shared memory (the host sizes it without alignment slack)
+        uint32_t dyn;
+        asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+        if (tmem_slot + 4 > smem_u32(smem_raw) + dyn) __trap();
+    }
 
     if (threadIdx.x == 0) {
-        mbar_init(qk_full, 1);
         for (int b = 0; b < 2; ++b) {
+            mbar_init(qk_full0 + 8 * b, 1);
             mbar_init(mma1_done0 + 8 * b, 1);
             mbar_init(s_free0 + 8 * b, kSoftThreads);
             mbar_init(v_full0 + 8 * b, 1);
@@ -365,33 +370,37 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     if (warp == 8) {
         // ===== Q / K loader + GEMM 1 =====
         if (lane == 0) {
-            auto load_qk = [&](int pair) {
-                mbar_expect_tx(qk_full, qk_bytes);
+            auto load_qk = [&](int pair, uint32_t qb) {
+                mbar_expect_tx(qk_full0 + 8 * qb, qk_bytes);
                 for (int db = 0; db < n_db; ++db)
                     for (int h = 0; h < 2; ++h) {
                         const int row = (2 * pair + h) * p.S;
-                        const uint32_t off = db * kBlkBytes + h * (kSeqPad * 128);
-                        tma_load_2d(q_s + off, &map_q, qk_full, db * kKB, row);
-                        tma_load_2d(k_s + off, &map_k, qk_full, db * kKB, row);
+                        const uint32_t off = (qb * n_db + db) * kBlkBytes + h * (kSeqPad * 128);
+                        tma_load_2d(q_s + off, &map_q, qk_full0 + 8 * qb, db * kKB, row);
+                        tma_load_2d(k_s + off, &map_k, qk_full0 + 8 * qb, db * kKB, row);
                     }
             };
-            if ((int)blockIdx.x < n_pairs) load_qk(blockIdx.x);
+            // with two Q/K buffers the loads of pair n+2 start when GEMM 1 of pair n retires: a full pair ahead
+            for (int j = 0; j < n_qkbuf; ++j)
+                if ((int)blockIdx.x + j * stride < n_pairs) load_qk(blockIdx.x + j * stride, (uint32_t)j);
             uint32_t n = 0;
             for (int pair = blockIdx.x; pair < n_pairs; pair += stride, ++n) {
                 const uint32_t b = n & 1u, use = (n >> 1) & 1u;
-                mbar_wait(qk_full, n & 1u);
+                const uint32_t qb = n_qkbuf == 2 ? b : 0u, quse = n_qkbuf == 2 ? use : (n & 1u);
+                mbar_wait(qk_full0 + 8 * qb, quse);
                 mbar_wait(s_free0 + 8 * b, use ^ 1u);               // softmax of pair n-2 has read this logit buffer
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int db = 0; db < n_db; ++db) {
-                    const uint64_t a = desc_kmajor(q_s + db * kBlkBytes), bd = desc_kmajor(k_s + db * kBlkBytes);
+                    const uint64_t a = desc_kmajor(q_s + (qb * n_db + db) * kBlkBytes), bd = desc_kmajor(k_s + (qb * n_db + db) * kBlkBytes);
 #pragma unroll
                     for (int k = 0; k < kKB / 8; ++k)
                         umma_tf32(tmem_base + b * 128u, a + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc1, (db | k) ? 1u : 0u);
                 }
                 umma_commit(mma1_done0 + 8 * b);
-                if (pair + stride < n_pairs) {
-                    mbar_wait(mma1_done0 + 8 * b, use);             // Q / K smem is free again
-                    load_qk(pair + stride);
+                const int nxt = pair + n_qkbuf * stride;
+                if (nxt < n_pairs) {
+                    mbar_wait(mma1_done0 + 8 * b, use);             // this Q / K buffer is free again
+                    load_qk(nxt, qb);
                 }
             }
         }
@@ -568,11 +577,14 @@ int launch_sdpa_tc(const float *q, const float *k, const float *v, const float *
         const int grid = n_pairs < sms * ctas_per_sm ? n_pairs : sms * ctas_per_sm;
         sdpa_tc_kernel_v1<<<grid, kThreads, smem, st>>>(mq, mk, mv, p);
     } else {
-        const int n_vbuf = n_db <= 2 ? 2 : 1;
-        const size_t smem = (size_t)((2 + n_vbuf) * n_db + 4) * kBlkBytes + 2048 + 1024 + 128;
+        // buffering that fits 227 KiB: dh = 32: Q/K x 2, V x 2 (160 KiB); dh = 64: Q/K x 2, V x 1 (224 KiB); dh = 96: x 1, x 1
+        const int n_qkbuf = n_db <= 2 ? 2 : 1, n_vbuf = n_db <= 1 ? 2 : 1;
+        // no alignment slack: the dynamic shared memory of a kernel without static shared memory starts 1 KiB aligned
+        // (the kernel traps if its carve-up does not fit)
+        const size_t smem = (size_t)((2 * n_qkbuf + n_vbuf) * n_db + 4) * kBlkBytes + 2048 + 128;
         RF_CUDA(cudaFuncSetAttribute(sdpa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int grid = n_pairs < sms ? n_pairs : sms;
-        sdpa_tc_kernel<<<grid, kThreads2, smem, st>>>(mq, mk, mv, p, n_vbuf);
+        sdpa_tc_kernel<<<grid, kThreads2, smem, st>>>(mq, mk, mv, p, n_vbuf, n_qkbuf);
     }
     RF_CUDA(cudaGetLastError());
     g_launches.fetch_add(1);
