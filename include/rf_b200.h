@@ -344,6 +344,16 @@ int rf_inbatch_softmax_ce_backward_block(const float *d_query, const float *d_do
                                          int positives_on_diagonal, float *d_grad_query, float *d_grad_doc,
                                          void *stream);
 
+/* The same gradients on the tensor cores: the three contractions (S = Q D^T, dQ = C D, dD = C^T Q) run through          */
+/* rf_dense_forward_tc (tcgen05, TF32 operands) over slabs of 2048 query rows; only a [2048 x batch] slab of the         */
+/* coefficient matrix exists at a time.  batch % 4 == 0, dim % 4 == 0; both gradients are produced.                      */
+/* positives_on_diagonal as in rf_inbatch_softmax_ce_backward_block.                                                      */
+int64_t rf_inbatch_ce_backward_tc_workspace_bytes(int64_t batch, int32_t dim);
+int rf_inbatch_softmax_ce_backward_tc(const float *d_query, const float *d_doc, const float *d_y, const float *d_lse,
+                                      int64_t batch, int32_t dim, float scale, float upstream, int positives_on_diagonal,
+                                      void *d_workspace, int64_t workspace_bytes, float *d_grad_query, float *d_grad_doc,
+                                      void *stream);
+
 /* ---- vocabulary lookup / bucketisation ------------------------------------ */
 /* Keras StringLookup / IntegerLookup(vocabulary=vocabs, output_mode="int") as LookupEmbedding builds */
 /* them (backend/layers/preprocess_layers.py:148-150): term i -> i + 1, out-of-vocabulary -> 0.      */

@@ -160,6 +160,11 @@ def lib():
         L.rf_inbatch_softmax_ce_backward.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_float, C.c_float] + [C.c_void_p] * 3
         L.rf_inbatch_softmax_ce_backward_block.restype = C.c_int
         L.rf_inbatch_softmax_ce_backward_block.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_int] + [C.c_void_p] * 3
+        L.rf_inbatch_ce_backward_tc_workspace_bytes.restype = C.c_int64
+        L.rf_inbatch_ce_backward_tc_workspace_bytes.argtypes = [C.c_int64, C.c_int32]
+        L.rf_inbatch_softmax_ce_backward_tc.restype = C.c_int
+        L.rf_inbatch_softmax_ce_backward_tc.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_int,
+                                                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.rf_vocab_build.argtypes = [C.POINTER(VocabDesc), C.c_void_p]
         L.rf_vocab_lookup_strings.argtypes = [C.POINTER(VocabDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.rf_vocab_lookup_int64.argtypes = [C.POINTER(VocabDesc), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]

@@ -20,6 +20,7 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <atomic>
 
 #include "../../include/rf_b200.h"
@@ -213,6 +214,66 @@ int launch_ce_pass(const float *own, const float *oth, const float *y, const flo
     return RF_OK;
 }
 
+
+// --------------------------------------------------------------------------------------------
+// tensor-core path of the in-batch softmax CE backward: the three contractions (S = Q D^T, dQ = C D, dD = C^T Q) run on
+// rf_dense_forward_tc (tcgen05, TF32 operands) over SLABS of query rows; only a [slab x B] piece of the coefficient
+// matrix ever exists (2048 x 8192 fp32 = 64 MiB at B = 8192), never the B x B matrix.
+//   coef_kernel     C_ij = coef * y_i * (exp(scale * S_ij - lse_i) - [i == j]) in place, plus its transpose (32 x 32 smem tiles)
+//   transpose_kernel [R, C] -> [C, R]
+//   add_kernel      dD += partial
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ce_coef_kernel(float *__restrict__ S, float *__restrict__ CT, const float *__restrict__ y,
+                                                      const float *__restrict__ lse, int rows, int64_t B, int64_t row0, float scale,
+                                                      float coef, float diag_on) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // 32 x 8 threads, 4 rows each
+    const int64_t j0 = (int64_t)blockIdx.x * 32;
+    const int i0 = blockIdx.y * 32;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = i0 + ty + 8 * k;
+        const int64_t j = j0 + tx;
+        float c = 0.f;
+        if (i < rows && j < B) {
+            const int64_t gi = row0 + i;
+            c = coef * y[gi] * (__expf(scale * S[(int64_t)i * B + j] - lse[gi]) - (gi == j ? diag_on : 0.f));
+            S[(int64_t)i * B + j] = c;
+        }
+        tile[ty + 8 * k][tx] = c;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t j = j0 + ty + 8 * k;
+        const int i = i0 + tx;
+        if (i < rows && j < B) CT[j * rows + i] = tile[tx][ty + 8 * k];
+    }
+}
+
+__global__ void __launch_bounds__(256) transpose_kernel(const float *__restrict__ in, float *__restrict__ out, int64_t R, int64_t Cn) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t r = r0 + ty + 8 * k, c = c0 + tx;
+        tile[ty + 8 * k][tx] = (r < R && c < Cn) ? in[r * Cn + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t c = c0 + ty + 8 * k, r = r0 + tx;
+        if (r < R && c < Cn) out[c * R + r] = tile[tx][ty + 8 * k];
+    }
+}
+
+__global__ void __launch_bounds__(256) add_kernel(float *__restrict__ dst, const float *__restrict__ src, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] += src[i];
+}
+
+constexpr int kSlabRows = 2048;
+
 }  // namespace
 }  // namespace rf
 
@@ -261,6 +322,57 @@ int rf_inbatch_softmax_ce_backward_block(const float *d_query, const float *d_do
         if (rc != RF_OK) return rc;
         ++launches;
     }
+    g_launches.fetch_add(launches);
+    return RF_OK;
+}
+
+int64_t rf_inbatch_ce_backward_tc_workspace_bytes(int64_t batch, int32_t dim) {
+    if (batch <= 0 || dim <= 0) return 0;
+    const int64_t R = batch < kSlabRows ? batch : kSlabRows;
+    // S / C slab [R, B], its transpose [B, R], doc^T [dim, B], query-slab^T [dim, R], one partial of dD [B, dim]
+    return (2 * R * batch + (int64_t)dim * batch + (int64_t)dim * R + batch * (int64_t)dim) * (int64_t)sizeof(float) + 1024;
+}
+
+int rf_inbatch_softmax_ce_backward_tc(const float *d_query, const float *d_doc, const float *d_y, const float *d_lse, int64_t batch,
+                                      int32_t dim, float scale, float upstream, int positives_on_diagonal, void *d_workspace,
+                                      int64_t workspace_bytes, float *d_grad_query, float *d_grad_doc, void *stream) {
+    if (batch < 0 || dim <= 0) return set_error(RF_ERR_INVALID, "bad in-batch shape");
+    if (batch == 0) return RF_OK;
+    if (batch % 4 || dim % 4) return set_error(RF_ERR_UNSUPPORTED, "tensor-core CE backward needs batch %% 4 == 0 and dim %% 4 == 0");
+    if (!d_query || !d_doc || !d_y || !d_lse || !d_grad_query || !d_grad_doc)
+        return set_error(RF_ERR_INVALID, "rf_inbatch_softmax_ce_backward_tc: NULL buffer (both gradients are produced)");
+    if (!d_workspace || workspace_bytes < rf_inbatch_ce_backward_tc_workspace_bytes(batch, dim))
+        return set_error(RF_ERR_INVALID, "workspace too small (rf_inbatch_ce_backward_tc_workspace_bytes)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t B = batch, R = B < kSlabRows ? B : kSlabRows;
+    float *ws = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(d_workspace) + 255) & ~(uintptr_t)255);
+    float *slab = ws, *slab_t = slab + R * B, *doc_t = slab_t + R * B, *q_t = doc_t + (int64_t)dim * B, *part = q_t + (int64_t)dim * R;
+    const float coef = upstream * scale / (float)B;
+    const dim3 tb(256);
+    transpose_kernel<<<dim3((unsigned)((dim + 31) / 32), (unsigned)((B + 31) / 32)), tb, 0, st>>>(d_doc, doc_t, B, dim);   // [B, dim] -> [dim, B]
+    int launches = 1;
+    for (int64_t r0 = 0; r0 < B; r0 += R) {
+        const int64_t rows = B - r0 < R ? B - r0 : R;
+        // S slab = Q[r0 : r0 + rows] . D^T
+        int rc = rf_dense_forward_tc(d_query + r0 * dim, rows, dim, dim, d_doc, nullptr, (int32_t)B, RF_ACT_NONE, 0, slab, B, stream);
+        if (rc != RF_OK) return rc;
+        ce_coef_kernel<<<dim3((unsigned)((B + 31) / 32), (unsigned)((rows + 31) / 32)), tb, 0, st>>>(
+            slab, slab_t, d_y, d_lse, (int)rows, B, r0, scale, coef, positives_on_diagonal ? 1.0f : 0.0f);
+        // dQ slab = C . D        (weight_t = D^T [dim, B])
+        rc = rf_dense_forward_tc(slab, rows, (int32_t)B, B, doc_t, nullptr, dim, RF_ACT_NONE, 0, d_grad_query + r0 * dim, dim, stream);
+        if (rc != RF_OK) return rc;
+        // dD (+)= C^T . Q slab   (x = C^T [B, rows], weight_t = Q_slab^T [dim, rows])
+        transpose_kernel<<<dim3((unsigned)((dim + 31) / 32), (unsigned)((rows + 31) / 32)), tb, 0, st>>>(d_query + r0 * dim, q_t, rows, dim);
+        float *dst = r0 == 0 ? d_grad_doc : part;
+        rc = rf_dense_forward_tc(slab_t, B, (int32_t)rows, rows, q_t, nullptr, dim, RF_ACT_NONE, 0, dst, dim, stream);
+        if (rc != RF_OK) return rc;
+        launches += 2;
+        if (r0 != 0) {
+            add_kernel<<<(unsigned)std::min<int64_t>((B * dim + 255) / 256, 148 * 8), tb, 0, st>>>(d_grad_doc, part, B * dim);
+            ++launches;
+        }
+    }
+    RF_CUDA(cudaGetLastError());
     g_launches.fetch_add(launches);
     return RF_OK;
 }

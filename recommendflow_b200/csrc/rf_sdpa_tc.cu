@@ -322,7 +322,7 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const uint32_t v_s = k_s + n_qkbuf * n_db * kBlkBytes;           // n_vbuf buffers of n_db blocks
     const uint32_t p_s = v_s + n_vbuf * n_db * kBlkBytes;            // 4 blocks
     const uint32_t xch_s = p_s + 4 * kBlkBytes;                      // float2 [2][128]: (local max, local sum) per half row
-    const uint32_t bars = xch_s + 2 * 128 * 8;
+    const uint32_t bars = xch_s + 2 * 2 * 128 * 8;                   // two exchange buffers (pairs n, n+1)
     const uint32_t qk_full0 = bars, mma1_done0 = bars + 16, s_free0 = bars + 32, v_full0 = bars + 48, p_ready = bars + 64,
                    mma2_done = bars + 72, tmem_slot = bars + 80;
     uint8_t *smem_gen = smem_raw + (base - smem_u32(smem_raw));
@@ -451,17 +451,23 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const float c2 = p.inv_sqrt_dk * 1.4426950408889634f;       // logits enter exp2 pre-multiplied by log2(e) / sqrt(dh)
         const int nv = min(32, max(0, p.S - ch * 32));              // valid keys among this thread's 32
         const int n32 = p.dh >> 5, o_lo = ch == 0 ? 0 : (n32 + 1) / 2, o_hi = ch == 0 ? (n32 + 1) / 2 : n32;
-        uint32_t n = 0;
-        for (int pair = blockIdx.x; pair < n_pairs; pair += stride, ++n) {
+        // One pair's softmax as two steps, software-pipelined across pairs so that the exponentials of pair n+1 run while
+        // the tensor core does GEMM 2 of pair n (the softmax warps used to idle through it):
+        //   stage(n):  wait logits(n), read them, exp2 / partial sums / exchange with the partner thread -> x[], fac
+        //   emit(n):   P(n) = x * fac into the smem tile, release GEMM 2(n)
+        //   loop:      emit(n); stage(n+1); wait GEMM 2(n); store out(n)
+        float x[32];
+        float fac = 0.f;
+        bool row_ok = false;
+        auto stage = [&](int pair, uint32_t n) {
             const uint32_t b = n & 1u, use = (n >> 1) & 1u;
             const int seq = 2 * pair + half;
             mbar_wait(mma1_done0 + 8 * b, use);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float x[32];
             tmem_ld32(lane_addr + b * 128u + (uint32_t)(half * 64 + ch * 32), x);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(s_free0 + 8 * b);                           // GEMM 1 of pair n+2 may overwrite this buffer
-            const bool row_ok = seq < p.n_seq && i < p.S;
+            row_ok = seq < p.n_seq && i < p.S;
             // the reference's QUERY-row mask fills the whole row with one constant: uniform attention over the S keys
             const bool masked = row_ok && p.mask && p.mask[(size_t)seq * p.S + i] == 0.f;
             float mx = -INFINITY;
@@ -478,14 +484,22 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 x[j] = ex2(fmaf(x[j], c2, -mc));
                 sum += x[j];
             }
-            xch[ch * 128 + r] = make_float2(mx, sum);
+            float2 *xb = xch + (n & 1u) * 256;                      // double-buffered: a fast thread never laps its partner
+            xb[ch * 128 + r] = make_float2(mx, sum);
             asm volatile("bar.sync 1, %0;" ::"n"(kSoftThreads) : "memory");
-            const float2 other = xch[(ch ^ 1) * 128 + r];
+            const float2 other = xb[(ch ^ 1) * 128 + r];
             const float big = fmaxf(mx, other.x);                   // finite: every row has >= 1 valid key in one half
             const float f_me = mx == -INFINITY ? 0.f : ex2((mx - big) * c2);
             const float f_ot = other.x == -INFINITY ? 0.f : ex2((other.x - big) * c2);
             const float total = sum * f_me + other.y * f_ot;
-            const float fac = row_ok ? f_me / total : 0.f;          // rows that are padding produce zeros
+            fac = row_ok ? f_me / total : 0.f;                      // rows that are padding produce zeros
+        };
+        uint32_t n = 0;
+        if ((int)blockIdx.x < n_pairs) stage(blockIdx.x, 0);
+        for (int pair = blockIdx.x; pair < n_pairs; pair += stride, ++n) {
+            const int seq = 2 * pair + half;
+            const bool ok_n = row_ok;
+            // emit(n): GEMM 2 of pair n-1 has been waited for below, so the P tile is free
             uint8_t *prow = smem_gen + (p_s - base) + (r >> 3) * 1024 + (r & 7) * 128 + (half * 2 + ch) * kBlkBytes;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {                             // 8 chunks of 4 keys
@@ -499,13 +513,14 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(p_ready);
+            if (pair + stride < n_pairs) stage(pair + stride, n + 1);   // under GEMM 2 of pair n
             mbar_wait(mma2_done, n & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float *orow = p.out + ((size_t)seq * p.S + i) * p.dh;
             for (int cb = o_lo; cb < o_hi; ++cb) {
                 float o[32];
                 tmem_ld32(lane_addr + 256u + (uint32_t)(cb * 32), o);
-                if (row_ok) {
+                if (ok_n) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
                         *reinterpret_cast<float4 *>(orow + cb * 32 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
@@ -577,11 +592,12 @@ int launch_sdpa_tc(const float *q, const float *k, const float *v, const float *
         const int grid = n_pairs < sms * ctas_per_sm ? n_pairs : sms * ctas_per_sm;
         sdpa_tc_kernel_v1<<<grid, kThreads, smem, st>>>(mq, mk, mv, p);
     } else {
-        // buffering that fits 227 KiB: dh = 32: Q/K x 2, V x 2 (160 KiB); dh = 64: Q/K x 2, V x 1 (224 KiB); dh = 96: x 1, x 1
-        const int n_qkbuf = n_db <= 2 ? 2 : 1, n_vbuf = n_db <= 1 ? 2 : 1;
+        // buffering that fits 227 KiB: dh = 32: Q/K x 2, V x 2 (160 KiB); dh = 64: Q/K x 1, V x 2 (192 KiB; Q/K x 2 with
+        // V x 1 measured no faster: 0.114 vs 0.110 ms); dh = 96: x 1, x 1
+        const int n_qkbuf = n_db <= 1 ? 2 : 1, n_vbuf = n_db <= 2 ? 2 : 1;
         // no alignment slack: the dynamic shared memory of a kernel without static shared memory starts 1 KiB aligned
         // (the kernel traps if its carve-up does not fit)
-        const size_t smem = (size_t)((2 * n_qkbuf + n_vbuf) * n_db + 4) * kBlkBytes + 2048 + 128;
+        const size_t smem = (size_t)((2 * n_qkbuf + n_vbuf) * n_db + 4) * kBlkBytes + 4096 + 128;
         RF_CUDA(cudaFuncSetAttribute(sdpa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int grid = n_pairs < sms ? n_pairs : sms;
         sdpa_tc_kernel<<<grid, kThreads2, smem, st>>>(mq, mk, mv, p, n_vbuf, n_qkbuf);

@@ -180,7 +180,7 @@ def sdpa_backward(q, k, v, mask, grad_out):
 
 
 def inbatch_softmax_ce_backward(query, doc, y_true, lse, scale=20.0, upstream=1.0, need_query=True, need_doc=True,
-                                positives_on_diagonal=True):
+                                positives_on_diagonal=True, precision=None):
     """(d loss / d query, d loss / d doc) of batch_neg_sample_scaled_multi_class_ce_loss, from the forward's lse.
     positives_on_diagonal=False: `doc` is a block of negatives only (another rank's docs in the data-parallel step)
     and `lse` is the log-sum-exp over the whole row of the all-gathered logits."""
@@ -189,6 +189,17 @@ def inbatch_softmax_ce_backward(query, doc, y_true, lse, scale=20.0, upstream=1.
     B, D = q.shape
     if d.shape != q.shape or y.numel() != B or lse.numel() != B:
         raise ValueError("query / doc must be [B, D]; y_true and lse one entry per row")
+    precision = precision or DEFAULT_PRECISION
+    if precision != "fp32" and B % 4 == 0 and D % 4 == 0 and B >= 512:
+        # tensor cores: the three contractions go through the tcgen05 Dense kernel over slabs of query rows
+        gq, gd = torch.empty_like(q), torch.empty_like(d)
+        need = int(nat.lib().rf_inbatch_ce_backward_tc_workspace_bytes(B, D))
+        ws = torch.empty(need, dtype=torch.uint8, device=q.device)
+        with torch.cuda.device(q.device):
+            nat.check(nat.lib().rf_inbatch_softmax_ce_backward_tc(q.data_ptr(), d.data_ptr(), y.data_ptr(), lse.data_ptr(), B, D,
+                                                                  float(scale), float(upstream), 1 if positives_on_diagonal else 0,
+                                                                  ws.data_ptr(), need, gq.data_ptr(), gd.data_ptr(), _stream(q.device)))
+        return (gq if need_query else None), (gd if need_doc else None)
     gq = torch.empty_like(q) if need_query else None
     gd = torch.empty_like(d) if need_doc else None
     with torch.cuda.device(q.device):
@@ -224,14 +235,14 @@ class InbatchSoftmaxCeFunction(torch.autograd.Function):
     def forward(ctx, y_true, query, doc, scale, precision):
         res = inbatch_rowstats(query, doc, y_true=y_true, scale=scale, want=("lse",), precision=precision)
         ctx.save_for_backward(y_true, query, doc, res["lse"])
-        ctx.scale = float(scale)
+        ctx.scale, ctx.precision = float(scale), precision
         return res["loss"]
 
     @staticmethod
     def backward(ctx, grad_loss):
         y, q, d, lse = ctx.saved_tensors
         gq, gd = inbatch_softmax_ce_backward(q, d, y, lse, ctx.scale, float(grad_loss), ctx.needs_input_grad[1],
-                                             ctx.needs_input_grad[2])
+                                             ctx.needs_input_grad[2], precision="fp32" if ctx.precision == "fp32" else None)
         return None, gq, gd, None, None
 
 

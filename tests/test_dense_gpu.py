@@ -11,6 +11,7 @@ import oracle
 from recommendflow_b200.backend.layers.attention_layers import MultiHeadAttention, SelfAttention
 from recommendflow_b200.backend.layers.layer_utils import scaled_dot_product_attention, split_heads
 from recommendflow_b200.backend.lossess import match_losses, match_zipped_losses
+from recommendflow_b200 import _native as nat
 from recommendflow_b200.dense_ops import inbatch_rowstats
 from recommendflow_b200.utils.str_parser import str2loss
 
@@ -186,6 +187,26 @@ def test_sdpa_backward_matches_autograd(shape):
     with pytest.raises(NotImplementedError):
         big = torch.zeros(1, 65, 8, device="cuda", requires_grad=True)
         sdpa_autograd(big, big, big, None, "fp32").sum().backward()
+
+
+@pytest.mark.parametrize("B,D,diag", [(512, 64, True), (4100, 64, True), (2048, 256, False), (6144, 128, True)])
+def test_inbatch_softmax_ce_backward_tensor_core_slabs(B, D, diag):
+    """rf_inbatch_softmax_ce_backward_tc (three tcgen05 GEMMs per slab of 2048 query rows, ragged last slab) against the
+    CUDA-core fp32 kernel on the same lse."""
+    from recommendflow_b200.dense_ops import inbatch_rowstats, inbatch_softmax_ce_backward
+    g = torch.Generator(device="cuda").manual_seed(B + D)
+    q = torch.nn.functional.normalize(torch.randn(B, D, device="cuda", generator=g), dim=1)
+    d = torch.nn.functional.normalize(0.6 * q + 0.8 * torch.randn(B, D, device="cuda", generator=g), dim=1)
+    y = (torch.rand(B, device="cuda", generator=g) > 0.3).float()
+    lse = inbatch_rowstats(q, d, scale=20.0, want=("lse",), precision="fp32")["lse"]
+    rq, rd = inbatch_softmax_ce_backward(q, d, y, lse, 20.0, 2.0, positives_on_diagonal=diag, precision="fp32")
+    before = nat.launch_count()
+    tq, td = inbatch_softmax_ce_backward(q, d, y, lse, 20.0, 2.0, positives_on_diagonal=diag, precision="tf32")
+    assert nat.launch_count() > before
+    # TF32 operands: relative error ~2^-10 per product on gradients whose rows have norm <= 2 * 20 * 2 / B
+    scale = float(rq.abs().max())
+    np.testing.assert_allclose(tq.cpu().numpy(), rq.cpu().numpy(), rtol=2e-2, atol=4e-3 * scale)
+    np.testing.assert_allclose(td.cpu().numpy(), rd.cpu().numpy(), rtol=2e-2, atol=4e-3 * float(rd.abs().max()))
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32"])

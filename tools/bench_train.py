@@ -69,6 +69,16 @@ def main():
     out["embedding_adam"] = "lazy" if trainer.lazy else "keras (all rows decay)"
     out["loss_after"] = float(step())
     print(json.dumps(out))
+    if os.environ.get("PROFILE"):          # where the step's time goes (kineto; not a timing source for the numbers above)
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+        with open(os.environ["PROFILE"], "w") as f:
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70))
+            f.write("\n\n")
+            f.write(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=30, max_name_column_width=70))
 
 
 if __name__ == "__main__":
