@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define RF_B200_ABI_VERSION 2
+#define RF_B200_ABI_VERSION 3
 
 typedef enum rf_status {
     RF_OK = 0,
@@ -195,6 +195,14 @@ typedef enum rf_activation {
 int rf_dense_forward_tc(const float *d_x, int64_t rows, int32_t in_dim, int64_t ldx, const float *d_weight_t,
                         const float *d_bias, int32_t units, int activation, int l2_normalize, float *d_out,
                         int64_t ldo, void *stream);
+/* The same product with a workspace: when the output has too few 128 x 64 tiles to occupy the GPU and the contraction is  */
+/* long (dW = X^T dZ of a tower stage: 4 x 4 tiles, K = batch), K is split over CTAs, the partial products go to the       */
+/* workspace and are summed in a fixed order (deterministic).  Only for bias == NULL, activation none, no normalisation;  */
+/* otherwise, or with d_workspace == NULL / too small, identical to rf_dense_forward_tc.                                   */
+int64_t rf_dense_tc_workspace_bytes(int64_t rows, int32_t in_dim, int32_t units);
+int rf_dense_forward_tc_ex(const float *d_x, int64_t rows, int32_t in_dim, int64_t ldx, const float *d_weight_t,
+                           const float *d_bias, int32_t units, int activation, int l2_normalize, float *d_out,
+                           int64_t ldo, void *d_workspace, int64_t workspace_bytes, void *stream);
 
 /* Same contract with bf16 operands (kind::f16, fp32 accumulate): the TF32 kernel is bound by L2 -> SM operand   */
 /* traffic; here a CTA keeps 256 query rows resident and streams 2-byte doc tiles (4x less traffic per flop).     */
@@ -295,6 +303,9 @@ typedef struct rf_adam_params {
     int64_t step;                    /* t >= 1: iterations + 1                  */
     int32_t lazy;
     int32_t reserved;
+    const float *d_lr_t;             /* NULL, or a device float holding lr * sqrt(1 - beta2^t) / (1 - beta1^t): read by the   */
+                                     /* kernels instead of the value derived from `step` -- required when the call is being   */
+                                     /* recorded into a CUDA graph (the host-side step would be frozen into the graph)        */
 } rf_adam_params;
 /* One table of a multi-table update.  All tables of a call share `dim`; sum of table_rows <= 2^32 - 1, */
 /* sum of n_keys <= 2^31 - 1.  grad_out: [batch, dim] view with row stride grad_stride (floats).         */
@@ -345,14 +356,36 @@ int rf_inbatch_softmax_ce_backward_block(const float *d_query, const float *d_do
                                          void *stream);
 
 /* The same gradients on the tensor cores: the three contractions (S = Q D^T, dQ = C D, dD = C^T Q) run through          */
-/* rf_dense_forward_tc (tcgen05, TF32 operands) over slabs of 2048 query rows; only a [2048 x batch] slab of the         */
-/* coefficient matrix exists at a time.  batch % 4 == 0, dim % 4 == 0; both gradients are produced.                      */
+/* rf_dense_forward_tc (tcgen05, TF32 operands) over slabs of query rows; only a [slab x batch] piece of the coefficient */
+/* matrix (<= 512 MiB, plus its transpose) exists at a time.  batch % 4 == 0, dim % 4 == 0; both gradients are produced.                      */
 /* positives_on_diagonal as in rf_inbatch_softmax_ce_backward_block.                                                      */
 int64_t rf_inbatch_ce_backward_tc_workspace_bytes(int64_t batch, int32_t dim);
 int rf_inbatch_softmax_ce_backward_tc(const float *d_query, const float *d_doc, const float *d_y, const float *d_lse,
                                       int64_t batch, int32_t dim, float scale, float upstream, int positives_on_diagonal,
                                       void *d_workspace, int64_t workspace_bytes, float *d_grad_query, float *d_grad_doc,
                                       void *stream);
+
+/* ---- training-time passes of one tower stage  y = act(BatchNormalization_batch(x) W + b) ------------------------------ */
+/* (backend/blocks/mlp.py:4-15 under model.fit).  The stage's three GEMMs are rf_dense_forward_tc; these are the          */
+/* HBM-bound column passes around them.  All buffers fp32 on the device; workspace: rf_tower_train_workspace_bytes(rows,   */
+/* max(dim, units)) bytes.  Deterministic (ordered partial sums).                                                         */
+int64_t rf_tower_train_workspace_bytes(int64_t rows, int32_t dim);
+/* Batch mean and BIASED variance of every column of x [rows, dim] (row pitch ldx floats), Keras BatchNormalization with   */
+/* training=True.  d_x_t: NULL, or [dim, rows] receiving x transposed in the same pass (operand of dW = X^T dZ).           */
+int rf_column_stats(const float *d_x, int64_t rows, int32_t dim, int64_t ldx, float *d_mean, float *d_var, float *d_x_t,
+                    void *d_workspace, int64_t workspace_bytes, void *stream);
+/* dZ = dY * act'(z) with the derivative taken from the stage's OUTPUT y = act(z) (none, relu, selu, tanh, sigmoid);        */
+/* d_grad_pre [rows, units], d_grad_pre_t NULL or [units, rows] (dZ transposed), d_grad_bias [units] = column sums of dZ.  */
+int rf_activation_backward(const float *d_grad_out, const float *d_out, int64_t rows, int32_t units, int activation,
+                           float *d_grad_pre, float *d_grad_pre_t, float *d_grad_bias, void *d_workspace,
+                           int64_t workspace_bytes, void *stream);
+/* BatchNormalization backward on batch statistics: given dXhat [rows, dim] (gradient w.r.t. the normalised + affine      */
+/* output), x, the batch mean, rstd = rsqrt(var + eps) and scale = gamma * rstd:                                           */
+/*   dbeta = colsum(dXhat), dgamma = colsum(dXhat * xn), dX = scale * (dXhat - dbeta / rows - xn * dgamma / rows),          */
+/*   xn = (x - mean) * rstd.  dim and ldx multiples of 4.                                                                  */
+int rf_batchnorm_backward(const float *d_grad_normed, const float *d_x, int64_t ldx, const float *d_mean, const float *d_rstd,
+                          const float *d_scale, int64_t rows, int32_t dim, float *d_grad_gamma, float *d_grad_beta,
+                          float *d_grad_x, void *d_workspace, int64_t workspace_bytes, void *stream);
 
 /* ---- vocabulary lookup / bucketisation ------------------------------------ */
 /* Keras StringLookup / IntegerLookup(vocabulary=vocabs, output_mode="int") as LookupEmbedding builds */

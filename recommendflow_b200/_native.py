@@ -45,7 +45,7 @@ class ShardCtx(C.Structure):
 
 class AdamParams(C.Structure):
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("epsilon", C.c_float),
-                ("step", C.c_int64), ("lazy", C.c_int32), ("reserved", C.c_int32)]
+                ("step", C.c_int64), ("lazy", C.c_int32), ("reserved", C.c_int32), ("d_lr_t", C.c_void_p)]
 
 
 class AdamField(C.Structure):
@@ -165,6 +165,22 @@ def lib():
         L.rf_inbatch_softmax_ce_backward_tc.restype = C.c_int
         L.rf_inbatch_softmax_ce_backward_tc.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_int,
                                                                           C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rf_dense_tc_workspace_bytes.restype = C.c_int64
+        L.rf_dense_tc_workspace_bytes.argtypes = [C.c_int64, C.c_int32, C.c_int32]
+        L.rf_dense_forward_tc_ex.restype = C.c_int
+        L.rf_dense_forward_tc_ex.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int,
+                                             C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+        L.rf_tower_train_workspace_bytes.restype = C.c_int64
+        L.rf_tower_train_workspace_bytes.argtypes = [C.c_int64, C.c_int32]
+        L.rf_column_stats.restype = C.c_int
+        L.rf_column_stats.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int64, C.c_void_p]
+        L.rf_activation_backward.restype = C.c_int
+        L.rf_activation_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.rf_batchnorm_backward.restype = C.c_int
+        L.rf_batchnorm_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                            C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.rf_vocab_build.argtypes = [C.POINTER(VocabDesc), C.c_void_p]
         L.rf_vocab_lookup_strings.argtypes = [C.POINTER(VocabDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.rf_vocab_lookup_int64.argtypes = [C.POINTER(VocabDesc), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]

@@ -9,8 +9,12 @@ statistics per distinct width (the only way the reference's towers [1024, 512, 2
 Inference (no gradient being recorded, moving statistics, no dropout): every [norm, Dense, activation] stage is
 ONE launch of the tcgen05 GEMM rf_dense_forward_tc -- BatchNormalization is an affine map per input column there
 and is folded into the Dense kernel and bias (cached until a weight changes); the last stage can also l2-normalise
-its rows in the same epilogue.  Under autograd (recommendflow_b200/training.py: batch statistics, dropout) the stages
-run as library GEMMs + elementwise torch ops, whose backward torch provides.
+its rows in the same epilogue.
+Under autograd (recommendflow_b200/training.py: batch statistics, dropout) a stage is ONE autograd node (`_TrainStage`):
+the batch statistics are one var_mean pass, the normalisation is folded into the weights exactly as at inference (it is
+an affine map per column for the batch too), and the forward GEMM and both backward GEMMs (dX = dZ W^T, dW = X^T dZ) run
+on the same tcgen05 kernel; the BatchNormalization backward is applied to dX in closed form.  Shapes the tensor-core kernel
+does not take (widths not multiples of 4, gelu) run as library GEMMs + elementwise torch ops.
 All learned state is registered (Parameters / buffers), so it is part of `state_dict()`.
 """
 import torch
@@ -102,6 +106,51 @@ class _Activated(Layer):
         return _ACT[self.activation](library_matmul(x, self.dense.kernel) + self.dense.bias)
 
 
+_SELU_SCALE, _SELU_ALPHA = 1.0507009873554805, 1.6732632423543772
+
+
+class _TrainStage(torch.autograd.Function):
+    """y = act(BN_batch(x) W + b) as one node.  BN_batch(x) = x * s + t with s = gamma * rsqrt(var + eps), t = beta - mean * s,
+    so z = x (diag(s) W) + (t W + b): one tcgen05 GEMM on x itself.  Backward, with dZ = dY * act'(y) and db = colsum(dZ):
+        dXhat = dZ W^T                                   (tcgen05; W [in, units] is already the [out, in] operand)
+        dW    = Xhat^T dZ = diag(s) (X^T dZ) + t (x) db  (tcgen05 on the transposes; Xhat is never materialised)
+        dbeta = colsum(dXhat), dgamma = colsum(dXhat * xn), dX = s / B * (B dXhat - dbeta - xn * dgamma),  xn = (x - mean) * rstd
+    (Keras BatchNormalization, training=True: biased batch variance.)"""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, kernel, bias, activation, eps, stats):
+        x = x if x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 else x.contiguous()
+        if gamma is not None:
+            mean, var, xt = dense_ops.column_stats(x, want_transpose=True)        # one read of x: statistics + x^T for dW
+            rstd = torch.rsqrt(var + eps)
+            s = gamma * rstd
+            t = beta - mean * s
+            wt = (kernel.t() * s[None, :]).contiguous()
+            b = torch.addmv(bias, kernel.t(), t)
+            stats["mean"], stats["var"] = mean, var
+        else:
+            mean = rstd = s = t = None
+            xt = x.t().contiguous()
+            wt, b = kernel.t().contiguous(), bias
+        y = dense_ops.dense_forward(x, wt, b, activation)
+        ctx.activation, ctx.has_norm = activation, gamma is not None
+        ctx.save_for_backward(x, xt, y, kernel, mean, rstd, s, t)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, xt, y, kernel, mean, rstd, s, t = ctx.saved_tensors
+        dz, dzt, db = dense_ops.activation_backward(dy, y, ctx.activation)           # one read of dY, y
+        dxh = dense_ops.dense_forward(dz, kernel, None, None)                        # [B, in]
+        xtdz = dense_ops.dense_forward(xt, dzt, None, None)                          # [in, units]
+        if not ctx.has_norm:
+            return dxh, None, None, xtdz, db, None, None, None
+        dw = xtdz.mul_(s[:, None])
+        dw.addr_(t, db)
+        dx, dgamma, dbeta = dense_ops.batchnorm_backward(dxh, x, mean, rstd, s)      # two reads of dXhat, x
+        return dx, dgamma, dbeta, dw, db, None, None, None
+
+
 class Dropout(Layer):
     """Keras Dropout(rate): identity unless `active` (a training step), then inverted dropout."""
 
@@ -173,10 +222,51 @@ class Sequential(Layer):
             d = act.dense.units
         return True
 
+    def _trainable_on_tc(self, x, stages):
+        if stages is None or dense_ops.DEFAULT_PRECISION != "tf32" or not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2:
+            return False
+        if not torch.is_grad_enabled() or x.shape[0] % 4:
+            return False
+        d = x.shape[-1]
+        for norm, act in stages:
+            if d % 4 or act.dense.units % 4 or act.activation == "gelu":
+                return False
+            d = act.dense.units
+        return True
+
+    def _train_call(self, x, stages):
+        """The gradient-recording path: one `_TrainStage` node per [norm, Dense + activation], then the stage's Dropout."""
+        drops = [l for l in self.layers if isinstance(l, Dropout)]
+        for idx, (norm, act) in enumerate(stages):
+            d = x.shape[-1]
+            act.dense.build(d, x.device)
+            gamma = beta = None
+            stats = {}
+            eps = 0.0
+            if norm is not None:
+                norm.ensure(d, x.device)
+                gamma, beta, mmean, mvar = norm.state(d)
+                eps = norm.epsilon
+                if not norm.batch_stats:      # moving statistics under autograd (fine-tuning with frozen statistics): plain layers
+                    x = act(norm(x))
+                    x = drops[idx](x) if idx < len(drops) else x
+                    continue
+            x = _TrainStage.apply(x, gamma, beta, act.dense.kernel, act.dense.bias, act.activation, eps, stats)
+            if norm is not None:
+                with torch.no_grad():
+                    mmean.mul_(norm.momentum).add_(stats["mean"] * (1 - norm.momentum))
+                    mvar.mul_(norm.momentum).add_(stats["var"] * (1 - norm.momentum))
+            if idx < len(drops):
+                x = drops[idx](x)
+        return x
+
     def call(self, x, l2_normalize=False):
         """l2_normalize: divide every output row by max(||row||, 1e-12) -- fused into the last stage's epilogue on
         the tensor-core path (the towers' embedding_norm)."""
         stages = self._stages()
+        if not self._fusable(x, stages) and self._trainable_on_tc(x, stages):
+            x = self._train_call(x, stages)
+            return torch.nn.functional.normalize(x, dim=1, eps=1e-12) if l2_normalize else x
         if self._fusable(x, stages) and (not l2_normalize or stages[-1][1].dense.units <= 256):
             for idx, (norm, act) in enumerate(stages):
                 d = x.shape[-1]

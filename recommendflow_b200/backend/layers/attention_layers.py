@@ -16,15 +16,41 @@ from .layer_utils import scaled_dot_product_attention, split_heads
 from .preprocess_layers import Layer
 
 
+class _Tf32Flag(object):
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = dense_ops.DEFAULT_PRECISION == "tf32"
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+
+
+class _LibraryMatmul(torch.autograd.Function):
+    """x [..., in] @ w [in, out] with the precision mode applied to the BACKWARD products as well (torch's own MmBackward
+    runs after the forward's flag has been restored, i.e. on the fp32 SIMT kernels)."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        with _Tf32Flag():
+            return torch.matmul(x, w)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        with _Tf32Flag():
+            gx = torch.matmul(g, w.t()) if ctx.needs_input_grad[0] else None
+            gw = torch.matmul(x.reshape(-1, x.shape[-1]).t(), g.reshape(-1, g.shape[-1])) if ctx.needs_input_grad[1] else None
+        return gx, gw
+
+
 def library_matmul(x, w):
     """Plain library GEMM (cuBLAS).  In the default "tf32" mode fp32 operands go through the TF32 tensor-core
     path, which is also TensorFlow's default for fp32 matmuls on Ampere-and-later GPUs."""
-    prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = dense_ops.DEFAULT_PRECISION == "tf32"
-    try:
+    if w.dim() == 2 and torch.is_grad_enabled() and (x.requires_grad or w.requires_grad):
+        return _LibraryMatmul.apply(x, w)
+    with _Tf32Flag():
         return torch.matmul(x, w)
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = prev
 
 
 class Dense(Layer):

@@ -323,12 +323,14 @@ class BagAdamGroup(object):
         for dst, src in zip(self.v, state["v"]):
             dst.copy_(src)
 
-    def apply_fused(self, ids, grad, cols, combiners, bag_lens, batch):
+    def apply_fused(self, ids, grad, cols, combiners, bag_lens, batch, lr_t=None):
         """The training loop's form of `apply`: table i gathered the keys `ids[i]` (int64 [batch * bag_lens[i]], dense bags)
         and its gradient is the column window grad[:, cols[i] : cols[i] + dim] of ONE [batch, total] gradient tensor.
         The C descriptors are built once and kept: as long as the id buffers stay where they are (the forward's cached
         plan keeps them), a step only re-bases the gradient pointers (one vector addition for all tables) -- the
-        round-1 step rebuilt 456 descriptors in Python (~7 ms) every time."""
+        round-1 step rebuilt 456 descriptors in Python (~7 ms) every time.
+        lr_t: optional 0-dim fp32 CUDA tensor holding lr * sqrt(1 - beta2^t) / (1 - beta1^t); the kernels read it from device
+        memory, which is what lets the call be recorded into a CUDA graph (training.GraphedTrainStep)."""
         import numpy as np
         n = len(self.tables)
         if not (len(ids) == len(cols) == len(combiners) == len(bag_lens) == n):
@@ -358,7 +360,7 @@ class BagAdamGroup(object):
         fz["view"][:, fz["col"]] = np.uint64(g.data_ptr()) + fz["cols4"]
         self.iterations += 1
         p = nat.AdamParams(lr=self.learning_rate, beta1=self.beta_1, beta2=self.beta_2, epsilon=self.epsilon,
-                           step=self.iterations, lazy=1 if self.lazy else 0)
+                           step=self.iterations, lazy=1 if self.lazy else 0, d_lr_t=None if lr_t is None else lr_t.data_ptr())
         dev = self.tables[0].device
         with torch.cuda.device(dev):
             if getattr(self, "_fused_need", None) is None or self._fused_need[0] != sig:

@@ -681,6 +681,40 @@ static DeviceState *device_state(int dev) {
     return states[dev];
 }
 
+// A run of descriptor slots for ONE captured launch: pinned host bytes that are never rewritten (the graph's memcpy node
+// re-reads them on every replay) and the matching device bytes.  Shared with the optimizer (rf_bag_adam.cu).
+static int graph_slots_locked(DeviceState *st, size_t bytes, char **host, char **device) {
+    if (!st->graph_host) return set_error(RF_ERR_CUDA, "run the call once outside stream capture before capturing it");
+    const int need = (int)((bytes + kGraphSlotBytes - 1) / kGraphSlotBytes);
+    if (need < 1 || st->graph_used + need > kGraphSlots)
+        return set_error(RF_ERR_UNSUPPORTED, "captured launches need more than the %d descriptor slots of %zu bytes (rf_release_captured_launches frees them)",
+                         kGraphSlots, kGraphSlotBytes);
+    *host = st->graph_host + (size_t)st->graph_used * kGraphSlotBytes;
+    *device = st->graph_dev + (size_t)st->graph_used * kGraphSlotBytes;
+    st->graph_used += need;
+    return RF_OK;
+}
+
+static int graph_pool_ready_locked(DeviceState *st) {
+    if (!st->graph_host) {
+        RF_CUDA(cudaMallocHost(reinterpret_cast<void **>(&st->graph_host), kGraphSlots * kGraphSlotBytes));
+        RF_CUDA(cudaMalloc(reinterpret_cast<void **>(&st->graph_dev), kGraphSlots * kGraphSlotBytes));
+    }
+    return RF_OK;
+}
+
+int graph_desc_slots(int dev, size_t bytes, char **host, char **device) {
+    DeviceState *st = device_state(dev);
+    std::lock_guard<std::mutex> lk(st->mu);
+    return graph_slots_locked(st, bytes, host, device);
+}
+
+int graph_desc_pool_ready(int dev) {
+    DeviceState *st = device_state(dev);
+    std::lock_guard<std::mutex> lk(st->mu);
+    return graph_pool_ready_locked(st);
+}
+
 // Optional cap on resident CTAs per SM (0 = none): the kernel walks its tiles grid-stride, so a
 // smaller grid leaves registers / CTA slots on every SM for kernels of OTHER streams -- used by the
 // sharded pipeline so that the routing of the next step really runs under the pooling of this one.
@@ -756,19 +790,16 @@ static int launch_fields(std::vector<DevField> &dev_fields, int ctas_per_sm, cud
     cudaStreamCaptureStatus capture = cudaStreamCaptureStatusNone;
     RF_CUDA(cudaStreamIsCapturing(stream, &capture));
     if (capture != cudaStreamCaptureStatusNone) {
-        if (!st->graph_host) return set_error(RF_ERR_CUDA, "run rf_bag_forward once outside stream capture before capturing it");
-        if (bytes > kGraphSlotBytes) return set_error(RF_ERR_UNSUPPORTED, "too many fields for a captured launch");
-        if (st->graph_used >= kGraphSlots) return set_error(RF_ERR_UNSUPPORTED, "more than %d captured launches", kGraphSlots);
-        char *h = st->graph_host + (size_t)st->graph_used * kGraphSlotBytes;
-        char *d = st->graph_dev + (size_t)st->graph_used * kGraphSlotBytes;
-        st->graph_used++;
+        char *h = nullptr, *d = nullptr;
+        int rc = graph_slots_locked(st, bytes, &h, &d);
+        if (rc != RF_OK) return rc;
         memcpy(h, dev_fields.data(), bytes);
         RF_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream));
         return launch_kernel(reinterpret_cast<const DevField *>(d), (int)dev_fields.size(), (int)tiles, ctas_per_sm, acc, stream);
     }
-    if (!st->graph_host) {
-        RF_CUDA(cudaMallocHost(reinterpret_cast<void **>(&st->graph_host), kGraphSlots * kGraphSlotBytes));
-        RF_CUDA(cudaMalloc(reinterpret_cast<void **>(&st->graph_dev), kGraphSlots * kGraphSlotBytes));
+    {
+        int rc = graph_pool_ready_locked(st);
+        if (rc != RF_OK) return rc;
     }
     DescSlot &slot = st->slots[st->next];
     st->next = (st->next + 1) % 8;

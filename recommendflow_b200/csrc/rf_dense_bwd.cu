@@ -218,7 +218,7 @@ int launch_ce_pass(const float *own, const float *oth, const float *y, const flo
 // --------------------------------------------------------------------------------------------
 // tensor-core path of the in-batch softmax CE backward: the three contractions (S = Q D^T, dQ = C D, dD = C^T Q) run on
 // rf_dense_forward_tc (tcgen05, TF32 operands) over SLABS of query rows; only a [slab x B] piece of the coefficient
-// matrix ever exists (2048 x 8192 fp32 = 64 MiB at B = 8192), never the B x B matrix.
+// matrix exists at a time (at most 512 MiB + its transpose; the whole 8192 x 8192 matrix at C3's batch, 2048 rows at B = 65536).
 //   coef_kernel     C_ij = coef * y_i * (exp(scale * S_ij - lse_i) - [i == j]) in place, plus its transpose (32 x 32 smem tiles)
 //   transpose_kernel [R, C] -> [C, R]
 //   add_kernel      dD += partial
@@ -272,7 +272,14 @@ __global__ void __launch_bounds__(256) add_kernel(float *__restrict__ dst, const
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] += src[i];
 }
 
-constexpr int kSlabRows = 2048;
+// rows of the coefficient matrix alive at a time: as many as 1 GiB holds (slab + its transpose), at least 512: a slab is the
+// M of two of the three GEMMs, and 2048 rows x 256 columns are only 64 tiles for 148 SMs
+inline int64_t slab_rows(int64_t batch) {
+    int64_t r = ((int64_t)1 << 27) / (batch > 0 ? batch : 1);
+    r = r / 128 * 128;
+    if (r < 512) r = 512;
+    return r < batch ? r : batch;
+}
 
 }  // namespace
 }  // namespace rf
@@ -328,7 +335,7 @@ int rf_inbatch_softmax_ce_backward_block(const float *d_query, const float *d_do
 
 int64_t rf_inbatch_ce_backward_tc_workspace_bytes(int64_t batch, int32_t dim) {
     if (batch <= 0 || dim <= 0) return 0;
-    const int64_t R = batch < kSlabRows ? batch : kSlabRows;
+    const int64_t R = slab_rows(batch);
     // S / C slab [R, B], its transpose [B, R], doc^T [dim, B], query-slab^T [dim, R], one partial of dD [B, dim]
     return (2 * R * batch + (int64_t)dim * batch + (int64_t)dim * R + batch * (int64_t)dim) * (int64_t)sizeof(float) + 1024;
 }
@@ -344,7 +351,7 @@ int rf_inbatch_softmax_ce_backward_tc(const float *d_query, const float *d_doc, 
     if (!d_workspace || workspace_bytes < rf_inbatch_ce_backward_tc_workspace_bytes(batch, dim))
         return set_error(RF_ERR_INVALID, "workspace too small (rf_inbatch_ce_backward_tc_workspace_bytes)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int64_t B = batch, R = B < kSlabRows ? B : kSlabRows;
+    const int64_t B = batch, R = slab_rows(B);
     float *ws = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(d_workspace) + 255) & ~(uintptr_t)255);
     float *slab = ws, *slab_t = slab + R * B, *doc_t = slab_t + R * B, *q_t = doc_t + (int64_t)dim * B, *part = q_t + (int64_t)dim * R;
     const float coef = upstream * scale / (float)B;

@@ -160,6 +160,9 @@ struct Params {
     int act, l2norm;
     int n_m_tiles, n_n_tiles;
     float l2_eps;
+    // split-K: tile t = (split, m_tile, n_tile); split s contracts k-blocks [s * kb_per, (s + 1) * kb_per) and stores its
+    // partial product at rows s * m_pad + ... of a [k_splits * m_pad, N] buffer (summed in order by splitk_sum_kernel)
+    int k_splits, kb_per, m_pad;
 };
 
 template <int BN>
@@ -179,7 +182,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const uint32_t full0 = bars, empty0 = bars + 8 * kStages;
     const uint32_t tmem_full0 = bars + 16 * kStages, tmem_empty0 = tmem_full0 + 16, tmem_slot = tmem_empty0 + 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tiles = p.n_m_tiles * p.n_n_tiles;
+    const int mn_tiles = p.n_m_tiles * p.n_n_tiles;
+    const int n_tiles = mn_tiles * p.k_splits;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -207,8 +211,10 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int m_tile = t / p.n_n_tiles, n_tile = t - m_tile * p.n_n_tiles;
-                for (int kb = 0; kb < n_kb; ++kb) {
+                const int split = t / mn_tiles, mn = t - split * mn_tiles;
+                const int m_tile = mn / p.n_n_tiles, n_tile = mn - m_tile * p.n_n_tiles;
+                const int kb0 = split * p.kb_per, kb1 = min(n_kb, kb0 + p.kb_per);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t dst = ring + stage * kStageBytes;
                     mbar_expect_tx(full0 + 8 * stage, kStageBytes);
@@ -230,7 +236,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 const uint32_t acc = (uint32_t)(local & 1);
                 mbar_wait(tmem_empty0 + 8 * acc, ((uint32_t)(local >> 1) & 1u) ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int kb = 0; kb < n_kb; ++kb) {
+                const int kb0 = (t / mn_tiles) * p.kb_per, kb1 = min(n_kb, kb0 + p.kb_per);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full0 + 8 * stage, phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t st_addr = ring + stage * kStageBytes;
@@ -238,7 +245,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k)
                         umma_tf32(tmem_base + acc * (uint32_t)BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kIdesc,
-                                  (kb | k) != 0 ? 1u : 0u);
+                                  (kb != kb0 || k != 0) ? 1u : 0u);
                     umma_commit(empty0 + 8 * stage);
                     if (++stage == kStages) {
                         stage = 0;
@@ -257,7 +264,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         int local = 0;
         uint32_t n_store = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++local) {
-            const int m_tile = t / p.n_n_tiles, n_tile = t - m_tile * p.n_n_tiles;
+            const int split = t / mn_tiles, mn = t - split * mn_tiles;
+            const int m_tile = mn / p.n_n_tiles, n_tile = mn - m_tile * p.n_n_tiles;
             const uint32_t acc = (uint32_t)(local & 1);
             mbar_wait(tmem_full0 + 8 * acc, (uint32_t)(local >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -284,7 +292,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 asm volatile("bar.sync 1, 256;" ::: "memory");                       // before the next tile overwrites xch
                 inv = 1.f / fmaxf(sqrtf(ss), p.l2_eps);
             }
-            const int row0 = m_tile * kBM + quarter * 32;
+            const int row0 = split * p.m_pad + m_tile * kBM + quarter * 32;
 #pragma unroll 1
             for (int c0 = half * 32; c0 < BN; c0 += 64) {
                 const int col0 = n_tile * BN + c0;
@@ -346,24 +354,62 @@ static int make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t c
     return RF_OK;
 }
 
+__global__ void __launch_bounds__(256) splitk_sum_kernel(const float *__restrict__ part, int splits, int64_t m_pad, int M, int N,
+                                                          float *__restrict__ out, int64_t ldo) {
+    const int q = N >> 2;
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < (int64_t)M * q; e += (int64_t)gridDim.x * 256) {
+        const int64_t m = e / q;
+        const int n = (int)(e - m * q) * 4;
+        float4 a = *reinterpret_cast<const float4 *>(part + m * N + n);
+        for (int s = 1; s < splits; ++s) {
+            const float4 b = *reinterpret_cast<const float4 *>(part + ((int64_t)s * m_pad + m) * N + n);
+            a.x += b.x;
+            a.y += b.y;
+            a.z += b.z;
+            a.w += b.w;
+        }
+        *reinterpret_cast<float4 *>(out + m * ldo + n) = a;
+    }
+}
+
 template <int BN>
-static int launch(const float *x, int64_t ldx, const float *wt, int64_t ldw, Params p, int sms, cudaStream_t st) {
+static int launch(const float *x, int64_t ldx, const float *wt, int64_t ldw, Params p, int sms, cudaStream_t st, float *partials) {
     CUtensorMap ma, mb, mo;
     int rc = make_map(&ma, x, p.M, p.K, ldx, kBM);
     if (rc != RF_OK) return rc;
     rc = make_map(&mb, wt, p.N, p.K, ldw, BN);
     if (rc != RF_OK) return rc;
-    rc = make_map(&mo, p.out, p.M, p.N, p.ldo, 32, CU_TENSOR_MAP_L2_PROMOTION_NONE);     // 32 x 32 store boxes
-    if (rc != RF_OK) return rc;
     p.n_m_tiles = (p.M + kBM - 1) / kBM;
     p.n_n_tiles = (p.N + BN - 1) / BN;
-    const int tiles = p.n_m_tiles * p.n_n_tiles;
+    p.m_pad = p.n_m_tiles * kBM;
+    if (p.k_splits > 1)
+        rc = make_map(&mo, partials, (int64_t)p.k_splits * p.m_pad, p.N, p.N, 32, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+    else
+        rc = make_map(&mo, p.out, p.M, p.N, p.ldo, 32, CU_TENSOR_MAP_L2_PROMOTION_NONE);     // 32 x 32 store boxes
+    if (rc != RF_OK) return rc;
+    const int tiles = p.n_m_tiles * p.n_n_tiles * p.k_splits;
     const int grid = tiles < sms ? tiles : sms;
     RF_CUDA(cudaFuncSetAttribute(dense_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::kSmem));
     dense_tc_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmem, st>>>(ma, mb, mo, p);
+    if (p.k_splits > 1) {
+        int64_t blocks = ((int64_t)p.M * (p.N / 4) + 255) / 256;
+        if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+        splitk_sum_kernel<<<(unsigned)blocks, 256, 0, st>>>(partials, p.k_splits, p.m_pad, p.M, p.N, p.out, p.ldo);
+    }
     RF_CUDA(cudaGetLastError());
-    g_launches.fetch_add(1);
+    g_launches.fetch_add(p.k_splits > 1 ? 2 : 1);
     return RF_OK;
+}
+
+// K splits for a product whose output has too few tiles to occupy the GPU (dW = X^T dZ of a tower stage: 4 x 4 tiles, K = 8192)
+static int pick_splits(int64_t rows, int units, int in_dim, int sms) {
+    const int64_t tiles = ((rows + kBM - 1) / kBM) * ((units + 63) / 64);
+    const int n_kb = (in_dim + kBK - 1) / kBK;
+    if (tiles * 2 > sms || n_kb < 16) return 1;
+    int64_t s = sms / tiles;
+    if (s > n_kb / 8) s = n_kb / 8;
+    if (s > 64) s = 64;
+    return s < 2 ? 1 : (int)s;
 }
 
 }  // namespace gemm_tc
@@ -371,9 +417,17 @@ static int launch(const float *x, int64_t ldx, const float *wt, int64_t ldw, Par
 
 using namespace rf;
 
-extern "C" int rf_dense_forward_tc(const float *d_x, int64_t rows, int32_t in_dim, int64_t ldx, const float *d_weight_t,
-                                   const float *d_bias, int32_t units, int activation, int l2_normalize, float *d_out,
-                                   int64_t ldo, void *stream) {
+extern "C" int64_t rf_dense_tc_workspace_bytes(int64_t rows, int32_t in_dim, int32_t units) {
+    using namespace gemm_tc;
+    if (rows <= 0 || in_dim <= 0 || units <= 0) return 0;
+    const int splits = pick_splits(rows, units, in_dim, 148);
+    if (splits <= 1) return 0;
+    return (int64_t)splits * ((rows + kBM - 1) / kBM) * kBM * units * (int64_t)sizeof(float);
+}
+
+extern "C" int rf_dense_forward_tc_ex(const float *d_x, int64_t rows, int32_t in_dim, int64_t ldx, const float *d_weight_t,
+                                      const float *d_bias, int32_t units, int activation, int l2_normalize, float *d_out,
+                                      int64_t ldo, void *d_workspace, int64_t workspace_bytes, void *stream) {
     using namespace gemm_tc;
     if (rows < 0 || in_dim <= 0 || units <= 0) return set_error(RF_ERR_INVALID, "bad Dense shape");
     if (activation < RF_ACT_NONE || activation > RF_ACT_GELU) return set_error(RF_ERR_INVALID, "Unknown activation function: %d", activation);
@@ -388,8 +442,22 @@ extern "C" int rf_dense_forward_tc(const float *d_x, int64_t rows, int32_t in_di
     int dev = 0, sms = 148;
     RF_CUDA(cudaGetDevice(&dev));
     RF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    Params p{d_bias, d_out, ldo, (int)rows, units, in_dim, activation, l2_normalize ? 1 : 0, 0, 0, 1e-12f};
+    Params p{d_bias, d_out, ldo, (int)rows, units, in_dim, activation, l2_normalize ? 1 : 0, 0, 0, 1e-12f, 1, 0, 0};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int n_kb = (in_dim + kBK - 1) / kBK;
+    p.kb_per = n_kb;
+    // split-K only for a plain product (no bias / activation / normalisation to apply to a partial sum) and only when the
+    // caller brought the workspace for it
+    if (d_workspace && !d_bias && activation == RF_ACT_NONE && !l2_normalize) {
+        const int splits = pick_splits(rows, units, in_dim, 148);
+        if (splits > 1 && workspace_bytes >= rf_dense_tc_workspace_bytes(rows, in_dim, units) &&
+            (reinterpret_cast<uintptr_t>(d_workspace) & 15) == 0) {
+            p.kb_per = (n_kb + splits - 1) / splits;
+            p.k_splits = (n_kb + p.kb_per - 1) / p.kb_per;
+        }
+    }
+    float *partials = static_cast<float *>(d_workspace);
+    if (p.k_splits > 1) return launch<64>(d_x, ldx, d_weight_t, in_dim, p, sms, st, partials);
     // column tile: the widest that keeps the persistent grid busy: cost = waves x tile width
     const int64_t m_tiles = (rows + kBM - 1) / kBM;
     int best_bn = 0;
@@ -404,7 +472,14 @@ extern "C" int rf_dense_forward_tc(const float *d_x, int64_t rows, int32_t in_di
             best_bn = bn;
         }
     }
-    if (best_bn == 256) return launch<256>(d_x, ldx, d_weight_t, in_dim, p, sms, st);
-    if (best_bn == 128) return launch<128>(d_x, ldx, d_weight_t, in_dim, p, sms, st);
-    return launch<64>(d_x, ldx, d_weight_t, in_dim, p, sms, st);
+    if (best_bn == 256) return launch<256>(d_x, ldx, d_weight_t, in_dim, p, sms, st, nullptr);
+    if (best_bn == 128) return launch<128>(d_x, ldx, d_weight_t, in_dim, p, sms, st, nullptr);
+    return launch<64>(d_x, ldx, d_weight_t, in_dim, p, sms, st, nullptr);
+}
+
+extern "C" int rf_dense_forward_tc(const float *d_x, int64_t rows, int32_t in_dim, int64_t ldx, const float *d_weight_t,
+                                   const float *d_bias, int32_t units, int activation, int l2_normalize, float *d_out,
+                                   int64_t ldo, void *stream) {
+    return rf_dense_forward_tc_ex(d_x, rows, in_dim, ldx, d_weight_t, d_bias, units, activation, l2_normalize, d_out, ldo, nullptr, 0,
+                                  stream);
 }

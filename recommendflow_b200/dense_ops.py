@@ -62,15 +62,67 @@ def dense_forward(x, weight_t, bias=None, activation=None, l2_normalize=False, o
         if out2.dtype != torch.float32 or out2.shape[0] != rows or out2.stride(1) != 1:
             raise ValueError("out must be an fp32 [rows, units] view with contiguous columns")
     b = None if bias is None else _f32(bias, "bias")
+    ws, need = None, 0
+    if b is None and activation in (None, "linear") and not l2_normalize:        # a plain product may split K (few output tiles, long K)
+        need = int(nat.lib().rf_dense_tc_workspace_bytes(rows, in_dim, units))
+        if need:
+            ws = torch.empty(need, dtype=torch.uint8, device=x2.device)
     with torch.cuda.device(x2.device):
-        nat.check(nat.lib().rf_dense_forward_tc(x2.data_ptr(), rows, in_dim, ldx, w.data_ptr(), None if b is None else b.data_ptr(),
-                                                units, nat.ACTIVATION[activation], 1 if l2_normalize else 0, out2.data_ptr(),
-                                                out2.stride(0) if rows > 1 else units, _stream(x2.device)))
+        nat.check(nat.lib().rf_dense_forward_tc_ex(x2.data_ptr(), rows, in_dim, ldx, w.data_ptr(), None if b is None else b.data_ptr(),
+                                                   units, nat.ACTIVATION[activation], 1 if l2_normalize else 0, out2.data_ptr(),
+                                                   out2.stride(0) if rows > 1 else units, None if ws is None else ws.data_ptr(), need,
+                                                   _stream(x2.device)))
     return out2.view(*lead, units) if out is None else out
 
 
 def sdpa_tc_shape_ok(S, dh):
     return 1 <= S <= 64 and dh in (32, 64, 96)
+
+
+def _tower_ws(rows, dim, device):
+    need = int(nat.lib().rf_tower_train_workspace_bytes(rows, dim))
+    return torch.empty(need, dtype=torch.uint8, device=device), need
+
+
+def column_stats(x, want_transpose=False):
+    """(mean, biased variance[, x^T]) of the columns of x [rows, dim] in one pass (rf_column_stats)."""
+    rows, dim = x.shape
+    mean = torch.empty(dim, dtype=torch.float32, device=x.device)
+    var = torch.empty_like(mean)
+    xt = torch.empty(dim, rows, dtype=torch.float32, device=x.device) if want_transpose else None
+    ws, need = _tower_ws(rows, dim, x.device)
+    with torch.cuda.device(x.device):
+        nat.check(nat.lib().rf_column_stats(x.data_ptr(), rows, dim, x.stride(0), mean.data_ptr(), var.data_ptr(),
+                                            None if xt is None else xt.data_ptr(), ws.data_ptr(), need, _stream(x.device)))
+    return mean, var, xt
+
+
+def activation_backward(dy, y, activation):
+    """(dZ, dZ^T, db) from dY and the stage output y (rf_activation_backward)."""
+    rows, units = dy.shape
+    dy = dy if dy.is_contiguous() else dy.contiguous()
+    dz = torch.empty(rows, units, dtype=torch.float32, device=dy.device)
+    dzt = torch.empty(units, rows, dtype=torch.float32, device=dy.device)
+    db = torch.empty(units, dtype=torch.float32, device=dy.device)
+    ws, need = _tower_ws(rows, units, dy.device)
+    with torch.cuda.device(dy.device):
+        nat.check(nat.lib().rf_activation_backward(dy.data_ptr(), y.data_ptr(), rows, units, nat.ACTIVATION[activation], dz.data_ptr(),
+                                                   dzt.data_ptr(), db.data_ptr(), ws.data_ptr(), need, _stream(dy.device)))
+    return dz, dzt, db
+
+
+def batchnorm_backward(dxh, x, mean, rstd, scale):
+    """(dX, dgamma, dbeta) of BatchNormalization on batch statistics (rf_batchnorm_backward)."""
+    rows, dim = x.shape
+    dx = torch.empty(rows, dim, dtype=torch.float32, device=x.device)
+    dgamma = torch.empty(dim, dtype=torch.float32, device=x.device)
+    dbeta = torch.empty_like(dgamma)
+    ws, need = _tower_ws(rows, dim, x.device)
+    with torch.cuda.device(x.device):
+        nat.check(nat.lib().rf_batchnorm_backward(dxh.data_ptr(), x.data_ptr(), x.stride(0), mean.data_ptr(), rstd.data_ptr(),
+                                                  scale.data_ptr(), rows, dim, dgamma.data_ptr(), dbeta.data_ptr(), dx.data_ptr(),
+                                                  ws.data_ptr(), need, _stream(x.device)))
+    return dx, dgamma, dbeta
 
 
 def sdpa(q, k, v, mask=None, precision=None):
@@ -241,9 +293,10 @@ class InbatchSoftmaxCeFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss):
         y, q, d, lse = ctx.saved_tensors
-        gq, gd = inbatch_softmax_ce_backward(q, d, y, lse, ctx.scale, float(grad_loss), ctx.needs_input_grad[1],
+        # upstream stays on the device (float(grad_loss) would stall the host on everything queued so far)
+        gq, gd = inbatch_softmax_ce_backward(q, d, y, lse, ctx.scale, 1.0, ctx.needs_input_grad[1],
                                              ctx.needs_input_grad[2], precision="fp32" if ctx.precision == "fp32" else None)
-        return None, gq, gd, None, None
+        return None, (None if gq is None else gq.mul_(grad_loss)), (None if gd is None else gd.mul_(grad_loss)), None, None
 
 
 def sdpa_autograd(q, k, v, mask=None, precision=None):

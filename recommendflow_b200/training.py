@@ -32,6 +32,17 @@ class KerasAdam(object):
         self.iterations = 0
         self.m = [torch.zeros_like(p) for p in self.params]
         self.v = [torch.zeros_like(p) for p in self.params]
+        # device-resident step (`capturable`): t and lr_t live in CUDA memory and are advanced by tensor ops, so that a step
+        # recorded into a CUDA graph keeps counting when it is replayed
+        self.capturable = False
+        self.step_t = self.lr_t = None
+
+    def make_capturable(self):
+        dev = self.params[0].device
+        self.capturable = True
+        self.step_t = torch.full((), float(self.iterations), dtype=torch.float64, device=dev)
+        self.lr_t = torch.zeros((), dtype=torch.float32, device=dev)
+        return self
 
     def zero_grad(self):
         for p in self.params:
@@ -41,7 +52,12 @@ class KerasAdam(object):
     def step(self):
         self.iterations += 1
         t = self.iterations
-        lr_t = self.learning_rate * (1.0 - self.beta_2 ** t) ** 0.5 / (1.0 - self.beta_1 ** t)
+        if self.capturable:
+            self.step_t += 1.0
+            lr = self.learning_rate * torch.sqrt(1.0 - torch.pow(self.beta_2, self.step_t)) / (1.0 - torch.pow(self.beta_1, self.step_t))
+            self.lr_t.copy_(lr)
+        else:
+            lr_t = self.learning_rate * (1.0 - self.beta_2 ** t) ** 0.5 / (1.0 - self.beta_1 ** t)
         idx = [i for i, p in enumerate(self.params) if p.grad is not None]
         if not idx:
             return
@@ -53,7 +69,12 @@ class KerasAdam(object):
         torch._foreach_addcmul_(vs, gs, gs, value=1.0 - self.beta_2)
         den = torch._foreach_sqrt(vs)
         torch._foreach_add_(den, self.epsilon)
-        torch._foreach_addcdiv_(ps, ms, den, value=-lr_t)
+        if self.capturable:
+            upd = torch._foreach_div(ms, den)
+            torch._foreach_mul_(upd, self.lr_t)
+            torch._foreach_sub_(ps, upd)
+        else:
+            torch._foreach_addcdiv_(ps, ms, den, value=-lr_t)
 
     def state_dict(self):
         return {"iterations": self.iterations, "m": [t.clone() for t in self.m], "v": [t.clone() for t in self.v]}
@@ -73,6 +94,7 @@ class RecallSdpaTrainer(object):
         self.lazy = lazy_embedding_adam
         self.dense_opt = None
         self.bag_opts = {}
+        self._fused_args = {}
         self.iterations = 0
 
     # ---- helpers ---------------------------------------------------------------------------------
@@ -151,18 +173,25 @@ class RecallSdpaTrainer(object):
         self.dense_opt.step()
         grad = leaf.grad
         for dim, (group, members) in self._bag_groups(layout).items():
-            id_list, cols, combs, lens = [], [], [], []
-            for name, t, bag in members:
-                layer = self.model.preprocessor[name]
-                combiner = layer.combiner if isinstance(layer, DoubleHashingEmbedding) else layer.pooling
-                if combiner not in ("sum", "avg"):
-                    raise NotImplementedError(f"feature {name}: backward is implemented for sum / avg pooling, not {combiner}")
-                rows, bag_len = ids[name]
-                id_list.append(rows[t])
-                cols.append(layout[name][0] + t * dim)
-                combs.append(combiner)
-                lens.append(bag_len)
-            group.apply_fused(id_list, grad, cols, combs, lens, grad.shape[0])
+            # the forward's cached plan keeps the id buffers in place: the per-table views are rebuilt only when they moved
+            key = tuple((ids[name][0].data_ptr(), ids[name][1]) for name, t, _ in members if t == 0)
+            hit = self._fused_args.get(dim)
+            if hit is None or hit[0] != key:
+                id_list, cols, combs, lens = [], [], [], []
+                for name, t, bag in members:
+                    layer = self.model.preprocessor[name]
+                    combiner = layer.combiner if isinstance(layer, DoubleHashingEmbedding) else layer.pooling
+                    if combiner not in ("sum", "avg"):
+                        raise NotImplementedError(f"feature {name}: backward is implemented for sum / avg pooling, not {combiner}")
+                    rows, bag_len = ids[name]
+                    id_list.append(rows[t])
+                    cols.append(layout[name][0] + t * dim)
+                    combs.append(combiner)
+                    lens.append(bag_len)
+                hit = (key, id_list, cols, combs, lens)
+                self._fused_args[dim] = hit
+            group.apply_fused(hit[1], grad, hit[2], hit[3], hit[4], grad.shape[0],
+                              lr_t=self.dense_opt.lr_t if self.dense_opt.capturable else None)
         self.iterations += 1
         return loss.detach()
 
@@ -193,3 +222,48 @@ class RecallSdpaTrainer(object):
             self.dense_opt.load_state_dict(state["dense"])
         for dim, st in state["bags"].items():
             self.bag_opts[dim][0].load_state_dict(st)
+
+
+class GraphedTrainStep(object):
+    """One training step recorded into a CUDA graph and replayed: the eager step issues ~350 launches from Python (forward
+    plan, autograd, two optimizers) and is bound by the host; the replay costs one launch.
+
+    The tensors of `batch`, `y_true` and `behaviour` given here are the graph's static inputs: refill them IN PLACE
+    (`.copy_`) between replays -- the standard CUDA-graph contract.  Shapes are fixed.  The step counters of both optimizers
+    live on the device (`KerasAdam.make_capturable`), so the bias correction keeps advancing under replay.
+        step = GraphedTrainStep(trainer, batch, y, behaviour);  loss = step()      # loss: 0-dim CUDA tensor, overwritten per replay
+    """
+
+    def __init__(self, trainer, batch, y_true, behaviour=None, warmup=3):
+        self.trainer = trainer
+        if trainer.dense_opt is None:
+            trainer.train_step(batch, y_true, behaviour)
+        if not trainer.dense_opt.capturable:
+            trainer.dense_opt.make_capturable()
+        dev = trainer.dense_opt.params[0].device
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):          # plans, workspaces and descriptor pools are built outside the capture
+                trainer.train_step(batch, y_true, behaviour)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = trainer.train_step(batch, y_true, behaviour)
+        # recording ran the Python of one step (host counters moved) but none of its kernels: take that step back
+        self._bump(-1)
+        self._keep = (batch, y_true, behaviour)
+
+    def _bump(self, by):
+        t = self.trainer
+        t.iterations += by
+        t.dense_opt.iterations += by
+        for group, _ in t.bag_opts.values():
+            group.iterations += by
+
+    def __call__(self):
+        self.graph.replay()
+        self._bump(1)
+        return self.loss

@@ -62,13 +62,13 @@ class AllGatherInbatchCE(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss):
         y, q, lse, *blocks = ctx.saved_tensors
-        up = float(grad_loss)
         dq = torch.zeros_like(q)
         da_all = []
-        for g in range(ctx.world):
-            gq, ga = ctx.ops.block_grads(q, blocks[g], y, lse, ctx.scale, up, g == ctx.rank)
+        for g in range(ctx.world):              # upstream = 1 in the kernels, applied on the device below (no host sync)
+            gq, ga = ctx.ops.block_grads(q, blocks[g], y, lse, ctx.scale, 1.0, g == ctx.rank)
             dq += gq
-            da_all.append(ga)
+            da_all.append(ga.mul_(grad_loss))
+        dq.mul_(grad_loss)
         # every rank holds a gradient for every rank's docs: sum them at the docs' owner
         if dist.get_backend(ctx.group) == "gloo":          # gloo has no reduce_scatter: all-reduce the stack, keep the own slice
             stack = torch.stack(da_all)

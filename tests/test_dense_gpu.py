@@ -407,6 +407,107 @@ def test_dense_forward_tc_strided_input_and_output_slot():
     assert torch.all(outw[:, :100] == 7.0) and torch.all(outw[:, 100 + N:] == 7.0)      # nothing outside the slot is touched
 
 
+@pytest.mark.parametrize("rows,in_dim,units", [(512, 8192, 256), (64, 40960, 192), (1888, 8192, 1024), (100, 1000, 68)])
+def test_dense_forward_split_k_matches_float64(rows, in_dim, units):
+    """A plain product with few output tiles and a long contraction (dW = X^T dZ) splits K over CTAs and sums the partial
+    products in order (rf_dense_forward_tc_ex); shapes that do not qualify take the single-pass kernel through the same entry."""
+    from recommendflow_b200.dense_ops import dense_forward
+    g = torch.Generator(device="cuda").manual_seed(rows + units)
+    x = torch.randn(rows, in_dim, device="cuda", generator=g)
+    wt = torch.randn(units, in_dim, device="cuda", generator=g)
+    split = int(nat.lib().rf_dense_tc_workspace_bytes(rows, in_dim, units)) > 0
+    assert split == ((rows, in_dim, units) != (1888, 8192, 1024))
+    before = nat.launch_count()
+    got = dense_forward(x, wt)
+    assert nat.launch_count() - before == (2 if split else 1)
+    want = x.double() @ wt.double().t()
+    # TF32 operands (2^-11 relative each), fp32 accumulation over in_dim terms of size ~1
+    np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=2e-2, atol=2e-3 * in_dim ** 0.5)
+    assert torch.equal(got, dense_forward(x, wt)), "ordered partial sums: run to run identical"
+
+
+@pytest.mark.parametrize("activation,with_norm", [("selu", True), ("relu", True), ("tanh", False), (None, True)])
+def test_tower_mlp_training_stage_gradients(activation, with_norm):
+    """The gradient-recording tower path (mlp._TrainStage: batch statistics folded into the tcgen05 GEMM, both backward
+    GEMMs on the same kernel, BatchNormalization backward in closed form) against the same layers run one torch op at a
+    time in float64 (Keras training=True semantics: biased batch variance, moving-average update)."""
+    import copy
+    from recommendflow_b200 import dense_ops
+    from recommendflow_b200.backend.blocks.mlp import BatchNormalization, create_mlp
+    torch.manual_seed(5)
+    B, d_in, units = 512, 96, [128, 64]
+    mlp = create_mlp(units, 0.0, activation, BatchNormalization(epsilon=1e-3) if with_norm else None, name="tower")
+    x = (torch.randn(B, d_in, device="cuda") * 0.7 + 0.2)
+    with torch.no_grad():
+        mlp(x)                                        # creates the variables
+    for p in mlp.parameters():
+        p.requires_grad_(True)
+        with torch.no_grad():
+            if p.dim() == 1:
+                p.add_(torch.rand_like(p) * 0.3)
+    ref = copy.deepcopy(mlp).double()
+    for m in list(mlp.modules()) + list(ref.modules()):
+        if isinstance(m, BatchNormalization):
+            m.batch_stats = True
+    w = torch.randn(B, units[-1], device="cuda")
+    xg = x.clone().requires_grad_(True)
+    before = nat.launch_count()
+    out = mlp(xg)
+    (out * w).sum().backward()
+    # per stage: forward = column statistics (2 launches, with a norm) + GEMM; backward = activation pass (2) + two GEMMs
+    # + BatchNormalization backward (3, with a norm); the dW GEMM (K = batch) may add its split-K summation launch
+    base = (10 if with_norm else 5) * len(units)
+    assert base <= nat.launch_count() - before <= base + len(units)
+    x64 = x.double().requires_grad_(True)
+    old = dense_ops.DEFAULT_PRECISION
+    dense_ops.DEFAULT_PRECISION = "fp32"              # the layer-by-layer path
+    normed = []
+    try:
+        h = x64
+        for layer in ref.layers:
+            h = layer(h)
+            if isinstance(layer, BatchNormalization):
+                h.retain_grad()
+                normed.append(h)
+    finally:
+        dense_ops.DEFAULT_PRECISION = old
+    (h * w.double()).sum().backward()
+    kinked = activation in ("selu", "relu")
+
+    def close(a, b, what, atol=None):
+        a, b = a.detach().double().cpu().numpy(), b.detach().cpu().numpy()
+        rtol, atol = 2e-2, (6e-3 * max(1e-6, float(np.abs(b).max())) if atol is None else atol)
+        if not kinked:
+            np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, err_msg=what)
+            return
+        # selu' and relu' jump at z = 0 (selu: 1.758 -> 1.051): a pre-activation within TF32 rounding (~1e-3) of zero lands on
+        # the other side of the jump than in float64 and changes that sample's whole dX row.  ~0.1 % of the B x units
+        # pre-activations are that close, so a few percent of the rows differ; the smooth cases of this test are exact.
+        ok = np.abs(a - b) <= atol + rtol * np.abs(b)
+        assert ok.mean() >= 0.93, (what, float(ok.mean()))
+        assert float(np.abs(a - b).mean()) <= max(atol, 5e-3 * float(np.abs(b).max())), what
+
+    close(out, h, "forward")
+    close(xg.grad, x64.grad, "dx")
+    got, want = dict(mlp.named_parameters()), dict(ref.named_parameters())
+    assert set(got) == set(want)
+    # d gamma / d beta are column sums over the batch of dXhat (* xn): the next stage's normalisation makes the loss (nearly)
+    # invariant to them, so the true sums cancel to ~0 while every summand carries TF32 rounding (2^-11 relative): the
+    # tolerance is set from the size of the summands, sqrt(sum_i dXhat_i^2), not from the size of the result
+    noise = {int(t.shape[1]): float(t.grad.pow(2).sum(dim=0).sqrt().max()) for t in normed}
+    # a bias in front of a normalisation has a gradient of exactly 0 (the batch mean removes it); what the kernels return there
+    # is fp32 summation noise, so every comparison also gets an absolute floor tied to the largest gradient of the stage stack
+    floor = 2e-3 * max(float(p.grad.abs().max()) for p in want.values())
+    for name in got:
+        assert got[name].grad is not None, name
+        atol = max(floor, 6e-3 * float(want[name].grad.abs().max()))
+        if "gamma_" in name or "beta_" in name:
+            atol = max(atol, (6e-2 if kinked else 2e-2) * noise[int(name.rsplit("_", 1)[1])])
+        close(got[name].grad, want[name].grad, name, atol)
+    for (n1, b1), (n2, b2) in zip(mlp.named_buffers(), ref.named_buffers()):        # moving statistics moved the same way
+        close(b1, b2, n1)
+
+
 def test_tower_mlp_fused_matches_layerwise_float64():
     """create_mlp([1024, 512, 256], 0.3, "selu", BatchNormalization(1e-6)) (dssm.py:25-26) at inference: the fused path
     (BN folded into each Dense, one tcgen05 launch per stage, l2 norm in the last epilogue) vs a float64 layer-by-layer

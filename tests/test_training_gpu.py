@@ -110,3 +110,72 @@ def test_checkpoint_round_trip_restores_weights_and_optimizer_state(golden_dir, 
     assert set(got) == set(want)
     for k in want:
         assert torch.equal(got[k], want[k]), k
+
+
+def test_graphed_train_step_replays_the_eager_step(golden_dir):
+    """training.GraphedTrainStep: the whole step (fused bag forward, towers, loss, autograd, both Adam updates with their
+    step counters on the device) recorded into ONE CUDA graph; replays on refilled static inputs follow the eager
+    trainer's losses and end on the same weights."""
+    from recommendflow_b200 import _native as nat
+    from recommendflow_b200.training import GraphedTrainStep
+    conf_path = os.path.join(golden_dir, "configs", "synth_recall_sdpa.yaml")
+    map_path = os.path.join(golden_dir, "configs", "synth_recall_sdpa.feature.map")
+
+    def fresh():
+        torch.manual_seed(4)
+        conf = Configuration(conf_path, slot_map_path=map_path)
+        keep = set(conf.features.user_feature_names[:3] + conf.features.ad_feature_names[:2])
+        for f in conf.features.features:
+            if f.is_hashing() and f.name not in keep:
+                f.working = False
+        model = RecallSdpa(conf, tower_units=(64, 32), behaviour_dim=32, num_heads=1)
+        for m in model.modules():
+            if hasattr(m, "rate"):
+                m.rate = 0.0
+        return model, RecallSdpaTrainer(model, learning_rate=5e-3)
+
+    rng = np.random.default_rng(21)
+    B, S, dm = 512, 10, 32
+
+    def make_batch(model):
+        item = rng.integers(0, 300, size=B)
+        batch = {n: StringColumn.from_lists([[f"{n[:4]}_{v:04d}"] for v in item]).to("cuda") for n in model.user_cols + model.ad_cols}
+        x = torch.from_numpy(rng.standard_normal((B, S, dm)).astype(np.float32)).cuda()
+        mask = torch.from_numpy((np.arange(S)[None, :, None] < rng.integers(1, S + 1, size=(B, 1, 1))).astype(np.float32)).cuda()
+        return batch, torch.ones(B, device="cuda"), (x, mask)
+
+    eager_model, eager = fresh()
+    batches = [make_batch(eager_model) for _ in range(5)]
+    b0, y0, beh0 = batches[0]
+    want = [float(eager.train_step(b0, y0, beh0)) for _ in range(3)]           # the graphed trainer's first step + 2 warm-up steps
+    want += [float(eager.train_step(b, y, beh)) for b, y, beh in batches[1:]]
+
+    model, trainer = fresh()
+    static = ({n: StringColumn(c.data.clone(), c.offsets.clone(), c.shape) for n, c in b0.items()}, y0.clone(),
+              (beh0[0].clone(), beh0[1].clone()))
+    step = GraphedTrainStep(trainer, *static, warmup=2)
+    assert trainer.iterations == 3
+    got = []
+    before = nat.launch_count()
+    for b, y, beh in batches[1:]:
+        for n, c in b.items():                                                 # refill the static inputs in place
+            static[0][n].data.copy_(c.data)
+            static[0][n].offsets.copy_(c.offsets)
+        static[1].copy_(y)
+        static[2][0].copy_(beh[0])
+        static[2][1].copy_(beh[1])
+        got.append(float(step()))
+    assert nat.launch_count() == before, "a replay goes through no host-side launch"
+    assert trainer.iterations == 3 + len(got) == eager.iterations
+    # the device-side step computes lr_t in float64 tensor ops and applies it as (m / den) * lr_t instead of addcdiv: last-bit
+    # differences per step, which Adam's sign-like update turns into a fraction of lr on the weights whose gradient is noise
+    np.testing.assert_allclose(got, want[3:], rtol=3e-3)
+    a, b = eager_model.state_dict(), model.state_dict()
+    assert set(a) == set(b)
+    lr, steps = 5e-3, trainer.iterations
+    for k in a:
+        diff = (b[k].double() - a[k].double()).abs()
+        if "moving_" in k:
+            np.testing.assert_allclose(b[k].cpu().numpy(), a[k].cpu().numpy(), rtol=5e-3, atol=1e-4, err_msg=k)
+        else:
+            assert float(diff.max()) <= lr * steps and float(diff.mean()) <= 0.05 * lr, (k, float(diff.max()), float(diff.mean()))

@@ -68,6 +68,13 @@ def main():
     out["launches_per_step"] = (nat.launch_count() - l0) / (steps + 2)
     out["embedding_adam"] = "lazy" if trainer.lazy else "keras (all rows decay)"
     out["loss_after"] = float(step())
+    if os.environ.get("GRAPH", "1") == "1":        # the same step recorded into one CUDA graph (training.GraphedTrainStep)
+        from recommendflow_b200.training import GraphedTrainStep
+        graphed = GraphedTrainStep(trainer, batch, y, (x, mask), warmup=2)
+        out["train_step_graphed_ms"] = timed(graphed, steps, warmup=2)
+        out["train_graphed_samples_per_s"] = B / (out["train_step_graphed_ms"] / 1e3)
+        out["loss_after_graphed"] = float(graphed())
+        step = graphed
     print(json.dumps(out))
     if os.environ.get("PROFILE"):          # where the step's time goes (kineto; not a timing source for the numbers above)
         from torch.profiler import ProfilerActivity, profile
