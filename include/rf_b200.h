@@ -306,6 +306,11 @@ typedef struct rf_adam_params {
     const float *d_lr_t;             /* NULL, or a device float holding lr * sqrt(1 - beta2^t) / (1 - beta1^t): read by the   */
                                      /* kernels instead of the value derived from `step` -- required when the call is being   */
                                      /* recorded into a CUDA graph (the host-side step would be frozen into the graph)        */
+    uint32_t *d_live_rows;           /* NULL, or a caller-owned device bitmap of ceil(sum table_rows / 32) + 1 words, zero before */
+                                     /* the first step and passed to EVERY step with the same table list (bit = running row   */
+                                     /* number over the tables in call order): the rows that ever received a gradient.  A row */
+                                     /* whose bit is clear still has m == v == 0, so the all-rows decay of non-lazy Adam       */
+                                     /* skips it without reading it (bit-identical results; all ones is always safe).          */
 } rf_adam_params;
 /* One table of a multi-table update.  All tables of a call share `dim`; sum of table_rows <= 2^32 - 1, */
 /* sum of n_keys <= 2^31 - 1.  grad_out: [batch, dim] view with row stride grad_stride (floats).         */
@@ -340,6 +345,12 @@ int rf_bag_backward_adam(const int64_t *d_ids, int64_t n_keys, const int32_t *d_
 int rf_sdpa_backward(const float *d_q, const float *d_k, const float *d_v, const float *d_mask,
                      const float *d_grad_out, int64_t n_batch_heads, int32_t seq_len, int32_t head_dim,
                      float *d_dq, float *d_dk, float *d_dv, void *stream);
+/* The same with q, k, v read at a row pitch of row_pitch floats (column windows of one fused q|k|v      */
+/* projection output) and dq, dk, dv written at grad_row_pitch; d_grad_out dense [n, seq_len, head_dim]. */
+/* head_dim and the pitches multiples of 4, 16-byte aligned buffers.                                     */
+int rf_sdpa_backward_strided(const float *d_q, const float *d_k, const float *d_v, int64_t row_pitch, const float *d_mask,
+                             const float *d_grad_out, int64_t n_batch_heads, int32_t seq_len, int32_t head_dim,
+                             float *d_dq, float *d_dk, float *d_dv, int64_t grad_row_pitch, void *stream);
 /* Gradient of batch_neg_sample_scaled_multi_class_ce_loss (match_losses.py:150-165) w.r.t. query   */
 /* and doc (either output may be NULL), times `upstream` (dL/d loss).  d_lse: the per-row            */
 /* log-sum-exp rf_inbatch_rowstats[_tc] produced for the same inputs.  dim <= 512.  Deterministic.   */
@@ -375,7 +386,8 @@ int64_t rf_tower_train_workspace_bytes(int64_t rows, int32_t dim);
 int rf_column_stats(const float *d_x, int64_t rows, int32_t dim, int64_t ldx, float *d_mean, float *d_var, float *d_x_t,
                     void *d_workspace, int64_t workspace_bytes, void *stream);
 /* dZ = dY * act'(z) with the derivative taken from the stage's OUTPUT y = act(z) (none, relu, selu, tanh, sigmoid);        */
-/* d_grad_pre [rows, units], d_grad_pre_t NULL or [units, rows] (dZ transposed), d_grad_bias [units] = column sums of dZ.  */
+/* d_grad_pre [rows, units] (may be NULL for activation none: dZ is dY), d_grad_pre_t NULL or [units, rows] (dZ           */
+/* transposed), d_grad_bias [units] = column sums of dZ.                                                                  */
 int rf_activation_backward(const float *d_grad_out, const float *d_out, int64_t rows, int32_t units, int activation,
                            float *d_grad_pre, float *d_grad_pre_t, float *d_grad_bias, void *d_workspace,
                            int64_t workspace_bytes, void *stream);

@@ -45,7 +45,8 @@ class ShardCtx(C.Structure):
 
 class AdamParams(C.Structure):
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("epsilon", C.c_float),
-                ("step", C.c_int64), ("lazy", C.c_int32), ("reserved", C.c_int32), ("d_lr_t", C.c_void_p)]
+                ("step", C.c_int64), ("lazy", C.c_int32), ("reserved", C.c_int32), ("d_lr_t", C.c_void_p),
+                ("d_live_rows", C.c_void_p)]
 
 
 class AdamField(C.Structure):
@@ -165,6 +166,9 @@ def lib():
         L.rf_inbatch_softmax_ce_backward_tc.restype = C.c_int
         L.rf_inbatch_softmax_ce_backward_tc.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_int,
                                                                           C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rf_sdpa_backward_strided.restype = C.c_int
+        L.rf_sdpa_backward_strided.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                               C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.rf_dense_tc_workspace_bytes.restype = C.c_int64
         L.rf_dense_tc_workspace_bytes.argtypes = [C.c_int64, C.c_int32, C.c_int32]
         L.rf_dense_forward_tc_ex.restype = C.c_int

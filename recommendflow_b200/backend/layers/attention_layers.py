@@ -130,6 +130,13 @@ class MultiHeadAttention(Layer):
                 w, b = self._fused_qkv_weights()
                 qkv = dense_ops.dense_forward(q, w, b, None)
                 return dense_ops.sdpa_fused_qkv(qkv, mask, self.d_model)
+            if q.shape[0] * q.shape[1] % 4 == 0:
+                # the same under autograd: the three kernels are concatenated on the tape (the gradient splits back to wq / wk /
+                # wv), one differentiable tensor-core Dense, and the attention backward returns dq | dk | dv as its one dY
+                wf = torch.cat([d.kernel for d in (self.wq, self.wk, self.wv)], dim=1)
+                bf = torch.cat([d.bias for d in (self.wq, self.wk, self.wv)])
+                qkv = dense_ops.dense_autograd(q, wf, bf, None)
+                return dense_ops.sdpa_fused_qkv_autograd(qkv, mask, self.d_model)
         q, k, v = self.wq(q), self.wk(k), self.wv(v)                       # (B, S, d_model)
         seq_len, d_model = q.shape[1], q.shape[2]
         depth = d_model // self.num_heads

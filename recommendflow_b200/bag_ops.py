@@ -322,6 +322,8 @@ class BagAdamGroup(object):
             dst.copy_(src)
         for dst, src in zip(self.v, state["v"]):
             dst.copy_(src)
+        if getattr(self, "_live", None) is not None:
+            self._live.fill_(-1)          # loaded moments may be non-zero anywhere: every row counts as touched (always safe)
 
     def apply_fused(self, ids, grad, cols, combiners, bag_lens, batch, lr_t=None):
         """The training loop's form of `apply`: table i gathered the keys `ids[i]` (int64 [batch * bag_lens[i]], dense bags)
@@ -359,9 +361,16 @@ class BagAdamGroup(object):
         fz = self._fused
         fz["view"][:, fz["col"]] = np.uint64(g.data_ptr()) + fz["cols4"]
         self.iterations += 1
-        p = nat.AdamParams(lr=self.learning_rate, beta1=self.beta_1, beta2=self.beta_2, epsilon=self.epsilon,
-                           step=self.iterations, lazy=1 if self.lazy else 0, d_lr_t=None if lr_t is None else lr_t.data_ptr())
         dev = self.tables[0].device
+        if getattr(self, "_live", None) is None and not self.lazy:
+            # rows that ever received a gradient (one bit per row over all tables): the all-rows decay skips the others unread.
+            # The moments start at zero; a group restored from a checkpoint marks everything (load_state_dict)
+            words = (sum(t.shape[0] for t in self.tables) + 31) // 32 + 1
+            fresh = self.iterations == 1 and all(float(m.abs().max()) == 0.0 for m in self.m[:1])
+            self._live = torch.zeros(words, dtype=torch.int32, device=dev) if fresh else torch.full((words,), -1, dtype=torch.int32, device=dev)
+        p = nat.AdamParams(lr=self.learning_rate, beta1=self.beta_1, beta2=self.beta_2, epsilon=self.epsilon,
+                           step=self.iterations, lazy=1 if self.lazy else 0, d_lr_t=None if lr_t is None else lr_t.data_ptr(),
+                           d_live_rows=None if self.lazy else self._live.data_ptr())
         with torch.cuda.device(dev):
             if getattr(self, "_fused_need", None) is None or self._fused_need[0] != sig:
                 need = int(nat.lib().rf_bag_adam_multi_workspace_bytes(fz["arr"], n))

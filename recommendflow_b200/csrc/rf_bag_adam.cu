@@ -105,6 +105,8 @@ struct Job {
     int per;              // dim / 4
     int64_t batch;
     uint32_t *bitmap;     // over the global rows; NULL in lazy mode
+    uint32_t *live;       // persistent across steps (caller-owned, rf_adam_params.d_live_rows): rows that EVER received a
+                          // gradient; a row whose bit is clear has m == v == 0 and is skipped by the decay pass unread.  NULL: none
 };
 
 // last field whose first global row (BY_ROW) / first global key position is <= x
@@ -176,6 +178,7 @@ __device__ __forceinline__ void apply_row(const Job &j, const DevAdamField &f, u
     reinterpret_cast<float4 *>(f.m)[at] = m;
     reinterpret_cast<float4 *>(f.v)[at] = v;
     if (c == 0 && j.bitmap) atomicOr(j.bitmap + (grow >> 5), 1u << (grow & 31));
+    if (c == 0 && j.live && !((j.live[grow >> 5] >> (grow & 31)) & 1u)) atomicOr(j.live + (grow >> 5), 1u << (grow & 31));
 }
 
 // one lane group per unique row; *n_unique is read from device memory (written by the select)
@@ -227,29 +230,38 @@ adam_heavy_kernel(const uint32_t *__restrict__ keys, const int32_t *__restrict__
     }
 }
 
-// every row whose bit is clear: decay the moments and move the row (Keras' non-lazy sparse Adam);
-// blockIdx.y = table
+// every row whose bit is clear: decay the moments and move the row (Keras' non-lazy sparse Adam); blockIdx.y = table.
+// A warp takes 32 consecutive rows: the touched / live bits of those rows are two (broadcast) word loads and a funnel shift,
+// and only the lanes whose row is due look at m and v (the per-element version paid a divide and two dependent loads for
+// each of the 91 M float4 of C3's tables, 0.3 ms with 8 % of the rows live).  Both bitmaps carry one spare word at the end.
 __global__ void __launch_bounds__(kAdamThreads) adam_dense_kernel(Job j, AdamC k_in) {
     const AdamC k = resolved(k_in);
     const DevAdamField &f = j.fields[blockIdx.y];
-    const int64_t total = f.rows * j.per;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool narrow = total <= (int64_t)UINT32_MAX;          // 32-bit row arithmetic (a 64-bit divide per element costs more than the loads)
-    // (the loop is HBM-bound as it stands: 456 tables of 100000 x 8 are 1.46 GB per array, m and v alone are 2.9 GB = 0.45 ms;
-    // a 4-way unrolled variant measured 0.55 ms against 0.49 ms for this one)
-    for (int64_t e = (int64_t)blockIdx.x * kAdamThreads + threadIdx.x; e < total; e += (int64_t)gridDim.x * kAdamThreads) {
-        const uint32_t grow = f.rbase + (narrow ? (uint32_t)e / (uint32_t)j.per : (uint32_t)(e / j.per));
-        if ((__ldg(j.bitmap + (grow >> 5)) >> (grow & 31)) & 1u) continue;
-        float4 m = reinterpret_cast<float4 *>(f.m)[e], v = reinterpret_cast<float4 *>(f.v)[e];
-        // a row that never received a gradient (or whose moments have decayed to zero) does not move: with m == 0 and v == 0
-        // the update is w -= 0, m = 0, v = 0 bit for bit, so neither the row nor its moments are touched -- two reads instead
-        // of three reads and three writes for the cold majority of a large table
-        if (m.x == 0.f && m.y == 0.f && m.z == 0.f && m.w == 0.f && v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
-        float4 w = reinterpret_cast<float4 *>(f.w)[e];
-        adam_vec(w, m, v, zero, false, k);
-        reinterpret_cast<float4 *>(f.w)[e] = w;
-        reinterpret_cast<float4 *>(f.m)[e] = m;
-        reinterpret_cast<float4 *>(f.v)[e] = v;
+    const int lane = threadIdx.x & 31;
+    const int64_t n_blocks = (f.rows + 31) >> 5;
+    const int64_t warp0 = ((int64_t)blockIdx.x * kAdamThreads + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * kAdamThreads) >> 5;
+    const int per = j.per, span = 32 * per;
+    for (int64_t blk = warp0; blk < n_blocks; blk += n_warps) {
+        const int64_t row0 = blk << 5;
+        const uint32_t g = f.rbase + (uint32_t)row0, wi = g >> 5, sh = g & 31;
+        uint32_t due = ~__funnelshift_r(__ldg(j.bitmap + wi), __ldg(j.bitmap + wi + 1), sh);         // not updated this step
+        if (j.live) due &= __funnelshift_r(j.live[wi], j.live[wi + 1], sh);                          // and ever touched
+        if (f.rows - row0 < 32) due &= (1u << (int)(f.rows - row0)) - 1u;
+        if (due == 0) continue;
+        for (int idx = lane; idx < span; idx += 32) {
+            const int r = idx / per;
+            if (!((due >> r) & 1u)) continue;
+            const int64_t e = row0 * per + idx;
+            float4 m = reinterpret_cast<float4 *>(f.m)[e], v = reinterpret_cast<float4 *>(f.v)[e];
+            // moments that are (still, or again after underflow) zero leave the row where it is: w -= 0, m = 0, v = 0 bit for bit
+            if (m.x == 0.f && m.y == 0.f && m.z == 0.f && m.w == 0.f && v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
+            float4 w = reinterpret_cast<float4 *>(f.w)[e];
+            adam_vec(w, m, v, zero, false, k);
+            reinterpret_cast<float4 *>(f.w)[e] = w;
+            reinterpret_cast<float4 *>(f.m)[e] = m;
+            reinterpret_cast<float4 *>(f.v)[e] = v;
+        }
     }
 }
 
@@ -294,7 +306,7 @@ int carve(Workspace &ws, char *base, int n_fields, int64_t n_keys, int64_t rows)
     ws.heads = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * ((size_t)n + 1)));
     ws.counters = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * 4));
     ws.heavy = reinterpret_cast<int2 *>(take(sizeof(int2) * ((size_t)n / kHeavyRun + 1)));
-    ws.bitmap_bytes = sizeof(uint32_t) * (size_t)((rows + 31) / 32);
+    ws.bitmap_bytes = sizeof(uint32_t) * (size_t)((rows + 31) / 32 + 1);       // + 1: the funnel shift reads word + 1
     ws.bitmap = reinterpret_cast<uint32_t *>(take(ws.bitmap_bytes));
     ws.cub_bytes = sort_bytes > select_bytes ? sort_bytes : select_bytes;
     ws.cub_temp = take(ws.cub_bytes);
@@ -416,7 +428,7 @@ int rf_bag_backward_adam_multi(const rf_adam_field *fields, int n_fields, int64_
         // the descriptors travel through a pageable staging copy: the driver snapshots `dev` before returning
         RF_CUDA(cudaMemcpyAsync(ws.fields, dev.data(), sizeof(DevAdamField) * (size_t)n_fields, cudaMemcpyHostToDevice, st));
     }
-    Job job{ws.fields, n_fields, dim / 4, batch, lazy ? nullptr : ws.bitmap};
+    Job job{ws.fields, n_fields, dim / 4, batch, lazy ? nullptr : ws.bitmap, lazy ? nullptr : params->d_live_rows};
     if (!lazy) RF_CUDA(cudaMemsetAsync(ws.bitmap, 0, ws.bitmap_bytes, st));
     int launches = 0;
     if (n_keys > 0) {
@@ -442,7 +454,7 @@ int rf_bag_backward_adam_multi(const rf_adam_field *fields, int n_fields, int64_
     if (!lazy) {
         int64_t max_rows = 0;
         for (int i = 0; i < n_fields; ++i) max_rows = fields[i].table_rows > max_rows ? fields[i].table_rows : max_rows;
-        int64_t blocks = (max_rows * job.per + kAdamThreads - 1) / kAdamThreads;
+        int64_t blocks = ((max_rows + 31) / 32 + kAdamThreads / 32 - 1) / (kAdamThreads / 32);      // one warp per 32 rows
         const int64_t cap = ((int64_t)sms * 16 + n_fields - 1) / n_fields;
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;

@@ -27,7 +27,7 @@ extern std::atomic<int64_t> g_launches;
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kSplitRows = 256;
+constexpr int kSplitRows = 256;      // rows per CTA: many CTAs keep the loads in flight; the finalize spreads the splits over 8 warps
 constexpr float kSeluScale = 1.0507009873554805f, kSeluAlpha = 1.6732632423543772f;
 
 __device__ __forceinline__ float act_grad(int act, float y) {
@@ -68,6 +68,7 @@ struct PassArgs {
     int64_t rows;
     int dim;
     int act;
+    int split_rows;
 };
 
 template <int MODE>
@@ -77,8 +78,8 @@ __global__ void __launch_bounds__(kThreads) column_pass_kernel(PassArgs p) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int c0 = blockIdx.x * 32, c = c0 + lane;
     const bool col_ok = c < p.dim;
-    const int64_t r_begin = (int64_t)blockIdx.y * kSplitRows;
-    const int64_t r_end = r_begin + kSplitRows < p.rows ? r_begin + kSplitRows : p.rows;
+    const int64_t r_begin = (int64_t)blockIdx.y * p.split_rows;
+    const int64_t r_end = r_begin + p.split_rows < p.rows ? r_begin + p.split_rows : p.rows;
     float s1 = 0.f, s2 = 0.f;
     float shift = 0.f, mean = 0.f, rstd = 0.f;
     if (MODE == 0 && col_ok) shift = __ldg(p.a + c);
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(kThreads) column_pass_kernel(PassArgs p) {
                 t = va[k] * act_grad(p.act, vb[k]);
                 if (ok) {
                     s1 += t;
-                    p.out[r * p.dim + c] = t;
+                    if (p.out) p.out[r * p.dim + c] = t;
                 }
             } else {
                 if (ok) {
@@ -144,13 +145,20 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreads) column_finalize_kernel(const float *__restrict__ partials, int splits, int dim, int64_t rows,
                                                                    const float *__restrict__ x_row0, float *__restrict__ out0,
                                                                    float *__restrict__ out1) {
-    const int c = blockIdx.x * kThreads + threadIdx.x;
-    if (c >= dim) return;
+    // one CTA per 32 columns: warp w adds splits w, w + 8, ... (in order), the 8 warp sums are added in order
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    const bool ok = c < dim;
     float a = 0.f, b = 0.f;
-    for (int s = 0; s < splits; ++s) {
-        a += partials[((int64_t)s * 2 + 0) * dim + c];
-        if (MODE != 1) b += partials[((int64_t)s * 2 + 1) * dim + c];
-    }
+    if (ok)
+        for (int s = w; s < splits; s += 8) {
+            a += partials[((int64_t)s * 2 + 0) * dim + c];
+            if (MODE != 1) b += partials[((int64_t)s * 2 + 1) * dim + c];
+        }
+    a = cta_column_sum(a, red);
+    if (MODE != 1) b = cta_column_sum(b, red);
+    if (w != 0 || !ok) return;
     if (MODE == 0) {
         const float inv = 1.f / (float)rows, m = a * inv;
         out0[c] = x_row0[c] + m;
@@ -186,7 +194,11 @@ __global__ void __launch_bounds__(kThreads) batchnorm_dx_kernel(const float *__r
     }
 }
 
-inline int splits_of(int64_t rows) { return (int)((rows + kSplitRows - 1) / kSplitRows); }
+inline int split_rows_of(int64_t) { return kSplitRows; }
+inline int splits_of(int64_t rows) {
+    const int64_t r = split_rows_of(rows);
+    return (int)((rows + r - 1) / r);
+}
 
 int check_ws(int64_t rows, int dim, const void *ws, int64_t ws_bytes) {
     const int64_t need = rf_tower_train_workspace_bytes(rows, dim);
@@ -214,10 +226,10 @@ int rf_column_stats(const float *d_x, int64_t rows, int32_t dim, int64_t ldx, fl
     int rc = check_ws(rows, dim, d_workspace, workspace_bytes);
     if (rc != RF_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    PassArgs p{d_x, nullptr, ldx, 0, nullptr, d_x_t, nullptr, nullptr, static_cast<float *>(d_workspace), rows, dim, 0};
+    PassArgs p{d_x, nullptr, ldx, 0, nullptr, d_x_t, nullptr, nullptr, static_cast<float *>(d_workspace), rows, dim, 0, split_rows_of(rows)};
     const int splits = splits_of(rows);
     column_pass_kernel<0><<<dim3((unsigned)((dim + 31) / 32), (unsigned)splits), kThreads, 0, st>>>(p);
-    column_finalize_kernel<0><<<(dim + kThreads - 1) / kThreads, kThreads, 0, st>>>(p.partials, splits, dim, rows, d_x, d_mean, d_var);
+    column_finalize_kernel<0><<<(dim + 31) / 32, kThreads, 0, st>>>(p.partials, splits, dim, rows, d_x, d_mean, d_var);
     RF_CUDA(cudaGetLastError());
     g_launches.fetch_add(2);
     return RF_OK;
@@ -228,16 +240,16 @@ int rf_activation_backward(const float *d_grad_out, const float *d_out, int64_t 
     if (rows <= 0 || units <= 0) return set_error(RF_ERR_INVALID, "rf_activation_backward: bad shape");
     if (activation < RF_ACT_NONE || activation > RF_ACT_SIGMOID)
         return set_error(RF_ERR_UNSUPPORTED, "rf_activation_backward: the derivative is taken from the output; activation %d is not covered", activation);
-    if (!d_grad_out || !d_grad_pre || !d_grad_bias || (activation != RF_ACT_NONE && !d_out))
+    if (!d_grad_out || !d_grad_bias || (activation != RF_ACT_NONE && (!d_out || !d_grad_pre)))
         return set_error(RF_ERR_INVALID, "rf_activation_backward: NULL buffer");
     int rc = check_ws(rows, units, d_workspace, workspace_bytes);
     if (rc != RF_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     PassArgs p{d_grad_out, d_out ? d_out : d_grad_out, units, units, d_grad_pre, d_grad_pre_t, nullptr, nullptr,
-               static_cast<float *>(d_workspace), rows, units, activation};
+               static_cast<float *>(d_workspace), rows, units, activation, split_rows_of(rows)};
     const int splits = splits_of(rows);
     column_pass_kernel<1><<<dim3((unsigned)((units + 31) / 32), (unsigned)splits), kThreads, 0, st>>>(p);
-    column_finalize_kernel<1><<<(units + kThreads - 1) / kThreads, kThreads, 0, st>>>(p.partials, splits, units, rows, nullptr, d_grad_bias, nullptr);
+    column_finalize_kernel<1><<<(units + 31) / 32, kThreads, 0, st>>>(p.partials, splits, units, rows, nullptr, d_grad_bias, nullptr);
     RF_CUDA(cudaGetLastError());
     g_launches.fetch_add(2);
     return RF_OK;
@@ -252,10 +264,10 @@ int rf_batchnorm_backward(const float *d_grad_normed, const float *d_x, int64_t 
     int rc = check_ws(rows, dim, d_workspace, workspace_bytes);
     if (rc != RF_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    PassArgs p{d_grad_normed, d_x, dim, ldx, nullptr, nullptr, d_mean, d_rstd, static_cast<float *>(d_workspace), rows, dim, 0};
+    PassArgs p{d_grad_normed, d_x, dim, ldx, nullptr, nullptr, d_mean, d_rstd, static_cast<float *>(d_workspace), rows, dim, 0, split_rows_of(rows)};
     const int splits = splits_of(rows);
     column_pass_kernel<2><<<dim3((unsigned)((dim + 31) / 32), (unsigned)splits), kThreads, 0, st>>>(p);
-    column_finalize_kernel<2><<<(dim + kThreads - 1) / kThreads, kThreads, 0, st>>>(p.partials, splits, dim, rows, nullptr, d_grad_beta, d_grad_gamma);
+    column_finalize_kernel<2><<<(dim + 31) / 32, kThreads, 0, st>>>(p.partials, splits, dim, rows, nullptr, d_grad_beta, d_grad_gamma);
     int64_t blocks = (rows * (dim / 4) + kThreads - 1) / kThreads;
     if (blocks > 148 * 16) blocks = 148 * 16;
     batchnorm_dx_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(d_grad_normed, d_x, ldx, d_mean, d_rstd, d_scale, d_grad_beta, d_grad_gamma,

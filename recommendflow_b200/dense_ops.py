@@ -98,16 +98,18 @@ def column_stats(x, want_transpose=False):
 
 
 def activation_backward(dy, y, activation):
-    """(dZ, dZ^T, db) from dY and the stage output y (rf_activation_backward)."""
+    """(dZ, dZ^T, db) from dY and the stage output y (rf_activation_backward).  Without an activation dZ is dY itself."""
     rows, units = dy.shape
     dy = dy if dy.is_contiguous() else dy.contiguous()
-    dz = torch.empty(rows, units, dtype=torch.float32, device=dy.device)
+    plain = activation in (None, "linear")
+    dz = dy if plain else torch.empty(rows, units, dtype=torch.float32, device=dy.device)
     dzt = torch.empty(units, rows, dtype=torch.float32, device=dy.device)
     db = torch.empty(units, dtype=torch.float32, device=dy.device)
     ws, need = _tower_ws(rows, units, dy.device)
     with torch.cuda.device(dy.device):
-        nat.check(nat.lib().rf_activation_backward(dy.data_ptr(), y.data_ptr(), rows, units, nat.ACTIVATION[activation], dz.data_ptr(),
-                                                   dzt.data_ptr(), db.data_ptr(), ws.data_ptr(), need, _stream(dy.device)))
+        nat.check(nat.lib().rf_activation_backward(dy.data_ptr(), None if plain else y.data_ptr(), rows, units, nat.ACTIVATION[activation],
+                                                   None if plain else dz.data_ptr(), dzt.data_ptr(), db.data_ptr(), ws.data_ptr(), need,
+                                                   _stream(dy.device)))
     return dz, dzt, db
 
 
@@ -297,6 +299,69 @@ class InbatchSoftmaxCeFunction(torch.autograd.Function):
         gq, gd = inbatch_softmax_ce_backward(q, d, y, lse, ctx.scale, 1.0, ctx.needs_input_grad[1],
                                              ctx.needs_input_grad[2], precision="fp32" if ctx.precision == "fp32" else None)
         return None, (None if gq is None else gq.mul_(grad_loss)), (None if gd is None else gd.mul_(grad_loss)), None, None
+
+
+class DenseFunction(torch.autograd.Function):
+    """act(x W + b) with all three products on the tcgen05 Dense kernel: forward (fused bias + activation), dX = dZ W^T,
+    dW = X^T dZ (split-K: the contraction runs over the rows); dZ^T and db come out of one pass over dY."""
+
+    @staticmethod
+    def forward(ctx, x, kernel, bias, activation):
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, x.shape[-1])
+        x2 = x2 if x2.stride(1) == 1 and x2.stride(0) % 4 == 0 and x2.data_ptr() % 16 == 0 else x2.contiguous()
+        y = dense_forward(x2, kernel.t().contiguous(), bias, activation)
+        ctx.activation, ctx.lead = activation, lead
+        ctx.save_for_backward(x2, y, kernel)
+        return y.view(*lead, kernel.shape[1])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, y, kernel = ctx.saved_tensors
+        dz, dzt, db = activation_backward(dy.reshape(-1, dy.shape[-1]), y, ctx.activation)
+        dx = dense_forward(dz, kernel, None, None).view(*ctx.lead, kernel.shape[0]) if ctx.needs_input_grad[0] else None
+        dw = dense_forward(x2.t().contiguous(), dzt, None, None)
+        return dx, dw, db, None
+
+
+def dense_autograd(x, kernel, bias, activation=None):
+    """Differentiable Keras Dense (kernel [in, units]) on the tensor cores; activation: None, relu, selu, tanh or sigmoid."""
+    return DenseFunction.apply(x, kernel, bias, activation)
+
+
+class SdpaFusedQkvFunction(torch.autograd.Function):
+    """`sdpa_fused_qkv` with its backward: the gradient comes out as ONE [..., S, 3 * dh] buffer (dq | dk | dv side by side,
+    rf_sdpa_backward_strided), i.e. directly the dY of the fused projection."""
+
+    @staticmethod
+    def forward(ctx, qkv, mask, dh):
+        qkv = qkv.contiguous()
+        ctx.dh = dh
+        ctx.save_for_backward(qkv, mask)
+        return sdpa_fused_qkv(qkv, mask, dh)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        qkv, mask = ctx.saved_tensors
+        dh, S = ctx.dh, qkv.shape[-2]
+        g = _f32(grad_out, "grad_out").contiguous()
+        nb = qkv.numel() // (S * 3 * dh)
+        m = None
+        if mask is not None:
+            m = _f32(mask, "mask")
+            if m.dim() == qkv.dim() and m.shape[-1] == 1:
+                m = m[..., 0]
+            m = m.expand(qkv.shape[:-1]).contiguous()
+        dqkv = torch.empty_like(qkv)
+        p, d = qkv.data_ptr(), dqkv.data_ptr()
+        with torch.cuda.device(qkv.device):
+            nat.check(nat.lib().rf_sdpa_backward_strided(p, p + 4 * dh, p + 8 * dh, 3 * dh, None if m is None else m.data_ptr(), g.data_ptr(),
+                                                         nb, S, dh, d, d + 4 * dh, d + 8 * dh, 3 * dh, _stream(qkv.device)))
+        return dqkv, None, None
+
+
+def sdpa_fused_qkv_autograd(qkv, mask, dh):
+    return SdpaFusedQkvFunction.apply(qkv, mask, dh)
 
 
 def sdpa_autograd(q, k, v, mask=None, precision=None):

@@ -79,7 +79,7 @@ def test_header_is_plain_c_and_ctypes_structs_match_it(tmp_path):
                                                 "int_mask_value", "out", "out_stride", "ids_out", "mask_bytes", "mask_len"]),
               "rf_shard_ctx": (nat.ShardCtx, ["rank", "world", "max_batch", "max_keys", "dim", "peer_exchange", "peer_signals"]),
               "rf_vocab_desc": (nat.VocabDesc, ["term_bytes", "term_offsets", "term_ints", "slots", "capacity", "n_terms"]),
-              "rf_adam_params": (nat.AdamParams, ["lr", "beta1", "beta2", "epsilon", "step", "lazy", "d_lr_t"]),
+              "rf_adam_params": (nat.AdamParams, ["lr", "beta1", "beta2", "epsilon", "step", "lazy", "d_lr_t", "d_live_rows"]),
               "rf_example_column": (nat.ExampleColumn, ["name", "name_len", "kind", "n_values", "n_bytes", "row_counts", "bytes_out",
                                                         "value_offsets", "floats_out", "ints_out"]),
               "rf_adam_field": (nat.AdamField, ["ids", "bag_offsets", "n_keys", "bag_len", "combiner", "grad_out", "grad_stride",

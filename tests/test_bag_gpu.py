@@ -437,3 +437,36 @@ def test_backward_adam_multi_table_single_pass(lazy):
                 np.testing.assert_allclose(got[~ok], want[~ok], rtol=2e-4, atol=1e-6, err_msg=f"{name} table {i} step {step}")
                 want[~ok] = got[~ok]
     assert nat.launch_count() - before == 3 * (3 if lazy else 4)              # per step: prep, rows, heavy (+ dense)
+
+
+def test_apply_fused_keras_adam_with_live_row_bitmap_is_bit_exact():
+    """BagAdamGroup.apply_fused (the training loop's entry: one fused gradient buffer, cached descriptors) keeps a bitmap of
+    the rows that ever received a gradient, and the all-rows decay of Keras' non-lazy Adam skips the others without reading
+    them.  Every table, both moments: bit for bit what the oracle's full pass gives, over steps that touch new rows."""
+    from recommendflow_b200.bag_ops import BagAdamGroup
+    rng = np.random.default_rng(77)
+    D, B = 8, 256
+    sizes, lens, combs = [5003, 1009, 40000], [3, 1, 2], ["sum", "avg", "sum"]
+    host = [tables(rng, 1, n, D)[0] for n in sizes]
+    ms, vs = [np.zeros_like(w) for w in host], [np.zeros_like(w) for w in host]
+    devs = [torch.from_numpy(w.copy()).cuda() for w in host]
+    group = BagAdamGroup(devs, learning_rate=2e-3)
+    ids_dev = [torch.zeros(B * L, dtype=torch.int64, device="cuda") for L in lens]       # static id buffers, refilled per step
+    for step in range(1, 6):
+        g_all = rng.normal(size=(B, 3 * D)).astype(np.float32)
+        dev_g = torch.from_numpy(g_all).cuda()
+        for i, (n, L) in enumerate(zip(sizes, lens)):
+            ids = rng.integers(0, min(n, 300 * step), size=B * L)                          # the touched set grows step by step
+            ids_dev[i].copy_(torch.from_numpy(ids))
+            oracle.bag_backward_adam(ids, np.ascontiguousarray(g_all[:, i * D:(i + 1) * D]), host[i], ms[i], vs[i], step, lr=2e-3,
+                                     combiner=combs[i], L=L)
+        group.apply_fused(ids_dev, dev_g, [0, D, 2 * D], combs, lens, B)
+        live = np.unpackbits(group._live.cpu().numpy().view(np.uint8), bitorder="little")
+        base = 0
+        for i, n in enumerate(sizes):
+            touched = (np.abs(ms[i]).sum(axis=1) > 0) | (np.abs(vs[i]).sum(axis=1) > 0)
+            assert np.array_equal(live[base:base + n].astype(bool) | ~touched, np.ones(n, dtype=bool)), "every row with a moment is marked"
+            assert live[base:base + n].sum() < n, "and cold rows stay unmarked"
+            base += n
+            for name, got, want in (("w", devs[i], host[i]), ("m", group.m[i], ms[i]), ("v", group.v[i], vs[i])):
+                assert np.array_equal(got.cpu().numpy().view(np.uint32), want.view(np.uint32)), (name, i, step)

@@ -15,16 +15,23 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
-    args = ap.parse_args()
     import torch
     from recommendflow_b200.dense_ops import dense_forward
+    ap.add_argument("--train", action="store_true", help="the products of one C3 training step (forward, dX, dW, CE backward)")
+    args = ap.parse_args()
     shapes = [(8192, 1888, 1024, "selu"), (8192, 1024, 512, "selu"), (8192, 512, 256, "selu"), (409600, 64, 64, None),
               (65536, 1888, 1024, "selu")]
+    if args.train:      # (rows, contraction, columns): dX = dZ W^T, dW = X^T dZ (contraction over the batch), q|k|v projection, CE slab products
+        shapes = [(8192, 1024, 1888, None), (8192, 512, 1024, None), (8192, 256, 512, None),
+                  (1888, 8192, 1024, None), (1024, 8192, 512, None), (512, 8192, 256, None),
+                  (409600, 64, 192, "bias"), (409600, 192, 64, None), (64, 409600, 192, None),
+                  (8192, 256, 8192, None), (8192, 8192, 256, None)]
     out = {}
     for M, K, N, act in shapes:
         x = torch.randn(M, K, device="cuda")
         w = torch.randn(N, K, device="cuda") * 0.02
-        b = torch.zeros(N, device="cuda")
+        b = torch.zeros(N, device="cuda") if act is not None else None
+        act = None if act == "bias" else act
         y = torch.empty(M, N, device="cuda")
         for _ in range(3):
             dense_forward(x, w, b, act, out=y)
