@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-c4", action="store_true", help="skip the row-sharded C4 measurement appended to the line")
     ap.add_argument("--no-c3", action="store_true", help="skip the C3 end-to-end forward appended to the line (N = 1)")
+    ap.add_argument("--no-train", action="store_true", help="skip the C3 training step appended to the line (N = 1)")
     return ap.parse_args()
 
 
@@ -680,12 +681,19 @@ def run_ours(args):
     if not args.no_c3 and name == "c2" and world == 1:
         c3 = run_c3full(dev, 20, 5, with_cpu=not args.no_cpu_baseline)
 
+    # ---- C3 training step (forward + backward + Keras Adam on every variable), eager and as one CUDA graph ----
+    train = None
+    if not args.no_train and name == "c2" and world == 1:
+        torch.cuda.empty_cache()
+        from tools.bench_train import run as train_run
+        train = train_run(steps=10)
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 pooling / u64 hashing", "data": "synthetic", "config": workload_config(name, world),
                 "gpu_launches": int(launches), "clocks": clocks.summary(), "e2e": e2e, "roofline": roofline,
-                "cpu_baseline": cpu, "parity_check": parity, "sharded_c4": c4, "c3full": c3}
+                "cpu_baseline": cpu, "parity_check": parity, "sharded_c4": c4, "c3full": c3, "train_c3": train}
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)

@@ -158,13 +158,28 @@ __global__ void __launch_bounds__(256) round_tf32_kernel(const float *__restrict
     }
 }
 
-// fp32 -> bf16, round to nearest even (the bf16 tensor-core variant's operand copies)
-__global__ void __launch_bounds__(256) to_bf16_kernel(const float *__restrict__ in, unsigned short *__restrict__ out, int64_t n) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        unsigned short r;
-        asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(r) : "f"(in[i]));
-        out[i] = r;
+// The bf16 variant's whole pre-pass in ONE launch (it was three: two conversions and the diagonal; at B = 8192 the launches
+// around the 36 us tensor-core kernel cost almost as much as the kernel): one warp per row reads q_i and d_i once, writes both
+// bf16 copies and leaves diag[i] = q_i . d_i in exact fp32, summed exactly as rowdot_kernel does.
+__global__ void __launch_bounds__(256) prep_bf16_kernel(const float *__restrict__ q, const float *__restrict__ d, int B, int Dt,
+                                                        unsigned short *__restrict__ q16, unsigned short *__restrict__ d16,
+                                                        float *__restrict__ diag) {
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= B) return;
+    float acc = 0.f;
+    for (int k = lane; k < Dt; k += 32) {
+        const float a = q[(size_t)row * Dt + k], b = d[(size_t)row * Dt + k];
+        unsigned short ra, rb;
+        asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(ra) : "f"(a));
+        asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(rb) : "f"(b));
+        q16[(size_t)row * Dt + k] = ra;
+        d16[(size_t)row * Dt + k] = rb;
+        acc = fmaf(a, b, acc);
     }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) diag[row] = acc;
 }
 
 // diag[i] = q_i . d_i (one warp per row)
@@ -433,11 +448,7 @@ int rf_inbatch_rowstats_bf16(const float *d_query, const float *d_doc, const flo
     uintptr_t p = (reinterpret_cast<uintptr_t>(fin_ws) + finalize_ws_bytes(B) + 255) & ~(uintptr_t)255;
     unsigned short *q16 = reinterpret_cast<unsigned short *>(p);
     unsigned short *d16 = q16 + (((size_t)B * dim + 127) & ~(size_t)127);
-    const int64_t n = (int64_t)B * dim;
-    const int rgrid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
-    to_bf16_kernel<<<rgrid, 256, 0, st>>>(d_query, q16, n);
-    to_bf16_kernel<<<rgrid, 256, 0, st>>>(d_doc, d16, n);
-    rowdot_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(d_query, d_doc, B, dim, diag);   // exact fp32 diagonal
+    prep_bf16_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(d_query, d_doc, B, dim, q16, d16, diag);   // bf16 copies + exact fp32 diagonal
     int splits = 0;
     const bool full = d_hinge != nullptr || d_maxoff != nullptr;
     int rc = launch_logits_bf16(q16, d16, diag, d_col_weight, B, dim, scale, margin, full, part, (int)max_splits, &splits, st);
@@ -445,7 +456,7 @@ int rf_inbatch_rowstats_bf16(const float *d_query, const float *d_doc, const flo
     rc = launch_finalize(part, splits, B, diag, d_y, scale, d_lse, d_hinge, d_maxoff, d_loss, fin_ws, st);
     if (rc != RF_OK) return rc;
     RF_CUDA(cudaGetLastError());
-    g_launches.fetch_add(4);
+    g_launches.fetch_add(2);
     return RF_OK;
 }
 

@@ -426,7 +426,47 @@ def test_dense_forward_split_k_matches_float64(rows, in_dim, units):
     assert torch.equal(got, dense_forward(x, wt)), "ordered partial sums: run to run identical"
 
 
-@pytest.mark.parametrize("activation,with_norm", [("selu", True), ("sigmoid", True), ("relu", False), ("tanh", False), (None, True)])
+@pytest.mark.parametrize("rows,dim", [(512, 96), (1000, 68), (8192, 256), (33, 4)])
+def test_tower_training_column_passes_match_torch(rows, dim):
+    """rf_column_stats / rf_activation_backward / rf_batchnorm_backward (the HBM-bound passes around a stage's three GEMMs)
+    against torch float64, every activation whose derivative is taken from the output."""
+    from recommendflow_b200 import dense_ops
+    g = torch.Generator(device="cuda").manual_seed(rows + dim)
+    x = torch.randn(rows, dim + 4, device="cuda", generator=g)[:, :dim] * 1.5 + 0.7           # a strided view: row pitch dim + 4
+    mean, var, xt = dense_ops.column_stats(x, want_transpose=True)
+    x64 = x.double()
+    np.testing.assert_allclose(mean.cpu().numpy(), x64.mean(0).cpu().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(var.cpu().numpy(), x64.var(0, unbiased=False).cpu().numpy(), rtol=2e-5, atol=1e-6)
+    assert torch.equal(xt, x.t().contiguous())
+    assert torch.equal(mean, dense_ops.column_stats(x)[0]), "ordered partial sums: deterministic"
+    dy = torch.randn(rows, dim, device="cuda", generator=g)
+    for act, fwd in (("relu", torch.relu), ("selu", torch.selu), ("tanh", torch.tanh), ("sigmoid", torch.sigmoid), (None, lambda t: t)):
+        z = torch.randn(rows, dim, device="cuda", generator=g).double().requires_grad_(True)
+        y64 = fwd(z)
+        (y64 * dy.double()).sum().backward()
+        dz, dzt, db = dense_ops.activation_backward(dy, y64.detach().float().contiguous(), act)
+        np.testing.assert_allclose(dz.cpu().numpy(), z.grad.cpu().numpy(), rtol=1e-4, atol=1e-5, err_msg=str(act))
+        assert torch.equal(dzt, dz.t().contiguous())
+        np.testing.assert_allclose(db.cpu().numpy(), z.grad.sum(0).cpu().numpy(), rtol=1e-4, atol=1e-4 * rows ** 0.5, err_msg=str(act))
+    # BatchNormalization (batch statistics) backward vs autograd
+    gamma = torch.rand(dim, device="cuda", generator=g) + 0.5
+    eps = 1e-3
+    xr = x64.clone().requires_grad_(True)
+    g64 = gamma.double().requires_grad_(True)
+    b64 = torch.zeros(dim, device="cuda", dtype=torch.float64, requires_grad=True)
+    v64, m64 = torch.var_mean(xr, dim=0, unbiased=False)
+    out = (xr - m64) * torch.rsqrt(v64 + eps) * g64 + b64
+    dxh = torch.randn(rows, dim, device="cuda", generator=g)
+    (out * dxh.double()).sum().backward()
+    rstd = torch.rsqrt(var + eps)
+    dx, dgamma, dbeta = dense_ops.batchnorm_backward(dxh, x, mean, rstd, gamma * rstd)
+    scale = float(xr.grad.abs().max())
+    np.testing.assert_allclose(dx.cpu().numpy(), xr.grad.cpu().numpy(), rtol=1e-3, atol=2e-5 * max(1.0, scale))
+    np.testing.assert_allclose(dgamma.cpu().numpy(), g64.grad.cpu().numpy(), rtol=1e-3, atol=2e-4 * rows ** 0.5)
+    np.testing.assert_allclose(dbeta.cpu().numpy(), b64.grad.cpu().numpy(), rtol=1e-3, atol=2e-4 * rows ** 0.5)
+
+
+@pytest.mark.parametrize("activation,with_norm", [("selu", True), ("sigmoid", True), ("tanh", False), (None, True)])
 def test_tower_mlp_training_stage_gradients(activation, with_norm):
     """The gradient-recording tower path (mlp._TrainStage: batch statistics folded into the tcgen05 GEMM, both backward
     GEMMs on the same kernel, BatchNormalization backward in closed form) against the same layers run one torch op at a

@@ -24,7 +24,8 @@ def timed(fn, steps, warmup=3):
     return e0.elapsed_time(e1) / steps
 
 
-def main():
+def run(steps=10, lazy=False, graph=True, profile_path=None):
+    """The measurements as a dict (bench.py appends it to its line as `train_c3`)."""
     import torch
     from recommendflow_b200 import _native as nat
     from recommendflow_b200.config_parser import Configuration
@@ -34,8 +35,10 @@ def main():
     from recommendflow_b200.synth import c2_field_keys
     from recommendflow_b200.training import RecallSdpaTrainer
 
-    B, S, dm, steps = 8192, 50, 64, int(os.environ.get("STEPS", "10"))
-    out = {"batch": B, "steps": steps}
+    B, S, dm = 8192, 50, 64
+    out = {"workload": "c3 training step: base_recall_sdpa two-tower model, batch 8192, 228 hashed features x 2 tables of 100000 x 8, "
+                       "SDPA encoder [B,50,64], towers [1024,512,256] with BatchNormalization (batch statistics) + dropout 0.3, in-batch "
+                       "softmax loss, Keras Adam on every variable (train.py:97-104)", "batch": B, "steps": steps}
     # kernels alone
     q = torch.nn.functional.normalize(torch.randn(B, 256, device="cuda"), dim=1)
     d = torch.nn.functional.normalize(torch.randn(B, 256, device="cuda"), dim=1)
@@ -51,7 +54,7 @@ def main():
     cfg = os.path.join(ROOT, "tests", "golden", "configs", "synth_recall_sdpa")
     conf = Configuration(cfg + ".yaml", slot_map_path=cfg + ".feature.map")
     model = RecallSdpa(conf, behaviour_dim=dm, num_heads=1)
-    trainer = RecallSdpaTrainer(model, learning_rate=1e-4, lazy_embedding_adam=os.environ.get("LAZY", "0") == "1")
+    trainer = RecallSdpaTrainer(model, learning_rate=1e-4, lazy_embedding_adam=lazy)
     names = model.user_cols + model.ad_cols
     batch = {}
     for i, n in enumerate(names):
@@ -68,24 +71,30 @@ def main():
     out["launches_per_step"] = (nat.launch_count() - l0) / (steps + 2)
     out["embedding_adam"] = "lazy" if trainer.lazy else "keras (all rows decay)"
     out["loss_after"] = float(step())
-    if os.environ.get("GRAPH", "1") == "1":        # the same step recorded into one CUDA graph (training.GraphedTrainStep)
+    if graph:        # the same step recorded into one CUDA graph (training.GraphedTrainStep)
         from recommendflow_b200.training import GraphedTrainStep
         graphed = GraphedTrainStep(trainer, batch, y, (x, mask), warmup=2)
         out["train_step_graphed_ms"] = timed(graphed, steps, warmup=2)
         out["train_graphed_samples_per_s"] = B / (out["train_step_graphed_ms"] / 1e3)
         out["loss_after_graphed"] = float(graphed())
         step = graphed
-    print(json.dumps(out))
-    if os.environ.get("PROFILE"):          # where the step's time goes (kineto; not a timing source for the numbers above)
+    if profile_path:          # where the step's time goes (kineto; not a timing source for the numbers above)
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
             for _ in range(3):
                 step()
             torch.cuda.synchronize()
-        with open(os.environ["PROFILE"], "w") as f:
+        with open(profile_path, "w") as f:
             f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70))
             f.write("\n\n")
             f.write(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=30, max_name_column_width=70))
+
+    return out
+
+
+def main():
+    print(json.dumps(run(int(os.environ.get("STEPS", "10")), os.environ.get("LAZY", "0") == "1", os.environ.get("GRAPH", "1") == "1",
+                         os.environ.get("PROFILE"))))
 
 
 if __name__ == "__main__":
