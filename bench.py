@@ -679,7 +679,8 @@ def run_ours(args):
     # ---- C3 end to end (host keys -> bags -> SDPA -> towers -> loss -> host), rank 0 of a single-GPU run ----
     c3 = None
     if not args.no_c3 and name == "c2" and world == 1:
-        c3 = run_c3full(dev, 20, 5, with_cpu=not args.no_cpu_baseline)
+        c3 = run_c3full(dev, int(os.environ.get("RF_BENCH_C3_STEPS", "20")), int(os.environ.get("RF_BENCH_C3_WARMUP", "5")),
+                        with_cpu=not args.no_cpu_baseline)
 
     # ---- C3 training step (forward + backward + Keras Adam on every variable), eager and as one CUDA graph ----
     train = None

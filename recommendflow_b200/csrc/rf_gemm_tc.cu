@@ -401,15 +401,41 @@ static int launch(const float *x, int64_t ldx, const float *wt, int64_t ldw, Par
     return RF_OK;
 }
 
-// K splits for a product whose output has too few tiles to occupy the GPU (dW = X^T dZ of a tower stage: 4 x 4 tiles, K = 8192)
-static int pick_splits(int64_t rows, int units, int in_dim, int sms) {
-    const int64_t tiles = ((rows + kBM - 1) / kBM) * ((units + 63) / 64);
+// Column-tile width and K splits.  The kernel is bound by L2 -> shared-memory traffic (fp32 operands: a 128 x BN tile pulls
+// (128 + BN) * K * 4 bytes), with a per-tile epilogue cost ~ 2 bytes-equivalents per output element, and the persistent grid
+// runs ceil(CTAs / SMs) waves -- measured on B200 (profiles/r2d_gemm_tile_sweep.txt), time ~ waves * ((128 + BN) * K + 256 * BN):
+// 8192 x 1888 x 1024 takes 0.065 / 0.083 / 0.123 ms at BN = 256 / 128 / 64 (model 1 : 1.30 : 1.68).  A product whose output
+// has few tiles and a long contraction (dW = X^T dZ: K = batch) additionally splits K over CTAs (partials summed in order by
+// splitk_sum_kernel, ~5 us of extra launch + traffic).
+struct TileChoice {
+    int bn, splits;
+};
+
+static TileChoice pick_config(int64_t rows, int units, int in_dim, int sms, bool allow_split, bool l2norm) {
+    const int64_t m_tiles = (rows + kBM - 1) / kBM;
     const int n_kb = (in_dim + kBK - 1) / kBK;
-    if (tiles * 2 > sms || n_kb < 16) return 1;
-    int64_t s = sms / tiles;
-    if (s > n_kb / 8) s = n_kb / 8;
-    if (s > 64) s = 64;
-    return s < 2 ? 1 : (int)s;
+    TileChoice best{64, 1};
+    double best_cost = 1e300;
+    static const int kSplits[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64};
+    for (int bn : {256, 128, 64}) {
+        if (l2norm && units > bn) continue;
+        if (bn > 64 && units <= bn / 2) continue;                      // a mostly empty column tile
+        const int64_t tiles = m_tiles * ((units + bn - 1) / bn);
+        for (int s : kSplits) {
+            if (s > 1 && (!allow_split || n_kb / s < 8)) break;
+            const int kb_per = (n_kb + s - 1) / s;
+            const int real = (n_kb + kb_per - 1) / kb_per;
+            if (real != s) continue;
+            const double waves = (double)((tiles * s + sms - 1) / sms);
+            double cost = waves * ((double)(kBM + bn) * kb_per * kBK + 2.0 * kBM * bn);
+            if (s > 1) cost += 120000.0 + 2.0 * (double)m_tiles * kBM * units * s / sms;      // extra launch + partials written and re-read (whole GPU)
+            if (cost < best_cost) {
+                best_cost = cost;
+                best = TileChoice{bn, s};
+            }
+        }
+    }
+    return best;
 }
 
 }  // namespace gemm_tc
@@ -420,9 +446,9 @@ using namespace rf;
 extern "C" int64_t rf_dense_tc_workspace_bytes(int64_t rows, int32_t in_dim, int32_t units) {
     using namespace gemm_tc;
     if (rows <= 0 || in_dim <= 0 || units <= 0) return 0;
-    const int splits = pick_splits(rows, units, in_dim, 148);
-    if (splits <= 1) return 0;
-    return (int64_t)splits * ((rows + kBM - 1) / kBM) * kBM * units * (int64_t)sizeof(float);
+    const TileChoice c = pick_config(rows, units, in_dim, 148, true, false);
+    if (c.splits <= 1) return 0;
+    return (int64_t)c.splits * ((rows + kBM - 1) / kBM) * kBM * units * (int64_t)sizeof(float);
 }
 
 extern "C" int rf_dense_forward_tc_ex(const float *d_x, int64_t rows, int32_t in_dim, int64_t ldx, const float *d_weight_t,
@@ -448,33 +474,22 @@ extern "C" int rf_dense_forward_tc_ex(const float *d_x, int64_t rows, int32_t in
     p.kb_per = n_kb;
     // split-K only for a plain product (no bias / activation / normalisation to apply to a partial sum) and only when the
     // caller brought the workspace for it
-    if (d_workspace && !d_bias && activation == RF_ACT_NONE && !l2_normalize) {
-        const int splits = pick_splits(rows, units, in_dim, 148);
-        if (splits > 1 && workspace_bytes >= rf_dense_tc_workspace_bytes(rows, in_dim, units) &&
-            (reinterpret_cast<uintptr_t>(d_workspace) & 15) == 0) {
-            p.kb_per = (n_kb + splits - 1) / splits;
-            p.k_splits = (n_kb + p.kb_per - 1) / p.kb_per;
-        }
+    const bool may_split = d_workspace && !d_bias && activation == RF_ACT_NONE && !l2_normalize &&
+                           (reinterpret_cast<uintptr_t>(d_workspace) & 15) == 0 &&
+                           workspace_bytes >= rf_dense_tc_workspace_bytes(rows, in_dim, units);
+    TileChoice c = pick_config(rows, units, in_dim, 148, may_split, l2_normalize != 0);
+    if (const char *force = getenv("RF_DENSE_BN")) {          // experiments: force the column tile (no split)
+        const int bn = atoi(force);
+        if ((bn == 64 || bn == 128 || bn == 256) && !(l2_normalize && units > bn)) c = TileChoice{bn, 1};
+    }
+    if (c.splits > 1) {
+        p.kb_per = (n_kb + c.splits - 1) / c.splits;
+        p.k_splits = (n_kb + p.kb_per - 1) / p.kb_per;
     }
     float *partials = static_cast<float *>(d_workspace);
-    if (p.k_splits > 1) return launch<64>(d_x, ldx, d_weight_t, in_dim, p, sms, st, partials);
-    // column tile: the widest that keeps the persistent grid busy: cost = waves x tile width
-    const int64_t m_tiles = (rows + kBM - 1) / kBM;
-    int best_bn = 0;
-    int64_t best_cost = INT64_MAX;
-    for (int bn : {256, 128, 64}) {
-        if (l2_normalize && units > bn) continue;
-        if (bn > 64 && units <= bn / 2) continue;                      // a mostly empty column tile
-        const int64_t tiles = m_tiles * ((units + bn - 1) / bn);
-        const int64_t cost = ((tiles + sms - 1) / sms) * bn;
-        if (cost < best_cost) {
-            best_cost = cost;
-            best_bn = bn;
-        }
-    }
-    if (best_bn == 256) return launch<256>(d_x, ldx, d_weight_t, in_dim, p, sms, st, nullptr);
-    if (best_bn == 128) return launch<128>(d_x, ldx, d_weight_t, in_dim, p, sms, st, nullptr);
-    return launch<64>(d_x, ldx, d_weight_t, in_dim, p, sms, st, nullptr);
+    if (c.bn == 256) return launch<256>(d_x, ldx, d_weight_t, in_dim, p, sms, st, partials);
+    if (c.bn == 128) return launch<128>(d_x, ldx, d_weight_t, in_dim, p, sms, st, partials);
+    return launch<64>(d_x, ldx, d_weight_t, in_dim, p, sms, st, partials);
 }
 
 extern "C" int rf_dense_forward_tc(const float *d_x, int64_t rows, int32_t in_dim, int64_t ldx, const float *d_weight_t,
