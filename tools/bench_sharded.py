@@ -309,7 +309,7 @@ def run(args, world, rank, dev):
                     dist.all_reduce(errs, op=dist.ReduceOp.MAX)
                     parity[tag] = {("bit_exact_vs_oracle" if mode == "ordered" else "within_reassociation_bound"):
                                    int(flags.item()) == 0, "ranks_checked": world, "max_abs_err": float(errs.item())}
-                    if B >= 32768 and mode == "ordered" and kind == "string":
+                    if mode == "ordered" and kind == "string":
                         acc = {}
                         for i in range(5):
                             layer.profile = []
