@@ -703,6 +703,22 @@ static int graph_pool_ready_locked(DeviceState *st) {
     return RF_OK;
 }
 
+// Upload of a captured launch's descriptors: a KERNEL node that reads the pinned host slot through its device mapping (UVA).
+// A cudaMemcpyAsync node would sit in the copy engine's queue, behind whatever bulk H2D the application prefetches for the
+// next step on another stream -- measured: a graph-replayed forward then waits for the next batch's 35 MB input copy.
+__global__ void __launch_bounds__(256) desc_copy_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, int n16) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+int graph_desc_upload(char *device, const char *host, size_t bytes, cudaStream_t stream) {
+    const int n16 = (int)((bytes + 15) / 16);                 // slots are 32 KiB granular: rounding up stays inside the slot run
+    int blocks = (n16 + 255) / 256;
+    if (blocks > 16) blocks = 16;
+    desc_copy_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4 *>(host), reinterpret_cast<uint4 *>(device), n16);
+    RF_CUDA(cudaGetLastError());
+    return RF_OK;
+}
+
 int graph_desc_slots(int dev, size_t bytes, char **host, char **device) {
     DeviceState *st = device_state(dev);
     std::lock_guard<std::mutex> lk(st->mu);
@@ -794,7 +810,8 @@ static int launch_fields(std::vector<DevField> &dev_fields, int ctas_per_sm, cud
         int rc = graph_slots_locked(st, bytes, &h, &d);
         if (rc != RF_OK) return rc;
         memcpy(h, dev_fields.data(), bytes);
-        RF_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream));
+        rc = graph_desc_upload(d, h, bytes, stream);
+        if (rc != RF_OK) return rc;
         return launch_kernel(reinterpret_cast<const DevField *>(d), (int)dev_fields.size(), (int)tiles, ctas_per_sm, acc, stream);
     }
     {

@@ -48,6 +48,7 @@ namespace rf {
 extern std::atomic<int64_t> g_launches;
 int graph_desc_slots(int dev, size_t bytes, char **host, char **device);       // rf_bag.cu
 int graph_desc_pool_ready(int dev);
+int graph_desc_upload(char *device, const char *host, size_t bytes, cudaStream_t stream);
 
 namespace {
 
@@ -421,7 +422,8 @@ int rf_bag_backward_adam_multi(const rf_adam_field *fields, int n_fields, int64_
         rc = graph_desc_slots(devid, sizeof(DevAdamField) * (size_t)n_fields, &h, &d);
         if (rc != RF_OK) return rc;
         memcpy(h, dev.data(), sizeof(DevAdamField) * (size_t)n_fields);
-        RF_CUDA(cudaMemcpyAsync(ws.fields, h, sizeof(DevAdamField) * (size_t)n_fields, cudaMemcpyHostToDevice, st));
+        rc = graph_desc_upload(reinterpret_cast<char *>(ws.fields), h, sizeof(DevAdamField) * (size_t)n_fields, st);
+        if (rc != RF_OK) return rc;
     } else {
         rc = graph_desc_pool_ready(devid);
         if (rc != RF_OK) return rc;

@@ -125,8 +125,17 @@ class CudaShardOps(object):
         """Keras Adam on this rank's shard from the routed rows of every source (rf_bag_backward_adam):
         rows [n] int64 local rows, offs_all [n_bags + 1] CSR over all (source, bag) pairs, grads [n_bags, D]."""
         n_bags = grads.shape[0]
+        live = None
+        if not params["lazy"]:
+            # rows of this shard that ever received a gradient: the all-rows decay of Keras' Adam skips the others unread
+            # (rf_adam_params.d_live_rows; bit-identical).  A state that does not start at step 1 (restored moments) marks all rows.
+            if state.get("live") is None:
+                words = (shard.shape[0] + 31) // 32 + 1
+                state["live"] = (torch.zeros(words, dtype=torch.int32, device=shard.device) if params["step"] == 1 else
+                                 torch.full((words,), -1, dtype=torch.int32, device=shard.device))
+            live = state["live"].data_ptr()
         p = nat.AdamParams(lr=params["learning_rate"], beta1=params["beta_1"], beta2=params["beta_2"], epsilon=params["epsilon"],
-                           step=params["step"], lazy=1 if params["lazy"] else 0)
+                           step=params["step"], lazy=1 if params["lazy"] else 0, d_live_rows=live)
         with torch.cuda.device(shard.device):
             need = int(nat.lib().rf_bag_adam_workspace_bytes(rows.numel(), shard.shape[0]))
             if need < 0:
