@@ -396,12 +396,9 @@ def run_c3full(dev, steps, warmup, with_cpu=True):
     piped = None
     try:
         main, sc = torch.cuda.current_stream(dev), torch.cuda.Stream(dev)
-        graphs, loss_dev = [], []
-        for bi in range(NBAT):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                loss_dev.append(forward(devb[bi]))
-            graphs.append(g)
+        from recommendflow_b200.graphs import GraphedCall
+        graphs = [GraphedCall(lambda bi=bi: forward(devb[bi])) for bi in range(NBAT)]      # the public wrapper: record once, replay
+        loss_dev = [g.outputs for g in graphs]
         loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(NBAT)]
         copied, done = [None] * NBAT, [None] * NBAT
 
@@ -422,7 +419,7 @@ def run_c3full(dev, steps, warmup, with_cpu=True):
         def launch(i):
             bi = i % NBAT
             main.wait_event(copied[bi])
-            graphs[bi].replay()
+            graphs[bi]()
             loss_host[bi].copy_(loss_dev[bi], non_blocking=True)
             done[bi] = torch.cuda.Event()
             done[bi].record(main)
@@ -441,12 +438,12 @@ def run_c3full(dev, steps, warmup, with_cpu=True):
             return float(loss_host[(n - 1) % NBAT])
 
         for bi in range(NBAT):                                           # device-resident: the recorded forward alone
-            graphs[bi].replay()
+            graphs[bi]()
         torch.cuda.synchronize()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         for i in range(steps):
-            graphs[i % NBAT].replay()
+            graphs[i % NBAT]()
         g1.record()
         torch.cuda.synchronize()
         graph_ms = g0.elapsed_time(g1) / steps
@@ -463,9 +460,8 @@ def run_c3full(dev, steps, warmup, with_cpu=True):
                  "path": "pinned host key arenas (+ mask, labels) -> H2D into static device buffers on a copy stream (prefetch of step "
                          "i + 1 under step i) -> the forward recorded as one CUDA graph per rotating batch -> D2H of the loss scalar "
                          "into pinned memory, read by the host one step behind; loss identical to the eager forward"}
-        del graphs
-        torch.cuda.synchronize()
-        nat.lib().rf_release_captured_launches()
+        for g in graphs:
+            g.release()
     except Exception as exc:                                             # the synchronous measurement stands on its own
         piped = {"error": f"{type(exc).__name__}: {exc}"}
     res = {"workload": "c3full: base_recall_sdpa two-tower forward, batch 8192: 228 hashed features x 2 tables of 100000 x 8 "
