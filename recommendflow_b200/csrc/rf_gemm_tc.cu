@@ -45,11 +45,14 @@ constexpr int kThreads = 64 + 256;
 constexpr int kEpiWarps = 8;
 constexpr int kOutStage = kEpiWarps * 2 * 4096;     // per epilogue warp: two 32-row x 128-byte staging tiles for the TMA store
 
-template <int BN>
+// PAIR: two CTAs of a cluster (one TPC) compute a 256 x BN tile with tcgen05.mma.cta_group::2: each CTA stages ITS 128 rows
+// of x and only HALF of the BN weight rows, the tensor core reads the other half from the partner's shared memory -- per CTA
+// (128 + BN / 2) * K * 4 bytes cross L2 -> smem per tile instead of (128 + BN) * K * 4, which is what bounds this kernel.
+template <int BN, bool PAIR = false>
 struct Cfg {
-    static constexpr int kBBytes = BN * kBK * 4;
+    static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * kBK * 4;          // weight rows this CTA stages
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = BN == 256 ? 3 : (BN == 128 ? 4 : 6);     // ring + 64 KiB of store staging <= 227 KiB
+    static constexpr int kStages = PAIR ? 4 : (BN == 256 ? 3 : (BN == 128 ? 4 : 6));     // ring + 64 KiB of store staging <= 227 KiB
     static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
     static constexpr size_t kSmem = (size_t)kStages * kStageBytes + kOutStage + 2048 + 1024 + 256;
 };
@@ -94,6 +97,47 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- CTA-pair (cta_group::2) forms -------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address of this CTA's window) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose completion is counted on a barrier that may live in the partner CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// completion of all prior MMAs of the pair, delivered to the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
     asm volatile(
@@ -165,15 +209,23 @@ struct Params {
     int k_splits, kb_per, m_pad;
 };
 
-template <int BN>
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ CUtensorMap map_o, Params p) {
     extern __shared__ uint8_t smem_raw[];
-    using C = Cfg<BN>;
+    using C = Cfg<BN, PAIR>;
+    // PAIR: launched as clusters of 2; rank 0 (the leader) issues the MMAs of the pair and owns the barriers the MMA issuer
+    // waits on (full: the TMA bytes of BOTH CTAs are counted there; tmem_empty: the epilogue warps of BOTH CTAs arrive there);
+    // the barriers the MMA completion signals (empty, tmem_full) exist in both CTAs and are hit by a multicast commit
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const int cta = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // tile walker index: a pair walks as one
+    const int n_ctas = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     constexpr int kStages = C::kStages;
     constexpr int kStageBytes = C::kStageBytes;
-    constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+    constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                ((uint32_t)((PAIR ? 2 * kBM : kBM) >> 4) << 24);
     const int n_kb = (p.K + kBK - 1) / kBK;
     const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t out_stage = ring + kStages * kStageBytes;      // 1024-byte aligned (stage sizes are multiples of 1 KiB)
@@ -192,16 +244,22 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full0 + 8 * a, 1);
-            mbar_init(tmem_empty0 + 8 * a, kEpiWarps);
+            mbar_init(tmem_empty0 + 8 * a, PAIR ? 2 * kEpiWarps : kEpiWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {               // one warp of EACH CTA of the pair performs the (symmetric) allocation
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (PAIR) cluster_sync_all();          // the partner's barriers are initialised before anything signals them
+    else __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -210,16 +268,25 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            for (int t = cta; t < n_tiles; t += n_ctas) {
                 const int split = t / mn_tiles, mn = t - split * mn_tiles;
-                const int m_tile = mn / p.n_n_tiles, n_tile = mn - m_tile * p.n_n_tiles;
+                const int m_tile = (mn / p.n_n_tiles) * (PAIR ? 2 : 1) + (int)rank, n_tile = mn - (mn / p.n_n_tiles) * p.n_n_tiles;
                 const int kb0 = split * p.kb_per, kb1 = min(n_kb, kb0 + p.kb_per);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t dst = ring + stage * kStageBytes;
-                    mbar_expect_tx(full0 + 8 * stage, kStageBytes);
-                    tma_load_2d(dst, &map_a, full0 + 8 * stage, kb * kBK, m_tile * kBM);
-                    tma_load_2d(dst + kABytes, &map_b, full0 + 8 * stage, kb * kBK, n_tile * BN);
+                    if (PAIR) {
+                        // both CTAs' bytes are counted on the LEADER's full barrier (the peer's complete_tx may land before the
+                        // leader's expect_tx of the phase: the pending arrival keeps the phase open)
+                        const uint32_t bar = mapa_rank(full0 + 8 * stage, 0);
+                        if (leader) mbar_expect_tx(full0 + 8 * stage, 2 * kStageBytes);
+                        tma_load_2d_pair(dst, &map_a, bar, kb * kBK, m_tile * kBM);
+                        tma_load_2d_pair(dst + kABytes, &map_b, bar, kb * kBK, n_tile * BN + (int)rank * (BN / 2));
+                    } else {
+                        mbar_expect_tx(full0 + 8 * stage, kStageBytes);
+                        tma_load_2d(dst, &map_a, full0 + 8 * stage, kb * kBK, m_tile * kBM);
+                        tma_load_2d(dst + kABytes, &map_b, full0 + 8 * stage, kb * kBK, n_tile * BN);
+                    }
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -229,10 +296,10 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
+        if (lane == 0 && leader) {
             uint32_t stage = 0, phase = 0;
             int local = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++local) {
+            for (int t = cta; t < n_tiles; t += n_ctas, ++local) {
                 const uint32_t acc = (uint32_t)(local & 1);
                 mbar_wait(tmem_empty0 + 8 * acc, ((uint32_t)(local >> 1) & 1u) ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -243,16 +310,23 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     const uint32_t st_addr = ring + stage * kStageBytes;
                     const uint64_t adesc = desc_sw128(st_addr), bdesc = desc_sw128(st_addr + kABytes);
 #pragma unroll
-                    for (int k = 0; k < kBK / kUmmaK; ++k)
-                        umma_tf32(tmem_base + acc * (uint32_t)BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kIdesc,
-                                  (kb != kb0 || k != 0) ? 1u : 0u);
-                    umma_commit(empty0 + 8 * stage);
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        if (PAIR)
+                            umma_tf32_pair(tmem_base + acc * (uint32_t)BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kIdesc,
+                                           (kb != kb0 || k != 0) ? 1u : 0u);
+                        else
+                            umma_tf32(tmem_base + acc * (uint32_t)BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kIdesc,
+                                      (kb != kb0 || k != 0) ? 1u : 0u);
+                    }
+                    if (PAIR) umma_commit_pair(empty0 + 8 * stage);
+                    else umma_commit(empty0 + 8 * stage);
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma_commit(tmem_full0 + 8 * acc);
+                if (PAIR) umma_commit_pair(tmem_full0 + 8 * acc);
+                else umma_commit(tmem_full0 + 8 * acc);
             }
         }
     } else {
@@ -263,9 +337,9 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         float2 *xch = reinterpret_cast<float2 *>(smem_raw + (xch_s - smem_u32(smem_raw)));
         int local = 0;
         uint32_t n_store = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++local) {
+        for (int t = cta; t < n_tiles; t += n_ctas, ++local) {
             const int split = t / mn_tiles, mn = t - split * mn_tiles;
-            const int m_tile = mn / p.n_n_tiles, n_tile = mn - m_tile * p.n_n_tiles;
+            const int m_tile = (mn / p.n_n_tiles) * (PAIR ? 2 : 1) + (int)rank, n_tile = mn - (mn / p.n_n_tiles) * p.n_n_tiles;
             const uint32_t acc = (uint32_t)(local & 1);
             mbar_wait(tmem_full0 + 8 * acc, (uint32_t)(local >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -318,16 +392,21 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty0 + 8 * acc);
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_cluster(mapa_rank(tmem_empty0 + 8 * acc, 0));      // the leader's MMA issuer waits for both CTAs
+                else mbar_arrive(tmem_empty0 + 8 * acc);
+            }
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // every store has landed before the CTA exits
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (PAIR) cluster_sync_all();          // the leader's MMAs read the partner's shared memory: nobody leaves early
+    else __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
     }
 }
 
@@ -372,25 +451,43 @@ __global__ void __launch_bounds__(256) splitk_sum_kernel(const float *__restrict
     }
 }
 
-template <int BN>
+template <int BN, bool PAIR = false>
 static int launch(const float *x, int64_t ldx, const float *wt, int64_t ldw, Params p, int sms, cudaStream_t st, float *partials) {
     CUtensorMap ma, mb, mo;
+    constexpr int kRowsPerTile = PAIR ? 2 * kBM : kBM;      // a pair of CTAs walks 256-row tiles
     int rc = make_map(&ma, x, p.M, p.K, ldx, kBM);
     if (rc != RF_OK) return rc;
-    rc = make_map(&mb, wt, p.N, p.K, ldw, BN);
+    rc = make_map(&mb, wt, p.N, p.K, ldw, PAIR ? BN / 2 : BN);
     if (rc != RF_OK) return rc;
-    p.n_m_tiles = (p.M + kBM - 1) / kBM;
+    p.n_m_tiles = (p.M + kRowsPerTile - 1) / kRowsPerTile;
     p.n_n_tiles = (p.N + BN - 1) / BN;
-    p.m_pad = p.n_m_tiles * kBM;
+    p.m_pad = p.n_m_tiles * kRowsPerTile;
     if (p.k_splits > 1)
         rc = make_map(&mo, partials, (int64_t)p.k_splits * p.m_pad, p.N, p.N, 32, CU_TENSOR_MAP_L2_PROMOTION_NONE);
     else
         rc = make_map(&mo, p.out, p.M, p.N, p.ldo, 32, CU_TENSOR_MAP_L2_PROMOTION_NONE);     // 32 x 32 store boxes
     if (rc != RF_OK) return rc;
     const int tiles = p.n_m_tiles * p.n_n_tiles * p.k_splits;
-    const int grid = tiles < sms ? tiles : sms;
-    RF_CUDA(cudaFuncSetAttribute(dense_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::kSmem));
-    dense_tc_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmem, st>>>(ma, mb, mo, p);
+    const int walkers = PAIR ? sms / 2 : sms;
+    const int grid = (tiles < walkers ? tiles : walkers) * (PAIR ? 2 : 1);
+    RF_CUDA(cudaFuncSetAttribute(dense_tc_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN, PAIR>::kSmem));
+    if (PAIR) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = Cfg<BN, PAIR>::kSmem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        RF_CUDA(cudaLaunchKernelEx(&cfg, dense_tc_kernel<BN, PAIR>, ma, mb, mo, p));
+    } else {
+        dense_tc_kernel<BN, PAIR><<<grid, kThreads, Cfg<BN, PAIR>::kSmem, st>>>(ma, mb, mo, p);
+    }
     if (p.k_splits > 1) {
         int64_t blocks = ((int64_t)p.M * (p.N / 4) + 255) / 256;
         if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
@@ -409,12 +506,13 @@ static int launch(const float *x, int64_t ldx, const float *wt, int64_t ldw, Par
 // splitk_sum_kernel, ~5 us of extra launch + traffic).
 struct TileChoice {
     int bn, splits;
+    bool pair;
 };
 
 static TileChoice pick_config(int64_t rows, int units, int in_dim, int sms, bool allow_split, bool l2norm) {
     const int64_t m_tiles = (rows + kBM - 1) / kBM;
     const int n_kb = (in_dim + kBK - 1) / kBK;
-    TileChoice best{64, 1};
+    TileChoice best{64, 1, false};
     double best_cost = 1e300;
     static const int kSplits[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64};
     for (int bn : {256, 128, 64}) {
@@ -431,7 +529,28 @@ static TileChoice pick_config(int64_t rows, int units, int in_dim, int sms, bool
             if (s > 1) cost += 120000.0 + 2.0 * (double)m_tiles * kBM * units * s / sms;      // extra launch + partials written and re-read (whole GPU)
             if (cost < best_cost) {
                 best_cost = cost;
-                best = TileChoice{bn, s};
+                best = TileChoice{bn, s, false};
+            }
+        }
+    }
+    // CTA pairs (cta_group::2): 256-row tiles, each CTA stages its 128 rows of x and half of the weight tile.  Measured
+    // (profiles/r2e_gemm_pair_sweep.txt): a gain where the single-CTA kernel is L2-bound -- at least a full wave of pair tiles
+    // and a contraction of 512 or more (8192 x 1888 x 1024: 0.067 -> 0.059 ms, 65536 rows: 0.425 -> 0.374 ms) -- and a loss
+    // for few tiles (half the walkers) or short contractions (epilogue-bound).  RF_DENSE_PAIR=0 turns pairs off, =2 forces
+    // them wherever they are legal (tests).
+    const char *env = getenv("RF_DENSE_PAIR");
+    const int mode = env ? atoi(env) : 1;
+    if (mode != 0 && rows >= 2 * kBM && !l2norm) {
+        const int64_t m_pairs = (rows + 2 * kBM - 1) / (2 * kBM);
+        for (int bn : {256, 128}) {
+            if (units <= bn / 2) continue;
+            const int64_t tiles = m_pairs * ((units + bn - 1) / bn);
+            if (mode != 2 && (tiles < sms / 2 || in_dim < 512)) continue;
+            const double waves = (double)((tiles + sms / 2 - 1) / (sms / 2));
+            const double cost = waves * ((double)(kBM + bn / 2) * n_kb * kBK + 2.0 * kBM * bn);
+            if (cost < best_cost || (mode == 2 && !best.pair)) {
+                best_cost = cost;
+                best = TileChoice{bn, 1, true};
             }
         }
     }
@@ -480,13 +599,15 @@ extern "C" int rf_dense_forward_tc_ex(const float *d_x, int64_t rows, int32_t in
     TileChoice c = pick_config(rows, units, in_dim, 148, may_split, l2_normalize != 0);
     if (const char *force = getenv("RF_DENSE_BN")) {          // experiments: force the column tile (no split)
         const int bn = atoi(force);
-        if ((bn == 64 || bn == 128 || bn == 256) && !(l2_normalize && units > bn)) c = TileChoice{bn, 1};
+        if ((bn == 64 || bn == 128 || bn == 256) && !(l2_normalize && units > bn)) c = TileChoice{bn, 1, false};
     }
     if (c.splits > 1) {
         p.kb_per = (n_kb + c.splits - 1) / c.splits;
         p.k_splits = (n_kb + p.kb_per - 1) / p.kb_per;
     }
     float *partials = static_cast<float *>(d_workspace);
+    if (c.pair && c.bn == 256) return launch<256, true>(d_x, ldx, d_weight_t, in_dim, p, sms, st, partials);
+    if (c.pair) return launch<128, true>(d_x, ldx, d_weight_t, in_dim, p, sms, st, partials);
     if (c.bn == 256) return launch<256>(d_x, ldx, d_weight_t, in_dim, p, sms, st, partials);
     if (c.bn == 128) return launch<128>(d_x, ldx, d_weight_t, in_dim, p, sms, st, partials);
     return launch<64>(d_x, ldx, d_weight_t, in_dim, p, sms, st, partials);

@@ -407,6 +407,28 @@ def test_dense_forward_tc_strided_input_and_output_slot():
     assert torch.all(outw[:, :100] == 7.0) and torch.all(outw[:, 100 + N:] == 7.0)      # nothing outside the slot is touched
 
 
+@pytest.mark.parametrize("rows,in_dim,units,act", [(512, 96, 256, "selu"), (300, 1000, 516, None), (2048, 1888, 1024, "relu"),
+                                                   (257, 64, 132, "tanh"), (8192, 512, 256, None)])
+def test_dense_forward_cta_pairs_match_float64(rows, in_dim, units, act, monkeypatch):
+    """The cta_group::2 variant of the Dense kernel (a cluster of two CTAs computes a 256-row tile; each stages its 128 rows of x
+    and half of the weight tile, the leader issues tcgen05.mma.cta_group::2 and a multicast commit frees both rings), forced on
+    (RF_DENSE_PAIR=2) for shapes with ragged last row pairs / column tiles, and compared with the single-CTA kernel."""
+    from recommendflow_b200.dense_ops import dense_forward
+    g = torch.Generator(device="cuda").manual_seed(rows + units)
+    x = torch.randn(rows, in_dim, device="cuda", generator=g)
+    wt = torch.randn(units, in_dim, device="cuda", generator=g) / in_dim ** 0.5
+    b = torch.randn(units, device="cuda", generator=g) * 0.1
+    monkeypatch.setenv("RF_DENSE_PAIR", "0")
+    single = dense_forward(x, wt, b, act)
+    monkeypatch.setenv("RF_DENSE_PAIR", "2")
+    pair = dense_forward(x, wt, b, act)
+    want = _act64(act, x.double().cpu().numpy() @ wt.double().cpu().numpy().T + b.double().cpu().numpy())
+    np.testing.assert_allclose(pair.cpu().numpy(), want, rtol=2e-2, atol=4e-3)
+    # same operands, same TF32 products, same accumulation order per output element: the two kernels agree bit for bit
+    assert torch.equal(pair, single)
+    assert torch.equal(pair, dense_forward(x, wt, b, act))
+
+
 @pytest.mark.parametrize("rows,in_dim,units", [(512, 8192, 256), (64, 40960, 192), (1888, 8192, 1024), (100, 1000, 68)])
 def test_dense_forward_split_k_matches_float64(rows, in_dim, units):
     """A plain product with few output tiles and a long contraction (dW = X^T dZ) splits K over CTAs and sums the partial
