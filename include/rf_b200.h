@@ -338,6 +338,15 @@ int rf_bag_backward_adam(const int64_t *d_ids, int64_t n_keys, const int32_t *d_
                          const rf_adam_params *params, float *d_table, float *d_m, float *d_v,
                          int64_t table_rows, void *d_workspace, int64_t workspace_bytes, void *stream);
 
+/* min / max pooling backward (tf.reduce_min / tf.reduce_max over the bag, preprocess_layers.py:43-68; TensorFlow's       */
+/* _MinOrMaxGrad): d_key_grads[k][d] = grad_out[bag(k)][d] * (table[ids[k]][d] == pooled[bag][d]) / (number of keys of the  */
+/* bag with that equality).  One gradient row per key ([n_keys, dim], dense); apply it with rf_bag_backward /                */
+/* rf_bag_backward_adam as sum pooling over bags of one key (bag_len = 1, batch = n_keys).  d_pooled: the forward's output.   */
+int rf_bag_minmax_key_grads(const int64_t *d_ids, int64_t n_keys, const int32_t *d_bag_offsets, int32_t bag_len,
+                            int64_t batch, const float *d_table, int32_t dim, const float *d_pooled,
+                            int64_t pooled_stride, const float *d_grad_out, int64_t grad_stride, float *d_key_grads,
+                            void *stream);
+
 /* ---- backward of the dense contractions (CUDA-core fp32; what model.fit differentiates) -------- */
 /* Gradient of scaled_dot_product_attention (layer_utils.py:4-24) w.r.t. q, k, v given d_grad_out =   */
 /* dL/d(out); same layouts as rf_sdpa_forward.  A masked query row passes gradient to v only.        */

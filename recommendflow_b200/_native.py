@@ -166,6 +166,9 @@ def lib():
         L.rf_inbatch_softmax_ce_backward_tc.restype = C.c_int
         L.rf_inbatch_softmax_ce_backward_tc.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_int,
                                                                           C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rf_bag_minmax_key_grads.restype = C.c_int
+        L.rf_bag_minmax_key_grads.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p,
+                                              C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.rf_sdpa_backward_strided.restype = C.c_int
         L.rf_sdpa_backward_strided.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                                C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]

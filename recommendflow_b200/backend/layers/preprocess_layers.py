@@ -334,15 +334,24 @@ class LookupEmbedding(Layer):
 
     The vocabulary is a device hash table (`vocab_ops.DeviceVocabulary`, rf_vocab_lookup_*); the ids feed
     the fused bag kernel.  The reference's factory passes `vocab_size=len(vocabs)`, one row short of the
-    largest index StringLookup can emit; the table here always has at least
+    largest index StringLookup can emit; by default the table here has at least
     `len(vocabs) + 1` rows so that the last term never indexes past it.
+    reference_rows=True keeps the reference's table shape exactly (`vocab_size` rows, i.e. `len(vocabs)` from its factory) so
+    that checkpoints are interchangeable.  The last vocabulary term then has no row; a batch that contains it raises, as the
+    reference's CPU gather does ("indices[...] is not in [0, N)") -- checked per call (one device-to-host read of the max id).
     """
 
-    def __init__(self, embedding_dim, dtype, vocabs, vocab_size=None, pooling="sum", name=None):
+    def __init__(self, embedding_dim, dtype, vocabs, vocab_size=None, pooling="sum", name=None, reference_rows=False):
         super().__init__(name=name)
         self.vocabulary = vocabs
         self.pooling = pooling
-        vocab_size = max(vocab_size or 0, len(vocabs) + 1)
+        self.reference_rows = bool(reference_rows)
+        if self.reference_rows:
+            vocab_size = int(vocab_size) if vocab_size else len(vocabs)
+            if vocab_size < 1:
+                raise ValueError("reference_rows needs a non-empty table")
+        else:
+            vocab_size = max(vocab_size or 0, len(vocabs) + 1)
         if dtype not in (TYPE_STR, TYPE_INT):
             raise ValueError(f"Unsupported type for lookup feature: {dtype}")
         self.key_type = dtype
@@ -357,7 +366,13 @@ class LookupEmbedding(Layer):
         device = keys.device
         if self._vocab is None or self._vocab.device != device:
             self._vocab = DeviceVocabulary(self._terms, device)
-        return self._vocab.lookup(keys)
+        ids = self._vocab.lookup(keys)
+        if self.reference_rows and len(self._terms) + 1 > self.embedding.input_dim and ids.numel():
+            top, rows = int(ids.max()), self.embedding.input_dim
+            if top >= rows:
+                raise ValueError(f"indices[...] = {top} is not in [0, {rows}): the reference-shaped table "
+                                 f"(reference_rows=True) has no row for the last vocabulary term")
+        return ids
 
     def call(self, inputs, *args, **kwargs):
         return self.embedding(self.lookup_ids(inputs))

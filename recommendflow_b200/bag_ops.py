@@ -236,6 +236,27 @@ def bag_backward(ids, table, grad_out, alpha, combiner="sum", bag_len=None, bag_
     return table
 
 
+def bag_minmax_key_grads(ids, table, pooled, grad_out, bag_len=None, bag_offsets=None):
+    """Per-key gradient rows [n_keys, dim] of "min" / "max" pooling (TensorFlow's _MinOrMaxGrad: the pooled element's gradient
+    goes to the keys whose row element equals it, split equally among ties).  `pooled`: the forward's output for these bags.
+    Apply with `bag_backward(ids, table, key_grads, alpha, "sum", bag_len=1)` or `BagAdam.apply(ids, key_grads, "sum", bag_len=1)`."""
+    ids = _require_cuda(ids, "ids").contiguous().view(-1)
+    _require_cuda(table, "table")
+    y, g = _require_cuda(pooled, "pooled"), _require_cuda(grad_out, "grad_out")
+    for t, what in ((y, "pooled"), (g, "grad_out")):
+        if t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1 or t.shape[1] != table.shape[1]:
+            raise ValueError(f"{what} must be fp32 [batch, dim] with contiguous columns")
+    if y.shape[0] != g.shape[0]:
+        raise ValueError("pooled and grad_out must have one row per bag")
+    out = torch.empty(ids.numel(), table.shape[1], dtype=torch.float32, device=table.device)
+    with torch.cuda.device(table.device):
+        nat.check(nat.lib().rf_bag_minmax_key_grads(ids.data_ptr(), ids.numel(), None if bag_offsets is None else bag_offsets.data_ptr(),
+                                                    bag_len or 0, g.shape[0], table.data_ptr(), table.shape[1], y.data_ptr(), y.stride(0),
+                                                    g.data_ptr(), g.stride(0), out.data_ptr(),
+                                                    C.c_void_p(torch.cuda.current_stream(table.device).cuda_stream)))
+    return out
+
+
 class BagAdam(object):
     """tf.keras.optimizers.Adam for one embedding table, applied from the pooled bag's gradient
     (rf_bag_backward_adam).  Reference: /root/reference/example/ranking_search/train.py:97-104.

@@ -290,6 +290,56 @@ def test_backward_sgd_matches_numpy(combiner, D):
     np.testing.assert_allclose(dev_w.cpu().numpy(), want, rtol=1e-5, atol=5e-4)
 
 
+@pytest.mark.parametrize("combiner", ["max", "min"])
+def test_minmax_pooling_backward_matches_tensorflow_gradient_rule(combiner):
+    """Backward of "min" / "max" pooling (tf.reduce_min / tf.reduce_max over the bag, preprocess_layers.py:43-68): TensorFlow's
+    _MinOrMaxGrad gives the pooled element's gradient to the keys whose row element equals it, split equally among ties.
+    Checked against torch autograd of amax / amin (the same tie rule) in float64, dense and jagged bags with duplicate keys,
+    then applied as an SGD step through the one-key-per-bag form of rf_bag_backward."""
+    from recommendflow_b200.bag_ops import bag_backward, bag_minmax_key_grads
+    rng = np.random.default_rng(23)
+    B, L, N, D = 300, 6, 211, 16
+    (w,) = tables(rng, 1, N, D)
+    w = np.round(w * 40).astype(np.float32) / 40                       # coarse values: plenty of exact ties between rows
+    ids = rng.integers(0, N, size=(B, L))
+    ids[:, 1] = ids[:, 0]                                              # and every bag holds a duplicated key
+    g = rng.standard_normal((B, D)).astype(np.float32)
+    dev_w, dev_ids, dev_g = torch.from_numpy(w).cuda(), torch.from_numpy(ids).cuda(), torch.from_numpy(g).cuda()
+    out = torch.empty(B, D, device="cuda")
+    bag_forward([FieldCall([(dev_w, N, None)], D, combiner, ids=dev_ids.view(1, -1), out=out, bag_len=L)], B)
+    w64 = torch.from_numpy(w).double().requires_grad_(True)
+    rows = w64[torch.from_numpy(ids)]                                  # [B, L, D]
+    y = rows.amax(dim=1) if combiner == "max" else rows.amin(dim=1)
+    assert np.array_equal(out.cpu().numpy(), y.detach().float().numpy())
+    rows.retain_grad()
+    (y * torch.from_numpy(g).double()).sum().backward()
+    kg = bag_minmax_key_grads(dev_ids.view(-1), dev_w, out, dev_g, bag_len=L)
+    np.testing.assert_allclose(kg.cpu().numpy().reshape(B, L, D), rows.grad.numpy(), rtol=1e-6, atol=1e-7)
+    # the row update: W -= lr * dW, dW = scatter-add of the per-key rows (what autograd accumulated into w64.grad)
+    before = dev_w.clone()
+    bag_backward(dev_ids.view(-1), dev_w, kg, -0.1, "sum", bag_len=1)
+    np.testing.assert_allclose(dev_w.cpu().numpy(), (before.double().cpu() - 0.1 * w64.grad).float().numpy(), rtol=1e-5, atol=1e-5)
+    # jagged bags (empty bags produce nothing)
+    lens = rng.integers(0, 7, size=B)
+    bag = np.zeros(B + 1, dtype=np.int32)
+    bag[1:] = np.cumsum(lens)
+    jid = rng.integers(0, N, size=int(bag[-1]))
+    dev_w = torch.from_numpy(w).cuda()
+    jout = torch.empty(B, D, device="cuda")
+    dev_bag = torch.from_numpy(bag).cuda()
+    bag_forward([FieldCall([(dev_w, N, None)], D, combiner, ids=torch.from_numpy(jid).cuda().view(1, -1), out=jout, bag_offsets=dev_bag,
+                           n_items=len(jid))], B)
+    kg = bag_minmax_key_grads(torch.from_numpy(jid).cuda(), dev_w, jout, dev_g, bag_offsets=dev_bag).cpu().numpy()
+    for b in rng.choice(B, size=40, replace=False):
+        k0, k1 = bag[b], bag[b + 1]
+        if k1 == k0:
+            continue
+        r = w[jid[k0:k1]].astype(np.float64)
+        yb = r.max(axis=0) if combiner == "max" else r.min(axis=0)
+        hit = r == yb
+        np.testing.assert_allclose(kg[k0:k1], hit * (g[b] / hit.sum(axis=0)), rtol=1e-6, atol=1e-7)
+
+
 def test_gapped_bags_with_explicit_ends():
     # bag_ends: bags in order but with unused gaps between them (the sharded "tile" routing layout);
     # the gaps hold garbage ids that must never be dereferenced

@@ -136,3 +136,22 @@ def test_keras_doc_examples_on_the_device():
     assert iv.lookup(torch.tensor([[12, 1138, 42], [42, 1000, 36]], device="cuda")).tolist() == [[1, 3, 4], [4, 0, 2]]
     x = torch.tensor([[-1.5, 1.0, 3.4, .5], [0.0, 3.0, 1.3, 0.0]], device="cuda")
     assert bucketize(x, torch.tensor([0., 1., 2.], device="cuda")).tolist() == [[0, 2, 3, 1], [1, 3, 2, 1]]
+
+
+def test_lookup_embedding_reference_rows_flag():
+    """reference_rows=True keeps the reference's table shape (`vocab_size=len(vocabs)` rows, preprocess_utils.py factory): the
+    checkpoint shape matches; the last term has no row and raises like the reference's CPU gather; the default allocates the
+    extra row."""
+    from recommendflow_b200.backend.layers.preprocess_layers import LookupEmbedding
+    from recommendflow_b200.strings import StringColumn
+    vocabs = ["a", "b", "c", "d"]
+    ref = LookupEmbedding(8, "str", vocabs, vocab_size=len(vocabs), pooling="sum", name="lookup_x", reference_rows=True)
+    ours = LookupEmbedding(8, "str", vocabs, vocab_size=len(vocabs), pooling="sum", name="lookup_y")
+    ok = StringColumn.from_lists([["a", "c"], ["zzz", "b"]]).to("cuda")
+    out = ref(ok)
+    assert ref.embedding.embeddings.shape == (4, 8) and ours(ok).shape == out.shape and ours.embedding.embeddings.shape == (5, 8)
+    w = ref.embedding.embeddings.detach()
+    assert torch.equal(out[0], w[1] + w[3]) and torch.equal(out[1], w[0] + w[2])
+    with pytest.raises(ValueError, match="is not in"):
+        ref(StringColumn.from_lists([["d", "a"], ["a", "a"]]).to("cuda"))
+    ours(StringColumn.from_lists([["d", "a"], ["a", "a"]]).to("cuda"))
