@@ -468,6 +468,8 @@ class ShardedEmbeddingBag(torch.nn.Module):
                 if not capturing:
                     b["combined"][j] = done
                 cur.wait_event(done)
+        # what the backward needs: this step's routing stays in exchange set j until the step after next overwrites it
+        self._saved = {"p2p_set": j, "tiles": ticket["tiles"], "B": B, "L": L, "bag_offsets": bag_offsets}
         return out
 
     def forward(self, keys, out=None):
@@ -525,9 +527,9 @@ class ShardedEmbeddingBag(torch.nn.Module):
         the (pre-scaled) gradients: every owner already holds, from the forward's routing, the local rows each
         source gathered per bag, so it can scatter source s's bag gradients to its rows directly.  Rows owned
         by this rank that no source touched decay and move like every Keras Adam variable (lazy=False).
-        nccl transport (the p2p transport's peer-pointer variant is not built); sum / avg combiners."""
-        if self.transport != "nccl":
-            raise NotImplementedError("apply_adam is implemented for the nccl transport")
+        p2p transport: the sources PUSH their gradients into every owner's receive buffer through the NVLink peer mapping
+        (two device-side barriers, no NCCL call), and the owner reads the routing of the forward from the exchange set it
+        is still sitting in.  sum / avg combiners."""
         if self.combiner not in ("sum", "avg"):
             raise NotImplementedError(f"backward is implemented for sum / avg pooling, not {self.combiner}")
         sv = getattr(self, "_saved", None)
@@ -544,15 +546,19 @@ class ShardedEmbeddingBag(torch.nn.Module):
             else:
                 g = g / float(max(sv["L"], 1))
         g = g.contiguous()
-        gathered = torch.empty(W, B, D, dtype=torch.float32, device=g.device)
-        dist.all_gather(list(gathered.unbind(0)), g, group=self.group)
-        # one CSR over all (source, bag) pairs: source s's offsets shifted by the keys of the sources before it
-        totals = [0]
-        for n in sv["recv_tot"]:
-            totals.append(totals[-1] + int(n))
-        base = torch.tensor(totals, dtype=torch.int64, device=g.device)
-        offs_all = (sv["offs_recv"][:, :B].to(torch.int64) + base[:W, None]).reshape(-1)
-        offs_all = torch.cat([offs_all, base[W:]]).to(torch.int32).contiguous()
+        if self.transport == "p2p":
+            gathered, rows, offs_all = self._p2p_reverse_exchange(g, sv)
+        else:
+            gathered = torch.empty(W, B, D, dtype=torch.float32, device=g.device)
+            dist.all_gather(list(gathered.unbind(0)), g, group=self.group)
+            # one CSR over all (source, bag) pairs: source s's offsets shifted by the keys of the sources before it
+            totals = [0]
+            for n in sv["recv_tot"]:
+                totals.append(totals[-1] + int(n))
+            base = torch.tensor(totals, dtype=torch.int64, device=g.device)
+            offs_all = (sv["offs_recv"][:, :B].to(torch.int64) + base[:W, None]).reshape(-1)
+            offs_all = torch.cat([offs_all, base[W:]]).to(torch.int32).contiguous()
+            rows = sv["rows"]
         st = getattr(self, "_adam", None)
         if st is None:
             st = self._adam = {"m": torch.zeros_like(self.shard.data), "v": torch.zeros_like(self.shard.data), "iterations": 0,
@@ -560,6 +566,41 @@ class ShardedEmbeddingBag(torch.nn.Module):
         st["iterations"] += 1
         params = {"learning_rate": learning_rate, "beta_1": beta_1, "beta_2": beta_2, "epsilon": epsilon,
                   "step": st["iterations"], "lazy": lazy}
-        self.ops.adam(self.shard.data, st["m"], st["v"], sv["rows"], offs_all, gathered.view(W * B, D), st, params)
+        self.ops.adam(self.shard.data, st["m"], st["v"], rows, offs_all, gathered.view(W * B, D), st, params)
         self._saved = None
         return self.shard
+
+    def _p2p_reverse_exchange(self, g, sv):
+        """p2p transport: (gradients of every source [W, B, D], this owner's routed rows in (source, bag, key) order, their CSR
+        [W * B + 1]).  Gradients travel by peer stores into a symmetric receive buffer; the routed rows are compacted out of the
+        forward's exchange set (the tile route leaves gaps between bags: per-tile capacity slots)."""
+        import torch.distributed._symmetric_memory as symm
+        b, W, D, me = self._bufs, self.world, self.output_dim, self.rank
+        B = sv["B"]
+        if b.get("grad_recv") is None:
+            raw = symm.empty(W * self.max_batch * D, dtype=torch.float32, device=self.device)
+            hdl = symm.rendezvous(raw, self.group)
+            b["grad_raw"], b["grad_hdl"] = raw, hdl
+            b["grad_recv"] = raw.view(W, self.max_batch, D)
+            b["grad_peer"] = [hdl.get_buffer(r, (W, self.max_batch, D), torch.float32, 0) for r in range(W)]
+        hdl = b["grad_hdl"]
+        hdl.barrier(channel=0)                           # every owner is done with the gradients of the previous step
+        for k in range(W):                               # rotated: at any moment the W sources store to W different owners
+            r = (me + k) % W
+            b["grad_peer"][r][me, :B].copy_(g)
+        hdl.barrier(channel=1)                           # every source's gradient has landed here
+        gathered = b["grad_recv"][:, :B]
+        if B != self.max_batch:
+            gathered = gathered.contiguous()
+        j = sv["p2p_set"]
+        begins = b["offs_recv"][j][:, :B].to(torch.int64)                                  # [W, B]
+        ends = (b["ends_recv"][j][:, :B] if sv["tiles"] else b["offs_recv"][j][:, 1:B + 1]).to(torch.int64)
+        lens = (ends - begins).reshape(-1)
+        offs_all = torch.zeros(W * B + 1, dtype=torch.int64, device=self.device)
+        torch.cumsum(lens, dim=0, out=offs_all[1:])
+        n = int(offs_all[-1].item())                     # host sync: the sort below is sized by it (the nccl path syncs for its split sizes)
+        src_base = (torch.arange(W, device=self.device, dtype=torch.int64) * self.max_keys)[:, None]
+        first = (begins + src_base).reshape(-1) - offs_all[:-1]                             # where bag (s, b) starts, minus its compact start
+        idx = torch.repeat_interleave(first, lens, output_size=n) + torch.arange(n, device=self.device, dtype=torch.int64)
+        rows = b["rows_recv"][j].reshape(-1)[idx]
+        return gathered, rows, offs_all.to(torch.int32).contiguous()

@@ -1,5 +1,5 @@
 """C5 (BASELINE.json configs[4]): one optimisation step of the two-tower recall model on G GPUs with the embedding
-tables ROW-SHARDED across them and the dense towers DATA-PARALLEL.
+tables ROW-SHARDED across them and the dense towers DATA-PARALLEL (either transport of the sharded bags: nccl or p2p).
 
 What the reference does instead (/root/reference/example/ranking_search/train.py:93-104 and
 backend/utils/gpu_utils.py:13-14): `tf.distribute.MirroredStrategy` -- every table replicated on every GPU, one
@@ -81,7 +81,7 @@ class AllGatherInbatchCE(torch.autograd.Function):
 
 
 class ShardedRecallTrainer(object):
-    """user_bags / ad_bags: {feature name: ShardedEmbeddingBag (nccl transport)}; user_tower / ad_tower: `create_mlp`
+    """user_bags / ad_bags: {feature name: ShardedEmbeddingBag (nccl or p2p transport)}; user_tower / ad_tower: `create_mlp`
     Sequentials (replicated: construct them from the same seed on every rank).  batch: {feature name: keys}."""
 
     def __init__(self, user_bags, ad_bags, user_tower, ad_tower, learning_rate=1e-4, scale=20.0, group=None, loss_ops=None,

@@ -119,7 +119,7 @@ def test_sharded_forward_multi_gpu(world):
             assert err <= 200 * 0.05 * 2.0 ** -21, (rank, key, err)     # fp32 re-association of <= 200 adds
 
 
-def _train_worker(rank, world, port, q):
+def _train_worker(rank, world, port, q, transport="nccl"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -128,7 +128,7 @@ def _train_worker(rank, world, port, q):
         from recommendflow_b200.strings import StringColumn
         N, D, B = 5003, 32, 256
         full = np.random.default_rng(1).uniform(-0.05, 0.05, size=(N, D)).astype(np.float32)
-        layer = ShardedEmbeddingBag(N, D, combiner="avg", salt=None, mask_value="", transport="nccl", max_batch=B,
+        layer = ShardedEmbeddingBag(N, D, combiner="avg", salt=None, mask_value="", transport=transport, max_batch=B,
                                     max_keys=B * 30)
         layer.set_full_weights(full)
         for step in (1, 2):
@@ -142,13 +142,15 @@ def _train_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_sharded_backward_adam_multi_gpu():
-    # same construction as tests/test_sharded_cpu.py::test_two_rank_gloo_sharded_backward_adam, on the CUDA kernels
+@pytest.mark.parametrize("transport", ["nccl", "p2p"])
+def test_sharded_backward_adam_multi_gpu(transport):
+    # same construction as tests/test_sharded_cpu.py::test_two_rank_gloo_sharded_backward_adam, on the CUDA kernels; p2p: the
+    # gradients reach the owners by peer stores and the routed rows are compacted out of the forward's (gapped) exchange set
     world, N, D, B = 2, 5003, 32, 256
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_train_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_train_worker, args=(r, world, port, q, transport)) for r in range(world)]
     for p in procs:
         p.start()
     res = {r: (w, m, v) for r, w, m, v in (q.get(timeout=300) for _ in procs)}
@@ -176,7 +178,7 @@ def test_sharded_backward_adam_multi_gpu():
 
 
 # ---- C5: sharded tables + data-parallel towers + all-gathered in-batch softmax on 2 GPUs ------------------------------
-def _c5_gpu_worker(rank, world, port, q):
+def _c5_gpu_worker(rank, world, port, q, transport="nccl"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
@@ -192,7 +194,7 @@ def _c5_gpu_worker(rank, world, port, q):
         full = {n: np.random.default_rng(i).uniform(-0.05, 0.05, size=(N, D)).astype(np.float32) for i, n in enumerate(("u", "a"))}
         bags = {}
         for n in ("u", "a"):
-            bags[n] = ShardedEmbeddingBag(N, D, combiner="avg", salt=None, mask_value="", transport="nccl", max_batch=B, max_keys=B * 8)
+            bags[n] = ShardedEmbeddingBag(N, D, combiner="avg", salt=None, mask_value="", transport=transport, max_batch=B, max_keys=B * 8)
             bags[n].set_full_weights(full[n])
         torch.manual_seed(5)
         towers = [create_mlp([32, 16], 0.0, "selu", None, name=t) for t in ("user_tower", "ad_tower")]
@@ -215,7 +217,8 @@ def _c5_gpu_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_c5_train_step_multi_gpu_matches_single_process():
+@pytest.mark.parametrize("transport", ["nccl", "p2p"])
+def test_c5_train_step_multi_gpu_matches_single_process(transport):
     """tests/test_sharded_cpu.py::test_two_rank_gloo_c5_train_step_matches_single_process on the CUDA kernels and NCCL:
     3 steps on 2 GPUs vs ONE CPU process with the full tables and the global batch."""
     from recommendflow_b200.backend.blocks.mlp import create_mlp
@@ -224,7 +227,7 @@ def test_c5_train_step_multi_gpu_matches_single_process():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_c5_gpu_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_c5_gpu_worker, args=(r, world, port, q, transport)) for r in range(world)]
     for p in procs:
         p.start()
     res = {r: (l, d, s) for r, l, d, s in (q.get(timeout=300) for _ in procs)}

@@ -111,16 +111,6 @@ def run_train_c5(world, rank, dev, barrier, steps=5):
     if N // world * D * 4 * 3 * n_feat > 150e9:
         return {"skipped": f"1 B rows need more than {world} GPUs for tables + Adam moments"}
     names = [f"user_{i}" for i in range(n_feat // 2)] + [f"ad_{i}" for i in range(n_feat // 2)]
-    bags = {n: ShardedEmbeddingBag(N, D, combiner="avg", salt=None, mask_value="", transport="nccl", max_batch=B, max_keys=B * max_len)
-            for n in names}
-    torch.manual_seed(11)
-    towers = [create_mlp([256, 128], 0.0, "selu", None, name=t) for t in ("user_tower", "ad_tower")]
-    x = torch.zeros(2, D * n_feat // 2)
-    for t in towers:
-        t(x)
-        t.to(dev)
-    trainer = ShardedRecallTrainer({n: bags[n] for n in names[:n_feat // 2]}, {n: bags[n] for n in names[n_feat // 2:]},
-                                   towers[0], towers[1], learning_rate=1e-3)
     batches = []
     for bi in range(2):
         b = {}
@@ -129,25 +119,51 @@ def run_train_c5(world, rank, dev, barrier, steps=5):
             b[n] = StringColumn.from_arena(arena, offs, (B, None), bag).to(dev)
         batches.append(b)
     y = torch.ones(B, device=dev)
-    losses = [float(trainer.train_step(batches[i % 2], y)) for i in range(2)]          # warm-up (builds optimizers)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        losses.append(float(trainer.train_step(batches[i % 2], y)))
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1) / steps
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    del trainer, bags
-    torch.cuda.empty_cache()
+
+    def one(transport):
+        bags = {n: ShardedEmbeddingBag(N, D, combiner="avg", salt=None, mask_value="", transport=transport, max_batch=B,
+                                       max_keys=B * max_len) for n in names}
+        torch.manual_seed(11)
+        towers = [create_mlp([256, 128], 0.0, "selu", None, name=t) for t in ("user_tower", "ad_tower")]
+        x = torch.zeros(2, D * n_feat // 2)
+        for t in towers:
+            t(x)
+            t.to(dev)
+        trainer = ShardedRecallTrainer({n: bags[n] for n in names[:n_feat // 2]}, {n: bags[n] for n in names[n_feat // 2:]},
+                                       towers[0], towers[1], learning_rate=1e-3)
+        losses = [float(trainer.train_step(batches[i % 2], y)) for i in range(2)]          # warm-up (builds optimizers)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            losses.append(float(trainer.train_step(batches[i % 2], y)))
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        del trainer, bags
+        torch.cuda.empty_cache()
+        return float(t.item()), losses
+
+    # both exchanges of the sharded bags: nccl (all_to_all forward, all_gather backward) and p2p (routing / pooled vectors /
+    # gradients through NVLink peer memory, device-side barriers)
+    per_transport = {}
+    for transport in ("nccl", "p2p"):
+        try:
+            per_transport[transport] = one(transport)
+        except Exception as exc:
+            per_transport[transport] = (None, f"{type(exc).__name__}: {exc}")
+    timed = {k: v for k, v in per_transport.items() if v[0] is not None}
+    if not timed:
+        return {"error": {k: v[1] for k, v in per_transport.items()}}
+    best = min(timed, key=lambda k: timed[k][0])
+    ms, losses = timed[best]
     return {"workload": f"c5: training step, {n_feat} features x {N} rows x {D} dims = {rows_total} table rows row-sharded id % {world} "
                         f"(Keras Adam on every row), towers [256, 128] data-parallel, in-batch softmax over the global batch "
                         f"{world} x {B}, jagged 1..{max_len} keys/bag",
-            "ms_per_step": ms, "samples_per_s": world * B / (ms / 1e3), "steps": steps, "losses": [round(v, 5) for v in losses],
-            "loss_fell": losses[-1] < losses[0]}
+            "ms_per_step": ms, "samples_per_s": world * B / (ms / 1e3), "steps": steps, "transport": best,
+            "ms_per_step_by_transport": {k: (v[0] if v[0] is not None else v[1]) for k, v in per_transport.items()},
+            "losses": [round(v, 5) for v in losses], "loss_fell": losses[-1] < losses[0]}
 
 
 def run(args, world, rank, dev):
