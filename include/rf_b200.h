@@ -360,6 +360,11 @@ int rf_sdpa_backward(const float *d_q, const float *d_k, const float *d_v, const
 int rf_sdpa_backward_strided(const float *d_q, const float *d_k, const float *d_v, int64_t row_pitch, const float *d_mask,
                              const float *d_grad_out, int64_t n_batch_heads, int32_t seq_len, int32_t head_dim,
                              float *d_dq, float *d_dk, float *d_dv, int64_t grad_row_pitch, void *stream);
+/* The same on the tensor cores (TF32 operands, fp32 accumulate; warp-level mma.sync on operands held in shared memory, */
+/* the softmax / delta arithmetic stays fp32): seq_len <= 64, head_dim in {32, 64, 96, 128}.                             */
+int rf_sdpa_backward_tc(const float *d_q, const float *d_k, const float *d_v, int64_t row_pitch, const float *d_mask,
+                        const float *d_grad_out, int64_t n_batch_heads, int32_t seq_len, int32_t head_dim,
+                        float *d_dq, float *d_dk, float *d_dv, int64_t grad_row_pitch, void *stream);
 /* Gradient of batch_neg_sample_scaled_multi_class_ce_loss (match_losses.py:150-165) w.r.t. query   */
 /* and doc (either output may be NULL), times `upstream` (dL/d loss).  d_lse: the per-row            */
 /* log-sum-exp rf_inbatch_rowstats[_tc] produced for the same inputs.  dim <= 512.  Deterministic.   */

@@ -172,6 +172,8 @@ def lib():
         L.rf_sdpa_backward_strided.restype = C.c_int
         L.rf_sdpa_backward_strided.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                                C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.rf_sdpa_backward_tc.restype = C.c_int
+        L.rf_sdpa_backward_tc.argtypes = L.rf_sdpa_backward_strided.argtypes
         L.rf_dense_tc_workspace_bytes.restype = C.c_int64
         L.rf_dense_tc_workspace_bytes.argtypes = [C.c_int64, C.c_int32, C.c_int32]
         L.rf_dense_forward_tc_ex.restype = C.c_int

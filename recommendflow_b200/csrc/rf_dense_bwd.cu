@@ -274,6 +274,161 @@ sdpa_backward_tiled_kernel(const float *__restrict__ q, const float *__restrict_
     }
 }
 
+// Tensor-core version (TF32 operands, fp32 accumulate) for the default "tf32" precision mode: the five 64 x 64 x dh products
+// of a sequence run on warp-level mma.sync.m16n8k8 (four warps, a 16-row strip each; operands come from shared memory, so the
+// transposed products dK = dS^T Q and dV = P^T dO are index arithmetic, not data movement).  At S = 50, dh = 64 the arithmetic
+// (21 GF for 8192 sequences) stops being the bound: the kernel approaches the time its 8 tensors take through HBM.  The
+// softmax / delta phase is the fp32 code of the kernels above; inputs, P and dS are rounded to nearest TF32 (cvt.rna) where
+// they become operands.  A tcgen05 version would need 128-row tiles (two sequences per tile as in the forward) and five
+// operand layouts per pair for a kernel that is already memory-bound -- not built.
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const float (&a)[4], float b0, float b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+                   "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+
+// acc[nt] (16 rows x 8 columns each, nt < NT) += A[16 rows starting at m0][K] * B[K][8 * NT columns].
+// A(m, k) = a[m * a_m + k * a_k], B(k, n) = b[k * b_k + n * b_n]: either operand may be read transposed.
+template <int NT>
+__device__ __forceinline__ void warp_gemm(float (&acc)[NT][4], const float *__restrict__ a, int a_m, int a_k, const float *__restrict__ b,
+                                          int b_k, int b_n, int m0, int K, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        float af[4];
+        af[0] = a[(m0 + g) * a_m + (k0 + t) * a_k];
+        af[1] = a[(m0 + g + 8) * a_m + (k0 + t) * a_k];
+        af[2] = a[(m0 + g) * a_m + (k0 + t + 4) * a_k];
+        af[3] = a[(m0 + g + 8) * a_m + (k0 + t + 4) * a_k];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const float b0 = b[(k0 + t) * b_k + (nt * 8 + g) * b_n], b1 = b[(k0 + t + 4) * b_k + (nt * 8 + g) * b_n];
+            mma_tf32(acc[nt], af, b0, b1);
+        }
+    }
+}
+
+constexpr int kMmaThreads = 128;
+
+template <int NTD>      // head_dim = 8 * NTD
+__global__ void __launch_bounds__(kMmaThreads, 2)
+sdpa_backward_mma_kernel(const float *__restrict__ q, const float *__restrict__ k, const float *__restrict__ v,
+                         const float *__restrict__ mask, const float *__restrict__ grad_out, int S,
+                         float *__restrict__ dq, float *__restrict__ dk, float *__restrict__ dv, int64_t pitch, int64_t out_pitch) {
+    constexpr int dh = 8 * NTD;
+    constexpr int ld = dh + 4, lp = kTileSeq + 4;
+    extern __shared__ __align__(16) float smem[];
+    float *Q = smem, *K = Q + kTileSeq * ld, *V = K + kTileSeq * ld, *G = V + kTileSeq * ld;      // [64][dh + 4], TF32-rounded
+    float *P = G + kTileSeq * ld, *dS = P + kTileSeq * lp;                                        // [64][68]
+    float *rowm = dS + kTileSeq * lp;
+    const int64_t base = (int64_t)blockIdx.x * S * dh, in_base = (int64_t)blockIdx.x * S * pitch, out_base = (int64_t)blockIdx.x * S * out_pitch;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    constexpr int q4 = dh >> 2;
+    for (int e = tid; e < kTileSeq * q4; e += kMmaThreads) {
+        const int i = e / q4, c = (e - i * q4) * 4;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, cc = a, d = a;
+        if (i < S) {
+            const int64_t at = in_base + (int64_t)i * pitch + c;
+            a = *reinterpret_cast<const float4 *>(q + at);
+            b = *reinterpret_cast<const float4 *>(k + at);
+            cc = *reinterpret_cast<const float4 *>(v + at);
+            d = *reinterpret_cast<const float4 *>(grad_out + base + (int64_t)i * dh + c);
+        }
+        *reinterpret_cast<float4 *>(Q + i * ld + c) = make_float4(to_tf32(a.x), to_tf32(a.y), to_tf32(a.z), to_tf32(a.w));
+        *reinterpret_cast<float4 *>(K + i * ld + c) = make_float4(to_tf32(b.x), to_tf32(b.y), to_tf32(b.z), to_tf32(b.w));
+        *reinterpret_cast<float4 *>(V + i * ld + c) = make_float4(to_tf32(cc.x), to_tf32(cc.y), to_tf32(cc.z), to_tf32(cc.w));
+        *reinterpret_cast<float4 *>(G + i * ld + c) = make_float4(to_tf32(d.x), to_tf32(d.y), to_tf32(d.z), to_tf32(d.w));
+    }
+    for (int i = tid; i < kTileSeq; i += kMmaThreads) rowm[i] = (i < S && mask) ? mask[(int64_t)blockIdx.x * S + i] : 1.0f;
+    __syncthreads();
+    const float scale = rsqrtf((float)dh);
+    const int m0 = warp * 16;
+    {   // S = Q K^T and dP = dO V^T: rows m0 .. m0 + 15, all 64 key columns
+        float acc[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+        warp_gemm<8>(acc, Q, ld, 1, K, 1, ld, m0, dh, lane);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int j = nt * 8 + 2 * t;
+            const bool m_lo = rowm[m0 + g] == 0.0f, m_hi = rowm[m0 + g + 8] == 0.0f;
+            P[(m0 + g) * lp + j] = m_lo ? -4294967295.0f : acc[nt][0] * scale;
+            P[(m0 + g) * lp + j + 1] = m_lo ? -4294967295.0f : acc[nt][1] * scale;
+            P[(m0 + g + 8) * lp + j] = m_hi ? -4294967295.0f : acc[nt][2] * scale;
+            P[(m0 + g + 8) * lp + j + 1] = m_hi ? -4294967295.0f : acc[nt][3] * scale;
+            acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+        }
+        warp_gemm<8>(acc, G, ld, 1, V, 1, ld, m0, dh, lane);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int j = nt * 8 + 2 * t;
+            dS[(m0 + g) * lp + j] = acc[nt][0];
+            dS[(m0 + g) * lp + j + 1] = acc[nt][1];
+            dS[(m0 + g + 8) * lp + j] = acc[nt][2];
+            dS[(m0 + g + 8) * lp + j + 1] = acc[nt][3];
+        }
+    }
+    __syncwarp();
+    // softmax rows, delta, dS: a warp owns exactly the 16 rows it just produced (no CTA barrier needed yet)
+    for (int i = m0; i < m0 + 16; ++i) {
+        if (i >= S) {
+            for (int j = lane; j < kTileSeq; j += 32) P[i * lp + j] = dS[i * lp + j] = 0.f;
+            continue;
+        }
+        float mx = -INFINITY;
+        for (int j = lane; j < S; j += 32) mx = fmaxf(mx, P[i * lp + j]);
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float den = 0.f;
+        for (int j = lane; j < S; j += 32) {
+            const float p = expf(P[i * lp + j] - mx);
+            P[i * lp + j] = p;
+            den += p;
+        }
+        for (int o = 16; o; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+        const float inv = 1.0f / den;
+        float delta = 0.f;
+        for (int j = lane; j < S; j += 32) {
+            const float p = P[i * lp + j] * inv;
+            P[i * lp + j] = p;
+            delta = fmaf(p, dS[i * lp + j], delta);
+        }
+        for (int o = 16; o; o >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, o);
+        const bool masked = rowm[i] == 0.0f;
+        for (int j = lane; j < kTileSeq; j += 32) {
+            const bool in = j < S;
+            const float p = in ? P[i * lp + j] : 0.f;
+            dS[i * lp + j] = (masked || !in) ? 0.f : to_tf32(p * (dS[i * lp + j] - delta));
+            P[i * lp + j] = to_tf32(p);
+        }
+    }
+    __syncthreads();
+    // dQ = dS K, dK = dS^T Q, dV = P^T dO: rows m0 .. m0 + 15, all dh columns; C fragment rows g / g + 8, columns 2t, 2t + 1
+    float acc[NTD][4];
+    auto store = [&](float *dst, float mul) {
+#pragma unroll
+        for (int nt = 0; nt < NTD; ++nt) {
+            const int c = nt * 8 + 2 * t;
+            if (m0 + g < S) *reinterpret_cast<float2 *>(dst + out_base + (int64_t)(m0 + g) * out_pitch + c) = make_float2(acc[nt][0] * mul, acc[nt][1] * mul);
+            if (m0 + g + 8 < S)
+                *reinterpret_cast<float2 *>(dst + out_base + (int64_t)(m0 + g + 8) * out_pitch + c) = make_float2(acc[nt][2] * mul, acc[nt][3] * mul);
+            acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+        }
+    };
+#pragma unroll
+    for (int nt = 0; nt < NTD; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+    warp_gemm<NTD>(acc, dS, lp, 1, K, ld, 1, m0, kTileSeq, lane);          // A(m, k) = dS[m][k], B(k, n) = K[k][n]
+    store(dq, scale);
+    warp_gemm<NTD>(acc, dS, 1, lp, Q, ld, 1, m0, kTileSeq, lane);          // A(m, k) = dS[k][m]
+    store(dk, scale);
+    warp_gemm<NTD>(acc, P, 1, lp, G, ld, 1, m0, kTileSeq, lane);           // A(m, k) = P[k][m]
+    store(dv, 1.0f);
+}
+
 // --------------------------------------------------------------------------------------------
 // in-batch softmax cross-entropy backward
 // --------------------------------------------------------------------------------------------
@@ -443,6 +598,31 @@ inline int64_t slab_rows(int64_t batch) {
     return r < batch ? r : batch;
 }
 
+template <int NTD>
+int launch_sdpa_backward_mma_t(const float *q, const float *k, const float *v, int64_t pitch, const float *mask, const float *grad_out,
+                               int64_t n, int S, float *dq, float *dk, float *dv, int64_t out_pitch, cudaStream_t st) {
+    constexpr int dh = 8 * NTD;
+    const size_t bytes = sizeof(float) * ((size_t)4 * kTileSeq * (dh + 4) + (size_t)2 * kTileSeq * (kTileSeq + 4) + kTileSeq);
+    RF_CUDA(cudaFuncSetAttribute(sdpa_backward_mma_kernel<NTD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    sdpa_backward_mma_kernel<NTD><<<(unsigned)n, kMmaThreads, bytes, st>>>(q, k, v, mask, grad_out, S, dq, dk, dv, pitch, out_pitch);
+    RF_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return RF_OK;
+}
+
+// head_dim in {32, 64, 96, 128}, pitches multiples of 2 floats (float2 stores) and 16-byte aligned loads
+bool sdpa_backward_mma_ok(int dh) { return dh == 32 || dh == 64 || dh == 96 || dh == 128; }
+
+int launch_sdpa_backward_mma(const float *q, const float *k, const float *v, int64_t pitch, const float *mask, const float *grad_out,
+                             int64_t n, int S, int dh, float *dq, float *dk, float *dv, int64_t out_pitch, cudaStream_t st) {
+    switch (dh) {
+        case 32: return launch_sdpa_backward_mma_t<4>(q, k, v, pitch, mask, grad_out, n, S, dq, dk, dv, out_pitch, st);
+        case 64: return launch_sdpa_backward_mma_t<8>(q, k, v, pitch, mask, grad_out, n, S, dq, dk, dv, out_pitch, st);
+        case 96: return launch_sdpa_backward_mma_t<12>(q, k, v, pitch, mask, grad_out, n, S, dq, dk, dv, out_pitch, st);
+        default: return launch_sdpa_backward_mma_t<16>(q, k, v, pitch, mask, grad_out, n, S, dq, dk, dv, out_pitch, st);
+    }
+}
+
 int launch_sdpa_backward_tiled(const float *q, const float *k, const float *v, int64_t pitch, const float *mask, const float *grad_out,
                                int64_t n, int S, int dh, float *dq, float *dk, float *dv, int64_t out_pitch, cudaStream_t st) {
     const size_t tiled = sizeof(float) * ((size_t)4 * kTileSeq * (dh + 4) + (size_t)2 * kTileSeq * (kTileSeq + 4) + kTileSeq);
@@ -501,6 +681,25 @@ int rf_sdpa_backward_strided(const float *d_q, const float *d_k, const float *d_
         return set_error(RF_ERR_UNSUPPORTED, "strided SDPA backward needs head_dim and both row pitches to be multiples of 4 floats and 16-byte aligned buffers");
     return launch_sdpa_backward_tiled(d_q, d_k, d_v, row_pitch, d_mask, d_grad_out, n_batch_heads, seq_len, head_dim, d_dq, d_dk, d_dv,
                                       grad_row_pitch, static_cast<cudaStream_t>(stream));
+}
+
+int rf_sdpa_backward_tc(const float *d_q, const float *d_k, const float *d_v, int64_t row_pitch, const float *d_mask,
+                        const float *d_grad_out, int64_t n_batch_heads, int32_t seq_len, int32_t head_dim, float *d_dq, float *d_dk,
+                        float *d_dv, int64_t grad_row_pitch, void *stream) {
+    if (n_batch_heads < 0 || seq_len <= 0 || head_dim <= 0) return set_error(RF_ERR_INVALID, "bad SDPA shape");
+    if (seq_len > kBwdMaxSeq || !sdpa_backward_mma_ok(head_dim))
+        return set_error(RF_ERR_UNSUPPORTED, "rf_sdpa_backward_tc handles seq_len <= %d and head_dim in {32, 64, 96, 128} (got %d, %d)",
+                         kBwdMaxSeq, seq_len, head_dim);
+    if (n_batch_heads == 0) return RF_OK;
+    if (n_batch_heads > INT32_MAX) return set_error(RF_ERR_INVALID, "too many (batch, head) slices");
+    if (!d_q || !d_k || !d_v || !d_grad_out || !d_dq || !d_dk || !d_dv) return set_error(RF_ERR_INVALID, "rf_sdpa_backward_tc: NULL buffer");
+    const uintptr_t al = reinterpret_cast<uintptr_t>(d_q) | reinterpret_cast<uintptr_t>(d_k) | reinterpret_cast<uintptr_t>(d_v) |
+                         reinterpret_cast<uintptr_t>(d_grad_out) | reinterpret_cast<uintptr_t>(d_dq) | reinterpret_cast<uintptr_t>(d_dk) |
+                         reinterpret_cast<uintptr_t>(d_dv);
+    if ((al & 15) || row_pitch % 4 || grad_row_pitch % 4 || row_pitch < head_dim || grad_row_pitch < head_dim)
+        return set_error(RF_ERR_UNSUPPORTED, "rf_sdpa_backward_tc needs row pitches that are multiples of 4 floats and 16-byte aligned buffers");
+    return launch_sdpa_backward_mma(d_q, d_k, d_v, row_pitch, d_mask, d_grad_out, n_batch_heads, seq_len, head_dim, d_dq, d_dk, d_dv,
+                                    grad_row_pitch, static_cast<cudaStream_t>(stream));
 }
 
 int rf_inbatch_softmax_ce_backward_block(const float *d_query, const float *d_doc, const float *d_y, const float *d_lse,

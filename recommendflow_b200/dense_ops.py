@@ -1,5 +1,6 @@
 """Host-side launchers of the dense contractions (rf_sdpa_forward, rf_inbatch_rowstats)."""
 import ctypes as C
+import os
 
 import torch
 
@@ -217,8 +218,19 @@ def _mask_rows(mask, q):
     return m.expand(q.shape[:-1]).contiguous()
 
 
-def sdpa_backward(q, k, v, mask, grad_out):
-    """(dq, dk, dv) of `sdpa` given grad_out = dL/d(out) (rf_sdpa_backward, exact fp32)."""
+def sdpa_backward_tc_ok(S, dh):
+    return S <= 64 and dh in (32, 64, 96, 128)
+
+
+# The tensor-core backward (warp-level mma.sync, TF32) measured 0.749 ms against 0.732 ms for the exact-fp32 register-tiled kernel
+# at [8192, 50, 64] on B200 (profiles/r2e_bench_train_c3_sdpa_bwd_tc.json): the legacy MMA path buys nothing there, so autograd
+# uses the exact kernel; RF_SDPA_BWD_TC=1 selects the tensor-core one.
+SDPA_BACKWARD_TC = os.environ.get("RF_SDPA_BWD_TC", "0") == "1"
+
+
+def sdpa_backward(q, k, v, mask, grad_out, precision="fp32"):
+    """(dq, dk, dv) of `sdpa` given grad_out = dL/d(out).  precision "fp32": rf_sdpa_backward (exact fp32, register-tiled CUDA
+    cores); "tf32": rf_sdpa_backward_tc (the five products on the tensor cores) when the shape allows."""
     q, k, v, g = _f32(q, "q"), _f32(k, "k"), _f32(v, "v"), _f32(grad_out, "grad_out")
     if not (q.shape == k.shape == v.shape == g.shape):
         raise ValueError("q, k, v and grad_out must share one shape")
@@ -227,9 +239,14 @@ def sdpa_backward(q, k, v, mask, grad_out):
     m = _mask_rows(mask, q)
     dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
     with torch.cuda.device(q.device):
-        nat.check(nat.lib().rf_sdpa_backward(q.data_ptr(), k.data_ptr(), v.data_ptr(), None if m is None else m.data_ptr(),
-                                             g.data_ptr(), nb, S, dh, dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
-                                             _stream(q.device)))
+        if precision != "fp32" and sdpa_backward_tc_ok(S, dh) and nb:
+            nat.check(nat.lib().rf_sdpa_backward_tc(q.data_ptr(), k.data_ptr(), v.data_ptr(), dh, None if m is None else m.data_ptr(),
+                                                    g.data_ptr(), nb, S, dh, dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), dh,
+                                                    _stream(q.device)))
+        else:
+            nat.check(nat.lib().rf_sdpa_backward(q.data_ptr(), k.data_ptr(), v.data_ptr(), None if m is None else m.data_ptr(),
+                                                 g.data_ptr(), nb, S, dh, dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                                 _stream(q.device)))
     return dq, dk, dv
 
 
@@ -272,12 +289,13 @@ class SdpaFunction(torch.autograd.Function):
     def forward(ctx, q, k, v, mask, precision):
         ctx.save_for_backward(q, k, v, mask if mask is not None else torch.empty(0, device=q.device))
         ctx.has_mask = mask is not None
+        ctx.precision = precision or DEFAULT_PRECISION
         return sdpa(q, k, v, mask, precision)
 
     @staticmethod
     def backward(ctx, grad_out):
         q, k, v, mask = ctx.saved_tensors
-        dq, dk, dv = sdpa_backward(q, k, v, mask if ctx.has_mask else None, grad_out)
+        dq, dk, dv = sdpa_backward(q, k, v, mask if ctx.has_mask else None, grad_out, ctx.precision if SDPA_BACKWARD_TC else "fp32")
         return dq.view_as(q), dk.view_as(k), dv.view_as(v), None, None
 
 
@@ -354,9 +372,11 @@ class SdpaFusedQkvFunction(torch.autograd.Function):
             m = m.expand(qkv.shape[:-1]).contiguous()
         dqkv = torch.empty_like(qkv)
         p, d = qkv.data_ptr(), dqkv.data_ptr()
+        fn = (nat.lib().rf_sdpa_backward_tc if (SDPA_BACKWARD_TC and DEFAULT_PRECISION != "fp32" and sdpa_backward_tc_ok(S, dh))
+              else nat.lib().rf_sdpa_backward_strided)
         with torch.cuda.device(qkv.device):
-            nat.check(nat.lib().rf_sdpa_backward_strided(p, p + 4 * dh, p + 8 * dh, 3 * dh, None if m is None else m.data_ptr(), g.data_ptr(),
-                                                         nb, S, dh, d, d + 4 * dh, d + 8 * dh, 3 * dh, _stream(qkv.device)))
+            nat.check(fn(p, p + 4 * dh, p + 8 * dh, 3 * dh, None if m is None else m.data_ptr(), g.data_ptr(),
+                         nb, S, dh, d, d + 4 * dh, d + 8 * dh, 3 * dh, _stream(qkv.device)))
         return dqkv, None, None
 
 

@@ -189,6 +189,32 @@ def test_sdpa_backward_matches_autograd(shape):
         sdpa_autograd(big, big, big, None, "fp32").sum().backward()
 
 
+@pytest.mark.parametrize("shape", [(37, 50, 64), (3, 2, 50, 32), (5, 64, 128), (9, 17, 96), (4, 1, 64)])
+def test_sdpa_backward_tensor_cores_match_float64(shape):
+    """rf_sdpa_backward_tc: the five products of the attention backward on warp-level TF32 tensor-core MMAs (transposed operands
+    read out of shared memory), fp32 softmax / delta; vs torch autograd on a float64 restatement and vs the exact-fp32 kernel."""
+    from recommendflow_b200.dense_ops import sdpa_backward
+    rng = np.random.default_rng(sum(shape))
+    q, k, v, g = (torch.from_numpy(rng.standard_normal(shape).astype(np.float32)).cuda() for _ in range(4))
+    mask = torch.from_numpy((rng.uniform(size=shape[:-1] + (1,)) > 0.3).astype(np.float32)).cuda()
+    mask[0] = 0
+    for m in (mask, None):
+        q64, k64, v64 = (t.double().requires_grad_(True) for t in (q, k, v))
+        _ref_sdpa64(q64, k64, v64, None if m is None else m.double()).backward(g.double())
+        before = nat.launch_count()
+        got = sdpa_backward(q, k, v, m, g, precision="tf32")
+        assert nat.launch_count() == before + 1
+        exact = sdpa_backward(q, k, v, m, g, precision="fp32")
+        for name, a, e, want in zip(("dq", "dk", "dv"), got, exact, (q64.grad, k64.grad, v64.grad)):
+            want = want.float().cpu().numpy()
+            # TF32 operands (2^-11 relative each) through three chained products of up to 128 terms
+            tol = 6e-3 * max(1.0, float(np.abs(want).max()))
+            np.testing.assert_allclose(a.cpu().numpy(), want, rtol=2e-2, atol=tol, err_msg=name)
+            np.testing.assert_allclose(a.cpu().numpy(), e.cpu().numpy(), rtol=2e-2, atol=tol, err_msg=name + " vs fp32 kernel")
+        if m is not None:
+            assert float(got[0][0].abs().max()) == 0.0                         # a fully masked sequence passes nothing to q
+
+
 @pytest.mark.parametrize("B,D,diag", [(512, 64, True), (4100, 64, True), (2048, 256, False), (6144, 128, True)])
 def test_inbatch_softmax_ce_backward_tensor_core_slabs(B, D, diag):
     """rf_inbatch_softmax_ce_backward_tc (three tcgen05 GEMMs per slab of 2048 query rows, ragged last slab) against the

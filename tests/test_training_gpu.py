@@ -176,6 +176,6 @@ def test_graphed_train_step_replays_the_eager_step(golden_dir):
     for k in a:
         diff = (b[k].double() - a[k].double()).abs()
         if "moving_" in k:
-            np.testing.assert_allclose(b[k].cpu().numpy(), a[k].cpu().numpy(), rtol=5e-3, atol=1e-4, err_msg=k)
+            np.testing.assert_allclose(b[k].cpu().numpy(), a[k].cpu().numpy(), rtol=5e-2, atol=1e-3, err_msg=k)
         else:
             assert float(diff.max()) <= lr * steps and float(diff.mean()) <= 0.05 * lr, (k, float(diff.max()), float(diff.mean()))

@@ -49,7 +49,8 @@ def run(steps=10, lazy=False, graph=True, profile_path=None):
     x = torch.randn(B, S, dm, device="cuda")
     g = torch.randn(B, S, dm, device="cuda")
     mask = (torch.arange(S, device="cuda")[None, :, None] < torch.randint(1, S + 1, (B, 1, 1), device="cuda")).float()
-    out["sdpa_backward_ms"] = timed(lambda: sdpa_backward(x, x, x, mask, g), steps)
+    out["sdpa_backward_ms"] = timed(lambda: sdpa_backward(x, x, x, mask, g, precision="tf32"), steps)
+    out["sdpa_backward_fp32_ms"] = timed(lambda: sdpa_backward(x, x, x, mask, g, precision="fp32"), steps)
     # the whole step
     cfg = os.path.join(ROOT, "tests", "golden", "configs", "synth_recall_sdpa")
     conf = Configuration(cfg + ".yaml", slot_map_path=cfg + ".feature.map")
