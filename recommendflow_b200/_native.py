@@ -239,3 +239,28 @@ def salt_to_key(salt):
     if isinstance(salt, (tuple, list)) and len(salt) == 2:
         return 1, int(salt[0]) & (2**64 - 1), int(salt[1]) & (2**64 - 1)
     raise ValueError(f"`salt` should be a tuple or list of two strong hash keys or a single integer. Received: salt={salt}.")
+
+
+class _NoSwitch(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_SWITCH = _NoSwitch()
+
+
+def on_device(device):
+    """`with on_device(dev):` = torch.cuda.device(dev) only when dev is not already the current device (the torch context
+    manager costs ~10 us of host time per launch -- more than the ctypes call it wraps)."""
+    import torch
+    if device is None:
+        return _NO_SWITCH
+    if not isinstance(device, torch.device):
+        device = torch.device(device)
+    idx = device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NO_SWITCH
+    return torch.cuda.device(device)

@@ -163,7 +163,7 @@ class BagPlan(object):
             return
         if stream is None:
             stream = torch.cuda.current_stream(self.device)
-        with torch.cuda.device(self.device):
+        with nat.on_device(self.device):
             nat.check(nat.lib().rf_bag_forward_ex(self.descs, self.n, self.batch, int(max_ctas_per_sm),
                                                   C.c_void_p(stream.cuda_stream)))
 
@@ -187,7 +187,7 @@ def hash_strings(col, num_bins, mask_value=None, salt=None):
         raise ValueError("`num_bins` cannot be `None` or non-positive values.")
     if col.n_items:
         stream = C.c_void_p(torch.cuda.current_stream(col.device).cuda_stream)
-        with torch.cuda.device(col.device):
+        with nat.on_device(col.device):
             if mode == nat.MASK_STRING_VALUE:     # any other string: the kernel compares the key bytes with it
                 nat.check(nat.lib().rf_hash_strings_masked(col.data.data_ptr(), col.offsets.data_ptr(), col.n_items,
                                                            int(num_bins), raw, len(raw), strong, k0, k1, out.data_ptr(), stream))
@@ -209,7 +209,7 @@ def hash_ints(values, num_bins, mask_value=None, salt=None):
     strong, k0, k1 = nat.salt_to_key(salt)
     mode = nat.MASK_NONE if mask_value is None else nat.MASK_INT_VALUE
     if vals.numel():
-        with torch.cuda.device(vals.device):
+        with nat.on_device(vals.device):
             nat.check(nat.lib().rf_hash_int64(vals.data_ptr(), vals.numel(), int(num_bins), mode,
                                               int(mask_value) if mask_value is not None else 0, strong, k0, k1,
                                               out.data_ptr(),
@@ -228,7 +228,7 @@ def bag_backward(ids, table, grad_out, alpha, combiner="sum", bag_len=None, bag_
     if table.dtype != torch.float32 or not table.is_contiguous():
         raise ValueError("table must be contiguous fp32")
     batch = g.shape[0]
-    with torch.cuda.device(table.device):
+    with nat.on_device(table.device):
         nat.check(nat.lib().rf_bag_backward(ids.data_ptr(), ids.numel(), None if bag_offsets is None else bag_offsets.data_ptr(),
                                             bag_len or 0, batch, g.data_ptr(), g.stride(0), table.shape[1],
                                             nat.COMBINER[combiner], float(alpha), table.data_ptr(),
@@ -249,7 +249,7 @@ def bag_minmax_key_grads(ids, table, pooled, grad_out, bag_len=None, bag_offsets
     if y.shape[0] != g.shape[0]:
         raise ValueError("pooled and grad_out must have one row per bag")
     out = torch.empty(ids.numel(), table.shape[1], dtype=torch.float32, device=table.device)
-    with torch.cuda.device(table.device):
+    with nat.on_device(table.device):
         nat.check(nat.lib().rf_bag_minmax_key_grads(ids.data_ptr(), ids.numel(), None if bag_offsets is None else bag_offsets.data_ptr(),
                                                     bag_len or 0, g.shape[0], table.data_ptr(), table.shape[1], y.data_ptr(), y.stride(0),
                                                     g.data_ptr(), g.stride(0), out.data_ptr(),
@@ -302,7 +302,7 @@ class BagAdam(object):
         self.iterations += 1
         p = nat.AdamParams(lr=self.learning_rate, beta1=self.beta_1, beta2=self.beta_2, epsilon=self.epsilon,
                            step=self.iterations, lazy=1 if self.lazy else 0)
-        with torch.cuda.device(self.table.device):
+        with nat.on_device(self.table.device):
             ws = self._workspace(ids.numel())
             nat.check(nat.lib().rf_bag_backward_adam(
                 ids.data_ptr(), ids.numel(), None if bag_offsets is None else bag_offsets.data_ptr(), bag_len or 0, g.shape[0],
@@ -392,7 +392,7 @@ class BagAdamGroup(object):
         p = nat.AdamParams(lr=self.learning_rate, beta1=self.beta_1, beta2=self.beta_2, epsilon=self.epsilon,
                            step=self.iterations, lazy=1 if self.lazy else 0, d_lr_t=None if lr_t is None else lr_t.data_ptr(),
                            d_live_rows=None if self.lazy else self._live.data_ptr())
-        with torch.cuda.device(dev):
+        with nat.on_device(dev):
             if getattr(self, "_fused_need", None) is None or self._fused_need[0] != sig:
                 need = int(nat.lib().rf_bag_adam_multi_workspace_bytes(fz["arr"], n))
                 if need < 0:
@@ -433,7 +433,7 @@ class BagAdamGroup(object):
         self.iterations += 1
         p = nat.AdamParams(lr=self.learning_rate, beta1=self.beta_1, beta2=self.beta_2, epsilon=self.epsilon,
                            step=self.iterations, lazy=1 if self.lazy else 0)
-        with torch.cuda.device(dev):
+        with nat.on_device(dev):
             need = int(nat.lib().rf_bag_adam_multi_workspace_bytes(arr, len(self.tables)))
             if need < 0:
                 nat.check(nat.RF_ERR_INVALID)

@@ -23,11 +23,16 @@ def _f32(t, what):
         t = torch.as_tensor(t)
     if not t.is_cuda:
         raise nat.NativeError(f"{what} must live on a CUDA device (got {t.device}); there is no CPU fallback")
+    if t.dtype == torch.float32 and t.is_contiguous():          # the common case: no dispatcher round trips
+        return t
     return t.to(torch.float32).contiguous()
 
 
 def _stream(dev):
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+_on = nat.on_device
 
 
 def dense_tc_ok(x, in_dim, units, l2_normalize=False):
@@ -68,7 +73,7 @@ def dense_forward(x, weight_t, bias=None, activation=None, l2_normalize=False, o
         need = int(nat.lib().rf_dense_tc_workspace_bytes(rows, in_dim, units))
         if need:
             ws = torch.empty(need, dtype=torch.uint8, device=x2.device)
-    with torch.cuda.device(x2.device):
+    with _on(x2.device):
         nat.check(nat.lib().rf_dense_forward_tc_ex(x2.data_ptr(), rows, in_dim, ldx, w.data_ptr(), None if b is None else b.data_ptr(),
                                                    units, nat.ACTIVATION[activation], 1 if l2_normalize else 0, out2.data_ptr(),
                                                    out2.stride(0) if rows > 1 else units, None if ws is None else ws.data_ptr(), need,
@@ -92,7 +97,7 @@ def column_stats(x, want_transpose=False):
     var = torch.empty_like(mean)
     xt = torch.empty(dim, rows, dtype=torch.float32, device=x.device) if want_transpose else None
     ws, need = _tower_ws(rows, dim, x.device)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         nat.check(nat.lib().rf_column_stats(x.data_ptr(), rows, dim, x.stride(0), mean.data_ptr(), var.data_ptr(),
                                             None if xt is None else xt.data_ptr(), ws.data_ptr(), need, _stream(x.device)))
     return mean, var, xt
@@ -107,7 +112,7 @@ def activation_backward(dy, y, activation):
     dzt = torch.empty(units, rows, dtype=torch.float32, device=dy.device)
     db = torch.empty(units, dtype=torch.float32, device=dy.device)
     ws, need = _tower_ws(rows, units, dy.device)
-    with torch.cuda.device(dy.device):
+    with _on(dy.device):
         nat.check(nat.lib().rf_activation_backward(dy.data_ptr(), None if plain else y.data_ptr(), rows, units, nat.ACTIVATION[activation],
                                                    None if plain else dz.data_ptr(), dzt.data_ptr(), db.data_ptr(), ws.data_ptr(), need,
                                                    _stream(dy.device)))
@@ -121,7 +126,7 @@ def batchnorm_backward(dxh, x, mean, rstd, scale):
     dgamma = torch.empty(dim, dtype=torch.float32, device=x.device)
     dbeta = torch.empty_like(dgamma)
     ws, need = _tower_ws(rows, dim, x.device)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         nat.check(nat.lib().rf_batchnorm_backward(dxh.data_ptr(), x.data_ptr(), x.stride(0), mean.data_ptr(), rstd.data_ptr(),
                                                   scale.data_ptr(), rows, dim, dgamma.data_ptr(), dbeta.data_ptr(), dx.data_ptr(),
                                                   ws.data_ptr(), need, _stream(x.device)))
@@ -147,7 +152,7 @@ def sdpa(q, k, v, mask=None, precision=None):
         m = m.expand(q.shape[:-1]).contiguous()
     out = torch.empty_like(q)
     fn = nat.lib().rf_sdpa_forward_tc if (precision == "tf32" and sdpa_tc_shape_ok(S, dh)) else nat.lib().rf_sdpa_forward
-    with torch.cuda.device(q.device):
+    with _on(q.device):
         nat.check(fn(q.data_ptr(), k.data_ptr(), v.data_ptr(), None if m is None else m.data_ptr(),
                      nb, S, dh, out.data_ptr(), _stream(q.device)))
     return out
@@ -169,7 +174,7 @@ def sdpa_fused_qkv(qkv, mask, dh):
             m = m[..., 0]
         m = m.expand(qkv.shape[:-1]).contiguous()
     out = torch.empty(*qkv.shape[:-1], dh, dtype=torch.float32, device=qkv.device)
-    with torch.cuda.device(qkv.device):
+    with _on(qkv.device):
         nat.check(nat.lib().rf_sdpa_forward_tc_strided(flat.data_ptr(), flat.data_ptr() + 4 * dh, flat.data_ptr() + 8 * dh, 3 * dh,
                                                        None if m is None else m.data_ptr(), nb, S, dh, out.data_ptr(),
                                                        _stream(qkv.device)))
@@ -200,7 +205,7 @@ def inbatch_rowstats(query, doc, y_true=None, col_weight=None, scale=20.0, margi
     loss = torch.zeros((), dtype=torch.float32, device=dev) if y is not None else None
     ptr = lambda t: None if t is None else t.data_ptr()
     fn = nat.lib().rf_inbatch_rowstats_bf16 if use_bf16 else (nat.lib().rf_inbatch_rowstats_tc if use_tc else nat.lib().rf_inbatch_rowstats)
-    with torch.cuda.device(dev):
+    with _on(dev):
         nat.check(fn(q.data_ptr(), d.data_ptr(), ptr(y), ptr(cw), B, D, float(scale), float(margin),
                      ws.data_ptr(), ptr(res.get("lse")), ptr(res.get("diag")), ptr(res.get("hinge")),
                      ptr(res.get("maxoff")), ptr(loss), _stream(dev)))
@@ -238,7 +243,7 @@ def sdpa_backward(q, k, v, mask, grad_out, precision="fp32"):
     nb = q.numel() // (S * dh) if S * dh else 0
     m = _mask_rows(mask, q)
     dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
-    with torch.cuda.device(q.device):
+    with _on(q.device):
         if precision != "fp32" and sdpa_backward_tc_ok(S, dh) and nb:
             nat.check(nat.lib().rf_sdpa_backward_tc(q.data_ptr(), k.data_ptr(), v.data_ptr(), dh, None if m is None else m.data_ptr(),
                                                     g.data_ptr(), nb, S, dh, dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), dh,
@@ -266,14 +271,14 @@ def inbatch_softmax_ce_backward(query, doc, y_true, lse, scale=20.0, upstream=1.
         gq, gd = torch.empty_like(q), torch.empty_like(d)
         need = int(nat.lib().rf_inbatch_ce_backward_tc_workspace_bytes(B, D))
         ws = torch.empty(need, dtype=torch.uint8, device=q.device)
-        with torch.cuda.device(q.device):
+        with _on(q.device):
             nat.check(nat.lib().rf_inbatch_softmax_ce_backward_tc(q.data_ptr(), d.data_ptr(), y.data_ptr(), lse.data_ptr(), B, D,
                                                                   float(scale), float(upstream), 1 if positives_on_diagonal else 0,
                                                                   ws.data_ptr(), need, gq.data_ptr(), gd.data_ptr(), _stream(q.device)))
         return (gq if need_query else None), (gd if need_doc else None)
     gq = torch.empty_like(q) if need_query else None
     gd = torch.empty_like(d) if need_doc else None
-    with torch.cuda.device(q.device):
+    with _on(q.device):
         nat.check(nat.lib().rf_inbatch_softmax_ce_backward_block(q.data_ptr(), d.data_ptr(), y.data_ptr(), lse.data_ptr(), B, D,
                                                                  float(scale), float(upstream), 1 if positives_on_diagonal else 0,
                                                                  None if gq is None else gq.data_ptr(),
@@ -374,7 +379,7 @@ class SdpaFusedQkvFunction(torch.autograd.Function):
         p, d = qkv.data_ptr(), dqkv.data_ptr()
         fn = (nat.lib().rf_sdpa_backward_tc if (SDPA_BACKWARD_TC and DEFAULT_PRECISION != "fp32" and sdpa_backward_tc_ok(S, dh))
               else nat.lib().rf_sdpa_backward_strided)
-        with torch.cuda.device(qkv.device):
+        with _on(qkv.device):
             nat.check(fn(p, p + 4 * dh, p + 8 * dh, 3 * dh, None if m is None else m.data_ptr(), g.data_ptr(),
                          nb, S, dh, d, d + 4 * dh, d + 8 * dh, 3 * dh, _stream(qkv.device)))
         return dqkv, None, None

@@ -51,10 +51,10 @@ class RecallSdpa(torch.nn.Module):
         return torch.nn.functional.normalize(x, dim=1, eps=1e-12)
 
     def towers(self, batch, behaviour=None):
-        names = self.user_cols + self.ad_cols
-        fused = set(self.preprocessor.fused_names())
+        plan = self._tower_plan()
+        names = plan["names"]
         if (self.seq_encoder is None or behaviour is None or torch.is_grad_enabled() and behaviour[0].requires_grad
-                or not all(n in fused for n in names)):
+                or not plan["all_fused"]):
             embs = self.preprocessor.forward_all(batch, names=names)
             return self.towers_from_embeddings(embs, behaviour)
         # One buffer [user features | encoded behaviour sequence | ad features]: the fused bag launch writes the two
@@ -62,24 +62,38 @@ class RecallSdpa(torch.nn.Module):
         # a strided view -- no concatenation copy of the [B, ~1900] tower inputs.
         x, mask = behaviour
         d_seq = self.seq_encoder.d_model
-        layout, col = {}, 0
-        for n in self.user_cols:
-            w = self.preprocessor._width(n)
-            layout[n] = (col, w)
-            col += w
-        gap = col
-        col += d_seq
-        for n in self.ad_cols:
-            w = self.preprocessor._width(n)
-            layout[n] = (col, w)
-            col += w
+        layout, gap, col = plan["layout"], plan["gap"], plan["total"]
         big = torch.empty(x.shape[0], col, dtype=torch.float32, device=x.device)
-        self.preprocessor.forward_all(batch, names=names, out=big, layout=layout)
+        self.preprocessor.forward_all(batch, names=names, out=big, layout=layout, views=False)
         big[:, gap:gap + d_seq] = self.seq_encoder(x, x, x, mask).mean(dim=1)
         u, a = big[:, :gap + d_seq], big[:, gap + d_seq:]
         if self.global_l2_norm:
             return self.embedding_norm(self.user_dense(u)), self.embedding_norm(self.ad_dense(a))
         return self.user_dense(u, l2_normalize=True), self.ad_dense(a, l2_normalize=True)
+
+    def _tower_plan(self):
+        """Feature order, fused-launch eligibility and the column layout [user features | sequence gap | ad features] of the
+        towers' input buffer: derived once (228 features make this ~0.3 ms of Python per call otherwise), rebuilt when the
+        preprocessing layers change."""
+        key = (len(self.preprocessor), tuple(self.user_cols), tuple(self.ad_cols), None if self.seq_encoder is None else self.seq_encoder.d_model)
+        plan = self.__dict__.get("_tower_plan_cache")
+        if plan is None or plan["key"] != key:
+            names = self.user_cols + self.ad_cols
+            fused = set(self.preprocessor.fused_names())
+            layout, col = {}, 0
+            for n in self.user_cols:
+                w = self.preprocessor._width(n)
+                layout[n] = (col, w)
+                col += w
+            gap = col
+            col += 0 if self.seq_encoder is None else self.seq_encoder.d_model
+            for n in self.ad_cols:
+                w = self.preprocessor._width(n)
+                layout[n] = (col, w)
+                col += w
+            plan = {"key": key, "names": names, "all_fused": all(n in fused for n in names), "layout": layout, "gap": gap, "total": col}
+            self.__dict__["_tower_plan_cache"] = plan
+        return plan
 
     def towers_from_embeddings(self, embs, behaviour=None):
         """The dense part: {feature name: pooled embedding} (+ behaviour sequence) -> normalised tower outputs."""
