@@ -168,7 +168,8 @@ class PreprocessLayers(dict):
                 return res
             batch = batch.columns()
         names = list(names) if names is not None else [n for n in self if n in batch]
-        fused = [n for n in names if n in set(self.fused_names())]
+        fusable = set(self.fused_names())
+        fused = [n for n in names if n in fusable]
         result = {}
         if fused:
             if layout is None:
