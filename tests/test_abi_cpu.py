@@ -118,3 +118,14 @@ def test_plain_c_program_links_against_the_library(tmp_path):
     assert res.returncode in (0, 77), res.stdout + res.stderr
     if res.returncode == 77:
         assert "no CPU fallback" in res.stderr
+
+
+def test_integration_doc_lists_every_exported_entry_point():
+    # INTEGRATION.md is the binder's map from C-ABI symbols to the reference code they replace: no symbol may be missing from it
+    import re
+    declared = set()
+    for h in ("rf_b200.h", "rf_tfrecord.h"):
+        declared |= set(re.findall(r"\b(rf_[a-z0-9_]+)\s*\(", open(os.path.join(ROOT, "include", h)).read()))
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = sorted(n for n in declared if n not in doc)
+    assert not missing, missing
