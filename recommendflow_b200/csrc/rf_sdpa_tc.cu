@@ -37,8 +37,6 @@ namespace sdpa_tc {
 constexpr int kRows = 128;            // UMMA M: two sequences of up to 64 rows
 constexpr int kSeqPad = 64;
 constexpr int kKB = 32;               // fp32 elements per 128-byte swizzle row
-constexpr int kThreads = 160;         // warps 0-3: rows; warp 4: TMA + MMA issue
-constexpr int kTmemCols = 256;        // logits: columns [0,128), output: [128, 128 + dh)
 constexpr int kBlkBytes = kRows * 128;   // one [128 rows x 128 B] swizzled block = 16 KiB
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -129,168 +127,6 @@ struct Params {
     int n_seq, S, dh;
     float inv_sqrt_dk;
 };
-
-__global__ void __launch_bounds__(kThreads, 1)
-sdpa_tc_kernel_v1(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-               const __grid_constant__ CUtensorMap map_v, Params p) {
-    extern __shared__ uint8_t smem_raw[];
-    const int n_db = p.dh / kKB;                                    // head_dim blocks of 32 floats
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t q_s = base;                                      // n_db blocks [128 x 128 B]   (A of GEMM 1, K-major)
-    const uint32_t k_s = q_s + n_db * kBlkBytes;                    // n_db blocks                  (B of GEMM 1, K-major)
-    const uint32_t v_s = k_s + n_db * kBlkBytes;                    // n_db blocks [128 keys x 128B] (B of GEMM 2, MN-major)
-    const uint32_t p_s = v_s + n_db * kBlkBytes;                    // 4 blocks [128 x 128 B]        (A of GEMM 2, K-major)
-    const uint32_t bars = p_s + 4 * kBlkBytes;
-    const uint32_t ld_full = bars, mma1_done = bars + 8, p_ready = bars + 16, mma2_done = bars + 24, tmem_slot = bars + 32;
-    uint8_t *smem_gen = smem_raw + (base - smem_u32(smem_raw));    // generic pointer to `base`
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    if (threadIdx.x == 0) {
-        mbar_init(ld_full, 1);
-        mbar_init(mma1_done, 1);
-        mbar_init(p_ready, 128);
-        mbar_init(mma2_done, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    // the off-diagonal blocks of P are zero forever: rows 0-63 never write key blocks 2,3; rows 64-127 never 0,1
-    {
-        uint4 *pz = reinterpret_cast<uint4 *>(smem_gen + (p_s - base));
-        for (int i = threadIdx.x; i < 4 * kBlkBytes / 16; i += kThreads) pz[i] = make_uint4(0, 0, 0, 0);
-    }
-    if (warp == 4) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zero fill must be visible to the MMA proxy
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    uint32_t tmem_base;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-    const int n_pairs = (p.n_seq + 1) / 2;
-    // GEMM 1: M128 N128, both K-major.  GEMM 2: M128 N=dh, A K-major, B MN-major (bit 16).
-    const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
-    const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(p.dh >> 3) << 17) |
-                            ((uint32_t)(kRows >> 4) << 24);
-    const uint32_t load_bytes = 3u * n_db * kBlkBytes;
-
-    uint32_t ph = 0;
-    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ph ^= 1) {
-        const int seq0 = 2 * pair;
-        if (warp == 4) {
-            if (lane == 0) {
-                // ---- TMA: both sequences of Q, K, V; 64-row boxes (rows past S spill into the next sequence) ----
-                mbar_expect_tx(ld_full, load_bytes);
-                for (int db = 0; db < n_db; ++db) {
-                    for (int h = 0; h < 2; ++h) {
-                        const int row = (seq0 + h) * p.S;
-                        const uint32_t off = db * kBlkBytes + h * (kSeqPad * 128);
-                        tma_load_2d(q_s + off, &map_q, ld_full, db * kKB, row);
-                        tma_load_2d(k_s + off, &map_k, ld_full, db * kKB, row);
-                        tma_load_2d(v_s + off, &map_v, ld_full, db * kKB, row);
-                    }
-                }
-                mbar_wait(ld_full, ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                // ---- GEMM 1: logits = Q K^T, K = dh in steps of 8 ----
-                for (int db = 0; db < n_db; ++db) {
-                    const uint64_t a = desc_kmajor(q_s + db * kBlkBytes), b = desc_kmajor(k_s + db * kBlkBytes);
-#pragma unroll
-                    for (int k = 0; k < kKB / 8; ++k) umma_tf32(tmem_base, a + (uint64_t)(2 * k), b + (uint64_t)(2 * k), idesc1, (db | k) ? 1u : 0u);
-                }
-                umma_commit(mma1_done);
-                // ---- GEMM 2: out = P V, K = 128 keys in steps of 8 (one 1024-byte atom of V each) ----
-                mbar_wait(p_ready, ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int kb = 0; kb < 4; ++kb) {
-                    const uint64_t a = desc_kmajor(p_s + kb * kBlkBytes);
-#pragma unroll
-                    for (int k = 0; k < kKB / 8; ++k) {
-                        const uint64_t b = desc_mnmajor(v_s + (uint32_t)(kb * 4 + k) * 1024u, (uint32_t)kBlkBytes);
-                        umma_tf32(tmem_base + 128u, a + (uint64_t)(2 * k), b, idesc2, (kb | k) ? 1u : 0u);
-                    }
-                }
-                umma_commit(mma2_done);
-                mbar_wait(mma2_done, ph);          // Q/K/V/P smem is free again before the next pair's TMA
-            }
-            __syncwarp();
-        } else {
-            // ---- softmax: thread = row of the pair tile ----
-            const int r = threadIdx.x;                  // 0..127
-            const int half = r >> 6, i = r & 63;        // sequence of the pair, query index
-            const int seq = seq0 + half;
-            const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-            mbar_wait(mma1_done, ph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float x[64];
-            {
-                float v0[32], v1[32];
-                tmem_ld32(lane_addr + (uint32_t)(half * 64), v0);
-                tmem_ld32(lane_addr + (uint32_t)(half * 64 + 32), v1);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    x[j] = v0[j];
-                    x[32 + j] = v1[j];
-                }
-            }
-            const bool row_ok = seq < p.n_seq && i < p.S;
-            const bool masked = row_ok && p.mask && p.mask[(size_t)seq * p.S + i] == 0.f;
-            float mx = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                float l = masked ? -4294967295.0f : x[j] * p.inv_sqrt_dk;
-                l = (j < p.S) ? l : -INFINITY;                       // padded keys take no probability
-                x[j] = l;
-                mx = fmaxf(mx, l);
-            }
-            float sum = 0.f;
-#pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                const float e = (j < p.S) ? __expf(x[j] - mx) : 0.f;
-                x[j] = e;
-                sum += e;
-            }
-            const float inv = row_ok ? 1.f / sum : 0.f;               // rows that are padding produce zeros
-            // write P[r][half*64 + j] (TF32) into the swizzled K-major tile: key block kb = half*2 + (j / 32)
-            uint8_t *prow = smem_gen + (p_s - base) + (r >> 3) * 1024 + (r & 7) * 128;
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {                            // 16 chunks of 4 keys
-                uint4 w;
-                w.x = to_tf32(x[c * 4 + 0] * inv);
-                w.y = to_tf32(x[c * 4 + 1] * inv);
-                w.z = to_tf32(x[c * 4 + 2] * inv);
-                w.w = to_tf32(x[c * 4 + 3] * inv);
-                const int kb = half * 2 + (c >> 3), cc = c & 7;
-                *reinterpret_cast<uint4 *>(prow + kb * kBlkBytes + ((cc ^ (r & 7)) << 4)) = w;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(p_ready);
-            // ---- output: thread = row, dh columns at TMEM column 128 ----
-            mbar_wait(mma2_done, ph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float *orow = p.out + ((size_t)seq * p.S + i) * p.dh;
-            for (int c0 = 0; c0 < p.dh; c0 += 32) {
-                float o[32];
-                tmem_ld32(lane_addr + 128u + (uint32_t)c0, o);
-                if (row_ok) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4 *>(orow + c0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-                }
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 4) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
-    }
-}
-
 
 // ------------------------------------------------------------------------------------------------------------
 // Round-2 kernel: the same arithmetic, software-pipelined across pairs, softmax on 8 warps.
@@ -584,14 +420,7 @@ int launch_sdpa_tc(const float *q, const float *k, const float *v, const float *
     RF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int n_pairs = (int)((n_seq + 1) / 2);
     Params p{mask, out, (int)n_seq, S, dh, 1.0f / sqrtf((float)dh)};
-    static const bool v1 = getenv("RF_SDPA_V1") && atoi(getenv("RF_SDPA_V1")) != 0;
-    if (v1) {        // round-1 kernel (single-stage), kept for A/B measurements
-        const size_t smem = (size_t)(3 * n_db + 4) * kBlkBytes + 1024 + 128;
-        RF_CUDA(cudaFuncSetAttribute(sdpa_tc_kernel_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int ctas_per_sm = smem <= 110 * 1024 ? 2 : 1;
-        const int grid = n_pairs < sms * ctas_per_sm ? n_pairs : sms * ctas_per_sm;
-        sdpa_tc_kernel_v1<<<grid, kThreads, smem, st>>>(mq, mk, mv, p);
-    } else {
+    {
         // buffering that fits 227 KiB: dh = 32: Q/K x 2, V x 2 (160 KiB); dh = 64: Q/K x 1, V x 2 (192 KiB; Q/K x 2 with
         // V x 1 measured no faster: 0.114 vs 0.110 ms); dh = 96: x 1, x 1
         const int n_qkbuf = n_db <= 1 ? 2 : 1, n_vbuf = n_db <= 2 ? 2 : 1;
