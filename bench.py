@@ -545,8 +545,8 @@ def run_ours(args):
     import torch.distributed as dist
 
     from recommendflow_b200 import _native as nat
-    from recommendflow_b200.backend.layers.preprocess_layers import DoubleHashingEmbedding, EmbeddingBag  # noqa: F401
-    from recommendflow_b200.bag_ops import BagPlan, FieldCall, bag_forward
+    from recommendflow_b200.backend.layers.preprocess_layers import DoubleHashingEmbedding
+    from recommendflow_b200.bag_ops import BagPlan, FieldCall
     from recommendflow_b200.synth import PackedBatch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))

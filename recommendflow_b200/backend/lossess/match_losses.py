@@ -13,7 +13,6 @@ the kernel, which is the same real number wherever the reference does not overfl
 (:180-186); the margin-rank loss multiplies the B x B hinge matrix by a [B] y_true, i.e. weights
 COLUMNS (:205).
 """
-from functools import partial
 
 import torch
 
@@ -221,5 +220,5 @@ def batch_softmax_probabilistic_combining_soft(batch_size, miu=0.6):
                               "row statistics kernel yet")
 
 
-__all__ = [n for n in dir() if not n.startswith("_") and n not in ("partial", "torch", "inbatch_rowstats",
+__all__ = [n for n in dir() if not n.startswith("_") and n not in ("torch", "inbatch_rowstats",
                                                                    "inbatch_softmax_ce_autograd")]

@@ -17,7 +17,7 @@ from ..layers.preprocess_layers import (_POOLED, DiscreteEmbedding, DoubleHashin
                                         _batch_and_len, _default_device, as_keys)
 from ...synth import PackedBatch
 from ... import _native as nat
-from ...bag_ops import BagPlan, bag_forward
+from ...bag_ops import BagPlan
 from ..layers import preprocess_layers as _pl
 
 

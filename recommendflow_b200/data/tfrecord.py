@@ -24,7 +24,7 @@ from collections import namedtuple
 import numpy as np
 import torch
 
-from ..config_parser.config_proto import TYPE_INT, TYPE_STR, FeatureDeal, float32 as TFFloat, int64 as INT64, string as TFString
+from ..config_parser.config_proto import TYPE_INT, TYPE_STR, FeatureDeal, float32 as TFFloat, int64 as INT64, string as TFString  # noqa: F401 (re-exported dtype names)
 from ..strings import StringColumn
 
 # ---- CRC32C (Castagnoli), table driven --------------------------------------------------------
