@@ -129,3 +129,22 @@ def test_integration_doc_lists_every_exported_entry_point():
     doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     missing = sorted(n for n in declared if n not in doc)
     assert not missing, missing
+
+
+def test_workspace_size_queries_are_host_only_and_consistent():
+    # size queries never touch the device: usable on a CPU-only box (the driver's build check) and by a binder planning memory
+    lib = nat.lib()
+    # split-K workspace: only for few output tiles + a long contraction (dW = X^T dZ), never for the big forward products
+    assert lib.rf_dense_tc_workspace_bytes(512, 8192, 256) > 0
+    assert lib.rf_dense_tc_workspace_bytes(64, 409600, 192) > 0
+    assert lib.rf_dense_tc_workspace_bytes(8192, 1888, 1024) == 0
+    assert lib.rf_dense_tc_workspace_bytes(0, 64, 64) == 0
+    # a split buffer holds whole 128-row tiles of the output, once per split
+    w = lib.rf_dense_tc_workspace_bytes(512, 8192, 256)
+    assert w % (512 * 256 * 4) == 0 and 2 <= w // (512 * 256 * 4) <= 64
+    # tower training passes: 2 values per column per 256-row split
+    assert lib.rf_tower_train_workspace_bytes(8192, 1888) == (8192 // 256) * 2 * 1888 * 4
+    assert lib.rf_tower_train_workspace_bytes(1, 4) == 2 * 4 * 4
+    # CE backward: slab + transpose + the two transposed operands + one partial; at most ~1 GiB of slab for any batch
+    small, big = lib.rf_inbatch_ce_backward_tc_workspace_bytes(8192, 256), lib.rf_inbatch_ce_backward_tc_workspace_bytes(65536, 256)
+    assert small >= 2 * 8192 * 8192 * 4 and big < 2 * (1 << 30) + 4 * 65536 * 256 * 4 + (1 << 20)
