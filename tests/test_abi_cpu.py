@@ -148,3 +148,17 @@ def test_workspace_size_queries_are_host_only_and_consistent():
     # CE backward: slab + transpose + the two transposed operands + one partial; at most ~1 GiB of slab for any batch
     small, big = lib.rf_inbatch_ce_backward_tc_workspace_bytes(8192, 256), lib.rf_inbatch_ce_backward_tc_workspace_bytes(65536, 256)
     assert small >= 2 * 8192 * 8192 * 4 and big < 2 * (1 << 30) + 4 * 65536 * 256 * 4 + (1 << 20)
+
+
+def test_integration_doc_ctypes_stub_matches_the_header():
+    # the minimal ctypes binding printed in INTEGRATION.md is executable and lays its structs out like the C compiler does
+    import ctypes as C
+    import re
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    code = re.search(r"```python\n(import ctypes as C.*?)```", doc, re.S).group(1)
+    code = code.replace('C.CDLL("recommendflow_b200/librf_b200.so")', f'C.CDLL("{os.path.join(ROOT, "recommendflow_b200", "librf_b200.so")}")')
+    ns = {}
+    exec(code, ns)
+    assert C.sizeof(ns["FieldDesc"]) == C.sizeof(nat.FieldDesc) and C.sizeof(ns["TableDesc"]) == C.sizeof(nat.TableDesc)
+    for name, _ in nat.FieldDesc._fields_:
+        assert getattr(ns["FieldDesc"], name).offset == getattr(nat.FieldDesc, name).offset, name
